@@ -1,0 +1,156 @@
+/*
+ * neurecon_b200 -- C-ABI of the B200-native ray-marched SDF volume-rendering hot path.
+ *
+ * This is the drop-in boundary.  The reference (SuwoongHeo/neurecon) is pure
+ * Python/PyTorch and has no FFI of its own; each entry point below replaces the
+ * reference Python function named in its comment (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller (PyTorch); the library
+ *    never allocates or frees caller memory.  Tensors are contiguous fp32 unless
+ *    stated.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *  - Return value: 0 = ok, negative = error (NR_ERR_*); the message is available
+ *    through nr_last_error().  Nothing throws across the ABI.  No host syncs:
+ *    all entry points are CUDA-graph capturable.
+ *  - There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef NEURECON_B200_H
+#define NEURECON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NR_OK 0
+#define NR_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define NR_ERR_CUDA (-2)      /* CUDA runtime error */
+#define NR_ERR_WORKSPACE (-3) /* workspace too small */
+
+#define NR_MAX_LAYERS 16
+
+/* activation codes */
+#define NR_ACT_NONE 0
+#define NR_ACT_SOFTPLUS100 1 /* nn.Softplus(beta=100, threshold=20), models/base.py:202 */
+#define NR_ACT_RELU 2
+#define NR_ACT_SIGMOID 3
+
+int nr_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf */
+int nr_last_error(char* buf, size_t n);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long nr_launch_count(void);
+/* device properties the host side needs (SM count, max dynamic smem) */
+int nr_device_info(int* sm_count, int* smem_optin, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Network descriptors.  Weights are the EFFECTIVE matrices W = g*v/||v|| (weight_norm is
+ * evaluated in PyTorch so autograd owns g and v; models/base.py:226-227), fp32 row-major
+ * [out_dim, in_pad] with in_pad = in_dim rounded up to a multiple of 4 (zero filled).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_layers;                /* D+1 linear layers (models/base.py:178) */
+  int32_t multires;                /* Embedder frequencies, <0 = identity (base.py:67-81) */
+  int32_t skip_layer;              /* layer whose input is cat([h, pe])/sqrt2 (base.py:248-250), -1 = none */
+  int32_t width;                   /* hidden width W */
+  int32_t in_dim[NR_MAX_LAYERS];   /* logical input width of layer i */
+  int32_t out_dim[NR_MAX_LAYERS];  /* logical output width of layer i */
+  const float* W[NR_MAX_LAYERS];   /* [out_dim, pad4(in_dim)]; 1/sqrt2 of the skip already folded in */
+  const float* b[NR_MAX_LAYERS];   /* [out_dim] */
+  const void* umma_image;          /* bf16 pre-swizzled operand image for the tcgen05 path (or NULL) */
+  const float* umma_bias;          /* fp32 bias table for the tcgen05 path (or NULL) */
+} nr_sdf_net_t;                    /* replaces ImplicitSurface parameters, models/base.py:131-282 */
+
+typedef struct {
+  int32_t n_layers;                /* D+1 (models/base.py:340) */
+  int32_t multires;                /* PE of x (embed_multires) */
+  int32_t multires_view;           /* PE of view dirs (embed_multires_view) */
+  int32_t feat_dim;                /* W_geo_feat */
+  int32_t in_dim[NR_MAX_LAYERS];
+  int32_t out_dim[NR_MAX_LAYERS];
+  const float* W[NR_MAX_LAYERS];
+  const float* b[NR_MAX_LAYERS];
+  const void* umma_image;
+  const float* umma_bias;
+} nr_radiance_net_t;               /* replaces RadianceNet parameters, models/base.py:312-391 */
+
+/* ------------------------------------------------------------------------------------------
+ * fp32 tier of the MLPs (<= 1e-4 relative to the reference).  Workspace is caller-allocated;
+ * query the size first.  n = number of points.
+ * ------------------------------------------------------------------------------------------ */
+/* ImplicitSurface.forward(x, return_h) -- models/base.py:243-263.  feat may be NULL. */
+size_t nr_sdf_forward_f32_workspace(const nr_sdf_net_t* net, int64_t n);
+int nr_sdf_forward_f32(const nr_sdf_net_t* net, const float* x, int64_t n, float* sdf,
+                       float* feat, int64_t feat_ld, void* ws, size_t ws_bytes, void* stream);
+
+/* ImplicitSurface.forward_with_nablas(x) -- models/base.py:265-282 (analytic forward-mode
+ * d sdf / d x instead of autograd.grad).  feat may be NULL. */
+size_t nr_sdf_forward_nablas_f32_workspace(const nr_sdf_net_t* net, int64_t n);
+int nr_sdf_forward_nablas_f32(const nr_sdf_net_t* net, const float* x, int64_t n, float* sdf,
+                              float* nabla, float* feat, int64_t feat_ld, void* ws,
+                              size_t ws_bytes, void* stream);
+
+/* RadianceNet.forward(x, view_dirs, normals, feat) -- models/base.py:372-391. */
+size_t nr_radiance_forward_f32_workspace(const nr_radiance_net_t* net, int64_t n);
+int nr_radiance_forward_f32(const nr_radiance_net_t* net, const float* x, const float* view,
+                            const float* normals, const float* feat, int64_t feat_ld, int64_t n,
+                            float* rgb, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ray geometry and inverse-CDF sampling -- utils/rend_util.py
+ * ------------------------------------------------------------------------------------------ */
+/* near_far_from_sphere(o, d, r) -- rend_util.py:167-185.  near/far: [R]. */
+int nr_near_far_from_sphere(const float* rays_o, const float* rays_d, int64_t R, float r,
+                            float* near, float* far, void* stream);
+
+/* sample_pdf(bins, weights, N, det, eps) -- rend_util.py:255-292.
+ * bins [R,M], weights [R,M-1], u [R,N] or NULL (det: torch.linspace(0,1,N) bit-exact),
+ * samples [R,N]; optional outputs: below/above int32 [R,N] (the gathered indices) and the
+ * CDF [R,M] the search ran on.  cdf_is_given != 0 turns this into sample_cdf
+ * (rend_util.py:294-327): `weights` then holds the un-normalised CDF [R,M-1]. */
+int nr_sample_pdf(const float* bins, const float* weights, const float* u, int64_t R, int32_t M,
+                  int32_t N, int32_t cdf_is_given, float eps, float* samples, int32_t* below,
+                  int32_t* above, float* cdf_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * NeuS -- models/frameworks/neus.py
+ * ------------------------------------------------------------------------------------------ */
+/* Ray prologue of render_rayschunk (neus.py:169-172,184-210): normalises rays_d, computes
+ * near/far (or the bypass values when >= 0... use NAN for "no bypass"), the coarse depths
+ * d_coarse = near*(1-t)+far*t with t = linspace(0,1,N_samples), and the coarse points.
+ * Outputs: dirs [R,3], near [R], far [R], d_new [R,N_samples], pts_new [R,N_samples,3]. */
+int nr_neus_ray_setup(const float* rays_o, const float* rays_d, int64_t R, float radius,
+                      float near_bypass, float far_bypass, int32_t n_samples, float* dirs,
+                      float* near, float* far, float* d_new, float* pts_new, void* stream);
+
+/* One iteration of the 'official_solution' up-sampler (neus.py:249-277), one warp per ray:
+ *   1. merge the n_new freshly evaluated samples (d_new, sdf_new) into the sorted per-ray
+ *      state (d_buf, sdf_buf: [R, cap], m_cur valid entries)            -- neus.py:272-276
+ *   2. if n_next > 0: slopes -> logistic CDF with s = 64*2^iter -> alpha -> weights ->
+ *      sample_pdf(n_next) -> d_next [R,n_next], pts_next [R,n_next,3]   -- neus.py:253-271
+ *      (u_next: [R,n_next] uniforms, NULL = deterministic linspace)
+ *   3. if n_next == 0 (final): emit pts [R,m,3], d_mid [R,m-1], pts_mid [R,m-1,3]
+ *                                                                       -- neus.py:284-288 */
+int nr_neus_upsample_step(const float* rays_o, const float* dirs, int64_t R, float* d_buf,
+                          float* sdf_buf, int32_t cap, int32_t m_cur, const float* d_new,
+                          const float* sdf_new, int32_t n_new, int32_t iter, int32_t n_next,
+                          const float* u_next, float* d_next, float* pts_next, float* pts_all,
+                          float* d_mid, float* pts_mid, void* stream);
+
+/* Alpha, exclusive-cumprod transmittance and compositing (neus.py:28-35,57-70,296,346-381)
+ * as one warp-scan pass.  sdf [R,M], nablas [R,M,3] (NULL if !calc_normal), radiance
+ * [R,M-1,3], d_mid [R,M-1], inv_s: device scalar s = exp(ln_s*speed) (neus.py:108-109).
+ * Per-ray outputs rgb [R,3], depth [R], acc [R], normals [R,3] (or NULL); optional
+ * per-sample outputs cdf [R,M], alpha [R,M-1], weights [R,M-1] (NULL to skip). */
+int nr_neus_composite(const float* sdf, const float* nablas, const float* radiance,
+                      const float* d_mid, const float* s_dev, int64_t R, int32_t M,
+                      int32_t white_bkgd, float* rgb, float* depth, float* acc, float* normals,
+                      float* cdf_out, float* alpha_out, float* weights_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURECON_B200_H */

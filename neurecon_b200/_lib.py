@@ -1,0 +1,154 @@
+"""ctypes binding of include/neurecon_b200.h (the C-ABI drop-in boundary)."""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+NR_MAX_LAYERS = 16
+ACT_NONE, ACT_SOFTPLUS100, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libneurecon_b200.so")
+_lib = None
+_lock = threading.Lock()
+_precision = os.environ.get("NEURECON_B200_PRECISION", "fp32")
+
+
+class SdfNet(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32), ("multires", C.c_int32), ("skip_layer", C.c_int32), ("width", C.c_int32),
+        ("in_dim", C.c_int32 * NR_MAX_LAYERS), ("out_dim", C.c_int32 * NR_MAX_LAYERS),
+        ("W", C.c_void_p * NR_MAX_LAYERS), ("b", C.c_void_p * NR_MAX_LAYERS),
+        ("umma_image", C.c_void_p), ("umma_bias", C.c_void_p),
+    ]
+
+
+class RadianceNetDesc(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32), ("multires", C.c_int32), ("multires_view", C.c_int32), ("feat_dim", C.c_int32),
+        ("in_dim", C.c_int32 * NR_MAX_LAYERS), ("out_dim", C.c_int32 * NR_MAX_LAYERS),
+        ("W", C.c_void_p * NR_MAX_LAYERS), ("b", C.c_void_p * NR_MAX_LAYERS),
+        ("umma_image", C.c_void_p), ("umma_bias", C.c_void_p),
+    ]
+
+
+_P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+_SIGNATURES = {
+    "nr_version": (C.c_int, []),
+    "nr_last_error": (C.c_int, [C.c_char_p, _SZ]),
+    "nr_launch_count": (C.c_longlong, []),
+    "nr_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
+    "nr_sdf_forward_f32_workspace": (_SZ, [C.POINTER(SdfNet), _I64]),
+    "nr_sdf_forward_f32": (C.c_int, [C.POINTER(SdfNet), _P, _I64, _P, _P, _I64, _P, _SZ, _P]),
+    "nr_sdf_forward_nablas_f32_workspace": (_SZ, [C.POINTER(SdfNet), _I64]),
+    "nr_sdf_forward_nablas_f32": (C.c_int, [C.POINTER(SdfNet), _P, _I64, _P, _P, _P, _I64, _P, _SZ, _P]),
+    "nr_radiance_forward_f32_workspace": (_SZ, [C.POINTER(RadianceNetDesc), _I64]),
+    "nr_radiance_forward_f32": (C.c_int, [C.POINTER(RadianceNetDesc), _P, _P, _P, _P, _I64, _I64, _P, _P, _SZ, _P]),
+    "nr_near_far_from_sphere": (C.c_int, [_P, _P, _I64, _F, _P, _P, _P]),
+    "nr_sample_pdf": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),
+    "nr_neus_ray_setup": (C.c_int, [_P, _P, _I64, _F, _F, _F, _I32, _P, _P, _P, _P, _P, _P]),
+    "nr_neus_upsample_step": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "nr_neus_composite": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+}
+
+
+def declared_symbols():
+    """Every symbol include/neurecon_b200.h declares (checked by the CPU test-suite)."""
+    return sorted(_SIGNATURES)
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def get_lib():
+    """Load (building first if the sources are newer and nvcc is present) the C-ABI library.
+    Raises RuntimeError when the library cannot be had -- there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        from . import build as _build
+        if _build._stale():
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            if os.path.exists(nvcc):
+                _build.build()
+            elif not os.path.exists(_LIB_PATH):
+                raise RuntimeError(
+                    "neurecon_b200: CUDA library %s is missing and nvcc is not available to build it; "
+                    "run `python -m neurecon_b200.build`. There is no CPU fallback." % _LIB_PATH)
+        lib = C.CDLL(_LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    buf = C.create_string_buffer(512)
+    get_lib().nr_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = last_error()
+        if rc == -1:
+            raise ValueError("neurecon_b200 %s: %s" % (what, msg))
+        raise RuntimeError("neurecon_b200 %s failed (code %d): %s" % (what, rc, msg))
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "neurecon_b200: the hot path runs only on CUDA tensors (got a %s tensor); there is no CPU fallback"
+                % t.device.type)
+
+
+def f32c(t):
+    """contiguous fp32 view/copy of a tensor (mirrors the reference's .float() at neus.py:169-170)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device, slot=0):
+    """Grow-only per-(device, stream, slot) scratch buffer; all kernels using it are ordered on
+    the caller's current stream, so reuse across calls is safe."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream, slot)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def set_precision(p):
+    """'fp32' (SIMT tier, <=1e-4 vs the reference) or 'bf16' (tcgen05 tier, <=1e-2)."""
+    global _precision
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _precision = p
+
+
+def get_precision():
+    return _precision

@@ -1,0 +1,437 @@
+// Ray geometry, inverse-CDF sampling, the NeuS coarse-to-fine up-sampler and the NeuS
+// alpha / transmittance / compositing pass.  All kernels are warp-per-ray: a ray's sample
+// buffers (<= a few KB) are staged once in shared memory, scans are warp-shuffle scans over
+// lane-contiguous segments, the inverse-CDF search is a per-lane binary search in smem.
+// These kernels are HBM-bound by design (SURVEY.md section 8d gives the bytes per ray).
+//
+// Reference semantics: utils/rend_util.py:167-185,255-327 and
+// models/frameworks/neus.py:21-70,184-210,249-288,296,346-381.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// In-place exclusive scan (sum or product) of arr[0..n) in shared memory by one warp.
+// Each lane owns a contiguous segment; returns the total.  `excl_out` may alias arr.
+template <bool kMul>
+__device__ __forceinline__ float warp_scan_excl(const float* arr, float* excl_out, float* incl_out, int n, int lane) {
+  const int seg = (n + 31) >> 5;
+  const int lo = min(lane * seg, n), hi = min(lo + seg, n);
+  float tot = kMul ? 1.0f : 0.0f;
+  for (int i = lo; i < hi; ++i) tot = kMul ? tot * arr[i] : tot + arr[i];
+  float incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl = kMul ? incl * t : incl + t;
+  }
+  float run = __shfl_up_sync(kFull, incl, 1);
+  if (lane == 0) run = kMul ? 1.0f : 0.0f;
+  const float total = __shfl_sync(kFull, incl, 31);
+  __syncwarp();
+  for (int i = lo; i < hi; ++i) {
+    const float v = arr[i];
+    if (excl_out) excl_out[i] = run;
+    run = kMul ? run * v : run + v;
+    if (incl_out) incl_out[i] = run;
+  }
+  __syncwarp();
+  return total;
+}
+
+// torch.searchsorted(cdf, u, right=False): first index i in [0, M] with cdf[i] >= u.
+__device__ __forceinline__ int lower_bound(const float* cdf, int M, float u) {
+  int lo = 0, hi = M;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] < u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Tail of sample_pdf / sample_cdf (rend_util.py:275-292), un-fused fp32 ops so that the
+// result is bit-identical to the separate torch elementwise kernels given the same cdf and u.
+__device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins, int M, float u, float eps,
+                                            int* below_out, int* above_out) {
+  const int ind = lower_bound(cdf, M, u);
+  const int below = max(ind - 1, 0), above = min(ind, M - 1);
+  const float cb = cdf[below], ca = cdf[above];
+  float denom = __fsub_rn(ca, cb);
+  if (denom < eps) denom = 1.0f;
+  const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+  const float bb = bins[below], ba = bins[above];
+  if (below_out) *below_out = below;
+  if (above_out) *above_out = above;
+  return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+}
+
+__global__ void near_far_kernel(const float* __restrict__ o, const float* __restrict__ d, int64_t R, float r,
+                                float* __restrict__ near, float* __restrict__ far) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  // torch.sum over the 3 products, left to right
+  const float dot = __fadd_rn(__fadd_rn(__fmul_rn(o[3 * i], d[3 * i]), __fmul_rn(o[3 * i + 1], d[3 * i + 1])),
+                              __fmul_rn(o[3 * i + 2], d[3 * i + 2]));
+  const float mid = -dot;
+  near[i] = fmaxf(mid - r, 0.0f);
+  far[i] = fmaxf(mid + r, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sample_pdf / sample_cdf: one warp per ray, CDF [M] staged in dynamic smem.
+// ---------------------------------------------------------------------------------------------
+__global__ void sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                  const float* __restrict__ u_in, int64_t R, int M, int N, int cdf_given, float eps,
+                                  float* __restrict__ samples, int* __restrict__ below, int* __restrict__ above,
+                                  float* __restrict__ cdf_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (ray >= R) return;
+  float* cdf = smem + (size_t)warp * 2 * M;  // [M]
+  float* sb = cdf + M;                       // bins [M]
+  const float* w = weights + ray * (int64_t)(M - 1);
+  const float* b = bins + ray * (int64_t)M;
+  for (int i = lane; i < M; i += 32) sb[i] = b[i];
+  if (cdf_given) {
+    for (int i = lane; i < M - 1; i += 32) cdf[i + 1] = w[i];
+    if (lane == 0) cdf[0] = 0.0f;
+    __syncwarp();
+  } else {
+    float part = 0.0f;
+    for (int i = lane; i < M - 1; i += 32) {
+      const float v = w[i] + 1e-5f;
+      cdf[i + 1] = v;
+      part += v;
+    }
+    const float tot = warp_sum(part);
+    __syncwarp();
+    for (int i = lane; i < M - 1; i += 32) cdf[i + 1] = __fdiv_rn(cdf[i + 1], tot);
+    if (lane == 0) cdf[0] = 0.0f;
+    __syncwarp();
+    warp_scan_excl<false>(cdf + 1, nullptr, cdf + 1, M - 1, lane);
+  }
+  if (cdf_out)
+    for (int i = lane; i < M; i += 32) cdf_out[ray * (int64_t)M + i] = cdf[i];
+  for (int j = lane; j < N; j += 32) {
+    const float u = u_in ? u_in[ray * (int64_t)N + j] : nr_linspace01(j, N);
+    int bl, ab;
+    const float s = invert_cdf(cdf, sb, M, u, eps, &bl, &ab);
+    samples[ray * (int64_t)N + j] = s;
+    if (below) below[ray * (int64_t)N + j] = bl;
+    if (above) above[ray * (int64_t)N + j] = ab;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NeuS ray prologue (neus.py:169-172,184-210)
+// ---------------------------------------------------------------------------------------------
+__global__ void neus_ray_setup_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t R,
+                                      float radius, float near_bypass, float far_bypass, int n_samples,
+                                      float* __restrict__ dirs, float* __restrict__ near_out,
+                                      float* __restrict__ far_out, float* __restrict__ d_new,
+                                      float* __restrict__ pts_new) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (ray >= R) return;
+  const float ox = rays_o[3 * ray], oy = rays_o[3 * ray + 1], oz = rays_o[3 * ray + 2];
+  float dx = rays_d[3 * ray], dy = rays_d[3 * ray + 1], dz = rays_d[3 * ray + 2];
+  // F.normalize(dim=-1): x / max(||x||, 1e-12)
+  const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
+  dx = __fdiv_rn(dx, nrm); dy = __fdiv_rn(dy, nrm); dz = __fdiv_rn(dz, nrm);
+  const float dot = __fadd_rn(__fadd_rn(__fmul_rn(ox, dx), __fmul_rn(oy, dy)), __fmul_rn(oz, dz));
+  const float mid = -dot;
+  float nr_ = fmaxf(mid - radius, 0.0f), fr_ = fmaxf(mid + radius, radius);
+  if (!isnan(near_bypass)) nr_ = near_bypass;
+  if (!isnan(far_bypass)) fr_ = far_bypass;
+  if (lane == 0) {
+    dirs[3 * ray] = dx; dirs[3 * ray + 1] = dy; dirs[3 * ray + 2] = dz;
+    near_out[ray] = nr_; far_out[ray] = fr_;
+  }
+  for (int i = lane; i < n_samples; i += 32) {
+    const float t = nr_linspace01(i, n_samples);
+    // near * (1 - t) + far * t  (separate torch ops)
+    const float d = __fadd_rn(__fmul_rn(nr_, __fsub_rn(1.0f, t)), __fmul_rn(fr_, t));
+    d_new[ray * (int64_t)n_samples + i] = d;
+    float* p = pts_new + (ray * (int64_t)n_samples + i) * 3;
+    p[0] = __fadd_rn(ox, __fmul_rn(d, dx));
+    p[1] = __fadd_rn(oy, __fmul_rn(d, dy));
+    p[2] = __fadd_rn(oz, __fmul_rn(d, dz));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NeuS up-sampling iteration (neus.py:249-277): merge + weights + inverse-CDF sampling.
+// smem per warp: d[cap], sdf[cap], a[cap], b[cap], dn[nmax], sn[nmax]
+// ---------------------------------------------------------------------------------------------
+__global__ void neus_upsample_kernel(const float* __restrict__ rays_o, const float* __restrict__ dirs, int64_t R,
+                                     float* __restrict__ d_buf, float* __restrict__ sdf_buf, int cap, int m_cur,
+                                     const float* __restrict__ d_new, const float* __restrict__ sdf_new, int n_new,
+                                     int iter, int n_next, const float* __restrict__ u_next,
+                                     float* __restrict__ d_next, float* __restrict__ pts_next,
+                                     float* __restrict__ pts_all, float* __restrict__ d_mid_out,
+                                     float* __restrict__ pts_mid) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (ray >= R) return;
+  float* sd = smem + (size_t)warp * (4 * cap + 2 * cap);
+  float* ss = sd + cap;
+  float* sa = ss + cap;   // scratch: alpha / weights / cdf
+  float* sc = sa + cap;   // scratch: old d (during merge) / cdf
+  float* dn = sc + cap;   // new d   [<= cap]
+  float* sn = dn + cap;   // new sdf [<= cap]
+  const int M = m_cur + n_new;
+
+  // ---- 1. merge (neus.py:272-276: cat, sort, gather) ----
+  float* od = sc;  // old d
+  float* os = sa;  // old sdf
+  for (int i = lane; i < m_cur; i += 32) {
+    od[i] = d_buf[ray * (int64_t)cap + i];
+    os[i] = sdf_buf[ray * (int64_t)cap + i];
+  }
+  for (int j = lane; j < n_new; j += 32) {
+    dn[j] = d_new[ray * (int64_t)n_new + j];
+    sn[j] = sdf_new[ray * (int64_t)n_new + j];
+  }
+  __syncwarp();
+  for (int i = lane; i < m_cur; i += 32) {  // old element: stable, old before equal new
+    const float v = od[i];
+    int c = 0;
+    for (int k = 0; k < n_new; ++k) c += (dn[k] < v);
+    sd[i + c] = v;
+    ss[i + c] = os[i];
+  }
+  for (int j = lane; j < n_new; j += 32) {
+    const float v = dn[j];
+    int lo = 0, hi = m_cur;  // upper_bound in old: count(old <= v)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (od[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    int c = lo;
+    for (int k = 0; k < n_new; ++k) c += (dn[k] < v) || (dn[k] == v && k < j);
+    sd[c] = v;
+    ss[c] = sn[j];
+  }
+  __syncwarp();
+  for (int i = lane; i < M; i += 32) {
+    d_buf[ray * (int64_t)cap + i] = sd[i];
+    sdf_buf[ray * (int64_t)cap + i] = ss[i];
+  }
+  const float ox = rays_o[3 * ray], oy = rays_o[3 * ray + 1], oz = rays_o[3 * ray + 2];
+  const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
+
+  if (n_next > 0) {
+    // ---- 2. slopes -> logistic CDF -> alpha (neus.py:253-268) ----
+    const float s = 64.0f * (float)(1 << iter);
+    for (int i = lane; i < M - 1; i += 32) {
+      const float ps = ss[i], ns = ss[i + 1], pz = sd[i], nz = sd[i + 1];
+      const float mid_sdf = __fmul_rn(__fadd_rn(ps, ns), 0.5f);
+      const float dot = __fdiv_rn(__fsub_rn(ns, ps), __fadd_rn(__fsub_rn(nz, pz), 1e-5f));
+      float prev_dot = 0.0f;
+      if (i > 0) prev_dot = __fdiv_rn(__fsub_rn(ps, ss[i - 1]), __fadd_rn(__fsub_rn(pz, sd[i - 1]), 1e-5f));
+      const float dv = fminf(fmaxf(fminf(prev_dot, dot), -10.0f), 0.0f);
+      const float dist = __fsub_rn(nz, pz);
+      const float half = __fmul_rn(__fmul_rn(dv, dist), 0.5f);
+      const float prev_cdf = nr_sigmoid(__fmul_rn(__fsub_rn(mid_sdf, half), s));
+      const float next_cdf = nr_sigmoid(__fmul_rn(__fadd_rn(mid_sdf, half), s));
+      const float alpha = __fdiv_rn(__fadd_rn(__fsub_rn(prev_cdf, next_cdf), 1e-5f), __fadd_rn(prev_cdf, 1e-5f));
+      sa[i] = alpha;
+      sc[i] = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+    }
+    __syncwarp();
+    // w = alpha * exclusive cumprod(1 - alpha + 1e-10)   (neus.py:57-70)
+    warp_scan_excl<true>(sc, sc, nullptr, M - 1, lane);
+    // sample_pdf (rend_util.py:255-292): w + 1e-5 -> pdf -> cdf
+    float part = 0.0f;
+    for (int i = lane; i < M - 1; i += 32) {
+      const float w = __fadd_rn(__fmul_rn(sa[i], sc[i]), 1e-5f);
+      sa[i] = w;
+      part += w;
+    }
+    const float tot = warp_sum(part);
+    __syncwarp();
+    for (int i = lane; i < M - 1; i += 32) sc[i + 1] = __fdiv_rn(sa[i], tot);
+    if (lane == 0) sc[0] = 0.0f;
+    __syncwarp();
+    warp_scan_excl<false>(sc + 1, nullptr, sc + 1, M - 1, lane);
+    for (int j = lane; j < n_next; j += 32) {
+      const float u = u_next ? u_next[ray * (int64_t)n_next + j] : nr_linspace01(j, n_next);
+      const float d = invert_cdf(sc, sd, M, u, 1e-5f, nullptr, nullptr);
+      d_next[ray * (int64_t)n_next + j] = d;
+      float* p = pts_next + (ray * (int64_t)n_next + j) * 3;
+      p[0] = __fadd_rn(ox, __fmul_rn(d, dx));
+      p[1] = __fadd_rn(oy, __fmul_rn(d, dy));
+      p[2] = __fadd_rn(oz, __fmul_rn(d, dz));
+    }
+  } else {
+    // ---- 3. final: points, mid depths and mid points (neus.py:284-288) ----
+    for (int i = lane; i < M; i += 32) {
+      const float d = sd[i];
+      float* p = pts_all + (ray * (int64_t)M + i) * 3;
+      p[0] = __fadd_rn(ox, __fmul_rn(dx, d));
+      p[1] = __fadd_rn(oy, __fmul_rn(dy, d));
+      p[2] = __fadd_rn(oz, __fmul_rn(dz, d));
+      if (i < M - 1) {
+        const float dm = __fmul_rn(0.5f, __fadd_rn(sd[i + 1], d));
+        d_mid_out[ray * (int64_t)(M - 1) + i] = dm;
+        float* q = pts_mid + (ray * (int64_t)(M - 1) + i) * 3;
+        q[0] = __fadd_rn(ox, __fmul_rn(dx, dm));
+        q[1] = __fadd_rn(oy, __fmul_rn(dy, dm));
+        q[2] = __fadd_rn(oz, __fmul_rn(dz, dm));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NeuS compositing (neus.py:28-35,57-70,346-381): one warp per ray, 32 intervals per step,
+// multiplicative warp scan with a running carry for the exclusive transmittance.
+// ---------------------------------------------------------------------------------------------
+__global__ void neus_composite_kernel(const float* __restrict__ sdf, const float* __restrict__ nablas,
+                                      const float* __restrict__ radiance, const float* __restrict__ d_mid,
+                                      const float* __restrict__ s_dev, int64_t R, int M, int white_bkgd,
+                                      float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ acc,
+                                      float* __restrict__ normals, float* __restrict__ cdf_out,
+                                      float* __restrict__ alpha_out, float* __restrict__ w_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (ray >= R) return;
+  const float s = *s_dev;
+  const float* sd = sdf + ray * (int64_t)M;
+  const float* rad = radiance + ray * (int64_t)(M - 1) * 3;
+  const float* dm = d_mid + ray * (int64_t)(M - 1);
+  float carry = 1.0f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aw = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  for (int base = 0; base < M - 1; base += 32) {
+    const int i = base + lane;
+    const bool ok = i < M - 1;
+    float alpha = 0.0f, c0 = 0.0f;
+    if (ok) {
+      c0 = nr_sigmoid(__fmul_rn(sd[i], s));
+      const float c1 = nr_sigmoid(__fmul_rn(sd[i + 1], s));
+      alpha = fmaxf(__fdiv_rn(__fsub_rn(c0, c1), __fadd_rn(c0, 1e-10f)), 0.0f);
+      if (cdf_out) {
+        cdf_out[ray * (int64_t)M + i] = c0;
+        if (i == M - 2) cdf_out[ray * (int64_t)M + i + 1] = c1;
+      }
+    }
+    const float f = ok ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+    float incl = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl *= t;
+    }
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float w = alpha * (carry * excl);
+    carry *= __shfl_sync(kFull, incl, 31);
+    if (ok) {
+      if (alpha_out) alpha_out[ray * (int64_t)(M - 1) + i] = alpha;
+      if (w_out) w_out[ray * (int64_t)(M - 1) + i] = w;
+      ar += w * rad[3 * i]; ag += w * rad[3 * i + 1]; ab += w * rad[3 * i + 2];
+      ad += w * dm[i];
+      aw += w;
+      if (nablas) {
+        const float* nb = nablas + (ray * (int64_t)M + i) * 3;
+        const float x = nb[0], y = nb[1], z = nb[2];
+        const float inv = 1.0f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+        nx += w * x * inv; ny += w * y * inv; nz += w * z * inv;
+      }
+    }
+  }
+  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aw = warp_sum(aw);
+  if (nablas) { nx = warp_sum(nx); ny = warp_sum(ny); nz = warp_sum(nz); }
+  if (lane == 0) {
+    if (white_bkgd) { ar += 1.0f - aw; ag += 1.0f - aw; ab += 1.0f - aw; }
+    rgb[3 * ray] = ar; rgb[3 * ray + 1] = ag; rgb[3 * ray + 2] = ab;
+    depth[ray] = ad / (aw + 1e-10f);
+    acc[ray] = aw;
+    if (normals) { normals[3 * ray] = nx; normals[3 * ray + 1] = ny; normals[3 * ray + 2] = nz; }
+  }
+}
+
+}  // namespace
+
+extern "C" int nr_near_far_from_sphere(const float* rays_o, const float* rays_d, int64_t R, float r, float* near,
+                                       float* far, void* stream) {
+  NR_CHECK_ARG(R >= 0 && rays_o && rays_d && near && far, "nr_near_far_from_sphere: bad arguments");
+  if (R == 0) return NR_OK;
+  near_far_kernel<<<(unsigned)nr_cdiv(R, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, R, r, near, far);
+  NR_CHECK_LAUNCH("near_far_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_sample_pdf(const float* bins, const float* weights, const float* u, int64_t R, int32_t M, int32_t N,
+                             int32_t cdf_is_given, float eps, float* samples, int32_t* below, int32_t* above,
+                             float* cdf_out, void* stream) {
+  NR_CHECK_ARG(bins && weights && samples, "nr_sample_pdf: null pointer");
+  NR_CHECK_ARG(R >= 0 && M >= 2 && N >= 1, "nr_sample_pdf: need R>=0, M>=2, N>=1 (got R=%lld M=%d N=%d)", (long long)R, M, N);
+  if (R == 0) return NR_OK;
+  const size_t smem = (size_t)kWarpsPerBlock * 2 * M * sizeof(float);
+  NR_CHECK_ARG(smem <= 200 * 1024, "nr_sample_pdf: M=%d too large for shared memory staging", M);
+  if (smem > 48 * 1024)
+    NR_CHECK_CUDA(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sample_pdf_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      bins, weights, u, R, M, N, cdf_is_given, eps, samples, below, above, cdf_out);
+  NR_CHECK_LAUNCH("sample_pdf_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_neus_ray_setup(const float* rays_o, const float* rays_d, int64_t R, float radius, float near_bypass,
+                                 float far_bypass, int32_t n_samples, float* dirs, float* near, float* far,
+                                 float* d_new, float* pts_new, void* stream) {
+  NR_CHECK_ARG(rays_o && rays_d && dirs && near && far && d_new && pts_new, "nr_neus_ray_setup: null pointer");
+  NR_CHECK_ARG(R >= 0 && n_samples >= 2, "nr_neus_ray_setup: bad sizes");
+  if (R == 0) return NR_OK;
+  neus_ray_setup_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      rays_o, rays_d, R, radius, near_bypass, far_bypass, n_samples, dirs, near, far, d_new, pts_new);
+  NR_CHECK_LAUNCH("neus_ray_setup_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_neus_upsample_step(const float* rays_o, const float* dirs, int64_t R, float* d_buf, float* sdf_buf,
+                                     int32_t cap, int32_t m_cur, const float* d_new, const float* sdf_new,
+                                     int32_t n_new, int32_t iter, int32_t n_next, const float* u_next, float* d_next,
+                                     float* pts_next, float* pts_all, float* d_mid, float* pts_mid, void* stream) {
+  NR_CHECK_ARG(rays_o && dirs && d_buf && sdf_buf && d_new && sdf_new, "nr_neus_upsample_step: null pointer");
+  NR_CHECK_ARG(m_cur >= 0 && n_new >= 1 && m_cur + n_new <= cap && m_cur + n_new >= 2,
+               "nr_neus_upsample_step: m_cur=%d n_new=%d cap=%d", m_cur, n_new, cap);
+  NR_CHECK_ARG(n_next >= 0 && iter >= 0 && iter < 24, "nr_neus_upsample_step: bad iter/n_next");
+  if (n_next > 0) NR_CHECK_ARG(d_next && pts_next, "nr_neus_upsample_step: d_next/pts_next required");
+  else NR_CHECK_ARG(pts_all && d_mid && pts_mid, "nr_neus_upsample_step: final outputs required");
+  if (R == 0) return NR_OK;
+  const size_t smem = (size_t)kWarpsPerBlock * 6 * cap * sizeof(float);
+  NR_CHECK_ARG(smem <= 200 * 1024, "nr_neus_upsample_step: cap=%d too large", cap);
+  if (smem > 48 * 1024)
+    NR_CHECK_CUDA(cudaFuncSetAttribute(neus_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  neus_upsample_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      rays_o, dirs, R, d_buf, sdf_buf, cap, m_cur, d_new, sdf_new, n_new, iter, n_next, u_next, d_next, pts_next,
+      pts_all, d_mid, pts_mid);
+  NR_CHECK_LAUNCH("neus_upsample_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_neus_composite(const float* sdf, const float* nablas, const float* radiance, const float* d_mid,
+                                 const float* s_dev, int64_t R, int32_t M, int32_t white_bkgd, float* rgb,
+                                 float* depth, float* acc, float* normals, float* cdf_out, float* alpha_out,
+                                 float* weights_out, void* stream) {
+  NR_CHECK_ARG(sdf && radiance && d_mid && s_dev && rgb && depth && acc, "nr_neus_composite: null pointer");
+  NR_CHECK_ARG(R >= 0 && M >= 2, "nr_neus_composite: bad sizes");
+  NR_CHECK_ARG((nablas != nullptr) == (normals != nullptr), "nr_neus_composite: nablas and normals go together");
+  if (R == 0) return NR_OK;
+  neus_composite_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      sdf, nablas, radiance, d_mid, s_dev, R, M, white_bkgd, rgb, depth, acc, normals, cdf_out, alpha_out,
+      weights_out);
+  NR_CHECK_LAUNCH("neus_composite_kernel");
+  return NR_OK;
+}

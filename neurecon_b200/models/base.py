@@ -1,0 +1,352 @@
+"""Drop-in for the hot-path part of the reference's ``models/base.py``.
+
+Same class names, constructor signatures, ``state_dict`` keys/shapes and call signatures as
+the reference (SuwoongHeo/neurecon ``models/base.py``):
+
+* ``Embedder`` / ``get_embedder``   -- base.py:14-81
+* ``DenseLayer``                    -- base.py:118-129
+* ``ImplicitSurface``               -- base.py:131-282 (``forward``, ``forward_with_nablas``)
+* ``RadianceNet``                   -- base.py:312-391
+* ``NeRF`` (NeRF++ background)      -- base.py:395-453
+
+Parameters stay ordinary ``nn.Parameter``s (``*.weight_g / *.weight_v / *.bias``) so reference
+checkpoints load unchanged; the arithmetic runs in the sm_100a kernels behind the C-ABI.
+The SIREN variant (``use_siren=True``) is outside the hot-path scope.
+"""
+import math
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .._lib import C
+
+
+# --------------------------------------------------------------------------------------------
+# Embedder (base.py:14-81).  Stand-alone use only; inside the MLP kernels the encoding is fused.
+# --------------------------------------------------------------------------------------------
+class Embedder(nn.Module):
+    def __init__(self, input_dim, max_freq_log2, N_freqs, log_sampling=True, include_input=True,
+                 periodic_fns=(torch.sin, torch.cos)):
+        super().__init__()
+        self.input_dim = input_dim
+        self.include_input = include_input
+        self.periodic_fns = periodic_fns
+        self.out_dim = (input_dim if include_input else 0) + input_dim * N_freqs * len(periodic_fns)
+        if log_sampling:
+            bands = 2.0 ** torch.linspace(0.0, max_freq_log2, N_freqs)
+        else:
+            bands = torch.linspace(2.0 ** 0.0, 2.0 ** max_freq_log2, N_freqs)
+        self.freq_bands = bands.numpy().tolist()
+
+    def forward(self, input):
+        assert input.shape[-1] == self.input_dim
+        parts = [input] if self.include_input else []
+        for f in self.freq_bands:
+            for fn in self.periodic_fns:
+                parts.append(fn(input * f))
+        return torch.cat(parts, dim=-1)
+
+
+def get_embedder(multires, input_dim=3):
+    if multires < 0:
+        return nn.Identity(), input_dim
+    emb = Embedder(input_dim=input_dim, max_freq_log2=multires - 1, N_freqs=multires,
+                   log_sampling=True, include_input=True, periodic_fns=[torch.sin, torch.cos])
+    return emb, emb.out_dim
+
+
+class DenseLayer(nn.Linear):
+    """nn.Linear + activation (base.py:118-129).  Only the parameter container and the
+    activation tag matter here; the product is evaluated by the fused kernels."""
+
+    def __init__(self, input_dim, out_dim, *args, activation=None, **kwargs):
+        super().__init__(input_dim, out_dim, *args, **kwargs)
+        self.activation = nn.ReLU(inplace=True) if activation is None else activation
+
+    def forward(self, x):
+        return self.activation(super().forward(x))
+
+
+def _weight_norm(layer):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return nn.utils.weight_norm(layer)
+
+
+def _effective_weight(layer):
+    """W = g * v / ||v||_row for weight-normed layers (old-style weight_norm, dim=0), else .weight.
+    Evaluated in PyTorch so that autograd owns g and v."""
+    if hasattr(layer, "weight_g"):
+        v, g = layer.weight_v, layer.weight_g
+        return v * (g / v.norm(dim=1, keepdim=True))
+    return layer.weight
+
+
+def _param_key(module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+def _pad4(k):
+    return (k + 3) & ~3
+
+
+def _pack_layers(weights, biases, scales=None):
+    """fp32 [out, pad4(in)] zero-padded copies + descriptor arrays."""
+    Ws, bs = [], []
+    for i, (W, b) in enumerate(zip(weights, biases)):
+        W = W.detach().float()
+        if scales is not None and scales[i] != 1.0:
+            W = W * scales[i]
+        out_d, in_d = W.shape
+        Wp = torch.zeros(out_d, _pad4(in_d), dtype=torch.float32, device=W.device)
+        Wp[:, :in_d] = W
+        Ws.append(Wp.contiguous())
+        bs.append(b.detach().float().contiguous())
+    return Ws, bs
+
+
+_MAX_POINTS_PER_CALL = 1 << 18
+
+
+class ImplicitSurface(nn.Module):
+    """Geometry MLP (base.py:131-282): PE -> D softplus(beta=100) layers with a skip
+    ``cat([h, pe])/sqrt(2)`` -> linear(1 + W_geo_feat)."""
+
+    def __init__(self, W=256, D=8, skips=[4], W_geo_feat=256, input_ch=3, radius_init=1.0,
+                 obj_bounding_size=2.0, geometric_init=True, embed_multires=6, weight_norm=True,
+                 use_siren=False):
+        super().__init__()
+        if use_siren:
+            raise NotImplementedError("SIREN surfaces are outside the neurecon_b200 hot-path scope")
+        self.radius_init = radius_init
+        self.register_buffer("obj_bounding_size", torch.tensor([obj_bounding_size]).float())
+        self.geometric_init = geometric_init
+        self.D, self.W, self.W_geo_feat = D, W, W_geo_feat
+        self.skips = list(skips)
+        self.use_siren = False
+        self.embed_multires = embed_multires
+        self.embed_fn, input_ch = get_embedder(embed_multires)
+        self._pe_dim = input_ch
+
+        layers = []
+        for l in range(D + 1):
+            if l == D:
+                out_dim = 1 + W_geo_feat if W_geo_feat > 0 else 1
+            elif (l + 1) in self.skips:
+                out_dim = W - input_ch
+            else:
+                out_dim = W
+            in_dim = input_ch if l == 0 else W
+            if l != D:
+                layer = DenseLayer(in_dim, out_dim, activation=nn.Softplus(beta=100))
+            else:
+                layer = nn.Linear(in_dim, out_dim)
+            if geometric_init:
+                self._sphere_init(layer, l, in_dim, out_dim, input_ch)
+            if weight_norm:
+                layer = _weight_norm(layer)
+            layers.append(layer)
+        self.surface_fc_layers = nn.ModuleList(layers)
+        self._cache = {}
+
+    def _sphere_init(self, layer, l, in_dim, out_dim, input_ch):
+        """SAL / IDR sphere initialisation (same distributions as base.py:207-224)."""
+        with torch.no_grad():
+            if l == self.D:
+                layer.weight.normal_(mean=math.sqrt(math.pi) / math.sqrt(in_dim), std=0.0001)
+                layer.bias.fill_(-self.radius_init)
+            elif self.embed_multires > 0 and l == 0:
+                layer.bias.zero_()
+                layer.weight[:, 3:].zero_()
+                layer.weight[:, :3].normal_(0.0, math.sqrt(2) / math.sqrt(out_dim))
+            elif self.embed_multires > 0 and l in self.skips:
+                layer.bias.zero_()
+                layer.weight.normal_(0.0, math.sqrt(2) / math.sqrt(out_dim))
+                layer.weight[:, -(input_ch - 3):].zero_()
+            else:
+                layer.bias.zero_()
+                layer.weight.normal_(0.0, math.sqrt(2) / math.sqrt(out_dim))
+
+    def pretrain_hook(self, configs={}):
+        configs["target_radius"] = self.radius_init
+        configs["obj_bounding_size"] = self.obj_bounding_size.item()
+        return False
+
+    # ---- packed weights / descriptor -------------------------------------------------------
+    def _check_supported(self):
+        if len(self.skips) > 1:
+            raise NotImplementedError("neurecon_b200 supports at most one skip connection")
+        if self.W_geo_feat <= 0:
+            raise NotImplementedError("neurecon_b200 supports the IDR-style geometry feature (W_geo_feat > 0)")
+        for s in self.skips:
+            if not (0 < s < self.D):
+                raise NotImplementedError("skip layer index must be in (0, D)")
+
+    def _descriptor(self):
+        """Device-resident packed weights + C descriptor, rebuilt only when a parameter changed."""
+        self._check_supported()
+        key = _param_key(self)
+        c = self._cache
+        if c.get("key") != key:
+            Wl = [_effective_weight(l) for l in self.surface_fc_layers]
+            bl = [l.bias for l in self.surface_fc_layers]
+            scales = [1.0 / math.sqrt(2) if i in self.skips else 1.0 for i in range(self.D + 1)]
+            Ws, bs = _pack_layers(Wl, bl, scales)
+            d = _lib.SdfNet()
+            d.n_layers = self.D + 1
+            d.multires = self.embed_multires
+            d.skip_layer = self.skips[0] if self.skips else -1
+            d.width = self.W
+            for i, l in enumerate(self.surface_fc_layers):
+                out_d, in_d = Wl[i].shape
+                d.in_dim[i], d.out_dim[i] = in_d, out_d
+                d.W[i], d.b[i] = Ws[i].data_ptr(), bs[i].data_ptr()
+            d.umma_image = None
+            d.umma_bias = None
+            c.clear()
+            c.update(key=key, desc=d, keep=(Ws, bs))
+        return c["desc"]
+
+    # ---- forward -----------------------------------------------------------------------------
+    def _needs_grad(self, x, has_grad):
+        return has_grad and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
+    def _run(self, x, want_nablas, want_feat):
+        _lib.require_cuda(x)
+        lib = _lib.get_lib()
+        shape = x.shape[:-1]
+        xf = _lib.f32c(x.detach().reshape(-1, 3))
+        n = xf.shape[0]
+        dev = xf.device
+        desc = self._descriptor()
+        sdf = torch.empty(n, dtype=torch.float32, device=dev)
+        nabla = torch.empty(n, 3, dtype=torch.float32, device=dev) if want_nablas else None
+        feat = torch.empty(n, self.W_geo_feat, dtype=torch.float32, device=dev) if want_feat else None
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            for i0 in range(0, n, _MAX_POINTS_PER_CALL):
+                m = min(_MAX_POINTS_PER_CALL, n - i0)
+                xs = xf[i0:i0 + m]
+                fptr = _lib.ptr(feat[i0:i0 + m]) if want_feat else None
+                if want_nablas:
+                    need = lib.nr_sdf_forward_nablas_f32_workspace(C.byref(desc), m)
+                    ws = _lib.workspace(need, dev)
+                    _lib.check(lib.nr_sdf_forward_nablas_f32(
+                        C.byref(desc), _lib.ptr(xs), m, _lib.ptr(sdf[i0:i0 + m]), _lib.ptr(nabla[i0:i0 + m]),
+                        fptr, self.W_geo_feat, _lib.ptr(ws), ws.numel(), st), "sdf_forward_nablas")
+                else:
+                    need = lib.nr_sdf_forward_f32_workspace(C.byref(desc), m)
+                    ws = _lib.workspace(need, dev)
+                    _lib.check(lib.nr_sdf_forward_f32(
+                        C.byref(desc), _lib.ptr(xs), m, _lib.ptr(sdf[i0:i0 + m]), fptr, self.W_geo_feat,
+                        _lib.ptr(ws), ws.numel(), st), "sdf_forward")
+        sdf = sdf.reshape(shape)
+        if nabla is not None:
+            nabla = nabla.reshape(*shape, 3)
+        if feat is not None:
+            feat = feat.reshape(*shape, self.W_geo_feat)
+        return sdf, nabla, feat
+
+    def forward(self, x, return_h=False):
+        """base.py:243-263."""
+        if self._needs_grad(x, torch.is_grad_enabled()):
+            from .autograd import sdf_forward_autograd
+            return sdf_forward_autograd(self, x, return_h)
+        sdf, _, feat = self._run(x, want_nablas=False, want_feat=return_h)
+        return (sdf, feat) if return_h else sdf
+
+    def forward_with_nablas(self, x, has_grad_bypass=None):
+        """base.py:265-282: (sdf, d sdf / d x, geometry feature).  The normal is the analytic
+        forward-mode derivative evaluated inside the kernel instead of ``autograd.grad``."""
+        has_grad = torch.is_grad_enabled() if has_grad_bypass is None else has_grad_bypass
+        if self._needs_grad(x, has_grad):
+            from .autograd import sdf_forward_with_nablas_autograd
+            return sdf_forward_with_nablas_autograd(self, x)
+        return self._run(x, want_nablas=True, want_feat=True)
+
+
+class RadianceNet(nn.Module):
+    """Appearance MLP (base.py:312-391): cat([PE(x), PE(view), normals, feature]) -> D ReLU
+    layers -> Sigmoid(3)."""
+
+    def __init__(self, D=4, W=256, skips=[], W_geo_feat=256, embed_multires=6, embed_multires_view=4,
+                 use_view_dirs=True, weight_norm=True, use_siren=False):
+        super().__init__()
+        if use_siren:
+            raise NotImplementedError("SIREN radiance nets are outside the neurecon_b200 hot-path scope")
+        self.skips = list(skips)
+        self.D, self.W = D, W
+        self.use_view_dirs = use_view_dirs
+        self.W_geo_feat = W_geo_feat
+        self.embed_multires, self.embed_multires_view = embed_multires, embed_multires_view
+        self.embed_fn, in_pts = get_embedder(embed_multires)
+        if use_view_dirs:
+            self.embed_fn_view, in_views = get_embedder(embed_multires_view)
+            in0 = in_pts + in_views + 3 + W_geo_feat
+        else:
+            in0 = in_pts + W_geo_feat
+        layers = []
+        for l in range(D + 1):
+            out_dim = 3 if l == D else W
+            in_dim = in0 if l == 0 else (in0 + W if l in self.skips else W)
+            act = nn.Sigmoid() if l == D else nn.ReLU(inplace=True)
+            layer = DenseLayer(in_dim, out_dim, activation=act)
+            if weight_norm:
+                layer = _weight_norm(layer)
+            layers.append(layer)
+        self.layers = nn.ModuleList(layers)
+        self._cache = {}
+
+    def _descriptor(self):
+        if self.skips or not self.use_view_dirs:
+            raise NotImplementedError("neurecon_b200 RadianceNet supports skips=[] with use_view_dirs=True "
+                                      "(every shipped reference config)")
+        key = _param_key(self)
+        c = self._cache
+        if c.get("key") != key:
+            Wl = [_effective_weight(l) for l in self.layers]
+            Ws, bs = _pack_layers(Wl, [l.bias for l in self.layers])
+            d = _lib.RadianceNetDesc()
+            d.n_layers = self.D + 1
+            d.multires, d.multires_view, d.feat_dim = self.embed_multires, self.embed_multires_view, self.W_geo_feat
+            for i in range(self.D + 1):
+                out_d, in_d = Wl[i].shape
+                d.in_dim[i], d.out_dim[i] = in_d, out_d
+                d.W[i], d.b[i] = Ws[i].data_ptr(), bs[i].data_ptr()
+            d.umma_image = None
+            d.umma_bias = None
+            c.clear()
+            c.update(key=key, desc=d, keep=(Ws, bs))
+        return c["desc"]
+
+    def forward(self, x, view_dirs, normals, geometry_feature):
+        """base.py:372-391."""
+        needs_grad = torch.is_grad_enabled() and (
+            normals.requires_grad or geometry_feature.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            from .autograd import radiance_forward_autograd
+            return radiance_forward_autograd(self, x, view_dirs, normals, geometry_feature)
+        _lib.require_cuda(x, view_dirs, normals, geometry_feature)
+        lib = _lib.get_lib()
+        shape = x.shape[:-1]
+        xf = _lib.f32c(x.detach().reshape(-1, 3))
+        vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
+        nf = _lib.f32c(normals.detach().reshape(-1, 3))
+        ff = _lib.f32c(geometry_feature.detach().reshape(-1, self.W_geo_feat))
+        n, dev = xf.shape[0], xf.device
+        desc = self._descriptor()
+        rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            for i0 in range(0, n, _MAX_POINTS_PER_CALL):
+                m = min(_MAX_POINTS_PER_CALL, n - i0)
+                need = lib.nr_radiance_forward_f32_workspace(C.byref(desc), m)
+                ws = _lib.workspace(need, dev)
+                _lib.check(lib.nr_radiance_forward_f32(
+                    C.byref(desc), _lib.ptr(xf[i0:i0 + m]), _lib.ptr(vf[i0:i0 + m]), _lib.ptr(nf[i0:i0 + m]),
+                    _lib.ptr(ff[i0:i0 + m]), self.W_geo_feat, m, _lib.ptr(rgb[i0:i0 + m]), _lib.ptr(ws),
+                    ws.numel(), st), "radiance_forward")
+        return rgb.reshape(*shape, 3)

@@ -1,0 +1,238 @@
+"""Drop-in for the reference's ``models/frameworks/neus.py`` hot path:
+``cdf_Phi_s`` / ``sdf_to_alpha`` / ``sdf_to_w`` / ``alpha_to_w`` (:21-70), the ``NeuS`` module
+(:72-115), ``volume_render`` (:118-397) and ``SingleRenderer`` (:399-405).
+
+``volume_render`` keeps the reference's signature, defaults and return structure; per ray chunk
+it issues a fixed sequence of library calls (no host syncs, CUDA-graph capturable):
+
+    ray_setup -> [sdf MLP, upsample_step] x (N_upsample_iters + 1) -> sdf+nabla MLP (pts)
+              -> sdf+nabla+feature+radiance MLP (mid points) -> composite
+"""
+import math
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ..base import ImplicitSurface, RadianceNet
+
+
+# --------------------------------------------------------------------------------------------
+# small tensor helpers of the reference API (neus.py:21-70); thin torch compositions, used by
+# debug tools -- the renderer itself goes through nr_neus_composite.
+# --------------------------------------------------------------------------------------------
+def cdf_Phi_s(x, s):
+    return torch.sigmoid(x * s)
+
+
+def sdf_to_alpha(sdf, s):
+    cdf = cdf_Phi_s(sdf, s)
+    alpha = ((cdf[..., :-1] - cdf[..., 1:]) / (cdf[..., :-1] + 1e-10)).clamp_min(0)
+    return cdf, alpha
+
+
+def alpha_to_w(alpha):
+    shifted = torch.cat([torch.ones_like(alpha[..., :1]), 1.0 - alpha + 1e-10], dim=-1)
+    return alpha * torch.cumprod(shifted, dim=-1)[..., :-1]
+
+
+def sdf_to_w(sdf, s):
+    cdf, alpha = sdf_to_alpha(sdf, s)
+    return cdf, alpha, alpha_to_w(alpha)
+
+
+class NeuS(nn.Module):
+    """neus.py:72-115 (same constructor, parameters and methods)."""
+
+    def __init__(self, variance_init=0.05, speed_factor=1.0, input_ch=3, W_geo_feat=-1, use_outside_nerf=False,
+                 obj_bounding_radius=1.0, surface_cfg=dict(), radiance_cfg=dict()):
+        super().__init__()
+        self.ln_s = nn.Parameter(data=torch.Tensor([-np.log(variance_init) / speed_factor]), requires_grad=True)
+        self.speed_factor = speed_factor
+        self.implicit_surface = ImplicitSurface(
+            W_geo_feat=W_geo_feat, input_ch=input_ch, obj_bounding_size=obj_bounding_radius, **surface_cfg)
+        if W_geo_feat < 0:
+            W_geo_feat = self.implicit_surface.W
+        self.radiance_net = RadianceNet(W_geo_feat=W_geo_feat, **radiance_cfg)
+        if use_outside_nerf:
+            from ..base import NeRF
+            self.nerf_outside = NeRF(input_ch=4, multires=10, multires_view=4, use_view_dirs=True)
+
+    def forward_radiance(self, x, view_dirs):
+        _, nablas, geometry_feature = self.implicit_surface.forward_with_nablas(x)
+        return self.radiance_net.forward(x, view_dirs, nablas, geometry_feature)
+
+    def forward_s(self):
+        return torch.exp(self.ln_s * self.speed_factor)
+
+    def forward(self, x, view_dirs):
+        sdf, nablas, geometry_feature = self.implicit_surface.forward_with_nablas(x)
+        radiances = self.radiance_net.forward(x, view_dirs, nablas, geometry_feature)
+        return radiances, sdf, nablas
+
+
+def _composite(sdf, nablas, radiances, d_mid, s, white_bkgd, calc_normal, detailed):
+    """nr_neus_composite on [R, M] per-sample tensors."""
+    lib = _lib.get_lib()
+    R, M = sdf.shape
+    dev = sdf.device
+    f = dict(dtype=torch.float32, device=dev)
+    rgb, depth, acc = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
+    normals = torch.empty(R, 3, **f) if calc_normal else None
+    cdf = torch.empty(R, M, **f) if detailed else None
+    alpha = torch.empty(R, M - 1, **f) if detailed else None
+    w = torch.empty(R, M - 1, **f) if detailed else None
+    _lib.check(lib.nr_neus_composite(
+        _lib.ptr(sdf), _lib.ptr(nablas) if calc_normal else None, _lib.ptr(radiances), _lib.ptr(d_mid), _lib.ptr(s),
+        R, M, int(bool(white_bkgd)), _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(normals),
+        _lib.ptr(cdf), _lib.ptr(alpha), _lib.ptr(w), _lib.stream_ptr(dev)), "neus_composite")
+    return rgb, depth, acc, normals, cdf, alpha, w
+
+
+def _upsample(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
+              N_upsample_iters, perturb):
+    """neus.py:184-288 for one flat ray chunk [R,3]: returns dirs, d_all, pts, d_mid, pts_mid."""
+    lib = _lib.get_lib()
+    R, dev = rays_o.shape[0], rays_o.device
+    f = dict(dtype=torch.float32, device=dev)
+    st = _lib.stream_ptr(dev)
+    n_fine = N_importance // N_upsample_iters
+    cap = N_samples + n_fine * N_upsample_iters
+    dirs, near, far = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
+    d_new, pts_new = torch.empty(R, N_samples, **f), torch.empty(R, N_samples, 3, **f)
+    nan = float("nan")
+    _lib.check(lib.nr_neus_ray_setup(
+        _lib.ptr(rays_o), _lib.ptr(rays_d_raw), R, float(obj_bounding_radius),
+        nan if near_bypass is None else float(near_bypass), nan if far_bypass is None else float(far_bypass),
+        N_samples, _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far), _lib.ptr(d_new), _lib.ptr(pts_new), st),
+        "neus_ray_setup")
+    d_buf, sdf_buf = torch.empty(R, cap, **f), torch.empty(R, cap, **f)
+    pts_all, d_mid, pts_mid = torch.empty(R, cap, 3, **f), torch.empty(R, cap - 1, **f), torch.empty(R, cap - 1, 3, **f)
+    m_cur, n_new = 0, N_samples
+    with torch.no_grad():
+        for it in range(N_upsample_iters + 1):
+            sdf_new = model.implicit_surface.forward(pts_new)
+            last = it == N_upsample_iters
+            n_next = 0 if last else n_fine
+            u = None
+            if not last and perturb:
+                u = torch.rand([R, n_next], device=dev)  # same call as rend_util.py:271
+            d_next = torch.empty(R, max(n_next, 1), **f)
+            pts_next = torch.empty(R, max(n_next, 1), 3, **f)
+            _lib.check(lib.nr_neus_upsample_step(
+                _lib.ptr(rays_o), _lib.ptr(dirs), R, _lib.ptr(d_buf), _lib.ptr(sdf_buf), cap, m_cur,
+                _lib.ptr(d_new), _lib.ptr(sdf_new), n_new, it, n_next, _lib.ptr(u), _lib.ptr(d_next),
+                _lib.ptr(pts_next), _lib.ptr(pts_all), _lib.ptr(d_mid), _lib.ptr(pts_mid), st), "neus_upsample_step")
+            m_cur += n_new
+            d_new, pts_new, n_new = d_next, pts_next, n_next
+    return dirs, d_buf, pts_all, d_mid, pts_mid
+
+
+def volume_render(
+        rays_o,
+        rays_d,
+        model: NeuS,
+
+        obj_bounding_radius=1.0,
+
+        batched=False,
+        batched_info={},
+
+        # render algorithm config
+        calc_normal=False,
+        use_view_dirs=True,
+        rayschunk=65536,
+        netchunk=1048576,
+        white_bkgd=False,
+        near_bypass: Optional[float] = None,
+        far_bypass: Optional[float] = None,
+
+        # render function config
+        detailed_output=True,
+        show_progress=False,
+
+        # sampling related
+        perturb=False,
+        fixed_s_recp=1 / 64.,
+        N_samples=64,
+        N_importance=64,
+        N_outside=0,
+
+        # upsample related
+        upsample_algo='official_solution',
+        N_nograd_samples=2048,
+        N_upsample_iters=4,
+
+        **dummy_kwargs):
+    """neus.py:118-397.  rays_o / rays_d: [(B,) N_rays, 3] (rays_d not normalised).
+    Returns (rgb, depth_volume, ret) with the reference's ``ret`` keys and shapes."""
+    if upsample_algo != 'official_solution':
+        raise NotImplementedError("upsample_algo=%r: only 'official_solution' (every shipped config) is built"
+                                  % upsample_algo)
+    if N_outside > 0:
+        raise NotImplementedError("NeuS with NeRF++ background (N_outside > 0) is not built yet")
+    if not use_view_dirs:
+        raise NotImplementedError("use_view_dirs=False is not supported")
+    _lib.require_cuda(rays_o, rays_d)
+    if batched:
+        B = rays_d.shape[0]
+        prefix = [B, -1]
+    else:
+        B = 1
+        prefix = [-1]
+    dev = rays_o.device
+    o_flat = _lib.f32c(rays_o.reshape(-1, 3))
+    d_flat = _lib.f32c(rays_d.reshape(-1, 3))
+    n_total = o_flat.shape[0]
+    rays_per_b = n_total // B
+    M = N_samples + (N_importance // N_upsample_iters) * N_upsample_iters
+    s = model.forward_s().detach().float().contiguous()
+
+    outs = []
+    with torch.cuda.device(dev):
+        # the reference chunks along the ray axis (neus.py:385-395); batches are flattened here
+        # because rays are independent, and chunk boundaries do not change any value.
+        step = int(rayschunk) * B
+        for i0 in range(0, n_total, step):
+            ro, rd = o_flat[i0:i0 + step], d_flat[i0:i0 + step]
+            R = ro.shape[0]
+            dirs, d_all, pts, d_mid, pts_mid = _upsample(
+                model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
+                N_upsample_iters, perturb)
+            sdf, nablas, _ = model.implicit_surface.forward_with_nablas(pts)
+            views = dirs.unsqueeze(-2).expand(R, M - 1, 3)
+            radiances = model.forward_radiance(pts_mid, views)
+            rgb, depth, acc, normals, cdf, alpha, w = _composite(
+                sdf, nablas, radiances, d_mid, s, white_bkgd, calc_normal, detailed_output)
+            ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
+            if calc_normal:
+                ret_i['normals_volume'] = normals
+            if detailed_output:
+                ret_i['implicit_nablas'] = nablas
+                ret_i['implicit_surface'] = sdf
+                ret_i['radiance'] = radiances
+                ret_i['alpha'] = alpha
+                ret_i['cdf'] = cdf
+                ret_i['visibility_weights'] = w
+                ret_i['d_final'] = d_mid
+            outs.append(ret_i)
+
+    ret = OrderedDict()
+    for k in outs[0].keys():
+        v = outs[0][k] if len(outs) == 1 else torch.cat([o[k] for o in outs], 0)
+        ret[k] = v.reshape(*prefix, *v.shape[1:]) if batched else v
+    return ret['rgb'], ret['depth_volume'], ret
+
+
+class SingleRenderer(nn.Module):
+    """neus.py:399-405."""
+
+    def __init__(self, model: NeuS):
+        super().__init__()
+        self.model = model
+
+    def forward(self, rays_o, rays_d, **kwargs):
+        return volume_render(rays_o, rays_d, self.model, **kwargs)

@@ -1,0 +1,91 @@
+"""Drop-in for the hot-path part of the reference's ``utils/rend_util.py``:
+``near_far_from_sphere`` (:167-185), ``get_sphere_intersection`` (:188-210),
+``get_dvals_from_radius`` (:213-234), ``sample_pdf`` (:255-292), ``sample_cdf`` (:294-327).
+All of them run in the CUDA library; CPU tensors raise."""
+import torch
+
+from .. import _lib
+
+
+def near_far_from_sphere(ray_origins, ray_directions, r=1.0, keepdim=True):
+    """rend_util.py:167-185.  ``ray_directions`` already normalised."""
+    _lib.require_cuda(ray_origins, ray_directions)
+    lib = _lib.get_lib()
+    shape = ray_origins.shape[:-1]
+    o = _lib.f32c(ray_origins.reshape(-1, 3))
+    d = _lib.f32c(ray_directions.expand_as(ray_origins).reshape(-1, 3))
+    R = o.shape[0]
+    near = torch.empty(R, dtype=torch.float32, device=o.device)
+    far = torch.empty(R, dtype=torch.float32, device=o.device)
+    with torch.cuda.device(o.device):
+        _lib.check(lib.nr_near_far_from_sphere(_lib.ptr(o), _lib.ptr(d), R, float(r), _lib.ptr(near),
+                                               _lib.ptr(far), _lib.stream_ptr(o.device)), "near_far_from_sphere")
+    out_shape = (*shape, 1) if keepdim else shape
+    return near.reshape(out_shape), far.reshape(out_shape)
+
+
+def _invert(bins, w_or_cdf, N_importance, det, eps, cdf_given, u=None, return_details=False):
+    _lib.require_cuda(bins, w_or_cdf)
+    lib = _lib.get_lib()
+    prefix = bins.shape[:-1]
+    M = bins.shape[-1]
+    assert w_or_cdf.shape[-1] == M - 1, "weights/cdf must have one entry per interval"
+    b = _lib.f32c(bins.detach().reshape(-1, M))
+    w = _lib.f32c(w_or_cdf.detach().reshape(-1, M - 1))
+    R, dev = b.shape[0], b.device
+    if u is None and not det:
+        # same RNG call as the reference: torch.rand(prefix + [N]) on the device (rend_util.py:271)
+        u = torch.rand(list(prefix) + [N_importance], device=dev)
+    if u is not None:
+        u = _lib.f32c(u.reshape(-1, N_importance))
+    samples = torch.empty(R, N_importance, dtype=torch.float32, device=dev)
+    below = above = cdf = None
+    if return_details:
+        below = torch.empty(R, N_importance, dtype=torch.int32, device=dev)
+        above = torch.empty(R, N_importance, dtype=torch.int32, device=dev)
+        cdf = torch.empty(R, M, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nr_sample_pdf(_lib.ptr(b), _lib.ptr(w), _lib.ptr(u), R, M, N_importance, int(cdf_given),
+                                     float(eps), _lib.ptr(samples), _lib.ptr(below), _lib.ptr(above), _lib.ptr(cdf),
+                                     _lib.stream_ptr(dev)), "sample_pdf")
+    samples = samples.reshape(*prefix, N_importance)
+    if return_details:
+        return (samples, below.reshape(*prefix, N_importance), above.reshape(*prefix, N_importance),
+                cdf.reshape(*prefix, M))
+    return samples
+
+
+def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5, u=None, return_details=False):
+    """rend_util.py:255-292.  Extra keyword ``u`` supplies the uniforms explicitly (parity
+    tests); ``return_details`` also returns (below, above, cdf)."""
+    return _invert(bins, weights, N_importance, det, eps, False, u, return_details)
+
+
+def sample_cdf(bins, cdf, N_importance, det=False, eps=1e-5, u=None, return_details=False):
+    """rend_util.py:294-327 (``cdf`` is the un-normalised CDF with one entry per interval)."""
+    return _invert(bins, cdf, N_importance, det, eps, True, u, return_details)
+
+
+def get_sphere_intersection(ray_origins, ray_directions, r=1.0):
+    """rend_util.py:188-210 (exact ray/sphere near & far with hit mask)."""
+    _lib.require_cuda(ray_origins, ray_directions)
+    o2 = (ray_origins ** 2).sum(-1, keepdim=True)
+    od = (ray_origins * ray_directions).sum(-1, keepdim=True)
+    under = od ** 2 + r ** 2 - o2
+    mask = under > 0
+    sq = torch.sqrt(under.clamp_min(0))
+    zero = torch.zeros_like(od)
+    near = torch.where(mask, -sq - od, zero).clamp_min(0.0)
+    far = torch.where(mask, sq - od, zero).clamp_min(0.0)
+    return near, far, mask
+
+
+def get_dvals_from_radius(ray_origins, ray_directions, rs, far_end=True):
+    """rend_util.py:213-234."""
+    _lib.require_cuda(ray_origins, ray_directions, rs)
+    o2 = (ray_origins ** 2).sum(-1, keepdim=True)
+    od = (ray_origins * ray_directions).sum(-1, keepdim=True)
+    under = rs ** 2 - (o2 - od ** 2)
+    assert (under > 0).all()
+    sq = torch.sqrt(under)
+    return (-od + sq) if far_end else (-od - sq).clamp_min(0.0)

@@ -1,0 +1,82 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, imported through oracle.ref_loader) on deterministic synthetic inputs.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Each .npz stores the inputs that are not reproducible from a seed (none: rays and weights are
+re-derived from numpy seeds by neurecon_b200.utils.synthetic) and the reference outputs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+from neurecon_b200.utils import synthetic  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def npz(name, **arrs):
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                 for k, v in arrs.items()})
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def golden_neus(ref):
+    torch.manual_seed(0)
+    m = ref.neus.NeuS(**synthetic.NEUS_MODEL_KWARGS)
+    synthetic.reseed_parameters(m, seed=1)
+    R = 48
+    o, d = synthetic.make_rays(R, shell_radius=2.5, jitter=0.1, seed=1)
+    with torch.no_grad():
+        rgb, depth, ret = ref.neus.volume_render(o, d, m, calc_normal=True, detailed_output=True, perturb=False)
+    keep = ["rgb", "depth_volume", "mask_volume", "normals_volume", "implicit_surface", "implicit_nablas",
+            "radiance", "alpha", "cdf", "visibility_weights", "d_final"]
+    npz("neus_render_r48.npz", seed=1, n_rays=R, **{k: ret[k] for k in keep})
+
+    # networks on fixed points
+    x = synthetic.make_points(256, extent=1.0, seed=2)
+    v = torch.nn.functional.normalize(synthetic.make_points(256, extent=1.0, seed=3), dim=-1)
+    with torch.no_grad():
+        sdf, nab, feat = m.implicit_surface.forward_with_nablas(x)
+        rad = m.radiance_net.forward(x, v, nab, feat)
+    npz("neus_nets_n256.npz", seed=1, sdf=sdf, nabla=nab, feat=feat, radiance=rad)
+
+
+def golden_sampling(ref):
+    rs = np.random.RandomState(5)
+    R, M, N = 32, 96, 16
+    bins = np.sort(rs.uniform(0.5, 4.0, size=(R, M)).astype(np.float32), axis=1)
+    w = (rs.uniform(size=(R, M - 1)) ** 4).astype(np.float32)
+    w[:, : M // 3] = 0.0  # long empty run: exercises the denom < eps branch
+    u = rs.uniform(size=(R, N)).astype(np.float32)
+    tb, tw = torch.from_numpy(bins), torch.from_numpy(w)
+    det = ref.rend_util.sample_pdf(tb, tw, N, det=True)
+    # replay the stochastic branch with known u by monkeypatching torch.rand
+    real_rand = torch.rand
+    try:
+        torch.rand = lambda *a, **k: torch.from_numpy(u)
+        sto = ref.rend_util.sample_pdf(tb, tw, N, det=False)
+        cdf_in = torch.cumsum(tw / tw.sum(-1, keepdim=True), -1) * 0.9  # tops out below 1
+        sto_cdf = ref.rend_util.sample_cdf(tb, cdf_in, N, det=False)
+    finally:
+        torch.rand = real_rand
+    det_cdf = ref.rend_util.sample_cdf(tb, cdf_in, N, det=True)
+    o, d = synthetic.make_rays(64, seed=4)
+    d = torch.nn.functional.normalize(d, dim=-1)
+    near, far = ref.rend_util.near_far_from_sphere(o, d, r=1.0)
+    npz("sampling.npz", bins=bins, weights=w, u=u, det=det, sto=sto, cdf_in=cdf_in, sto_cdf=sto_cdf,
+        det_cdf=det_cdf, near=near, far=far)
+
+
+if __name__ == "__main__":
+    ref = ref_loader.load()
+    golden_neus(ref)
+    golden_sampling(ref)

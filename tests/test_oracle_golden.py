@@ -1,0 +1,100 @@
+"""CPU: pin the oracle against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py), and -- when /root/reference is present -- against the live
+reference.  Tolerances: the oracle re-states the same fp32 torch ops, so it tracks the reference
+to a few ulp of accumulated rounding (different chunk shapes change BLAS blocking)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import NEUS_CFG, build_neus, cpu_state_dict, frac_close, load_golden, rel_err
+from oracle import nets, neus as oneus, ref_loader, sampling
+from neurecon_b200.utils import synthetic
+
+
+def test_linspace_bit_exact():
+    for n in (2, 3, 16, 17, 32, 33, 64, 66, 128, 256, 512, 514, 2048):
+        assert torch.equal(torch.linspace(0, 1, n), sampling.linspace01(n)), n
+
+
+def test_sampling_golden_bit_exact():
+    g = load_golden("sampling.npz")
+    bins, w, u = g["bins"], g["weights"], g["u"]
+    N = u.shape[-1]
+    assert torch.equal(sampling.sample_pdf(bins, w, N, det=True), g["det"])
+    assert torch.equal(sampling.sample_pdf(bins, w, N, u=u), g["sto"])
+    assert torch.equal(sampling.sample_cdf(bins, g["cdf_in"], N, u=u), g["sto_cdf"])
+    assert torch.equal(sampling.sample_cdf(bins, g["cdf_in"], N, det=True), g["det_cdf"])
+    o, d = synthetic.make_rays(64, seed=4)
+    d = torch.nn.functional.normalize(d, dim=-1)
+    near, far = sampling.near_far_from_sphere(o, d, 1.0)
+    assert torch.equal(near, g["near"]) and torch.equal(far, g["far"])
+
+
+def test_nets_golden():
+    g = load_golden("neus_nets_n256.npz")
+    sd = cpu_state_dict(build_neus(seed=1))
+    x = synthetic.make_points(256, extent=1.0, seed=2)
+    v = torch.nn.functional.normalize(synthetic.make_points(256, extent=1.0, seed=3), dim=-1)
+    L = nets.layers_from_state_dict(sd, "implicit_surface.surface_fc_layers", 9)
+    Lr = nets.layers_from_state_dict(sd, "radiance_net.layers", 5)
+    sdf, nab, feat = nets.sdf_forward_with_nablas(x, L)
+    rad = nets.radiance_forward(x, v, nab, feat, Lr, -1, 4)
+    assert rel_err(sdf, g["sdf"]) < 2e-6
+    assert rel_err(nab, g["nabla"]) < 2e-5
+    assert rel_err(feat, g["feat"]) < 2e-6
+    assert rel_err(rad, g["radiance"]) < 2e-6
+    # forward-mode (kernel formulation) == autograd (reference formulation)
+    s2, n2, f2 = nets.sdf_forward_with_nablas_analytic(x, L)
+    assert rel_err(n2, nab) < 2e-5 and rel_err(s2, sdf) < 1e-6 and rel_err(f2, feat) < 1e-6
+    # fp64 truth bounds the fp32 reference's own error
+    L64 = nets.layers_from_state_dict(sd, "implicit_surface.surface_fc_layers", 9, dtype=torch.float64)
+    s64, n64, _ = nets.sdf_forward_with_nablas(x.double(), L64)
+    assert rel_err(g["sdf"], s64) < 1e-5 and rel_err(g["nabla"], n64) < 1e-4
+
+
+def test_neus_render_golden():
+    g = load_golden("neus_render_r48.npz")
+    sd = cpu_state_dict(build_neus(seed=1))
+    o, d = synthetic.make_rays(48, shell_radius=2.5, jitter=0.1, seed=1)
+    rgb, depth, ret = oneus.volume_render(o, d, sd, NEUS_CFG, calc_normal=True)
+    for k, tol in [("rgb", 1e-5), ("depth_volume", 1e-5), ("mask_volume", 1e-5), ("normals_volume", 5e-5)]:
+        assert rel_err(ret[k], g[k]) < tol, (k, rel_err(ret[k], g[k]))
+    for k in ("implicit_surface", "radiance", "visibility_weights", "d_final", "alpha", "cdf"):
+        assert frac_close(ret[k], g[k], 1e-4) > 0.97, (k, frac_close(ret[k], g[k], 1e-4))
+
+
+def test_state_dict_is_reference_compatible():
+    """A reference-layout state_dict (from the golden generator's seed) loads into the
+    neurecon_b200 modules with identical keys and shapes."""
+    m = build_neus(seed=1)
+    keys = set(m.state_dict().keys())
+    for i in range(9):
+        for s in ("weight_g", "weight_v", "bias"):
+            assert "implicit_surface.surface_fc_layers.%d.%s" % (i, s) in keys
+    for i in range(5):
+        for s in ("weight_g", "weight_v", "bias"):
+            assert "radiance_net.layers.%d.%s" % (i, s) in keys
+    assert "ln_s" in keys and "implicit_surface.obj_bounding_size" in keys
+    sd = m.state_dict()
+    assert tuple(sd["implicit_surface.surface_fc_layers.0.weight_v"].shape) == (256, 39)
+    assert tuple(sd["implicit_surface.surface_fc_layers.3.weight_v"].shape) == (217, 256)
+    assert tuple(sd["implicit_surface.surface_fc_layers.8.weight_v"].shape) == (257, 256)
+    assert tuple(sd["radiance_net.layers.0.weight_v"].shape) == (256, 289)
+    assert tuple(sd["radiance_net.layers.4.weight_g"].shape) == (3, 1)
+    assert sum(p.numel() for p in m.parameters()) == 802491
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference not present (GPU box)")
+def test_live_reference_matches_oracle_and_loads_our_state_dict():
+    ref = ref_loader.load()
+    ours = build_neus(seed=1)
+    torch.manual_seed(0)
+    theirs = ref.neus.NeuS(**synthetic.NEUS_MODEL_KWARGS)
+    theirs.load_state_dict(ours.state_dict())  # strict: identical keys and shapes
+    o, d = synthetic.make_rays(24, seed=9)
+    with torch.no_grad():
+        _, _, r = ref.neus.volume_render(o, d, theirs, calc_normal=True, detailed_output=True, perturb=False,
+                                         white_bkgd=True)
+    _, _, q = oneus.volume_render(o, d, cpu_state_dict(ours), NEUS_CFG, calc_normal=True, white_bkgd=True)
+    for k in ("rgb", "depth_volume", "mask_volume", "normals_volume"):
+        assert rel_err(q[k], r[k]) < 1e-5, k

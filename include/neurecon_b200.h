@@ -150,6 +150,14 @@ int nr_neus_composite(const float* sdf, const float* nablas, const float* radian
                       int32_t white_bkgd, float* rgb, float* depth, float* acc, float* normals,
                       float* cdf_out, float* alpha_out, float* weights_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * tcgen05 self-test: D[128,N] = A[128,K] B[K,N] through the operand layouts / descriptors of
+ * the fused MLP kernel.  a_image: bf16 K-major SWIZZLE_128B tiles (16 KB per 64 columns of K),
+ * B: fp32 [K,N] row-major, D: fp32 [128,N].  variant = 0 is the production encoding.
+ * ------------------------------------------------------------------------------------------ */
+int nr_selftest_umma(const void* a_image, const float* B, int32_t K, int32_t N, float* D,
+                     int32_t variant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

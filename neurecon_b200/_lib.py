@@ -50,6 +50,7 @@ _SIGNATURES = {
     "nr_sample_pdf": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "nr_neus_ray_setup": (C.c_int, [_P, _P, _I64, _F, _F, _F, _I32, _P, _P, _P, _P, _P, _P]),
     "nr_neus_upsample_step": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
     "nr_neus_composite": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 

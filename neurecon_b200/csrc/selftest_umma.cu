@@ -1,0 +1,98 @@
+// Single-CTA tcgen05 self-test: D[128, N] = A[128, K] * B[K, N] with exactly the operand layouts,
+// descriptors, TMEM addressing and barrier protocol the fused MLP kernel uses.  Exercised by
+// tests/test_gpu_umma.py against a bf16-rounded CPU matmul.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+selftest_umma_kernel(const uint8_t* __restrict__ a_image, const float* __restrict__ B, int K, int N,
+                     float* __restrict__ D, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int kchunks = (K + 63) / 64;
+  uint8_t* sA = smem;                       // kchunks x 16 KB
+  uint8_t* sB = smem + kchunks * 16384;     // K x N bf16, MN-major SW128
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t lbo_b = (uint32_t)((K + 7) / 8) * 1024;  // 64-column blocks are K/8 atoms apart
+
+  if (warp == 0) {
+    umma::tmem_alloc(&tmem_base_s, 128);
+    umma::tmem_relinquish();
+  }
+  if (tid == 0) {
+    umma::mbar_init(&bar_load, 1);
+    umma::mbar_init(&bar_mma, 1);
+    umma::fence_barrier_init();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (tid == 0) {
+    umma::mbar_arrive_expect_tx(&bar_load, (uint32_t)kchunks * 16384u);
+    for (int c = 0; c < kchunks; ++c) umma::bulk_g2s(sA + c * 16384, a_image + (size_t)c * 16384, 16384u, &bar_load);
+  }
+  // B: thread owns k-rows tid, tid+128, ... and writes 16-byte chunks of 8 columns
+  for (int k = tid; k < K; k += 128) {
+    for (int n8 = 0; n8 < N / 8; ++n8) {
+      const float* src = B + (size_t)k * N + n8 * 8;
+      uint4 v;
+      v.x = umma::pack_bf16(src[0], src[1]);
+      v.y = umma::pack_bf16(src[2], src[3]);
+      v.z = umma::pack_bf16(src[4], src[5]);
+      v.w = umma::pack_bf16(src[6], src[7]);
+      *reinterpret_cast<uint4*>(sB + umma::b_chunk_offset(k, n8, lbo_b)) = v;
+    }
+  }
+  umma::fence_proxy_async_smem();
+  __syncthreads();
+
+  if (tid == 0) {
+    umma::mbar_wait(&bar_load, 0);
+    umma::tc_fence_after();
+    const uint32_t idesc = umma::make_idesc_bf16(128, N, 0, 1);
+    const uint32_t a_lbo = (variant & 1) ? 0u : 16u;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t a_addr = umma::smem_u32(sA) + (ks >> 2) * 16384 + (ks & 3) * 32;
+      const uint32_t b_addr = umma::smem_u32(sB) + ks * 2048;
+      const uint64_t da = umma::make_smem_desc(a_addr, a_lbo, 1024);
+      const uint64_t db = (variant & 2) ? umma::make_smem_desc(b_addr, 1024, lbo_b)
+                                        : umma::make_smem_desc(b_addr, lbo_b, 1024);
+      umma::mma_bf16_ss(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma::mma_commit(&bar_mma);
+  }
+  __syncwarp();
+  umma::mbar_wait(&bar_mma, 0);
+  umma::tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    umma::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    umma::tmem_ld_wait();
+    const int row = warp * 32 + (tid & 31);
+    for (int j = 0; j < 32; ++j) D[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+extern "C" int nr_selftest_umma(const void* a_image, const float* B, int32_t K, int32_t N, float* D, int32_t variant,
+                                void* stream) {
+  NR_CHECK_ARG(a_image && B && D, "nr_selftest_umma: null pointer");
+  NR_CHECK_ARG(K >= 16 && K <= 256 && K % 16 == 0, "nr_selftest_umma: K must be a multiple of 16 in [16,256]");
+  NR_CHECK_ARG(N >= 32 && N <= 128 && N % 32 == 0, "nr_selftest_umma: N must be 32, 64, 96 or 128");
+  const int kchunks = (K + 63) / 64;
+  const size_t smem = 1024 + (size_t)kchunks * 16384 + (size_t)((K + 7) / 8) * 1024 * ((N + 63) / 64);
+  NR_CHECK_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const uint8_t*)a_image, B, K, N, D, variant);
+  NR_CHECK_LAUNCH("selftest_umma_kernel");
+  return NR_OK;
+}

@@ -1,0 +1,31 @@
+"""GPU: tcgen05 / TMEM / bulk-copy plumbing of the fused MLP kernel, checked on a plain GEMM."""
+import pytest
+import torch
+
+from neurecon_b200 import _lib, umma_pack
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run(K, N, variant=0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    img = umma_pack.pack_a_tiles(A.to(DEV))
+    D = torch.full((128, N), float("nan"), device=DEV)
+    Bd = B.to(DEV).contiguous()
+    lib = _lib.get_lib()
+    _lib.check(lib.nr_selftest_umma(_lib.ptr(img), _lib.ptr(Bd), K, N, _lib.ptr(D), variant, _lib.stream_ptr()), "selftest")
+    torch.cuda.synchronize()
+    want = A.to(torch.bfloat16).double() @ B.to(torch.bfloat16).double()
+    err = ((D.double().cpu() - want).abs().max() / want.abs().max()).item()
+    return err
+
+
+@pytest.mark.parametrize("K,N", [(16, 32), (64, 128), (48, 128), (256, 128), (256, 32), (128, 64)])
+def test_umma_gemm_matches_bf16_matmul(K, N):
+    err = _run(K, N)
+    if not err < 1e-5:
+        alts = {v: _run(K, N, v) for v in (1, 2, 3)}
+        pytest.fail("production encoding err=%g; variants: %s" % (err, alts))

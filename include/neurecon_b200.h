@@ -151,6 +151,50 @@ int nr_neus_composite(const float* sdf, const float* nablas, const float* radian
                       float* cdf_out, float* alpha_out, float* weights_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * bf16 tier: fused PE + SDF MLP (+ forward-mode normals) + radiance MLP on tcgen05 / TMEM.
+ * The host packs the weights once into a pre-swizzled bf16 image (16 KB chunks = A tiles of
+ * 128 features x 64 k) and describes the network as a short program of steps; the kernel
+ * keeps all hidden activations on-chip.  Replaces, per launch, batchify_query over
+ * ImplicitSurface.forward / forward_with_nablas / NeuS.forward_radiance / VolSDF.forward
+ * (utils/train_util.py:23-71, models/base.py:243-282,372-391, neus.py:103-106).
+ * ------------------------------------------------------------------------------------------ */
+#define NR_UMMA_MAX_STEPS 24
+#define NR_UMMA_EPI_HIDDEN 0  /* softplus(beta=100) hidden layer, tangents scaled by its derivative */
+#define NR_UMMA_EPI_SDF_OUT 1 /* sdf row (replicated over 32 rows): sdf / nabla to global */
+#define NR_UMMA_EPI_FEAT 2    /* geometry feature rows: to global and/or the radiance operand */
+#define NR_UMMA_EPI_RELU 3    /* radiance hidden layer */
+#define NR_UMMA_EPI_RGB 4     /* sigmoid, 3 rows, to global */
+
+typedef struct {
+  int32_t chunk_begin; /* first 16 KB weight chunk of this step; chunks ordered (M-tile, k-chunk) */
+  int32_t n_mt;        /* M-tiles of 128 output features (1 or 2) */
+  int32_t k_steps;     /* K / 16 */
+  int32_t n_cols;      /* MMA N: operand columns consumed (32, 64 or 128) */
+  int32_t epi;         /* NR_UMMA_EPI_* */
+  int32_t bias_off;    /* offset of n_mt*128 fp32 biases in the bias table */
+  int32_t out_rows;    /* valid output features */
+  int32_t pe_fill;     /* 1: rows [out_rows, out_rows+pe_dim) of the next operand are the embedding (skip) */
+  int32_t to_rad;      /* EPI_FEAT: also build the radiance operand [feat | PE(x) | PE(view) | normals] */
+} nr_umma_step_t;
+
+typedef struct {
+  int32_t n_steps;
+  int32_t tangents;          /* 1: tiles of 32 points x (value + 3 tangents); 0: 128 points, values only */
+  int32_t multires;          /* embedding of x for the SDF net */
+  int32_t rad_multires;      /* embedding of x for the radiance net (<0: identity) */
+  int32_t rad_multires_view; /* embedding of the view direction */
+  int32_t rad_extra_rows;    /* zero-padded rows after the 256 feature rows of the radiance operand */
+  nr_umma_step_t steps[NR_UMMA_MAX_STEPS];
+} nr_umma_program_t;
+
+/* x [n,3]; view [n,3] or NULL; outputs (each may be NULL): sdf [n], nabla [n,3], feat [n,feat_ld],
+ * rgb [n,3].  image: the packed bf16 weight chunks, bias: fp32 bias table. */
+int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
+                        const float* bias, size_t bias_floats, const float* x, const float* view,
+                        int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * tcgen05 self-test: D[128,N] = A[128,K] B[K,N] through the operand layouts / descriptors of
  * the fused MLP kernel.  a_image: bf16 K-major SWIZZLE_128B tiles (16 KB per 64 columns of K),
  * B: fp32 [K,N] row-major, D: fp32 [128,N].  variant = 0 is the production encoding.

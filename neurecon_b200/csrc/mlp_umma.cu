@@ -1,0 +1,457 @@
+// Fused positional-encoding + SDF MLP (+ analytic normals) + radiance MLP on tcgen05 / TMEM.
+//
+// Orientation: D[feature, column] = W[feature, k] * H[k, column].
+//   * A operand = weights, streamed per layer from a pre-swizzled bf16 image in global memory
+//     (L2 resident, ~1.6 MB) by 16 KB bulk async copies (TMA unit) into a 5-stage smem ring.
+//   * B operand = activations, RESIDENT in shared memory for the whole network: every layer's
+//     epilogue writes the next layer's operand in place (MN-major, 128-byte swizzle), so hidden
+//     activations never touch HBM.  PE is evaluated on-chip from the 12-byte point.
+//   * Accumulators live in TMEM: 2 point-tiles x 2 M-tiles x 128 columns = all 512 columns.
+//   * A column is one (point, component): with normals a tile holds 32 points x {value, d/dx,
+//     d/dy, d/dz} (forward-mode tangents ride through the same weights); without, 128 points.
+//     TMEM lane = feature, so one thread owns a feature for all columns: the tangent epilogue
+//     t' = softplus'(z) * (W t) is register-local, no shuffles.
+//   * Warp roles (384 threads): warp 0 bulk-copy producer, warp 1 MMA issuer (one thread),
+//     warp 2 TMEM allocator, warps 4-7 / 8-11 epilogue warpgroups for tile A / tile B.  The two
+//     tiles ping-pong: while the tensor core runs layer l of tile B, warpgroup A applies layer
+//     l's activation to tile A and publishes its next operand.
+//
+// Reference semantics: models/base.py:46-64 (Embedder), :243-282 (ImplicitSurface.forward /
+// forward_with_nablas), :372-391 (RadianceNet.forward).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int kStages = 5;
+constexpr uint32_t kChunkBytes = 16384;      // one A tile: 128 features x 64 k, bf16
+constexpr uint32_t kActBytes = 65536;        // one tile's B operand: 256 k-rows x 128 columns, bf16
+constexpr uint32_t kLbo = 32768;             // bytes between 64-column blocks of the B operand
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+
+enum : int32_t {
+  EPI_HIDDEN = 0,   // softplus(beta=100) hidden layer (+ tangents), next operand in smem
+  EPI_SDF_OUT = 1,  // row-replicated sdf row: sdf / nabla to global (+ normal stash)
+  EPI_FEAT = 2,     // geometry feature: to global and/or radiance operand rows [0,256) + extras
+  EPI_RELU = 3,     // radiance hidden layer
+  EPI_RGB = 4,      // sigmoid, rows 0..2 to global
+};
+
+struct DevProgram {
+  nr_umma_program_t p;
+};
+
+struct SmemLayout {
+  // offsets from the 1024-aligned base
+  static constexpr uint32_t act = 0;                                 // 2 x 64 KB
+  static constexpr uint32_t ring = 2 * kActBytes;                    // kStages x 16 KB
+  static constexpr uint32_t xs = ring + kStages * kChunkBytes;       // 2 x 128 x 3 floats
+  static constexpr uint32_t vs = xs + 2 * 384 * 4;                   // 2 x 32 x 3 floats (view dirs)
+  static constexpr uint32_t nabs = vs + 2 * 96 * 4;                  // 2 x 32 x 3 floats (normal stash)
+  static constexpr uint32_t bars = nabs + 2 * 96 * 4;                // mbarriers
+  static constexpr uint32_t total = bars + 256;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// softplus(beta=100, threshold=20) and its derivative sigmoid(100 z)
+__device__ __forceinline__ void softplus100_fast(float z, float& sp, float& sg) {
+  const float tl = z * 144.26950408889634f;      // 100 z log2(e)
+  const float e = ex2_approx(tl);
+  const float d = 1.0f + e;
+  const float l = lg2_approx(d) * 0.0069314718055994531f;  // ln2 / 100
+  sp = tl > 28.853900817779268f ? z : l;         // 100 z > 20
+  sg = 1.0f - rcp_approx(d);
+}
+__device__ __forceinline__ float softplus100_fast(float z) {
+  const float tl = z * 144.26950408889634f;
+  const float l = lg2_approx(1.0f + ex2_approx(tl)) * 0.0069314718055994531f;
+  return tl > 28.853900817779268f ? z : l;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+
+// Row j of Embedder.forward(x) (models/base.py:53-61): [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...]
+// value (comp_t < 0) or derivative w.r.t. x[comp_t].
+__device__ __forceinline__ float pe_row(int j, int multires, const float* x3, int comp_t) {
+  if (multires < 0 || j < 3) {
+    if (j >= 3) return 0.0f;
+    return comp_t < 0 ? x3[j] : (comp_t == j ? 1.0f : 0.0f);
+  }
+  const int q = (j - 3) / 6, r = (j - 3) % 6, comp = r % 3;
+  if (q >= multires) return 0.0f;
+  const float f = (float)(1 << q);
+  float s, c;
+  __sincosf(x3[comp] * f, &s, &c);
+  if (comp_t < 0) return r < 3 ? s : c;
+  if (comp_t != comp) return 0.0f;
+  return r < 3 ? f * c : -f * s;
+}
+
+__device__ __forceinline__ void store_row32(uint8_t* act, int k, int col0, const float (&v)[32]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    uint4 w;
+    w.x = umma::pack_bf16(v[8 * j4 + 0], v[8 * j4 + 1]);
+    w.y = umma::pack_bf16(v[8 * j4 + 2], v[8 * j4 + 3]);
+    w.z = umma::pack_bf16(v[8 * j4 + 4], v[8 * j4 + 5]);
+    w.w = umma::pack_bf16(v[8 * j4 + 6], v[8 * j4 + 7]);
+    *reinterpret_cast<uint4*>(act + umma::b_chunk_offset(k, (col0 >> 3) + j4, kLbo)) = w;
+  }
+}
+__device__ __forceinline__ void store_elem(uint8_t* act, int k, int n, float v) {
+  *reinterpret_cast<__nv_bfloat16*>(act + umma::b_chunk_offset(k, n >> 3, kLbo) + (n & 7) * 2) = __float2bfloat16_rn(v);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct KArgs {
+  const uint8_t* image;
+  const float* bias;
+  const float* x;      // [n,3]
+  const float* view;   // [n,3] or null
+  int64_t n;
+  float* sdf;          // [n] or null
+  float* nabla;        // [n,3] or null
+  float* feat;         // [n, feat_ld] or null
+  int64_t feat_ld;
+  float* rgb;          // [n,3] or null
+};
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_constant__ DevProgram prog, const KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + SmemLayout::bars);
+  uint64_t* w_full = bars;                   // [kStages]
+  uint64_t* w_empty = bars + kStages;        // [kStages]
+  uint64_t* in_ready = bars + 2 * kStages;   // [2]
+  uint64_t* acc_ready = in_ready + 2;        // [2]
+  __shared__ uint32_t tmem_base_s;
+
+  const nr_umma_program_t& P = prog.p;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tang = P.tangents;
+  const int ppt = tang ? 32 : 128;                       // points per tile
+  const int64_t n_tiles = (a.n + ppt - 1) / ppt;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
+    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], 128); umma::mbar_init(&acc_ready[t], 1); }
+    umma::fence_barrier_init();
+  }
+  if (warp == 2) {
+    umma::tmem_alloc(&tmem_base_s, 512);
+    umma::tmem_relinquish();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== weight producer (one lane) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
+        for (int s = 0; s < P.n_steps; ++s) {
+          const int nch = P.steps[s].n_mt * ((P.steps[s].k_steps + 3) >> 2);
+          for (int t = 0; t < ntl; ++t) {
+            for (int c = 0; c < nch; ++c) {
+              umma::mbar_wait(&w_empty[stage], phase ^ 1);
+              umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
+              umma::bulk_g2s(smem + SmemLayout::ring + stage * kChunkBytes,
+                             a.image + (size_t)(P.steps[s].chunk_begin + c) * kChunkBytes, kChunkBytes,
+                             &w_full[stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t in_par[2] = {0, 0};
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
+        for (int s = 0; s < P.n_steps; ++s) {
+          const int n_mt = P.steps[s].n_mt, k_steps = P.steps[s].k_steps;
+          const int nkc = (k_steps + 3) >> 2;
+          const uint32_t idesc = umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
+          for (int t = 0; t < ntl; ++t) {
+            umma::mbar_wait(&in_ready[t], in_par[t]);
+            in_par[t] ^= 1;
+            umma::tc_fence_after();
+            const uint32_t act_addr = umma::smem_u32(smem + SmemLayout::act + t * kActBytes);
+            for (int mt = 0; mt < n_mt; ++mt) {
+              const uint32_t d_addr = tmem_base + (uint32_t)(t * 256 + mt * 128);
+              for (int kc = 0; kc < nkc; ++kc) {
+                umma::mbar_wait(&w_full[stage], phase);
+                umma::tc_fence_after();
+                const uint32_t w_addr = umma::smem_u32(smem + SmemLayout::ring + stage * kChunkBytes);
+                const int kn = min(4, k_steps - 4 * kc);
+                for (int k4 = 0; k4 < kn; ++k4) {
+                  const int ks = 4 * kc + k4;
+                  const uint64_t da = umma::make_smem_desc(w_addr + k4 * 32, 16, 1024);
+                  const uint64_t db = umma::make_smem_desc(act_addr + ks * 2048, kLbo, 1024);
+                  umma::mma_bf16_ss(d_addr, da, db, idesc, ks > 0 ? 1u : 0u);
+                }
+                umma::mma_commit(&w_empty[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+              }
+            }
+            umma::mma_commit(&acc_ready[t]);
+          }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue warpgroups =====================
+    const int t = (warp - kEpiWarp0) >> 2;          // tile slot 0 / 1
+    const int q = warp & 3;                         // TMEM lane quarter
+    const int etid = (warp - kEpiWarp0 - 4 * t) * 32 + lane;  // 0..127 inside the warpgroup
+    uint8_t* act = smem + SmemLayout::act + t * kActBytes;
+    float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
+    float* vs = (float*)(smem + SmemLayout::vs) + t * 96;
+    float* nabs = (float*)(smem + SmemLayout::nabs) + t * 96;
+    const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
+    uint32_t acc_par = 0;
+    const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
+
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + t;
+      if (tile >= n_tiles) continue;
+      const int64_t p0 = tile * ppt;
+
+      // ---- prologue: stage the points, evaluate the embedding into operand rows [0, k0) ----
+      for (int i = etid; i < ppt * 3; i += 128) {
+        const int64_t gi = p0 * 3 + i;
+        xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
+        if (a.view && i < 96) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
+      }
+      named_bar_sync(1 + t, 128);
+      {
+        const int n = etid;                            // operand column
+        const int p = tang ? (n & 31) : n;
+        const int ct = tang ? (n >> 5) - 1 : -1;       // -1: value column, 0..2: tangent component
+        const float x3[3] = {xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]};
+        const int k0 = P.steps[0].k_steps * 16;
+        for (int j = 0; j < k0; ++j) store_elem(act, j, n, j < pe_dim ? pe_row(j, P.multires, x3, ct) : 0.0f);
+      }
+      umma::fence_proxy_async_smem();
+      umma::tc_fence_before();
+      umma::mbar_arrive(&in_ready[t]);
+
+      for (int s = 0; s < P.n_steps; ++s) {
+        const nr_umma_step_t& S = P.steps[s];
+        umma::mbar_wait(&acc_ready[t], acc_par);
+        acc_par ^= 1;
+        umma::tc_fence_after();
+
+        if (S.epi == EPI_HIDDEN) {
+          for (int mt = 0; mt < S.n_mt; ++mt) {
+            const int F = mt * 128 + 32 * q + lane;
+            const float b = a.bias[S.bias_off + F];
+            const uint32_t taddr = tmem_tile + (uint32_t)(mt * 128);
+            const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
+            uint32_t raw[32];
+            float v[32];
+            if (tang) {
+              float sg[32];
+              umma::tmem_ld32(taddr, raw);
+              umma::tmem_ld_wait();
+              if (!is_pe) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) softplus100_fast(__uint_as_float(raw[j]) + b, v[j], sg[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * j, -1);
+              }
+              store_row32(act, F, 0, v);
+#pragma unroll 1
+              for (int c = 1; c < 4; ++c) {
+                umma::tmem_ld32(taddr + 32 * c, raw);
+                umma::tmem_ld_wait();
+                if (!is_pe) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * sg[j];
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * j, c - 1);
+                }
+                store_row32(act, F, 32 * c, v);
+              }
+            } else {
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                umma::tmem_ld32(taddr + 32 * c, raw);
+                umma::tmem_ld_wait();
+                if (!is_pe) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (32 * c + j), -1);
+                }
+                store_row32(act, F, 32 * c, v);
+              }
+            }
+          }
+        } else if (S.epi == EPI_SDF_OUT) {
+          // rows 0..31 of this M-tile all hold the sdf row: lane l keeps column l of each chunk
+          if (q == 0) {
+            const float b = a.bias[S.bias_off];
+            for (int c = 0; c < 4; ++c) {
+              uint32_t raw[32];
+              umma::tmem_ld32(tmem_tile + 32 * c, raw);
+              umma::tmem_ld_wait();
+              float mine = 0.0f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mine = (lane == j) ? __uint_as_float(raw[j]) : mine;
+              if (tang) {
+                const int64_t gp = p0 + lane;
+                if (c == 0) {
+                  if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
+                } else {
+                  nabs[3 * lane + (c - 1)] = mine;
+                  if (a.nabla && gp < a.n) a.nabla[gp * 3 + (c - 1)] = mine;
+                }
+              } else {
+                const int64_t gp = p0 + 32 * c + lane;
+                if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
+              }
+            }
+          }
+        } else if (S.epi == EPI_FEAT) {
+          const int nchunk = S.n_cols >> 5;
+          for (int mt = 0; mt < S.n_mt; ++mt) {
+            const int F = mt * 128 + 32 * q + lane;
+            const float b = a.bias[S.bias_off + F];
+            for (int c = 0; c < nchunk; ++c) {
+              uint32_t raw[32];
+              float v[32];
+              umma::tmem_ld32(tmem_tile + (uint32_t)(mt * 128 + 32 * c), raw);
+              umma::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + b;
+              if (a.feat && F < S.out_rows) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int64_t gp = p0 + 32 * c + j;
+                  if (gp < a.n) a.feat[gp * a.feat_ld + F] = v[j];
+                }
+              }
+              if (S.to_rad) store_row32(act, F, 32 * c, v);
+            }
+          }
+          if (S.to_rad) {
+            // operand rows [256, 256 + extras): [PE(x) | PE(view) | normals | 0-pad]  (tangent tiles)
+            named_bar_sync(1 + t, 128);  // normal stash of EPI_SDF_OUT visible
+            const int p = etid & 31, g = etid >> 5;
+            const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
+            const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
+            const int extra = P.rad_extra_rows;
+            for (int r = g; r < extra; r += 4) {
+              float val = 0.0f;
+              if (r < px) val = pe_row(r, P.rad_multires, xs + 3 * p, -1);
+              else if (r < px + pv) val = pe_row(r - px, P.rad_multires_view, vs + 3 * p, -1);
+              else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
+              store_elem(act, 256 + r, p, val);
+            }
+          }
+        } else if (S.epi == EPI_RELU) {
+          for (int mt = 0; mt < S.n_mt; ++mt) {
+            const int F = mt * 128 + 32 * q + lane;
+            const float b = a.bias[S.bias_off + F];
+            uint32_t raw[32];
+            float v[32];
+            umma::tmem_ld32(tmem_tile + (uint32_t)(mt * 128), raw);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
+            store_row32(act, F, 0, v);
+          }
+        } else if (S.epi == EPI_RGB) {
+          if (q == 0) {
+            uint32_t raw[32];
+            umma::tmem_ld32(tmem_tile, raw);
+            umma::tmem_ld_wait();
+            if (lane < 3 && a.rgb) {
+              const float b = a.bias[S.bias_off + lane];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int64_t gp = p0 + j;
+                if (gp < a.n) a.rgb[gp * 3 + lane] = sigmoid_fast(__uint_as_float(raw[j]) + b);
+              }
+            }
+          }
+        }
+        if (s + 1 < P.n_steps) {
+          umma::fence_proxy_async_smem();
+          umma::tc_fence_before();
+          umma::mbar_arrive(&in_ready[t]);
+        }
+      }
+      umma::tc_fence_before();
+      named_bar_sync(1 + t, 128);  // all TMEM reads of this tile retired before its slot is reused
+    }
+  }
+
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) umma::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
+                                   const float* bias, size_t bias_floats, const float* x, const float* view,
+                                   int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
+                                   void* stream) {
+  NR_CHECK_ARG(prog && image && bias && x, "nr_mlp_umma_forward: null pointer");
+  NR_CHECK_ARG(n >= 0, "nr_mlp_umma_forward: n < 0");
+  NR_CHECK_ARG(prog->n_steps >= 1 && prog->n_steps <= NR_UMMA_MAX_STEPS, "nr_mlp_umma_forward: n_steps=%d", prog->n_steps);
+  NR_CHECK_ARG(((uintptr_t)image & 15) == 0, "nr_mlp_umma_forward: image must be 16-byte aligned");
+  bool has_rad = false;
+  for (int s = 0; s < prog->n_steps; ++s) {
+    const nr_umma_step_t& S = prog->steps[s];
+    const int nch = S.n_mt * ((S.k_steps + 3) / 4);
+    NR_CHECK_ARG(S.n_mt >= 1 && S.n_mt <= 2, "step %d: n_mt=%d", s, S.n_mt);
+    NR_CHECK_ARG(S.k_steps >= 1 && S.k_steps <= 32, "step %d: k_steps=%d", s, S.k_steps);
+    NR_CHECK_ARG(S.n_cols == 32 || S.n_cols == 64 || S.n_cols == 128, "step %d: n_cols=%d", s, S.n_cols);
+    NR_CHECK_ARG(S.k_steps <= 16 || S.n_cols <= 64, "step %d: K > 256 needs n_cols <= 64", s);
+    NR_CHECK_ARG(S.chunk_begin >= 0 && (size_t)(S.chunk_begin + nch) * kChunkBytes <= image_bytes,
+                 "step %d: weight chunks [%d,%d) exceed the image", s, S.chunk_begin, S.chunk_begin + nch);
+    NR_CHECK_ARG(S.bias_off >= 0 && (size_t)S.bias_off + S.n_mt * 128 <= bias_floats, "step %d: bias range", s);
+    NR_CHECK_ARG(S.epi >= EPI_HIDDEN && S.epi <= EPI_RGB, "step %d: epi=%d", s, S.epi);
+    if (S.epi == EPI_RELU || S.epi == EPI_RGB || (S.epi == EPI_FEAT && S.to_rad)) has_rad = true;
+  }
+  NR_CHECK_ARG(prog->steps[0].k_steps * 16 >= (prog->multires < 0 ? 3 : 3 + 6 * prog->multires),
+               "nr_mlp_umma_forward: step 0 K does not cover the embedding");
+  if (has_rad) NR_CHECK_ARG(prog->tangents && view, "nr_mlp_umma_forward: the radiance steps need tangent tiles and view dirs");
+  if (n == 0) return NR_OK;
+  int dev = 0, sms = 0;
+  NR_CHECK_CUDA(cudaGetDevice(&dev));
+  NR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int ppt = prog->tangents ? 32 : 128;
+  const int64_t n_pairs = (nr_cdiv(n, ppt) + 1) / 2;
+  const int grid = (int)(n_pairs < sms ? n_pairs : sms);
+  const size_t smem = SmemLayout::total + 1024;
+  static unsigned long long attr_set = 0;  // per-device bit: the attribute is per (function, device)
+  if (!(attr_set >> (dev & 63) & 1ull)) {
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set |= 1ull << (dev & 63);
+  }
+  DevProgram dp;
+  dp.p = *prog;
+  KArgs ka{(const uint8_t*)image, bias, x, view, n, sdf, nabla, feat, feat_ld, rgb};
+  mlp_umma_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+  NR_CHECK_LAUNCH("mlp_umma_kernel");
+  return NR_OK;
+}

@@ -374,9 +374,9 @@ extern "C" int nr_near_far_from_sphere(const float* rays_o, const float* rays_d,
 extern "C" int nr_sample_pdf(const float* bins, const float* weights, const float* u, int64_t R, int32_t M, int32_t N,
                              int32_t cdf_is_given, float eps, float* samples, int32_t* below, int32_t* above,
                              float* cdf_out, void* stream) {
-  NR_CHECK_ARG(bins && weights && samples, "nr_sample_pdf: null pointer");
   NR_CHECK_ARG(R >= 0 && M >= 2 && N >= 1, "nr_sample_pdf: need R>=0, M>=2, N>=1 (got R=%lld M=%d N=%d)", (long long)R, M, N);
-  if (R == 0) return NR_OK;
+  if (R == 0) return NR_OK;  // empty batches carry null data pointers
+  NR_CHECK_ARG(bins && weights && samples, "nr_sample_pdf: null pointer");
   const size_t smem = (size_t)kWarpsPerBlock * 2 * M * sizeof(float);
   NR_CHECK_ARG(smem <= 200 * 1024, "nr_sample_pdf: M=%d too large for shared memory staging", M);
   if (smem > 48 * 1024)

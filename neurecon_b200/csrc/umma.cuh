@@ -42,7 +42,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin)
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
     if (mbar_try_wait(bar, parity)) return;
   printf("neurecon_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
   __trap();

@@ -210,12 +210,67 @@ class ImplicitSurface(nn.Module):
             c.update(key=key, desc=d, keep=(Ws, bs))
         return c["desc"]
 
+    def _umma_net(self, radiance_net=None):
+        """bf16 image / bias table / step templates for the tcgen05 tier (cached like _descriptor)."""
+        self._check_supported()
+        from .. import umma_pack
+        key = (_param_key(self), None if radiance_net is None else _param_key(radiance_net))
+        slot = "umma_fused" if radiance_net is not None else "umma"
+        c = self._cache.get(slot)
+        if c is None or c[0] != key:
+            with torch.no_grad():
+                Wl = [_effective_weight(l).detach().float() for l in self.surface_fc_layers]
+                bl = [l.bias.detach().float() for l in self.surface_fc_layers]
+                for i in self.skips:
+                    Wl[i] = Wl[i] / math.sqrt(2)
+                kw = {}
+                if radiance_net is not None:
+                    if radiance_net.skips or not radiance_net.use_view_dirs:
+                        raise NotImplementedError("bf16 tier: RadianceNet needs skips=[] and use_view_dirs=True")
+                    kw = dict(rad_W=[_effective_weight(l).detach().float() for l in radiance_net.layers],
+                              rad_b=[l.bias.detach().float() for l in radiance_net.layers],
+                              rad_multires=radiance_net.embed_multires,
+                              rad_multires_view=radiance_net.embed_multires_view)
+                net = umma_pack.UmmaNet(Wl, bl, self.embed_multires, self.skips[0] if self.skips else -1, **kw)
+            c = (key, net)
+            self._cache[slot] = c
+        return c[1]
+
+    def _run_umma(self, x, mode, want_feat=False, radiance_net=None, view_dirs=None, want_sdf=True,
+                  want_nablas=True):
+        """One launch of the fused tcgen05 kernel.  mode: 'sdf' | 'nablas' | 'fused'."""
+        _lib.require_cuda(x, view_dirs)
+        lib = _lib.get_lib()
+        shape = x.shape[:-1]
+        xf = _lib.f32c(x.detach().reshape(-1, 3))
+        n, dev = xf.shape[0], xf.device
+        net = self._umma_net(radiance_net if mode == "fused" else None)
+        prog = net.program(mode, want_feat=want_feat)
+        f = dict(dtype=torch.float32, device=dev)
+        sdf = torch.empty(n, **f) if want_sdf else None
+        nabla = torch.empty(n, 3, **f) if (mode != "sdf" and want_nablas) else None
+        feat = torch.empty(n, net.feat_dim, **f) if (want_feat and mode != "fused") else None
+        rgb = torch.empty(n, 3, **f) if mode == "fused" else None
+        vf = None
+        if mode == "fused":
+            vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
+        with torch.cuda.device(dev):
+            _lib.check(lib.nr_mlp_umma_forward(
+                C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias), net.bias.numel(),
+                _lib.ptr(xf), _lib.ptr(vf), n, _lib.ptr(sdf), _lib.ptr(nabla), _lib.ptr(feat),
+                net.feat_dim, _lib.ptr(rgb), _lib.stream_ptr(dev)), "mlp_umma_forward")
+        rs = lambda t, *tail: None if t is None else t.reshape(*shape, *tail)
+        return rs(sdf), rs(nabla, 3), rs(feat, net.feat_dim), rs(rgb, 3)
+
     # ---- forward -----------------------------------------------------------------------------
     def _needs_grad(self, x, has_grad):
         return has_grad and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
 
     def _run(self, x, want_nablas, want_feat):
         _lib.require_cuda(x)
+        if _lib.get_precision() == "bf16":
+            sdf, nabla, feat, _ = self._run_umma(x, "nablas" if want_nablas else "sdf", want_feat=want_feat)
+            return sdf, nabla, feat
         lib = _lib.get_lib()
         shape = x.shape[:-1]
         xf = _lib.f32c(x.detach().reshape(-1, 3))
@@ -350,3 +405,17 @@ class RadianceNet(nn.Module):
                     _lib.ptr(ff[i0:i0 + m]), self.W_geo_feat, m, _lib.ptr(rgb[i0:i0 + m]), _lib.ptr(ws),
                     ws.numel(), st), "radiance_forward")
         return rgb.reshape(*shape, 3)
+
+
+def query_radiance(surface, radiance_net, x, view_dirs, normalize_normals=False):
+    """Inference composition of ``forward_with_nablas`` + ``RadianceNet.forward`` at the same
+    points (NeuS.forward_radiance neus.py:103-106, VolSDF.forward volsdf.py:327-331): returns
+    (radiance, sdf, nablas).  bf16 tier: ONE fused kernel, the 256-wide feature and the normal
+    never leave the SM; fp32 tier: the two library calls."""
+    if _lib.get_precision() == "bf16" and not normalize_normals:
+        sdf, nabla, _, rgb = surface._run_umma(x, "fused", radiance_net=radiance_net, view_dirs=view_dirs)
+        return rgb, sdf, nabla
+    sdf, nabla, feat = surface._run(x, want_nablas=True, want_feat=True)
+    normals = torch.nn.functional.normalize(nabla) if normalize_normals else nabla
+    rgb = radiance_net.forward(x, view_dirs, normals, feat)
+    return rgb, sdf, nabla

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from ... import _lib
-from ..base import ImplicitSurface, RadianceNet
+from ..base import ImplicitSurface, RadianceNet, query_radiance
 
 
 # --------------------------------------------------------------------------------------------
@@ -177,6 +177,13 @@ def volume_render(
     if not use_view_dirs:
         raise NotImplementedError("use_view_dirs=False is not supported")
     _lib.require_cuda(rays_o, rays_d)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
+        from .neus_train import volume_render_train
+        return volume_render_train(
+            rays_o, rays_d, model, obj_bounding_radius=obj_bounding_radius, batched=batched, calc_normal=calc_normal,
+            rayschunk=rayschunk, white_bkgd=white_bkgd, near_bypass=near_bypass, far_bypass=far_bypass,
+            detailed_output=detailed_output, perturb=perturb, N_samples=N_samples, N_importance=N_importance,
+            N_upsample_iters=N_upsample_iters)
     if batched:
         B = rays_d.shape[0]
         prefix = [B, -1]
@@ -202,9 +209,10 @@ def volume_render(
             dirs, d_all, pts, d_mid, pts_mid = _upsample(
                 model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
                 N_upsample_iters, perturb)
-            sdf, nablas, _ = model.implicit_surface.forward_with_nablas(pts)
-            views = dirs.unsqueeze(-2).expand(R, M - 1, 3)
-            radiances = model.forward_radiance(pts_mid, views)
+            with torch.no_grad():
+                sdf, nablas, _ = model.implicit_surface._run(pts, want_nablas=True, want_feat=False)
+                views = dirs.unsqueeze(-2).expand(R, M - 1, 3)
+                radiances, _, _ = query_radiance(model.implicit_surface, model.radiance_net, pts_mid, views)
             rgb, depth, acc, normals, cdf, alpha, w = _composite(
                 sdf, nablas, radiances, d_mid, s, white_bkgd, calc_normal, detailed_output)
             ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])

@@ -32,3 +32,122 @@ def pack_a_tiles(W, n_mtiles=None, k_pad=None):
     out = torch.empty_like(tiles)
     out[:, idx] = tiles
     return out.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# Programs for the fused tcgen05 MLP kernel (csrc/mlp_umma.cu, include/neurecon_b200.h)
+# --------------------------------------------------------------------------------------------
+EPI_HIDDEN, EPI_SDF_OUT, EPI_FEAT, EPI_RELU, EPI_RGB = 0, 1, 2, 3, 4
+
+
+def _pe_dim(multires):
+    return 3 if multires < 0 else 3 + 6 * multires
+
+
+class UmmaNet:
+    """bf16 weight image + bias table + step templates for one (surface[, radiance]) pair."""
+
+    def __init__(self, surface_W, surface_b, multires, skip_layer, rad_W=None, rad_b=None, rad_multires=-1,
+                 rad_multires_view=-1):
+        dev = surface_W[0].device
+        self.multires = multires
+        self.rad_multires, self.rad_multires_view = rad_multires, rad_multires_view
+        chunks, biases = [], []
+        self._n_chunks, self._n_bias = 0, 0
+
+        def add(W, b, k_steps, n_mt):
+            img = pack_a_tiles(W, n_mtiles=n_mt, k_pad=k_steps * 16)
+            assert img.shape[0] == n_mt * ((k_steps + 3) // 4)
+            bt = torch.zeros(n_mt * 128, dtype=torch.float32, device=dev)
+            if b is not None:
+                bt[: b.numel()] = b.float()
+            c0, b0 = self._n_chunks, self._n_bias
+            chunks.append(img)
+            biases.append(bt)
+            self._n_chunks += img.shape[0]
+            self._n_bias += bt.numel()
+            return c0, b0
+
+        L = len(surface_W)
+        pe = _pe_dim(multires)
+        if pe > 64:
+            raise NotImplementedError("bf16 tier: embedding wider than 64 is not supported")
+        self.hidden = []
+        for l in range(L - 1):
+            W, b = surface_W[l], surface_b[l]
+            out_d, in_d = W.shape
+            if in_d > 256 or out_d > 256:
+                raise NotImplementedError("bf16 tier supports hidden widths up to 256")
+            k_steps, n_mt = (in_d + 15) // 16, (out_d + 127) // 128
+            c0, b0 = add(W, b, k_steps, n_mt)
+            pe_fill = 1 if (l + 1 == skip_layer) else 0
+            if pe_fill and out_d + pe > 256:
+                raise NotImplementedError("bf16 tier: skip operand wider than 256")
+            self.hidden.append(dict(chunk_begin=c0, n_mt=n_mt, k_steps=k_steps, epi=EPI_HIDDEN, bias_off=b0,
+                                    out_rows=out_d, pe_fill=pe_fill, to_rad=0))
+        Wl, bl = surface_W[L - 1], surface_b[L - 1]
+        in_d = Wl.shape[1]
+        k_steps = (in_d + 15) // 16
+        c0, b0 = add(Wl[0:1].expand(32, in_d), bl[0:1].expand(32), k_steps, 1)
+        self.sdf_out = dict(chunk_begin=c0, n_mt=1, k_steps=k_steps, epi=EPI_SDF_OUT, bias_off=b0, out_rows=1,
+                            pe_fill=0, to_rad=0)
+        self.feat_dim = Wl.shape[0] - 1
+        if self.feat_dim > 0:
+            if self.feat_dim > 256:
+                raise NotImplementedError("bf16 tier: geometry feature wider than 256")
+            n_mt = (self.feat_dim + 127) // 128
+            c0, b0 = add(Wl[1:], bl[1:], k_steps, n_mt)
+            self.feat = dict(chunk_begin=c0, n_mt=n_mt, k_steps=k_steps, epi=EPI_FEAT, bias_off=b0,
+                             out_rows=self.feat_dim, pe_fill=0, to_rad=0)
+        self.rad = None
+        self.rad_extra_rows = 0
+        if rad_W is not None:
+            if self.feat_dim != 256:
+                raise NotImplementedError("bf16 tier: the fused radiance path needs W_geo_feat == 256")
+            px, pv = _pe_dim(rad_multires), _pe_dim(rad_multires_view)
+            n_extra = px + pv + 3
+            self.rad_extra_rows = (n_extra + 15) // 16 * 16
+            if 256 + self.rad_extra_rows > 512:
+                raise NotImplementedError("bf16 tier: radiance input too wide")
+            W0 = rad_W[0]
+            assert W0.shape[1] == n_extra + 256, "RadianceNet layer 0 width"
+            # reference order [PE(x) | PE(view) | normals | feat] (base.py:382) -> operand order [feat | ... ]
+            W0p = torch.cat([W0[:, n_extra:], W0[:, :n_extra]], dim=1)
+            steps = []
+            Ls = len(rad_W)
+            for l in range(Ls):
+                W = W0p if l == 0 else rad_W[l]
+                out_d, in_d = W.shape
+                if l > 0 and in_d > 256 or out_d > 256:
+                    raise NotImplementedError("bf16 tier supports radiance widths up to 256 (no skips)")
+                k_steps = (256 + self.rad_extra_rows) // 16 if l == 0 else (in_d + 15) // 16
+                n_mt = (out_d + 127) // 128
+                c0, b0 = add(W, rad_b[l], k_steps, n_mt)
+                steps.append(dict(chunk_begin=c0, n_mt=n_mt, k_steps=k_steps, epi=EPI_RGB if l == Ls - 1 else EPI_RELU,
+                                  bias_off=b0, out_rows=out_d, pe_fill=0, to_rad=0))
+            if steps[-1]["out_rows"] != 3:
+                raise NotImplementedError("bf16 tier: radiance output must be rgb")
+            self.rad = steps
+        self.image = torch.cat(chunks, 0).contiguous()
+        self.bias = torch.cat(biases, 0).contiguous()
+
+    def program(self, mode, want_feat=False):
+        """mode: 'sdf' (128-point tiles), 'nablas' (32-point tangent tiles), 'fused' (+ radiance)."""
+        from . import _lib
+        tang = 0 if mode == "sdf" else 1
+        steps = [dict(s, n_cols=128) for s in self.hidden]
+        steps.append(dict(self.sdf_out, n_cols=128))
+        if mode == "fused":
+            assert self.rad is not None
+            steps.append(dict(self.feat, n_cols=32, to_rad=1))
+            steps += [dict(s, n_cols=32) for s in self.rad]
+        elif want_feat:
+            steps.append(dict(self.feat, n_cols=32 if tang else 128))
+        P = _lib.UmmaProgram()
+        assert len(steps) <= _lib.NR_UMMA_MAX_STEPS
+        P.n_steps, P.tangents, P.multires = len(steps), tang, self.multires
+        P.rad_multires, P.rad_multires_view, P.rad_extra_rows = self.rad_multires, self.rad_multires_view, self.rad_extra_rows
+        for i, s in enumerate(steps):
+            for k, v in s.items():
+                setattr(P.steps[i], k, int(v))
+        return P

@@ -1,0 +1,87 @@
+"""GPU parity of the bf16 tcgen05 tier (fused PE + SDF MLP + normals + radiance MLP).
+Tolerance (north_star): <= 1e-2 relative for the bf16-MLP path."""
+import pytest
+import torch
+
+import neurecon_b200
+from conftest import NEUS_CFG, build_neus, cpu_state_dict, load_golden, rel_err
+from oracle import nets, neus as oneus
+from neurecon_b200.models.base import query_radiance
+from neurecon_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _bf16():
+    neurecon_b200.set_precision("bf16")
+    yield
+    neurecon_b200.set_precision("fp32")
+
+
+def _oracle(m, x, v):
+    sd = cpu_state_dict(m)
+    L = nets.layers_from_state_dict(sd, "implicit_surface.surface_fc_layers", 9)
+    Lr = nets.layers_from_state_dict(sd, "radiance_net.layers", 5)
+    sdf, nab, feat = nets.sdf_forward_with_nablas(x, L)
+    return sdf, nab, feat, nets.radiance_forward(x, v, nab, feat, Lr, -1, 4)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 128, 257, 5000])
+def test_sdf_only_plain_tiles(n):
+    m = build_neus(seed=1, device=DEV)
+    x = synthetic.make_points(n, extent=1.0, seed=2)
+    with torch.no_grad():
+        sdf = m.implicit_surface.forward(x.to(DEV))
+    torch.cuda.synchronize()
+    want = _oracle(m, x, x)[0]
+    assert sdf.shape == (n,)
+    assert rel_err(sdf, want) < 1e-2, rel_err(sdf, want)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 64, 65, 1000, 9999])
+def test_nablas_feat_and_fused_radiance(n):
+    m = build_neus(seed=1, device=DEV)
+    x = synthetic.make_points(n, extent=1.0, seed=2)
+    v = torch.nn.functional.normalize(synthetic.make_points(n, extent=1.0, seed=3), dim=-1)
+    with torch.no_grad():
+        sdf, nab, feat = m.implicit_surface.forward_with_nablas(x.to(DEV))
+        sdf2, feat2 = m.implicit_surface.forward(x.to(DEV), return_h=True)
+        rgb, sdf3, nab3 = query_radiance(m.implicit_surface, m.radiance_net, x.to(DEV), v.to(DEV))
+    torch.cuda.synchronize()
+    osdf, onab, ofeat, orad = _oracle(m, x, v)
+    errs = dict(sdf=rel_err(sdf, osdf), nab=rel_err(nab, onab), feat=rel_err(feat, ofeat), sdf2=rel_err(sdf2, osdf),
+                feat2=rel_err(feat2, ofeat), rgb=rel_err(rgb, orad), sdf3=rel_err(sdf3, osdf), nab3=rel_err(nab3, onab))
+    assert all(e < 1e-2 for e in errs.values()), errs
+
+
+def test_bf16_golden_nets():
+    m = build_neus(seed=1, device=DEV)
+    g = load_golden("neus_nets_n256.npz")
+    x = synthetic.make_points(256, extent=1.0, seed=2)
+    v = torch.nn.functional.normalize(synthetic.make_points(256, extent=1.0, seed=3), dim=-1)
+    with torch.no_grad():
+        rgb, sdf, nab = query_radiance(m.implicit_surface, m.radiance_net, x.to(DEV), v.to(DEV))
+    assert rel_err(sdf, g["sdf"]) < 1e-2 and rel_err(nab, g["nabla"]) < 1e-2 and rel_err(rgb, g["radiance"]) < 1e-2
+
+
+def test_neus_volume_render_bf16_vs_golden():
+    from neurecon_b200.models.frameworks import neus
+    m = build_neus(seed=1, device=DEV)
+    g = load_golden("neus_render_r48.npz")
+    o, d = synthetic.make_rays(48, shell_radius=2.5, jitter=0.1, seed=1)
+    with torch.no_grad():
+        rgb, depth, ret = neus.volume_render(o.to(DEV), d.to(DEV), m, calc_normal=True, detailed_output=True)
+    errs = {k: rel_err(ret[k], g[k]) for k in ("rgb", "depth_volume", "mask_volume", "normals_volume")}
+    assert all(e < 1e-2 for e in errs.values()), errs
+
+
+def test_bf16_large_batch_matches_small_batches():
+    """Persistent scheduling / tile ping-pong: a big launch equals per-slice launches bit for bit."""
+    m = build_neus(seed=1, device=DEV)
+    x = synthetic.make_points(40000, extent=1.0, seed=5).to(DEV)
+    with torch.no_grad():
+        a = m.implicit_surface.forward_with_nablas(x)
+        b = m.implicit_surface.forward_with_nablas(x[:64 * 300])
+    assert torch.equal(a[0][:64 * 300], b[0]) and torch.equal(a[1][:64 * 300], b[1])

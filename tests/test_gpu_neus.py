@@ -123,7 +123,9 @@ def test_mlp_accepts_prefix_shapes_and_empty():
         sdf, nab, feat = m.implicit_surface.forward_with_nablas(x)
         assert sdf.shape == (2, 5, 7) and nab.shape == (2, 5, 7, 3) and feat.shape == (2, 5, 7, 256)
         flat = m.implicit_surface.forward(x.reshape(-1, 3))
-        assert torch.equal(flat.reshape(2, 5, 7), sdf)  # rows are independent of batch position
+        assert rel_err(flat.reshape(2, 5, 7), sdf) < 1e-6  # rows are independent of batch position
+        again = m.implicit_surface.forward(x)
+        assert torch.equal(again.reshape(-1), flat)       # and bit-reproducible
         e = m.implicit_surface.forward(torch.zeros(0, 3, device=DEV))
         assert e.shape == (0,)
 
@@ -141,7 +143,7 @@ def test_neus_upsample_matches_oracle():
     d_coarse = near * (1 - t) + far * t
     want, _ = oneus.upsample(lambda p: nets.sdf_forward(p, L), o, dn, d_coarse)
     dirs, d_all, pts, d_mid, pts_mid = neus._upsample(m, o.to(DEV), d.to(DEV), 1.0, None, None, 64, 64, 4, False)
-    assert torch.equal(dirs.cpu(), dn)
+    assert rel_err(dirs, dn) < 1e-6
     assert frac_close(d_all, want, 1e-4) > 0.97
     assert torch.equal(d_mid.cpu(), 0.5 * (d_all.cpu()[:, 1:] + d_all.cpu()[:, :-1]))
     assert (d_all[:, 1:] >= d_all[:, :-1]).all()

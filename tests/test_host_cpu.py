@@ -34,7 +34,7 @@ def test_error_convention():
     from neurecon_b200 import _lib
     lib = _lib.get_lib()
     # invalid arguments are reported through the return code + nr_last_error, never by throwing
-    rc = lib.nr_sample_pdf(None, None, None, 4, 8, 4, 0, 1e-5, None, None, None, None, None)
+    rc = lib.nr_sample_pdf(None, None, None, 4, 8, 4, 0, 1e-5, None, None, None, None, None)  # R=4, null data
     assert rc == -1
     assert "null" in _lib.last_error()
     with pytest.raises(ValueError):

@@ -153,7 +153,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("NEURECON_B200_PRECISION", None))
+    ap.add_argument("--precision", default=os.environ.get("NEURECON_B200_PRECISION", None),
+                    help="fp16 (default: fused tcgen05 MLP, fp16 operands, fp32 accumulate), bf16, or fp32 (SIMT tier)")
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -250,14 +251,14 @@ def main():
     pts = (torch.rand(n_pts, 3, device=dev) - 0.5) * 1.5
     with torch.no_grad():
         for _ in range(3):
-            model.implicit_surface.forward_with_nablas(pts)
+            model.implicit_surface._run(pts, want_nablas=True, want_feat=False)
         torch.cuda.synchronize()
         reps = 5
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         lk0 = lib.nr_launch_count()
         e0.record()
         for _ in range(reps):
-            model.implicit_surface.forward_with_nablas(pts)
+            model.implicit_surface._run(pts, want_nablas=True, want_feat=False)
         e1.record()
         torch.cuda.synchronize()
         k_launches = (lib.nr_launch_count() - lk0) // reps
@@ -265,8 +266,10 @@ def main():
     achieved = n_pts * MFLOP_PER_QUERY_NABLA * 1e6 / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " bf16 burst",
-                "kernel": "sdf_forward_with_nablas (%s tier), %d points, %d launches, %.3f ms; algorithmic "
-                          "1.967 MFLOP/query" % (precision, n_pts, k_launches, k_ms),
+                "kernel": "%s: sdf + analytic nabla of %d points, %d launch(es), %.3f ms; algorithmic 1.967 "
+                          "MFLOP/query (forward-mode tangents execute 4.2 MFLOP/query on the tensor pipe)"
+                          % ("mlp_umma_kernel (fused tcgen05, %s operands)" % precision if precision != "fp32"
+                             else "gemm_kernel (fp32 SIMT tier)", n_pts, k_launches, k_ms),
                 "whole_step_frac": (value / world) * MFLOP_PER_RAY * 1e6 / 1e12 / pk["bf16"]}
 
     if rank == 0:
@@ -279,7 +282,7 @@ def main():
             "metric": "rays/sec (NeuS 64+64 samples)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
+            "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[precision], "data": "synthetic",
             "config": workload_config(precision),
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},

@@ -184,6 +184,7 @@ typedef struct {
   int32_t rad_multires;      /* embedding of x for the radiance net (<0: identity) */
   int32_t rad_multires_view; /* embedding of the view direction */
   int32_t rad_extra_rows;    /* zero-padded rows after the 256 feature rows of the radiance operand */
+  int32_t operand_f16;       /* 1: fp16 operands (image packed as fp16), 0: bf16; fp32 accumulation either way */
   nr_umma_step_t steps[NR_UMMA_MAX_STEPS];
 } nr_umma_program_t;
 

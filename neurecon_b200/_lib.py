@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "lib", "libneurecon_b200.so")
 _lib = None
 _lock = threading.Lock()
-_precision = os.environ.get("NEURECON_B200_PRECISION", "fp32")
+_precision = os.environ.get("NEURECON_B200_PRECISION", "fp16")
 
 
 class SdfNet(C.Structure):
@@ -43,7 +43,7 @@ class UmmaStep(C.Structure):
 
 class UmmaProgram(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_steps", "tangents", "multires", "rad_multires", "rad_multires_view",
-                                         "rad_extra_rows")] + [("steps", UmmaStep * NR_UMMA_MAX_STEPS)]
+                                         "rad_extra_rows", "operand_f16")] + [("steps", UmmaStep * NR_UMMA_MAX_STEPS)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -158,12 +158,18 @@ def workspace(nbytes, device, slot=0):
 
 
 def set_precision(p):
-    """'fp32' (SIMT tier, <=1e-4 vs the reference) or 'bf16' (tcgen05 tier, <=1e-2)."""
+    """'fp32' (SIMT tier, <=1e-4 vs the reference), or the tcgen05 tier with 'fp16' or 'bf16'
+    operands (fp32 accumulation; same tensor rate -- fp16 carries 3 more mantissa bits)."""
     global _precision
-    if p not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if p not in ("fp32", "bf16", "fp16"):
+        raise ValueError("precision must be 'fp32', 'fp16' or 'bf16'")
     _precision = p
 
 
 def get_precision():
     return _precision
+
+
+def tensor_tier():
+    """True when the MLPs run on the fused tcgen05 kernel."""
+    return _precision in ("fp16", "bf16")

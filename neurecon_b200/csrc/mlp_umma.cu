@@ -90,19 +90,21 @@ __device__ __forceinline__ float pe_row(int j, int multires, const float* x3, in
   return r < 3 ? f * c : -f * s;
 }
 
+template <bool kF16>
 __device__ __forceinline__ void store_row32(uint8_t* act, int k, int col0, const float (&v)[32]) {
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
     uint4 w;
-    w.x = umma::pack_bf16(v[8 * j4 + 0], v[8 * j4 + 1]);
-    w.y = umma::pack_bf16(v[8 * j4 + 2], v[8 * j4 + 3]);
-    w.z = umma::pack_bf16(v[8 * j4 + 4], v[8 * j4 + 5]);
-    w.w = umma::pack_bf16(v[8 * j4 + 6], v[8 * j4 + 7]);
+    w.x = umma::pack2<kF16>(v[8 * j4 + 0], v[8 * j4 + 1]);
+    w.y = umma::pack2<kF16>(v[8 * j4 + 2], v[8 * j4 + 3]);
+    w.z = umma::pack2<kF16>(v[8 * j4 + 4], v[8 * j4 + 5]);
+    w.w = umma::pack2<kF16>(v[8 * j4 + 6], v[8 * j4 + 7]);
     *reinterpret_cast<uint4*>(act + umma::b_chunk_offset(k, (col0 >> 3) + j4, kLbo)) = w;
   }
 }
+template <bool kF16>
 __device__ __forceinline__ void store_elem(uint8_t* act, int k, int n, float v) {
-  *reinterpret_cast<__nv_bfloat16*>(act + umma::b_chunk_offset(k, n >> 3, kLbo) + (n & 7) * 2) = __float2bfloat16_rn(v);
+  *reinterpret_cast<uint16_t*>(act + umma::b_chunk_offset(k, n >> 3, kLbo) + (n & 7) * 2) = umma::pack1<kF16>(v);
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -121,6 +123,7 @@ struct KArgs {
   float* rgb;          // [n,3] or null
 };
 
+template <bool kF16>
 __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_constant__ DevProgram prog, const KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -183,7 +186,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         for (int s = 0; s < P.n_steps; ++s) {
           const int n_mt = P.steps[s].n_mt, k_steps = P.steps[s].k_steps;
           const int nkc = (k_steps + 3) >> 2;
-          const uint32_t idesc = umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
+          const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, P.steps[s].n_cols, 0, 1)
+                                     : umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
           for (int t = 0; t < ntl; ++t) {
             umma::mbar_wait(&in_ready[t], in_par[t]);
             in_par[t] ^= 1;
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         const int ct = tang ? (n >> 5) - 1 : -1;       // -1: value column, 0..2: tangent component
         const float x3[3] = {xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]};
         const int k0 = P.steps[0].k_steps * 16;
-        for (int j = 0; j < k0; ++j) store_elem(act, j, n, j < pe_dim ? pe_row(j, P.multires, x3, ct) : 0.0f);
+        for (int j = 0; j < k0; ++j) store_elem<kF16>(act, j, n, j < pe_dim ? pe_row(j, P.multires, x3, ct) : 0.0f);
       }
       umma::fence_proxy_async_smem();
       umma::tc_fence_before();
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * j, -1);
               }
-              store_row32(act, F, 0, v);
+              store_row32<kF16>(act, F, 0, v);
 #pragma unroll 1
               for (int c = 1; c < 4; ++c) {
                 umma::tmem_ld32(taddr + 32 * c, raw);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll
                   for (int j = 0; j < 32; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * j, c - 1);
                 }
-                store_row32(act, F, 32 * c, v);
+                store_row32<kF16>(act, F, 32 * c, v);
               }
             } else {
 #pragma unroll 1
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll
                   for (int j = 0; j < 32; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (32 * c + j), -1);
                 }
-                store_row32(act, F, 32 * c, v);
+                store_row32<kF16>(act, F, 32 * c, v);
               }
             }
           }
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                   if (gp < a.n) a.feat[gp * a.feat_ld + F] = v[j];
                 }
               }
-              if (S.to_rad) store_row32(act, F, 32 * c, v);
+              if (S.to_rad) store_row32<kF16>(act, F, 32 * c, v);
             }
           }
           if (S.to_rad) {
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               if (r < px) val = pe_row(r, P.rad_multires, xs + 3 * p, -1);
               else if (r < px + pv) val = pe_row(r - px, P.rad_multires_view, vs + 3 * p, -1);
               else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
-              store_elem(act, 256 + r, p, val);
+              store_elem<kF16>(act, 256 + r, p, val);
             }
           }
         } else if (S.epi == EPI_RELU) {
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             umma::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
-            store_row32(act, F, 0, v);
+            store_row32<kF16>(act, F, 0, v);
           }
         } else if (S.epi == EPI_RGB) {
           if (q == 0) {
@@ -445,13 +449,15 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
   const size_t smem = SmemLayout::total + 1024;
   static unsigned long long attr_set = 0;  // per-device bit: the attribute is per (function, device)
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set |= 1ull << (dev & 63);
   }
   DevProgram dp;
   dp.p = *prog;
   KArgs ka{(const uint8_t*)image, bias, x, view, n, sdf, nabla, feat, feat_ld, rgb};
-  mlp_umma_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+  if (prog->operand_f16) mlp_umma_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+  else mlp_umma_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
   NR_CHECK_LAUNCH("mlp_umma_kernel");
   return NR_OK;
 }

@@ -9,6 +9,7 @@
 //                    LBO apart.  Chunk (n%64)/8 of row k is stored at chunk ((n%64)/8 ^ (k & 7)).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -106,6 +107,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Same with fp16 operands (a/b format 0): identical tensor rate and bytes, 3 more mantissa bits.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
 __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -138,6 +144,19 @@ __host__ __device__ constexpr uint32_t b_chunk_offset(int k, int n8, uint32_t lb
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// kF16 ? fp16 : bf16 operand element pair / single element (16-bit payload)
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kF16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+template <bool kF16>
+__device__ __forceinline__ uint16_t pack1(float v) {
+  if (kF16) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&b);
 }
 
 }  // namespace umma

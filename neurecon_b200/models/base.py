@@ -214,7 +214,7 @@ class ImplicitSurface(nn.Module):
         """bf16 image / bias table / step templates for the tcgen05 tier (cached like _descriptor)."""
         self._check_supported()
         from .. import umma_pack
-        key = (_param_key(self), None if radiance_net is None else _param_key(radiance_net))
+        key = (_param_key(self), None if radiance_net is None else _param_key(radiance_net), _lib.get_precision())
         slot = "umma_fused" if radiance_net is not None else "umma"
         c = self._cache.get(slot)
         if c is None or c[0] != key:
@@ -231,7 +231,8 @@ class ImplicitSurface(nn.Module):
                               rad_b=[l.bias.detach().float() for l in radiance_net.layers],
                               rad_multires=radiance_net.embed_multires,
                               rad_multires_view=radiance_net.embed_multires_view)
-                net = umma_pack.UmmaNet(Wl, bl, self.embed_multires, self.skips[0] if self.skips else -1, **kw)
+                net = umma_pack.UmmaNet(Wl, bl, self.embed_multires, self.skips[0] if self.skips else -1,
+                                        operand=_lib.get_precision(), **kw)
             c = (key, net)
             self._cache[slot] = c
         return c[1]
@@ -268,7 +269,7 @@ class ImplicitSurface(nn.Module):
 
     def _run(self, x, want_nablas, want_feat):
         _lib.require_cuda(x)
-        if _lib.get_precision() == "bf16":
+        if _lib.tensor_tier():
             sdf, nabla, feat, _ = self._run_umma(x, "nablas" if want_nablas else "sdf", want_feat=want_feat)
             return sdf, nabla, feat
         lib = _lib.get_lib()
@@ -412,7 +413,7 @@ def query_radiance(surface, radiance_net, x, view_dirs, normalize_normals=False)
     points (NeuS.forward_radiance neus.py:103-106, VolSDF.forward volsdf.py:327-331): returns
     (radiance, sdf, nablas).  bf16 tier: ONE fused kernel, the 256-wide feature and the normal
     never leave the SM; fp32 tier: the two library calls."""
-    if _lib.get_precision() == "bf16" and not normalize_normals:
+    if _lib.tensor_tier() and not normalize_normals:
         sdf, nabla, _, rgb = surface._run_umma(x, "fused", radiance_net=radiance_net, view_dirs=view_dirs)
         return rgb, sdf, nabla
     sdf, nabla, feat = surface._run(x, want_nablas=True, want_feat=True)

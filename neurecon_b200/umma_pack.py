@@ -17,7 +17,7 @@ def _a_tile_index():
     return _A_IDX
 
 
-def pack_a_tiles(W, n_mtiles=None, k_pad=None):
+def pack_a_tiles(W, n_mtiles=None, k_pad=None, dtype=torch.bfloat16):
     """W: [rows, K] float tensor -> int16 tensor [n_mtiles * n_kchunks, 8192] of A tiles ordered
     (mt major, kc minor); rows/K zero-padded to 128 / 64 multiples."""
     rows, K = W.shape
@@ -26,7 +26,7 @@ def pack_a_tiles(W, n_mtiles=None, k_pad=None):
     n_kc = (kp + 63) // 64
     full = torch.zeros(n_mt * 128, n_kc * 64, dtype=torch.float32, device=W.device)
     full[:rows, :K] = W.float()
-    bf = full.to(torch.bfloat16).view(torch.int16)
+    bf = full.to(dtype).view(torch.int16)
     tiles = bf.reshape(n_mt, 128, n_kc, 64).permute(0, 2, 1, 3).reshape(n_mt * n_kc, 128 * 64)
     idx = _a_tile_index().to(W.device).reshape(-1)
     out = torch.empty_like(tiles)
@@ -48,15 +48,17 @@ class UmmaNet:
     """bf16 weight image + bias table + step templates for one (surface[, radiance]) pair."""
 
     def __init__(self, surface_W, surface_b, multires, skip_layer, rad_W=None, rad_b=None, rad_multires=-1,
-                 rad_multires_view=-1):
+                 rad_multires_view=-1, operand="fp16"):
         dev = surface_W[0].device
+        self.operand = operand
+        op_dtype = torch.float16 if operand == "fp16" else torch.bfloat16
         self.multires = multires
         self.rad_multires, self.rad_multires_view = rad_multires, rad_multires_view
         chunks, biases = [], []
         self._n_chunks, self._n_bias = 0, 0
 
         def add(W, b, k_steps, n_mt):
-            img = pack_a_tiles(W, n_mtiles=n_mt, k_pad=k_steps * 16)
+            img = pack_a_tiles(W, n_mtiles=n_mt, k_pad=k_steps * 16, dtype=op_dtype)
             assert img.shape[0] == n_mt * ((k_steps + 3) // 4)
             bt = torch.zeros(n_mt * 128, dtype=torch.float32, device=dev)
             if b is not None:
@@ -147,6 +149,7 @@ class UmmaNet:
         assert len(steps) <= _lib.NR_UMMA_MAX_STEPS
         P.n_steps, P.tangents, P.multires = len(steps), tang, self.multires
         P.rad_multires, P.rad_multires_view, P.rad_extra_rows = self.rad_multires, self.rad_multires_view, self.rad_extra_rows
+        P.operand_f16 = 1 if self.operand == "fp16" else 0
         for i, s in enumerate(steps):
             for k, v in s.items():
                 setattr(P.steps[i], k, int(v))

@@ -15,6 +15,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _fp32_tier():
+    import neurecon_b200
+    neurecon_b200.set_precision("fp32")
+    yield
+    neurecon_b200.set_precision("fp16")
+
+
 def test_native_library_is_loaded():
     from neurecon_b200 import _lib
     lib = _lib.get_lib()

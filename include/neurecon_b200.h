@@ -185,6 +185,7 @@ typedef struct {
   int32_t rad_multires_view; /* embedding of the view direction */
   int32_t rad_extra_rows;    /* zero-padded rows after the 256 feature rows of the radiance operand */
   int32_t operand_f16;       /* 1: fp16 operands (image packed as fp16), 0: bf16; fp32 accumulation either way */
+  int32_t debug_flags;       /* profiling only (results invalid): 1 = no weight copies, 2 = no epilogue math/stores */
   nr_umma_step_t steps[NR_UMMA_MAX_STEPS];
 } nr_umma_program_t;
 

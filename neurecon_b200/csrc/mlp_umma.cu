@@ -166,10 +166,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
           for (int t = 0; t < ntl; ++t) {
             for (int c = 0; c < nch; ++c) {
               umma::mbar_wait(&w_empty[stage], phase ^ 1);
-              umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
-              umma::bulk_g2s(smem + SmemLayout::ring + stage * kChunkBytes,
-                             a.image + (size_t)(P.steps[s].chunk_begin + c) * kChunkBytes, kChunkBytes,
-                             &w_full[stage]);
+              if (P.debug_flags & 1) {
+                umma::mbar_arrive(&w_full[stage]);
+              } else {
+                umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
+                umma::bulk_g2s(smem + SmemLayout::ring + stage * kChunkBytes,
+                               a.image + (size_t)(P.steps[s].chunk_begin + c) * kChunkBytes, kChunkBytes,
+                               &w_full[stage]);
+              }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -258,7 +262,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         acc_par ^= 1;
         umma::tc_fence_after();
 
-        if (S.epi == EPI_HIDDEN) {
+        if (P.debug_flags & 2) {
+          // profiling: MMA + weight pipeline only
+        } else if (S.epi == EPI_HIDDEN) {
           for (int mt = 0; mt < S.n_mt; ++mt) {
             const int F = mt * 128 + 32 * q + lane;
             const float b = a.bias[S.bias_off + F];

@@ -76,7 +76,53 @@ def golden_sampling(ref):
         det_cdf=det_cdf, near=near, far=far)
 
 
+def golden_volsdf(ref):
+    for tag, beta_init, npp in (("b0p1", 0.1, False), ("b0p01", 0.01, False), ("b0p003", 0.003, False),
+                                ("b0p01_nerfpp", 0.01, True)):
+        kw = dict(synthetic.VOLSDF_MODEL_KWARGS, beta_init=beta_init, use_nerfplusplus=npp)
+        torch.manual_seed(0)
+        m = ref.volsdf.VolSDF(**kw)
+        synthetic.reseed_parameters(m, seed=3)
+        R = 24
+        o, d = synthetic.make_rays(R, shell_radius=3.0 / 1.1, jitter=0.1, seed=3)
+        with torch.no_grad():
+            _, _, ret = ref.volsdf.volume_render(
+                o, d, m, calc_normal=True, detailed_output=True, perturb=False, near=0.0, far=6.0,
+                obj_bounding_radius=3.0, max_upsample_steps=5 if npp else 6, use_nerfplusplus=npp, N_outside=32)
+        keep = ["rgb", "depth_volume", "mask_volume", "normals_volume", "beta_map", "iter_usage", "d_vals", "sigma",
+                "visibility_weights"]
+        npz("volsdf_render_%s_r24.npz" % tag, seed=3, beta_init=beta_init, nerfpp=int(npp), **{k: ret[k] for k in keep})
+
+    # error_bound / sdf_to_sigma on synthetic 1-D data (incl. overflow -> inf entries)
+    rs = np.random.RandomState(11)
+    R, M = 16, 200
+    dv = np.sort(rs.uniform(0, 6, size=(R, M)).astype(np.float32), axis=1)
+    sdf = (np.abs(dv - 3.0) - 1.0 + 0.05 * rs.normal(size=(R, M))).astype(np.float32)
+    outs = {}
+    for i, beta in enumerate((0.5, 0.05, 0.002)):
+        b = torch.tensor(beta)
+        outs["bound_%d" % i] = ref.volsdf.error_bound(torch.from_numpy(dv), torch.from_numpy(sdf), 1.0 / b, b)
+        outs["sigma_%d" % i] = ref.volsdf.sdf_to_sigma(torch.from_numpy(sdf), 1.0 / b, b)
+    npz("volsdf_error_bound.npz", d_vals=dv, sdf=sdf, betas=np.array([0.5, 0.05, 0.002], dtype=np.float32), **outs)
+
+
+def golden_unisurf(ref):
+    torch.manual_seed(0)
+    m = ref.unisurf.UNISURF(**synthetic.UNISURF_MODEL_KWARGS)
+    synthetic.reseed_parameters(m, seed=4)
+    R = 40
+    o, d = synthetic.make_rays(R, shell_radius=3.0, jitter=0.25, seed=4)
+    with torch.no_grad():
+        _, _, ret = ref.unisurf.volume_render(o[None], d[None], m, batched=True, calc_normal=True, detailed_output=True,
+                                              perturb=False, logit_tau=0.0, radius_of_interest=4.0, interval=1.0)
+    keep = ["rgb", "depth_volume", "mask_volume", "normals_volume", "surface_points", "mask_surface", "depth_surface",
+            "implicit_surface", "alpha", "visibility_weights"]
+    npz("unisurf_render_r40.npz", seed=4, **{k: ret[k][0] for k in keep})
+
+
 if __name__ == "__main__":
     ref = ref_loader.load()
     golden_neus(ref)
     golden_sampling(ref)
+    golden_volsdf(ref)
+    golden_unisurf(ref)

@@ -98,3 +98,69 @@ def test_live_reference_matches_oracle_and_loads_our_state_dict():
     _, _, q = oneus.volume_render(o, d, cpu_state_dict(ours), NEUS_CFG, calc_normal=True, white_bkgd=True)
     for k in ("rgb", "depth_volume", "mask_volume", "normals_volume"):
         assert rel_err(q[k], r[k]) < 1e-5, k
+
+
+VOLSDF_CFG = dict(multires=6, multires_view=-1, rad_multires=-1, skips=[4], D=8, D_rad=4, speed_factor=10.0)
+UNISURF_CFG = dict(multires=6, multires_view=-1, rad_multires=-1, skips=[4], D=8, D_rad=4)
+
+
+def build_volsdf(beta_init=0.1, nerfpp=False, seed=3, device="cpu"):
+    from neurecon_b200.models.frameworks import volsdf
+    torch.manual_seed(0)
+    m = volsdf.VolSDF(**dict(synthetic.VOLSDF_MODEL_KWARGS, beta_init=beta_init, use_nerfplusplus=nerfpp))
+    synthetic.reseed_parameters(m, seed=seed)
+    return m.to(device)
+
+
+def build_unisurf(seed=4, device="cpu"):
+    from neurecon_b200.models.frameworks import unisurf
+    torch.manual_seed(0)
+    m = unisurf.UNISURF(**synthetic.UNISURF_MODEL_KWARGS)
+    synthetic.reseed_parameters(m, seed=seed)
+    return m.to(device)
+
+
+def test_volsdf_error_bound_golden():
+    from oracle import volsdf as ov
+    g = load_golden("volsdf_error_bound.npz")
+    for i, beta in enumerate(g["betas"].tolist()):
+        b = torch.tensor(beta)
+        got = ov.error_bound(g["d_vals"], g["sdf"], 1.0 / b, b)
+        want = g["bound_%d" % i]
+        assert torch.equal(torch.isinf(got), torch.isinf(want))
+        fin = torch.isfinite(want)
+        assert rel_err(got[fin], want[fin]) < 1e-6
+        assert rel_err(ov.sdf_to_sigma(g["sdf"], 1.0 / b, b), g["sigma_%d" % i]) < 1e-6
+    assert torch.isinf(g["bound_2"]).any(), "fixture should exercise the overflow -> inf branch"
+
+
+@pytest.mark.parametrize("tag,beta_init,nerfpp", [("b0p1", 0.1, False), ("b0p01", 0.01, False),
+                                                  ("b0p003", 0.003, False), ("b0p01_nerfpp", 0.01, True)])
+def test_volsdf_render_golden(tag, beta_init, nerfpp):
+    from oracle import volsdf as ov
+    g = load_golden("volsdf_render_%s_r24.npz" % tag)
+    sd = cpu_state_dict(build_volsdf(beta_init, nerfpp))
+    o, d = synthetic.make_rays(24, shell_radius=3.0 / 1.1, jitter=0.1, seed=3)
+    _, _, ret = ov.volume_render(o, d, sd, VOLSDF_CFG, max_upsample_steps=5 if nerfpp else 6, use_nerfplusplus=nerfpp)
+    assert torch.equal(ret["iter_usage"], g["iter_usage"])
+    if beta_init < 0.1:
+        assert (g["iter_usage"] != 0).any(), "fixture should exercise the beta iteration"
+    assert rel_err(ret["beta_map"], g["beta_map"]) < 1e-6
+    for k in ("rgb", "depth_volume", "mask_volume", "normals_volume"):
+        assert rel_err(ret[k], g[k]) < 1e-5, (k, rel_err(ret[k], g[k]))
+    for k in ("d_vals", "sigma", "visibility_weights"):
+        assert frac_close(ret[k], g[k], 1e-4) > 0.97, k
+
+
+def test_unisurf_render_golden():
+    from oracle import unisurf as ou
+    g = load_golden("unisurf_render_r40.npz")
+    sd = cpu_state_dict(build_unisurf())
+    o, d = synthetic.make_rays(40, shell_radius=3.0, jitter=0.25, seed=4)
+    _, _, ret = ou.volume_render(o, d, sd, UNISURF_CFG)
+    assert torch.equal(ret["mask_surface"], g["mask_surface"].bool())
+    assert 0 < g["mask_surface"].sum() < 40, "fixture should contain both hit and miss rays"
+    for k in ("rgb", "depth_volume", "mask_volume", "normals_volume", "surface_points", "depth_surface"):
+        assert rel_err(ret[k], g[k]) < 1e-5, (k, rel_err(ret[k], g[k]))
+    for k in ("implicit_surface", "alpha", "visibility_weights"):
+        assert frac_close(ret[k], g[k], 1e-4) > 0.97, k

@@ -156,66 +156,70 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    // ===================== weight producer (one lane) =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
-        for (int s = 0; s < P.n_steps; ++s) {
-          const int nch = P.steps[s].n_mt * ((P.steps[s].k_steps + 3) >> 2);
-          for (int t = 0; t < ntl; ++t) {
-            for (int c = 0; c < nch; ++c) {
-              umma::mbar_wait(&w_empty[stage], phase ^ 1);
+    // ===================== weight producer (warp-uniform loop, one elected lane copies) ==========
+    uint32_t stage = 0, phase = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
+      for (int s = 0; s < P.n_steps; ++s) {
+        const int nch = P.steps[s].n_mt * ((P.steps[s].k_steps + 3) >> 2);
+        const uint8_t* src = a.image + (size_t)P.steps[s].chunk_begin * kChunkBytes;
+        for (int t = 0; t < ntl; ++t) {
+          for (int c = 0; c < nch; ++c) {
+            umma::mbar_wait(&w_empty[stage], phase ^ 1);
+            if (umma::elect_one()) {
               if (P.debug_flags & 1) {
                 umma::mbar_arrive(&w_full[stage]);
               } else {
                 umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
-                umma::bulk_g2s(smem + SmemLayout::ring + stage * kChunkBytes,
-                               a.image + (size_t)(P.steps[s].chunk_begin + c) * kChunkBytes, kChunkBytes,
-                               &w_full[stage]);
+                umma::bulk_g2s(smem + SmemLayout::ring + stage * kChunkBytes, src + (size_t)c * kChunkBytes,
+                               kChunkBytes, &w_full[stage]);
               }
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      uint32_t in_par[2] = {0, 0};
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
-        for (int s = 0; s < P.n_steps; ++s) {
-          const int n_mt = P.steps[s].n_mt, k_steps = P.steps[s].k_steps;
-          const int nkc = (k_steps + 3) >> 2;
-          const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, P.steps[s].n_cols, 0, 1)
-                                     : umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
-          for (int t = 0; t < ntl; ++t) {
-            umma::mbar_wait(&in_ready[t], in_par[t]);
-            in_par[t] ^= 1;
-            umma::tc_fence_after();
-            const uint32_t act_addr = umma::smem_u32(smem + SmemLayout::act + t * kActBytes);
-            for (int mt = 0; mt < n_mt; ++mt) {
-              const uint32_t d_addr = tmem_base + (uint32_t)(t * 256 + mt * 128);
-              for (int kc = 0; kc < nkc; ++kc) {
-                umma::mbar_wait(&w_full[stage], phase);
-                umma::tc_fence_after();
-                const uint32_t w_addr = umma::smem_u32(smem + SmemLayout::ring + stage * kChunkBytes);
-                const int kn = min(4, k_steps - 4 * kc);
-                for (int k4 = 0; k4 < kn; ++k4) {
-                  const int ks = 4 * kc + k4;
-                  const uint64_t da = umma::make_smem_desc(w_addr + k4 * 32, 16, 1024);
-                  const uint64_t db = umma::make_smem_desc(act_addr + ks * 2048, kLbo, 1024);
-                  umma::mma_bf16_ss(d_addr, da, db, idesc, ks > 0 ? 1u : 0u);
-                }
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) ================
+    uint32_t stage = 0, phase = 0;
+    uint32_t in_par[2] = {0, 0};
+    const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
+    const uint32_t ring_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::ring), 16);
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
+      for (int s = 0; s < P.n_steps; ++s) {
+        const int n_mt = P.steps[s].n_mt, k_steps = P.steps[s].k_steps;
+        const int nkc = (k_steps + 3) >> 2;
+        const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, P.steps[s].n_cols, 0, 1)
+                                    : umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
+        for (int t = 0; t < ntl; ++t) {
+          umma::mbar_wait(&in_ready[t], in_par[t]);
+          in_par[t] ^= 1;
+          umma::tc_fence_after();
+          const uint32_t act_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::act + t * kActBytes), kLbo);
+          for (int mt = 0; mt < n_mt; ++mt) {
+            const uint32_t d_addr = tmem_base + (uint32_t)(t * 256 + mt * 128);
+            for (int kc = 0; kc < nkc; ++kc) {
+              umma::mbar_wait(&w_full[stage], phase);
+              umma::tc_fence_after();
+              const uint32_t a_lo = ring_lo + stage * (kChunkBytes >> 4);
+              const uint32_t b_lo = act_lo + kc * (4 * 2048 >> 4);
+              const int kn = k_steps - 4 * kc;  // >= 1
+              if (umma::elect_one()) {
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, kc > 0 ? 1u : 0u);
+                if (kn > 1) umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
+                if (kn > 2) umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
+                if (kn > 3) umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
                 umma::mma_commit(&w_empty[stage]);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
               }
+              __syncwarp();
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            umma::mma_commit(&acc_ready[t]);
           }
+          if (umma::elect_one()) umma::mma_commit(&acc_ready[t]);
+          __syncwarp();
         }
       }
     }

@@ -420,3 +420,35 @@ def query_radiance(surface, radiance_net, x, view_dirs, normalize_normals=False)
     normals = torch.nn.functional.normalize(nabla) if normalize_normals else nabla
     rgb = radiance_net.forward(x, view_dirs, normals, feat)
     return rgb, sdf, nabla
+
+
+class NeRF(nn.Module):
+    """NeRF++ background MLP (base.py:395-453): same constructor, parameter names
+    (``pts_linears.{i}``, ``views_linears.0``, ``feature_linear``, ``alpha_linear``,
+    ``rgb_linear``; plain ``weight``/``bias``) and ``forward(input_pts, input_views) -> (sigma, rgb)``."""
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_view=3, multires=-1, multires_view=-1, output_ch=4,
+                 skips=[4], use_view_dirs=False):
+        super().__init__()
+        self.D, self.W = D, W
+        self.skips = list(skips)
+        self.use_view_dirs = use_view_dirs
+        self.multires, self.multires_view = multires, multires_view
+        self.input_dim, self.input_dim_view = input_ch, input_ch_view
+        self.embed_fn, input_ch = get_embedder(multires, input_dim=input_ch)
+        self.embed_fn_view, input_ch_view = get_embedder(multires_view, input_dim=input_ch_view)
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)]
+            + [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + input_ch, W) for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_view + W, W // 2)])
+        if use_view_dirs:
+            self.feature_linear = nn.Linear(W, W)
+            self.alpha_linear = nn.Linear(W, 1)
+            self.rgb_linear = nn.Linear(W // 2, 3)
+        else:
+            self.output_linear = nn.Linear(W, output_ch)
+        self._cache = {}
+
+    def forward(self, input_pts, input_views):
+        from .nerfpp import nerf_forward
+        return nerf_forward(self, input_pts, input_views)

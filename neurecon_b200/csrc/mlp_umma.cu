@@ -11,10 +11,11 @@
 //     d/dy, d/dz} (forward-mode tangents ride through the same weights); without, 128 points.
 //     TMEM lane = feature, so one thread owns a feature for all columns: the tangent epilogue
 //     t' = softplus'(z) * (W t) is register-local, no shuffles.
-//   * Warp roles (384 threads): warp 0 bulk-copy producer, warp 1 MMA issuer (one thread),
-//     warp 2 TMEM allocator, warps 4-7 / 8-11 epilogue warpgroups for tile A / tile B.  The two
-//     tiles ping-pong: while the tensor core runs layer l of tile B, warpgroup A applies layer
-//     l's activation to tile A and publishes its next operand.
+//   * Warp roles (640 threads): warp 0 bulk-copy producer, warp 1 MMA issuer (one elected lane),
+//     warp 2 TMEM allocator, warps 4-11 / 12-19 epilogue warps of tile A / tile B (one warpgroup
+//     per M-tile, so every SM sub-partition holds 4 epilogue warps to hide TMEM-load and MUFU
+//     latency).  The two tiles ping-pong: while the tensor core runs layer l of tile B, tile A's
+//     warps apply layer l's activation and publish its next operand.
 //
 // Reference semantics: models/base.py:46-64 (Embedder), :243-282 (ImplicitSurface.forward /
 // forward_with_nablas), :372-391 (RadianceNet.forward).
@@ -27,7 +28,8 @@ constexpr int kStages = 5;
 constexpr uint32_t kChunkBytes = 16384;      // one A tile: 128 features x 64 k, bf16
 constexpr uint32_t kActBytes = 65536;        // one tile's B operand: 256 k-rows x 128 columns, bf16
 constexpr uint32_t kLbo = 32768;             // bytes between 64-column blocks of the B operand
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilogue warps
+constexpr int kEpiPerTile = 256;
 constexpr int kEpiWarp0 = 4;
 
 enum : int32_t {
@@ -91,9 +93,35 @@ __device__ __forceinline__ float pe_row(int j, int multires, const float* x3, in
 }
 
 template <bool kF16>
-__device__ __forceinline__ void store_row32(uint8_t* act, int k, int col0, const float (&v)[32]) {
+__device__ __forceinline__ void store_row32(uint8_t* act, int k, int col0, const float (&v)[32], bool skip = false) {
+  if (skip) {  // profiling: keep the math alive without touching shared memory
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += v[j];
+    if (acc == 123.456f) *reinterpret_cast<float*>(act) = acc;
+    return;
+  }
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
+    uint4 w;
+    w.x = umma::pack2<kF16>(v[8 * j4 + 0], v[8 * j4 + 1]);
+    w.y = umma::pack2<kF16>(v[8 * j4 + 2], v[8 * j4 + 3]);
+    w.z = umma::pack2<kF16>(v[8 * j4 + 4], v[8 * j4 + 5]);
+    w.w = umma::pack2<kF16>(v[8 * j4 + 6], v[8 * j4 + 7]);
+    *reinterpret_cast<uint4*>(act + umma::b_chunk_offset(k, (col0 >> 3) + j4, kLbo)) = w;
+  }
+}
+template <bool kF16>
+__device__ __forceinline__ void store_row16(uint8_t* act, int k, int col0, const float (&v)[16], bool skip = false) {
+  if (skip) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc += v[j];
+    if (acc == 123.456f) *reinterpret_cast<float*>(act) = acc;
+    return;
+  }
+#pragma unroll
+  for (int j4 = 0; j4 < 2; ++j4) {
     uint4 w;
     w.x = umma::pack2<kF16>(v[8 * j4 + 0], v[8 * j4 + 1]);
     w.y = umma::pack2<kF16>(v[8 * j4 + 2], v[8 * j4 + 3]);
@@ -143,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
-    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], 128); umma::mbar_init(&acc_ready[t], 1); }
+    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], kEpiPerTile); umma::mbar_init(&acc_ready[t], 1); }
     umma::fence_barrier_init();
   }
   if (warp == 2) {
@@ -224,10 +252,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue warpgroups =====================
-    const int t = (warp - kEpiWarp0) >> 2;          // tile slot 0 / 1
-    const int q = warp & 3;                         // TMEM lane quarter
-    const int etid = (warp - kEpiWarp0 - 4 * t) * 32 + lane;  // 0..127 inside the warpgroup
+    // ===================== epilogue: 8 warps per tile, one warpgroup per M-tile =====================
+    const int e = warp - kEpiWarp0;                 // 0..15
+    const int t = e >> 3;                           // tile slot 0 / 1
+    const int mo = (e >> 2) & 1;                    // M-tile this warpgroup owns
+    const int q = warp & 3;                         // TMEM lane quarter (hardware: warp id % 4)
+    const int etid = (e & 7) * 32 + lane;           // 0..255 inside the tile's epilogue group
     uint8_t* act = smem + SmemLayout::act + t * kActBytes;
     float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
     float* vs = (float*)(smem + SmemLayout::vs) + t * 96;
@@ -235,6 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
     const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
     uint32_t acc_par = 0;
     const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
+    const bool no_st = P.debug_flags & 8;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + t;
@@ -242,19 +273,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
       const int64_t p0 = tile * ppt;
 
       // ---- prologue: stage the points, evaluate the embedding into operand rows [0, k0) ----
-      for (int i = etid; i < ppt * 3; i += 128) {
+      for (int i = etid; i < ppt * 3; i += kEpiPerTile) {
         const int64_t gi = p0 * 3 + i;
         xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
         if (a.view && i < 96) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
       }
-      named_bar_sync(1 + t, 128);
+      named_bar_sync(1 + t, kEpiPerTile);
       {
-        const int n = etid;                            // operand column
+        const int n = etid & 127;                      // operand column
         const int p = tang ? (n & 31) : n;
         const int ct = tang ? (n >> 5) - 1 : -1;       // -1: value column, 0..2: tangent component
         const float x3[3] = {xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]};
         const int k0 = P.steps[0].k_steps * 16;
-        for (int j = 0; j < k0; ++j) store_elem<kF16>(act, j, n, j < pe_dim ? pe_row(j, P.multires, x3, ct) : 0.0f);
+        for (int j = etid >> 7; j < k0; j += 2)
+          store_elem<kF16>(act, j, n, j < pe_dim ? pe_row(j, P.multires, x3, ct) : 0.0f);
       }
       umma::fence_proxy_async_smem();
       umma::tc_fence_before();
@@ -265,62 +297,74 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         umma::mbar_wait(&acc_ready[t], acc_par);
         acc_par ^= 1;
         umma::tc_fence_after();
+        const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
+        const uint32_t taddr = tmem_tile + (uint32_t)(mo * 128);
 
         if (P.debug_flags & 2) {
           // profiling: MMA + weight pipeline only
         } else if (S.epi == EPI_HIDDEN) {
-          for (int mt = 0; mt < S.n_mt; ++mt) {
-            const int F = mt * 128 + 32 * q + lane;
+          if (mo < S.n_mt) {
             const float b = a.bias[S.bias_off + F];
-            const uint32_t taddr = tmem_tile + (uint32_t)(mt * 128);
             const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
-            uint32_t raw[32];
-            float v[32];
-            if (tang) {
-              float sg[32];
-              umma::tmem_ld32(taddr, raw);
-              umma::tmem_ld_wait();
-              if (!is_pe) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) softplus100_fast(__uint_as_float(raw[j]) + b, v[j], sg[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * j, -1);
+            uint32_t raw[16];
+            float v[16];
+            if (P.debug_flags & 4) {
+              for (int c = 0; c < 8; ++c) {
+                umma::tmem_ld16(taddr + 16 * c, raw);
+                umma::tmem_ld_wait();
+                if (__uint_as_float(raw[0]) == 123.456f) act[0] = 1;
               }
-              store_row32<kF16>(act, F, 0, v);
+            } else if (tang) {
+              // columns: [0,32) values of 32 points, [32c, 32c+32) d/dx_c; processed in two 16-point halves
 #pragma unroll 1
-              for (int c = 1; c < 4; ++c) {
-                umma::tmem_ld32(taddr + 32 * c, raw);
+              for (int h = 0; h < 2; ++h) {
+                float sg[16];
+                umma::tmem_ld16(taddr + 16 * h, raw);
                 umma::tmem_ld_wait();
                 if (!is_pe) {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * sg[j];
+                  for (int j = 0; j < 16; ++j) softplus100_fast(__uint_as_float(raw[j]) + b, v[j], sg[j]);
                 } else {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * j, c - 1);
+                  for (int j = 0; j < 16; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (16 * h + j), -1);
                 }
-                store_row32<kF16>(act, F, 32 * c, v);
+                store_row16<kF16>(act, F, 16 * h, v, no_st);
+#pragma unroll 1
+                for (int c = 1; c < 4; ++c) {
+                  umma::tmem_ld16(taddr + 32 * c + 16 * h, raw);
+                  umma::tmem_ld_wait();
+                  if (!is_pe) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * sg[j];
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                      v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (16 * h + j), c - 1);
+                  }
+                  store_row16<kF16>(act, F, 32 * c + 16 * h, v, no_st);
+                }
               }
             } else {
 #pragma unroll 1
-              for (int c = 0; c < 4; ++c) {
-                umma::tmem_ld32(taddr + 32 * c, raw);
+              for (int c = 0; c < 8; ++c) {
+                umma::tmem_ld16(taddr + 16 * c, raw);
                 umma::tmem_ld_wait();
                 if (!is_pe) {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
+                  for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
                 } else {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (32 * c + j), -1);
+                  for (int j = 0; j < 16; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (16 * c + j), -1);
                 }
-                store_row32<kF16>(act, F, 32 * c, v);
+                store_row16<kF16>(act, F, 16 * c, v, no_st);
               }
             }
           }
         } else if (S.epi == EPI_SDF_OUT) {
-          // rows 0..31 of this M-tile all hold the sdf row: lane l keeps column l of each chunk
-          if (q == 0) {
+          // rows 0..31 of this M-tile all hold the sdf row: lane l keeps column l of each 32-column chunk
+          if (mo == 0 && q == 0) {
             const float b = a.bias[S.bias_off];
+#pragma unroll 1
             for (int c = 0; c < 4; ++c) {
               uint32_t raw[32];
               umma::tmem_ld32(tmem_tile + 32 * c, raw);
@@ -343,35 +387,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             }
           }
         } else if (S.epi == EPI_FEAT) {
-          const int nchunk = S.n_cols >> 5;
-          for (int mt = 0; mt < S.n_mt; ++mt) {
-            const int F = mt * 128 + 32 * q + lane;
+          if (mo < S.n_mt) {
             const float b = a.bias[S.bias_off + F];
+            const int nchunk = S.n_cols >> 4;
+#pragma unroll 1
             for (int c = 0; c < nchunk; ++c) {
-              uint32_t raw[32];
-              float v[32];
-              umma::tmem_ld32(tmem_tile + (uint32_t)(mt * 128 + 32 * c), raw);
+              uint32_t raw[16];
+              float v[16];
+              umma::tmem_ld16(taddr + 16 * c, raw);
               umma::tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + b;
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + b;
               if (a.feat && F < S.out_rows) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int64_t gp = p0 + 32 * c + j;
+                for (int j = 0; j < 16; ++j) {
+                  const int64_t gp = p0 + 16 * c + j;
                   if (gp < a.n) a.feat[gp * a.feat_ld + F] = v[j];
                 }
               }
-              if (S.to_rad) store_row32<kF16>(act, F, 32 * c, v);
+              if (S.to_rad) store_row16<kF16>(act, F, 16 * c, v);
             }
           }
           if (S.to_rad) {
             // operand rows [256, 256 + extras): [PE(x) | PE(view) | normals | 0-pad]  (tangent tiles)
-            named_bar_sync(1 + t, 128);  // normal stash of EPI_SDF_OUT visible
+            named_bar_sync(1 + t, kEpiPerTile);  // normal stash of EPI_SDF_OUT visible
             const int p = etid & 31, g = etid >> 5;
             const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
             const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
             const int extra = P.rad_extra_rows;
-            for (int r = g; r < extra; r += 4) {
+            for (int r = g; r < extra; r += 8) {
               float val = 0.0f;
               if (r < px) val = pe_row(r, P.rad_multires, xs + 3 * p, -1);
               else if (r < px + pv) val = pe_row(r - px, P.rad_multires_view, vs + 3 * p, -1);
@@ -380,19 +424,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             }
           }
         } else if (S.epi == EPI_RELU) {
-          for (int mt = 0; mt < S.n_mt; ++mt) {
-            const int F = mt * 128 + 32 * q + lane;
+          if (mo < S.n_mt) {
             const float b = a.bias[S.bias_off + F];
-            uint32_t raw[32];
-            float v[32];
-            umma::tmem_ld32(tmem_tile + (uint32_t)(mt * 128), raw);
-            umma::tmem_ld_wait();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              uint32_t raw[16];
+              float v[16];
+              umma::tmem_ld16(taddr + 16 * c, raw);
+              umma::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
-            store_row32<kF16>(act, F, 0, v);
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
+              store_row16<kF16>(act, F, 16 * c, v);
+            }
           }
         } else if (S.epi == EPI_RGB) {
-          if (q == 0) {
+          if (mo == 0 && q == 0) {
             uint32_t raw[32];
             umma::tmem_ld32(tmem_tile, raw);
             umma::tmem_ld_wait();
@@ -413,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         }
       }
       umma::tc_fence_before();
-      named_bar_sync(1 + t, 128);  // all TMEM reads of this tile retired before its slot is reused
+      named_bar_sync(1 + t, kEpiPerTile);  // staging buffers and TMEM slot free before the next tile
     }
   }
 

@@ -166,9 +166,9 @@ int nr_neus_composite(const float* sdf, const float* nablas, const float* radian
 #define NR_UMMA_EPI_RGB 4     /* sigmoid, 3 rows, to global */
 
 typedef struct {
-  int32_t chunk_begin; /* first 16 KB weight chunk of this step; chunks ordered (M-tile, k-chunk) */
+  int32_t chunk_begin; /* first 16 KB weight chunk of this step; chunks ordered (k-chunk major, M-tile minor) */
   int32_t n_mt;        /* M-tiles of 128 output features (1 or 2) */
-  int32_t k_steps;     /* K / 16 */
+  int32_t k_steps;     /* K / 16, a multiple of 4 (K zero-padded to a multiple of 64) */
   int32_t n_cols;      /* MMA N: operand columns consumed (32, 64 or 128) */
   int32_t epi;         /* NR_UMMA_EPI_* */
   int32_t bias_off;    /* offset of n_mt*128 fp32 biases in the bias table */

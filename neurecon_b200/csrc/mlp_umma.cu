@@ -11,8 +11,8 @@
 //     d/dy, d/dz} (forward-mode tangents ride through the same weights); without, 128 points.
 //     TMEM lane = feature, so one thread owns a feature for all columns: the tangent epilogue
 //     t' = softplus'(z) * (W t) is register-local, no shuffles.
-//   * Warp roles (640 threads): warp 0 bulk-copy producer, warp 1 MMA issuer (one elected lane),
-//     warp 2 TMEM allocator, warps 4-11 / 12-19 epilogue warps of tile A / tile B (one warpgroup
+//   * Warp roles (640 threads): warp 0 bulk-copy producer, warps 1 and 3 MMA issuers (one elected
+//     lane each, one M-tile each), warp 2 TMEM allocator, warps 4-11 / 12-19 epilogue warps of tile A / tile B (one warpgroup
 //     per M-tile, so every SM sub-partition holds 4 epilogue warps to hide TMEM-load and MUFU
 //     latency).  The two tiles ping-pong: while the tensor core runs layer l of tile B, tile A's
 //     warps apply layer l's activation and publish its next operand.
@@ -30,6 +30,7 @@ constexpr uint32_t kActBytes = 65536;        // one tile's B operand: 256 k-rows
 constexpr uint32_t kLbo = 32768;             // bytes between 64-column blocks of the B operand
 constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilogue warps
 constexpr int kEpiPerTile = 256;
+constexpr int kEpiWarpsPerTile = 8;
 constexpr int kEpiWarp0 = 4;
 
 enum : int32_t {
@@ -111,24 +112,33 @@ __device__ __forceinline__ void store_row32(uint8_t* act, int k, int col0, const
     *reinterpret_cast<uint4*>(act + umma::b_chunk_offset(k, (col0 >> 3) + j4, kLbo)) = w;
   }
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// Row k of the operand as a 32-bit shared address + its swizzle key; a 16-byte chunk n8 of that row
+// then lives at row_addr + (n8 >> 3) * LBO + (((n8 & 7) ^ key) << 4)  (see umma::b_chunk_offset).
+struct RowAddr {
+  uint32_t base, key;
+  __device__ __forceinline__ RowAddr(uint32_t act_s, int k)
+      : base(act_s + (uint32_t)((k >> 3) * 1024 + (k & 7) * 128)), key((uint32_t)(k & 7)) {}
+  __device__ __forceinline__ uint32_t chunk(int n8) const {
+    return base + (uint32_t)(n8 >> 3) * kLbo + ((((uint32_t)n8 & 7u) ^ key) << 4);
+  }
+};
 template <bool kF16>
-__device__ __forceinline__ void store_row16(uint8_t* act, int k, int col0, const float (&v)[16], bool skip = false) {
+__device__ __forceinline__ void store_row16(const RowAddr& ra, int col0, const float (&v)[16], bool skip = false) {
   if (skip) {
     float acc = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc += v[j];
-    if (acc == 123.456f) *reinterpret_cast<float*>(act) = acc;
+    if (acc == 123.456f) st_shared_v4(ra.base, 0, 0, 0, 0);
     return;
   }
 #pragma unroll
-  for (int j4 = 0; j4 < 2; ++j4) {
-    uint4 w;
-    w.x = umma::pack2<kF16>(v[8 * j4 + 0], v[8 * j4 + 1]);
-    w.y = umma::pack2<kF16>(v[8 * j4 + 2], v[8 * j4 + 3]);
-    w.z = umma::pack2<kF16>(v[8 * j4 + 4], v[8 * j4 + 5]);
-    w.w = umma::pack2<kF16>(v[8 * j4 + 6], v[8 * j4 + 7]);
-    *reinterpret_cast<uint4*>(act + umma::b_chunk_offset(k, (col0 >> 3) + j4, kLbo)) = w;
-  }
+  for (int j4 = 0; j4 < 2; ++j4)
+    st_shared_v4(ra.chunk((col0 >> 3) + j4), umma::pack2<kF16>(v[8 * j4 + 0], v[8 * j4 + 1]),
+                 umma::pack2<kF16>(v[8 * j4 + 2], v[8 * j4 + 3]), umma::pack2<kF16>(v[8 * j4 + 4], v[8 * j4 + 5]),
+                 umma::pack2<kF16>(v[8 * j4 + 6], v[8 * j4 + 7]));
 }
 template <bool kF16>
 __device__ __forceinline__ void store_elem(uint8_t* act, int k, int n, float v) {
@@ -136,6 +146,15 @@ __device__ __forceinline__ void store_elem(uint8_t* act, int k, int n, float v) 
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Epilogue -> MMA hand-off: every lane makes its generic-proxy smem writes visible to the async
+// proxy and orders its TMEM reads, then one lane per warp arrives (8 arrivals per tile).
+__device__ __forceinline__ void publish(uint64_t* bar, int debug_flags) {
+  if (!(debug_flags & 32)) umma::fence_proxy_async_smem();
+  umma::tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar);
 }
 
 struct KArgs {
@@ -171,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
-    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], kEpiPerTile); umma::mbar_init(&acc_ready[t], 1); }
+    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], kEpiWarpsPerTile); umma::mbar_init(&acc_ready[t], 2); }
     umma::fence_barrier_init();
   }
   if (warp == 2) {
@@ -189,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
       for (int s = 0; s < P.n_steps; ++s) {
-        const int nch = P.steps[s].n_mt * ((P.steps[s].k_steps + 3) >> 2);
+        const int nch = P.steps[s].n_mt * (P.steps[s].k_steps >> 2);
         const uint8_t* src = a.image + (size_t)P.steps[s].chunk_begin * kChunkBytes;
         for (int t = 0; t < ntl; ++t) {
           for (int c = 0; c < nch; ++c) {
@@ -209,45 +228,54 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) ================
-    uint32_t stage = 0, phase = 0;
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers: warp 1 owns M-tile 0, warp 3 owns M-tile 1 =====================
+    // Two issuing threads because one cannot sustain an N=128 MMA every 64 cycles (measured ~110
+    // cycles of scalar/uniform work per MMA).  Different M-tiles are different accumulators, so the
+    // relative order of the two warps' MMAs is irrelevant.  Chunks are interleaved (k-chunk major,
+    // M-tile minor) in the ring: warp w consumes chunk kc*n_mt + w of every step.
+    const int my_mt = warp == 1 ? 0 : 1;
+    uint32_t stage = 0, phase = 0;     // ring position of the first chunk of the current (step, tile)
     uint32_t in_par[2] = {0, 0};
     const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
     const uint32_t ring_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::ring), 16);
+    auto advance = [&](uint32_t& st, uint32_t& ph, uint32_t n) {
+      st += n;
+      while (st >= (uint32_t)kStages) { st -= kStages; ph ^= 1; }
+    };
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
       for (int s = 0; s < P.n_steps; ++s) {
-        const int n_mt = P.steps[s].n_mt, k_steps = P.steps[s].k_steps;
-        const int nkc = (k_steps + 3) >> 2;
+        const uint32_t n_mt = P.steps[s].n_mt, nkc = P.steps[s].k_steps >> 2;
         const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, P.steps[s].n_cols, 0, 1)
                                     : umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
         for (int t = 0; t < ntl; ++t) {
           umma::mbar_wait(&in_ready[t], in_par[t]);
           in_par[t] ^= 1;
           umma::tc_fence_after();
-          const uint32_t act_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::act + t * kActBytes), kLbo);
-          for (int mt = 0; mt < n_mt; ++mt) {
-            const uint32_t d_addr = tmem_base + (uint32_t)(t * 256 + mt * 128);
-            for (int kc = 0; kc < nkc; ++kc) {
-              umma::mbar_wait(&w_full[stage], phase);
+          if ((uint32_t)my_mt < n_mt) {
+            const uint32_t act_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::act + t * kActBytes), kLbo);
+            const uint32_t d_addr = tmem_base + (uint32_t)(t * 256 + my_mt * 128);
+            uint32_t st = stage, ph = phase;
+            advance(st, ph, (uint32_t)my_mt);
+            uint32_t b_lo = act_lo;
+            for (uint32_t kc = 0; kc < nkc; ++kc) {
+              umma::mbar_wait(&w_full[st], ph);
               umma::tc_fence_after();
-              const uint32_t a_lo = ring_lo + stage * (kChunkBytes >> 4);
-              const uint32_t b_lo = act_lo + kc * (4 * 2048 >> 4);
-              const int kn = k_steps - 4 * kc;  // >= 1
+              const uint32_t a_lo = ring_lo + st * (kChunkBytes >> 4);
               if (umma::elect_one()) {
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, kc > 0 ? 1u : 0u);
-                if (kn > 1) umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
-                if (kn > 2) umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
-                if (kn > 3) umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
-                umma::mma_commit(&w_empty[stage]);
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
+                umma::mma_commit(&w_empty[st]);
               }
-              __syncwarp();
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              b_lo += 512;
+              advance(st, ph, n_mt);
             }
           }
           if (umma::elect_one()) umma::mma_commit(&acc_ready[t]);
-          __syncwarp();
+          advance(stage, phase, n_mt * nkc);
         }
       }
     }
@@ -288,9 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         for (int j = etid >> 7; j < k0; j += 2)
           store_elem<kF16>(act, j, n, j < pe_dim ? pe_row(j, P.multires, x3, ct) : 0.0f);
       }
-      umma::fence_proxy_async_smem();
-      umma::tc_fence_before();
-      umma::mbar_arrive(&in_ready[t]);
+      publish(&in_ready[t], P.debug_flags);
 
       for (int s = 0; s < P.n_steps; ++s) {
         const nr_umma_step_t& S = P.steps[s];
@@ -299,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         umma::tc_fence_after();
         const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
         const uint32_t taddr = tmem_tile + (uint32_t)(mo * 128);
+        const RowAddr ra(umma::smem_u32(act), F);
 
         if (P.debug_flags & 2) {
           // profiling: MMA + weight pipeline only
@@ -328,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (16 * h + j), -1);
                 }
-                store_row16<kF16>(act, F, 16 * h, v, no_st);
+                store_row16<kF16>(ra, 16 * h, v, no_st);
 #pragma unroll 1
                 for (int c = 1; c < 4; ++c) {
                   umma::tmem_ld16(taddr + 32 * c + 16 * h, raw);
@@ -341,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                     for (int j = 0; j < 16; ++j)
                       v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (16 * h + j), c - 1);
                   }
-                  store_row16<kF16>(act, F, 32 * c + 16 * h, v, no_st);
+                  store_row16<kF16>(ra, 32 * c + 16 * h, v, no_st);
                 }
               }
             } else {
@@ -356,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (16 * c + j), -1);
                 }
-                store_row16<kF16>(act, F, 16 * c, v, no_st);
+                store_row16<kF16>(ra, 16 * c, v, no_st);
               }
             }
           }
@@ -405,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                   if (gp < a.n) a.feat[gp * a.feat_ld + F] = v[j];
                 }
               }
-              if (S.to_rad) store_row16<kF16>(act, F, 16 * c, v);
+              if (S.to_rad) store_row16<kF16>(ra, 16 * c, v);
             }
           }
           if (S.to_rad) {
@@ -434,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               umma::tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
-              store_row16<kF16>(act, F, 16 * c, v);
+              store_row16<kF16>(ra, 16 * c, v);
             }
           }
         } else if (S.epi == EPI_RGB) {
@@ -452,11 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             }
           }
         }
-        if (s + 1 < P.n_steps) {
-          umma::fence_proxy_async_smem();
-          umma::tc_fence_before();
-          umma::mbar_arrive(&in_ready[t]);
-        }
+        if (s + 1 < P.n_steps) publish(&in_ready[t], P.debug_flags);
       }
       umma::tc_fence_before();
       named_bar_sync(1 + t, kEpiPerTile);  // staging buffers and TMEM slot free before the next tile
@@ -481,7 +504,8 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
   bool has_rad = false;
   for (int s = 0; s < prog->n_steps; ++s) {
     const nr_umma_step_t& S = prog->steps[s];
-    const int nch = S.n_mt * ((S.k_steps + 3) / 4);
+    const int nch = S.n_mt * (S.k_steps / 4);
+    NR_CHECK_ARG(S.k_steps % 4 == 0, "step %d: k_steps=%d must be a multiple of 4 (K padded to 64)", s, S.k_steps);
     NR_CHECK_ARG(S.n_mt >= 1 && S.n_mt <= 2, "step %d: n_mt=%d", s, S.n_mt);
     NR_CHECK_ARG(S.k_steps >= 1 && S.k_steps <= 32, "step %d: k_steps=%d", s, S.k_steps);
     NR_CHECK_ARG(S.n_cols == 32 || S.n_cols == 64 || S.n_cols == 128, "step %d: n_cols=%d", s, S.n_cols);

@@ -18,8 +18,9 @@ def _a_tile_index():
 
 
 def pack_a_tiles(W, n_mtiles=None, k_pad=None, dtype=torch.bfloat16):
-    """W: [rows, K] float tensor -> int16 tensor [n_mtiles * n_kchunks, 8192] of A tiles ordered
-    (mt major, kc minor); rows/K zero-padded to 128 / 64 multiples."""
+    """W: [rows, K] float tensor -> int16 tensor [n_kchunks * n_mtiles, 8192] of A tiles ordered
+    (k-chunk major, M-tile minor: the order the two MMA-issuing warps consume them);
+    rows/K zero-padded to 128 / 64 multiples."""
     rows, K = W.shape
     n_mt = n_mtiles if n_mtiles is not None else (rows + 127) // 128
     kp = k_pad if k_pad is not None else K
@@ -27,7 +28,7 @@ def pack_a_tiles(W, n_mtiles=None, k_pad=None, dtype=torch.bfloat16):
     full = torch.zeros(n_mt * 128, n_kc * 64, dtype=torch.float32, device=W.device)
     full[:rows, :K] = W.float()
     bf = full.to(dtype).view(torch.int16)
-    tiles = bf.reshape(n_mt, 128, n_kc, 64).permute(0, 2, 1, 3).reshape(n_mt * n_kc, 128 * 64)
+    tiles = bf.reshape(n_mt, 128, n_kc, 64).permute(2, 0, 1, 3).reshape(n_kc * n_mt, 128 * 64)
     idx = _a_tile_index().to(W.device).reshape(-1)
     out = torch.empty_like(tiles)
     out[:, idx] = tiles
@@ -58,8 +59,9 @@ class UmmaNet:
         self._n_chunks, self._n_bias = 0, 0
 
         def add(W, b, k_steps, n_mt):
+            assert k_steps % 4 == 0
             img = pack_a_tiles(W, n_mtiles=n_mt, k_pad=k_steps * 16, dtype=op_dtype)
-            assert img.shape[0] == n_mt * ((k_steps + 3) // 4)
+            assert img.shape[0] == n_mt * (k_steps // 4)
             bt = torch.zeros(n_mt * 128, dtype=torch.float32, device=dev)
             if b is not None:
                 bt[: b.numel()] = b.float()
@@ -80,7 +82,7 @@ class UmmaNet:
             out_d, in_d = W.shape
             if in_d > 256 or out_d > 256:
                 raise NotImplementedError("bf16 tier supports hidden widths up to 256")
-            k_steps, n_mt = (in_d + 15) // 16, (out_d + 127) // 128
+            k_steps, n_mt = (in_d + 63) // 64 * 4, (out_d + 127) // 128
             c0, b0 = add(W, b, k_steps, n_mt)
             pe_fill = 1 if (l + 1 == skip_layer) else 0
             if pe_fill and out_d + pe > 256:
@@ -89,7 +91,7 @@ class UmmaNet:
                                     out_rows=out_d, pe_fill=pe_fill, to_rad=0))
         Wl, bl = surface_W[L - 1], surface_b[L - 1]
         in_d = Wl.shape[1]
-        k_steps = (in_d + 15) // 16
+        k_steps = (in_d + 63) // 64 * 4
         c0, b0 = add(Wl[0:1].expand(32, in_d), bl[0:1].expand(32), k_steps, 1)
         self.sdf_out = dict(chunk_begin=c0, n_mt=1, k_steps=k_steps, epi=EPI_SDF_OUT, bias_off=b0, out_rows=1,
                             pe_fill=0, to_rad=0)
@@ -108,7 +110,7 @@ class UmmaNet:
                 raise NotImplementedError("bf16 tier: the fused radiance path needs W_geo_feat == 256")
             px, pv = _pe_dim(rad_multires), _pe_dim(rad_multires_view)
             n_extra = px + pv + 3
-            self.rad_extra_rows = (n_extra + 15) // 16 * 16
+            self.rad_extra_rows = (n_extra + 63) // 64 * 64
             if 256 + self.rad_extra_rows > 512:
                 raise NotImplementedError("bf16 tier: radiance input too wide")
             W0 = rad_W[0]
@@ -122,7 +124,7 @@ class UmmaNet:
                 out_d, in_d = W.shape
                 if l > 0 and in_d > 256 or out_d > 256:
                     raise NotImplementedError("bf16 tier supports radiance widths up to 256 (no skips)")
-                k_steps = (256 + self.rad_extra_rows) // 16 if l == 0 else (in_d + 15) // 16
+                k_steps = (256 + self.rad_extra_rows) // 16 if l == 0 else (in_d + 63) // 64 * 4
                 n_mt = (out_d + 127) // 128
                 c0, b0 = add(W, rad_b[l], k_steps, n_mt)
                 steps.append(dict(chunk_begin=c0, n_mt=n_mt, k_steps=k_steps, epi=EPI_RGB if l == Ls - 1 else EPI_RELU,

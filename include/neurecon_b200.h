@@ -196,6 +196,10 @@ int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t
                         int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
                         void* stream);
 
+/* profiling hook (tools/trace_mlp.py): device buffer [3][2048][4] int64 receiving clock64 stamps of the
+ * MMA <-> epilogue hand-offs of CTA 0; NULL disables. */
+int nr_mlp_umma_set_trace(void* buf);
+
 /* ------------------------------------------------------------------------------------------
  * tcgen05 self-test: D[128,N] = A[128,K] B[K,N] through the operand layouts / descriptors of
  * the fused MLP kernel.  a_image: bf16 K-major SWIZZLE_128B tiles (16 KB per 64 columns of K),

@@ -29,8 +29,8 @@ constexpr uint32_t kChunkBytes = 16384;      // one A tile: 128 features x 64 k,
 constexpr uint32_t kActBytes = 65536;        // one tile's B operand: 256 k-rows x 128 columns, bf16
 constexpr uint32_t kLbo = 32768;             // bytes between 64-column blocks of the B operand
 constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilogue warps
-constexpr int kEpiPerTile = 256;
-constexpr int kEpiWarpsPerTile = 8;
+constexpr int kEpiThreads = 512;
+constexpr int kEpiWarps = 16;
 constexpr int kEpiWarp0 = 4;
 
 enum : int32_t {
@@ -92,6 +92,29 @@ __device__ __forceinline__ float pe_row(int j, int multires, const float* x3, in
   if (comp_t != comp) return 0.0f;
   return r < 3 ? f * c : -f * s;
 }
+
+// One embedding row with its (frequency, component, function) decoded once, so that evaluating it for
+// many points costs one sincos each.
+struct PeRow {
+  int kind, comp;  // kind: 0 identity, 1 sin, 2 cos, 3 zero padding
+  float freq;
+  __device__ __forceinline__ PeRow(int j, int multires) {
+    const int pe_dim = multires < 0 ? 3 : 3 + 6 * multires;
+    if (j < 0 || j >= pe_dim) { kind = 3; comp = 0; freq = 0.f; }
+    else if (j < 3) { kind = 0; comp = j; freq = 1.f; }
+    else { const int q = (j - 3) / 6, r = (j - 3) % 6; comp = r % 3; freq = (float)(1 << q); kind = r < 3 ? 1 : 2; }
+  }
+  // value (ct < 0) or derivative w.r.t. x[ct]
+  __device__ __forceinline__ float eval(const float* x3, int ct) const {
+    if (kind == 3) return 0.f;
+    if (kind == 0) return ct < 0 ? x3[comp] : (ct == comp ? 1.f : 0.f);
+    if (ct >= 0 && ct != comp) return 0.f;
+    float sn, cs;
+    __sincosf(x3[comp] * freq, &sn, &cs);
+    if (ct < 0) return kind == 1 ? sn : cs;
+    return kind == 1 ? freq * cs : -freq * sn;
+  }
+};
 
 template <bool kF16>
 __device__ __forceinline__ void store_row32(uint8_t* act, int k, int col0, const float (&v)[32], bool skip = false) {
@@ -168,7 +191,15 @@ struct KArgs {
   float* feat;         // [n, feat_ld] or null
   int64_t feat_ld;
   float* rgb;          // [n,3] or null
+  long long* trace;    // profiling only: [3][kTraceCap][4] (event, step*2+tile, clock, pair) from CTA 0
 };
+constexpr int kTraceCap = 2048;
+__device__ __forceinline__ void trace_ev(long long* tr, int region, int& cnt, int ev, int st, long long pair) {
+  if (!tr || blockIdx.x != 0 || cnt >= kTraceCap) return;
+  long long* p = tr + ((size_t)region * kTraceCap + cnt) * 4;
+  p[0] = ev; p[1] = st; p[2] = clock64(); p[3] = pair;
+  ++cnt;
+}
 
 template <bool kF16>
 __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_constant__ DevProgram prog, const KArgs a) {
@@ -190,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
-    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], kEpiWarpsPerTile); umma::mbar_init(&acc_ready[t], 2); }
+    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], kEpiWarps); umma::mbar_init(&acc_ready[t], 2); }
     umma::fence_barrier_init();
   }
   if (warp == 2) {
@@ -235,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
     // relative order of the two warps' MMAs is irrelevant.  Chunks are interleaved (k-chunk major,
     // M-tile minor) in the ring: warp w consumes chunk kc*n_mt + w of every step.
     const int my_mt = warp == 1 ? 0 : 1;
+    int tcnt = 0;
     uint32_t stage = 0, phase = 0;     // ring position of the first chunk of the current (step, tile)
     uint32_t in_par[2] = {0, 0};
     const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
@@ -250,101 +282,141 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, P.steps[s].n_cols, 0, 1)
                                     : umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
         for (int t = 0; t < ntl; ++t) {
+          if (lane == 0) trace_ev(a.trace, my_mt, tcnt, 10, s * 2 + t, pair);
           umma::mbar_wait(&in_ready[t], in_par[t]);
           in_par[t] ^= 1;
           umma::tc_fence_after();
+          if (lane == 0) trace_ev(a.trace, my_mt, tcnt, 11, s * 2 + t, pair);
           if ((uint32_t)my_mt < n_mt) {
             const uint32_t act_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::act + t * kActBytes), kLbo);
             const uint32_t d_addr = tmem_base + (uint32_t)(t * 256 + my_mt * 128);
             uint32_t st = stage, ph = phase;
             advance(st, ph, (uint32_t)my_mt);
             uint32_t b_lo = act_lo;
+            bool ready = umma::mbar_try_wait(&w_full[st], ph);
             for (uint32_t kc = 0; kc < nkc; ++kc) {
-              umma::mbar_wait(&w_full[st], ph);
+              if (!ready) umma::mbar_wait(&w_full[st], ph);
               umma::tc_fence_after();
               const uint32_t a_lo = ring_lo + st * (kChunkBytes >> 4);
+              const uint32_t st_cur = st;
+              advance(st, ph, n_mt);
+              // probe the next chunk's barrier now: its ~100+ cycle latency overlaps the MMA issue below
+              ready = (kc + 1 < nkc) ? umma::mbar_try_wait(&w_full[st], ph) : false;
               if (umma::elect_one()) {
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, kc > 0 ? 1u : 0u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
-                umma::mma_commit(&w_empty[st]);
+                umma::mma_commit(&w_empty[st_cur]);
               }
               b_lo += 512;
-              advance(st, ph, n_mt);
             }
           }
           if (umma::elect_one()) umma::mma_commit(&acc_ready[t]);
+          if (lane == 0) trace_ev(a.trace, my_mt, tcnt, 12, s * 2 + t, pair);
           advance(stage, phase, n_mt * nkc);
         }
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue: 8 warps per tile, one warpgroup per M-tile =====================
+    // ===================== epilogue: all 16 warps serve whichever tile is ready =====================
+    // work item of a warp inside a tile-step: (M-tile mo, TMEM lane quarter q, column half h)
     const int e = warp - kEpiWarp0;                 // 0..15
-    const int t = e >> 3;                           // tile slot 0 / 1
-    const int mo = (e >> 2) & 1;                    // M-tile this warpgroup owns
+    const int h = e >> 3;                           // column half
+    const int mo = (e >> 2) & 1;                    // M-tile
     const int q = warp & 3;                         // TMEM lane quarter (hardware: warp id % 4)
-    const int etid = (e & 7) * 32 + lane;           // 0..255 inside the tile's epilogue group
-    uint8_t* act = smem + SmemLayout::act + t * kActBytes;
-    float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
-    float* vs = (float*)(smem + SmemLayout::vs) + t * 96;
-    float* nabs = (float*)(smem + SmemLayout::nabs) + t * 96;
-    const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
-    uint32_t acc_par = 0;
+    const int etid = e * 32 + lane;                 // 0..511
+    const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
+    uint32_t acc_par[2] = {0, 0};
+    int tcnt = 0;
+    const bool tracer = (e == 0 && lane == 0);
     const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
     const bool no_st = P.debug_flags & 8;
+    float* xs_all = (float*)(smem + SmemLayout::xs);
+    float* vs_all = (float*)(smem + SmemLayout::vs);
+    float* nabs_all = (float*)(smem + SmemLayout::nabs);
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int64_t tile = 2 * pair + t;
-      if (tile >= n_tiles) continue;
-      const int64_t p0 = tile * ppt;
+      const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
 
       // ---- prologue: stage the points, evaluate the embedding into operand rows [0, k0) ----
-      for (int i = etid; i < ppt * 3; i += kEpiPerTile) {
-        const int64_t gi = p0 * 3 + i;
-        xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
-        if (a.view && i < 96) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
+      for (int t = 0; t < ntl; ++t) {
+        const int64_t p0 = (2 * pair + t) * ppt;
+        float* xs = xs_all + t * 384;
+        float* vs = vs_all + t * 96;
+        for (int i = etid; i < ppt * 3; i += kEpiThreads) {
+          const int64_t gi = p0 * 3 + i;
+          xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
+          if (a.view && i < 96) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
+        }
       }
-      named_bar_sync(1 + t, kEpiPerTile);
-      {
+      named_bar_sync(1, kEpiThreads);
+      for (int t = 0; t < ntl; ++t) {
+        uint8_t* act = smem + SmemLayout::act + t * kActBytes;
+        const float* xs = xs_all + t * 384;
         const int n = etid & 127;                      // operand column
+        const int part = etid >> 7;                    // 0..3: splits the rows
         const int p = tang ? (n & 31) : n;
         const int ct = tang ? (n >> 5) - 1 : -1;       // -1: value column, 0..2: tangent component
         const float x3[3] = {xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]};
         const int k0 = P.steps[0].k_steps * 16;
-        for (int j = etid >> 7; j < k0; j += 2)
-          store_elem<kF16>(act, j, n, j < pe_dim ? pe_row(j, P.multires, x3, ct) : 0.0f);
+        if (part == 0) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) store_elem<kF16>(act, j, n, ct < 0 ? x3[j] : (ct == j ? 1.f : 0.f));
+        }
+        for (int qf = part; qf < P.multires; qf += 4) {
+          const float f = (float)(1 << qf);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sv = 0.f, cv = 0.f;
+            if (ct < 0 || ct == c) {
+              float sn, cs;
+              __sincosf(x3[c] * f, &sn, &cs);
+              sv = ct < 0 ? sn : f * cs;
+              cv = ct < 0 ? cs : -f * sn;
+            }
+            store_elem<kF16>(act, 3 + 6 * qf + c, n, sv);
+            store_elem<kF16>(act, 3 + 6 * qf + 3 + c, n, cv);
+          }
+        }
+        for (int j = pe_dim + part; j < k0; j += 4) store_elem<kF16>(act, j, n, 0.f);
+        publish(&in_ready[t], P.debug_flags);
       }
-      publish(&in_ready[t], P.debug_flags);
 
       for (int s = 0; s < P.n_steps; ++s) {
         const nr_umma_step_t& S = P.steps[s];
-        umma::mbar_wait(&acc_ready[t], acc_par);
-        acc_par ^= 1;
-        umma::tc_fence_after();
-        const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
-        const uint32_t taddr = tmem_tile + (uint32_t)(mo * 128);
-        const RowAddr ra(umma::smem_u32(act), F);
+        for (int t = 0; t < ntl; ++t) {
+          const int64_t p0 = (2 * pair + t) * ppt;
+          uint8_t* act = smem + SmemLayout::act + t * kActBytes;
+          const float* xs = xs_all + t * 384;
+          const float* vs = vs_all + t * 96;
+          float* nabs = nabs_all + t * 96;
+          const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
+          const uint32_t taddr = tmem_tile + (uint32_t)(mo * 128);
+          const RowAddr ra(umma::smem_u32(act), F);
+          if (tracer) trace_ev(a.trace, 2, tcnt, 20, s * 2 + t, pair);
+          umma::mbar_wait(&acc_ready[t], acc_par[t]);
+          acc_par[t] ^= 1;
+          umma::tc_fence_after();
+          if (tracer) trace_ev(a.trace, 2, tcnt, 21, s * 2 + t, pair);
 
-        if (P.debug_flags & 2) {
-          // profiling: MMA + weight pipeline only
-        } else if (S.epi == EPI_HIDDEN) {
-          if (mo < S.n_mt) {
-            const float b = a.bias[S.bias_off + F];
-            const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
-            uint32_t raw[16];
-            float v[16];
-            if (P.debug_flags & 4) {
-              for (int c = 0; c < 8; ++c) {
-                umma::tmem_ld16(taddr + 16 * c, raw);
-                umma::tmem_ld_wait();
-                if (__uint_as_float(raw[0]) == 123.456f) act[0] = 1;
-              }
-            } else if (tang) {
-              // columns: [0,32) values of 32 points, [32c, 32c+32) d/dx_c; processed in two 16-point halves
-#pragma unroll 1
-              for (int h = 0; h < 2; ++h) {
+          if (P.debug_flags & 2) {
+            // profiling: MMA + weight pipeline only
+          } else if (S.epi == EPI_HIDDEN) {
+            if (mo < S.n_mt) {
+              const float b = a.bias[S.bias_off + F];
+              const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
+              const PeRow pr(is_pe ? F - S.out_rows : -1, P.multires);
+              uint32_t raw[16];
+              float v[16];
+              if (P.debug_flags & 4) {
+                for (int c = 0; c < 4; ++c) {
+                  umma::tmem_ld16(taddr + 16 * (4 * h + c), raw);
+                  umma::tmem_ld_wait();
+                  if (__uint_as_float(raw[0]) == 123.456f) act[0] = 1;
+                }
+              } else if (tang) {
+                // columns [0,32): values of 32 points, [32c, 32c+32): d/dx_c; this warp owns points [16h, 16h+16)
                 float sg[16];
                 umma::tmem_ld16(taddr + 16 * h, raw);
                 umma::tmem_ld_wait();
@@ -352,8 +424,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll
                   for (int j = 0; j < 16; ++j) softplus100_fast(__uint_as_float(raw[j]) + b, v[j], sg[j]);
                 } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (16 * h + j), -1);
+#pragma unroll 4
+                  for (int j = 0; j < 16; ++j) v[j] = pr.eval(xs + 3 * (16 * h + j), -1);
                 }
                 store_row16<kF16>(ra, 16 * h, v, no_st);
 #pragma unroll 1
@@ -364,125 +436,124 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * sg[j];
                   } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                      v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (16 * h + j), c - 1);
+#pragma unroll 4
+                    for (int j = 0; j < 16; ++j) v[j] = pr.eval(xs + 3 * (16 * h + j), c - 1);
                   }
                   store_row16<kF16>(ra, 32 * c + 16 * h, v, no_st);
                 }
-              }
-            } else {
+              } else {
 #pragma unroll 1
-              for (int c = 0; c < 8; ++c) {
+                for (int c = 4 * h; c < 4 * h + 4; ++c) {
+                  umma::tmem_ld16(taddr + 16 * c, raw);
+                  umma::tmem_ld_wait();
+                  if (!is_pe) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
+                  } else {
+#pragma unroll 4
+                    for (int j = 0; j < 16; ++j) v[j] = pr.eval(xs + 3 * (16 * c + j), -1);
+                  }
+                  store_row16<kF16>(ra, 16 * c, v, no_st);
+                }
+              }
+            }
+          } else if (S.epi == EPI_SDF_OUT) {
+            // rows 0..31 of this M-tile all hold the sdf row: lane l keeps column l of each 32-column chunk;
+            // the two (mo = 0, q = 0) warps take two chunks each
+            if (mo == 0 && q == 0) {
+              const float b = a.bias[S.bias_off];
+#pragma unroll 1
+              for (int c = 2 * h; c < 2 * h + 2; ++c) {
+                uint32_t raw[32];
+                umma::tmem_ld32(tmem_tile + 32 * c, raw);
+                umma::tmem_ld_wait();
+                float mine = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mine = (lane == j) ? __uint_as_float(raw[j]) : mine;
+                if (tang) {
+                  const int64_t gp = p0 + lane;
+                  if (c == 0) {
+                    if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
+                  } else {
+                    nabs[3 * lane + (c - 1)] = mine;
+                    if (a.nabla && gp < a.n) a.nabla[gp * 3 + (c - 1)] = mine;
+                  }
+                } else {
+                  const int64_t gp = p0 + 32 * c + lane;
+                  if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
+                }
+              }
+            }
+          } else if (S.epi == EPI_FEAT) {
+            if (mo < S.n_mt) {
+              const float b = a.bias[S.bias_off + F];
+              const int nchunk = S.n_cols >> 4;
+#pragma unroll 1
+              for (int c = h; c < nchunk; c += 2) {
+                uint32_t raw[16];
+                float v[16];
                 umma::tmem_ld16(taddr + 16 * c, raw);
                 umma::tmem_ld_wait();
-                if (!is_pe) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
-                } else {
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + b;
+                if (a.feat && F < S.out_rows) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = pe_row(F - S.out_rows, P.multires, xs + 3 * (16 * c + j), -1);
+                  for (int j = 0; j < 16; ++j) {
+                    const int64_t gp = p0 + 16 * c + j;
+                    if (gp < a.n) a.feat[gp * a.feat_ld + F] = v[j];
+                  }
                 }
-                store_row16<kF16>(ra, 16 * c, v, no_st);
+                if (S.to_rad) store_row16<kF16>(ra, 16 * c, v);
               }
             }
-          }
-        } else if (S.epi == EPI_SDF_OUT) {
-          // rows 0..31 of this M-tile all hold the sdf row: lane l keeps column l of each 32-column chunk
-          if (mo == 0 && q == 0) {
-            const float b = a.bias[S.bias_off];
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t raw[32];
-              umma::tmem_ld32(tmem_tile + 32 * c, raw);
-              umma::tmem_ld_wait();
-              float mine = 0.0f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) mine = (lane == j) ? __uint_as_float(raw[j]) : mine;
-              if (tang) {
-                const int64_t gp = p0 + lane;
-                if (c == 0) {
-                  if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
-                } else {
-                  nabs[3 * lane + (c - 1)] = mine;
-                  if (a.nabla && gp < a.n) a.nabla[gp * 3 + (c - 1)] = mine;
-                }
-              } else {
-                const int64_t gp = p0 + 32 * c + lane;
-                if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
+            if (S.to_rad) {
+              // operand rows [256, 256 + extras): [PE(x) | PE(view) | normals | 0-pad]  (tangent tiles)
+              named_bar_sync(1, kEpiThreads);  // normal stash of EPI_SDF_OUT visible
+              const int p = etid & 31, g = etid >> 5;
+              const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
+              const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
+              const int extra = P.rad_extra_rows;
+              for (int r = g; r < extra; r += 16) {
+                float val = 0.0f;
+                if (r < px) val = PeRow(r, P.rad_multires).eval(xs + 3 * p, -1);
+                else if (r < px + pv) val = PeRow(r - px, P.rad_multires_view).eval(vs + 3 * p, -1);
+                else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
+                store_elem<kF16>(act, 256 + r, p, val);
               }
             }
-          }
-        } else if (S.epi == EPI_FEAT) {
-          if (mo < S.n_mt) {
-            const float b = a.bias[S.bias_off + F];
-            const int nchunk = S.n_cols >> 4;
-#pragma unroll 1
-            for (int c = 0; c < nchunk; ++c) {
+          } else if (S.epi == EPI_RELU) {
+            if (mo < S.n_mt) {
+              const float b = a.bias[S.bias_off + F];
               uint32_t raw[16];
               float v[16];
-              umma::tmem_ld16(taddr + 16 * c, raw);
-              umma::tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + b;
-              if (a.feat && F < S.out_rows) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int64_t gp = p0 + 16 * c + j;
-                  if (gp < a.n) a.feat[gp * a.feat_ld + F] = v[j];
-                }
-              }
-              if (S.to_rad) store_row16<kF16>(ra, 16 * c, v);
-            }
-          }
-          if (S.to_rad) {
-            // operand rows [256, 256 + extras): [PE(x) | PE(view) | normals | 0-pad]  (tangent tiles)
-            named_bar_sync(1 + t, kEpiPerTile);  // normal stash of EPI_SDF_OUT visible
-            const int p = etid & 31, g = etid >> 5;
-            const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
-            const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
-            const int extra = P.rad_extra_rows;
-            for (int r = g; r < extra; r += 8) {
-              float val = 0.0f;
-              if (r < px) val = pe_row(r, P.rad_multires, xs + 3 * p, -1);
-              else if (r < px + pv) val = pe_row(r - px, P.rad_multires_view, vs + 3 * p, -1);
-              else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
-              store_elem<kF16>(act, 256 + r, p, val);
-            }
-          }
-        } else if (S.epi == EPI_RELU) {
-          if (mo < S.n_mt) {
-            const float b = a.bias[S.bias_off + F];
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-              uint32_t raw[16];
-              float v[16];
-              umma::tmem_ld16(taddr + 16 * c, raw);
+              umma::tmem_ld16(taddr + 16 * h, raw);
               umma::tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
-              store_row16<kF16>(ra, 16 * c, v);
+              store_row16<kF16>(ra, 16 * h, v);
             }
-          }
-        } else if (S.epi == EPI_RGB) {
-          if (mo == 0 && q == 0) {
-            uint32_t raw[32];
-            umma::tmem_ld32(tmem_tile, raw);
-            umma::tmem_ld_wait();
-            if (lane < 3 && a.rgb) {
-              const float b = a.bias[S.bias_off + lane];
+          } else if (S.epi == EPI_RGB) {
+            if (mo == 0 && q == 0 && h == 0) {
+              uint32_t raw[32];
+              umma::tmem_ld32(tmem_tile, raw);
+              umma::tmem_ld_wait();
+              if (lane < 3 && a.rgb) {
+                const float b = a.bias[S.bias_off + lane];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int64_t gp = p0 + j;
-                if (gp < a.n) a.rgb[gp * 3 + lane] = sigmoid_fast(__uint_as_float(raw[j]) + b);
+                for (int j = 0; j < 32; ++j) {
+                  const int64_t gp = p0 + j;
+                  if (gp < a.n) a.rgb[gp * 3 + lane] = sigmoid_fast(__uint_as_float(raw[j]) + b);
+                }
               }
             }
           }
+          if (tracer) trace_ev(a.trace, 2, tcnt, 22, s * 2 + t, pair);
+          if (s + 1 < P.n_steps) publish(&in_ready[t], P.debug_flags);
+          if (tracer) trace_ev(a.trace, 2, tcnt, 23, s * 2 + t, pair);
         }
-        if (s + 1 < P.n_steps) publish(&in_ready[t], P.debug_flags);
       }
       umma::tc_fence_before();
-      named_bar_sync(1 + t, kEpiPerTile);  // staging buffers and TMEM slot free before the next tile
+      named_bar_sync(1, kEpiThreads);  // staging buffers and TMEM slots free before the next pair
     }
   }
 
@@ -492,6 +563,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 }
 
 }  // namespace
+
+static long long* g_trace = nullptr;
+// profiling hook: timestamps of the MMA <-> epilogue hand-offs of CTA 0 ([3][2048][4] int64, device memory)
+extern "C" int nr_mlp_umma_set_trace(void* buf) { g_trace = (long long*)buf; return NR_OK; }
 
 extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
                                    const float* bias, size_t bias_floats, const float* x, const float* view,
@@ -535,7 +610,7 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
   }
   DevProgram dp;
   dp.p = *prog;
-  KArgs ka{(const uint8_t*)image, bias, x, view, n, sdf, nabla, feat, feat_ld, rgb};
+  KArgs ka{(const uint8_t*)image, bias, x, view, n, sdf, nabla, feat, feat_ld, rgb, g_trace};
   if (prog->operand_f16) mlp_umma_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
   else mlp_umma_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
   NR_CHECK_LAUNCH("mlp_umma_kernel");

@@ -29,8 +29,8 @@ constexpr uint32_t kChunkBytes = 16384;      // one A tile: 128 features x 64 k,
 constexpr uint32_t kActBytes = 65536;        // one tile's B operand: 256 k-rows x 128 columns, bf16
 constexpr uint32_t kLbo = 32768;             // bytes between 64-column blocks of the B operand
 constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilogue warps
-constexpr int kEpiThreads = 512;
-constexpr int kEpiWarps = 16;
+constexpr int kEpiPerTile = 256;
+constexpr int kEpiWarpsPerTile = 8;
 constexpr int kEpiWarp0 = 4;
 
 enum : int32_t {
@@ -60,19 +60,30 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// softplus(beta=100, threshold=20) and its derivative sigmoid(100 z)
+// softplus(beta=100) and its derivative sigmoid(100 z) with 2 MUFU ops (B200 issues 8 MUFU/clk/SM, the
+// scarcest pipe of this kernel):  ln(1 + e^t) = max(t, 0) + log1p(u),  u = e^{-|t|} in (0, 1];
+// log1p(u) = u * P5(u) (Chebyshev fit, |err| < 6.1e-6, i.e. < 6.1e-8 after the 1/100);
+// sigmoid(t) = r for t >= 0 and u * r otherwise, r = 1 / (1 + u).  The threshold-20 linear branch of
+// nn.Softplus needs no select: beyond it log1p(u) < 2.1e-9.
+__device__ __forceinline__ float log1p_poly(float u) {
+  float p = -0.02397957257926464f;
+  p = fmaf(p, u, 0.10150004923343658f);
+  p = fmaf(p, u, -0.2102936953306198f);
+  p = fmaf(p, u, 0.3252951502799988f);
+  p = fmaf(p, u, -0.49937260150909424f);
+  p = fmaf(p, u, 0.9999918341636658f);
+  return p * u;
+}
 __device__ __forceinline__ void softplus100_fast(float z, float& sp, float& sg) {
   const float tl = z * 144.26950408889634f;      // 100 z log2(e)
-  const float e = ex2_approx(tl);
-  const float d = 1.0f + e;
-  const float l = lg2_approx(d) * 0.0069314718055994531f;  // ln2 / 100
-  sp = tl > 28.853900817779268f ? z : l;         // 100 z > 20
-  sg = 1.0f - rcp_approx(d);
+  const float u = ex2_approx(-fabsf(tl));
+  sp = fmaf(log1p_poly(u), 0.01f, fmaxf(z, 0.0f));
+  const float r = rcp_approx(1.0f + u);
+  sg = z >= 0.0f ? r : u * r;
 }
 __device__ __forceinline__ float softplus100_fast(float z) {
-  const float tl = z * 144.26950408889634f;
-  const float l = lg2_approx(1.0f + ex2_approx(tl)) * 0.0069314718055994531f;
-  return tl > 28.853900817779268f ? z : l;
+  const float u = ex2_approx(-fabsf(z * 144.26950408889634f));
+  return fmaf(log1p_poly(u), 0.01f, fmaxf(z, 0.0f));
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
@@ -221,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
-    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], kEpiWarps); umma::mbar_init(&acc_ready[t], 2); }
+    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], kEpiWarpsPerTile); umma::mbar_init(&acc_ready[t], 2); }
     umma::fence_barrier_init();
   }
   if (warp == 2) {
@@ -319,43 +330,41 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue: all 16 warps serve whichever tile is ready =====================
-    // work item of a warp inside a tile-step: (M-tile mo, TMEM lane quarter q, column half h)
+    // ===================== epilogue: 8 warps per tile, one warpgroup per M-tile =====================
     const int e = warp - kEpiWarp0;                 // 0..15
-    const int h = e >> 3;                           // column half
-    const int mo = (e >> 2) & 1;                    // M-tile
+    const int t = e >> 3;                           // tile slot 0 / 1
+    const int mo = (e >> 2) & 1;                    // M-tile this warpgroup owns
     const int q = warp & 3;                         // TMEM lane quarter (hardware: warp id % 4)
-    const int etid = e * 32 + lane;                 // 0..511
+    const int etid = (e & 7) * 32 + lane;           // 0..255 inside the tile's epilogue group
     const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
-    uint32_t acc_par[2] = {0, 0};
+    uint8_t* act = smem + SmemLayout::act + t * kActBytes;
+    float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
+    float* vs = (float*)(smem + SmemLayout::vs) + t * 96;
+    float* nabs = (float*)(smem + SmemLayout::nabs) + t * 96;
+    const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
+    const uint32_t taddr = tmem_tile + (uint32_t)(mo * 128);
+    const RowAddr ra(umma::smem_u32(act), F);
+    uint32_t acc_par = 0;
     int tcnt = 0;
-    const bool tracer = (e == 0 && lane == 0);
+    const bool tracer = (mo == 0 && q == 0 && lane == 0 && t == 0);
     const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
     const bool no_st = P.debug_flags & 8;
-    float* xs_all = (float*)(smem + SmemLayout::xs);
-    float* vs_all = (float*)(smem + SmemLayout::vs);
-    float* nabs_all = (float*)(smem + SmemLayout::nabs);
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
+      const int64_t tile = 2 * pair + t;
+      if (tile >= n_tiles) continue;
+      const int64_t p0 = tile * ppt;
 
       // ---- prologue: stage the points, evaluate the embedding into operand rows [0, k0) ----
-      for (int t = 0; t < ntl; ++t) {
-        const int64_t p0 = (2 * pair + t) * ppt;
-        float* xs = xs_all + t * 384;
-        float* vs = vs_all + t * 96;
-        for (int i = etid; i < ppt * 3; i += kEpiThreads) {
-          const int64_t gi = p0 * 3 + i;
-          xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
-          if (a.view && i < 96) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
-        }
+      for (int i = etid; i < ppt * 3; i += kEpiPerTile) {
+        const int64_t gi = p0 * 3 + i;
+        xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
+        if (a.view && i < 96) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
       }
-      named_bar_sync(1, kEpiThreads);
-      for (int t = 0; t < ntl; ++t) {
-        uint8_t* act = smem + SmemLayout::act + t * kActBytes;
-        const float* xs = xs_all + t * 384;
+      named_bar_sync(1 + t, kEpiPerTile);
+      {
         const int n = etid & 127;                      // operand column
-        const int part = etid >> 7;                    // 0..3: splits the rows
+        const int part = etid >> 7;                    // 0..1: splits the rows
         const int p = tang ? (n & 31) : n;
         const int ct = tang ? (n >> 5) - 1 : -1;       // -1: value column, 0..2: tangent component
         const float x3[3] = {xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]};
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 3; ++j) store_elem<kF16>(act, j, n, ct < 0 ? x3[j] : (ct == j ? 1.f : 0.f));
         }
-        for (int qf = part; qf < P.multires; qf += 4) {
+        for (int qf = part; qf < P.multires; qf += 2) {   // one sincos per (frequency, component)
           const float f = (float)(1 << qf);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -379,44 +388,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             store_elem<kF16>(act, 3 + 6 * qf + 3 + c, n, cv);
           }
         }
-        for (int j = pe_dim + part; j < k0; j += 4) store_elem<kF16>(act, j, n, 0.f);
-        publish(&in_ready[t], P.debug_flags);
+        for (int j = pe_dim + part; j < k0; j += 2) store_elem<kF16>(act, j, n, 0.f);
       }
+      publish(&in_ready[t], P.debug_flags);
 
       for (int s = 0; s < P.n_steps; ++s) {
         const nr_umma_step_t& S = P.steps[s];
-        for (int t = 0; t < ntl; ++t) {
-          const int64_t p0 = (2 * pair + t) * ppt;
-          uint8_t* act = smem + SmemLayout::act + t * kActBytes;
-          const float* xs = xs_all + t * 384;
-          const float* vs = vs_all + t * 96;
-          float* nabs = nabs_all + t * 96;
-          const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
-          const uint32_t taddr = tmem_tile + (uint32_t)(mo * 128);
-          const RowAddr ra(umma::smem_u32(act), F);
-          if (tracer) trace_ev(a.trace, 2, tcnt, 20, s * 2 + t, pair);
-          umma::mbar_wait(&acc_ready[t], acc_par[t]);
-          acc_par[t] ^= 1;
-          umma::tc_fence_after();
-          if (tracer) trace_ev(a.trace, 2, tcnt, 21, s * 2 + t, pair);
+        if (tracer) trace_ev(a.trace, 2, tcnt, 20, s * 2 + t, pair);
+        umma::mbar_wait(&acc_ready[t], acc_par);
+        acc_par ^= 1;
+        umma::tc_fence_after();
+        if (tracer) trace_ev(a.trace, 2, tcnt, 21, s * 2 + t, pair);
 
-          if (P.debug_flags & 2) {
-            // profiling: MMA + weight pipeline only
-          } else if (S.epi == EPI_HIDDEN) {
-            if (mo < S.n_mt) {
-              const float b = a.bias[S.bias_off + F];
-              const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
-              const PeRow pr(is_pe ? F - S.out_rows : -1, P.multires);
-              uint32_t raw[16];
-              float v[16];
-              if (P.debug_flags & 4) {
-                for (int c = 0; c < 4; ++c) {
-                  umma::tmem_ld16(taddr + 16 * (4 * h + c), raw);
-                  umma::tmem_ld_wait();
-                  if (__uint_as_float(raw[0]) == 123.456f) act[0] = 1;
-                }
-              } else if (tang) {
-                // columns [0,32): values of 32 points, [32c, 32c+32): d/dx_c; this warp owns points [16h, 16h+16)
+        if (P.debug_flags & 2) {
+          // profiling: MMA + weight pipeline only
+        } else if (S.epi == EPI_HIDDEN) {
+          if (mo < S.n_mt) {
+            const float b = a.bias[S.bias_off + F];
+            const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
+            const PeRow pr(is_pe ? F - S.out_rows : -1, P.multires);
+            uint32_t raw[16];
+            float v[16];
+            if (P.debug_flags & 4) {
+              for (int c = 0; c < 8; ++c) {
+                umma::tmem_ld16(taddr + 16 * c, raw);
+                umma::tmem_ld_wait();
+                if (__uint_as_float(raw[0]) == 123.456f) act[0] = 1;
+              }
+            } else if (tang) {
+              // columns [0,32): values of 32 points, [32c, 32c+32): d/dx_c; two 16-point halves
+#pragma unroll 1
+              for (int h = 0; h < 2; ++h) {
                 float sg[16];
                 umma::tmem_ld16(taddr + 16 * h, raw);
                 umma::tmem_ld_wait();
@@ -441,119 +443,121 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                   }
                   store_row16<kF16>(ra, 32 * c + 16 * h, v, no_st);
                 }
-              } else {
-#pragma unroll 1
-                for (int c = 4 * h; c < 4 * h + 4; ++c) {
-                  umma::tmem_ld16(taddr + 16 * c, raw);
-                  umma::tmem_ld_wait();
-                  if (!is_pe) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
-                  } else {
-#pragma unroll 4
-                    for (int j = 0; j < 16; ++j) v[j] = pr.eval(xs + 3 * (16 * c + j), -1);
-                  }
-                  store_row16<kF16>(ra, 16 * c, v, no_st);
-                }
               }
-            }
-          } else if (S.epi == EPI_SDF_OUT) {
-            // rows 0..31 of this M-tile all hold the sdf row: lane l keeps column l of each 32-column chunk;
-            // the two (mo = 0, q = 0) warps take two chunks each
-            if (mo == 0 && q == 0) {
-              const float b = a.bias[S.bias_off];
+            } else {
 #pragma unroll 1
-              for (int c = 2 * h; c < 2 * h + 2; ++c) {
-                uint32_t raw[32];
-                umma::tmem_ld32(tmem_tile + 32 * c, raw);
-                umma::tmem_ld_wait();
-                float mine = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) mine = (lane == j) ? __uint_as_float(raw[j]) : mine;
-                if (tang) {
-                  const int64_t gp = p0 + lane;
-                  if (c == 0) {
-                    if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
-                  } else {
-                    nabs[3 * lane + (c - 1)] = mine;
-                    if (a.nabla && gp < a.n) a.nabla[gp * 3 + (c - 1)] = mine;
-                  }
-                } else {
-                  const int64_t gp = p0 + 32 * c + lane;
-                  if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
-                }
-              }
-            }
-          } else if (S.epi == EPI_FEAT) {
-            if (mo < S.n_mt) {
-              const float b = a.bias[S.bias_off + F];
-              const int nchunk = S.n_cols >> 4;
-#pragma unroll 1
-              for (int c = h; c < nchunk; c += 2) {
-                uint32_t raw[16];
-                float v[16];
+              for (int c = 0; c < 8; ++c) {
                 umma::tmem_ld16(taddr + 16 * c, raw);
                 umma::tmem_ld_wait();
+                if (!is_pe) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + b;
-                if (a.feat && F < S.out_rows) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const int64_t gp = p0 + 16 * c + j;
-                    if (gp < a.n) a.feat[gp * a.feat_ld + F] = v[j];
-                  }
+                  for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
+                } else {
+#pragma unroll 4
+                  for (int j = 0; j < 16; ++j) v[j] = pr.eval(xs + 3 * (16 * c + j), -1);
                 }
-                if (S.to_rad) store_row16<kF16>(ra, 16 * c, v);
-              }
-            }
-            if (S.to_rad) {
-              // operand rows [256, 256 + extras): [PE(x) | PE(view) | normals | 0-pad]  (tangent tiles)
-              named_bar_sync(1, kEpiThreads);  // normal stash of EPI_SDF_OUT visible
-              const int p = etid & 31, g = etid >> 5;
-              const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
-              const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
-              const int extra = P.rad_extra_rows;
-              for (int r = g; r < extra; r += 16) {
-                float val = 0.0f;
-                if (r < px) val = PeRow(r, P.rad_multires).eval(xs + 3 * p, -1);
-                else if (r < px + pv) val = PeRow(r - px, P.rad_multires_view).eval(vs + 3 * p, -1);
-                else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
-                store_elem<kF16>(act, 256 + r, p, val);
-              }
-            }
-          } else if (S.epi == EPI_RELU) {
-            if (mo < S.n_mt) {
-              const float b = a.bias[S.bias_off + F];
-              uint32_t raw[16];
-              float v[16];
-              umma::tmem_ld16(taddr + 16 * h, raw);
-              umma::tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
-              store_row16<kF16>(ra, 16 * h, v);
-            }
-          } else if (S.epi == EPI_RGB) {
-            if (mo == 0 && q == 0 && h == 0) {
-              uint32_t raw[32];
-              umma::tmem_ld32(tmem_tile, raw);
-              umma::tmem_ld_wait();
-              if (lane < 3 && a.rgb) {
-                const float b = a.bias[S.bias_off + lane];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int64_t gp = p0 + j;
-                  if (gp < a.n) a.rgb[gp * 3 + lane] = sigmoid_fast(__uint_as_float(raw[j]) + b);
-                }
+                store_row16<kF16>(ra, 16 * c, v, no_st);
               }
             }
           }
-          if (tracer) trace_ev(a.trace, 2, tcnt, 22, s * 2 + t, pair);
-          if (s + 1 < P.n_steps) publish(&in_ready[t], P.debug_flags);
-          if (tracer) trace_ev(a.trace, 2, tcnt, 23, s * 2 + t, pair);
+        } else if (S.epi == EPI_SDF_OUT) {
+          // rows 0..31 of this M-tile all hold the sdf row: lane l keeps column l of each 32-column chunk
+          if (mo == 0 && q == 0) {
+            const float b = a.bias[S.bias_off];
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t raw[32];
+              umma::tmem_ld32(tmem_tile + 32 * c, raw);
+              umma::tmem_ld_wait();
+              float mine = 0.0f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mine = (lane == j) ? __uint_as_float(raw[j]) : mine;
+              if (tang) {
+                const int64_t gp = p0 + lane;
+                if (c == 0) {
+                  if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
+                } else {
+                  nabs[3 * lane + (c - 1)] = mine;
+                  if (a.nabla && gp < a.n) a.nabla[gp * 3 + (c - 1)] = mine;
+                }
+              } else {
+                const int64_t gp = p0 + 32 * c + lane;
+                if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
+              }
+            }
+          }
+        } else if (S.epi == EPI_FEAT) {
+          if (mo < S.n_mt) {
+            const float b = a.bias[S.bias_off + F];
+            const int nchunk = S.n_cols >> 4;
+#pragma unroll 1
+            for (int c = 0; c < nchunk; ++c) {
+              uint32_t raw[16];
+              float v[16];
+              umma::tmem_ld16(taddr + 16 * c, raw);
+              umma::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + b;
+              if (a.feat && F < S.out_rows) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int64_t gp = p0 + 16 * c + j;
+                  if (gp < a.n) a.feat[gp * a.feat_ld + F] = v[j];
+                }
+              }
+              if (S.to_rad) store_row16<kF16>(ra, 16 * c, v);
+            }
+          }
+          if (S.to_rad) {
+            // operand rows [256, 256 + extras): [PE(x) | PE(view) | normals | 0-pad]  (tangent tiles)
+            named_bar_sync(1 + t, kEpiPerTile);  // normal stash of EPI_SDF_OUT visible
+            const int p = etid & 31, g = etid >> 5;
+            const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
+            const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
+            const int extra = P.rad_extra_rows;
+            for (int r = g; r < extra; r += 8) {
+              float val = 0.0f;
+              if (r < px) val = PeRow(r, P.rad_multires).eval(xs + 3 * p, -1);
+              else if (r < px + pv) val = PeRow(r - px, P.rad_multires_view).eval(vs + 3 * p, -1);
+              else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
+              store_elem<kF16>(act, 256 + r, p, val);
+            }
+          }
+        } else if (S.epi == EPI_RELU) {
+          if (mo < S.n_mt) {
+            const float b = a.bias[S.bias_off + F];
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              uint32_t raw[16];
+              float v[16];
+              umma::tmem_ld16(taddr + 16 * c, raw);
+              umma::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
+              store_row16<kF16>(ra, 16 * c, v);
+            }
+          }
+        } else if (S.epi == EPI_RGB) {
+          if (mo == 0 && q == 0) {
+            uint32_t raw[32];
+            umma::tmem_ld32(tmem_tile, raw);
+            umma::tmem_ld_wait();
+            if (lane < 3 && a.rgb) {
+              const float b = a.bias[S.bias_off + lane];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int64_t gp = p0 + j;
+                if (gp < a.n) a.rgb[gp * 3 + lane] = sigmoid_fast(__uint_as_float(raw[j]) + b);
+              }
+            }
+          }
         }
+        if (tracer) trace_ev(a.trace, 2, tcnt, 22, s * 2 + t, pair);
+        if (s + 1 < P.n_steps) publish(&in_ready[t], P.debug_flags);
+        if (tracer) trace_ev(a.trace, 2, tcnt, 23, s * 2 + t, pair);
       }
       umma::tc_fence_before();
-      named_bar_sync(1, kEpiThreads);  // staging buffers and TMEM slots free before the next pair
+      named_bar_sync(1 + t, kEpiPerTile);  // staging buffers and TMEM slot free before the next tile
     }
   }
 

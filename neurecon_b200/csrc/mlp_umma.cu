@@ -2,7 +2,7 @@
 //
 // Orientation: D[feature, column] = W[feature, k] * H[k, column].
 //   * A operand = weights, streamed per layer from a pre-swizzled bf16 image in global memory
-//     (L2 resident, ~1.6 MB) by 16 KB bulk async copies (TMA unit) into a 5-stage smem ring.
+//     (L2 resident, ~1.6 MB) by 16 KB bulk async copies (TMA unit) into a 4-stage smem ring.
 //   * B operand = activations, RESIDENT in shared memory for the whole network: every layer's
 //     epilogue writes the next layer's operand in place (MN-major, 128-byte swizzle), so hidden
 //     activations never touch HBM.  PE is evaluated on-chip from the 12-byte point.
@@ -24,7 +24,8 @@
 
 namespace {
 
-constexpr int kStages = 5;
+constexpr int kStages = 4;
+constexpr int kPeStashRows = 40;          // embedding rows kept for the skip layer (multires <= 6)
 constexpr uint32_t kChunkBytes = 16384;      // one A tile: 128 features x 64 k, bf16
 constexpr uint32_t kActBytes = 65536;        // one tile's B operand: 256 k-rows x 128 columns, bf16
 constexpr uint32_t kLbo = 32768;             // bytes between 64-column blocks of the B operand
@@ -52,7 +53,8 @@ struct SmemLayout {
   static constexpr uint32_t xs = ring + kStages * kChunkBytes;       // 2 x 128 x 3 floats
   static constexpr uint32_t vs = xs + 2 * 384 * 4;                   // 2 x 32 x 3 floats (view dirs)
   static constexpr uint32_t nabs = vs + 2 * 96 * 4;                  // 2 x 32 x 3 floats (normal stash)
-  static constexpr uint32_t bars = nabs + 2 * 96 * 4;                // mbarriers
+  static constexpr uint32_t pes = nabs + 2 * 96 * 4;                 // 2 x 40 rows x 256 B: embedding stash (skip)
+  static constexpr uint32_t bars = pes + 2 * kPeStashRows * 256;     // mbarriers
   static constexpr uint32_t total = bars + 256;
 };
 
@@ -60,30 +62,19 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// softplus(beta=100) and its derivative sigmoid(100 z) with 2 MUFU ops (B200 issues 8 MUFU/clk/SM, the
-// scarcest pipe of this kernel):  ln(1 + e^t) = max(t, 0) + log1p(u),  u = e^{-|t|} in (0, 1];
-// log1p(u) = u * P5(u) (Chebyshev fit, |err| < 6.1e-6, i.e. < 6.1e-8 after the 1/100);
-// sigmoid(t) = r for t >= 0 and u * r otherwise, r = 1 / (1 + u).  The threshold-20 linear branch of
-// nn.Softplus needs no select: beyond it log1p(u) < 2.1e-9.
-__device__ __forceinline__ float log1p_poly(float u) {
-  float p = -0.02397957257926464f;
-  p = fmaf(p, u, 0.10150004923343658f);
-  p = fmaf(p, u, -0.2102936953306198f);
-  p = fmaf(p, u, 0.3252951502799988f);
-  p = fmaf(p, u, -0.49937260150909424f);
-  p = fmaf(p, u, 0.9999918341636658f);
-  return p * u;
-}
+// softplus(beta=100, threshold=20) and its derivative sigmoid(100 z)
 __device__ __forceinline__ void softplus100_fast(float z, float& sp, float& sg) {
   const float tl = z * 144.26950408889634f;      // 100 z log2(e)
-  const float u = ex2_approx(-fabsf(tl));
-  sp = fmaf(log1p_poly(u), 0.01f, fmaxf(z, 0.0f));
-  const float r = rcp_approx(1.0f + u);
-  sg = z >= 0.0f ? r : u * r;
+  const float e = ex2_approx(tl);
+  const float d = 1.0f + e;
+  const float l = lg2_approx(d) * 0.0069314718055994531f;  // ln2 / 100
+  sp = tl > 28.853900817779268f ? z : l;         // 100 z > 20
+  sg = 1.0f - rcp_approx(d);
 }
 __device__ __forceinline__ float softplus100_fast(float z) {
-  const float u = ex2_approx(-fabsf(z * 144.26950408889634f));
-  return fmaf(log1p_poly(u), 0.01f, fmaxf(z, 0.0f));
+  const float tl = z * 144.26950408889634f;
+  const float l = lg2_approx(1.0f + ex2_approx(tl)) * 0.0069314718055994531f;
+  return tl > 28.853900817779268f ? z : l;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
@@ -103,29 +94,6 @@ __device__ __forceinline__ float pe_row(int j, int multires, const float* x3, in
   if (comp_t != comp) return 0.0f;
   return r < 3 ? f * c : -f * s;
 }
-
-// One embedding row with its (frequency, component, function) decoded once, so that evaluating it for
-// many points costs one sincos each.
-struct PeRow {
-  int kind, comp;  // kind: 0 identity, 1 sin, 2 cos, 3 zero padding
-  float freq;
-  __device__ __forceinline__ PeRow(int j, int multires) {
-    const int pe_dim = multires < 0 ? 3 : 3 + 6 * multires;
-    if (j < 0 || j >= pe_dim) { kind = 3; comp = 0; freq = 0.f; }
-    else if (j < 3) { kind = 0; comp = j; freq = 1.f; }
-    else { const int q = (j - 3) / 6, r = (j - 3) % 6; comp = r % 3; freq = (float)(1 << q); kind = r < 3 ? 1 : 2; }
-  }
-  // value (ct < 0) or derivative w.r.t. x[ct]
-  __device__ __forceinline__ float eval(const float* x3, int ct) const {
-    if (kind == 3) return 0.f;
-    if (kind == 0) return ct < 0 ? x3[comp] : (ct == comp ? 1.f : 0.f);
-    if (ct >= 0 && ct != comp) return 0.f;
-    float sn, cs;
-    __sincosf(x3[comp] * freq, &sn, &cs);
-    if (ct < 0) return kind == 1 ? sn : cs;
-    return kind == 1 ? freq * cs : -freq * sn;
-  }
-};
 
 template <bool kF16>
 __device__ __forceinline__ void store_row32(uint8_t* act, int k, int col0, const float (&v)[32], bool skip = false) {
@@ -173,6 +141,13 @@ __device__ __forceinline__ void store_row16(const RowAddr& ra, int col0, const f
     st_shared_v4(ra.chunk((col0 >> 3) + j4), umma::pack2<kF16>(v[8 * j4 + 0], v[8 * j4 + 1]),
                  umma::pack2<kF16>(v[8 * j4 + 2], v[8 * j4 + 3]), umma::pack2<kF16>(v[8 * j4 + 4], v[8 * j4 + 5]),
                  umma::pack2<kF16>(v[8 * j4 + 6], v[8 * j4 + 7]));
+}
+// Copy 16 columns [col0, col0+16) of stash row j (linear, 256 B per row) into operand row ra.
+__device__ __forceinline__ void copy_row16(const RowAddr& ra, const uint8_t* stash, int j, int col0) {
+  const uint4* src = reinterpret_cast<const uint4*>(stash + j * 256 + col0 * 2);
+  const uint4 c0 = src[0], c1 = src[1];
+  st_shared_v4(ra.chunk(col0 >> 3), c0.x, c0.y, c0.z, c0.w);
+  st_shared_v4(ra.chunk((col0 >> 3) + 1), c1.x, c1.y, c1.z, c1.w);
 }
 template <bool kF16>
 __device__ __forceinline__ void store_elem(uint8_t* act, int k, int n, float v) {
@@ -293,7 +268,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, P.steps[s].n_cols, 0, 1)
                                     : umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
         for (int t = 0; t < ntl; ++t) {
-          if (lane == 0) trace_ev(a.trace, my_mt, tcnt, 10, s * 2 + t, pair);
           umma::mbar_wait(&in_ready[t], in_par[t]);
           in_par[t] ^= 1;
           umma::tc_fence_after();
@@ -304,23 +278,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             uint32_t st = stage, ph = phase;
             advance(st, ph, (uint32_t)my_mt);
             uint32_t b_lo = act_lo;
-            bool ready = umma::mbar_try_wait(&w_full[st], ph);
             for (uint32_t kc = 0; kc < nkc; ++kc) {
-              if (!ready) umma::mbar_wait(&w_full[st], ph);
+              umma::mbar_wait(&w_full[st], ph);
               umma::tc_fence_after();
               const uint32_t a_lo = ring_lo + st * (kChunkBytes >> 4);
-              const uint32_t st_cur = st;
-              advance(st, ph, n_mt);
-              // probe the next chunk's barrier now: its ~100+ cycle latency overlaps the MMA issue below
-              ready = (kc + 1 < nkc) ? umma::mbar_try_wait(&w_full[st], ph) : false;
               if (umma::elect_one()) {
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, kc > 0 ? 1u : 0u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
-                umma::mma_commit(&w_empty[st_cur]);
+                umma::mma_commit(&w_empty[st]);
               }
               b_lo += 512;
+              advance(st, ph, n_mt);
             }
           }
           if (umma::elect_one()) umma::mma_commit(&acc_ready[t]);
@@ -336,17 +306,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
     const int mo = (e >> 2) & 1;                    // M-tile this warpgroup owns
     const int q = warp & 3;                         // TMEM lane quarter (hardware: warp id % 4)
     const int etid = (e & 7) * 32 + lane;           // 0..255 inside the tile's epilogue group
-    const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
     uint8_t* act = smem + SmemLayout::act + t * kActBytes;
     float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
     float* vs = (float*)(smem + SmemLayout::vs) + t * 96;
     float* nabs = (float*)(smem + SmemLayout::nabs) + t * 96;
     const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
-    const uint32_t taddr = tmem_tile + (uint32_t)(mo * 128);
-    const RowAddr ra(umma::smem_u32(act), F);
     uint32_t acc_par = 0;
     int tcnt = 0;
     const bool tracer = (mo == 0 && q == 0 && lane == 0 && t == 0);
+    uint8_t* pes = smem + SmemLayout::pes + t * (kPeStashRows * 256);   // embedding rows, linear [row][128 cols] 16-bit
     const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
     const bool no_st = P.debug_flags & 8;
 
@@ -369,9 +337,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         const int ct = tang ? (n >> 5) - 1 : -1;       // -1: value column, 0..2: tangent component
         const float x3[3] = {xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]};
         const int k0 = P.steps[0].k_steps * 16;
+        uint16_t* stash = reinterpret_cast<uint16_t*>(pes) + n;   // row j at stash[j * 128]
+        auto put = [&](int j, float val) {             // operand row j of layer 0 + copy kept for the skip layer
+          store_elem<kF16>(act, j, n, val);
+          if (j < kPeStashRows) stash[j * 128] = umma::pack1<kF16>(val);
+        };
         if (part == 0) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) store_elem<kF16>(act, j, n, ct < 0 ? x3[j] : (ct == j ? 1.f : 0.f));
+          for (int j = 0; j < 3; ++j) put(j, ct < 0 ? x3[j] : (ct == j ? 1.f : 0.f));
         }
         for (int qf = part; qf < P.multires; qf += 2) {   // one sincos per (frequency, component)
           const float f = (float)(1 << qf);
@@ -384,8 +357,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               sv = ct < 0 ? sn : f * cs;
               cv = ct < 0 ? cs : -f * sn;
             }
-            store_elem<kF16>(act, 3 + 6 * qf + c, n, sv);
-            store_elem<kF16>(act, 3 + 6 * qf + 3 + c, n, cv);
+            put(3 + 6 * qf + c, sv);
+            put(3 + 6 * qf + 3 + c, cv);
           }
         }
         for (int j = pe_dim + part; j < k0; j += 2) store_elem<kF16>(act, j, n, 0.f);
@@ -394,11 +367,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 
       for (int s = 0; s < P.n_steps; ++s) {
         const nr_umma_step_t& S = P.steps[s];
-        if (tracer) trace_ev(a.trace, 2, tcnt, 20, s * 2 + t, pair);
         umma::mbar_wait(&acc_ready[t], acc_par);
         acc_par ^= 1;
         umma::tc_fence_after();
         if (tracer) trace_ev(a.trace, 2, tcnt, 21, s * 2 + t, pair);
+        const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
+        const uint32_t taddr = tmem_tile + (uint32_t)(mo * 128);
+        const RowAddr ra(umma::smem_u32(act), F);
 
         if (P.debug_flags & 2) {
           // profiling: MMA + weight pipeline only
@@ -406,7 +381,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
           if (mo < S.n_mt) {
             const float b = a.bias[S.bias_off + F];
             const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
-            const PeRow pr(is_pe ? F - S.out_rows : -1, P.multires);
             uint32_t raw[16];
             float v[16];
             if (P.debug_flags & 4) {
@@ -416,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                 if (__uint_as_float(raw[0]) == 123.456f) act[0] = 1;
               }
             } else if (tang) {
-              // columns [0,32): values of 32 points, [32c, 32c+32): d/dx_c; two 16-point halves
+              // columns: [0,32) values of 32 points, [32c, 32c+32) d/dx_c; processed in two 16-point halves
 #pragma unroll 1
               for (int h = 0; h < 2; ++h) {
                 float sg[16];
@@ -425,11 +399,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                 if (!is_pe) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) softplus100_fast(__uint_as_float(raw[j]) + b, v[j], sg[j]);
-                } else {
-#pragma unroll 4
-                  for (int j = 0; j < 16; ++j) v[j] = pr.eval(xs + 3 * (16 * h + j), -1);
                 }
-                store_row16<kF16>(ra, 16 * h, v, no_st);
+                if (!is_pe) store_row16<kF16>(ra, 16 * h, v, no_st);
+                else copy_row16(ra, pes, F - S.out_rows, 16 * h);
 #pragma unroll 1
                 for (int c = 1; c < 4; ++c) {
                   umma::tmem_ld16(taddr + 32 * c + 16 * h, raw);
@@ -437,11 +409,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                   if (!is_pe) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * sg[j];
-                  } else {
-#pragma unroll 4
-                    for (int j = 0; j < 16; ++j) v[j] = pr.eval(xs + 3 * (16 * h + j), c - 1);
                   }
-                  store_row16<kF16>(ra, 32 * c + 16 * h, v, no_st);
+                  if (!is_pe) store_row16<kF16>(ra, 32 * c + 16 * h, v, no_st);
+                  else copy_row16(ra, pes, F - S.out_rows, 32 * c + 16 * h);
                 }
               }
             } else {
@@ -452,11 +422,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                 if (!is_pe) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
-                } else {
-#pragma unroll 4
-                  for (int j = 0; j < 16; ++j) v[j] = pr.eval(xs + 3 * (16 * c + j), -1);
                 }
-                store_row16<kF16>(ra, 16 * c, v, no_st);
+                if (!is_pe) store_row16<kF16>(ra, 16 * c, v, no_st);
+                else copy_row16(ra, pes, F - S.out_rows, 16 * c);
               }
             }
           }
@@ -517,8 +485,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             const int extra = P.rad_extra_rows;
             for (int r = g; r < extra; r += 8) {
               float val = 0.0f;
-              if (r < px) val = PeRow(r, P.rad_multires).eval(xs + 3 * p, -1);
-              else if (r < px + pv) val = PeRow(r - px, P.rad_multires_view).eval(vs + 3 * p, -1);
+              if (r < px) val = pe_row(r, P.rad_multires, xs + 3 * p, -1);
+              else if (r < px + pv) val = pe_row(r - px, P.rad_multires_view, vs + 3 * p, -1);
               else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
               store_elem<kF16>(act, 256 + r, p, val);
             }
@@ -554,7 +522,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         }
         if (tracer) trace_ev(a.trace, 2, tcnt, 22, s * 2 + t, pair);
         if (s + 1 < P.n_steps) publish(&in_ready[t], P.debug_flags);
-        if (tracer) trace_ev(a.trace, 2, tcnt, 23, s * 2 + t, pair);
       }
       umma::tc_fence_before();
       named_bar_sync(1 + t, kEpiPerTile);  // staging buffers and TMEM slot free before the next tile
@@ -597,6 +564,10 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
   }
   NR_CHECK_ARG(prog->steps[0].k_steps * 16 >= (prog->multires < 0 ? 3 : 3 + 6 * prog->multires),
                "nr_mlp_umma_forward: step 0 K does not cover the embedding");
+  for (int s = 0; s < prog->n_steps; ++s)
+    if (prog->steps[s].pe_fill)
+      NR_CHECK_ARG((prog->multires < 0 ? 3 : 3 + 6 * prog->multires) <= kPeStashRows,
+                   "nr_mlp_umma_forward: skip connections need an embedding of at most %d rows", kPeStashRows);
   if (has_rad) NR_CHECK_ARG(prog->tangents && view, "nr_mlp_umma_forward: the radiance steps need tangent tiles and view dirs");
   if (n == 0) return NR_OK;
   int dev = 0, sms = 0;

@@ -151,6 +151,62 @@ int nr_neus_composite(const float* sdf, const float* nablas, const float* radian
                       float* cdf_out, float* alpha_out, float* weights_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * VolSDF -- models/frameworks/volsdf.py
+ * ------------------------------------------------------------------------------------------ */
+/* error_bound(d_vals, sdf, alpha, beta) -- volsdf.py:38-74.  d_vals, sdf [R,M]; alpha / beta are
+ * device arrays read at [ray * stride] (stride 0 = one scalar for all rays); bounds [R,M-1] and/or
+ * the per-ray maximum bound_max [R] (either may be NULL).  NaN -> inf as in the reference. */
+int nr_volsdf_error_bound(const float* d_vals, const float* sdf, int64_t R, int32_t M,
+                          const float* alpha, int32_t alpha_stride, const float* beta,
+                          int32_t beta_stride, float* bounds, float* bound_max, void* stream);
+
+/* Ray prologue of render_rayschunk (volsdf.py:169-172,402-427): normalised dirs [R,3], fars [R]
+ * (`far`, or the exact sphere exit of get_sphere_intersection when sphere_radius > 0 -- rays that
+ * miss are counted in *miss_count, the reference asserts on them), the dense initial depths
+ * linspace(near, far, n_init) written to d_buf[:, :n_init] (row stride cap) and their points. */
+int nr_volsdf_ray_setup(const float* rays_o, const float* rays_d, int64_t R, float near, float far,
+                        float sphere_radius, int32_t n_init, float* dirs, float* fars,
+                        int32_t* miss_count, float* d_buf, int32_t cap, float* pts_new, void* stream);
+
+/* sdf = min(sdf, radius - |x|): the bounding-sphere background of VolSDF.forward_surface /
+ * forward_surface_with_nablas (volsdf.py:310-325). */
+int nr_sphere_min(const float* pts, float* sdf, int64_t n, float radius, void* stream);
+
+/* One iteration of fine_sample (volsdf.py:129-270), one warp per ray, no host synchronisation.
+ * it = 0: bound check of the m0 initial samples (sdf_new [R,n_new=m0]) with the network's beta;
+ *         converged rays get their final samples, the others beta+ (:129) and n_up proposals.
+ * it >= 1: merge last iteration's proposals (d_new_in, sdf_new [R,n_new=n_up]) into the sorted state
+ *         (d_buf, sdf_buf [R,cap], m_cur valid), re-check, bisect beta+ (max_bisection steps), propose
+ *         again -- or, at it == max_iter, sample with the last beta+ (iter_usage = -1).
+ * Per-ray state: beta [R], status [R] (0 active / 1 done), outputs iter_usage [R], beta_map [R],
+ * d_fine [R,n_final]; proposals d_new_out [R,n_up], pts_new [R,n_up,3] (zeros for finished rays).
+ * u_final: [R,n_final] uniforms for the final inverse-CDF draw, NULL = deterministic. */
+int nr_volsdf_fine_iter(const float* rays_o, const float* dirs, const float* fars, int64_t R,
+                        float* d_buf, float* sdf_buf, int32_t cap, int32_t m_cur, const float* sdf_new,
+                        int32_t n_new, const float* d_new_in, const float* alpha_net,
+                        const float* beta_net, float eps, int32_t it, int32_t max_iter,
+                        int32_t max_bisection, int32_t n_up, int32_t n_final, const float* u_final,
+                        int32_t m0, float* beta, int32_t* status, float* iter_usage, float* beta_map,
+                        float* d_fine, float* d_new_out, float* pts_new, void* stream);
+
+/* d_all = sort(cat(linspace(near, far, n_coarse), d_fine)) and its points (volsdf.py:436-444). */
+int nr_volsdf_merge(const float* rays_o, const float* dirs, const float* fars, int64_t R, float near,
+                    int32_t n_coarse, const float* d_fine, int32_t n_fine, float* d_all, float* pts,
+                    void* stream);
+
+/* Density + compositing (volsdf.py:452-503).  Inside samples: sdf [R,M_in], nablas [R,M_in,3] or
+ * NULL, radiance [R,M_in,3], d_in [R,M_in]; alpha/beta device scalars (forward_ab, :306-308).
+ * Optional NeRF++ samples appended after them: sigma_out [R,M_out] (raw), radiance_out
+ * [R,M_out,3], d_out [R,M_out] (M_out = 0: none).  Outputs rgb [R,3], depth [R], acc [R], normals
+ * [R,3] or NULL; optional per-sample sigma_all [R,M], p_out [R,M-1], tau_out [R,M-1]. */
+int nr_volsdf_composite(const float* sdf, const float* nablas, const float* radiance,
+                        const float* d_in, const float* alpha_dev, const float* beta_dev, int64_t R,
+                        int32_t M_in, const float* sigma_out, const float* radiance_out,
+                        const float* d_out, int32_t M_out, int32_t white_bkgd, float* rgb, float* depth,
+                        float* acc, float* normals, float* sigma_all, float* p_out, float* tau_out,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * bf16 tier: fused PE + SDF MLP (+ forward-mode normals) + radiance MLP on tcgen05 / TMEM.
  * The host packs the weights once into a pre-swizzled bf16 image (16 KB chunks = A tiles of
  * 128 features x 64 k) and describes the network as a short program of steps; the kernel

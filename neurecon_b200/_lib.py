@@ -63,6 +63,14 @@ _SIGNATURES = {
     "nr_sample_pdf": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "nr_neus_ray_setup": (C.c_int, [_P, _P, _I64, _F, _F, _F, _I32, _P, _P, _P, _P, _P, _P]),
     "nr_neus_upsample_step": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "nr_volsdf_error_bound": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P, _I32, _P, _P, _P]),
+    "nr_volsdf_ray_setup": (C.c_int, [_P, _P, _I64, _F, _F, _F, _I32, _P, _P, _P, _P, _I32, _P, _P]),
+    "nr_sphere_min": (C.c_int, [_P, _P, _I64, _F, _P]),
+    "nr_volsdf_fine_iter": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I32, _I32, _P, _I32, _P, _P, _P, _F, _I32, _I32, _I32,
+                                      _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nr_volsdf_merge": (C.c_int, [_P, _P, _P, _I64, _F, _I32, _P, _I32, _P, _P, _P]),
+    "nr_volsdf_composite": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P,
+                                      _P, _P, _P]),
     "nr_mlp_umma_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _P, _I64, _P, _P, _P, _I64, _P, _P]),
     "nr_mlp_umma_set_trace": (C.c_int, [_P]),
     "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),

@@ -99,6 +99,27 @@ int nr_radiance_forward_f32(const nr_radiance_net_t* net, const float* x, const 
                             const float* normals, const float* feat, int64_t feat_ld, int64_t n,
                             float* rgb, void* ws, size_t ws_bytes, void* stream);
 
+/* NeRF++ background network, NeRF.forward(input_pts, input_views) -- models/base.py:395-453
+ * (use_view_dirs=True).  Plain (not weight-normed) layers; weights fp32 [out, pad4(in)]. */
+typedef struct {
+  int32_t depth;          /* D: number of pts_linears */
+  int32_t width;          /* W */
+  int32_t input_dim;      /* 4 for the inverted-sphere parametrisation [x/r, 1/r] */
+  int32_t multires;       /* PE of the point (10) */
+  int32_t multires_view;  /* PE of the view direction (4) */
+  int32_t skip;           /* the embedding is re-concatenated in front of h after this layer (base.py:434) */
+  const float* pts_W[NR_MAX_LAYERS];
+  const float* pts_b[NR_MAX_LAYERS];
+  const float* alpha_W;   const float* alpha_b;    /* [1, W] */
+  const float* feature_W; const float* feature_b;  /* [W, W] */
+  const float* views_W;   const float* views_b;    /* [W/2, W + pe_view] */
+  const float* rgb_W;     const float* rgb_b;      /* [3, W/2] */
+} nr_nerf_net_t;
+size_t nr_nerf_forward_f32_workspace(const nr_nerf_net_t* net, int64_t n);
+/* x [n,input_dim], view [n,3] -> sigma [n] (raw), rgb [n,3] (sigmoid) */
+int nr_nerf_forward_f32(const nr_nerf_net_t* net, const float* x, const float* view, int64_t n,
+                        float* sigma, float* rgb, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Ray geometry and inverse-CDF sampling -- utils/rend_util.py
  * ------------------------------------------------------------------------------------------ */

@@ -33,6 +33,13 @@ class RadianceNetDesc(C.Structure):
     ]
 
 
+class NerfNet(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("depth", "width", "input_dim", "multires", "multires_view", "skip")] + [
+        ("pts_W", C.c_void_p * NR_MAX_LAYERS), ("pts_b", C.c_void_p * NR_MAX_LAYERS),
+        ("alpha_W", C.c_void_p), ("alpha_b", C.c_void_p), ("feature_W", C.c_void_p), ("feature_b", C.c_void_p),
+        ("views_W", C.c_void_p), ("views_b", C.c_void_p), ("rgb_W", C.c_void_p), ("rgb_b", C.c_void_p)]
+
+
 NR_UMMA_MAX_STEPS = 24
 
 
@@ -59,6 +66,8 @@ _SIGNATURES = {
     "nr_sdf_forward_nablas_f32": (C.c_int, [C.POINTER(SdfNet), _P, _I64, _P, _P, _P, _I64, _P, _SZ, _P]),
     "nr_radiance_forward_f32_workspace": (_SZ, [C.POINTER(RadianceNetDesc), _I64]),
     "nr_radiance_forward_f32": (C.c_int, [C.POINTER(RadianceNetDesc), _P, _P, _P, _P, _I64, _I64, _P, _P, _SZ, _P]),
+    "nr_nerf_forward_f32_workspace": (_SZ, [C.POINTER(NerfNet), _I64]),
+    "nr_nerf_forward_f32": (C.c_int, [C.POINTER(NerfNet), _P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "nr_near_far_from_sphere": (C.c_int, [_P, _P, _I64, _F, _P, _P, _P]),
     "nr_sample_pdf": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "nr_neus_ray_setup": (C.c_int, [_P, _P, _I64, _F, _F, _F, _I32, _P, _P, _P, _P, _P, _P]),

@@ -449,3 +449,93 @@ extern "C" int nr_radiance_forward_f32(const nr_radiance_net_t* net, const float
   }
   return NR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// NeRF++ background MLP (NeRF.forward, models/base.py:426-453, use_view_dirs=True):
+// PE(x4) -> D ReLU layers, the embedding re-concatenated IN FRONT of h after layer `skip`
+// (base.py:434-435) -> sigma = alpha_linear(h) (raw) ; feature_linear(h) | PE(view) -> W/2 ReLU ->
+// rgb_linear -> sigmoid.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NerfWs { float *pe, *h[2], *fv, *hv; int ldpe, ldh, ldfv, ldhv; size_t bytes; };
+
+int pe_dim_of(int in_dim, int multires) { return multires < 0 ? in_dim : in_dim * (1 + 2 * multires); }
+
+NerfWs carve_nerf_ws(const nr_nerf_net_t* net, int64_t n, void* ws) {
+  NerfWs w{};
+  const int pe = pe_dim_of(net->input_dim, net->multires), pv = pe_dim_of(3, net->multires_view);
+  w.ldpe = nr_pad4(pe);
+  w.ldh = nr_pad4(net->width + pe);
+  w.ldfv = nr_pad4(net->width + pv);
+  w.ldhv = nr_pad4(net->width / 2);
+  char* p = (char*)ws;
+  size_t off = 0;
+  auto take = [&](size_t nfloats) { float* r = (float*)(p + off); off += nr_align(nfloats * sizeof(float)); return r; };
+  w.pe = take((size_t)n * w.ldpe);
+  w.h[0] = take((size_t)n * w.ldh);
+  w.h[1] = take((size_t)n * w.ldh);
+  w.fv = take((size_t)n * w.ldfv);
+  w.hv = take((size_t)n * w.ldhv);
+  w.bytes = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t nr_nerf_forward_f32_workspace(const nr_nerf_net_t* net, int64_t n) {
+  if (!net || n < 0) return 0;
+  return carve_nerf_ws(net, n, nullptr).bytes;
+}
+
+extern "C" int nr_nerf_forward_f32(const nr_nerf_net_t* net, const float* x, const float* view, int64_t n, float* sigma,
+                                   float* rgb, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NR_CHECK_ARG(net && n >= 0, "nr_nerf_forward_f32: bad arguments");
+  NR_CHECK_ARG(net->depth >= 2 && net->depth <= NR_MAX_LAYERS && net->input_dim >= 1 && net->input_dim <= 4,
+               "nr_nerf_forward_f32: depth=%d input_dim=%d", net->depth, net->input_dim);
+  if (n == 0) return NR_OK;
+  NR_CHECK_ARG(x && view && sigma && rgb, "nr_nerf_forward_f32: null pointer");
+  NerfWs w = carve_nerf_ws(net, n, ws);
+  if (w.bytes > ws_bytes || !ws) {
+    nr_set_error("nerf forward: workspace %zu bytes < required %zu", ws_bytes, w.bytes);
+    return NR_ERR_WORKSPACE;
+  }
+  const int pe = pe_dim_of(net->input_dim, net->multires), pv = pe_dim_of(3, net->multires_view), W = net->width;
+  int rc;
+  if ((rc = launch_embed(x, n, net->input_dim, net->multires, w.pe, w.ldpe, 0, nullptr, 0, 0, 1.0f, st))) return rc;
+  const float* hin = w.pe; int ldin = w.ldpe; int kin = pe;
+  for (int i = 0; i < net->depth; ++i) {
+    // layer i's output goes behind the embedding when the NEXT layer consumes cat([pe, h])
+    const bool cat_next = (i == net->skip);
+    float* hout = w.h[i & 1];
+    GemmArgs g{};
+    g.A = hin; g.lda = ldin; g.W = net->pts_W[i]; g.ldw = nr_pad4(kin); g.bias = net->pts_b[i];
+    g.M = (int)n; g.N = W; g.K = kin; g.Y = hout + (cat_next ? pe : 0); g.ldy = w.ldh; g.mode = EPI_RELU;
+    NR_CHECK_ARG(!cat_next || (pe & 3) == 0, "nr_nerf_forward_f32: embedding width must be a multiple of 4 for the skip");
+    if ((rc = launch_gemm(g, st))) return rc;
+    if (cat_next && (rc = launch_copy_cols(w.pe, w.ldpe, 0, hout, w.ldh, 0, n, pe, 1.0f, st))) return rc;
+    hin = hout; ldin = w.ldh; kin = cat_next ? W + pe : W;
+  }
+  // sigma = alpha_linear(h)  (raw, base.py:438)
+  if ((rc = launch_rowdot(hin, ldin, net->alpha_W, net->alpha_b, n, kin, sigma, n, 1, st))) return rc;
+  // feature_linear(h) | PE(view)
+  {
+    GemmArgs g{};
+    g.A = hin; g.lda = ldin; g.W = net->feature_W; g.ldw = nr_pad4(kin); g.bias = net->feature_b;
+    g.M = (int)n; g.N = W; g.K = kin; g.Y = w.fv; g.ldy = w.ldfv; g.mode = EPI_NONE;
+    if ((rc = launch_gemm(g, st))) return rc;
+    if ((rc = launch_embed(view, n, 3, net->multires_view, w.fv, w.ldfv, W, nullptr, 0, 0, 1.0f, st))) return rc;
+  }
+  {
+    GemmArgs g{};
+    g.A = w.fv; g.lda = w.ldfv; g.W = net->views_W; g.ldw = nr_pad4(W + pv); g.bias = net->views_b;
+    g.M = (int)n; g.N = W / 2; g.K = W + pv; g.Y = w.hv; g.ldy = w.ldhv; g.mode = EPI_RELU;
+    if ((rc = launch_gemm(g, st))) return rc;
+  }
+  {
+    GemmArgs g{};
+    g.A = w.hv; g.lda = w.ldhv; g.W = net->rgb_W; g.ldw = nr_pad4(W / 2); g.bias = net->rgb_b;
+    g.M = (int)n; g.N = 3; g.K = W / 2; g.Y = rgb; g.ldy = 3; g.mode = EPI_SIGMOID;
+    if ((rc = launch_gemm(g, st))) return rc;
+  }
+  return NR_OK;
+}

@@ -51,3 +51,245 @@ class VolSDF(nn.Module):
         sdf, nablas, geometry_feature = self.forward_surface_with_nablas(x)
         radiances = self.radiance_net.forward(x, view_dirs, nablas, geometry_feature)
         return radiances, sdf, nablas
+
+
+# --------------------------------------------------------------------------------------------
+# tensor helpers of the reference API
+# --------------------------------------------------------------------------------------------
+def sdf_to_sigma(sdf, alpha, beta):
+    """volsdf.py:16-35 (Laplace-CDF density).  Thin torch composition for API users; the renderer
+    evaluates it inside nr_volsdf_composite / nr_volsdf_fine_iter."""
+    e = 0.5 * torch.exp(-torch.abs(sdf) / beta)
+    return alpha * torch.where(sdf >= 0, e, 1 - e)
+
+
+def _as_ray_param(v, R, dev):
+    """scalar / 0-d / [R,1] / [R] -> (contiguous fp32 tensor, stride)"""
+    if not torch.is_tensor(v):
+        v = torch.tensor(float(v), device=dev)
+    v = v.detach().float().to(dev)
+    if v.numel() == 1:
+        return v.reshape(1).contiguous(), 0
+    assert v.numel() == R, "per-ray parameter must have one entry per ray"
+    return v.reshape(R).contiguous(), 1
+
+
+def error_bound(d_vals, sdf, alpha, beta):
+    """volsdf.py:38-74: [..., N_pts] -> [..., N_pts-1] error bounds (NaN -> inf)."""
+    _lib.require_cuda(d_vals, sdf)
+    lib = _lib.get_lib()
+    prefix, M = d_vals.shape[:-1], d_vals.shape[-1]
+    d = _lib.f32c(d_vals.detach().reshape(-1, M))
+    s = _lib.f32c(sdf.detach().reshape(-1, M))
+    R, dev = d.shape[0], d.device
+    a, a_st = _as_ray_param(alpha, R, dev)
+    b, b_st = _as_ray_param(beta, R, dev)
+    out = torch.empty(R, M - 1, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nr_volsdf_error_bound(_lib.ptr(d), _lib.ptr(s), R, M, _lib.ptr(a), a_st, _lib.ptr(b), b_st,
+                                             _lib.ptr(out), None, _lib.stream_ptr(dev)), "volsdf_error_bound")
+    return out.reshape(*prefix, M - 1)
+
+
+def fine_sample(implicit_surface_fn, init_dvals, rays_o, rays_d, alpha_net, beta_net, far, eps=0.1, max_iter: int = 5,
+                max_bisection: int = 10, final_N_importance: int = 64, N_up: int = 128, perturb=True,
+                early_exit=True):
+    """volsdf.py:77-272 (error-bounded beta iteration).  Same arguments and returns
+    (d_fine [..., N], beta [..., 1], iter_usage [...]); ``implicit_surface_fn(pts[..., 3]) -> sdf``.
+    The per-ray state machine runs on the device; ``early_exit`` reads one flag per iteration to skip the
+    remaining network queries once every ray is finished (set False for a sync-free, graph-capturable run)."""
+    _lib.require_cuda(init_dvals, rays_o, rays_d)
+    lib = _lib.get_lib()
+    prefix, N0 = init_dvals.shape[:-1], init_dvals.shape[-1]
+    o = _lib.f32c(rays_o.detach().reshape(-1, 3))
+    dirs = _lib.f32c(rays_d.detach().reshape(-1, 3))
+    R, dev = o.shape[0], o.device
+    f = dict(dtype=torch.float32, device=dev)
+    cap = N0 + max_iter * N_up
+    d_buf, sdf_buf = torch.empty(R, cap, **f), torch.empty(R, cap, **f)
+    d_buf[:, :N0] = init_dvals.detach().reshape(R, N0)
+    fars, _ = _as_ray_param(far, R, dev)
+    fars = fars.expand(R).contiguous()
+    a_net = alpha_net.detach().float().reshape(1).contiguous() if torch.is_tensor(alpha_net) else torch.tensor([float(alpha_net)], **f)
+    b_net = beta_net.detach().float().reshape(1).contiguous() if torch.is_tensor(beta_net) else torch.tensor([float(beta_net)], **f)
+    beta, status = torch.zeros(R, **f), torch.zeros(R, dtype=torch.int32, device=dev)
+    iter_usage, beta_map, d_fine = torch.zeros(R, **f), torch.zeros(R, **f), torch.zeros(R, final_N_importance, **f)
+    d_new = [torch.zeros(R, N_up, **f), torch.zeros(R, N_up, **f)]
+    pts_new = torch.empty(R, N_up, 3, **f)
+    u_final = None if not perturb else torch.rand(R, final_N_importance, device=dev)
+    with torch.cuda.device(dev), torch.no_grad():
+        st = _lib.stream_ptr(dev)
+        pts0 = o[:, None, :] + dirs[:, None, :] * d_buf[:, :N0, None]
+        sdf_new = _lib.f32c(implicit_surface_fn(pts0).reshape(R, N0))
+        for it in range(max_iter + 1):
+            n_new = N0 if it == 0 else N_up
+            m_cur = 0 if it == 0 else N0 + (it - 1) * N_up
+            _lib.check(lib.nr_volsdf_fine_iter(
+                _lib.ptr(o), _lib.ptr(dirs), _lib.ptr(fars), R, _lib.ptr(d_buf), _lib.ptr(sdf_buf), cap, m_cur,
+                _lib.ptr(sdf_new), n_new, None if it == 0 else _lib.ptr(d_new[(it - 1) & 1]), _lib.ptr(a_net),
+                _lib.ptr(b_net), float(eps), it, max_iter, max_bisection, N_up, final_N_importance, _lib.ptr(u_final),
+                N0, _lib.ptr(beta), _lib.ptr(status), _lib.ptr(iter_usage), _lib.ptr(beta_map), _lib.ptr(d_fine),
+                _lib.ptr(d_new[it & 1]), _lib.ptr(pts_new), st), "volsdf_fine_iter")
+            if it == max_iter:
+                break
+            if early_exit and bool((status != 0).all()):
+                break
+            sdf_new = _lib.f32c(implicit_surface_fn(pts_new).reshape(R, N_up))
+    return (d_fine.reshape(*prefix, final_N_importance), beta_map.reshape(*prefix, 1), iter_usage.reshape(*prefix))
+
+
+def _surface_sdf(model, pts):
+    """VolSDF.forward_surface (volsdf.py:310-315) with the bounding-sphere min fused in place."""
+    sdf = model.implicit_surface.forward(pts)
+    if model.use_sphere_bg:
+        lib = _lib.get_lib()
+        p = _lib.f32c(pts.reshape(-1, 3))
+        _lib.check(lib.nr_sphere_min(_lib.ptr(p), _lib.ptr(sdf), p.shape[0], float(model.obj_bounding_radius),
+                                     _lib.stream_ptr(p.device)), "sphere_min")
+    return sdf
+
+
+def volume_render(
+        rays_o,
+        rays_d,
+        model: VolSDF,
+
+        near=0.0,
+        far=6.0,
+        obj_bounding_radius=3.0,
+
+        batched=False,
+        batched_info={},
+
+        # render algorithm config
+        calc_normal=False,
+        use_view_dirs=True,
+        rayschunk=65536,
+        netchunk=1048576,
+        white_bkgd=False,
+        use_nerfplusplus=False,
+
+        # render function config
+        detailed_output=True,
+        show_progress=False,
+
+        # sampling related
+        perturb=False,
+        N_samples=128,
+        N_importance=64,
+        N_outside=32,
+        max_upsample_steps=5,
+        max_bisection_steps=10,
+        epsilon=0.1,
+        **dummy_kwargs):
+    """volsdf.py:334-551.  rays_o / rays_d: [(B,) N_rays, 3].  Returns (rgb, depth_volume, ret)."""
+    if not use_view_dirs:
+        raise NotImplementedError("use_view_dirs=False is not supported")
+    _lib.require_cuda(rays_o, rays_d)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
+        raise NotImplementedError("neurecon_b200: VolSDF volume_render under autograd is not built yet; "
+                                  "wrap inference in torch.no_grad()")
+    lib = _lib.get_lib()
+    B = rays_d.shape[0] if batched else 1
+    prefix = [B, -1] if batched else [-1]
+    dev = rays_o.device
+    o_flat = _lib.f32c(rays_o.reshape(-1, 3))
+    d_flat = _lib.f32c(rays_d.reshape(-1, 3))
+    n_total = o_flat.shape[0]
+    f = dict(dtype=torch.float32, device=dev)
+    alpha_t, beta_t = model.forward_ab()
+    alpha_t, beta_t = alpha_t.detach().float().contiguous(), beta_t.detach().float().contiguous()
+    N_init = N_samples * 4
+    M_in = N_samples + N_importance
+    M_out = N_outside if use_nerfplusplus else 0
+    M = M_in + M_out
+    miss = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    outs = []
+    with torch.cuda.device(dev), torch.no_grad():
+        st = _lib.stream_ptr(dev)
+        step = int(rayschunk) * B
+        for i0 in range(0, n_total, step):
+            ro, rd = o_flat[i0:i0 + step], d_flat[i0:i0 + step]
+            R = ro.shape[0]
+            dirs, fars = torch.empty(R, 3, **f), torch.empty(R, **f)
+            d_init, pts_init = torch.empty(R, N_init, **f), torch.empty(R, N_init, 3, **f)
+            _lib.check(lib.nr_volsdf_ray_setup(
+                _lib.ptr(ro), _lib.ptr(rd), R, float(near), float(far),
+                float(obj_bounding_radius) if use_nerfplusplus else -1.0, N_init, _lib.ptr(dirs), _lib.ptr(fars),
+                _lib.ptr(miss), _lib.ptr(d_init), N_init, _lib.ptr(pts_init), st), "volsdf_ray_setup")
+            d_fine, beta_map, iter_usage = fine_sample(
+                lambda p: _surface_sdf(model, p), d_init, ro, dirs, alpha_t, beta_t, fars, eps=epsilon,
+                max_iter=max_upsample_steps, max_bisection=max_bisection_steps, final_N_importance=N_importance,
+                N_up=N_samples * 4, perturb=perturb)
+            d_in, pts = torch.empty(R, M_in, **f), torch.empty(R, M_in, 3, **f)
+            _lib.check(lib.nr_volsdf_merge(_lib.ptr(ro), _lib.ptr(dirs), _lib.ptr(fars), R, float(near), N_samples,
+                                           _lib.ptr(d_fine), N_importance, _lib.ptr(d_in), _lib.ptr(pts), st), "volsdf_merge")
+            views = dirs.unsqueeze(-2).expand(R, M_in, 3)
+            radiances, sdf, nablas = query_radiance(model.implicit_surface, model.radiance_net, pts, views)
+            if model.use_sphere_bg:
+                _lib.check(lib.nr_sphere_min(_lib.ptr(pts), _lib.ptr(sdf), R * M_in, float(model.obj_bounding_radius), st),
+                           "sphere_min")
+            sigma_out = radiance_out = d_out = None
+            if use_nerfplusplus:
+                # inverse-sphere samples (volsdf.py:456-467): tiny [R, N_outside] host-side compositions
+                from ...utils import rend_util
+                t_ = torch.linspace(0, 1, N_outside + 2)[..., 1:-1].float().to(dev)
+                rs = (obj_bounding_radius / torch.flip(t_, dims=[-1])).expand(R, N_outside)
+                if perturb:
+                    mids = .5 * (rs[..., 1:] + rs[..., :-1])
+                    upper = torch.cat([mids, rs[..., -1:]], -1)
+                    lower = torch.cat([rs[..., :1], mids], -1)
+                    rs = lower + (upper - lower) * torch.rand(upper.shape).float().to(dev)
+                d_out = rend_util.get_dvals_from_radius(ro, dirs, rs).contiguous()
+                pts_out = ro[..., None, :] + dirs[..., None, :] * d_out[..., :, None]
+                x_out = torch.cat([pts_out / rs[..., None], 1. / rs[..., None]], dim=-1)
+                sigma_out, radiance_out = model.nerf_outside.forward(x_out, dirs.unsqueeze(-2).expand(R, N_outside, 3))
+                sigma_out, radiance_out = sigma_out.contiguous(), radiance_out.contiguous()
+            rgb, depth, acc = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
+            normals = torch.empty(R, 3, **f) if calc_normal else None
+            sigma_all = torch.empty(R, M, **f) if detailed_output else None
+            p_i = torch.empty(R, M - 1, **f) if detailed_output else None
+            tau = torch.empty(R, M - 1, **f) if detailed_output else None
+            _lib.check(lib.nr_volsdf_composite(
+                _lib.ptr(sdf), _lib.ptr(nablas) if calc_normal else None, _lib.ptr(radiances), _lib.ptr(d_in),
+                _lib.ptr(alpha_t), _lib.ptr(beta_t), R, M_in, _lib.ptr(sigma_out), _lib.ptr(radiance_out),
+                _lib.ptr(d_out), M_out, int(bool(white_bkgd)), _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc),
+                _lib.ptr(normals), _lib.ptr(sigma_all), _lib.ptr(p_i), _lib.ptr(tau), st), "volsdf_composite")
+            ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
+            if calc_normal:
+                ret_i['normals_volume'] = normals
+            if detailed_output:
+                ret_i['implicit_surface'] = sdf
+                ret_i['implicit_nablas'] = nablas
+                ret_i['radiance'] = radiances if not use_nerfplusplus else torch.cat([radiances, radiance_out], dim=-2)
+                ret_i['alpha'] = 1.0 - p_i
+                ret_i['p_i'] = p_i
+                ret_i['visibility_weights'] = tau
+                ret_i['d_vals'] = d_in if not use_nerfplusplus else torch.cat([d_in, d_out], dim=-1)
+                ret_i['sigma'] = sigma_all
+                ret_i['beta_map'] = beta_map
+                ret_i['iter_usage'] = iter_usage
+                if use_nerfplusplus:
+                    ret_i['sigma_out'] = sigma_out
+                    ret_i['radiance_out'] = radiance_out
+            outs.append(ret_i)
+    if use_nerfplusplus:
+        assert int(miss.item()) == 0, "every ray must intersect the bounding sphere (volsdf.py:404-405)"
+
+    ret = OrderedDict()
+    for k in outs[0].keys():
+        v = outs[0][k] if len(outs) == 1 else torch.cat([o_[k] for o_ in outs], 0)
+        ret[k] = v.reshape(*prefix, *v.shape[1:]) if batched else v
+    return ret['rgb'], ret['depth_volume'], ret
+
+
+class SingleRenderer(nn.Module):
+    """volsdf.py:554-560."""
+
+    def __init__(self, model: VolSDF):
+        super().__init__()
+        self.model = model
+
+    def forward(self, rays_o, rays_d, **kwargs):
+        return volume_render(rays_o, rays_d, self.model, **kwargs)

@@ -1,5 +1,58 @@
-"""NeRF++ background network forward (models/base.py:426-453) -- built with the VolSDF milestone."""
+"""NeRF++ background network forward (models/base.py:426-453) on the fp32 GEMM kernels."""
+import torch
+
+from .. import _lib
+from .._lib import C
+from .base import _pack_layers, _param_key, _MAX_POINTS_PER_CALL
+
+
+def _descriptor(module):
+    if not module.use_view_dirs:
+        raise NotImplementedError("neurecon_b200 NeRF supports use_view_dirs=True (the NeRF++ background configuration)")
+    if len(module.skips) > 1:
+        raise NotImplementedError("neurecon_b200 NeRF supports one skip")
+    key = _param_key(module)
+    c = module._cache
+    if c.get("key") != key:
+        lin = list(module.pts_linears)
+        Ws, bs = _pack_layers([l.weight for l in lin], [l.bias for l in lin])
+        others = [module.alpha_linear, module.feature_linear, module.views_linears[0], module.rgb_linear]
+        Wo, bo = _pack_layers([l.weight for l in others], [l.bias for l in others])
+        d = _lib.NerfNet()
+        d.depth, d.width, d.input_dim = module.D, module.W, module.input_dim
+        d.multires, d.multires_view = module.multires, module.multires_view
+        d.skip = module.skips[0] if module.skips else -1
+        for i in range(module.D):
+            d.pts_W[i], d.pts_b[i] = Ws[i].data_ptr(), bs[i].data_ptr()
+        d.alpha_W, d.alpha_b = Wo[0].data_ptr(), bo[0].data_ptr()
+        d.feature_W, d.feature_b = Wo[1].data_ptr(), bo[1].data_ptr()
+        d.views_W, d.views_b = Wo[2].data_ptr(), bo[2].data_ptr()
+        d.rgb_W, d.rgb_b = Wo[3].data_ptr(), bo[3].data_ptr()
+        c.clear()
+        c.update(key=key, desc=d, keep=(Ws, bs, Wo, bo))
+    return c["desc"]
 
 
 def nerf_forward(module, input_pts, input_views):
-    raise NotImplementedError("neurecon_b200: the NeRF++ background MLP kernels are not built yet")
+    """NeRF.forward(input_pts [..., 4], input_views [..., 3]) -> (sigma [...], rgb [..., 3])."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+        raise NotImplementedError("neurecon_b200: NeRF++ training backward is not built yet; use torch.no_grad()")
+    _lib.require_cuda(input_pts, input_views)
+    lib = _lib.get_lib()
+    shape = input_pts.shape[:-1]
+    xf = _lib.f32c(input_pts.detach().reshape(-1, module.input_dim))
+    vf = _lib.f32c(input_views.detach().expand(*shape, 3).reshape(-1, 3))
+    n, dev = xf.shape[0], xf.device
+    desc = _descriptor(module)
+    sigma = torch.empty(n, dtype=torch.float32, device=dev)
+    rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        for i0 in range(0, n, _MAX_POINTS_PER_CALL):
+            m = min(_MAX_POINTS_PER_CALL, n - i0)
+            need = lib.nr_nerf_forward_f32_workspace(C.byref(desc), m)
+            ws = _lib.workspace(need, dev)
+            _lib.check(lib.nr_nerf_forward_f32(C.byref(desc), _lib.ptr(xf[i0:i0 + m]), _lib.ptr(vf[i0:i0 + m]), m,
+                                               _lib.ptr(sigma[i0:i0 + m]), _lib.ptr(rgb[i0:i0 + m]), _lib.ptr(ws),
+                                               ws.numel(), st), "nerf_forward")
+    return sigma.reshape(shape), rgb.reshape(*shape, 3)

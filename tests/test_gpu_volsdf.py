@@ -1,0 +1,109 @@
+"""GPU parity of the VolSDF path against the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+import neurecon_b200
+from conftest import cpu_state_dict, frac_close, load_golden, rel_err
+from test_oracle_golden import VOLSDF_CFG, build_volsdf
+from oracle import nets, sampling, volsdf as ov
+from neurecon_b200.models.frameworks import volsdf
+from neurecon_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(params=["fp32", "fp16"])
+def tier(request):
+    neurecon_b200.set_precision(request.param)
+    yield request.param
+    neurecon_b200.set_precision("fp16")
+
+
+def test_error_bound_golden_incl_inf_pattern():
+    g = load_golden("volsdf_error_bound.npz")
+    for i, beta in enumerate(g["betas"].tolist()):
+        b = torch.tensor(beta)
+        got = volsdf.error_bound(g["d_vals"].to(DEV), g["sdf"].to(DEV), 1.0 / b, b).cpu()
+        want = g["bound_%d" % i]
+        assert torch.equal(torch.isinf(got), torch.isinf(want))
+        fin = torch.isfinite(want)
+        assert rel_err(got[fin], want[fin]) < 1e-4
+    # per-ray alpha / beta tensors [R,1]
+    R = g["d_vals"].shape[0]
+    bb = torch.linspace(0.05, 0.5, R)[:, None]
+    got = volsdf.error_bound(g["d_vals"].to(DEV), g["sdf"].to(DEV), (1.0 / bb).to(DEV), bb.to(DEV)).cpu()
+    want = ov.error_bound(g["d_vals"], g["sdf"], 1.0 / bb, bb)
+    fin = torch.isfinite(want)
+    assert torch.equal(torch.isinf(got), torch.isinf(want)) and rel_err(got[fin], want[fin]) < 1e-4
+
+
+@pytest.mark.parametrize("beta_net", [0.1, 0.01, 0.003, 0.001])
+def test_fine_sample_analytic_sdf(beta_net):
+    """fine_sample with an analytic sphere SDF callback: iter_usage identical,
+    beta_map <= 1e-5, d_fine <= 1e-4."""
+    rs = np.random.RandomState(17)
+    R = 45
+    o, d = synthetic.make_rays(R, shell_radius=2.6, jitter=0.25, seed=17)
+    d = torch.nn.functional.normalize(d, dim=-1)
+    sdf_fn = lambda p: p.norm(dim=-1) - 1.0
+    t = sampling.linspace01(128)
+    init = (0.0 * (1 - t) + 6.0 * t).expand(R, 128).contiguous()
+    b = torch.tensor(beta_net)
+    want_d, want_b, want_it = ov.fine_sample(sdf_fn, init, o, d, 1.0 / b, b, 6.0, eps=0.1, max_iter=5,
+                                             max_bisection=10, final_N_importance=64, N_up=128, perturb=False)
+    got_d, got_b, got_it = volsdf.fine_sample(sdf_fn, init.to(DEV), o.to(DEV), d.to(DEV), (1.0 / b).to(DEV), b.to(DEV),
+                                              6.0, eps=0.1, max_iter=5, max_bisection=10, final_N_importance=64,
+                                              N_up=128, perturb=False)
+    assert got_d.shape == (R, 64) and got_b.shape == (R, 1) and got_it.shape == (R,)
+    assert torch.equal(got_it.cpu(), want_it), (got_it.cpu(), want_it)
+    assert rel_err(got_b, want_b) < 1e-5
+    assert frac_close(got_d, want_d, 1e-4) > 0.97
+    # sync-free variant gives the same result
+    d2, b2, it2 = volsdf.fine_sample(sdf_fn, init.to(DEV), o.to(DEV), d.to(DEV), (1.0 / b).to(DEV), b.to(DEV), 6.0,
+                                     eps=0.1, max_iter=5, max_bisection=10, final_N_importance=64, N_up=128,
+                                     perturb=False, early_exit=False)
+    assert torch.equal(d2, got_d) and torch.equal(it2, got_it)
+
+
+@pytest.mark.parametrize("tag,beta_init,nerfpp", [("b0p1", 0.1, False), ("b0p01", 0.01, False),
+                                                  ("b0p003", 0.003, False), ("b0p01_nerfpp", 0.01, True)])
+def test_volsdf_render_vs_golden(tier, tag, beta_init, nerfpp):
+    g = load_golden("volsdf_render_%s_r24.npz" % tag)
+    m = build_volsdf(beta_init, nerfpp, device=DEV)
+    o, d = synthetic.make_rays(24, shell_radius=3.0 / 1.1, jitter=0.1, seed=3)
+    with torch.no_grad():
+        rgb, depth, ret = volsdf.volume_render(
+            o.to(DEV), d.to(DEV), m, calc_normal=True, detailed_output=True, perturb=False, near=0.0, far=6.0,
+            obj_bounding_radius=3.0, max_upsample_steps=5 if nerfpp else 6, use_nerfplusplus=nerfpp, N_outside=32)
+    keys = ["rgb", "depth_volume", "mask_volume", "normals_volume", "implicit_surface", "implicit_nablas", "radiance",
+            "alpha", "p_i", "visibility_weights", "d_vals", "sigma", "beta_map", "iter_usage"]
+    if nerfpp:
+        keys += ["sigma_out", "radiance_out"]
+    assert list(ret.keys()) == keys
+    Mtot = 224 if nerfpp else 192
+    assert ret["d_vals"].shape == (24, Mtot) and ret["visibility_weights"].shape == (24, Mtot - 1)
+    assert ret["beta_map"].shape == (24, 1) and ret["iter_usage"].shape == (24,)
+    tol = 1e-4 if tier == "fp32" else 1e-2
+    if tier == "fp32":
+        assert torch.equal(ret["iter_usage"].cpu(), g["iter_usage"])
+        assert rel_err(ret["beta_map"], g["beta_map"]) < 1e-5
+    else:
+        # the tensor tier's sdf differs by ~1e-3, which may move a ray across the eps threshold
+        assert (ret["iter_usage"].cpu() == g["iter_usage"]).float().mean() > 0.8
+    errs = {k: rel_err(ret[k], g[k]) for k in ("rgb", "depth_volume", "mask_volume", "normals_volume")}
+    assert all(e < tol for e in errs.values()), errs
+
+
+def test_volsdf_batched_and_chunked():
+    neurecon_b200.set_precision("fp32")
+    m = build_volsdf(0.01, False, device=DEV)
+    o, d = synthetic.make_rays(30, shell_radius=3.0 / 1.1, jitter=0.1, seed=8)
+    o, d = o.to(DEV), d.to(DEV)
+    with torch.no_grad():
+        a = volsdf.volume_render(o, d, m, detailed_output=False, max_upsample_steps=6)[0]
+        b = volsdf.volume_render(o.reshape(2, 15, 3), d.reshape(2, 15, 3), m, batched=True, detailed_output=False,
+                                 max_upsample_steps=6, rayschunk=4)[0]
+    neurecon_b200.set_precision("fp16")
+    assert b.shape == (2, 15, 3) and torch.equal(b.reshape(30, 3), a)

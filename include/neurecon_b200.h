@@ -228,6 +228,39 @@ int nr_volsdf_composite(const float* sdf, const float* nablas, const float* radi
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * UNISURF -- models/ray_casting.py, models/frameworks/unisurf.py
+ * ------------------------------------------------------------------------------------------ */
+/* unisurf.py:124-131 + ray_casting.py:69-77: normalised dirs [R,3], near/far [R] from the sphere of
+ * interest (NAN bypass = none) and the n_steps uniform proposal points pts [R,n_steps,3]. */
+int nr_unisurf_ray_setup(const float* rays_o, const float* rays_d, int64_t R, float radius,
+                         float near_bypass, float far_bypass, int32_t n_steps, float* dirs, float* near,
+                         float* far, float* pts, void* stream);
+/* ray_casting.py:84-137: val [R,n_steps] = surface_query_fn(proposals); first sign change of
+ * (val - logit_tau), the three masks (uint8 [R]), the secant bracket and first estimate
+ * (state [5][R] = d_low, f_low, d_high, f_high, d_pred) and its point pts_pred [R,3]. */
+int nr_unisurf_first_crossing(const float* val, const float* rays_o, const float* dirs, const float* near,
+                              const float* far, int64_t R, int32_t n_steps, float logit_tau, float* state,
+                              uint8_t* mask, uint8_t* mask_sign_change, uint8_t* mask_0_free,
+                              float* pts_pred, void* stream);
+/* run_secant_method, one step (ray_casting.py:16-29): f_mid [R] = surface_query_fn(pts_pred). */
+int nr_unisurf_secant_step(const float* f_mid, float logit_tau, const float* rays_o, const float* dirs,
+                           const uint8_t* mask, int64_t R, float* state, float* pts_pred, void* stream);
+/* ray_casting.py:139-151 + unisurf.py:147-207: depth_surface [R] (clamped to [near, far]),
+ * surface_pts [R,3], the n_query interval + n_free free-space depths merged and sorted d_all
+ * [R,n_query+n_free] and their points.  u_int / u_free: stratified jitter uniforms or NULL. */
+int nr_unisurf_sample(const float* rays_o, const float* dirs, const float* near, const float* far,
+                      const float* state, const uint8_t* mask, const uint8_t* mask_sign_change,
+                      const uint8_t* mask_0_free, int64_t R, float interval, float too_close,
+                      int32_t n_query, int32_t n_free, const float* u_int, const float* u_free,
+                      float* depth_surface, float* surface_pts, float* d_all, float* pts, void* stream);
+/* unisurf.py:216-240: occupancy logits [R,M] -> alpha, exclusive-cumprod weights, rgb / depth / acc /
+ * normals; optional per-sample alpha_out, weights_out [R,M]. */
+int nr_unisurf_composite(const float* logits, const float* nablas, const float* radiance,
+                         const float* d_all, int64_t R, int32_t M, int32_t white_bkgd, float* rgb,
+                         float* depth, float* acc, float* normals, float* alpha_out, float* weights_out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * bf16 tier: fused PE + SDF MLP (+ forward-mode normals) + radiance MLP on tcgen05 / TMEM.
  * The host packs the weights once into a pre-swizzled bf16 image (16 KB chunks = A tiles of
  * 128 features x 64 k) and describes the network as a short program of steps; the kernel
@@ -267,11 +300,13 @@ typedef struct {
 } nr_umma_program_t;
 
 /* x [n,3]; view [n,3] or NULL; outputs (each may be NULL): sdf [n], nabla [n,3], feat [n,feat_ld],
- * rgb [n,3].  image: the packed bf16 weight chunks, bias: fp32 bias table. */
+ * rgb [n,3].  image: the packed 16-bit weight chunks, bias: fp32 bias table.  normal_scale: NULL, or
+ * 3 device floats multiplied into the normals the radiance net sees (UNISURF's chunk-wide
+ * F.normalize, unisurf.py:36); the nabla output stays unscaled. */
 int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
                         const float* bias, size_t bias_floats, const float* x, const float* view,
                         int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
-                        void* stream);
+                        const float* normal_scale, void* stream);
 
 /* profiling hook (tools/trace_mlp.py): device buffer [3][2048][4] int64 receiving clock64 stamps of the
  * MMA <-> epilogue hand-offs of CTA 0; NULL disables. */

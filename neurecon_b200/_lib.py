@@ -80,7 +80,12 @@ _SIGNATURES = {
     "nr_volsdf_merge": (C.c_int, [_P, _P, _P, _I64, _F, _I32, _P, _I32, _P, _P, _P]),
     "nr_volsdf_composite": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P,
                                       _P, _P, _P]),
-    "nr_mlp_umma_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _P, _I64, _P, _P, _P, _I64, _P, _P]),
+    "nr_unisurf_ray_setup": (C.c_int, [_P, _P, _I64, _F, _F, _F, _I32, _P, _P, _P, _P, _P]),
+    "nr_unisurf_first_crossing": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P]),
+    "nr_unisurf_secant_step": (C.c_int, [_P, _F, _P, _P, _P, _I64, _P, _P, _P]),
+    "nr_unisurf_sample": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _F, _F, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "nr_unisurf_composite": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "nr_mlp_umma_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _P, _I64, _P, _P, _P, _I64, _P, _P, _P]),
     "nr_mlp_umma_set_trace": (C.c_int, [_P]),
     "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
     "nr_neus_composite": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),

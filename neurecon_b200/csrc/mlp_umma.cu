@@ -177,6 +177,7 @@ struct KArgs {
   float* feat;         // [n, feat_ld] or null
   int64_t feat_ld;
   float* rgb;          // [n,3] or null
+  const float* normal_scale;  // [3] or null: normals fed to the radiance net = nabla * scale (UNISURF)
   long long* trace;    // profiling only: [3][kTraceCap][4] (event, step*2+tile, clock, pair) from CTA 0
 };
 constexpr int kTraceCap = 2048;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                 if (c == 0) {
                   if (a.sdf && gp < a.n) a.sdf[gp] = mine + b;
                 } else {
-                  nabs[3 * lane + (c - 1)] = mine;
+                  nabs[3 * lane + (c - 1)] = a.normal_scale ? mine * a.normal_scale[c - 1] : mine;
                   if (a.nabla && gp < a.n) a.nabla[gp * 3 + (c - 1)] = mine;
                 }
               } else {
@@ -542,7 +543,7 @@ extern "C" int nr_mlp_umma_set_trace(void* buf) { g_trace = (long long*)buf; ret
 extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
                                    const float* bias, size_t bias_floats, const float* x, const float* view,
                                    int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
-                                   void* stream) {
+                                   const float* normal_scale, void* stream) {
   NR_CHECK_ARG(prog && image && bias && x, "nr_mlp_umma_forward: null pointer");
   NR_CHECK_ARG(n >= 0, "nr_mlp_umma_forward: n < 0");
   NR_CHECK_ARG(prog->n_steps >= 1 && prog->n_steps <= NR_UMMA_MAX_STEPS, "nr_mlp_umma_forward: n_steps=%d", prog->n_steps);
@@ -585,7 +586,7 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
   }
   DevProgram dp;
   dp.p = *prog;
-  KArgs ka{(const uint8_t*)image, bias, x, view, n, sdf, nabla, feat, feat_ld, rgb, g_trace};
+  KArgs ka{(const uint8_t*)image, bias, x, view, n, sdf, nabla, feat, feat_ld, rgb, normal_scale, g_trace};
   if (prog->operand_f16) mlp_umma_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
   else mlp_umma_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
   NR_CHECK_LAUNCH("mlp_umma_kernel");

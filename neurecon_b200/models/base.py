@@ -238,7 +238,7 @@ class ImplicitSurface(nn.Module):
         return c[1]
 
     def _run_umma(self, x, mode, want_feat=False, radiance_net=None, view_dirs=None, want_sdf=True,
-                  want_nablas=True):
+                  want_nablas=True, normal_scale=None):
         """One launch of the fused tcgen05 kernel.  mode: 'sdf' | 'nablas' | 'fused'."""
         _lib.require_cuda(x, view_dirs)
         lib = _lib.get_lib()
@@ -259,7 +259,7 @@ class ImplicitSurface(nn.Module):
             _lib.check(lib.nr_mlp_umma_forward(
                 C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias), net.bias.numel(),
                 _lib.ptr(xf), _lib.ptr(vf), n, _lib.ptr(sdf), _lib.ptr(nabla), _lib.ptr(feat),
-                net.feat_dim, _lib.ptr(rgb), _lib.stream_ptr(dev)), "mlp_umma_forward")
+                net.feat_dim, _lib.ptr(rgb), _lib.ptr(normal_scale), _lib.stream_ptr(dev)), "mlp_umma_forward")
         rs = lambda t, *tail: None if t is None else t.reshape(*shape, *tail)
         return rs(sdf), rs(nabla, 3), rs(feat, net.feat_dim), rs(rgb, 3)
 
@@ -408,18 +408,31 @@ class RadianceNet(nn.Module):
         return rgb.reshape(*shape, 3)
 
 
-def query_radiance(surface, radiance_net, x, view_dirs, normalize_normals=False):
+def query_radiance(surface, radiance_net, x, view_dirs, chunk_normalize=False):
     """Inference composition of ``forward_with_nablas`` + ``RadianceNet.forward`` at the same
-    points (NeuS.forward_radiance neus.py:103-106, VolSDF.forward volsdf.py:327-331): returns
-    (radiance, sdf, nablas).  bf16 tier: ONE fused kernel, the 256-wide feature and the normal
-    never leave the SM; fp32 tier: the two library calls."""
-    if _lib.tensor_tier() and not normalize_normals:
-        sdf, nabla, _, rgb = surface._run_umma(x, "fused", radiance_net=radiance_net, view_dirs=view_dirs)
+    points (NeuS.forward_radiance neus.py:103-106, VolSDF.forward volsdf.py:327-331, UNISURF.forward
+    unisurf.py:34-38): returns (radiance, sdf, nablas).  Tensor tier: ONE fused kernel, the 256-wide
+    feature and the normal never leave the SM; fp32 tier: the two library calls.
+
+    ``chunk_normalize`` reproduces UNISURF's ``F.normalize(nablas)`` (no ``dim`` => dim=1 => the POINT
+    axis of the whole chunk) for a flat chunk x [n, 3]: every component is
+    divided by its L2 norm over all n points.  That couples the points, so it takes two passes: normals
+    first, then the (3-float) column norms, then the radiance with the scale applied inside the kernel."""
+    if not chunk_normalize:
+        if _lib.tensor_tier():
+            sdf, nabla, _, rgb = surface._run_umma(x, "fused", radiance_net=radiance_net, view_dirs=view_dirs)
+            return rgb, sdf, nabla
+        sdf, nabla, feat = surface._run(x, want_nablas=True, want_feat=True)
+        return radiance_net.forward(x, view_dirs, nabla, feat), sdf, nabla
+    if _lib.tensor_tier():
+        sdf, nabla, _, _ = surface._run_umma(x, "nablas")
+        scale = (1.0 / nabla.reshape(-1, 3).norm(dim=0).clamp_min(1e-12)).contiguous()
+        _, _, _, rgb = surface._run_umma(x, "fused", radiance_net=radiance_net, view_dirs=view_dirs, want_sdf=False,
+                                         want_nablas=False, normal_scale=scale)
         return rgb, sdf, nabla
     sdf, nabla, feat = surface._run(x, want_nablas=True, want_feat=True)
-    normals = torch.nn.functional.normalize(nabla) if normalize_normals else nabla
-    rgb = radiance_net.forward(x, view_dirs, normals, feat)
-    return rgb, sdf, nabla
+    normals = nabla / nabla.reshape(-1, 3).norm(dim=0).clamp_min(1e-12)
+    return radiance_net.forward(x, view_dirs, normals, feat), sdf, nabla
 
 
 class NeRF(nn.Module):

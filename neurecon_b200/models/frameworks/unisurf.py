@@ -1,7 +1,7 @@
 """Drop-in for the reference's ``models/frameworks/unisurf.py`` hot path: the ``UNISURF`` module
 (:16-62), ``volume_render`` (:64-283) and ``SingleRenderer`` (:285-291)."""
 from collections import OrderedDict
-from typing import Union
+from typing import Optional, Union
 
 import numpy as np
 import torch
@@ -45,3 +45,136 @@ class UNISURF(nn.Module):
         else:
             odds = np.exp(-1. * imp_surface)
         return odds / (1 + odds)
+
+
+def volume_render(
+        rays_o,
+        rays_d,
+        model: UNISURF,
+
+        batched=False,
+        batched_info={},
+
+        # render algorithm config
+        calc_normal=False,
+        logit_tau=0.0,
+        use_view_dirs=True,
+        method='secant',
+        rayschunk=65536,
+        netchunk=1048576,
+        white_bkgd=False,
+        near_bypass: Optional[float] = None,
+        far_bypass: Optional[float] = None,
+
+        # render function config
+        detailed_output=True,
+        show_progress=False,
+
+        # sampling related
+        radius_of_interest=4.0,
+        perturb=False,
+        interval=1.0,
+        too_close_threshold=0.1,
+        N_query=64,
+        N_freespace=32,
+        **dummy_kwargs):
+    """unisurf.py:64-283.  rays_o / rays_d: [(B,) N_rays, 3].  Returns (rgb, depth_volume, ret).
+
+    Like the reference, the normals fed to the radiance net are normalised over the point axis of each
+    net-chunk (``F.normalize`` without ``dim``, unisurf.py:36), so results depend on ``rayschunk`` /
+    ``netchunk`` exactly as they do there; ``batched=False`` (which raises IndexError in the reference)
+    is treated as one batch."""
+    if method != 'secant':
+        raise NotImplementedError("only method='secant' (every shipped config) is built")
+    if not use_view_dirs:
+        raise NotImplementedError("use_view_dirs=False is not supported")
+    _lib.require_cuda(rays_o, rays_d)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
+        raise NotImplementedError("neurecon_b200: UNISURF volume_render under autograd is not built yet; "
+                                  "wrap inference in torch.no_grad()")
+    from ..ray_casting import _root_find
+    lib = _lib.get_lib()
+    B = rays_d.shape[0] if batched else 1
+    dev = rays_o.device
+    o_b = _lib.f32c(rays_o.reshape(B, -1, 3))
+    d_b = _lib.f32c(rays_d.reshape(B, -1, 3))
+    n_rays = o_b.shape[1]
+    f = dict(dtype=torch.float32, device=dev)
+    M = N_query + N_freespace
+    N_steps, N_secant = 256, 8  # root_finding_surface_points defaults (ray_casting.py:43-46)
+    nan = float("nan")
+    surface_fn = model.implicit_surface.forward
+
+    per_batch = []
+    with torch.cuda.device(dev), torch.no_grad():
+        st = _lib.stream_ptr(dev)
+        for b in range(B):
+            outs = []
+            for i0 in range(0, n_rays, int(rayschunk)):
+                ro, rd = o_b[b, i0:i0 + rayschunk].contiguous(), d_b[b, i0:i0 + rayschunk].contiguous()
+                R = ro.shape[0]
+                dirs, near, far = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
+                pts_prop = torch.empty(R, N_steps, 3, **f)
+                _lib.check(lib.nr_unisurf_ray_setup(
+                    _lib.ptr(ro), _lib.ptr(rd), R, float(radius_of_interest), nan if near_bypass is None else float(near_bypass),
+                    nan if far_bypass is None else float(far_bypass), N_steps, _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far),
+                    _lib.ptr(pts_prop), st), "unisurf_ray_setup")
+                state, mask, msc, m0 = _root_find(surface_fn, ro, dirs, near, far, pts_prop, N_steps, logit_tau, N_secant)
+                u_int = torch.rand([R, N_query], device=dev) if perturb else None     # unisurf.py:164
+                u_free = torch.rand([R, N_freespace], device=dev) if perturb else None  # unisurf.py:193
+                depth_s, surf_pts = torch.empty(R, **f), torch.empty(R, 3, **f)
+                d_all, pts = torch.empty(R, M, **f), torch.empty(R, M, 3, **f)
+                _lib.check(lib.nr_unisurf_sample(
+                    _lib.ptr(ro), _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far), _lib.ptr(state), _lib.ptr(mask),
+                    _lib.ptr(msc), _lib.ptr(m0), R, float(interval), float(too_close_threshold), N_query, N_freespace,
+                    _lib.ptr(u_int), _lib.ptr(u_free), _lib.ptr(depth_s), _lib.ptr(surf_pts), _lib.ptr(d_all),
+                    _lib.ptr(pts), st), "unisurf_sample")
+                # network query, one net-chunk of the flattened points at a time (batchify_query semantics)
+                flat_pts = pts.reshape(-1, 3)
+                flat_views = dirs.unsqueeze(-2).expand(R, M, 3).reshape(-1, 3)
+                rad_l, sdf_l, nab_l = [], [], []
+                for j0 in range(0, R * M, int(netchunk)):
+                    r_, s_, n_ = query_radiance(model.implicit_surface, model.radiance_net, flat_pts[j0:j0 + netchunk],
+                                                flat_views[j0:j0 + netchunk], chunk_normalize=True)
+                    rad_l.append(r_); sdf_l.append(s_); nab_l.append(n_)
+                radiances = (rad_l[0] if len(rad_l) == 1 else torch.cat(rad_l)).reshape(R, M, 3)
+                logits = (sdf_l[0] if len(sdf_l) == 1 else torch.cat(sdf_l)).reshape(R, M)
+                nablas = (nab_l[0] if len(nab_l) == 1 else torch.cat(nab_l)).reshape(R, M, 3)
+                rgb, depth, acc = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
+                normals = torch.empty(R, 3, **f) if calc_normal else None
+                alpha = torch.empty(R, M, **f) if detailed_output else None
+                w = torch.empty(R, M, **f) if detailed_output else None
+                _lib.check(lib.nr_unisurf_composite(
+                    _lib.ptr(logits), _lib.ptr(nablas) if calc_normal else None, _lib.ptr(radiances), _lib.ptr(d_all), R, M,
+                    int(bool(white_bkgd)), _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(normals),
+                    _lib.ptr(alpha), _lib.ptr(w), st), "unisurf_composite")
+                ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
+                if calc_normal:
+                    ret_i['normals_volume'] = normals
+                if detailed_output:
+                    ret_i['surface_points'] = surf_pts
+                    ret_i['mask_surface'] = mask.bool()
+                    ret_i['depth_surface'] = depth_s
+                    ret_i['radiance'] = radiances
+                    ret_i['implicit_surface'] = logits
+                    ret_i['implicit_nablas'] = nablas
+                    ret_i['alpha'] = alpha
+                    ret_i['visibility_weights'] = w
+                outs.append(ret_i)
+            per_batch.append(OrderedDict((k, outs[0][k] if len(outs) == 1 else torch.cat([o_[k] for o_ in outs], 0))
+                                         for k in outs[0].keys()))
+    ret = OrderedDict()
+    for k in per_batch[0].keys():
+        ret[k] = torch.stack([pb[k] for pb in per_batch], 0) if batched else per_batch[0][k]
+    return ret['rgb'], ret['depth_volume'], ret
+
+
+class SingleRenderer(nn.Module):
+    """unisurf.py:285-291."""
+
+    def __init__(self, model: UNISURF):
+        super().__init__()
+        self.model = model
+
+    def forward(self, rays_o, rays_d, **kwargs):
+        return volume_render(rays_o, rays_d, self.model, **kwargs)

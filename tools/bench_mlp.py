@@ -23,7 +23,7 @@ def run(net, prog, x, v, n, reps):
     def go():
         _lib.check(lib.nr_mlp_umma_forward(C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias),
                                            net.bias.numel(), _lib.ptr(x), _lib.ptr(v), n, _lib.ptr(sdf), _lib.ptr(nab),
-                                           None, 256, _lib.ptr(rgb), _lib.stream_ptr(dev)), "umma")
+                                           None, 256, _lib.ptr(rgb), None, _lib.stream_ptr(dev)), "umma")
     for _ in range(2):
         go()
     torch.cuda.synchronize()

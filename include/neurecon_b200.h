@@ -136,6 +136,12 @@ int nr_sample_pdf(const float* bins, const float* weights, const float* u, int64
                   int32_t N, int32_t cdf_is_given, float eps, float* samples, int32_t* below,
                   int32_t* above, float* cdf_out, void* stream);
 
+/* Lattice points i0 .. i0+count-1 of the N^3 grid of extract_mesh (utils/mesh_util.py:82-100), fp32
+ * [count,3], computed in float64 like the reference.  faithful != 0 reproduces the reference's
+ * true-division indices (a sheared lattice), 0 gives the intended integer lattice. */
+int nr_grid_points(int64_t i0, int64_t count, int32_t N, double volume_size, int32_t faithful, float* pts,
+                   void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * NeuS -- models/frameworks/neus.py
  * ------------------------------------------------------------------------------------------ */

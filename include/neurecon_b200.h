@@ -99,6 +99,35 @@ int nr_radiance_forward_f32(const nr_radiance_net_t* net, const float* x, const 
                             const float* normals, const float* feat, int64_t feat_ld, int64_t n,
                             float* rgb, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Building blocks of the training path (fp32).  neurecon_b200/models/autograd.py composes them into
+ * torch.autograd.Functions that replace autograd through ImplicitSurface.forward_with_nablas
+ * (create_graph=True, models/base.py:265-282) and RadianceNet.forward: the forward-mode network is
+ * differentiated by hand, including the second-order path the eikonal loss needs (neus.py:458).
+ * ------------------------------------------------------------------------------------------ */
+/* Y[M,N] = epilogue(A[M,K] W[N,K]^T + bias).  mode: 0 none, 1 softplus(beta=100) (S, if given, receives
+ * its derivative), 2 ReLU, 3 sigmoid, 4 tangent: Y = (A W^T) * aux[row % m_val, col] (no bias),
+ * 5 tangent-linear: Y = A W^T (no bias).  lda/ldw multiples of 4. */
+int nr_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, const float* bias, int64_t M,
+                int32_t N, int32_t K, float* Y, int32_t ldy, int32_t mode, float* S, int32_t lds,
+                const float* aux, int32_t ldaux, int64_t m_val, void* stream);
+/* dW[N,K] += G[rows,N]^T X[rows,K]  (weight gradient; split over rows, fp32 atomics) */
+int nr_gemm_tn_f32(const float* G, int32_t ldg, const float* X, int32_t ldx, int64_t rows, int32_t N,
+                   int32_t K, float* dW, int32_t lddw, void* stream);
+/* out[N] += column sums of G[rows,N]  (bias gradient) */
+int nr_colsum_f32(const float* G, int32_t ldg, int64_t rows, int32_t N, float* out, void* stream);
+/* in place: gh <- g_z = gh*S + sum_c gt_c*u_c*100*S*(1-S),  gt_c <- g_u_c = gt_c*S.
+ * gh,S: [n,N]; gt,u: [3n,N] (component-major row blocks). */
+int nr_sdf_bwd_act_f32(float* gh, int32_t ldgh, float* gt, int32_t ldgt, const float* S, int32_t lds,
+                       const float* u, int32_t ldu, int64_t n, int32_t N, void* stream);
+/* in place: x *= (ref > 0) (mode 0, ReLU backward) or x *= ref*(1-ref) (mode 1, sigmoid backward) */
+int nr_act_bwd_f32(float* x, int32_t ldx, const float* ref, int32_t ldr, int64_t rows, int32_t N,
+                   int32_t mode, void* stream);
+/* Embedder.forward (models/base.py:46-64) into pe[:, col_off:], and/or its three tangents d pe/d x_c
+ * stacked as row blocks [c*n + m] into tpe[:, tcol_off:] (in_dim = 3 only for the tangents). */
+int nr_embed_f32(const float* x, int64_t n, int32_t in_dim, int32_t multires, float* pe, int32_t ld,
+                 int32_t col_off, float* tpe, int32_t ldt, int32_t tcol_off, void* stream);
+
 /* NeRF++ background network, NeRF.forward(input_pts, input_views) -- models/base.py:395-453
  * (use_view_dirs=True).  Plain (not weight-normed) layers; weights fp32 [out, pad4(in)]. */
 typedef struct {

@@ -9,6 +9,7 @@
 // the same weights as 3n extra GEMM rows, so forward_with_nablas is four row blocks through one
 // kernel and nothing but the current layer has to be kept (models/base.py:243-282 does the same
 // job with autograd.grad).  The tcgen05 path (mlp_umma.cu) uses the same formulation.
+#include <algorithm>
 #include "common.cuh"
 
 namespace {
@@ -538,4 +539,203 @@ extern "C" int nr_nerf_forward_f32(const nr_nerf_net_t* net, const float* x, con
     if ((rc = launch_gemm(g, st))) return rc;
   }
   return NR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Building blocks of the TRAINING path (neurecon_b200/models/autograd.py).  The backward of the
+// forward-mode network (value rows h, tangent rows t_c; z = W h + b, u_c = W t_c, h' = sp(z),
+// t'_c = sp'(z) u_c) for upstream gradients (g_h', g_t'_c) is
+//     g_u_c = g_t'_c * sp'(z)
+//     g_z   = g_h' * sp'(z) + sum_c g_t'_c * u_c * sp''(z)          <- second-order (eikonal) path
+//     g_W   = g_z^T h + sum_c g_u_c^T t_c ,  g_b = colsum(g_z)
+//     g_h   = g_z W ,  g_t_c = g_u_c W
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// g_z / g_u in place of g_h' / g_t' (see above).  S = sp'(z) [n, N]; u [3n, N]; sp'' = 100 S (1 - S).
+__global__ void sdf_bwd_act_kernel(float* __restrict__ gh, int ldgh, float* __restrict__ gt, int ldgt,
+                                   const float* __restrict__ S, int lds, const float* __restrict__ u, int ldu, int64_t n,
+                                   int N) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * N) return;
+  const int64_t m = idx / N;
+  const int j = (int)(idx % N);
+  const float s = S[m * lds + j];
+  const float s2 = 100.0f * s * (1.0f - s);
+  float gz = gh[m * ldgh + j] * s;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int64_t r = c * n + m;
+    const float g = gt[r * ldgt + j];
+    gz += g * u[r * ldu + j] * s2;
+    gt[r * ldgt + j] = g * s;
+  }
+  gh[m * ldgh + j] = gz;
+}
+
+// dW[i, j] += sum_r G[r, i] * X[r, j]   (i < N, j < K), split over row ranges, fp32 atomics.
+__global__ void __launch_bounds__(kThreads) gemm_tn_kernel(const float* __restrict__ G, int ldg,
+                                                           const float* __restrict__ X, int ldx, int64_t rows, int N,
+                                                           int K, float* __restrict__ dW, int lddw, int rows_per_block) {
+  __shared__ __align__(16) float As[2][BK][kPadM];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * BM, j0 = blockIdx.y * BN;
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  const int lr = tid >> 5, lc = (tid & 31) * 4;  // 8 rows x 128 columns per tile: one float4 per thread
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  auto load = [&](const float* base, int ld, int64_t r, int c0, int cmax, float (&v)[4]) {
+    v[0] = v[1] = v[2] = v[3] = 0.0f;
+    if (r >= r_end) return;
+    const float* p = base + r * ld + c0;
+    if (c0 + 3 < cmax && (ld & 3) == 0) {
+      const float4 q = *reinterpret_cast<const float4*>(p);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (c0 + j < cmax) v[j] = p[j];
+    }
+  };
+  float ra[4], rb[4];
+  const int nk = (int)((r_end - r_begin + BK - 1) / BK);
+  if (nk <= 0) return;
+  load(G, ldg, r_begin + lr, i0 + lc, N, ra);
+  load(X, ldx, r_begin + lr, j0 + lc, K, rb);
+  *reinterpret_cast<float4*>(&As[0][lr][lc]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+  *reinterpret_cast<float4*>(&Bs[0][lr][lc]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      load(G, ldg, r_begin + (int64_t)(kt + 1) * BK + lr, i0 + lc, N, ra);
+      load(X, ldx, r_begin + (int64_t)(kt + 1) * BK + lr, j0 + lc, K, rb);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      *reinterpret_cast<float4*>(&As[cur ^ 1][lr][lc]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+      *reinterpret_cast<float4*>(&Bs[cur ^ 1][lr][lc]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (row >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = j0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (col < K) atomicAdd(&dW[(size_t)row * lddw + col], acc[i][j]);
+    }
+  }
+}
+
+// out[j] += sum_r G[r, j]
+__global__ void colsum_kernel(const float* __restrict__ G, int ldg, int64_t rows, int N, float* __restrict__ out,
+                              int rows_per_block) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s = 0.0f;
+  for (int64_t r = r0; r < r1; ++r) s += G[r * ldg + j];
+  atomicAdd(&out[j], s);
+}
+
+// y = x * (ref > 0)   (ReLU backward) / y = x * ref * (1 - ref)   (sigmoid backward), in place on x
+__global__ void act_bwd_kernel(float* __restrict__ x, int ldx, const float* __restrict__ ref, int ldr, int64_t rows,
+                               int N, int mode) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= rows * N) return;
+  const int64_t r = idx / N;
+  const int j = (int)(idx % N);
+  const float y = ref[r * ldr + j];
+  x[r * ldx + j] *= (mode == 0) ? (y > 0.0f ? 1.0f : 0.0f) : y * (1.0f - y);
+}
+}  // namespace
+
+extern "C" int nr_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, const float* bias, int64_t M,
+                           int32_t N, int32_t K, float* Y, int32_t ldy, int32_t mode, float* S, int32_t lds,
+                           const float* aux, int32_t ldaux, int64_t m_val, void* stream) {
+  NR_CHECK_ARG(M >= 0 && M < ((int64_t)1 << 31) && N >= 1 && K >= 1, "nr_gemm_f32: bad sizes");
+  if (M == 0) return NR_OK;
+  NR_CHECK_ARG(A && W && Y, "nr_gemm_f32: null pointer");
+  NR_CHECK_ARG(mode >= EPI_NONE && mode <= EPI_TANGENT_LIN, "nr_gemm_f32: mode %d", mode);
+  NR_CHECK_ARG((lda & 3) == 0 && (ldw & 3) == 0, "nr_gemm_f32: lda / ldw must be multiples of 4");
+  NR_CHECK_ARG(mode == EPI_TANGENT || mode == EPI_TANGENT_LIN || bias, "nr_gemm_f32: bias required");
+  NR_CHECK_ARG(mode != EPI_TANGENT || (aux && m_val > 0), "nr_gemm_f32: tangent mode needs the derivative matrix");
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.M = (int)M; g.N = N; g.K = K; g.Y = Y; g.ldy = ldy;
+  g.S = S; g.lds = lds; g.Sin = aux; g.ldsin = ldaux; g.m_val = (int)m_val; g.mode = mode;
+  return launch_gemm(g, (cudaStream_t)stream);
+}
+
+extern "C" int nr_gemm_tn_f32(const float* G, int32_t ldg, const float* X, int32_t ldx, int64_t rows, int32_t N,
+                              int32_t K, float* dW, int32_t lddw, void* stream) {
+  NR_CHECK_ARG(rows >= 0 && N >= 1 && K >= 1, "nr_gemm_tn_f32: bad sizes");
+  if (rows == 0) return NR_OK;
+  NR_CHECK_ARG(G && X && dW, "nr_gemm_tn_f32: null pointer");
+  const int tiles = (int)(nr_cdiv(N, BM) * nr_cdiv(K, BN));
+  int splits = (int)std::min<int64_t>(std::max<int64_t>(1, (148 * 4) / tiles), nr_cdiv(rows, 256));
+  const int rpb = (int)(nr_cdiv(nr_cdiv(rows, splits), BK) * BK);
+  splits = (int)nr_cdiv(rows, rpb);
+  dim3 grid((unsigned)nr_cdiv(N, BM), (unsigned)nr_cdiv(K, BN), (unsigned)splits);
+  gemm_tn_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(G, ldg, X, ldx, rows, N, K, dW, lddw, rpb);
+  NR_CHECK_LAUNCH("gemm_tn_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_colsum_f32(const float* G, int32_t ldg, int64_t rows, int32_t N, float* out, void* stream) {
+  NR_CHECK_ARG(rows >= 0 && N >= 1, "nr_colsum_f32: bad sizes");
+  if (rows == 0) return NR_OK;
+  NR_CHECK_ARG(G && out, "nr_colsum_f32: null pointer");
+  const int rpb = 512;
+  dim3 grid((unsigned)nr_cdiv(N, 128), (unsigned)nr_cdiv(rows, rpb));
+  colsum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(G, ldg, rows, N, out, rpb);
+  NR_CHECK_LAUNCH("colsum_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_sdf_bwd_act_f32(float* gh, int32_t ldgh, float* gt, int32_t ldgt, const float* S, int32_t lds,
+                                  const float* u, int32_t ldu, int64_t n, int32_t N, void* stream) {
+  NR_CHECK_ARG(n >= 0 && N >= 1, "nr_sdf_bwd_act_f32: bad sizes");
+  if (n == 0) return NR_OK;
+  NR_CHECK_ARG(gh && gt && S && u, "nr_sdf_bwd_act_f32: null pointer");
+  sdf_bwd_act_kernel<<<(unsigned)nr_cdiv(n * N, 256), 256, 0, (cudaStream_t)stream>>>(gh, ldgh, gt, ldgt, S, lds, u, ldu, n, N);
+  NR_CHECK_LAUNCH("sdf_bwd_act_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_act_bwd_f32(float* x, int32_t ldx, const float* ref, int32_t ldr, int64_t rows, int32_t N,
+                              int32_t mode, void* stream) {
+  NR_CHECK_ARG(rows >= 0 && N >= 1 && (mode == 0 || mode == 1), "nr_act_bwd_f32: bad arguments");
+  if (rows == 0) return NR_OK;
+  NR_CHECK_ARG(x && ref, "nr_act_bwd_f32: null pointer");
+  act_bwd_kernel<<<(unsigned)nr_cdiv(rows * N, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, ref, ldr, rows, N, mode);
+  NR_CHECK_LAUNCH("act_bwd_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_embed_f32(const float* x, int64_t n, int32_t in_dim, int32_t multires, float* pe, int32_t ld,
+                            int32_t col_off, float* tpe, int32_t ldt, int32_t tcol_off, void* stream) {
+  NR_CHECK_ARG(n >= 0 && in_dim >= 1 && in_dim <= 4, "nr_embed_f32: bad sizes");
+  if (n == 0) return NR_OK;
+  NR_CHECK_ARG(x && (pe || tpe), "nr_embed_f32: null pointer");
+  return launch_embed(x, n, in_dim, multires, pe, ld, col_off, tpe, ldt, tcol_off, 1.0f, (cudaStream_t)stream);
 }

@@ -1,11 +1,294 @@
-"""Training (autograd) entry points of the MLP kernels -- implemented in a later milestone."""
+"""Training path of the MLPs: ``torch.autograd.Function``s over the fp32 CUDA building blocks of
+``csrc/mlp_f32.cu`` (nr_gemm_f32, nr_gemm_tn_f32, nr_colsum_f32, nr_sdf_bwd_act_f32, nr_act_bwd_f32,
+nr_embed_f32).
+
+The reference differentiates ``ImplicitSurface.forward_with_nablas`` twice (``autograd.grad(...,
+create_graph=True)``, models/base.py:265-282, then ``loss.backward()`` through the eikonal term,
+neus.py:443-458).  Here the normal is produced by forward-mode differentiation inside the network
+(value rows h, tangent rows t_c sharing the weights), so ONE hand-written first-order backward of
+that extended network covers the whole second-order path:
+
+    forward:   z = W h + b,  u_c = W t_c,  h' = sp(z),  t'_c = sp'(z) u_c
+    backward:  g_u_c = g_t'_c sp'(z)
+               g_z   = g_h' sp'(z) + sum_c g_t'_c u_c sp''(z)
+               g_W   = g_z^T h + sum_c g_u_c^T t_c,   g_b = colsum(g_z)
+               g_h   = g_z W,  g_t_c = g_u_c W
+
+Weight-norm (``W = g v/||v||``) stays in PyTorch on top of the effective weights, so ``weight_g`` /
+``weight_v`` receive their gradients through ordinary autograd.  The sample points are constants
+(they come from the no-grad up-sampling), so no gradient w.r.t. x is produced.
+"""
+import math
+
+import torch
+
+from .. import _lib
+
+MODE_NONE, MODE_SOFTPLUS, MODE_RELU, MODE_SIGMOID, MODE_TANGENT, MODE_LINEAR = 0, 1, 2, 3, 4, 5
 
 
-def _todo(*a, **k):
-    raise NotImplementedError(
-        "neurecon_b200: the training backward of the fused MLPs is not built yet; call under torch.no_grad()")
+def _pad4(k):
+    return (k + 3) & ~3
 
 
-sdf_forward_autograd = _todo
-sdf_forward_with_nablas_autograd = _todo
-radiance_forward_autograd = _todo
+def _padded(W):
+    """[out, in] -> contiguous fp32 [out, pad4(in)] (zero filled)."""
+    out_d, in_d = W.shape
+    Wp = torch.zeros(out_d, _pad4(in_d), dtype=torch.float32, device=W.device)
+    Wp[:, :in_d] = W
+    return Wp
+
+
+def _gemm(A, K, W, bias, N, mode, S=None, aux=None, m_val=0):
+    """Y[M, pad4(N)] = epilogue(A[:, :K] @ W[:N, :K]^T + bias); pad columns are zero."""
+    lib = _lib.get_lib()
+    M = A.shape[0]
+    ldy = _pad4(N)
+    Y = torch.zeros(M, ldy, dtype=torch.float32, device=A.device) if ldy != N else torch.empty(M, ldy, dtype=torch.float32, device=A.device)
+    _lib.check(lib.nr_gemm_f32(_lib.ptr(A), A.shape[1], _lib.ptr(W), W.shape[1], _lib.ptr(bias), M, N, K, _lib.ptr(Y), ldy,
+                               mode, _lib.ptr(S), 0 if S is None else S.shape[1], _lib.ptr(aux),
+                               0 if aux is None else aux.shape[1], m_val, _lib.stream_ptr(A.device)), "gemm_f32")
+    return Y
+
+
+def _gemm_tn(G, N, X, K, dW):
+    """dW[:N, :K] += G[:, :N]^T X[:, :K]"""
+    lib = _lib.get_lib()
+    _lib.check(lib.nr_gemm_tn_f32(_lib.ptr(G), G.shape[1], _lib.ptr(X), X.shape[1], G.shape[0], N, K, _lib.ptr(dW),
+                                  dW.shape[1], _lib.stream_ptr(G.device)), "gemm_tn_f32")
+
+
+def _colsum(G, N):
+    lib = _lib.get_lib()
+    out = torch.zeros(N, dtype=torch.float32, device=G.device)
+    _lib.check(lib.nr_colsum_f32(_lib.ptr(G), G.shape[1], G.shape[0], N, _lib.ptr(out), _lib.stream_ptr(G.device)), "colsum_f32")
+    return out
+
+
+class _SdfFn(torch.autograd.Function):
+    """(x, W_0, b_0, ..., W_D, b_D) -> (sdf [n], nabla [n,3], feat [n,F]).  W_l are the EFFECTIVE weights
+    (the skip layer's already divided by sqrt 2)."""
+
+    @staticmethod
+    def forward(ctx, x, multires, skip, want_nablas, *wb):
+        lib = _lib.get_lib()
+        dev = x.device
+        n = x.shape[0]
+        L = len(wb) // 2
+        Ws = [_padded(w.detach().float()) for w in wb[0::2]]
+        bs = [b.detach().float().contiguous() for b in wb[1::2]]
+        dims = [(w.shape[0], w.shape[1]) for w in wb[0::2]]  # (out, in)
+        pe_dim = 3 if multires < 0 else 3 * (1 + 2 * multires)
+        ldpe = _pad4(pe_dim)
+        f = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            pe = torch.zeros(n, ldpe, **f)
+            tpe = torch.zeros(3 * n, ldpe, **f) if want_nablas else None
+            _lib.check(lib.nr_embed_f32(_lib.ptr(x), n, 3, multires, _lib.ptr(pe), ldpe, 0, _lib.ptr(tpe), ldpe, 0,
+                                        _lib.stream_ptr(dev)), "embed_f32")
+            h, t = pe, tpe
+            saved = []
+            for l in range(L - 1):
+                N, K = dims[l]
+                if l == skip:
+                    prev = dims[l - 1][0]
+                    hc = torch.zeros(n, _pad4(K), **f)
+                    hc[:, :prev] = h[:, :prev]
+                    hc[:, prev:prev + pe_dim] = pe[:, :pe_dim]
+                    h = hc
+                    if want_nablas:
+                        tc = torch.zeros(3 * n, _pad4(K), **f)
+                        tc[:, :prev] = t[:, :prev]
+                        tc[:, prev:prev + pe_dim] = tpe[:, :pe_dim]
+                        t = tc
+                S = torch.zeros(n, _pad4(N), **f)
+                h_out = _gemm(h, K, Ws[l], bs[l], N, MODE_SOFTPLUS, S=S)
+                u = t_out = None
+                if want_nablas:
+                    u = _gemm(t, K, Ws[l], None, N, MODE_LINEAR)
+                    t_out = (u.view(3, n, -1) * S.unsqueeze(0)).reshape(3 * n, -1)
+                saved.append((h, t, S, u))
+                h, t = h_out, t_out
+            N, K = dims[L - 1]
+            out = _gemm(h, K, Ws[L - 1], bs[L - 1], N, MODE_NONE)
+            sdf = out[:, 0].contiguous()
+            feat = out[:, 1:N].contiguous()
+            if want_nablas:
+                tout = _gemm(t, K, Ws[L - 1], None, 1, MODE_LINEAR)       # [3n, 4], column 0 valid
+                nabla = tout[:, 0].reshape(3, n).t().contiguous()
+            else:
+                nabla = torch.zeros(n, 3, **f)
+        ctx.saved = saved
+        ctx.last = (h, t)
+        ctx.Ws, ctx.dims, ctx.skip, ctx.want_nablas, ctx.n = Ws, dims, skip, want_nablas, n
+        ctx.mark_non_differentiable(*([nabla] if not want_nablas else []))
+        return sdf, nabla, feat
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_nabla, g_feat):
+        lib = _lib.get_lib()
+        Ws, dims, skip, wn, n = ctx.Ws, ctx.dims, ctx.skip, ctx.want_nablas, ctx.n
+        L = len(Ws)
+        h_last, t_last = ctx.last
+        dev = h_last.device
+        f = dict(dtype=torch.float32, device=dev)
+        grads = [None] * (2 * L)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            # ---- last (linear) layer: rows = [sdf | feat] ----
+            N, K = dims[L - 1]
+            g_out = torch.zeros(n, _pad4(N), **f)
+            if g_sdf is not None:
+                g_out[:, 0] = g_sdf
+            if g_feat is not None:
+                g_out[:, 1:N] = g_feat
+            dW = torch.zeros(N, _pad4(K), **f)
+            _gemm_tn(g_out, N, h_last, K, dW)
+            grads[2 * (L - 1) + 1] = _colsum(g_out, N)
+            Wt = _padded(Ws[L - 1][:, :K].t().contiguous())
+            g_h = _gemm(g_out, N, Wt, None, K, MODE_LINEAR)
+            g_t = None
+            if wn:
+                g_tout = torch.zeros(3 * n, 4, **f)
+                if g_nabla is not None:
+                    g_tout[:, 0] = g_nabla.t().reshape(-1)
+                _gemm_tn(g_tout, 1, t_last, K, dW)                      # adds to row 0
+                g_t = torch.zeros(3 * n, _pad4(K), **f)
+                g_t[:, :K] = g_tout[:, :1] * Ws[L - 1][0:1, :K]
+            grads[2 * (L - 1)] = dW[:, :K]
+            # ---- hidden softplus layers ----
+            for l in range(L - 2, -1, -1):
+                N, K = dims[l]
+                h_in, t_in, S, u = ctx.saved[l]
+                if wn:
+                    _lib.check(lib.nr_sdf_bwd_act_f32(_lib.ptr(g_h), g_h.shape[1], _lib.ptr(g_t), g_t.shape[1], _lib.ptr(S),
+                                                      S.shape[1], _lib.ptr(u), u.shape[1], n, N, st), "sdf_bwd_act")
+                else:
+                    g_h[:, :N] *= S[:, :N]
+                dW = torch.zeros(N, _pad4(K), **f)
+                _gemm_tn(g_h, N, h_in, K, dW)
+                if wn:
+                    _gemm_tn(g_t, N, t_in, K, dW)
+                grads[2 * l] = dW[:, :K]
+                grads[2 * l + 1] = _colsum(g_h, N)
+                if l > 0:
+                    Wt = _padded(Ws[l][:, :K].t().contiguous())
+                    g_h = _gemm(g_h, N, Wt, None, K, MODE_LINEAR)      # [n, pad4(K)]; for the skip layer only the
+                    if wn:                                             # first out_{l-1} columns are used below
+                        g_t = _gemm(g_t, N, Wt, None, K, MODE_LINEAR)
+        ctx.saved = ctx.last = None
+        return (None, None, None, None, *grads)
+
+
+class _RadianceFn(torch.autograd.Function):
+    """(x, view, normals, feat, W_0, b_0, ...) -> rgb [n,3]; gradients for normals, feat and the weights."""
+
+    @staticmethod
+    def forward(ctx, x, view, normals, feat, multires, multires_view, *wb):
+        lib = _lib.get_lib()
+        dev = x.device
+        n = x.shape[0]
+        L = len(wb) // 2
+        Ws = [_padded(w.detach().float()) for w in wb[0::2]]
+        bs = [b.detach().float().contiguous() for b in wb[1::2]]
+        dims = [(w.shape[0], w.shape[1]) for w in wb[0::2]]
+        px = 3 if multires < 0 else 3 * (1 + 2 * multires)
+        pv = 3 if multires_view < 0 else 3 * (1 + 2 * multires_view)
+        in0 = px + pv + 3 + feat.shape[1]
+        assert in0 == dims[0][1], "RadianceNet layer 0 width"
+        f = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            a0 = torch.zeros(n, _pad4(in0), **f)
+            _lib.check(lib.nr_embed_f32(_lib.ptr(x), n, 3, multires, _lib.ptr(a0), a0.shape[1], 0, None, 0, 0, st), "embed")
+            _lib.check(lib.nr_embed_f32(_lib.ptr(view), n, 3, multires_view, _lib.ptr(a0), a0.shape[1], px, None, 0, 0, st), "embed")
+            a0[:, px + pv:px + pv + 3] = normals
+            a0[:, px + pv + 3:in0] = feat
+            acts = [a0]
+            h = a0
+            for l in range(L):
+                N, K = dims[l]
+                h = _gemm(h, K, Ws[l], bs[l], N, MODE_SIGMOID if l == L - 1 else MODE_RELU)
+                acts.append(h)
+        ctx.acts, ctx.Ws, ctx.dims, ctx.n = acts, Ws, dims, n
+        ctx.split = (px + pv, in0)
+        return acts[-1][:, :3].contiguous()
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        lib = _lib.get_lib()
+        acts, Ws, dims, n = ctx.acts, ctx.Ws, ctx.dims, ctx.n
+        L = len(Ws)
+        dev = acts[0].device
+        f = dict(dtype=torch.float32, device=dev)
+        grads = [None] * (2 * L)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            g = torch.zeros(n, 4, **f)
+            g[:, :3] = g_rgb
+            for l in range(L - 1, -1, -1):
+                N, K = dims[l]
+                _lib.check(lib.nr_act_bwd_f32(_lib.ptr(g), g.shape[1], _lib.ptr(acts[l + 1]), acts[l + 1].shape[1], n, N,
+                                              1 if l == L - 1 else 0, st), "act_bwd")
+                dW = torch.zeros(N, _pad4(K), **f)
+                _gemm_tn(g, N, acts[l], K, dW)
+                grads[2 * l] = dW[:, :K]
+                grads[2 * l + 1] = _colsum(g, N)
+                Wt = _padded(Ws[l][:, :K].t().contiguous())
+                g = _gemm(g, N, Wt, None, K, MODE_LINEAR)
+        off, in0 = ctx.split
+        g_normals = g[:, off:off + 3].contiguous()
+        g_feat = g[:, off + 3:in0].contiguous()
+        ctx.acts = None
+        return (None, None, g_normals, g_feat, None, None, *grads)
+
+
+def _surface_weights(surface):
+    from .base import _effective_weight
+    wb = []
+    for i, layer in enumerate(surface.surface_fc_layers):
+        W = _effective_weight(layer)
+        if i in surface.skips:
+            W = W / math.sqrt(2)
+        wb += [W, layer.bias]
+    return wb
+
+
+def _run_sdf(surface, x, want_nablas):
+    _lib.require_cuda(x)
+    surface._check_supported()
+    shape = x.shape[:-1]
+    xf = _lib.f32c(x.detach().reshape(-1, 3))
+    skip = surface.skips[0] if surface.skips else -1
+    sdf, nabla, feat = _SdfFn.apply(xf, surface.embed_multires, skip, want_nablas, *_surface_weights(surface))
+    return sdf.reshape(shape), nabla.reshape(*shape, 3), feat.reshape(*shape, -1)
+
+
+def sdf_forward_autograd(surface, x, return_h=False):
+    """ImplicitSurface.forward under autograd (models/base.py:243-263)."""
+    sdf, _, feat = _run_sdf(surface, x, want_nablas=False)
+    return (sdf, feat) if return_h else sdf
+
+
+def sdf_forward_with_nablas_autograd(surface, x):
+    """ImplicitSurface.forward_with_nablas with has_grad=True (models/base.py:265-282): the returned
+    nabla is differentiable w.r.t. the weights (what create_graph=True provides in the reference)."""
+    return _run_sdf(surface, x, want_nablas=True)
+
+
+def radiance_forward_autograd(rad, x, view_dirs, normals, geometry_feature):
+    """RadianceNet.forward under autograd (models/base.py:372-391)."""
+    from .base import _effective_weight
+    if rad.skips or not rad.use_view_dirs:
+        raise NotImplementedError("neurecon_b200 RadianceNet supports skips=[] with use_view_dirs=True")
+    _lib.require_cuda(x, view_dirs, normals, geometry_feature)
+    shape = x.shape[:-1]
+    xf = _lib.f32c(x.detach().reshape(-1, 3))
+    vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
+    nf = normals.reshape(-1, 3).float()
+    ff = geometry_feature.reshape(-1, geometry_feature.shape[-1]).float()
+    wb = []
+    for layer in rad.layers:
+        wb += [_effective_weight(layer), layer.bias]
+    rgb = _RadianceFn.apply(xf, vf, nf, ff, rad.embed_multires, rad.embed_multires_view, *wb)
+    return rgb.reshape(*shape, 3)

@@ -1,6 +1,66 @@
-"""Training (autograd) path of NeuS volume_render -- built in a later milestone."""
+"""NeuS ``volume_render`` under autograd (the training path, neus.py:118-397 called from
+``Trainer.forward`` neus.py:440 with ``detailed_output=True``).
+
+* up-sampling is ``no_grad`` in the reference (neus.py:214) -> the inference kernels (any tier);
+* the two with-grad network queries (neus.py:294,298) go through the hand-written fp32 forward/backward
+  of ``models/autograd.py`` (incl. the second-order path of the eikonal loss);
+* alpha / transmittance / compositing (neus.py:296,346-352) are a dozen [R,128] tensor ops whose
+  gradients reach ``ln_s``, the sdf values and the radiances through PyTorch autograd -- < 0.1 % of the
+  step's work (the step is ~1 TFLOP of MLP), so they are not worth a custom backward.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+from ... import _lib
 
 
-def volume_render_train(*a, **k):
-    raise NotImplementedError(
-        "neurecon_b200: NeuS volume_render under autograd is not built yet; wrap inference in torch.no_grad()")
+def volume_render_train(rays_o, rays_d, model, obj_bounding_radius=1.0, batched=False, calc_normal=False,
+                        rayschunk=65536, white_bkgd=False, near_bypass=None, far_bypass=None, detailed_output=True,
+                        perturb=False, N_samples=64, N_importance=64, N_upsample_iters=4):
+    from . import neus
+    B = rays_d.shape[0] if batched else 1
+    prefix = [B, -1] if batched else [-1]
+    o_flat = _lib.f32c(rays_o.reshape(-1, 3))
+    d_flat = _lib.f32c(rays_d.reshape(-1, 3))
+    n_total = o_flat.shape[0]
+    M = N_samples + (N_importance // N_upsample_iters) * N_upsample_iters
+    outs = []
+    with torch.cuda.device(o_flat.device):
+        step = int(rayschunk) * B
+        for i0 in range(0, n_total, step):
+            ro, rd = o_flat[i0:i0 + step], d_flat[i0:i0 + step]
+            R = ro.shape[0]
+            with torch.no_grad():
+                dirs, d_all, pts, d_mid, pts_mid = neus._upsample(
+                    model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
+                    N_upsample_iters, perturb)
+            sdf, nablas, _ = model.implicit_surface.forward_with_nablas(pts)          # neus.py:294
+            views = dirs.unsqueeze(-2).expand(R, M - 1, 3)
+            radiances = model.forward_radiance(pts_mid, views)                         # neus.py:298
+            cdf, alpha = neus.sdf_to_alpha(sdf, model.forward_s())                     # neus.py:296
+            w = neus.alpha_to_w(alpha)                                                 # neus.py:346
+            rgb = torch.sum(w[..., None] * radiances, -2)
+            depth = torch.sum(w / (w.sum(-1, keepdim=True) + 1e-10) * d_mid, -1)
+            acc = torch.sum(w, -1)
+            if white_bkgd:
+                rgb = rgb + (1.0 - acc[..., None])
+            ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
+            if calc_normal:
+                nm = F.normalize(nablas, dim=-1)
+                ret_i['normals_volume'] = (nm[..., :M - 1, :] * w[..., :M - 1, None]).sum(dim=-2)
+            if detailed_output:
+                ret_i['implicit_nablas'] = nablas
+                ret_i['implicit_surface'] = sdf
+                ret_i['radiance'] = radiances
+                ret_i['alpha'] = alpha
+                ret_i['cdf'] = cdf
+                ret_i['visibility_weights'] = w
+                ret_i['d_final'] = d_mid
+            outs.append(ret_i)
+    ret = OrderedDict()
+    for k in outs[0].keys():
+        v = outs[0][k] if len(outs) == 1 else torch.cat([o[k] for o in outs], 0)
+        ret[k] = v.reshape(*prefix, *v.shape[1:]) if batched else v
+    return ret['rgb'], ret['depth_volume'], ret

@@ -90,8 +90,10 @@ def volume_render(
         raise NotImplementedError("use_view_dirs=False is not supported")
     _lib.require_cuda(rays_o, rays_d)
     if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
-        raise NotImplementedError("neurecon_b200: UNISURF volume_render under autograd is not built yet; "
-                                  "wrap inference in torch.no_grad()")
+        from .train_paths import unisurf_render_train
+        return unisurf_render_train(rays_o, rays_d, model, batched, calc_normal, logit_tau, rayschunk, netchunk, white_bkgd,
+                                    near_bypass, far_bypass, detailed_output, radius_of_interest, perturb, interval,
+                                    too_close_threshold, N_query, N_freespace)
     from ..ray_casting import _root_find
     lib = _lib.get_lib()
     B = rays_d.shape[0] if batched else 1

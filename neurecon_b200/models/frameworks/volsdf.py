@@ -187,8 +187,10 @@ def volume_render(
         raise NotImplementedError("use_view_dirs=False is not supported")
     _lib.require_cuda(rays_o, rays_d)
     if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
-        raise NotImplementedError("neurecon_b200: VolSDF volume_render under autograd is not built yet; "
-                                  "wrap inference in torch.no_grad()")
+        from .train_paths import volsdf_render_train
+        return volsdf_render_train(rays_o, rays_d, model, near, far, obj_bounding_radius, batched, calc_normal, rayschunk,
+                                   white_bkgd, use_nerfplusplus, detailed_output, perturb, N_samples, N_importance,
+                                   N_outside, max_upsample_steps, max_bisection_steps, epsilon)
     lib = _lib.get_lib()
     B = rays_d.shape[0] if batched else 1
     prefix = [B, -1] if batched else [-1]

@@ -119,3 +119,35 @@ def test_neus_training_step_matches_autograd_oracle():
         assert rel_err(m.ln_s.grad, sd["ln_s"].grad) < 1e-3
     finally:
         neurecon_b200.set_precision("fp16")
+
+
+def test_volsdf_and_unisurf_training_renders():
+    """Training-mode renders of the other two frameworks: same values as the inference path (fp32 tier), every
+    parameter (incl. ln_beta) receives a finite gradient from the framework's loss terms."""
+    from test_oracle_golden import build_unisurf, build_volsdf
+    from neurecon_b200.models.frameworks import unisurf, volsdf
+    neurecon_b200.set_precision("fp32")
+    try:
+        m = build_volsdf(0.01, False, device=DEV)
+        o, d = synthetic.make_rays(24, shell_radius=3.0 / 1.1, jitter=0.1, seed=3)
+        with torch.no_grad():
+            ref_rgb = volsdf.volume_render(o.to(DEV), d.to(DEV), m, detailed_output=False, max_upsample_steps=6)[0]
+        rgb, _, ret = volsdf.volume_render(o.to(DEV), d.to(DEV), m, detailed_output=True, max_upsample_steps=6)
+        assert rgb.requires_grad and rel_err(rgb, ref_rgb) < 1e-4
+        nn_ = ret["implicit_nablas"].norm(dim=-1)
+        (rgb.mean() + 0.1 * ((nn_ - 1) ** 2).mean()).backward()
+        for name, p in m.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        assert m.ln_beta.grad.abs().item() > 0
+
+        u = build_unisurf(device=DEV)
+        o, d = synthetic.make_rays(40, shell_radius=3.0, jitter=0.25, seed=4)
+        with torch.no_grad():
+            ref_rgb = unisurf.volume_render(o[None].to(DEV), d[None].to(DEV), u, batched=True, detailed_output=False)[0]
+        rgb, _, ret = unisurf.volume_render(o[None].to(DEV), d[None].to(DEV), u, batched=True, detailed_output=True)
+        assert rgb.requires_grad and rel_err(rgb, ref_rgb) < 1e-4
+        rgb.mean().backward()
+        for name, p in u.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    finally:
+        neurecon_b200.set_precision("fp16")

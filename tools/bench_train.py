@@ -1,0 +1,45 @@
+"""NeuS training step (512 rays: render under autograd + L1 + eikonal + mask BCE, backward) -- ms per step and
+rays/s on one GPU, next to the oracle port on the CPU.  Usage: python tools/bench_train.py [rays] [steps]"""
+import os, sys, time
+import torch
+import torch.nn.functional as F
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import neurecon_b200
+from conftest import build_neus
+from neurecon_b200.models.frameworks import neus
+from neurecon_b200.utils import synthetic
+
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+dev = torch.device("cuda:0")
+m = build_neus(seed=1, device=dev)
+opt = torch.optim.Adam(m.parameters(), lr=5e-4)
+o, d = synthetic.make_rays(R, seed=3)
+o, d = o.to(dev), d.to(dev)
+target = torch.rand(R, 3, device=dev)
+
+
+def step():
+    opt.zero_grad(set_to_none=True)
+    rgb, _, ret = neus.volume_render(o, d, m, detailed_output=True, perturb=True)
+    nn_ = ret["implicit_nablas"].norm(dim=-1)
+    loss = F.l1_loss(rgb, target) + 0.1 * F.mse_loss(nn_, torch.ones_like(nn_)) \
+        + F.binary_cross_entropy(ret["mask_volume"].clamp(1e-3, 1 - 1e-3), torch.ones(R, device=dev))
+    loss.backward()
+    opt.step()
+    return loss
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(steps):
+    loss = step()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+print("NeuS training step, %d rays: %.2f ms/step, %.0f rays/s, loss %.4f, peak mem %.2f GB (algorithmic ~1.85 GFLOP/ray => %.1f TFLOP/s)"
+      % (R, ms, R / ms * 1e3, loss.item(), torch.cuda.max_memory_allocated() / 2**30, R * 1.85e9 / (ms * 1e-3) / 1e12))

@@ -102,6 +102,8 @@ def cpu_reference_rate(n_rays, reps, seed=1):
     import torch
     from oracle import neus as oneus
     from neurecon_b200.utils import synthetic
+    # all host threads the process may use (torchrun pins OMP_NUM_THREADS=1 unless told otherwise)
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     m = build_model(seed, "cpu")
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     o, d = synthetic.make_rays(n_rays, shell_radius=2.5, jitter=0.1, seed=seed)

@@ -206,6 +206,23 @@ int nr_neus_composite(const float* sdf, const float* nablas, const float* radian
                       int32_t white_bkgd, float* rgb, float* depth, float* acc, float* normals,
                       float* cdf_out, float* alpha_out, float* weights_out, void* stream);
 
+/* NeuS with the NeRF++ background (N_outside > 0, neus.py:303-343).
+ * nr_neus_outside_points: d_vals [R, M1+n_out] = cat(d_mid, far / flip(linspace(0,1,n_out+2)[1:-1]))
+ * (u [R,n_out]: stratified jitter uniforms or NULL) and the inverted-sphere inputs x_out [R, M1+n_out, 4]
+ * = [p/|p|, 1/|p|] of NeRF.forward.
+ * nr_neus_composite_bg: like nr_neus_composite, with alpha / radiance taken from the background net
+ * (sigma_out raw, radiance_out; both [R, M-1+n_out]) wherever the mid point lies outside the bounding
+ * sphere and for the appended samples.  Optional per-sample outputs over M-1+n_out entries. */
+int nr_neus_outside_points(const float* rays_o, const float* dirs, const float* far, const float* d_mid,
+                           int64_t R, int32_t M1, int32_t n_out, const float* u, float* d_vals, float* x_out,
+                           void* stream);
+int nr_neus_composite_bg(const float* sdf, const float* nablas, const float* radiance, const float* rays_o,
+                         const float* dirs, const float* d_vals, const float* sigma_out,
+                         const float* radiance_out, const float* s_dev, float radius, int64_t R, int32_t M,
+                         int32_t n_out, int32_t white_bkgd, float* rgb, float* depth, float* acc,
+                         float* normals, float* cdf_out, float* alpha_out, float* weights_out,
+                         float* radiance_blend_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * VolSDF -- models/frameworks/volsdf.py
  * ------------------------------------------------------------------------------------------ */

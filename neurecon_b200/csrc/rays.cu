@@ -360,6 +360,132 @@ __global__ void neus_composite_kernel(const float* __restrict__ sdf, const float
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// NeuS + NeRF++ background (neus.py:303-343).
+// ---------------------------------------------------------------------------------------------
+// Outside samples: d_out = far / flip(linspace(0,1,N_out+2)[1:-1]) (optionally jittered), appended to
+// d_mid; inverted-sphere coordinates x_out = [p/|p|, 1/|p|] for all M1 + N_out depths.
+__global__ void neus_outside_points_kernel(const float* __restrict__ rays_o, const float* __restrict__ dirs,
+                                           const float* __restrict__ far, const float* __restrict__ d_mid, int64_t R,
+                                           int M1, int n_out, const float* __restrict__ u, float* __restrict__ d_vals,
+                                           float* __restrict__ x_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (ray >= R) return;
+  const int T = M1 + n_out;
+  const float fr = far[ray];
+  const float ox = rays_o[3 * ray], oy = rays_o[3 * ray + 1], oz = rays_o[3 * ray + 2];
+  const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
+  auto dout = [&](int j) {  // j in [0, n_out): far / t, t = linspace(0,1,n_out+2)[n_out - j]
+    return __fdiv_rn(fr, nr_linspace01(n_out - j, n_out + 2));
+  };
+  for (int i = lane; i < T; i += 32) {
+    float d;
+    if (i < M1) {
+      d = d_mid[ray * (int64_t)M1 + i];
+    } else {
+      const int j = i - M1;
+      d = dout(j);
+      if (u) {  // stratified jitter between the mid-points of neighbouring depths (neus.py:306-311)
+        const float lo = j == 0 ? d : __fmul_rn(0.5f, __fadd_rn(d, dout(j - 1)));
+        const float hi = j == n_out - 1 ? d : __fmul_rn(0.5f, __fadd_rn(dout(j + 1), d));
+        d = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u[ray * (int64_t)n_out + j]));
+      }
+    }
+    d_vals[ray * (int64_t)T + i] = d;
+    const float px = ox + d * dx, py = oy + d * dy, pz = oz + d * dz;
+    const float r = sqrtf(px * px + py * py + pz * pz);
+    float* x = x_out + (ray * (int64_t)T + i) * 4;
+    x[0] = px / r; x[1] = py / r; x[2] = pz / r; x[3] = 1.0f / r;
+  }
+}
+
+// Compositing with the background blend (neus.py:320-352): inside alpha from the sdf where the mid
+// point is inside the bounding sphere, NeRF++ alpha = 1 - exp(-softplus(sigma) * dist) elsewhere and for
+// the n_out appended samples (last dist = 1e10).
+__global__ void neus_composite_bg_kernel(const float* __restrict__ sdf, const float* __restrict__ nablas,
+                                         const float* __restrict__ radiance, const float* __restrict__ rays_o,
+                                         const float* __restrict__ dirs, const float* __restrict__ d_vals,
+                                         const float* __restrict__ sigma_out, const float* __restrict__ radiance_out,
+                                         const float* __restrict__ s_dev, float radius, int64_t R, int M, int n_out,
+                                         int white_bkgd, float* __restrict__ rgb, float* __restrict__ depth,
+                                         float* __restrict__ acc, float* __restrict__ normals, float* __restrict__ cdf_out,
+                                         float* __restrict__ alpha_out, float* __restrict__ w_out,
+                                         float* __restrict__ rad_blend_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (ray >= R) return;
+  const float s = *s_dev;
+  const int M1 = M - 1, T = M1 + n_out;
+  const float* sd = sdf + ray * (int64_t)M;
+  const float* dv = d_vals + ray * (int64_t)T;
+  const float ox = rays_o[3 * ray], oy = rays_o[3 * ray + 1], oz = rays_o[3 * ray + 2];
+  const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
+  float carry = 1.0f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aw = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  for (int base = 0; base < T; base += 32) {
+    const int i = base + lane;
+    const bool ok = i < T;
+    float alpha = 0.0f, c[3] = {0.f, 0.f, 0.f}, d = 0.0f;
+    if (ok) {
+      d = dv[i];
+      const float dist = i + 1 < T ? dv[i + 1] - d : 1e10f;
+      const float so = sigma_out[ray * (int64_t)T + i];
+      const float sp = so > 20.0f ? so : log1pf(expf(so));              // F.softplus (beta=1, threshold=20)
+      const float a_bg = 1.0f - expf(-sp * dist);
+      const float* cb = radiance_out + (ray * (int64_t)T + i) * 3;
+      bool inside = false;
+      if (i < M1) {
+        const float px = ox + d * dx, py = oy + d * dy, pz = oz + d * dz;
+        inside = sqrtf(px * px + py * py + pz * pz) <= radius;
+        const float c0 = nr_sigmoid(__fmul_rn(sd[i], s)), c1 = nr_sigmoid(__fmul_rn(sd[i + 1], s));
+        if (cdf_out) { cdf_out[ray * (int64_t)M + i] = c0; if (i == M1 - 1) cdf_out[ray * (int64_t)M + i + 1] = c1; }
+        if (inside) alpha = fmaxf(__fdiv_rn(__fsub_rn(c0, c1), __fadd_rn(c0, 1e-10f)), 0.0f);
+      }
+      if (!inside) alpha = a_bg;
+      const float* ci = radiance + (ray * (int64_t)M1 + min(i, M1 - 1)) * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c[k] = inside ? ci[k] : cb[k];
+    }
+    const float f = ok ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+    float incl = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl *= t;
+    }
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float w = alpha * (carry * excl);
+    carry *= __shfl_sync(kFull, incl, 31);
+    if (ok) {
+      if (alpha_out) alpha_out[ray * (int64_t)T + i] = alpha;
+      if (w_out) w_out[ray * (int64_t)T + i] = w;
+      if (rad_blend_out) {
+        float* ro = rad_blend_out + (ray * (int64_t)T + i) * 3;
+        ro[0] = c[0]; ro[1] = c[1]; ro[2] = c[2];
+      }
+      ar += w * c[0]; ag += w * c[1]; ab += w * c[2];
+      ad += w * d;
+      aw += w;
+      if (nablas && i < M) {  // N_pts = min(len(w), len(normals)) = M (neus.py:366)
+        const float* nb = nablas + (ray * (int64_t)M + i) * 3;
+        const float x = nb[0], y = nb[1], z = nb[2];
+        const float inv = 1.0f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+        nx += w * x * inv; ny += w * y * inv; nz += w * z * inv;
+      }
+    }
+  }
+  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aw = warp_sum(aw);
+  if (nablas) { nx = warp_sum(nx); ny = warp_sum(ny); nz = warp_sum(nz); }
+  if (lane == 0) {
+    if (white_bkgd) { ar += 1.0f - aw; ag += 1.0f - aw; ab += 1.0f - aw; }
+    rgb[3 * ray] = ar; rgb[3 * ray + 1] = ag; rgb[3 * ray + 2] = ab;
+    depth[ray] = ad / (aw + 1e-10f);
+    acc[ray] = aw;
+    if (normals) { normals[3 * ray] = nx; normals[3 * ray + 1] = ny; normals[3 * ray + 2] = nz; }
+  }
+}
+
 }  // namespace
 
 extern "C" int nr_near_far_from_sphere(const float* rays_o, const float* rays_d, int64_t R, float r, float* near,
@@ -433,5 +559,35 @@ extern "C" int nr_neus_composite(const float* sdf, const float* nablas, const fl
       sdf, nablas, radiance, d_mid, s_dev, R, M, white_bkgd, rgb, depth, acc, normals, cdf_out, alpha_out,
       weights_out);
   NR_CHECK_LAUNCH("neus_composite_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_neus_outside_points(const float* rays_o, const float* dirs, const float* far, const float* d_mid,
+                                      int64_t R, int32_t M1, int32_t n_out, const float* u, float* d_vals, float* x_out,
+                                      void* stream) {
+  NR_CHECK_ARG(R >= 0 && M1 >= 1 && n_out >= 1, "nr_neus_outside_points: bad sizes");
+  if (R == 0) return NR_OK;
+  NR_CHECK_ARG(rays_o && dirs && far && d_mid && d_vals && x_out, "nr_neus_outside_points: null pointer");
+  neus_outside_points_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      rays_o, dirs, far, d_mid, R, M1, n_out, u, d_vals, x_out);
+  NR_CHECK_LAUNCH("neus_outside_points_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_neus_composite_bg(const float* sdf, const float* nablas, const float* radiance, const float* rays_o,
+                                    const float* dirs, const float* d_vals, const float* sigma_out,
+                                    const float* radiance_out, const float* s_dev, float radius, int64_t R, int32_t M,
+                                    int32_t n_out, int32_t white_bkgd, float* rgb, float* depth, float* acc,
+                                    float* normals, float* cdf_out, float* alpha_out, float* weights_out,
+                                    float* radiance_blend_out, void* stream) {
+  NR_CHECK_ARG(R >= 0 && M >= 2 && n_out >= 1, "nr_neus_composite_bg: bad sizes");
+  if (R == 0) return NR_OK;
+  NR_CHECK_ARG(sdf && radiance && rays_o && dirs && d_vals && sigma_out && radiance_out && s_dev && rgb && depth && acc,
+               "nr_neus_composite_bg: null pointer");
+  NR_CHECK_ARG((nablas != nullptr) == (normals != nullptr), "nr_neus_composite_bg: nablas and normals go together");
+  neus_composite_bg_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      sdf, nablas, radiance, rays_o, dirs, d_vals, sigma_out, radiance_out, s_dev, radius, R, M, n_out, white_bkgd, rgb,
+      depth, acc, normals, cdf_out, alpha_out, weights_out, radiance_blend_out);
+  NR_CHECK_LAUNCH("neus_composite_bg_kernel");
   return NR_OK;
 }

@@ -92,8 +92,37 @@ def _composite(sdf, nablas, radiances, d_mid, s, white_bkgd, calc_normal, detail
     return rgb, depth, acc, normals, cdf, alpha, w
 
 
+def _composite_bg(model, rays_o, dirs, far, sdf, nablas, radiances, d_mid, s, radius, N_outside, perturb, white_bkgd,
+                  calc_normal, detailed):
+    """NeRF++ background (neus.py:303-352): outside samples, NeRF.forward, blended compositing."""
+    lib = _lib.get_lib()
+    R, M = sdf.shape
+    dev = sdf.device
+    f = dict(dtype=torch.float32, device=dev)
+    st = _lib.stream_ptr(dev)
+    T = M - 1 + N_outside
+    u = torch.rand([R, N_outside]).float().to(dev) if perturb else None   # CPU RNG like neus.py:310
+    d_vals, x_out = torch.empty(R, T, **f), torch.empty(R, T, 4, **f)
+    _lib.check(lib.nr_neus_outside_points(_lib.ptr(rays_o), _lib.ptr(dirs), _lib.ptr(far), _lib.ptr(d_mid), R, M - 1,
+                                          N_outside, _lib.ptr(u), _lib.ptr(d_vals), _lib.ptr(x_out), st), "neus_outside_points")
+    sigma_out, radiance_out = model.nerf_outside.forward(x_out, dirs.unsqueeze(-2).expand(R, T, 3))
+    sigma_out, radiance_out = sigma_out.contiguous(), radiance_out.contiguous()
+    rgb, depth, acc = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
+    normals = torch.empty(R, 3, **f) if calc_normal else None
+    cdf = torch.empty(R, M, **f) if detailed else None
+    alpha = torch.empty(R, T, **f) if detailed else None
+    w = torch.empty(R, T, **f) if detailed else None
+    blend = torch.empty(R, T, 3, **f) if detailed else None
+    _lib.check(lib.nr_neus_composite_bg(
+        _lib.ptr(sdf), _lib.ptr(nablas) if calc_normal else None, _lib.ptr(radiances), _lib.ptr(rays_o), _lib.ptr(dirs),
+        _lib.ptr(d_vals), _lib.ptr(sigma_out), _lib.ptr(radiance_out), _lib.ptr(s), float(radius), R, M, N_outside,
+        int(bool(white_bkgd)), _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(normals), _lib.ptr(cdf),
+        _lib.ptr(alpha), _lib.ptr(w), _lib.ptr(blend), st), "neus_composite_bg")
+    return rgb, depth, acc, normals, cdf, alpha, w, blend, d_vals, sigma_out, radiance_out
+
+
 def _upsample(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
-              N_upsample_iters, perturb):
+              N_upsample_iters, perturb, return_far=False):
     """neus.py:184-288 for one flat ray chunk [R,3]: returns dirs, d_all, pts, d_mid, pts_mid."""
     lib = _lib.get_lib()
     R, dev = rays_o.shape[0], rays_o.device
@@ -128,6 +157,8 @@ def _upsample(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_b
                 _lib.ptr(pts_next), _lib.ptr(pts_all), _lib.ptr(d_mid), _lib.ptr(pts_mid), st), "neus_upsample_step")
             m_cur += n_new
             d_new, pts_new, n_new = d_next, pts_next, n_next
+    if return_far:
+        return dirs, d_buf, pts_all, d_mid, pts_mid, far
     return dirs, d_buf, pts_all, d_mid, pts_mid
 
 
@@ -172,8 +203,8 @@ def volume_render(
     if upsample_algo != 'official_solution':
         raise NotImplementedError("upsample_algo=%r: only 'official_solution' (every shipped config) is built"
                                   % upsample_algo)
-    if N_outside > 0:
-        raise NotImplementedError("NeuS with NeRF++ background (N_outside > 0) is not built yet")
+    if N_outside > 0 and not hasattr(model, "nerf_outside"):
+        raise ValueError("N_outside > 0 needs a model built with use_outside_nerf=True")
     if not use_view_dirs:
         raise NotImplementedError("use_view_dirs=False is not supported")
     _lib.require_cuda(rays_o, rays_d)
@@ -183,7 +214,7 @@ def volume_render(
             rays_o, rays_d, model, obj_bounding_radius=obj_bounding_radius, batched=batched, calc_normal=calc_normal,
             rayschunk=rayschunk, white_bkgd=white_bkgd, near_bypass=near_bypass, far_bypass=far_bypass,
             detailed_output=detailed_output, perturb=perturb, N_samples=N_samples, N_importance=N_importance,
-            N_upsample_iters=N_upsample_iters)
+            N_upsample_iters=N_upsample_iters, N_outside=N_outside)
     if batched:
         B = rays_d.shape[0]
         prefix = [B, -1]
@@ -206,15 +237,23 @@ def volume_render(
         for i0 in range(0, n_total, step):
             ro, rd = o_flat[i0:i0 + step], d_flat[i0:i0 + step]
             R = ro.shape[0]
-            dirs, d_all, pts, d_mid, pts_mid = _upsample(
+            dirs, d_all, pts, d_mid, pts_mid, far = _upsample(
                 model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
-                N_upsample_iters, perturb)
+                N_upsample_iters, perturb, return_far=True)
             with torch.no_grad():
                 sdf, nablas, _ = model.implicit_surface._run(pts, want_nablas=True, want_feat=False)
                 views = dirs.unsqueeze(-2).expand(R, M - 1, 3)
                 radiances, _, _ = query_radiance(model.implicit_surface, model.radiance_net, pts_mid, views)
-            rgb, depth, acc, normals, cdf, alpha, w = _composite(
-                sdf, nablas, radiances, d_mid, s, white_bkgd, calc_normal, detailed_output)
+            sigma_out = radiance_out = None
+            d_final = d_mid
+            if N_outside > 0:
+                with torch.no_grad():
+                    (rgb, depth, acc, normals, cdf, alpha, w, radiances, d_final, sigma_out, radiance_out) = _composite_bg(
+                        model, ro, dirs, far, sdf, nablas, radiances, d_mid, s, obj_bounding_radius, N_outside, perturb,
+                        white_bkgd, calc_normal, detailed_output)
+            else:
+                rgb, depth, acc, normals, cdf, alpha, w = _composite(
+                    sdf, nablas, radiances, d_mid, s, white_bkgd, calc_normal, detailed_output)
             ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
             if calc_normal:
                 ret_i['normals_volume'] = normals
@@ -225,7 +264,10 @@ def volume_render(
                 ret_i['alpha'] = alpha
                 ret_i['cdf'] = cdf
                 ret_i['visibility_weights'] = w
-                ret_i['d_final'] = d_mid
+                ret_i['d_final'] = d_final
+                if N_outside > 0:
+                    ret_i['sigma_out'] = sigma_out
+                    ret_i['radiance_out'] = radiance_out
             outs.append(ret_i)
 
     ret = OrderedDict()

@@ -18,7 +18,9 @@ from ... import _lib
 
 def volume_render_train(rays_o, rays_d, model, obj_bounding_radius=1.0, batched=False, calc_normal=False,
                         rayschunk=65536, white_bkgd=False, near_bypass=None, far_bypass=None, detailed_output=True,
-                        perturb=False, N_samples=64, N_importance=64, N_upsample_iters=4):
+                        perturb=False, N_samples=64, N_importance=64, N_upsample_iters=4, N_outside=0):
+    if N_outside > 0:
+        raise NotImplementedError("neurecon_b200: training with the NeRF++ background is not built yet")
     from . import neus
     B = rays_d.shape[0] if batched else 1
     prefix = [B, -1] if batched else [-1]

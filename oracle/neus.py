@@ -76,9 +76,45 @@ def composite(sdf, nablas, radiances, d_all, s, white_bkgd=False, calc_normal=Tr
     return ret
 
 
+def composite_bg(sdf, nablas, radiances, d_all, s, rays_o, rays_d, far, sd, radius, N_outside, white_bkgd=False,
+                 calc_normal=True):
+    """neus.py:303-381 with the NeRF++ background (perturb=False)."""
+    d_mid = 0.5 * (d_all[..., 1:] + d_all[..., :-1])
+    pts_mid = rays_o[..., None, :] + rays_d[..., None, :] * d_mid[..., :, None]
+    cdf, alpha_in = sdf_to_alpha(sdf, s)
+    t = sampling.linspace01(N_outside + 2, sdf.dtype)[1:-1]
+    d_out = far / torch.flip(t, dims=[-1])
+    d_vals = torch.cat([d_mid, d_out], dim=-1)
+    pts_out = rays_o[..., None, :] + rays_d[..., None, :] * d_vals[..., :, None]
+    r = pts_out.norm(dim=-1, keepdim=True)
+    x_out = torch.cat([pts_out / r, 1.0 / r], dim=-1)
+    sigma_out, radiance_out = nets.nerf_forward(x_out, rays_d.unsqueeze(-2).expand_as(pts_out), sd)
+    dists = torch.cat([d_vals[..., 1:] - d_vals[..., :-1], 1e10 * torch.ones_like(d_vals[..., :1])], dim=-1)
+    alpha_out = 1 - torch.exp(-F.softplus(sigma_out) * dists)
+    n1 = d_mid.shape[-1]
+    inside = (pts_mid.norm(dim=-1) <= radius).to(sdf.dtype)
+    alpha = torch.cat([alpha_in * inside + alpha_out[..., :n1] * (1 - inside), alpha_out[..., n1:]], dim=-1)
+    rad = torch.cat([radiances * inside[..., None] + radiance_out[..., :n1, :] * (1 - inside)[..., None],
+                     radiance_out[..., n1:, :]], dim=-2)
+    w = alpha_to_w(alpha)
+    rgb = (w[..., None] * rad).sum(-2)
+    depth = (w / (w.sum(-1, keepdim=True) + 1e-10) * d_vals).sum(-1)
+    acc = w.sum(-1)
+    if white_bkgd:
+        rgb = rgb + (1.0 - acc[..., None])
+    ret = OrderedDict(rgb=rgb, depth_volume=depth, mask_volume=acc)
+    if calc_normal:
+        n = F.normalize(nablas, dim=-1)
+        N = min(w.shape[-1], n.shape[-2])
+        ret["normals_volume"] = (n[..., :N, :] * w[..., :N, None]).sum(-2)
+    ret.update(alpha=alpha, cdf=cdf, visibility_weights=w, d_final=d_vals, radiance=rad, sigma_out=sigma_out,
+               radiance_out=radiance_out)
+    return ret
+
+
 def volume_render(rays_o, rays_d, sd, cfg, obj_bounding_radius=1.0, calc_normal=True,
                   white_bkgd=False, perturb=False, N_samples=64, N_importance=64,
-                  N_upsample_iters=4, near_bypass=None, far_bypass=None, dtype=torch.float32):
+                  N_upsample_iters=4, near_bypass=None, far_bypass=None, dtype=torch.float32, N_outside=0):
     """neus.py:118-397 ('official_solution', no NeRF++), one ray chunk, inference.
 
     ``sd``: reference-layout state_dict; ``cfg``: dict(multires, multires_view,
@@ -110,6 +146,11 @@ def volume_render(rays_o, rays_d, sd, cfg, obj_bounding_radius=1.0, calc_normal=
     views = rays_d.unsqueeze(-2).expand_as(pts_mid)
     radiances = nets.radiance_forward(pts_mid, views, nab_mid, feat_mid, rad_layers,
                                       cfg["rad_multires"], cfg["multires_view"])
+    if N_outside > 0:
+        ret = composite_bg(sdf, nablas, radiances, d_all, s, rays_o, rays_d, far, sd, obj_bounding_radius, N_outside,
+                           white_bkgd, calc_normal)
+        ret.update(implicit_nablas=nablas, implicit_surface=sdf, d_all=d_all)
+        return ret["rgb"], ret["depth_volume"], ret
     ret = composite(sdf, nablas, radiances, d_all, s, white_bkgd, calc_normal)
     ret.update(implicit_nablas=nablas, implicit_surface=sdf, radiance=radiances, d_all=d_all)
     return ret["rgb"], ret["depth_volume"], ret

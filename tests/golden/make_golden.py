@@ -41,6 +41,15 @@ def golden_neus(ref):
             "radiance", "alpha", "cdf", "visibility_weights", "d_final"]
     npz("neus_render_r48.npz", seed=1, n_rays=R, **{k: ret[k] for k in keep})
 
+    # NeuS without mask: NeRF++ background (configs/neus_nomask.yaml: N_outside = 32)
+    torch.manual_seed(0)
+    mb = ref.neus.NeuS(**dict(synthetic.NEUS_MODEL_KWARGS, use_outside_nerf=True))
+    synthetic.reseed_parameters(mb, seed=5)
+    ob, db = synthetic.make_rays(24, shell_radius=2.5, jitter=0.15, seed=5)
+    with torch.no_grad():
+        _, _, retb = ref.neus.volume_render(ob, db, mb, calc_normal=True, detailed_output=True, perturb=False, N_outside=32)
+    npz("neus_render_nerfpp_r24.npz", seed=5, **{k: retb[k] for k in keep + ["sigma_out", "radiance_out"]})
+
     # networks on fixed points
     x = synthetic.make_points(256, extent=1.0, seed=2)
     v = torch.nn.functional.normalize(synthetic.make_points(256, extent=1.0, seed=3), dim=-1)

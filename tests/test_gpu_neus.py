@@ -226,3 +226,26 @@ def test_neus_volume_render_api_variants():
         # render through SingleRenderer
         r2 = neus.SingleRenderer(m)(o, d, calc_normal=True, detailed_output=False)[0]
         assert torch.equal(r2, rgb)
+
+
+@pytest.mark.parametrize("tier,tol", [("fp32", 1e-4), ("fp16", 1e-2)])
+def test_neus_nerfpp_background_vs_golden(tier, tol):
+    """NeuS without mask: NeRF++ background net + blended compositing (neus.py:303-343)."""
+    import neurecon_b200
+    from test_oracle_golden import build_neus_bg
+    from neurecon_b200.models.frameworks import neus
+    neurecon_b200.set_precision(tier)
+    m = build_neus_bg(device=DEV)
+    g = load_golden("neus_render_nerfpp_r24.npz")
+    o, d = synthetic.make_rays(24, shell_radius=2.5, jitter=0.15, seed=5)
+    with torch.no_grad():
+        rgb, depth, ret = neus.volume_render(o.to(DEV), d.to(DEV), m, calc_normal=True, detailed_output=True,
+                                             perturb=False, N_outside=32)
+        assert list(ret.keys())[-2:] == ["sigma_out", "radiance_out"]
+        assert ret["alpha"].shape == (24, 159) and ret["radiance"].shape == (24, 159, 3) and ret["d_final"].shape == (24, 159)
+        for k, t in (("rgb", tol), ("depth_volume", max(tol, 2e-3)), ("mask_volume", tol), ("normals_volume", tol)):
+            assert rel_err(ret[k], g[k]) < t, (k, rel_err(ret[k], g[k]))
+        if tier == "fp32":
+            assert rel_err(ret["sigma_out"], g["sigma_out"]) < 1e-4 and rel_err(ret["radiance_out"], g["radiance_out"]) < 1e-4
+        pj = neus.volume_render(o.to(DEV), d.to(DEV), m, detailed_output=False, perturb=True, N_outside=32)[0]
+        assert torch.isfinite(pj).all()

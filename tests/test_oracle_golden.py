@@ -167,3 +167,23 @@ def test_unisurf_render_golden():
         assert rel_err(ret[k], g[k]) < 1e-5, (k, rel_err(ret[k], g[k]))
     for k in ("implicit_surface", "alpha", "visibility_weights"):
         assert frac_close(ret[k], g[k], 1e-4) > 0.97, k
+
+
+def build_neus_bg(seed=5, device="cpu"):
+    from neurecon_b200.models.frameworks import neus
+    torch.manual_seed(0)
+    m = neus.NeuS(**dict(synthetic.NEUS_MODEL_KWARGS, use_outside_nerf=True))
+    synthetic.reseed_parameters(m, seed=seed)
+    return m.to(device)
+
+
+def test_neus_nerfpp_render_golden():
+    g = load_golden("neus_render_nerfpp_r24.npz")
+    sd = cpu_state_dict(build_neus_bg())
+    assert sum(v.numel() for k, v in sd.items() if k.startswith("nerf_outside.")) == 606596
+    o, d = synthetic.make_rays(24, shell_radius=2.5, jitter=0.15, seed=5)
+    _, _, ret = oneus.volume_render(o, d, sd, NEUS_CFG, calc_normal=True, N_outside=32)
+    assert ret["visibility_weights"].shape == (24, 127 + 32) and ret["sigma_out"].shape == (24, 159)
+    # depth sums weights times background depths up to far/0.03 ~ 1e2, so ulp-level weight changes show at 1e-4
+    for k, tol in (("rgb", 2e-5), ("depth_volume", 1e-3), ("mask_volume", 2e-5), ("normals_volume", 2e-5)):
+        assert rel_err(ret[k], g[k]) < tol, (k, rel_err(ret[k], g[k]))

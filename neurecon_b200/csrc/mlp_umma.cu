@@ -403,41 +403,75 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                 if (__uint_as_float(raw[0]) == 123.456f) act[0] = 1;
               }
             } else if (tang) {
-              // columns: [0,32) values of 32 points, [32c, 32c+32) d/dx_c; processed in two 16-point halves
+              // columns: [0,32) values of 32 points, [32c, 32c+32) d/dx_c; two 16-point halves.  TMEM loads are
+              // double-buffered: the load of chunk k+1 is in flight while chunk k is processed.
+              uint32_t rawB[16];
+              float sg[16];
+              const int jpe = F - S.out_rows;
+              umma::tmem_ld16(taddr, raw);
 #pragma unroll 1
               for (int h = 0; h < 2; ++h) {
-                float sg[16];
-                umma::tmem_ld16(taddr + 16 * h, raw);
                 umma::tmem_ld_wait();
+                umma::tmem_ld16(taddr + 32 + 16 * h, rawB);
                 if (!is_pe) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) softplus100_fast(__uint_as_float(raw[j]) + b, v[j], sg[j]);
+                  store_row16<kF16>(ra, 16 * h, v, no_st);
+                } else {
+                  copy_row16(ra, pes, jpe, 16 * h);
                 }
-                if (!is_pe) store_row16<kF16>(ra, 16 * h, v, no_st);
-                else copy_row16(ra, pes, F - S.out_rows, 16 * h);
-#pragma unroll 1
-                for (int c = 1; c < 4; ++c) {
-                  umma::tmem_ld16(taddr + 32 * c + 16 * h, raw);
-                  umma::tmem_ld_wait();
-                  if (!is_pe) {
+                umma::tmem_ld_wait();
+                umma::tmem_ld16(taddr + 64 + 16 * h, raw);
+                if (!is_pe) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * sg[j];
-                  }
-                  if (!is_pe) store_row16<kF16>(ra, 32 * c + 16 * h, v, no_st);
-                  else copy_row16(ra, pes, F - S.out_rows, 32 * c + 16 * h);
+                  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rawB[j]) * sg[j];
+                  store_row16<kF16>(ra, 32 + 16 * h, v, no_st);
+                } else {
+                  copy_row16(ra, pes, jpe, 32 + 16 * h);
+                }
+                umma::tmem_ld_wait();
+                umma::tmem_ld16(taddr + 96 + 16 * h, rawB);
+                if (!is_pe) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * sg[j];
+                  store_row16<kF16>(ra, 64 + 16 * h, v, no_st);
+                } else {
+                  copy_row16(ra, pes, jpe, 64 + 16 * h);
+                }
+                umma::tmem_ld_wait();
+                if (h == 0) umma::tmem_ld16(taddr + 16, raw);
+                if (!is_pe) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rawB[j]) * sg[j];
+                  store_row16<kF16>(ra, 96 + 16 * h, v, no_st);
+                } else {
+                  copy_row16(ra, pes, jpe, 96 + 16 * h);
                 }
               }
             } else {
+              uint32_t rawB[16];
+              const int jpe = F - S.out_rows;
+              umma::tmem_ld16(taddr, raw);
 #pragma unroll 1
-              for (int c = 0; c < 8; ++c) {
-                umma::tmem_ld16(taddr + 16 * c, raw);
+              for (int c = 0; c < 8; c += 2) {
                 umma::tmem_ld_wait();
+                umma::tmem_ld16(taddr + 16 * (c + 1), rawB);
                 if (!is_pe) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
+                  store_row16<kF16>(ra, 16 * c, v, no_st);
+                } else {
+                  copy_row16(ra, pes, jpe, 16 * c);
                 }
-                if (!is_pe) store_row16<kF16>(ra, 16 * c, v, no_st);
-                else copy_row16(ra, pes, F - S.out_rows, 16 * c);
+                umma::tmem_ld_wait();
+                if (c + 2 < 8) umma::tmem_ld16(taddr + 16 * (c + 2), raw);
+                if (!is_pe) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(rawB[j]) + b);
+                  store_row16<kF16>(ra, 16 * (c + 1), v, no_st);
+                } else {
+                  copy_row16(ra, pes, jpe, 16 * (c + 1));
+                }
               }
             }
           }

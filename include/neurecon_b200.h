@@ -156,6 +156,12 @@ int nr_nerf_forward_f32(const nr_nerf_net_t* net, const float* x, const float* v
 int nr_near_far_from_sphere(const float* rays_o, const float* rays_d, int64_t R, float r,
                             float* near, float* far, void* stream);
 
+/* get_rays(c2w, intrinsics, H, W, N_rays) -- rend_util.py:95-164 (the step in front of volume_render in
+ * all three callers).  pose [B,4,4] camera-to-world, intr [B,5] = fx, fy, cx, cy, skew, select_inds
+ * int64 [B,N] (pixel = h*W + w) or NULL for all N = H*W pixels; rays_o, rays_d [B,N,3] (not normalised). */
+int nr_get_rays(const float* pose, const float* intr, const int64_t* select_inds, int32_t B, int32_t W,
+                int64_t N, float* rays_o, float* rays_d, void* stream);
+
 /* sample_pdf(bins, weights, N, det, eps) -- rend_util.py:255-292.
  * bins [R,M], weights [R,M-1], u [R,N] or NULL (det: torch.linspace(0,1,N) bit-exact),
  * samples [R,N]; optional outputs: below/above int32 [R,N] (the gathered indices) and the

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "nr_nerf_forward_f32": (C.c_int, [C.POINTER(NerfNet), _P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "nr_near_far_from_sphere": (C.c_int, [_P, _P, _I64, _F, _P, _P, _P]),
     "nr_grid_points": (C.c_int, [_I64, _I64, _I32, C.c_double, _I32, _P, _P]),
+    "nr_get_rays": (C.c_int, [_P, _P, _P, _I32, _I32, _I64, _P, _P, _P]),
     "nr_sample_pdf": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "nr_neus_ray_setup": (C.c_int, [_P, _P, _I64, _F, _F, _F, _I32, _P, _P, _P, _P, _P, _P]),
     "nr_neus_upsample_step": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),

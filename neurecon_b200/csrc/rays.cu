@@ -486,6 +486,34 @@ __global__ void neus_composite_bg_kernel(const float* __restrict__ sdf, const fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// get_rays (rend_util.py:95-164): pinhole rays for selected pixels of B cameras.  pose [B,4,4]
+// camera-to-world, intr [B,5] = fx, fy, cx, cy, skew; select_inds [B,N] (pixel = h*W + w) or NULL = all.
+// ---------------------------------------------------------------------------------------------
+__global__ void get_rays_kernel(const float* __restrict__ pose, const float* __restrict__ intr,
+                                const int64_t* __restrict__ select_inds, int B, int W, int64_t N,
+                                float* __restrict__ rays_o, float* __restrict__ rays_d) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * N) return;
+  const int b = (int)(idx / N);
+  const int64_t pix = select_inds ? select_inds[idx] : idx % N;
+  const float x = (float)(pix % W), y = (float)(pix / W);
+  const float fx = intr[5 * b], fy = intr[5 * b + 1], cx = intr[5 * b + 2], cy = intr[5 * b + 3], sk = intr[5 * b + 4];
+  // lift (rend_util.py:95-109), z = 1
+  const float xl = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(x, cx), __fdiv_rn(__fmul_rn(cy, sk), fy)),
+                                       __fdiv_rn(__fmul_rn(sk, y), fy)), fx);
+  const float yl = __fdiv_rn(__fsub_rn(y, cy), fy);
+  const float* p = pose + 16 * b;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    // world = p @ [xl, yl, 1, 1]; rays_d = world - cam_loc   (same two roundings as the reference)
+    const float t = p[4 * r + 3];
+    const float w = p[4 * r] * xl + p[4 * r + 1] * yl + p[4 * r + 2] + t;
+    rays_d[3 * idx + r] = __fsub_rn(w, t);
+    rays_o[3 * idx + r] = t;
+  }
+}
+
 }  // namespace
 
 extern "C" int nr_near_far_from_sphere(const float* rays_o, const float* rays_d, int64_t R, float r, float* near,
@@ -589,5 +617,16 @@ extern "C" int nr_neus_composite_bg(const float* sdf, const float* nablas, const
       sdf, nablas, radiance, rays_o, dirs, d_vals, sigma_out, radiance_out, s_dev, radius, R, M, n_out, white_bkgd, rgb,
       depth, acc, normals, cdf_out, alpha_out, weights_out, radiance_blend_out);
   NR_CHECK_LAUNCH("neus_composite_bg_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_get_rays(const float* pose, const float* intr, const int64_t* select_inds, int32_t B, int32_t W,
+                           int64_t N, float* rays_o, float* rays_d, void* stream) {
+  NR_CHECK_ARG(B >= 0 && N >= 0 && W >= 1, "nr_get_rays: bad sizes");
+  if ((int64_t)B * N == 0) return NR_OK;
+  NR_CHECK_ARG(pose && intr && rays_o && rays_d, "nr_get_rays: null pointer");
+  get_rays_kernel<<<(unsigned)nr_cdiv((int64_t)B * N, 256), 256, 0, (cudaStream_t)stream>>>(pose, intr, select_inds, B, W,
+                                                                                            N, rays_o, rays_d);
+  NR_CHECK_LAUNCH("get_rays_kernel");
   return NR_OK;
 }

@@ -89,3 +89,53 @@ def get_dvals_from_radius(ray_origins, ray_directions, rs, far_end=True):
     assert (under > 0).all()
     sq = torch.sqrt(under)
     return (-od + sq) if far_end else (-od - sq).clamp_min(0.0)
+
+
+def quat_to_rot(q):
+    """rend_util.py:76-93 (tiny host-side composition; only used by get_rays for 7-vector poses)."""
+    import torch.nn.functional as F
+    q = F.normalize(q, dim=-1)
+    qr, qi, qj, qk = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    R = torch.stack([
+        1 - 2 * (qj ** 2 + qk ** 2), 2 * (qj * qi - qk * qr), 2 * (qi * qk + qr * qj),
+        2 * (qj * qi + qk * qr), 1 - 2 * (qi ** 2 + qk ** 2), 2 * (qj * qk - qi * qr),
+        2 * (qk * qi - qj * qr), 2 * (qj * qk + qi * qr), 1 - 2 * (qi ** 2 + qj ** 2)], dim=-1)
+    return R.reshape(*q.shape[:-1], 3, 3)
+
+
+def get_rays(c2w, intrinsics, H, W, N_rays=-1):
+    """rend_util.py:112-164: (rays_o, rays_d, select_inds) for [..., 4, 4] (or [..., 7] quaternion + position)
+    poses.  Pixel selection draws the same two ``torch.randint`` calls on the CPU generator as the reference."""
+    _lib.require_cuda(c2w)
+    lib = _lib.get_lib()
+    dev = c2w.device
+    if c2w.shape[-1] == 7:
+        p = torch.eye(4, device=dev).repeat([*c2w.shape[:-1], 1, 1]).float()
+        p[..., :3, :3] = quat_to_rot(c2w[..., :4])
+        p[..., :3, 3] = c2w[..., 4:]
+    else:
+        p = c2w
+    prefix = p.shape[:-2]
+    B = 1
+    for s in prefix:
+        B *= s
+    pose = _lib.f32c(p.reshape(B, 4, 4))
+    K = intrinsics.to(dev).float().expand(*prefix, *intrinsics.shape[-2:]).reshape(B, *intrinsics.shape[-2:])
+    intr = torch.stack([K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2], K[:, 0, 1]], dim=-1).contiguous()
+    if N_rays > 0:
+        N_rays = min(N_rays, H * W)
+        select_hs = torch.randint(0, H, size=[N_rays]).to(dev)
+        select_ws = torch.randint(0, W, size=[N_rays]).to(dev)
+        select_inds = (select_hs * W + select_ws).expand([*prefix, N_rays])
+        N = N_rays
+        sel = select_inds.reshape(B, N).contiguous()
+    else:
+        N = H * W
+        select_inds = torch.arange(N, device=dev).expand([*prefix, N])
+        sel = None
+    rays_o = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    rays_d = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nr_get_rays(_lib.ptr(pose), _lib.ptr(intr), _lib.ptr(sel), B, W, N, _lib.ptr(rays_o), _lib.ptr(rays_d),
+                                   _lib.stream_ptr(dev)), "get_rays")
+    return rays_o.reshape(*prefix, N, 3), rays_d.reshape(*prefix, N, 3), select_inds

@@ -94,3 +94,23 @@ def make_rays(n_rays, shell_radius=2.5, jitter=0.1, seed=0):
 def make_points(n, extent=1.0, seed=0):
     rs = np.random.RandomState(seed + 104729)
     return _t(rs.uniform(-extent, extent, size=(n, 3)))
+
+
+def look_at_pose(eye, target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0)):
+    """4x4 camera-to-world (OpenCV convention: +z forward, +y down) looking from `eye` at `target`."""
+    eye, target, up = (np.asarray(v, dtype=np.float64) for v in (eye, target, up))
+    z = target - eye
+    z /= np.linalg.norm(z)
+    x = np.cross(z, up)
+    x /= np.linalg.norm(x)
+    y = np.cross(z, x)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = x, y, z, eye
+    return _t(m)
+
+
+def pinhole_intrinsics(H, W, fov_deg=50.0, skew=0.0):
+    f = 0.5 * W / math.tan(0.5 * math.radians(fov_deg))
+    K = np.eye(4)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[0, 1] = f, f * 1.01, 0.5 * W - 0.3, 0.5 * H + 0.2, skew
+    return _t(K)

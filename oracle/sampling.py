@@ -101,3 +101,23 @@ def sample_cdf(bins, cdf, n, det=False, eps=1e-5, u=None, return_inds=False):
     if u is None:
         u = make_u(cdf.shape[:-1], n, det, cdf.dtype)
     return invert_cdf(bins, cdf, u, eps, return_inds)
+
+
+def get_rays(c2w, intrinsics, H, W, select_inds=None):
+    """utils/rend_util.py:95-164 for [..., 4, 4] poses; ``select_inds`` [..., N] (pixel = h*W + w) or None = all."""
+    prefix = c2w.shape[:-2]
+    ii, jj = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing="ij")
+    i = ii.t().reshape([*[1] * len(prefix), H * W]).expand([*prefix, H * W])
+    j = jj.t().reshape([*[1] * len(prefix), H * W]).expand([*prefix, H * W])
+    if select_inds is not None:
+        i, j = torch.gather(i, -1, select_inds), torch.gather(j, -1, select_inds)
+    fx, fy = intrinsics[..., 0, 0].unsqueeze(-1), intrinsics[..., 1, 1].unsqueeze(-1)
+    cx, cy, sk = intrinsics[..., 0, 2].unsqueeze(-1), intrinsics[..., 1, 2].unsqueeze(-1), intrinsics[..., 0, 1].unsqueeze(-1)
+    z = torch.ones_like(i)
+    x_lift = (i - cx + cy * sk / fy - sk * j / fy) / fx * z
+    y_lift = (j - cy) / fy * z
+    cam = torch.stack((x_lift, y_lift, z, torch.ones_like(z)), dim=-1).transpose(-1, -2)
+    world = torch.matmul(c2w, cam).transpose(-1, -2)[..., :3]
+    cam_loc = c2w[..., :3, 3]
+    rays_d = world - cam_loc[..., None, :]
+    return cam_loc[..., None, :].expand_as(rays_d), rays_d

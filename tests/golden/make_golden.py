@@ -81,6 +81,14 @@ def golden_sampling(ref):
     o, d = synthetic.make_rays(64, seed=4)
     d = torch.nn.functional.normalize(d, dim=-1)
     near, far = ref.rend_util.near_far_from_sphere(o, d, r=1.0)
+    # get_rays: two cameras, skewed intrinsics, random pixel selection from a seeded CPU generator
+    H, W = 24, 32
+    c2w = torch.stack([synthetic.look_at_pose([2.0, 1.0, 1.5]), synthetic.look_at_pose([-1.5, 2.2, 0.4])])
+    K = synthetic.pinhole_intrinsics(H, W, skew=0.7)[None].expand(2, 4, 4).contiguous()
+    ro_all, rd_all, _ = ref.rend_util.get_rays(c2w, K, H, W, N_rays=-1)
+    torch.manual_seed(123)
+    ro_sel, rd_sel, sel = ref.rend_util.get_rays(c2w, K, H, W, N_rays=50)
+    npz("get_rays.npz", rays_o_all=ro_all, rays_d_all=rd_all, rays_o_sel=ro_sel.contiguous(), rays_d_sel=rd_sel, select_inds=sel.contiguous())
     npz("sampling.npz", bins=bins, weights=w, u=u, det=det, sto=sto, cdf_in=cdf_in, sto_cdf=sto_cdf,
         det_cdf=det_cdf, near=near, far=far)
 

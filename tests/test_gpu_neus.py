@@ -253,3 +253,22 @@ def test_neus_nerfpp_background_vs_golden(tier, tol):
             assert rel_err(ret["sigma_out"], g["sigma_out"]) < 1e-4 and rel_err(ret["radiance_out"], g["radiance_out"]) < 1e-4
         pj = neus.volume_render(o.to(DEV), d.to(DEV), m, detailed_output=False, perturb=True, N_outside=32)[0]
         assert torch.isfinite(pj).all()
+
+
+def test_get_rays_vs_golden():
+    from test_oracle_golden import _cams
+    g = load_golden("get_rays.npz")
+    c2w, K, H, W = _cams()
+    ro, rd, sel = rend_util.get_rays(c2w.to(DEV), K.to(DEV), H, W, N_rays=-1)
+    assert ro.shape == (2, H * W, 3) and sel.shape == (2, H * W)
+    assert torch.equal(ro.cpu(), g["rays_o_all"]) and rel_err(rd, g["rays_d_all"]) < 1e-6
+    torch.manual_seed(123)  # same CPU generator draws as the reference (rend_util.py:137-138)
+    ro, rd, sel = rend_util.get_rays(c2w.to(DEV), K.to(DEV), H, W, N_rays=50)
+    assert torch.equal(sel.cpu(), g["select_inds"])
+    assert torch.equal(ro.cpu(), g["rays_o_sel"]) and rel_err(rd, g["rays_d_sel"]) < 1e-6
+    # single camera without batch prefix, 3x3 intrinsics, quaternion pose
+    ro1, rd1, _ = rend_util.get_rays(c2w[0].to(DEV), K[0, :3, :3].to(DEV), H, W)
+    assert ro1.shape == (H * W, 3) and torch.equal(rd1, rend_util.get_rays(c2w[:1].to(DEV), K[:1].to(DEV), H, W)[1][0])
+    q = torch.tensor([[0.9, 0.1, -0.3, 0.2, 1.0, 2.0, 3.0]], device=DEV)
+    roq, rdq, _ = rend_util.get_rays(q, K[:1].to(DEV), H, W)
+    assert torch.allclose(roq[0, 0].cpu(), torch.tensor([1.0, 2.0, 3.0])) and torch.isfinite(rdq).all()

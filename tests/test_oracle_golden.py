@@ -191,3 +191,19 @@ def test_neus_nerfpp_render_golden():
     for k, tol in (("rgb", 2e-5), ("depth_volume", 1e-4), ("mask_volume", 2e-5), ("normals_volume", 5e-5)):
         assert rel_err(ret[k][same], g[k][same]) < tol, (k, rel_err(ret[k][same], g[k][same]))
         assert rel_err(ret[k], g[k]) < 5e-3, (k, rel_err(ret[k], g[k]))
+
+
+def _cams():
+    H, W = 24, 32
+    c2w = torch.stack([synthetic.look_at_pose([2.0, 1.0, 1.5]), synthetic.look_at_pose([-1.5, 2.2, 0.4])])
+    K = synthetic.pinhole_intrinsics(H, W, skew=0.7)[None].expand(2, 4, 4).contiguous()
+    return c2w, K, H, W
+
+
+def test_get_rays_golden():
+    g = load_golden("get_rays.npz")
+    c2w, K, H, W = _cams()
+    ro, rd = sampling.get_rays(c2w, K, H, W)
+    assert rel_err(rd, g["rays_d_all"]) < 1e-6 and torch.equal(ro, g["rays_o_all"])
+    ro, rd = sampling.get_rays(c2w, K, H, W, g["select_inds"])
+    assert rel_err(rd, g["rays_d_sel"]) < 1e-6 and torch.equal(ro, g["rays_o_sel"])

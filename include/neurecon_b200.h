@@ -318,6 +318,11 @@ int nr_unisurf_composite(const float* logits, const float* nablas, const float* 
                          float* depth, float* acc, float* normals, float* alpha_out, float* weights_out,
                          void* stream);
 
+/* sphere_tracing_surface_points, one iteration (ray_casting.py:178-183): d[mask] += val[mask]
+ * (val = NULL: only emit the points of the current d), mask cleared where d leaves [0, far], pts = o + d*dir. */
+int nr_sphere_trace_step(const float* val, const float* rays_o, const float* dirs, float far, int64_t R,
+                         float* d, uint8_t* mask, float* pts, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * bf16 tier: fused PE + SDF MLP (+ forward-mode normals) + radiance MLP on tcgen05 / TMEM.
  * The host packs the weights once into a pre-swizzled bf16 image (16 KB chunks = A tiles of

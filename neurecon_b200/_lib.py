@@ -95,6 +95,7 @@ _SIGNATURES = {
     "nr_unisurf_first_crossing": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P]),
     "nr_unisurf_secant_step": (C.c_int, [_P, _F, _P, _P, _P, _I64, _P, _P, _P]),
     "nr_unisurf_sample": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _F, _F, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "nr_sphere_trace_step": (C.c_int, [_P, _P, _P, _F, _I64, _P, _P, _P, _P]),
     "nr_unisurf_composite": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "nr_mlp_umma_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _P, _I64, _P, _P, _P, _I64, _P, _P, _P]),
     "nr_mlp_umma_set_trace": (C.c_int, [_P]),

@@ -249,6 +249,23 @@ __global__ void unisurf_composite_kernel(const float* __restrict__ logits, const
   }
 }
 
+// One sphere-tracing update (ray_casting.py:178-183): d[mask] += sdf[mask]; rays leaving [0, far] are dropped;
+// emits the next query points.
+__global__ void sphere_trace_step_kernel(const float* __restrict__ val, const float* __restrict__ rays_o,
+                                         const float* __restrict__ dirs, float far, int64_t R, float* __restrict__ d,
+                                         uint8_t* __restrict__ mask, float* __restrict__ pts) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  float di = d[i];
+  uint8_t m = mask[i];
+  if (val && m) di = __fadd_rn(di, val[i]);
+  if (di > far || di < 0.0f) m = 0;
+  d[i] = di; mask[i] = m;
+  pts[3 * i] = __fadd_rn(rays_o[3 * i], __fmul_rn(dirs[3 * i], di));
+  pts[3 * i + 1] = __fadd_rn(rays_o[3 * i + 1], __fmul_rn(dirs[3 * i + 1], di));
+  pts[3 * i + 2] = __fadd_rn(rays_o[3 * i + 2], __fmul_rn(dirs[3 * i + 2], di));
+}
+
 }  // namespace
 
 extern "C" int nr_unisurf_ray_setup(const float* rays_o, const float* rays_d, int64_t R, float radius,
@@ -318,5 +335,15 @@ extern "C" int nr_unisurf_composite(const float* logits, const float* nablas, co
   unisurf_composite_kernel<<<(unsigned)nr_cdiv(R, 4), 128, 0, (cudaStream_t)stream>>>(
       logits, nablas, radiance, d_all, R, M, white_bkgd, rgb, depth, acc, normals, alpha_out, weights_out);
   NR_CHECK_LAUNCH("unisurf_composite_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_sphere_trace_step(const float* val, const float* rays_o, const float* dirs, float far, int64_t R,
+                                    float* d, uint8_t* mask, float* pts, void* stream) {
+  NR_CHECK_ARG(R >= 0, "nr_sphere_trace_step: bad sizes");
+  if (R == 0) return NR_OK;
+  NR_CHECK_ARG(rays_o && dirs && d && mask && pts, "nr_sphere_trace_step: null pointer");
+  sphere_trace_step_kernel<<<(unsigned)nr_cdiv(R, 256), 256, 0, (cudaStream_t)stream>>>(val, rays_o, dirs, far, R, d, mask, pts);
+  NR_CHECK_LAUNCH("sphere_trace_step_kernel");
   return NR_OK;
 }

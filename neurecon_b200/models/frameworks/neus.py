@@ -61,7 +61,12 @@ class NeuS(nn.Module):
             from ..base import NeRF
             self.nerf_outside = NeRF(input_ch=4, multires=10, multires_view=4, use_view_dirs=True)
 
+    def _needs_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def forward_radiance(self, x, view_dirs):
+        if not self._needs_grad():
+            return query_radiance(self.implicit_surface, self.radiance_net, x, view_dirs)[0]
         _, nablas, geometry_feature = self.implicit_surface.forward_with_nablas(x)
         return self.radiance_net.forward(x, view_dirs, nablas, geometry_feature)
 
@@ -69,6 +74,8 @@ class NeuS(nn.Module):
         return torch.exp(self.ln_s * self.speed_factor)
 
     def forward(self, x, view_dirs):
+        if not self._needs_grad():
+            return query_radiance(self.implicit_surface, self.radiance_net, x, view_dirs)
         sdf, nablas, geometry_feature = self.implicit_surface.forward_with_nablas(x)
         radiances = self.radiance_net.forward(x, view_dirs, nablas, geometry_feature)
         return radiances, sdf, nablas

@@ -48,6 +48,11 @@ class VolSDF(nn.Module):
         return sdf, nablas, h
 
     def forward(self, x, view_dirs):
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            radiances, sdf, nablas = query_radiance(self.implicit_surface, self.radiance_net, x, view_dirs)
+            if self.use_sphere_bg:
+                sdf = torch.min(sdf, self.obj_bounding_radius - x.norm(dim=-1))
+            return radiances, sdf, nablas
         sdf, nablas, geometry_feature = self.forward_surface_with_nablas(x)
         radiances = self.radiance_net.forward(x, view_dirs, nablas, geometry_feature)
         return radiances, sdf, nablas

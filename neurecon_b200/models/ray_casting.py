@@ -56,3 +56,67 @@ def root_finding_surface_points(surface_query_fn, rays_o, rays_d, near=0.0, far=
         d_out = torch.where(mask, d_pred, fill)
         d_out = torch.where(m0, d_out, torch.zeros_like(d_out))
     return d_out.reshape(prefix), pt_pred.reshape(*prefix, 3), mask.reshape(prefix), msc.reshape(prefix)
+
+
+def sphere_tracing_surface_points(implicit_surface, rays_o, rays_d, near=0.0, far=6.0, batched=True, batched_info={},
+                                  N_iters=20):
+    """ray_casting.py:163-184: N_iters steps of d += sdf(o + d*dir) (rays_d normalised).  Returns (d_preds, pts, mask)."""
+    _lib.require_cuda(rays_o, rays_d)
+    lib = _lib.get_lib()
+    with torch.no_grad():
+        prefix = rays_o.shape[:-1]
+        o = _lib.f32c(rays_o.detach().reshape(-1, 3))
+        d = _lib.f32c(rays_d.detach().reshape(-1, 3))
+        R, dev = o.shape[0], o.device
+        d_preds = torch.full((R,), float(near), dtype=torch.float32, device=dev)
+        mask = torch.ones(R, dtype=torch.uint8, device=dev)
+        pts = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            val = None
+            for _ in range(N_iters + 1):
+                _lib.check(lib.nr_sphere_trace_step(_lib.ptr(val), _lib.ptr(o), _lib.ptr(d), float(far), R, _lib.ptr(d_preds),
+                                                    _lib.ptr(mask), _lib.ptr(pts), st), "sphere_trace_step")
+                if _ == N_iters:
+                    break
+                val = _lib.f32c(implicit_surface.forward(pts).reshape(R))
+    return d_preds.reshape(prefix), pts.reshape(*prefix, 3), mask.bool().reshape(prefix)
+
+
+def surface_render(rays_o, rays_d, model, calc_normal=True, rayschunk=8192, netchunk=1048576, batched=True,
+                   use_view_dirs=True, show_progress=False, ray_casting_algo='', ray_casting_cfgs={}, **not_used_kwargs):
+    """ray_casting.py:187-263: surface rendering (the reference's "100x faster" mode): find the surface point per
+    ray, evaluate ``model.forward`` there.  Returns (colors, depths, extras)."""
+    from collections import OrderedDict
+    import torch.nn.functional as F
+    _lib.require_cuda(rays_o, rays_d)
+    if not use_view_dirs:
+        raise NotImplementedError("use_view_dirs=False is not supported")
+    with torch.no_grad():
+        B = rays_d.shape[0] if batched else None
+        shape = [B, -1, 3] if batched else [-1, 3]
+        dim = 1 if batched else 0
+        rays_o = torch.reshape(rays_o, shape).float()
+        rays_d = F.normalize(torch.reshape(rays_d, shape).float(), dim=-1)
+        colors, depths, nablas, masks = [], [], [], []
+        for i in range(0, rays_o.shape[dim], rayschunk):
+            ro = rays_o[:, i:i + rayschunk] if batched else rays_o[i:i + rayschunk]
+            rd = rays_d[:, i:i + rayschunk] if batched else rays_d[i:i + rayschunk]
+            if ray_casting_algo == 'root_finding':
+                d_pred, pt_pred, mask, *_ = root_finding_surface_points(model.implicit_surface, ro, rd, batched=batched,
+                                                                        **ray_casting_cfgs)
+            elif ray_casting_algo == 'sphere_tracing':
+                d_pred, pt_pred, mask = sphere_tracing_surface_points(model.implicit_surface, ro, rd, batched=batched,
+                                                                      **ray_casting_cfgs)
+            else:
+                raise NotImplementedError
+            color, _, nab = model.forward(pt_pred, rd)
+            color = torch.where(mask[..., None], color, torch.zeros_like(color))
+            colors.append(color); depths.append(d_pred); nablas.append(nab); masks.append(mask)
+        colors, depths = torch.cat(colors, dim), torch.cat(depths, dim)
+        nablas, masks = torch.cat(nablas, dim), torch.cat(masks, dim)
+        extras = OrderedDict([('implicit_nablas', nablas), ('mask_surface', masks)])
+        if calc_normal:
+            normals = F.normalize(nablas, dim=-1)
+            extras['normals_surface'] = torch.where(masks[..., None], normals, torch.zeros_like(normals))
+        return colors, depths, extras

@@ -115,3 +115,14 @@ def volume_render(rays_o, rays_d, sd, cfg, calc_normal=True, logit_tau=0.0, whit
     ret.update(surface_points=pt_pred, mask_surface=mask, depth_surface=d_pred, radiance=radiances,
                implicit_surface=logits, implicit_nablas=nablas, d_all=d_all, mask_sign_change=mask_sign_change)
     return ret["rgb"], ret["depth_volume"], ret
+
+
+def sphere_tracing(sdf_fn, rays_o, rays_d, near=0.0, far=6.0, N_iters=20):
+    """ray_casting.py:163-184."""
+    d = torch.ones(rays_o.shape[:-1], dtype=rays_o.dtype) * near
+    mask = torch.ones_like(d, dtype=torch.bool)
+    for _ in range(N_iters):
+        val = sdf_fn(rays_o + rays_d * d[..., None])
+        d = torch.where(mask, d + val, d)
+        mask = mask & ~(d > far) & ~(d < 0)
+    return d, rays_o + rays_d * d[..., None], mask

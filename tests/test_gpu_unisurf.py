@@ -80,3 +80,39 @@ def test_unisurf_unbatched_perturb_and_chunks():
         # like the reference, chunking changes the normalisation set of the radiance normals
         c = unisurf.volume_render(o, d, m, detailed_output=False, rayschunk=11)[0]
         assert c.shape == rgb.shape and torch.isfinite(c).all()
+
+
+def test_sphere_tracing_and_surface_render():
+    """§8(f) rank 2: surface rendering.  Sphere tracing vs the oracle (analytic SDF: exact; network SDF: fp32 tier),
+    and surface_render's contract (colour zero off-surface, normals, keys)."""
+    from conftest import build_neus
+    from oracle import nets
+    R = 90
+    o, d = synthetic.make_rays(R, shell_radius=2.5, jitter=0.2, seed=23)
+    d = torch.nn.functional.normalize(d, dim=-1)
+    sph = lambda p: p.norm(dim=-1) - 0.5
+
+    class _S:  # duck-typed "implicit_surface"
+        forward = staticmethod(sph)
+    want_d, want_p, want_m = ou.sphere_tracing(sph, o, d, near=0.0, far=6.0)
+    got_d, got_p, got_m = ray_casting.sphere_tracing_surface_points(_S, o[None].to(DEV), d[None].to(DEV), near=0.0, far=6.0)
+    assert got_d.shape == (1, R) and torch.equal(got_m[0].cpu(), want_m) and 0 < want_m.sum() < R
+    assert rel_err(got_d[0], want_d) < 1e-6 and rel_err(got_p[0], want_p) < 1e-6
+    neurecon_b200.set_precision("fp32")
+    try:
+        m = build_neus(seed=1, device=DEV)
+        L = nets.layers_from_state_dict(cpu_state_dict(m), "implicit_surface.surface_fc_layers", 9)
+        want_d, _, want_m = ou.sphere_tracing(lambda p: nets.sdf_forward(p, L), o, d, near=0.0, far=6.0)
+        with torch.no_grad():
+            col, dep, ext = ray_casting.surface_render(o.to(DEV), d.to(DEV), m, batched=False, ray_casting_algo="sphere_tracing",
+                                                       ray_casting_cfgs=dict(near=0.0, far=6.0))
+        assert list(ext.keys()) == ["implicit_nablas", "mask_surface", "normals_surface"] and col.shape == (R, 3)
+        assert (ext["mask_surface"].cpu() == want_m).float().mean() > 0.97
+        both = ext["mask_surface"].cpu() & want_m
+        assert rel_err(dep.cpu()[both], want_d[both]) < 1e-4
+        assert (col[~ext["mask_surface"]] == 0).all() and (ext["normals_surface"][~ext["mask_surface"]] == 0).all()
+        col2 = ray_casting.surface_render(o[None].to(DEV), d[None].to(DEV), m, batched=True, ray_casting_algo="root_finding",
+                                          ray_casting_cfgs=dict(near=0.0, far=6.0))[0]
+        assert col2.shape == (1, R, 3) and torch.isfinite(col2).all()
+    finally:
+        neurecon_b200.set_precision("fp16")

@@ -383,6 +383,12 @@ int nr_mlp_umma_set_trace(void* buf);
 int nr_selftest_umma(const void* a_image, const float* B, int32_t K, int32_t N, float* D,
                      int32_t variant, void* stream);
 
+/* Tensor-pipe rate probe (tools/bench_umma_rate.py): cycles for n_mmas back-to-back 128 x N x 16 MMAs on operands
+ * resident in shared memory, optionally under concurrent shared-memory store / bulk-copy traffic.
+ * gsrc: >= 1 MiB of device memory (copy source); out: [grid][2] int64 = {issue..completion, issue loop} cycles. */
+int nr_bench_umma(int32_t N, int32_t n_mmas, int32_t store_warps, int32_t bulk_copies, const void* gsrc,
+                  int32_t grid, long long* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,6 +99,7 @@ _SIGNATURES = {
     "nr_unisurf_composite": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "nr_mlp_umma_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _P, _I64, _P, _P, _P, _I64, _P, _P, _P]),
     "nr_mlp_umma_set_trace": (C.c_int, [_P]),
+    "nr_bench_umma": (C.c_int, [_I32, _I32, _I32, _I32, _P, _I32, _P, _P]),
     "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
     "nr_neus_composite": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
@@ -131,7 +132,7 @@ def get_lib():
                 raise RuntimeError(
                     "neurecon_b200: CUDA library %s is missing and nvcc is not available to build it; "
                     "run `python -m neurecon_b200.build`. There is no CPU fallback." % _LIB_PATH)
-        lib = C.CDLL(_LIB_PATH)
+        lib = C.CDLL(os.environ.get("NEURECON_B200_LIB", _LIB_PATH))  # override: kernel experiments only
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
             fn.restype = res

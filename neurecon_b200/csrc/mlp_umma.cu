@@ -24,7 +24,11 @@
 
 namespace {
 
-constexpr int kStages = 4;
+#ifndef NR_EXP_STAGES
+#define NR_EXP_STAGES 4
+#endif
+constexpr int kStages = NR_EXP_STAGES;
+constexpr int kStashCopies = NR_EXP_STAGES > 4 ? 1 : 2;   // experiment only: >4 stages share one stash (wrong results)
 constexpr int kPeStashRows = 40;          // embedding rows kept for the skip layer (multires <= 6)
 constexpr uint32_t kChunkBytes = 16384;      // one A tile: 128 features x 64 k, bf16
 constexpr uint32_t kActBytes = 65536;        // one tile's B operand: 256 k-rows x 128 columns, bf16
@@ -54,7 +58,7 @@ struct SmemLayout {
   static constexpr uint32_t vs = xs + 2 * 384 * 4;                   // 2 x 32 x 3 floats (view dirs)
   static constexpr uint32_t nabs = vs + 2 * 96 * 4;                  // 2 x 32 x 3 floats (normal stash)
   static constexpr uint32_t pes = nabs + 2 * 96 * 4;                 // 2 x 40 rows x 256 B: embedding stash (skip)
-  static constexpr uint32_t bars = pes + 2 * kPeStashRows * 256;     // mbarriers
+  static constexpr uint32_t bars = pes + kStashCopies * kPeStashRows * 256;     // mbarriers
   static constexpr uint32_t total = bars + 256;
 };
 
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
     uint32_t acc_par = 0;
     int tcnt = 0;
     const bool tracer = (mo == 0 && q == 0 && lane == 0 && t == 0);
-    uint8_t* pes = smem + SmemLayout::pes + t * (kPeStashRows * 256);   // embedding rows, linear [row][128 cols] 16-bit
+    uint8_t* pes = smem + SmemLayout::pes + (kStashCopies > 1 ? t : 0) * (kPeStashRows * 256);   // embedding rows, linear [row][128 cols] 16-bit
     const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
     const bool no_st = P.debug_flags & 8;
 

@@ -82,6 +82,84 @@ selftest_umma_kernel(const uint8_t* __restrict__ a_image, const float* __restric
   if (warp == 0) umma::tmem_dealloc(tmem_base, 128);
 }
 
+// Tensor-pipe rate probe: one lane issues `n_mmas` back-to-back M=128 x N x 16 MMAs on operands resident in
+// shared memory (K = 256 cycled), optionally while `store_warps` other warps hammer shared memory with 16-byte
+// stores and/or a producer keeps 16 KB bulk copies in flight -- the traffic mix of the fused MLP kernel.
+// out[block] = cycles from the first issue to the completion of the last MMA.
+__global__ void __launch_bounds__(640, 1)
+bench_umma_kernel(int N, int n_mmas, int store_warps, int bulk_copies, const uint8_t* __restrict__ gsrc,
+                  long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                 // 64 KB: 4 chunks of 128 x 64
+  uint8_t* sB = smem + 65536;         // 64 KB (N <= 128) or 128 KB (N = 256): 256 k-rows, MN-major SW128
+  uint8_t* sX = smem + 65536 + 131072;  // 16 KB scratch for the store / copy traffic
+  __shared__ uint64_t bar_mma, bar_copy;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int stop_flag;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < (65536 + 131072 + 16384) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 0) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
+  if (tid == 0) {
+    umma::mbar_init(&bar_mma, 1);
+    umma::mbar_init(&bar_copy, 1);
+    umma::fence_barrier_init();
+    stop_flag = 0;
+  }
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (warp == 1) {
+    const uint32_t idesc = umma::make_idesc_f16(128, N, 0, 1);
+    const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
+    const uint32_t a_lo0 = umma::smem_desc_lo(umma::smem_u32(sA), 16), b_lo0 = umma::smem_desc_lo(umma::smem_u32(sB), 32768);
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mmas; i += 4) {
+      const uint32_t kc = (uint32_t)(i >> 2) & 3u;
+      const uint32_t a_lo = a_lo0 + kc * 1024, b_lo = b_lo0 + kc * 512;
+      const uint32_t d = tmem_base + (((uint32_t)i >> 4) & 1u) * (uint32_t)N;
+      if (umma::elect_one()) {
+        umma::mma_bf16_ss(d, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, 1u);
+        umma::mma_bf16_ss(d, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
+        umma::mma_bf16_ss(d, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
+        umma::mma_bf16_ss(d, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (umma::elect_one()) umma::mma_commit(&bar_mma);
+    __syncwarp();
+    umma::mbar_wait(&bar_mma, 0);
+    const long long t2 = clock64();
+    if (lane == 0) { out[2 * blockIdx.x] = t2 - t0; out[2 * blockIdx.x + 1] = t1 - t0; stop_flag = 1; }
+  } else if (warp == 2 && bulk_copies) {
+    uint32_t ph = 0;
+    while (!stop_flag) {
+      if (lane == 0) {
+        umma::mbar_arrive_expect_tx(&bar_copy, 16384u);
+        umma::bulk_g2s(sX, gsrc + (size_t)((blockIdx.x * 7 + ph) % 64) * 16384, 16384u, &bar_copy);
+      }
+      __syncwarp();
+      umma::mbar_wait(&bar_copy, ph & 1);
+      ++ph;
+    }
+  } else if (warp >= 4 && warp < 4 + store_warps) {
+    const uint32_t base = umma::smem_u32(sX) + (uint32_t)((warp - 4) & 7) * 2048 + lane * 16;
+    uint32_t it = 0;
+    while (!stop_flag) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + r * 512), "r"(it) : "memory");
+      ++it;
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 extern "C" int nr_selftest_umma(const void* a_image, const float* B, int32_t K, int32_t N, float* D, int32_t variant,
@@ -94,5 +172,17 @@ extern "C" int nr_selftest_umma(const void* a_image, const float* B, int32_t K, 
   NR_CHECK_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const uint8_t*)a_image, B, K, N, D, variant);
   NR_CHECK_LAUNCH("selftest_umma_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_bench_umma(int32_t N, int32_t n_mmas, int32_t store_warps, int32_t bulk_copies, const void* gsrc,
+                             int32_t grid, long long* out, void* stream) {
+  NR_CHECK_ARG(out && gsrc, "nr_bench_umma: null pointer");
+  NR_CHECK_ARG(N == 32 || N == 64 || N == 128 || N == 256, "nr_bench_umma: N");
+  NR_CHECK_ARG(n_mmas >= 4 && n_mmas % 4 == 0 && store_warps >= 0 && store_warps <= 16 && grid >= 1, "nr_bench_umma: sizes");
+  const size_t smem = 1024 + 65536 + 131072 + 16384;
+  NR_CHECK_CUDA(cudaFuncSetAttribute(bench_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bench_umma_kernel<<<grid, 640, smem, (cudaStream_t)stream>>>(N, n_mmas, store_warps, bulk_copies, (const uint8_t*)gsrc, out);
+  NR_CHECK_LAUNCH("bench_umma_kernel");
   return NR_OK;
 }

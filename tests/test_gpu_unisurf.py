@@ -97,7 +97,7 @@ def test_sphere_tracing_and_surface_render():
     want_d, want_p, want_m = ou.sphere_tracing(sph, o, d, near=0.0, far=6.0)
     got_d, got_p, got_m = ray_casting.sphere_tracing_surface_points(_S, o[None].to(DEV), d[None].to(DEV), near=0.0, far=6.0)
     assert got_d.shape == (1, R) and torch.equal(got_m[0].cpu(), want_m) and 0 < want_m.sum() < R
-    assert rel_err(got_d[0], want_d) < 1e-6 and rel_err(got_p[0], want_p) < 1e-6
+    assert rel_err(got_d[0], want_d) < 1e-5 and rel_err(got_p[0], want_p) < 1e-5
     neurecon_b200.set_precision("fp32")
     try:
         m = build_neus(seed=1, device=DEV)

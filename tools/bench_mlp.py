@@ -45,7 +45,7 @@ def main():
     v = torch.nn.functional.normalize(torch.randn(n, 3, device=dev), dim=-1)
     net = m.implicit_surface._umma_net(m.radiance_net)
     for mode, mflop in (("sdf", 1.049 * 459008 / 524544), ("nablas", 1.967), ("fused", 1.967 + 0.543)):
-        for flags in (0, 2):
+        for flags in [int(f) for f in os.environ.get("NR_FLAGS", "0,2").split(",")]:
             prog = net.program(mode)
             prog.debug_flags = flags
             ms = run(net, prog, x, v, n, reps)

@@ -348,6 +348,7 @@ typedef struct {
   int32_t out_rows;    /* valid output features */
   int32_t pe_fill;     /* 1: rows [out_rows, out_rows+pe_dim) of the next operand are the embedding (skip) */
   int32_t to_rad;      /* EPI_FEAT: also build the radiance operand [feat | PE(x) | PE(view) | normals] */
+  int32_t accumulate;  /* 1: the step's MMAs add onto the previous step's accumulators (split-K over two operands) */
 } nr_umma_step_t;
 
 typedef struct {
@@ -359,17 +360,22 @@ typedef struct {
   int32_t rad_extra_rows;    /* zero-padded rows after the 256 feature rows of the radiance operand */
   int32_t operand_f16;       /* 1: fp16 operands (image packed as fp16), 0: bf16; fp32 accumulation either way */
   int32_t debug_flags;       /* profiling only (results invalid): 1 = no weight copies, 2 = no epilogue math/stores */
+  int32_t input_mode;        /* 0: points -> embedding -> SDF net; 1: radiance net alone on 128-point tiles, its operand
+                                rows [0,256) bulk-copied from the feature image a previous launch wrote (feat_img) */
   nr_umma_step_t steps[NR_UMMA_MAX_STEPS];
 } nr_umma_program_t;
 
 /* x [n,3]; view [n,3] or NULL; outputs (each may be NULL): sdf [n], nabla [n,3], feat [n,feat_ld],
  * rgb [n,3].  image: the packed 16-bit weight chunks, bias: fp32 bias table.  normal_scale: NULL, or
  * 3 device floats multiplied into the normals the radiance net sees (UNISURF's chunk-wide
- * F.normalize, unisurf.py:36); the nabla output stays unscaled. */
+ * F.normalize, unisurf.py:36); the nabla output stays unscaled.
+ * feat_img: NULL, or ceil(n/128) x 64 KB of device memory holding the geometry feature as the radiance net's
+ * 16-bit shared-memory operand image (128 points per block, MN-major, 128-byte swizzle): written by an EPI_FEAT
+ * step when input_mode = 0, read when input_mode = 1 (then nabla [n,3] is an INPUT: the normals). */
 int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
                         const float* bias, size_t bias_floats, const float* x, const float* view,
                         int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
-                        const float* normal_scale, void* stream);
+                        const float* normal_scale, void* feat_img, void* stream);
 
 /* profiling hook (tools/trace_mlp.py): device buffer [3][2048][4] int64 receiving clock64 stamps of the
  * MMA <-> epilogue hand-offs of CTA 0; NULL disables. */

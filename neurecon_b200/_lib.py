@@ -45,12 +45,12 @@ NR_UMMA_MAX_STEPS = 24
 
 class UmmaStep(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("chunk_begin", "n_mt", "k_steps", "n_cols", "epi", "bias_off", "out_rows",
-                                         "pe_fill", "to_rad")]
+                                         "pe_fill", "to_rad", "accumulate")]
 
 
 class UmmaProgram(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_steps", "tangents", "multires", "rad_multires", "rad_multires_view",
-                                         "rad_extra_rows", "operand_f16", "debug_flags")] + [("steps", UmmaStep * NR_UMMA_MAX_STEPS)]
+                                         "rad_extra_rows", "operand_f16", "debug_flags", "input_mode")] + [("steps", UmmaStep * NR_UMMA_MAX_STEPS)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -97,7 +97,7 @@ _SIGNATURES = {
     "nr_unisurf_sample": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _F, _F, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "nr_sphere_trace_step": (C.c_int, [_P, _P, _P, _F, _I64, _P, _P, _P, _P]),
     "nr_unisurf_composite": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
-    "nr_mlp_umma_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _P, _I64, _P, _P, _P, _I64, _P, _P, _P]),
+    "nr_mlp_umma_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "nr_mlp_umma_set_trace": (C.c_int, [_P]),
     "nr_bench_umma": (C.c_int, [_I32, _I32, _I32, _I32, _P, _I32, _P, _P]),
     "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),

@@ -44,6 +44,7 @@ enum : int32_t {
   EPI_FEAT = 2,     // geometry feature: to global and/or radiance operand rows [0,256) + extras
   EPI_RELU = 3,     // radiance hidden layer
   EPI_RGB = 4,      // sigmoid, rows 0..2 to global
+  EPI_EXTRAS = 5,   // radiance-only mode: no accumulator read; operand rows [0, extras) <- [PE(x)|PE(view)|normals|0]
 };
 
 struct DevProgram {
@@ -55,9 +56,9 @@ struct SmemLayout {
   static constexpr uint32_t act = 0;                                 // 2 x 64 KB
   static constexpr uint32_t ring = 2 * kActBytes;                    // kStages x 16 KB
   static constexpr uint32_t xs = ring + kStages * kChunkBytes;       // 2 x 128 x 3 floats
-  static constexpr uint32_t vs = xs + 2 * 384 * 4;                   // 2 x 32 x 3 floats (view dirs)
-  static constexpr uint32_t nabs = vs + 2 * 96 * 4;                  // 2 x 32 x 3 floats (normal stash)
-  static constexpr uint32_t pes = nabs + 2 * 96 * 4;                 // 2 x 40 rows x 256 B: embedding stash (skip)
+  static constexpr uint32_t vs = xs + 2 * 384 * 4;                   // 2 x 128 x 3 floats (view dirs)
+  static constexpr uint32_t nabs = vs + 2 * 384 * 4;                 // 2 x 128 x 3 floats (normal stash)
+  static constexpr uint32_t pes = nabs + 2 * 384 * 4;                // 2 x 40 rows x 256 B: embedding stash (skip)
   static constexpr uint32_t bars = pes + kStashCopies * kPeStashRows * 256;     // mbarriers
   static constexpr uint32_t total = bars + 256;
 };
@@ -194,6 +195,7 @@ struct KArgs {
   int64_t feat_ld;
   float* rgb;          // [n,3] or null
   const float* normal_scale;  // [3] or null: normals fed to the radiance net = nabla * scale (UNISURF)
+  uint8_t* feat_img;   // [ceil(n/128)][64 KB] geometry feature as the radiance operand image (out: mode 0, in: mode 1)
   long long* trace;    // profiling only: [3][kTraceCap][4] (event, step*2+tile, clock, pair) from CTA 0
 };
 constexpr int kTraceCap = 2048;
@@ -213,18 +215,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
   uint64_t* w_empty = bars + kStages;        // [kStages]
   uint64_t* in_ready = bars + 2 * kStages;   // [2]
   uint64_t* acc_ready = in_ready + 2;        // [2]
+  uint64_t* feat_full = acc_ready + 2;       // [2] radiance-only mode: feature image landed in the operand buffer
   __shared__ uint32_t tmem_base_s;
 
   const nr_umma_program_t& P = prog.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tang = P.tangents;
+  const bool rad_only = P.input_mode == 1;
   const int ppt = tang ? 32 : 128;                       // points per tile
   const int64_t n_tiles = (a.n + ppt - 1) / ppt;
   const int64_t n_pairs = (n_tiles + 1) / 2;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
-    for (int t = 0; t < 2; ++t) { umma::mbar_init(&in_ready[t], kEpiWarpsPerTile); umma::mbar_init(&acc_ready[t], 2); }
+    for (int t = 0; t < 2; ++t) {
+      umma::mbar_init(&in_ready[t], kEpiWarpsPerTile);
+      umma::mbar_init(&acc_ready[t], 2);
+      umma::mbar_init(&feat_full[t], 1);
+    }
     umma::fence_barrier_init();
   }
   if (warp == 2) {
@@ -282,6 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
       const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
       for (int s = 0; s < P.n_steps; ++s) {
         const uint32_t n_mt = P.steps[s].n_mt, nkc = P.steps[s].k_steps >> 2;
+        const bool acc0 = P.steps[s].accumulate != 0;
         const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, P.steps[s].n_cols, 0, 1)
                                     : umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
         for (int t = 0; t < ntl; ++t) {
@@ -300,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               umma::tc_fence_after();
               const uint32_t a_lo = ring_lo + st * (kChunkBytes >> 4);
               if (umma::elect_one()) {
-                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, kc > 0 ? 1u : 0u);
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, (kc > 0 || acc0) ? 1u : 0u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
@@ -325,8 +334,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
     const int etid = (e & 7) * 32 + lane;           // 0..255 inside the tile's epilogue group
     uint8_t* act = smem + SmemLayout::act + t * kActBytes;
     float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
-    float* vs = (float*)(smem + SmemLayout::vs) + t * 96;
-    float* nabs = (float*)(smem + SmemLayout::nabs) + t * 96;
+    float* vs = (float*)(smem + SmemLayout::vs) + t * 384;
+    float* nabs = (float*)(smem + SmemLayout::nabs) + t * 384;
+    uint32_t feat_par = 0;
     const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
     uint32_t acc_par = 0;
     int tcnt = 0;
@@ -344,8 +354,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
       for (int i = etid; i < ppt * 3; i += kEpiPerTile) {
         const int64_t gi = p0 * 3 + i;
         xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
-        if (a.view && i < 96) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
+        if (a.view && (rad_only || i < 96)) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
+        if (rad_only) nabs[i] = gi < a.n * 3 ? a.nabla[gi] * (a.normal_scale ? a.normal_scale[i % 3] : 1.0f) : 0.0f;
       }
+      if (rad_only) {
+        // operand rows [0,256) = this tile's 64 KB block of the feature image, four 16 KB bulk copies
+        if (etid == 0) {
+          umma::mbar_arrive_expect_tx(&feat_full[t], kActBytes);
+          const uint8_t* src = a.feat_img + (size_t)tile * kActBytes;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) umma::bulk_g2s(act + c * kChunkBytes, src + c * kChunkBytes, kChunkBytes, &feat_full[t]);
+        }
+        umma::mbar_wait(&feat_full[t], feat_par);
+        feat_par ^= 1;
+        named_bar_sync(1 + t, kEpiPerTile);
+      } else {
       named_bar_sync(1 + t, kEpiPerTile);
       {
         const int n = etid & 127;                      // operand column
@@ -379,6 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
           }
         }
         for (int j = pe_dim + part; j < k0; j += 2) store_elem<kF16>(act, j, n, 0.f);
+      }
       }
       publish(&in_ready[t], P.debug_flags);
 
@@ -525,6 +549,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                 }
               }
               if (S.to_rad) store_row16<kF16>(ra, 16 * c, v);
+              if (a.feat_img && F < S.out_rows) {
+                // the same 16-bit operand row, placed in the 128-point block of the image: tangent tiles hold 32 points
+                // (block column 32 * (tile & 3)), value tiles 128
+                const int col0 = (tang ? 32 * (int)(tile & 3) : 0) + 16 * c;
+                uint8_t* blk = a.feat_img + (size_t)(tang ? (tile >> 2) : tile) * kActBytes + (F >> 3) * 1024 + (F & 7) * 128 +
+                               (size_t)(col0 >> 6) * kLbo;
+#pragma unroll
+                for (int j4 = 0; j4 < 2; ++j4) {
+                  uint4 w;
+                  w.x = umma::pack2<kF16>(v[8 * j4 + 0], v[8 * j4 + 1]);
+                  w.y = umma::pack2<kF16>(v[8 * j4 + 2], v[8 * j4 + 3]);
+                  w.z = umma::pack2<kF16>(v[8 * j4 + 4], v[8 * j4 + 5]);
+                  w.w = umma::pack2<kF16>(v[8 * j4 + 6], v[8 * j4 + 7]);
+                  *reinterpret_cast<uint4*>(blk + ((((((col0 & 63) >> 3) + j4) & 7) ^ (F & 7)) << 4)) = w;
+                }
+              }
             }
           }
           if (S.to_rad) {
@@ -542,31 +582,54 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               store_elem<kF16>(act, 256 + r, p, val);
             }
           }
+        } else if (S.epi == EPI_EXTRAS) {
+          // radiance-only mode, after the feature part of layer 0: the feature rows are dead, rows [0, extras) become
+          // [PE(x) | PE(view) | normals | 0-pad] of the tile's 128 points; the next step accumulates their product.
+          const int p = etid & 127;
+          const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
+          const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
+          for (int r = etid >> 7; r < P.rad_extra_rows; r += 2) {
+            float val = 0.0f;
+            if (r < px) val = pe_row(r, P.rad_multires, xs + 3 * p, -1);
+            else if (r < px + pv) val = pe_row(r - px, P.rad_multires_view, vs + 3 * p, -1);
+            else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
+            store_elem<kF16>(act, r, p, val);
+          }
         } else if (S.epi == EPI_RELU) {
           if (mo < S.n_mt) {
             const float b = a.bias[S.bias_off + F];
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-              uint32_t raw[16];
-              float v[16];
-              umma::tmem_ld16(taddr + 16 * c, raw);
+            const int nchunk = S.n_cols >> 4;
+            uint32_t raw[16], rawB[16];
+            float v[16];
+            umma::tmem_ld16(taddr, raw);
+            for (int c = 0; c < nchunk; c += 2) {
               umma::tmem_ld_wait();
+              umma::tmem_ld16(taddr + 16 * (c + 1), rawB);
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
               store_row16<kF16>(ra, 16 * c, v);
+              umma::tmem_ld_wait();
+              if (c + 2 < nchunk) umma::tmem_ld16(taddr + 16 * (c + 2), raw);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(rawB[j]) + b, 0.0f);
+              store_row16<kF16>(ra, 16 * (c + 1), v);
             }
           }
         } else if (S.epi == EPI_RGB) {
           if (mo == 0 && q == 0) {
-            uint32_t raw[32];
-            umma::tmem_ld32(tmem_tile, raw);
-            umma::tmem_ld_wait();
-            if (lane < 3 && a.rgb) {
-              const float b = a.bias[S.bias_off + lane];
+            const float b = lane < 3 ? a.bias[S.bias_off + lane] : 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < (S.n_cols >> 5); ++c) {
+              uint32_t raw[32];
+              umma::tmem_ld32(tmem_tile + 32 * c, raw);
+              umma::tmem_ld_wait();
+              if (lane < 3 && a.rgb) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int64_t gp = p0 + j;
-                if (gp < a.n) a.rgb[gp * 3 + lane] = sigmoid_fast(__uint_as_float(raw[j]) + b);
+                for (int j = 0; j < 32; ++j) {
+                  const int64_t gp = p0 + 32 * c + j;
+                  if (gp < a.n) a.rgb[gp * 3 + lane] = sigmoid_fast(__uint_as_float(raw[j]) + b);
+                }
               }
             }
           }
@@ -593,7 +656,7 @@ extern "C" int nr_mlp_umma_set_trace(void* buf) { g_trace = (long long*)buf; ret
 extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
                                    const float* bias, size_t bias_floats, const float* x, const float* view,
                                    int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
-                                   const float* normal_scale, void* stream) {
+                                   const float* normal_scale, void* feat_img, void* stream) {
   NR_CHECK_ARG(prog && image && bias && x, "nr_mlp_umma_forward: null pointer");
   NR_CHECK_ARG(n >= 0, "nr_mlp_umma_forward: n < 0");
   NR_CHECK_ARG(prog->n_steps >= 1 && prog->n_steps <= NR_UMMA_MAX_STEPS, "nr_mlp_umma_forward: n_steps=%d", prog->n_steps);
@@ -610,16 +673,31 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
     NR_CHECK_ARG(S.chunk_begin >= 0 && (size_t)(S.chunk_begin + nch) * kChunkBytes <= image_bytes,
                  "step %d: weight chunks [%d,%d) exceed the image", s, S.chunk_begin, S.chunk_begin + nch);
     NR_CHECK_ARG(S.bias_off >= 0 && (size_t)S.bias_off + S.n_mt * 128 <= bias_floats, "step %d: bias range", s);
-    NR_CHECK_ARG(S.epi >= EPI_HIDDEN && S.epi <= EPI_RGB, "step %d: epi=%d", s, S.epi);
+    NR_CHECK_ARG(S.epi >= EPI_HIDDEN && S.epi <= EPI_EXTRAS, "step %d: epi=%d", s, S.epi);
+    NR_CHECK_ARG(!S.accumulate || (s > 0 && prog->steps[s - 1].n_mt == S.n_mt && prog->steps[s - 1].n_cols == S.n_cols &&
+                                   prog->steps[s - 1].epi == EPI_EXTRAS),
+                 "step %d: accumulate needs a preceding EPI_EXTRAS step of the same shape", s);
+    NR_CHECK_ARG(S.epi != EPI_EXTRAS || (prog->input_mode == 1 && s + 1 < prog->n_steps && prog->steps[s + 1].accumulate &&
+                                         prog->steps[s + 1].k_steps * 16 == prog->rad_extra_rows),
+                 "step %d: EPI_EXTRAS needs input_mode 1 and a following accumulate step over the extra rows", s);
     if (S.epi == EPI_RELU || S.epi == EPI_RGB || (S.epi == EPI_FEAT && S.to_rad)) has_rad = true;
   }
-  NR_CHECK_ARG(prog->steps[0].k_steps * 16 >= (prog->multires < 0 ? 3 : 3 + 6 * prog->multires),
-               "nr_mlp_umma_forward: step 0 K does not cover the embedding");
+  if (prog->input_mode == 1) {
+    NR_CHECK_ARG(!prog->tangents && view && nabla && feat_img && prog->steps[0].k_steps == 16 && prog->steps[0].epi == EPI_EXTRAS,
+                 "nr_mlp_umma_forward: radiance-only programs need value tiles, view dirs, normals, the feature image and a "
+                 "K = 256 first step");
+    NR_CHECK_ARG(((uintptr_t)feat_img & 15) == 0, "nr_mlp_umma_forward: feat_img must be 16-byte aligned");
+  } else {
+    NR_CHECK_ARG(prog->input_mode == 0, "nr_mlp_umma_forward: input_mode=%d", prog->input_mode);
+    NR_CHECK_ARG(prog->steps[0].k_steps * 16 >= (prog->multires < 0 ? 3 : 3 + 6 * prog->multires),
+                 "nr_mlp_umma_forward: step 0 K does not cover the embedding");
+  }
   for (int s = 0; s < prog->n_steps; ++s)
     if (prog->steps[s].pe_fill)
       NR_CHECK_ARG((prog->multires < 0 ? 3 : 3 + 6 * prog->multires) <= kPeStashRows,
                    "nr_mlp_umma_forward: skip connections need an embedding of at most %d rows", kPeStashRows);
-  if (has_rad) NR_CHECK_ARG(prog->tangents && view, "nr_mlp_umma_forward: the radiance steps need tangent tiles and view dirs");
+  if (has_rad && prog->input_mode == 0)
+    NR_CHECK_ARG(prog->tangents && view, "nr_mlp_umma_forward: the radiance steps need tangent tiles and view dirs");
   if (n == 0) return NR_OK;
   int dev = 0, sms = 0;
   NR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -636,7 +714,7 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
   }
   DevProgram dp;
   dp.p = *prog;
-  KArgs ka{(const uint8_t*)image, bias, x, view, n, sdf, nabla, feat, feat_ld, rgb, normal_scale, g_trace};
+  KArgs ka{(const uint8_t*)image, bias, x, view, n, sdf, nabla, feat, feat_ld, rgb, normal_scale, (uint8_t*)feat_img, g_trace};
   if (prog->operand_f16) mlp_umma_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
   else mlp_umma_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
   NR_CHECK_LAUNCH("mlp_umma_kernel");

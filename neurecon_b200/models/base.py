@@ -17,6 +17,8 @@ import math
 import warnings
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -109,6 +111,8 @@ def _pack_layers(weights, biases, scales=None):
 
 
 _MAX_POINTS_PER_CALL = 1 << 18
+_SPLIT_POINTS = 1 << 21          # points per (geometry, radiance) launch pair of the tensor tier: 1 GiB feature image
+_FUSED_MODE = os.environ.get("NEURECON_B200_FUSED", "split")   # 'split' | 'fused' (single launch)
 
 
 class ImplicitSurface(nn.Module):
@@ -239,29 +243,44 @@ class ImplicitSurface(nn.Module):
 
     def _run_umma(self, x, mode, want_feat=False, radiance_net=None, view_dirs=None, want_sdf=True,
                   want_nablas=True, normal_scale=None):
-        """One launch of the fused tcgen05 kernel.  mode: 'sdf' | 'nablas' | 'fused'."""
+        """The fused tcgen05 kernel.  mode: 'sdf' | 'nablas' | 'fused' (one launch, radiance steps 32 columns wide) |
+        'split' (two launches per <= 2M points: SDF net + normals + feature image, then the radiance net on 128-point
+        tiles -- the radiance MMAs run 128 columns wide, 2.5x the rate of the 32-column ones)."""
         _lib.require_cuda(x, view_dirs)
         lib = _lib.get_lib()
         shape = x.shape[:-1]
         xf = _lib.f32c(x.detach().reshape(-1, 3))
         n, dev = xf.shape[0], xf.device
-        net = self._umma_net(radiance_net if mode == "fused" else None)
-        prog = net.program(mode, want_feat=want_feat)
+        with_rad = mode in ("fused", "split")
+        net = self._umma_net(radiance_net if with_rad else None)
         f = dict(dtype=torch.float32, device=dev)
         sdf = torch.empty(n, **f) if want_sdf else None
-        nabla = torch.empty(n, 3, **f) if (mode != "sdf" and want_nablas) else None
-        feat = torch.empty(n, net.feat_dim, **f) if (want_feat and mode != "fused") else None
-        rgb = torch.empty(n, 3, **f) if mode == "fused" else None
-        vf = None
-        if mode == "fused":
-            vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
-        with torch.cuda.device(dev):
+        nabla = torch.empty(n, 3, **f) if (mode != "sdf" and (want_nablas or mode == "split")) else None
+        feat = torch.empty(n, net.feat_dim, **f) if (want_feat and not with_rad) else None
+        rgb = torch.empty(n, 3, **f) if with_rad else None
+        vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3)) if with_rad else None
+
+        def launch(prog, i0, m, sdf_o, nabla_o, feat_o, rgb_o, img):
+            sl = lambda t: None if t is None else t[i0:i0 + m]
             _lib.check(lib.nr_mlp_umma_forward(
                 C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias), net.bias.numel(),
-                _lib.ptr(xf), _lib.ptr(vf), n, _lib.ptr(sdf), _lib.ptr(nabla), _lib.ptr(feat),
-                net.feat_dim, _lib.ptr(rgb), _lib.ptr(normal_scale), _lib.stream_ptr(dev)), "mlp_umma_forward")
+                _lib.ptr(xf[i0:i0 + m]), _lib.ptr(sl(vf)), m, _lib.ptr(sl(sdf_o)), _lib.ptr(sl(nabla_o)), _lib.ptr(sl(feat_o)),
+                net.feat_dim, _lib.ptr(sl(rgb_o)), _lib.ptr(normal_scale), _lib.ptr(img), _lib.stream_ptr(dev)),
+                "mlp_umma_forward")
+
+        with torch.cuda.device(dev):
+            if mode == "split":
+                p_geo, p_rad = net.program("nablas_img"), net.program("radiance")
+                step = _SPLIT_POINTS
+                img = _lib.workspace((min(n, step) + 127) // 128 * 65536, dev, slot=1)
+                for i0 in range(0, n, step):
+                    m = min(step, n - i0)
+                    launch(p_geo, i0, m, sdf, nabla, None, None, img)
+                    launch(p_rad, i0, m, None, nabla, None, rgb, img)
+            else:
+                launch(net.program(mode, want_feat=want_feat), 0, n, sdf, nabla, feat, rgb, None)
         rs = lambda t, *tail: None if t is None else t.reshape(*shape, *tail)
-        return rs(sdf), rs(nabla, 3), rs(feat, net.feat_dim), rs(rgb, 3)
+        return rs(sdf), rs(nabla if want_nablas else None, 3), rs(feat, net.feat_dim), rs(rgb, 3)
 
     # ---- forward -----------------------------------------------------------------------------
     def _needs_grad(self, x, has_grad):
@@ -420,14 +439,14 @@ def query_radiance(surface, radiance_net, x, view_dirs, chunk_normalize=False):
     first, then the (3-float) column norms, then the radiance with the scale applied inside the kernel."""
     if not chunk_normalize:
         if _lib.tensor_tier():
-            sdf, nabla, _, rgb = surface._run_umma(x, "fused", radiance_net=radiance_net, view_dirs=view_dirs)
+            sdf, nabla, _, rgb = surface._run_umma(x, _FUSED_MODE, radiance_net=radiance_net, view_dirs=view_dirs)
             return rgb, sdf, nabla
         sdf, nabla, feat = surface._run(x, want_nablas=True, want_feat=True)
         return radiance_net.forward(x, view_dirs, nabla, feat), sdf, nabla
     if _lib.tensor_tier():
         sdf, nabla, _, _ = surface._run_umma(x, "nablas")
         scale = (1.0 / nabla.reshape(-1, 3).norm(dim=0).clamp_min(1e-12)).contiguous()
-        _, _, _, rgb = surface._run_umma(x, "fused", radiance_net=radiance_net, view_dirs=view_dirs, want_sdf=False,
+        _, _, _, rgb = surface._run_umma(x, _FUSED_MODE, radiance_net=radiance_net, view_dirs=view_dirs, want_sdf=False,
                                          want_nablas=False, normal_scale=scale)
         return rgb, sdf, nabla
     sdf, nabla, feat = surface._run(x, want_nablas=True, want_feat=True)

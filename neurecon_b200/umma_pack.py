@@ -38,7 +38,7 @@ def pack_a_tiles(W, n_mtiles=None, k_pad=None, dtype=torch.bfloat16):
 # --------------------------------------------------------------------------------------------
 # Programs for the fused tcgen05 MLP kernel (csrc/mlp_umma.cu, include/neurecon_b200.h)
 # --------------------------------------------------------------------------------------------
-EPI_HIDDEN, EPI_SDF_OUT, EPI_FEAT, EPI_RELU, EPI_RGB = 0, 1, 2, 3, 4
+EPI_HIDDEN, EPI_SDF_OUT, EPI_FEAT, EPI_RELU, EPI_RGB, EPI_EXTRAS = 0, 1, 2, 3, 4, 5
 
 
 def _pe_dim(multires):
@@ -136,20 +136,37 @@ class UmmaNet:
         self.bias = torch.cat(biases, 0).contiguous()
 
     def program(self, mode, want_feat=False):
-        """mode: 'sdf' (128-point tiles), 'nablas' (32-point tangent tiles), 'fused' (+ radiance)."""
+        """mode: 'sdf' (128-point tiles), 'nablas' (32-point tangent tiles; want_feat: fp32 feature rows or, for
+        'nablas_img', the radiance operand image), 'radiance' (the radiance net alone on 128-point tiles fed by that
+        image: layer 0 = feature part, then the [PE(x)|PE(view)|normals] part accumulated onto it),
+        'fused' (everything in one launch, radiance steps 32 columns wide)."""
         from . import _lib
+        if mode == "radiance":
+            assert self.rad is not None
+            r0 = self.rad[0]
+            steps = [dict(r0, k_steps=16, epi=EPI_EXTRAS, n_cols=128),
+                     dict(r0, chunk_begin=r0["chunk_begin"] + r0["n_mt"] * 4, k_steps=self.rad_extra_rows // 16,
+                          accumulate=1, n_cols=128)]
+            steps += [dict(s, n_cols=128) for s in self.rad[1:]]
+            return self._finish(steps, tang=0, input_mode=1)
         tang = 0 if mode == "sdf" else 1
         steps = [dict(s, n_cols=128) for s in self.hidden]
         steps.append(dict(self.sdf_out, n_cols=128))
-        if mode == "fused":
+        if mode == "nablas_img":
+            steps.append(dict(self.feat, n_cols=32))
+        elif mode == "fused":
             assert self.rad is not None
             steps.append(dict(self.feat, n_cols=32, to_rad=1))
             steps += [dict(s, n_cols=32) for s in self.rad]
         elif want_feat:
             steps.append(dict(self.feat, n_cols=32 if tang else 128))
+        return self._finish(steps, tang)
+
+    def _finish(self, steps, tang, input_mode=0):
+        from . import _lib
         P = _lib.UmmaProgram()
         assert len(steps) <= _lib.NR_UMMA_MAX_STEPS
-        P.n_steps, P.tangents, P.multires = len(steps), tang, self.multires
+        P.n_steps, P.tangents, P.multires, P.input_mode = len(steps), tang, self.multires, input_mode
         P.rad_multires, P.rad_multires_view, P.rad_extra_rows = self.rad_multires, self.rad_multires_view, self.rad_extra_rows
         P.operand_f16 = 1 if self.operand == "fp16" else 0
         for i, s in enumerate(steps):

@@ -14,7 +14,7 @@ from neurecon_b200._lib import C  # noqa: E402
 from conftest import build_neus  # noqa: E402
 
 
-def run(net, prog, x, v, n, reps):
+def run(net, prog, x, v, n, reps, img=None):
     lib = _lib.get_lib()
     dev = x.device
     f = dict(dtype=torch.float32, device=dev)
@@ -23,7 +23,7 @@ def run(net, prog, x, v, n, reps):
     def go():
         _lib.check(lib.nr_mlp_umma_forward(C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias),
                                            net.bias.numel(), _lib.ptr(x), _lib.ptr(v), n, _lib.ptr(sdf), _lib.ptr(nab),
-                                           None, 256, _lib.ptr(rgb), None, _lib.stream_ptr(dev)), "umma")
+                                           None, 256, _lib.ptr(rgb), None, _lib.ptr(img), _lib.stream_ptr(dev)), "umma")
     for _ in range(2):
         go()
     torch.cuda.synchronize()
@@ -44,11 +44,13 @@ def main():
     x = (torch.rand(n, 3, device=dev) - 0.5) * 1.5
     v = torch.nn.functional.normalize(torch.randn(n, 3, device=dev), dim=-1)
     net = m.implicit_surface._umma_net(m.radiance_net)
-    for mode, mflop in (("sdf", 1.049 * 459008 / 524544), ("nablas", 1.967), ("fused", 1.967 + 0.543)):
+    img = torch.zeros((n + 127) // 128 * 65536, dtype=torch.uint8, device=dev)
+    for mode, mflop in (("sdf", 1.049 * 459008 / 524544), ("nablas", 1.967), ("fused", 1.967 + 0.543),
+                        ("nablas_img", 1.967 + 0.1316), ("radiance", 0.543 - 0.1316)):
         for flags in [int(f) for f in os.environ.get("NR_FLAGS", "0,2").split(",")]:
             prog = net.program(mode)
             prog.debug_flags = flags
-            ms = run(net, prog, x, v, n, reps)
+            ms = run(net, prog, x, v, n, reps, img if mode in ("nablas_img", "radiance") else None)
             print("mode=%-6s flags=%d  %8.3f ms  %7.1f Mpts/s  %6.1f algorithmic TFLOP/s" % (
                 mode, flags, ms, n / ms / 1e3, n * mflop * 1e6 / (ms * 1e-3) / 1e12), flush=True)
 

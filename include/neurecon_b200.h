@@ -395,6 +395,13 @@ int nr_selftest_umma(const void* a_image, const float* B, int32_t K, int32_t N, 
 int nr_bench_umma(int32_t N, int32_t n_mmas, int32_t store_warps, int32_t bulk_copies, const void* gsrc,
                   int32_t grid, long long* out, void* stream);
 
+/* Issue-rate probe (tools/probe_alu.py): cycles for iters x 8 independent ops per thread; op 0 ex2, 1 rcp,
+ * 2 cvt.f16x2.f32, 3 fma, 4 cvt.bf16x2.f32, 5 lg2.  cycles: [grid] int64. */
+int nr_probe_alu(int32_t op, int32_t threads, int32_t iters, int32_t grid, float* out, long long* cycles, void* stream);
+
+/* TMEM read-rate probe: `warps` warps x iters x 4 tcgen05.ld.32x32b.x16 (2 KB each); out: [grid] int64 cycles. */
+int nr_bench_ldtm(int32_t warps, int32_t iters, int32_t grid, long long* out, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,8 @@ namespace {
 #define NR_EXP_STAGES 4
 #endif
 constexpr int kStages = NR_EXP_STAGES;
+constexpr int kStagesLog2 = 2;
+static_assert(kStages == (1 << kStagesLog2), "the ring position arithmetic assumes a power-of-two ring");
 constexpr int kStashCopies = NR_EXP_STAGES > 4 ? 1 : 2;   // experiment only: >4 stages share one stash (wrong results)
 constexpr int kPeStashRows = 40;          // embedding rows kept for the skip layer (multires <= 6)
 constexpr uint32_t kChunkBytes = 16384;      // one A tile: 128 features x 64 k, bf16
@@ -37,6 +39,12 @@ constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilog
 constexpr int kEpiPerTile = 256;
 constexpr int kEpiWarpsPerTile = 8;
 constexpr int kEpiWarp0 = 4;
+#ifndef NR_SHARE_EPILOGUE
+#define NR_SHARE_EPILOGUE 0
+#endif
+// 1: the wide activation steps (EPI_HIDDEN, EPI_RELU) of a tile are drained by all 16 epilogue warps, each group
+// taking half of the points; 0: by the tile's own 8 warps.
+constexpr bool kShare = NR_SHARE_EPILOGUE != 0;
 
 enum : int32_t {
   EPI_HIDDEN = 0,   // softplus(beta=100) hidden layer (+ tangents), next operand in smem
@@ -64,34 +72,55 @@ struct SmemLayout {
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// softplus(beta=100) and its derivative sigmoid(100 z) with 2 MUFU ops.  B200 issues only 8 MUFU/clk/SM
-// (16 cycles per warp instruction per sub-partition), which makes the XU pipe the scarcest resource of
-// the epilogue:  ln(1 + e^t) = max(t, 0) + log1p(u),  u = e^{-|t|} in (0, 1];
-// log1p(u) = u * P5(u) (Chebyshev fit, |err| < 6.1e-6, i.e. < 6.1e-8 after the 1/100);
-// sigmoid(t) = r for t >= 0 and u * r otherwise, r = 1 / (1 + u).  The threshold-20 linear branch of
-// nn.Softplus needs no select: beyond it log1p(u) < 2.1e-9.
-__device__ __forceinline__ float log1p_poly(float u) {
-  float p = -0.02397957257926464f;
-  p = fmaf(p, u, 0.10150004923343658f);
-  p = fmaf(p, u, -0.2102936953306198f);
-  p = fmaf(p, u, 0.3252951502799988f);
-  p = fmaf(p, u, -0.49937260150909424f);
-  p = fmaf(p, u, 0.9999918341636658f);
-  return p * u;
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2): one issue slot for two lanes of math.  The epilogue is
+// bound by instruction issue (an epilogue warp issues ~0.3 instr/clk, ncu round 1), not by a math pipe, so the
+// activation is written on register pairs wherever the two values take the same path.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 splat2(float x) { return pk2(x, x); }
+
+// softplus(beta=100)(z) and its derivative sigmoid(100 z), z = acc + bias, for a pair of accumulators.
+//   t  = 100 z log2(e) = fma(acc, 144.27, bias * 144.27)          (b144 = splat(bias * 144.27))
+//   u  = 2^-|t| in (0, 1]                                          1 MUFU per value
+//   softplus = max(t, 0) ln2/100 + log1p(u)/100,  log1p(u)/100 = u (c0 + c1 u + c2 u^2 + c3 u^3): |err| < 7.1e-7
+//     absolute, a fifth of a half-ulp of the 16-bit operand it is rounded to; nn.Softplus's threshold-20 linear
+//     branch needs no select (beyond it log1p(u) < 2.1e-9)
+//   sigmoid = 1/2 + copysign(r - 1/2, t),  r = 1 / (1 + u) in [1/2, 1)   1 MUFU per value
+__device__ __forceinline__ void softplus_sig2(float a0, float a1, f32x2 b144, float& sp0, float& sp1, f32x2& sg) {
+  const f32x2 t2 = fma2(pk2(a0, a1), splat2(144.26950408889634f), b144);
+  float t0, t1;
+  upk2(t2, t0, t1);
+  const f32x2 u2 = pk2(ex2_approx(-fabsf(t0)), ex2_approx(-fabsf(t1)));
+  f32x2 p = fma2(u2, splat2(-0.05875718221068382e-2f), splat2(0.22568579018115997e-2f));
+  p = fma2(p, u2, splat2(-0.4713013470172882e-2f));
+  p = fma2(p, u2, splat2(0.9974489808082581e-2f));
+  const f32x2 q = mul2(p, u2);
+  const f32x2 sp2 = fma2(pk2(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), splat2(0.006931471805599453f), q);
+  upk2(sp2, sp0, sp1);
+  float d0, d1;
+  upk2(add2(u2, splat2(1.0f)), d0, d1);
+  float s0, s1;
+  upk2(add2(pk2(rcp_approx(d0), rcp_approx(d1)), splat2(-0.5f)), s0, s1);
+  s0 = __uint_as_float(__float_as_uint(s0) | (__float_as_uint(t0) & 0x80000000u));
+  s1 = __uint_as_float(__float_as_uint(s1) | (__float_as_uint(t1) & 0x80000000u));
+  sg = add2(pk2(s0, s1), splat2(0.5f));
 }
-__device__ __forceinline__ void softplus100_fast(float z, float& sp, float& sg) {
-  const float tl = z * 144.26950408889634f;      // 100 z log2(e)
-  const float u = ex2_approx(-fabsf(tl));
-  sp = fmaf(log1p_poly(u), 0.01f, fmaxf(z, 0.0f));
-  const float r = rcp_approx(1.0f + u);
-  sg = z >= 0.0f ? r : u * r;
-}
-__device__ __forceinline__ float softplus100_fast(float z) {
-  const float u = ex2_approx(-fabsf(z * 144.26950408889634f));
-  return fmaf(log1p_poly(u), 0.01f, fmaxf(z, 0.0f));
+__device__ __forceinline__ void softplus2(float a0, float a1, f32x2 b144, float& sp0, float& sp1) {
+  const f32x2 t2 = fma2(pk2(a0, a1), splat2(144.26950408889634f), b144);
+  float t0, t1;
+  upk2(t2, t0, t1);
+  const f32x2 u2 = pk2(ex2_approx(-fabsf(t0)), ex2_approx(-fabsf(t1)));
+  f32x2 p = fma2(u2, splat2(-0.05875718221068382e-2f), splat2(0.22568579018115997e-2f));
+  p = fma2(p, u2, splat2(-0.4713013470172882e-2f));
+  p = fma2(p, u2, splat2(0.9974489808082581e-2f));
+  const f32x2 q = mul2(p, u2);
+  upk2(fma2(pk2(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), splat2(0.006931471805599453f), q), sp0, sp1);
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
@@ -137,11 +166,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t
 // Row k of the operand as a 32-bit shared address + its swizzle key; a 16-byte chunk n8 of that row
 // then lives at row_addr + (n8 >> 3) * LBO + (((n8 & 7) ^ key) << 4)  (see umma::b_chunk_offset).
 struct RowAddr {
-  uint32_t base, key;
+  uint32_t base, xbase;   // xbase = base ^ (key << 4): bits 4..6 of base are zero (1024-byte aligned operand, 128-byte rows)
   __device__ __forceinline__ RowAddr(uint32_t act_s, int k)
-      : base(act_s + (uint32_t)((k >> 3) * 1024 + (k & 7) * 128)), key((uint32_t)(k & 7)) {}
-  __device__ __forceinline__ uint32_t chunk(int n8) const {
-    return base + (uint32_t)(n8 >> 3) * kLbo + ((((uint32_t)n8 & 7u) ^ key) << 4);
+      : base(act_s + (uint32_t)((k >> 3) * 1024 + (k & 7) * 128)), xbase(base ^ ((uint32_t)(k & 7) << 4)) {}
+  __device__ __forceinline__ uint32_t chunk(int n8) const {   // one LOP3 + an immediate offset for a compile-time n8
+    return (xbase ^ (((uint32_t)n8 & 7u) << 4)) + (uint32_t)(n8 >> 3) * kLbo;
   }
 };
 template <bool kF16>
@@ -176,11 +205,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // Epilogue -> MMA hand-off: every lane makes its generic-proxy smem writes visible to the async
 // proxy and orders its TMEM reads, then one lane per warp arrives (8 arrivals per tile).
-__device__ __forceinline__ void publish(uint64_t* bar, int debug_flags) {
+__device__ __forceinline__ void publish(uint64_t* bar, int debug_flags, uint32_t count = 1) {
   if (!(debug_flags & 32)) umma::fence_proxy_async_smem();
   umma::tc_fence_before();
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar);
+  if ((threadIdx.x & 31) == 0) umma::mbar_arrive_n(bar, count);
 }
 
 struct KArgs {
@@ -219,7 +248,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
   __shared__ uint32_t tmem_base_s;
 
   const nr_umma_program_t& P = prog.p;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so the role loops below keep their ring
+  // positions, barrier addresses and MMA descriptors in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tang = P.tangents;
   const bool rad_only = P.input_mode == 1;
   const int ppt = tang ? 32 : 128;                       // points per tile
@@ -229,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
-      umma::mbar_init(&in_ready[t], kEpiWarpsPerTile);
+      umma::mbar_init(&in_ready[t], kShare ? 2 * kEpiWarpsPerTile : kEpiWarpsPerTile);
       umma::mbar_init(&acc_ready[t], 2);
       umma::mbar_init(&feat_full[t], 1);
     }
@@ -246,15 +277,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 
   if (warp == 0) {
     // ===================== weight producer (warp-uniform loop, one elected lane copies) ==========
-    uint32_t stage = 0, phase = 0;
+    // Ring position = running chunk count: stage = cnt % kStages, phase parity = (cnt / kStages) & 1.
+    uint32_t cnt = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
       for (int s = 0; s < P.n_steps; ++s) {
         const int nch = P.steps[s].n_mt * (P.steps[s].k_steps >> 2);
         const uint8_t* src = a.image + (size_t)P.steps[s].chunk_begin * kChunkBytes;
         for (int t = 0; t < ntl; ++t) {
-          for (int c = 0; c < nch; ++c) {
-            umma::mbar_wait(&w_empty[stage], phase ^ 1);
+          for (int c = 0; c < nch; ++c, ++cnt) {
+            const uint32_t stage = cnt & (kStages - 1);
+            umma::mbar_wait(&w_empty[stage], ((cnt >> kStagesLog2) & 1u) ^ 1u);
             if (umma::elect_one()) {
               if (P.debug_flags & 1) {
                 umma::mbar_arrive(&w_full[stage]);
@@ -265,90 +298,94 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               }
             }
             __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1 || warp == 3) {
     // ===================== MMA issuers: warp 1 owns M-tile 0, warp 3 owns M-tile 1 =====================
-    // Two issuing threads because one cannot sustain an N=128 MMA every 64 cycles (measured ~110
-    // cycles of scalar/uniform work per MMA).  Different M-tiles are different accumulators, so the
-    // relative order of the two warps' MMAs is irrelevant.  Chunks are interleaved (k-chunk major,
-    // M-tile minor) in the ring: warp w consumes chunk kc*n_mt + w of every step.
-    const int my_mt = warp == 1 ? 0 : 1;
+    // Two issuing warps: the tensor pipe accepts an MMA only every 64 cycles (N = 128) with a queue about two deep
+    // (tools/umma_queue_depth.py), so whatever else the issuing thread does between MMAs (barrier probes, descriptor
+    // arithmetic, at a fifth of the issue slots of a sub-partition shared with four epilogue warps) must fit
+    // under the other warp's MMAs.  Different M-tiles are different accumulators, so the relative order of the two
+    // warps' MMAs is irrelevant.  Chunks are interleaved (k-chunk major, M-tile minor) in the ring: warp w consumes
+    // chunk kc*n_mt + w of every step.
+    const uint32_t my_mt = warp == 1 ? 0u : 1u;
     int tcnt = 0;
-    uint32_t stage = 0, phase = 0;     // ring position of the first chunk of the current (step, tile)
-    uint32_t in_par[2] = {0, 0};
+    uint32_t cnt = 0;                  // chunks consumed by the CTA before the current (step, tile)
+    uint32_t in_par = 0;               // bit t: parity of in_ready[t]
     const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
     const uint32_t ring_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::ring), 16);
-    auto advance = [&](uint32_t& st, uint32_t& ph, uint32_t n) {
-      st += n;
-      while (st >= (uint32_t)kStages) { st -= kStages; ph ^= 1; }
-    };
+    const uint32_t act_lo0 = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::act), kLbo);
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
       for (int s = 0; s < P.n_steps; ++s) {
         const uint32_t n_mt = P.steps[s].n_mt, nkc = P.steps[s].k_steps >> 2;
-        const bool acc0 = P.steps[s].accumulate != 0;
+        const uint32_t acc0 = P.steps[s].accumulate != 0 ? 1u : 0u;
         const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, P.steps[s].n_cols, 0, 1)
                                     : umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
         for (int t = 0; t < ntl; ++t) {
-          umma::mbar_wait(&in_ready[t], in_par[t]);
-          in_par[t] ^= 1;
+          umma::mbar_wait(&in_ready[t], (in_par >> t) & 1u);
+          in_par ^= 1u << t;
           umma::tc_fence_after();
           if (lane == 0) trace_ev(a.trace, my_mt, tcnt, 11, s * 2 + t, pair);
-          if ((uint32_t)my_mt < n_mt) {
-            const uint32_t act_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::act + t * kActBytes), kLbo);
-            const uint32_t d_addr = tmem_base + (uint32_t)(t * 256 + my_mt * 128);
-            uint32_t st = stage, ph = phase;
-            advance(st, ph, (uint32_t)my_mt);
-            uint32_t b_lo = act_lo;
-            for (uint32_t kc = 0; kc < nkc; ++kc) {
-              umma::mbar_wait(&w_full[st], ph);
+          if (my_mt < n_mt) {
+            const uint32_t d_addr = tmem_base + (uint32_t)t * 256u + my_mt * 128u;
+            uint32_t b_lo = act_lo0 + (uint32_t)t * (kActBytes >> 4);
+            uint32_t c = cnt + my_mt;
+#pragma unroll 1
+            for (uint32_t kc = 0; kc < nkc; ++kc, c += n_mt, b_lo += 512) {
+              const uint32_t st = c & (kStages - 1);
+              umma::mbar_wait(&w_full[st], (c >> kStagesLog2) & 1u);
               umma::tc_fence_after();
               const uint32_t a_lo = ring_lo + st * (kChunkBytes >> 4);
               if (umma::elect_one()) {
-                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, (kc > 0 || acc0) ? 1u : 0u);
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, (kc | acc0) ? 1u : 0u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
                 umma::mma_commit(&w_empty[st]);
               }
-              b_lo += 512;
-              advance(st, ph, n_mt);
+              __syncwarp();
             }
           }
           if (umma::elect_one()) umma::mma_commit(&acc_ready[t]);
+          __syncwarp();
           if (lane == 0) trace_ev(a.trace, my_mt, tcnt, 12, s * 2 + t, pair);
-          advance(stage, phase, n_mt * nkc);
+          cnt += n_mt * nkc;
         }
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue: 8 warps per tile, one warpgroup per M-tile =====================
+    // ===================== epilogue: 16 warps; group g = e >> 3 owns tile slot g =====================
+    // The owner group runs the tile's prologue and its narrow output steps.  With kShare the wide activation steps
+    // are drained by BOTH groups (owner: first half of the points, other group: second half): a step's activation is
+    // a latency chain (TMEM load -> MUFU -> pack -> st.shared) that two warps per sub-partition cannot hide, and
+    // halving it is what lets the other tile's MMA burst cover it.
     const int e = warp - kEpiWarp0;                 // 0..15
-    const int t = e >> 3;                           // tile slot 0 / 1
+    const int g = e >> 3;                           // group
     const int mo = (e >> 2) & 1;                    // M-tile this warpgroup owns
     const int q = warp & 3;                         // TMEM lane quarter (hardware: warp id % 4)
-    const int etid = (e & 7) * 32 + lane;           // 0..255 inside the tile's epilogue group
-    uint8_t* act = smem + SmemLayout::act + t * kActBytes;
-    float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
-    float* vs = (float*)(smem + SmemLayout::vs) + t * 384;
-    float* nabs = (float*)(smem + SmemLayout::nabs) + t * 384;
+    const int etid = (e & 7) * 32 + lane;           // 0..255 inside the group
     uint32_t feat_par = 0;
-    const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
-    uint32_t acc_par = 0;
+    uint32_t acc_par = 0;                           // bit t: parity of acc_ready[t]
     int tcnt = 0;
-    const bool tracer = (mo == 0 && q == 0 && lane == 0 && t == 0);
-    uint8_t* pes = smem + SmemLayout::pes + (kStashCopies > 1 ? t : 0) * (kPeStashRows * 256);   // embedding rows, linear [row][128 cols] 16-bit
+    const bool tracer = (mo == 0 && q == 0 && lane == 0 && g == 0);
     const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
     const bool no_st = P.debug_flags & 8;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int ntl = (2 * pair + 1 < n_tiles) ? 2 : 1;
+      if (!kShare && g >= ntl) continue;
+      if (g < ntl) {
+      const int t = g;
       const int64_t tile = 2 * pair + t;
-      if (tile >= n_tiles) continue;
       const int64_t p0 = tile * ppt;
+      uint8_t* act = smem + SmemLayout::act + t * kActBytes;
+      float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
+      float* vs = (float*)(smem + SmemLayout::vs) + t * 384;
+      float* nabs = (float*)(smem + SmemLayout::nabs) + t * 384;
+      uint8_t* pes = smem + SmemLayout::pes + (kStashCopies > 1 ? t : 0) * (kPeStashRows * 256);
 
       // ---- prologue: stage the points, evaluate the embedding into operand rows [0, k0) ----
       for (int i = etid; i < ppt * 3; i += kEpiPerTile) {
@@ -404,12 +441,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         for (int j = pe_dim + part; j < k0; j += 2) store_elem<kF16>(act, j, n, 0.f);
       }
       }
-      publish(&in_ready[t], P.debug_flags);
+      publish(&in_ready[t], P.debug_flags, kShare ? 2 : 1);
+      }
 
       for (int s = 0; s < P.n_steps; ++s) {
+       for (int t = kShare ? 0 : g; t < (kShare ? ntl : g + 1); ++t) {
         const nr_umma_step_t& S = P.steps[s];
-        umma::mbar_wait(&acc_ready[t], acc_par);
-        acc_par ^= 1;
+        const bool own = (t == g);
+        const int64_t tile = 2 * pair + t;
+        const int64_t p0 = tile * ppt;
+        uint8_t* act = smem + SmemLayout::act + t * kActBytes;
+        float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
+        float* vs = (float*)(smem + SmemLayout::vs) + t * 384;
+        float* nabs = (float*)(smem + SmemLayout::nabs) + t * 384;
+        uint8_t* pes = smem + SmemLayout::pes + (kStashCopies > 1 ? t : 0) * (kPeStashRows * 256);
+        const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
+#if defined(NR_ACC_SLEEP_NS)
+        umma::mbar_wait_backoff(&acc_ready[t], (acc_par >> t) & 1u, NR_ACC_SLEEP_NS, NR_ACC_POLL_NS);
+#else
+        umma::mbar_wait(&acc_ready[t], (acc_par >> t) & 1u);
+#endif
+        acc_par ^= 1u << t;
         umma::tc_fence_after();
         if (tracer) trace_ev(a.trace, 2, tcnt, 21, s * 2 + t, pair);
         const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
@@ -425,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             uint32_t raw[16];
             float v[16];
             if (P.debug_flags & 4) {
-              for (int c = 0; c < 8; ++c) {
+              for (int c = (kShare && !own) ? 4 : 0; c < ((kShare && own) ? 4 : 8); ++c) {
                 umma::tmem_ld16(taddr + 16 * c, raw);
                 umma::tmem_ld_wait();
                 if (__uint_as_float(raw[0]) == 123.456f) act[0] = 1;
@@ -434,75 +486,74 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               // columns: [0,32) values of 32 points, [32c, 32c+32) d/dx_c; two 16-point halves.  TMEM loads are
               // double-buffered: the load of chunk k+1 is in flight while chunk k is processed.
               uint32_t rawB[16];
-              float sg[16];
+              f32x2 sg[8];
               const int jpe = F - S.out_rows;
-              umma::tmem_ld16(taddr, raw);
-#pragma unroll 1
+              const f32x2 b144 = splat2(b * 144.26950408889634f);
+              auto tangent = [&](const uint32_t (&r)[16], int col0) {   // t' = sigmoid * (W t), 16 points of one component
+                if (!is_pe) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    upk2(mul2(pk2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), sg[j]), v[2 * j], v[2 * j + 1]);
+                  store_row16<kF16>(ra, col0, v, no_st);
+                } else {
+                  copy_row16(ra, pes, jpe, col0);
+                }
+              };
+              const int h0 = kShare ? (own ? 0 : 1) : 0, h1 = kShare ? h0 + 1 : 2;   // 16-point halves this warp drains
+              umma::tmem_ld16(taddr + 16 * h0, raw);
+#pragma unroll
               for (int h = 0; h < 2; ++h) {
+                if (h < h0 || h >= h1) continue;
                 umma::tmem_ld_wait();
                 umma::tmem_ld16(taddr + 32 + 16 * h, rawB);
                 if (!is_pe) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) softplus100_fast(__uint_as_float(raw[j]) + b, v[j], sg[j]);
+                  for (int j = 0; j < 8; ++j)
+                    softplus_sig2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]), b144, v[2 * j], v[2 * j + 1], sg[j]);
                   store_row16<kF16>(ra, 16 * h, v, no_st);
                 } else {
                   copy_row16(ra, pes, jpe, 16 * h);
                 }
                 umma::tmem_ld_wait();
                 umma::tmem_ld16(taddr + 64 + 16 * h, raw);
-                if (!is_pe) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rawB[j]) * sg[j];
-                  store_row16<kF16>(ra, 32 + 16 * h, v, no_st);
-                } else {
-                  copy_row16(ra, pes, jpe, 32 + 16 * h);
-                }
+                tangent(rawB, 32 + 16 * h);
                 umma::tmem_ld_wait();
                 umma::tmem_ld16(taddr + 96 + 16 * h, rawB);
-                if (!is_pe) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * sg[j];
-                  store_row16<kF16>(ra, 64 + 16 * h, v, no_st);
-                } else {
-                  copy_row16(ra, pes, jpe, 64 + 16 * h);
-                }
+                tangent(raw, 64 + 16 * h);
                 umma::tmem_ld_wait();
-                if (h == 0) umma::tmem_ld16(taddr + 16, raw);
-                if (!is_pe) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rawB[j]) * sg[j];
-                  store_row16<kF16>(ra, 96 + 16 * h, v, no_st);
-                } else {
-                  copy_row16(ra, pes, jpe, 96 + 16 * h);
-                }
+                if (h + 1 < h1) umma::tmem_ld16(taddr + 16 * (h + 1), raw);
+                tangent(rawB, 96 + 16 * h);
               }
             } else {
               uint32_t rawB[16];
               const int jpe = F - S.out_rows;
-              umma::tmem_ld16(taddr, raw);
-#pragma unroll 1
+              const f32x2 b144 = splat2(b * 144.26950408889634f);
+              auto values = [&](const uint32_t (&r)[16], int col0) {
+                if (!is_pe) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    softplus2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, v[2 * j], v[2 * j + 1]);
+                  store_row16<kF16>(ra, col0, v, no_st);
+                } else {
+                  copy_row16(ra, pes, jpe, col0);
+                }
+              };
+              const int c0 = kShare ? (own ? 0 : 4) : 0, c1 = kShare ? c0 + 4 : 8;   // 16-point chunks this warp drains
+              umma::tmem_ld16(taddr + 16 * c0, raw);
+#pragma unroll
               for (int c = 0; c < 8; c += 2) {
+                if (c < c0 || c >= c1) continue;
                 umma::tmem_ld_wait();
                 umma::tmem_ld16(taddr + 16 * (c + 1), rawB);
-                if (!is_pe) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(raw[j]) + b);
-                  store_row16<kF16>(ra, 16 * c, v, no_st);
-                } else {
-                  copy_row16(ra, pes, jpe, 16 * c);
-                }
+                values(raw, 16 * c);
                 umma::tmem_ld_wait();
-                if (c + 2 < 8) umma::tmem_ld16(taddr + 16 * (c + 2), raw);
-                if (!is_pe) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = softplus100_fast(__uint_as_float(rawB[j]) + b);
-                  store_row16<kF16>(ra, 16 * (c + 1), v, no_st);
-                } else {
-                  copy_row16(ra, pes, jpe, 16 * (c + 1));
-                }
+                if (c + 2 < c1) umma::tmem_ld16(taddr + 16 * (c + 2), raw);
+                values(rawB, 16 * (c + 1));
               }
             }
           }
+        } else if (!own && S.epi != EPI_RELU) {
+          // narrow output steps: the owner group alone
         } else if (S.epi == EPI_SDF_OUT) {
           // rows 0..31 of this M-tile all hold the sdf row: lane l keeps column l of each 32-column chunk
           if (mo == 0 && q == 0) {
@@ -599,11 +650,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
           if (mo < S.n_mt) {
             const float b = a.bias[S.bias_off + F];
 #pragma unroll 1
-            const int nchunk = S.n_cols >> 4;
+            const int nall = S.n_cols >> 4;              // 16-column chunks; split between the groups when >= 4
+            const bool split = kShare && nall >= 4;
+            const int cb = split ? (own ? 0 : nall >> 1) : 0, nchunk = split ? cb + (nall >> 1) : (own ? nall : 0);
             uint32_t raw[16], rawB[16];
             float v[16];
-            umma::tmem_ld16(taddr, raw);
-            for (int c = 0; c < nchunk; c += 2) {
+            if (cb < nchunk) umma::tmem_ld16(taddr + 16 * cb, raw);
+            for (int c = cb; c < nchunk; c += 2) {
               umma::tmem_ld_wait();
               umma::tmem_ld16(taddr + 16 * (c + 1), rawB);
 #pragma unroll
@@ -636,9 +689,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         }
         if (tracer) trace_ev(a.trace, 2, tcnt, 22, s * 2 + t, pair);
         if (s + 1 < P.n_steps) publish(&in_ready[t], P.debug_flags);
+       }
       }
       umma::tc_fence_before();
-      named_bar_sync(1 + t, kEpiPerTile);  // staging buffers and TMEM slot free before the next tile
+      if (kShare) named_bar_sync(3, 2 * kEpiPerTile);   // staging buffers and TMEM slots free before the next pair
+      else named_bar_sync(1 + g, kEpiPerTile);
     }
   }
 

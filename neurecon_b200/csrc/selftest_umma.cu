@@ -160,6 +160,36 @@ bench_umma_kernel(int N, int n_mmas, int store_warps, int bulk_copies, const uin
   if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
 }
 
+// TMEM read-rate probe: `warps` warps each issue `iters` x 4 tcgen05.ld.32x32b.x16 (2 KB per instruction) on their
+// lane quarter, waiting once per group of 4.  out[0] = cycles of warp 0.
+__global__ void __launch_bounds__(1024, 1) bench_ldtm_kernel(int iters, long long* __restrict__ out, float* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t taddr = tmem_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) & 3) * 128u;
+  uint32_t a0[16], a1[16], a2[16], a3[16];
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    umma::tmem_ld16(taddr, a0);
+    umma::tmem_ld16(taddr + 16, a1);
+    umma::tmem_ld16(taddr + 32, a2);
+    umma::tmem_ld16(taddr + 48, a3);
+    umma::tmem_ld_wait();
+    acc += __uint_as_float(a0[0] ^ a1[1] ^ a2[2] ^ a3[3]);
+  }
+  const long long t1 = clock64();
+  if (acc == 123.456f) sink[0] = acc;
+  if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base_s, 512);
+}
+
 }  // namespace
 
 extern "C" int nr_selftest_umma(const void* a_image, const float* B, int32_t K, int32_t N, float* D, int32_t variant,
@@ -184,5 +214,12 @@ extern "C" int nr_bench_umma(int32_t N, int32_t n_mmas, int32_t store_warps, int
   NR_CHECK_CUDA(cudaFuncSetAttribute(bench_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   bench_umma_kernel<<<grid, 640, smem, (cudaStream_t)stream>>>(N, n_mmas, store_warps, bulk_copies, (const uint8_t*)gsrc, out);
   NR_CHECK_LAUNCH("bench_umma_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_bench_ldtm(int32_t warps, int32_t iters, int32_t grid, long long* out, float* sink, void* stream) {
+  NR_CHECK_ARG(out && sink && warps >= 1 && warps <= 32 && iters > 0 && grid > 0, "nr_bench_ldtm: args");
+  bench_ldtm_kernel<<<grid, warps * 32, 0, (cudaStream_t)stream>>>(iters, out, sink);
+  NR_CHECK_LAUNCH("bench_ldtm_kernel");
   return NR_OK;
 }

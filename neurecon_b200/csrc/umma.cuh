@@ -44,10 +44,65 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU box.
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint elapses)
+// instead of returning after the short default limit -- a polling warp otherwise burns a quarter of the SM's
+// issue slots on TRYWAIT/BRA pairs (ncu, round 1).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU box.  Plain try_wait polling measured
+// fastest: parking the warp with a suspend-time hint (NR_WAIT_MODE 1) frees issue slots but wakes up later (+2.5 %
+// kernel time), see profiles/mlp_umma_r1_history.md.
+#ifndef NR_WAIT_MODE
+#define NR_WAIT_MODE 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if NR_WAIT_MODE == 1
+  if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 12); ++spin)
+    if (mbar_try_wait_hint(bar, parity, 1000000u)) return;
+#elif NR_WAIT_MODE == 2
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin)
+    if (mbar_test_wait(bar, parity)) return;
+#else
   for (uint32_t spin = 0; spin < (1u << 22); ++spin)
     if (mbar_try_wait(bar, parity)) return;
+#endif
+  printf("neurecon_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+
+// Wait with back-off for long, predictable waits (the epilogue's wait for the next accumulator): sleep `first_ns`
+// once, then poll with `poll_ns` naps, so the waiting warps stop competing for issue slots with the working ones.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t first_ns, uint32_t poll_ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (first_ns) asm volatile("nanosleep.u32 %0;" ::"r"(first_ns));
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (poll_ns) asm volatile("nanosleep.u32 %0;" ::"r"(poll_ns));
+  }
   printf("neurecon_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
   __trap();
 }

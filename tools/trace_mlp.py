@@ -34,7 +34,7 @@ ev.sort()
 # keep the last launch only (clock restarts are monotonic; take events of the final 'pair' sequence)
 t0 = ev[0][0]
 names = {10: "mma: wait in_ready", 11: "mma: got in_ready", 12: "mma: issued+commit", 20: "epi: wait acc", 21: "epi: got acc",
-         22: "epi: math done", 23: "epi: published"}
+         22: "epi: math done", 23: "epi: published", 31: "epi: values half done", 33: "epi: tangents 0,1 half done"}
 print("mode", mode, "flags", flags, "ms", ms)
-for c, r, e, st, pair in ev[:140]:
+for c, r, e, st, pair in ev[:int(os.environ.get('NR_TRACE_N', '140'))]:
     print("%9d  region %d  pair %d  step %2d tile %d  %s" % (c - t0, r, pair, st // 2, st % 2, names.get(e, e)))

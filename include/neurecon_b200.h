@@ -391,7 +391,8 @@ int nr_selftest_umma(const void* a_image, const float* B, int32_t K, int32_t N, 
 
 /* Tensor-pipe rate probe (tools/bench_umma_rate.py): cycles for n_mmas back-to-back 128 x N x 16 MMAs on operands
  * resident in shared memory, optionally under concurrent shared-memory store / bulk-copy traffic.
- * gsrc: >= 1 MiB of device memory (copy source); out: [grid][2] int64 = {issue..completion, issue loop} cycles. */
+ * gsrc: >= 1 MiB of device memory (copy source); out: [3][grid] int64: [2*b], [2*b+1] = {issue..completion, issue loop}
+ * cycles of block b, [2*grid + b] = 512-byte stores retired by one store warp.  n_mmas < 0: no MMAs, window of -n_mmas cycles. */
 int nr_bench_umma(int32_t N, int32_t n_mmas, int32_t store_warps, int32_t bulk_copies, const void* gsrc,
                   int32_t grid, long long* out, void* stream);
 

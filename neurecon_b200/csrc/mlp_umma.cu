@@ -77,6 +77,9 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 // ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2): one issue slot for two lanes of math.  The epilogue is
 // bound by instruction issue (an epilogue warp issues ~0.3 instr/clk, ncu round 1), not by a math pipe, so the
 // activation is written on register pairs wherever the two values take the same path.
+#ifndef NR_SIGMOID_NEWTON
+#define NR_SIGMOID_NEWTON 0
+#endif
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
@@ -103,10 +106,22 @@ __device__ __forceinline__ void softplus_sig2(float a0, float a1, f32x2 b144, fl
   const f32x2 q = mul2(p, u2);
   const f32x2 sp2 = fma2(pk2(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), splat2(0.006931471805599453f), q);
   upk2(sp2, sp0, sp1);
+  float s0, s1;
+#if NR_SIGMOID_NEWTON
+  // r = 1/(1+u) on the FMA pipe (the XU pipe issues a warp instruction only every 8 cycles per sub-partition and the
+  // ex2 above already fills half of it): cubic minimax guess (2.5e-3) + one Newton step -> 6.4e-6 relative
+  f32x2 r = fma2(u2, splat2(-0.23549793660640717f), splat2(0.6862913966178894f));
+  r = fma2(r, u2, splat2(-0.950793445110321f));
+  r = fma2(r, u2, splat2(0.9987373352050781f));
+  const f32x2 d = add2(u2, splat2(1.0f));
+  const f32x2 e = fma2(d, r ^ 0x8000000080000000ull, splat2(1.0f));   // 1 - d r
+  r = fma2(r, e, r);
+  upk2(add2(r, splat2(-0.5f)), s0, s1);
+#else
   float d0, d1;
   upk2(add2(u2, splat2(1.0f)), d0, d1);
-  float s0, s1;
   upk2(add2(pk2(rcp_approx(d0), rcp_approx(d1)), splat2(-0.5f)), s0, s1);
+#endif
   s0 = __uint_as_float(__float_as_uint(s0) | (__float_as_uint(t0) & 0x80000000u));
   s1 = __uint_as_float(__float_as_uint(s1) | (__float_as_uint(t1) & 0x80000000u));
   sg = add2(pk2(s0, s1), splat2(0.5f));
@@ -508,8 +523,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                 umma::tmem_ld16(taddr + 32 + 16 * h, rawB);
                 if (!is_pe) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    softplus_sig2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]), b144, v[2 * j], v[2 * j + 1], sg[j]);
+                  for (int j = 0; j < 8; ++j) {
+                    if (P.debug_flags & 16) {   // profiling: no activation math, loads + packs + stores only
+                      v[2 * j] = __uint_as_float(raw[2 * j]); v[2 * j + 1] = __uint_as_float(raw[2 * j + 1]); sg[j] = b144;
+                    } else {
+                      softplus_sig2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]), b144, v[2 * j], v[2 * j + 1], sg[j]);
+                    }
+                  }
                   store_row16<kF16>(ra, 16 * h, v, no_st);
                 } else {
                   copy_row16(ra, pes, jpe, 16 * h);

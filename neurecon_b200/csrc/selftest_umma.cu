@@ -116,6 +116,7 @@ bench_umma_kernel(int N, int n_mmas, int store_warps, int bulk_copies, const uin
     const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
     const uint32_t a_lo0 = umma::smem_desc_lo(umma::smem_u32(sA), 16), b_lo0 = umma::smem_desc_lo(umma::smem_u32(sB), 32768);
     const long long t0 = clock64();
+    if (n_mmas < 0) { while (clock64() - t0 < -(long long)n_mmas) {} }   // no MMAs: just hold the window open
     for (int i = 0; i < n_mmas; i += 4) {
       const uint32_t kc = (uint32_t)(i >> 2) & 3u;
       const uint32_t a_lo = a_lo0 + kc * 1024, b_lo = b_lo0 + kc * 512;
@@ -154,6 +155,7 @@ bench_umma_kernel(int N, int n_mmas, int store_warps, int bulk_copies, const uin
         asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + r * 512), "r"(it) : "memory");
       ++it;
     }
+    if (lane == 0 && warp == 4) out[2 * gridDim.x + blockIdx.x] = (long long)it * 4;   // 512-byte stores of one warp
   }
   umma::tc_fence_before();
   __syncthreads();
@@ -209,7 +211,7 @@ extern "C" int nr_bench_umma(int32_t N, int32_t n_mmas, int32_t store_warps, int
                              int32_t grid, long long* out, void* stream) {
   NR_CHECK_ARG(out && gsrc, "nr_bench_umma: null pointer");
   NR_CHECK_ARG(N == 32 || N == 64 || N == 128 || N == 256, "nr_bench_umma: N");
-  NR_CHECK_ARG(n_mmas >= 4 && n_mmas % 4 == 0 && store_warps >= 0 && store_warps <= 16 && grid >= 1, "nr_bench_umma: sizes");
+  NR_CHECK_ARG((n_mmas < 0 || (n_mmas >= 4 && n_mmas % 4 == 0)) && store_warps >= 0 && store_warps <= 16 && grid >= 1, "nr_bench_umma: sizes");
   const size_t smem = 1024 + 65536 + 131072 + 16384;
   NR_CHECK_CUDA(cudaFuncSetAttribute(bench_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   bench_umma_kernel<<<grid, 640, smem, (cudaStream_t)stream>>>(N, n_mmas, store_warps, bulk_copies, (const uint8_t*)gsrc, out);

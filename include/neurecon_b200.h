@@ -389,6 +389,12 @@ int nr_mlp_umma_set_trace(void* buf);
 int nr_selftest_umma(const void* a_image, const float* B, int32_t K, int32_t N, float* D,
                      int32_t variant, void* stream);
 
+/* CTA-pair variant: D[256,N] = A[256,K] B[K,N] with tcgen05.mma.cta_group::2 on a 2-CTA cluster (a_image: fp16 tiles
+ * ordered k-chunk major / M-tile minor; N = 64, 128 or 256).  variant bit 0: each CTA writes its peer's half of B
+ * through distributed shared memory. */
+int nr_selftest_umma2(const void* a_image, const float* B, int32_t K, int32_t N, float* D,
+                      int32_t variant, void* stream);
+
 /* Tensor-pipe rate probe (tools/bench_umma_rate.py): cycles for n_mmas back-to-back 128 x N x 16 MMAs on operands
  * resident in shared memory, optionally under concurrent shared-memory store / bulk-copy traffic.
  * gsrc: >= 1 MiB of device memory (copy source); out: [3][grid] int64: [2*b], [2*b+1] = {issue..completion, issue loop}

@@ -102,6 +102,7 @@ _SIGNATURES = {
     "nr_bench_ldtm": (C.c_int, [_I32, _I32, _I32, _P, _P, _P]),
     "nr_probe_alu": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P]),
     "nr_bench_umma": (C.c_int, [_I32, _I32, _I32, _I32, _P, _I32, _P, _P]),
+    "nr_selftest_umma2": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
     "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
     "nr_neus_composite": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -82,6 +82,88 @@ selftest_umma_kernel(const uint8_t* __restrict__ a_image, const float* __restric
   if (warp == 0) umma::tmem_dealloc(tmem_base, 128);
 }
 
+// CTA-pair self-test: D[256, N] = A[256, K] * B[K, N] with tcgen05.mma.cta_group::2.  CTA r of the pair holds rows
+// [128r, 128r+128) of A and of D and columns [N/2 r, N/2 (r+1)) of B.  variant bit 0: each CTA writes the PEER's half
+// of B through distributed shared memory (the path the fused MLP's epilogue would use for its activations).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+selftest_umma2_kernel(const uint8_t* __restrict__ a_image, const float* __restrict__ B, int K, int N,
+                      float* __restrict__ D, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int kchunks = (K + 63) / 64;
+  const int nh = N / 2;                      // columns of B per CTA
+  uint8_t* sA = smem;                       // kchunks x 16 KB: this CTA's 128 rows
+  uint8_t* sB = smem + kchunks * 16384;     // K x nh, MN-major SW128
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = umma::cluster_ctarank();
+  const uint32_t lbo_b = (uint32_t)((K + 7) / 8) * 1024;
+
+  if (tid == 0) {
+    umma::mbar_init(&bar_load, 1);
+    umma::mbar_init(&bar_mma, 1);
+    umma::fence_barrier_init();
+  }
+  __syncthreads();
+  umma::cluster_sync_all();                 // barriers of both CTAs initialised before anything can arrive on them
+  if (warp == 0) {
+    umma::tmem_alloc2(&tmem_base_s, 256);
+    umma::tmem_relinquish2();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (tid == 0) {
+    umma::mbar_arrive_expect_tx(&bar_load, (uint32_t)kchunks * 16384u);
+    // image layout: [k-chunk][M-tile 0 | M-tile 1] 16 KB each
+    for (int c = 0; c < kchunks; ++c)
+      umma::bulk_g2s(sA + c * 16384, a_image + ((size_t)c * 2 + rank) * 16384, 16384u, &bar_load);
+  }
+  // B: this CTA fills the half of `dst` = itself, or its peer (variant & 1) -- with the columns that half owns
+  const uint32_t dst = (variant & 1) ? (rank ^ 1u) : rank;
+  const uint32_t sB_dst = umma::map_to_cta(umma::smem_u32(sB), dst);
+  for (int k = tid; k < K; k += 128) {
+    for (int n8 = 0; n8 < nh / 8; ++n8) {
+      const float* src = B + (size_t)k * N + dst * nh + n8 * 8;
+      umma::st_cluster_v4(sB_dst + umma::b_chunk_offset(k, n8, lbo_b), umma::pack_f16(src[0], src[1]), umma::pack_f16(src[2], src[3]),
+                          umma::pack_f16(src[4], src[5]), umma::pack_f16(src[6], src[7]));
+    }
+  }
+  umma::mbar_wait(&bar_load, 0);
+  umma::fence_proxy_async_smem();
+  __syncthreads();
+  umma::cluster_sync_all();                 // both halves of A and B in place and visible
+
+  if (rank == 0 && tid == 0) {
+    umma::tc_fence_after();
+    const uint32_t idesc = umma::make_idesc_f16(256, N, 0, 1);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t a_addr = umma::smem_u32(sA) + (ks >> 2) * 16384 + (ks & 3) * 32;
+      const uint32_t b_addr = umma::smem_u32(sB) + ks * 2048;
+      umma::mma2_f16_ss(tmem_base, umma::make_smem_desc(a_addr, 16, 1024), umma::make_smem_desc(b_addr, lbo_b, 1024), idesc,
+                        ks > 0 ? 1u : 0u);
+    }
+    umma::mma2_commit_mc(&bar_mma, 3);
+  }
+  __syncwarp();
+  umma::mbar_wait(&bar_mma, 0);
+  umma::tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    umma::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    umma::tmem_ld_wait();
+    const int row = (int)rank * 128 + warp * 32 + (tid & 31);
+    for (int j = 0; j < 32; ++j) D[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync_all();
+  if (warp == 0) umma::tmem_dealloc2(tmem_base, 256);
+}
+
 // Tensor-pipe rate probe: one lane issues `n_mmas` back-to-back M=128 x N x 16 MMAs on operands resident in
 // shared memory (K = 256 cycled), optionally while `store_warps` other warps hammer shared memory with 16-byte
 // stores and/or a producer keeps 16 KB bulk copies in flight -- the traffic mix of the fused MLP kernel.
@@ -223,5 +305,18 @@ extern "C" int nr_bench_ldtm(int32_t warps, int32_t iters, int32_t grid, long lo
   NR_CHECK_ARG(out && sink && warps >= 1 && warps <= 32 && iters > 0 && grid > 0, "nr_bench_ldtm: args");
   bench_ldtm_kernel<<<grid, warps * 32, 0, (cudaStream_t)stream>>>(iters, out, sink);
   NR_CHECK_LAUNCH("bench_ldtm_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_selftest_umma2(const void* a_image, const float* B, int32_t K, int32_t N, float* D, int32_t variant,
+                                 void* stream) {
+  NR_CHECK_ARG(a_image && B && D, "nr_selftest_umma2: null pointer");
+  NR_CHECK_ARG(K >= 16 && K <= 256 && K % 16 == 0, "nr_selftest_umma2: K must be a multiple of 16 in [16,256]");
+  NR_CHECK_ARG(N == 64 || N == 128 || N == 256, "nr_selftest_umma2: N must be 64, 128 or 256");
+  const int kchunks = (K + 63) / 64;
+  const size_t smem = 1024 + (size_t)kchunks * 16384 + (size_t)((K + 7) / 8) * 1024 * ((N / 2 + 63) / 64);
+  NR_CHECK_CUDA(cudaFuncSetAttribute(selftest_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  selftest_umma2_kernel<<<2, 128, smem, (cudaStream_t)stream>>>((const uint8_t*)a_image, B, K, N, D, variant);
+  NR_CHECK_LAUNCH("selftest_umma2_kernel");
   return NR_OK;
 }

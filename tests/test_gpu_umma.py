@@ -29,3 +29,24 @@ def test_umma_gemm_matches_bf16_matmul(K, N):
     if not err < 1e-5:
         alts = {v: _run(K, N, v) for v in (1, 2, 3)}
         pytest.fail("production encoding err=%g; variants: %s" % (err, alts))
+
+
+def _run2(K, N, variant=0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(256, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    img = umma_pack.pack_a_tiles(A.to(DEV), dtype=torch.float16)     # k-chunk major, M-tile minor
+    D = torch.full((256, N), float("nan"), device=DEV)
+    Bd = B.to(DEV).contiguous()
+    lib = _lib.get_lib()
+    _lib.check(lib.nr_selftest_umma2(_lib.ptr(img), _lib.ptr(Bd), K, N, _lib.ptr(D), variant, _lib.stream_ptr()), "selftest2")
+    torch.cuda.synchronize()
+    want = A.to(torch.float16).double() @ B.to(torch.float16).double()
+    return ((D.double().cpu() - want).abs().max() / want.abs().max()).item()
+
+
+@pytest.mark.parametrize("K,N,variant", [(64, 128, 0), (256, 256, 0), (256, 256, 1), (128, 64, 1), (256, 128, 1)])
+def test_umma_cta_pair_gemm(K, N, variant):
+    """tcgen05.mma.cta_group::2 on a 2-CTA cluster: M = 256 split over the pair, B halves local (variant 0) or written
+    into the peer's shared memory through DSMEM (variant 1)."""
+    assert _run2(K, N, variant) < 1e-5

@@ -377,6 +377,13 @@ int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t
                         int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
                         const float* normal_scale, void* feat_img, void* stream);
 
+/* The same network on CTA pairs (tcgen05.mma.cta_group::2, 2-CTA clusters): programs made of EPI_HIDDEN,
+ * EPI_SDF_OUT and EPI_FEAT (to_rad = 0) steps whose weight chunks all come as M-tile pairs (n_mt = 2; the sdf row
+ * replicated into both M-tiles).  Halves the shared-memory traffic per SM of nr_mlp_umma_forward; same outputs. */
+int nr_mlp_umma2_forward(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
+                         const float* bias, size_t bias_floats, const float* x, int64_t n, float* sdf,
+                         float* nabla, float* feat, int64_t feat_ld, void* feat_img, void* stream);
+
 /* profiling hook (tools/trace_mlp.py): device buffer [3][2048][4] int64 receiving clock64 stamps of the
  * MMA <-> epilogue hand-offs of CTA 0; NULL disables. */
 int nr_mlp_umma_set_trace(void* buf);

@@ -94,7 +94,7 @@ selftest_umma2_kernel(const uint8_t* __restrict__ a_image, const float* __restri
   const int nh = N / 2;                      // columns of B per CTA
   uint8_t* sA = smem;                       // kchunks x 16 KB: this CTA's 128 rows
   uint8_t* sB = smem + kchunks * 16384;     // K x nh, MN-major SW128
-  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint64_t bar_load, bar_mma, bar_ready;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t rank = umma::cluster_ctarank();
@@ -103,6 +103,7 @@ selftest_umma2_kernel(const uint8_t* __restrict__ a_image, const float* __restri
   if (tid == 0) {
     umma::mbar_init(&bar_load, 1);
     umma::mbar_init(&bar_mma, 1);
+    umma::mbar_init(&bar_ready, 8);           // 4 warps x 2 CTAs
     umma::fence_barrier_init();
   }
   __syncthreads();
@@ -133,9 +134,18 @@ selftest_umma2_kernel(const uint8_t* __restrict__ a_image, const float* __restri
     }
   }
   umma::mbar_wait(&bar_load, 0);
-  umma::fence_proxy_async_smem();
-  __syncthreads();
-  umma::cluster_sync_all();                 // both halves of A and B in place and visible
+  if (variant & 2) {
+    // the fused kernel's hand-off: every warp of both CTAs arrives (release.cluster) on the LEADER's barrier after a
+    // full async-proxy fence; the issuing thread acquires at cluster scope
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+    if ((tid & 31) == 0) umma::mbar_arrive_cluster(umma::map_to_cta(umma::smem_u32(&bar_ready), 0));
+    if (rank == 0 && tid == 0) umma::mbar_wait_cluster(&bar_ready, 0);
+  } else {
+    umma::fence_proxy_async_smem();
+    __syncthreads();
+    umma::cluster_sync_all();                 // both halves of A and B in place and visible
+  }
 
   if (rank == 0 && tid == 0) {
     umma::tc_fence_after();

@@ -246,10 +246,21 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag = 0) {
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 22); ++spin)
     if (mbar_try_wait_cluster(bar, parity)) return;
-  printf("neurecon_b200: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  if ((threadIdx.x & 31) == 0)
+    printf("neurecon_b200: cluster mbarrier wait %d timed out (block %d warp %d)\n", tag, blockIdx.x, threadIdx.x >> 5);
+  __trap();
+}
+// mbar_wait with a tag in the time-out message (the pair kernel has many distinct waits)
+__device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+  if ((threadIdx.x & 31) == 0)
+    printf("neurecon_b200: mbarrier wait %d timed out (block %d warp %d)\n", tag, blockIdx.x, threadIdx.x >> 5);
   __trap();
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {   // one warp of EACH CTA of the pair

@@ -113,6 +113,9 @@ def _pack_layers(weights, biases, scales=None):
 _MAX_POINTS_PER_CALL = 1 << 18
 _SPLIT_POINTS = 1 << 21          # points per (geometry, radiance) launch pair of the tensor tier: 1 GiB feature image
 _FUSED_MODE = os.environ.get("NEURECON_B200_FUSED", "split")   # 'split' | 'fused' (single launch)
+# SDF net on CTA pairs (tcgen05.mma.cta_group::2, csrc/mlp_umma2.cu): numerically identical, but measured slower on
+# B200 (DSMEM activation exchange at ~20 B/clk/SM, weight round trip through a relay) -- opt-in until that is fixed
+_PAIR_KERNEL = os.environ.get("NEURECON_B200_PAIR", "0") != "0"
 
 
 class ImplicitSurface(nn.Module):
@@ -260,6 +263,15 @@ class ImplicitSurface(nn.Module):
         rgb = torch.empty(n, 3, **f) if with_rad else None
         vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3)) if with_rad else None
 
+        pair = _PAIR_KERNEL and net.pair_ok()
+
+        def launch_pair(prog, i0, m, sdf_o, nabla_o, feat_o, img):
+            sl = lambda t: None if t is None else t[i0:i0 + m]
+            _lib.check(lib.nr_mlp_umma2_forward(
+                C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias), net.bias.numel(),
+                _lib.ptr(xf[i0:i0 + m]), m, _lib.ptr(sl(sdf_o)), _lib.ptr(sl(nabla_o)), _lib.ptr(sl(feat_o)),
+                net.feat_dim, _lib.ptr(img), _lib.stream_ptr(dev)), "mlp_umma2_forward")
+
         def launch(prog, i0, m, sdf_o, nabla_o, feat_o, rgb_o, img):
             sl = lambda t: None if t is None else t[i0:i0 + m]
             _lib.check(lib.nr_mlp_umma_forward(
@@ -270,13 +282,18 @@ class ImplicitSurface(nn.Module):
 
         with torch.cuda.device(dev):
             if mode == "split":
-                p_geo, p_rad = net.program("nablas_img"), net.program("radiance")
+                p_geo, p_rad = net.program("nablas_img", pair=pair), net.program("radiance")
                 step = _SPLIT_POINTS
                 img = _lib.workspace((min(n, step) + 127) // 128 * 65536, dev, slot=1)
                 for i0 in range(0, n, step):
                     m = min(step, n - i0)
-                    launch(p_geo, i0, m, sdf, nabla, None, None, img)
+                    if pair:
+                        launch_pair(p_geo, i0, m, sdf, nabla, None, img)
+                    else:
+                        launch(p_geo, i0, m, sdf, nabla, None, None, img)
                     launch(p_rad, i0, m, None, nabla, None, rgb, img)
+            elif pair and mode in ("sdf", "nablas"):
+                launch_pair(net.program(mode, want_feat=want_feat, pair=True), 0, n, sdf, nabla, feat, None)
             else:
                 launch(net.program(mode, want_feat=want_feat), 0, n, sdf, nabla, feat, rgb, None)
         rs = lambda t, *tail: None if t is None else t.reshape(*shape, *tail)

@@ -95,6 +95,16 @@ class UmmaNet:
         c0, b0 = add(Wl[0:1].expand(32, in_d), bl[0:1].expand(32), k_steps, 1)
         self.sdf_out = dict(chunk_begin=c0, n_mt=1, k_steps=k_steps, epi=EPI_SDF_OUT, bias_off=b0, out_rows=1,
                             pe_fill=0, to_rad=0)
+        # CTA-pair kernel: the replicated sdf row in BOTH M-tiles, so each CTA of a pair finds it in its own TMEM lanes
+        rep = torch.zeros(256, in_d, dtype=Wl.dtype, device=dev)
+        rep[0:32] = Wl[0:1]
+        rep[128:160] = Wl[0:1]
+        brep = torch.zeros(256, dtype=bl.dtype, device=dev)
+        brep[0:32] = bl[0]
+        brep[128:160] = bl[0]
+        c0, b0 = add(rep, brep, k_steps, 2)
+        self.sdf_out2 = dict(chunk_begin=c0, n_mt=2, k_steps=k_steps, epi=EPI_SDF_OUT, bias_off=b0, out_rows=1,
+                             pe_fill=0, to_rad=0)
         self.feat_dim = Wl.shape[0] - 1
         if self.feat_dim > 0:
             if self.feat_dim > 256:
@@ -135,7 +145,11 @@ class UmmaNet:
         self.image = torch.cat(chunks, 0).contiguous()
         self.bias = torch.cat(biases, 0).contiguous()
 
-    def program(self, mode, want_feat=False):
+    def pair_ok(self):
+        """The CTA-pair kernel needs every step as an M-tile pair (hidden width > 128) and the feature, if any, too."""
+        return all(h["n_mt"] == 2 for h in self.hidden) and (self.feat_dim == 0 or self.feat["n_mt"] == 2)
+
+    def program(self, mode, want_feat=False, pair=False):
         """mode: 'sdf' (128-point tiles), 'nablas' (32-point tangent tiles; want_feat: fp32 feature rows or, for
         'nablas_img', the radiance operand image), 'radiance' (the radiance net alone on 128-point tiles fed by that
         image: layer 0 = feature part, then the [PE(x)|PE(view)|normals] part accumulated onto it),
@@ -151,7 +165,7 @@ class UmmaNet:
             return self._finish(steps, tang=0, input_mode=1)
         tang = 0 if mode == "sdf" else 1
         steps = [dict(s, n_cols=128) for s in self.hidden]
-        steps.append(dict(self.sdf_out, n_cols=128))
+        steps.append(dict(self.sdf_out2 if pair else self.sdf_out, n_cols=128))
         if mode == "nablas_img":
             steps.append(dict(self.feat, n_cols=32))
         elif mode == "fused":

@@ -90,3 +90,27 @@ def test_bf16_large_batch_matches_small_batches():
         a = m.implicit_surface.forward_with_nablas(x)
         b = m.implicit_surface.forward_with_nablas(x[:64 * 300])
     assert torch.equal(a[0][:64 * 300], b[0]) and torch.equal(a[1][:64 * 300], b[1])
+
+
+@pytest.mark.parametrize("n", [1, 31, 64, 129, 5000])
+def test_pair_kernel_matches_single_cta_kernel(n):
+    """The cta_group::2 kernel (CTA pairs, DSMEM activation exchange) against the one-CTA kernel: same operands, same
+    accumulation order -> same numbers (to the last bits of the fp32 accumulators), for every ragged size."""
+    from neurecon_b200.models import base
+    from conftest import build_neus
+    m = build_neus(seed=1, device=DEV)
+    x = (torch.rand(n, 3, device=DEV) - 0.5) * 1.6
+    old = base._PAIR_KERNEL
+    try:
+        outs = {}
+        for pair in (False, True):
+            base._PAIR_KERNEL = pair
+            with torch.no_grad():
+                sdf0 = m.implicit_surface.forward(x)
+                sdf, nab, feat = m.implicit_surface.forward_with_nablas(x)
+            outs[pair] = (sdf0, sdf, nab, feat)
+        for a_, b_ in zip(outs[False], outs[True]):
+            assert torch.isfinite(b_).all()
+            assert rel_err(b_, a_) < 2e-6, rel_err(b_, a_)
+    finally:
+        base._PAIR_KERNEL = old

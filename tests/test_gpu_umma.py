@@ -45,8 +45,9 @@ def _run2(K, N, variant=0, seed=0):
     return ((D.double().cpu() - want).abs().max() / want.abs().max()).item()
 
 
-@pytest.mark.parametrize("K,N,variant", [(64, 128, 0), (256, 256, 0), (256, 256, 1), (128, 64, 1), (256, 128, 1)])
+@pytest.mark.parametrize("K,N,variant", [(64, 128, 0), (256, 256, 0), (256, 256, 1), (128, 64, 1), (256, 128, 1), (256, 256, 3), (64, 128, 2)])
 def test_umma_cta_pair_gemm(K, N, variant):
     """tcgen05.mma.cta_group::2 on a 2-CTA cluster: M = 256 split over the pair, B halves local (variant 0) or written
-    into the peer's shared memory through DSMEM (variant 1)."""
+    into the peer's shared memory through DSMEM (variant bit 0); hand-off by cluster barrier or (variant bit 1) by
+    release.cluster arrivals of all warps on the leader's mbarrier, as in the fused pair kernel."""
     assert _run2(K, N, variant) < 1e-5

@@ -347,7 +347,8 @@ typedef struct {
   int32_t bias_off;    /* offset of n_mt*128 fp32 biases in the bias table */
   int32_t out_rows;    /* valid output features */
   int32_t pe_fill;     /* 1: rows [out_rows, out_rows+pe_dim) of the next operand are the embedding (skip) */
-  int32_t to_rad;      /* EPI_FEAT: also build the radiance operand [feat | PE(x) | PE(view) | normals] */
+  int32_t to_rad;      /* EPI_FEAT: also build the radiance operand [feat | PE(x) | PE(view) | normals];
+                          EPI_EXTRAS: which rows to write: 0 = the radiance extras, 1 = PE(x), 2 = PE(view) */
   int32_t accumulate;  /* 1: the step's MMAs add onto the previous step's accumulators (split-K over two operands) */
 } nr_umma_step_t;
 
@@ -361,7 +362,10 @@ typedef struct {
   int32_t operand_f16;       /* 1: fp16 operands (image packed as fp16), 0: bf16; fp32 accumulation either way */
   int32_t debug_flags;       /* profiling only (results invalid): 1 = no weight copies, 2 = no epilogue math/stores */
   int32_t input_mode;        /* 0: points -> embedding -> SDF net; 1: radiance net alone on 128-point tiles, its operand
-                                rows [0,256) bulk-copied from the feature image a previous launch wrote (feat_img) */
+                                rows [0,256) bulk-copied from the feature image a previous launch wrote (feat_img);
+                                2: NeRF++ background net on 128-point tiles: x = [n, input_dim] points, operand rows
+                                [0, K0) = PE(x) (multires), view dirs embedded with rad_multires_view */
+  int32_t input_dim;         /* components of a point (3; 4 for the NeRF++ inverted-sphere parametrisation) */
   nr_umma_step_t steps[NR_UMMA_MAX_STEPS];
 } nr_umma_program_t;
 

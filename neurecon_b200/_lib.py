@@ -50,7 +50,7 @@ class UmmaStep(C.Structure):
 
 class UmmaProgram(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_steps", "tangents", "multires", "rad_multires", "rad_multires_view",
-                                         "rad_extra_rows", "operand_f16", "debug_flags", "input_mode")] + [("steps", UmmaStep * NR_UMMA_MAX_STEPS)]
+                                         "rad_extra_rows", "operand_f16", "debug_flags", "input_mode", "input_dim")] + [("steps", UmmaStep * NR_UMMA_MAX_STEPS)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t

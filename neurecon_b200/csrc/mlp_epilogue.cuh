@@ -17,7 +17,9 @@ enum : int32_t {
   EPI_FEAT = 2,     // geometry feature: to global and/or radiance operand rows [0,256) + extras
   EPI_RELU = 3,     // radiance hidden layer
   EPI_RGB = 4,      // sigmoid, rows 0..2 to global
-  EPI_EXTRAS = 5,   // radiance-only mode: no accumulator read; operand rows [0, extras) <- [PE(x)|PE(view)|normals|0]
+  EPI_EXTRAS = 5,   // no accumulator read: operand rows [0, K of the next step) <- the second operand of a split-K layer
+                    // (to_rad 0: [PE(x)|PE(view)|normals|0] of the radiance net, 1: PE(x), 2: PE(view)); next step accumulates
+  EPI_LINEAR = 6,   // bias only (NeRF++ feature_linear), next operand in smem
 };
 
 struct DevProgram {
@@ -107,6 +109,17 @@ __device__ __forceinline__ float pe_row(int j, int multires, const float* x3, in
   if (comp_t < 0) return r < 3 ? s : c;
   if (comp_t != comp) return 0.0f;
   return r < 3 ? f * c : -f * s;
+}
+
+// Row j of Embedder.forward(x) for a `dim`-component input (models/base.py:53-61): [x, sin(2^0 x), cos(2^0 x), ...]
+__device__ __forceinline__ float pe_row_nd(int j, int multires, const float* x, int dim) {
+  if (j < dim) return x[j];
+  if (multires < 0) return 0.0f;
+  const int q = (j - dim) / (2 * dim), r = (j - dim) % (2 * dim);
+  if (q >= multires) return 0.0f;
+  float s, c;
+  __sincosf(x[r % dim] * (float)(1 << q), &s, &c);
+  return r < dim ? s : c;
 }
 
 template <bool kF16>

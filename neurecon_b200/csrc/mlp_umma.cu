@@ -45,8 +45,8 @@ struct SmemLayout {
   // offsets from the 1024-aligned base
   static constexpr uint32_t act = 0;                                 // 2 x 64 KB
   static constexpr uint32_t ring = 2 * kActBytes;                    // kStages x 16 KB
-  static constexpr uint32_t xs = ring + kStages * kChunkBytes;       // 2 x 128 x 3 floats
-  static constexpr uint32_t vs = xs + 2 * 384 * 4;                   // 2 x 128 x 3 floats (view dirs)
+  static constexpr uint32_t xs = ring + kStages * kChunkBytes;       // 2 x 128 x (3 | 4) floats
+  static constexpr uint32_t vs = xs + 2 * 512 * 4;                   // 2 x 128 x 3 floats (view dirs)
   static constexpr uint32_t nabs = vs + 2 * 384 * 4;                 // 2 x 128 x 3 floats (normal stash)
   static constexpr uint32_t pes = nabs + 2 * 384 * 4;                // 2 x 40 rows x 256 B: embedding stash (skip)
   static constexpr uint32_t bars = pes + kStashCopies * kPeStashRows * 256;     // mbarriers
@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tang = P.tangents;
   const bool rad_only = P.input_mode == 1;
+  const bool nerf = P.input_mode == 2;
+  const int xdim = nerf ? P.input_dim : 3;
   const int ppt = tang ? 32 : 128;                       // points per tile
   const int64_t n_tiles = (a.n + ppt - 1) / ppt;
   const int64_t n_pairs = (n_tiles + 1) / 2;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
       const int64_t tile = 2 * pair + t;
       const int64_t p0 = tile * ppt;
       uint8_t* act = smem + SmemLayout::act + t * kActBytes;
-      float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
+      float* xs = (float*)(smem + SmemLayout::xs) + t * 512;
       float* vs = (float*)(smem + SmemLayout::vs) + t * 384;
       float* nabs = (float*)(smem + SmemLayout::nabs) + t * 384;
       uint8_t* pes = smem + SmemLayout::pes + (kStashCopies > 1 ? t : 0) * (kPeStashRows * 256);
@@ -225,9 +227,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
       // ---- prologue: stage the points, evaluate the embedding into operand rows [0, k0) ----
       for (int i = etid; i < ppt * 3; i += kEpiPerTile) {
         const int64_t gi = p0 * 3 + i;
-        xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
-        if (a.view && (rad_only || i < 96)) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
+        if (!nerf) xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
+        if (a.view && (rad_only || nerf || i < 96)) vs[i] = gi < a.n * 3 ? a.view[gi] : 0.0f;
         if (rad_only) nabs[i] = gi < a.n * 3 ? a.nabla[gi] * (a.normal_scale ? a.normal_scale[i % 3] : 1.0f) : 0.0f;
+      }
+      if (nerf) {
+        for (int i = etid; i < ppt * xdim; i += kEpiPerTile) {
+          const int64_t gi = p0 * xdim + i;
+          xs[i] = gi < a.n * xdim ? a.x[gi] : 0.0f;
+        }
       }
       if (rad_only) {
         // operand rows [0,256) = this tile's 64 KB block of the feature image, four 16 KB bulk copies
@@ -240,6 +248,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         umma::mbar_wait(&feat_full[t], feat_par);
         feat_par ^= 1;
         named_bar_sync(1 + t, kEpiPerTile);
+      } else if (nerf) {
+        // NeRF++: operand rows [0, K0) = PE(x) of the tile's 128 points (x has xdim components), zero padded
+        named_bar_sync(1 + t, kEpiPerTile);
+        const int p = etid & 127, k0 = P.steps[0].k_steps * 16;
+        const int npe = P.multires < 0 ? xdim : xdim * (1 + 2 * P.multires);
+        for (int r = etid >> 7; r < k0; r += 2) store_elem<kF16>(act, r, p, r < npe ? pe_row_nd(r, P.multires, xs + xdim * p, xdim) : 0.0f);
       } else {
       named_bar_sync(1 + t, kEpiPerTile);
       {
@@ -286,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         const int64_t tile = 2 * pair + t;
         const int64_t p0 = tile * ppt;
         uint8_t* act = smem + SmemLayout::act + t * kActBytes;
-        float* xs = (float*)(smem + SmemLayout::xs) + t * 384;
+        float* xs = (float*)(smem + SmemLayout::xs) + t * 512;
         float* vs = (float*)(smem + SmemLayout::vs) + t * 384;
         float* nabs = (float*)(smem + SmemLayout::nabs) + t * 384;
         uint8_t* pes = smem + SmemLayout::pes + (kStashCopies > 1 ? t : 0) * (kPeStashRows * 256);
@@ -392,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               }
             }
           }
-        } else if (!own && S.epi != EPI_RELU) {
+        } else if (!own && S.epi != EPI_RELU && S.epi != EPI_LINEAR) {
           // narrow output steps: the owner group alone
         } else if (S.epi == EPI_SDF_OUT) {
           // rows 0..31 of this M-tile all hold the sdf row: lane l keeps column l of each 32-column chunk
@@ -474,19 +488,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             }
           }
         } else if (S.epi == EPI_EXTRAS) {
-          // radiance-only mode, after the feature part of layer 0: the feature rows are dead, rows [0, extras) become
-          // [PE(x) | PE(view) | normals | 0-pad] of the tile's 128 points; the next step accumulates their product.
-          const int p = etid & 127;
-          const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
-          const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
-          for (int r = etid >> 7; r < P.rad_extra_rows; r += 2) {
-            float val = 0.0f;
-            if (r < px) val = pe_row(r, P.rad_multires, xs + 3 * p, -1);
-            else if (r < px + pv) val = pe_row(r - px, P.rad_multires_view, vs + 3 * p, -1);
-            else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
-            store_elem<kF16>(act, r, p, val);
+          // split-K layer, after its first part: the rows that part read are dead; rows [0, K of the next step) become the
+          // second operand, whose product the next step accumulates onto the same TMEM columns.
+          const int p = etid & 127, pad = P.steps[s + 1].k_steps * 16;
+          if (S.to_rad == 0) {       // radiance net: [PE(x) | PE(view) | normals | 0-pad]
+            const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
+            const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
+            for (int r = etid >> 7; r < pad; r += 2) {
+              float val = 0.0f;
+              if (r < px) val = pe_row(r, P.rad_multires, xs + 3 * p, -1);
+              else if (r < px + pv) val = pe_row(r - px, P.rad_multires_view, vs + 3 * p, -1);
+              else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
+              store_elem<kF16>(act, r, p, val);
+            }
+          } else if (S.to_rad == 1) {   // PE(x) again (skip connection cat([PE(x), h]))
+            const int npe = P.multires < 0 ? xdim : xdim * (1 + 2 * P.multires);
+            for (int r = etid >> 7; r < pad; r += 2)
+              store_elem<kF16>(act, r, p, r < npe ? pe_row_nd(r, P.multires, xs + xdim * p, xdim) : 0.0f);
+          } else {                      // PE(view) (cat([feature, PE(view)]))
+            const int npe = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
+            for (int r = etid >> 7; r < pad; r += 2)
+              store_elem<kF16>(act, r, p, r < npe ? pe_row_nd(r, P.rad_multires_view, vs + 3 * p, 3) : 0.0f);
           }
-        } else if (S.epi == EPI_RELU) {
+        } else if (S.epi == EPI_RELU || S.epi == EPI_LINEAR) {
+          const float lo = S.epi == EPI_RELU ? 0.0f : -INFINITY;
           if (mo < S.n_mt) {
             const float b = a.bias[S.bias_off + F];
 #pragma unroll 1
@@ -500,12 +525,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               umma::tmem_ld_wait();
               umma::tmem_ld16(taddr + 16 * (c + 1), rawB);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, 0.0f);
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + b, lo);
               store_row16<kF16>(ra, 16 * c, v);
               umma::tmem_ld_wait();
               if (c + 2 < nchunk) umma::tmem_ld16(taddr + 16 * (c + 2), raw);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(rawB[j]) + b, 0.0f);
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(rawB[j]) + b, lo);
               store_row16<kF16>(ra, 16 * (c + 1), v);
             }
           }
@@ -568,20 +593,25 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
     NR_CHECK_ARG(S.chunk_begin >= 0 && (size_t)(S.chunk_begin + nch) * kChunkBytes <= image_bytes,
                  "step %d: weight chunks [%d,%d) exceed the image", s, S.chunk_begin, S.chunk_begin + nch);
     NR_CHECK_ARG(S.bias_off >= 0 && (size_t)S.bias_off + S.n_mt * 128 <= bias_floats, "step %d: bias range", s);
-    NR_CHECK_ARG(S.epi >= EPI_HIDDEN && S.epi <= EPI_EXTRAS, "step %d: epi=%d", s, S.epi);
+    NR_CHECK_ARG(S.epi >= EPI_HIDDEN && S.epi <= EPI_LINEAR, "step %d: epi=%d", s, S.epi);
     NR_CHECK_ARG(!S.accumulate || (s > 0 && prog->steps[s - 1].n_mt == S.n_mt && prog->steps[s - 1].n_cols == S.n_cols &&
                                    prog->steps[s - 1].epi == EPI_EXTRAS),
                  "step %d: accumulate needs a preceding EPI_EXTRAS step of the same shape", s);
-    NR_CHECK_ARG(S.epi != EPI_EXTRAS || (prog->input_mode == 1 && s + 1 < prog->n_steps && prog->steps[s + 1].accumulate &&
-                                         prog->steps[s + 1].k_steps * 16 == prog->rad_extra_rows),
-                 "step %d: EPI_EXTRAS needs input_mode 1 and a following accumulate step over the extra rows", s);
-    if (S.epi == EPI_RELU || S.epi == EPI_RGB || (S.epi == EPI_FEAT && S.to_rad)) has_rad = true;
+    NR_CHECK_ARG(S.epi != EPI_EXTRAS || (prog->input_mode >= 1 && s + 1 < prog->n_steps && prog->steps[s + 1].accumulate &&
+                                         S.to_rad >= 0 && S.to_rad <= 2 && (S.to_rad == 0) == (prog->input_mode == 1)),
+                 "step %d: EPI_EXTRAS needs a value-tile program and a following accumulate step", s);
+    if (prog->input_mode != 2 && (S.epi == EPI_RELU || S.epi == EPI_RGB || (S.epi == EPI_FEAT && S.to_rad))) has_rad = true;
   }
   if (prog->input_mode == 1) {
     NR_CHECK_ARG(!prog->tangents && view && nabla && feat_img && prog->steps[0].k_steps == 16 && prog->steps[0].epi == EPI_EXTRAS,
                  "nr_mlp_umma_forward: radiance-only programs need value tiles, view dirs, normals, the feature image and a "
                  "K = 256 first step");
     NR_CHECK_ARG(((uintptr_t)feat_img & 15) == 0, "nr_mlp_umma_forward: feat_img must be 16-byte aligned");
+  } else if (prog->input_mode == 2) {
+    NR_CHECK_ARG(!prog->tangents && view && prog->input_dim >= 1 && prog->input_dim <= 4,
+                 "nr_mlp_umma_forward: NeRF++ programs need value tiles, view dirs and 1..4 input components");
+    NR_CHECK_ARG(prog->steps[0].k_steps * 16 >= prog->input_dim * (prog->multires < 0 ? 1 : 1 + 2 * prog->multires),
+                 "nr_mlp_umma_forward: step 0 K does not cover the embedding");
   } else {
     NR_CHECK_ARG(prog->input_mode == 0, "nr_mlp_umma_forward: input_mode=%d", prog->input_mode);
     NR_CHECK_ARG(prog->steps[0].k_steps * 16 >= (prog->multires < 0 ? 3 : 3 + 6 * prog->multires),

@@ -33,6 +33,16 @@ def _descriptor(module):
     return c["desc"]
 
 
+def _umma_net(module):
+    from ..umma_pack import UmmaNerfNet
+    key = (_param_key(module), _lib.get_precision())
+    c = module._cache
+    if c.get("umma_key") != key:
+        c["umma_net"] = UmmaNerfNet(module, operand=_lib.get_precision())
+        c["umma_key"] = key
+    return c["umma_net"]
+
+
 def nerf_forward(module, input_pts, input_views):
     """NeRF.forward(input_pts [..., 4], input_views [..., 3]) -> (sigma [...], rgb [..., 3])."""
     if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
@@ -43,9 +53,19 @@ def nerf_forward(module, input_pts, input_views):
     xf = _lib.f32c(input_pts.detach().reshape(-1, module.input_dim))
     vf = _lib.f32c(input_views.detach().expand(*shape, 3).reshape(-1, 3))
     n, dev = xf.shape[0], xf.device
-    desc = _descriptor(module)
     sigma = torch.empty(n, dtype=torch.float32, device=dev)
     rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    if _lib.tensor_tier() and n > 0:
+        # tensor tier: the whole net in one launch of the fused tcgen05 kernel (csrc/mlp_umma.cu, input_mode 2)
+        net = _umma_net(module)
+        prog = net.program()
+        with torch.cuda.device(dev):
+            _lib.check(lib.nr_mlp_umma_forward(
+                C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias), net.bias.numel(),
+                _lib.ptr(xf), _lib.ptr(vf), n, _lib.ptr(sigma), None, None, 0, _lib.ptr(rgb), None, None,
+                _lib.stream_ptr(dev)), "mlp_umma_forward (NeRF++)")
+        return sigma.reshape(shape), rgb.reshape(*shape, 3)
+    desc = _descriptor(module)
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
         for i0 in range(0, n, _MAX_POINTS_PER_CALL):

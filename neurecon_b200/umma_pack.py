@@ -187,3 +187,87 @@ class UmmaNet:
             for k, v in s.items():
                 setattr(P.steps[i], k, int(v))
         return P
+
+
+EPI_LINEAR = 6
+
+
+class UmmaNerfNet:
+    """16-bit weight image + bias table + program of the NeRF++ background net (models/base.py:395-453, the
+    ``use_view_dirs=True`` form) for the fused tcgen05 kernel, 128-point value tiles (input_mode 2).
+
+    Layers whose input is a concatenation run as split-K pairs of steps over two operands that live in the same rows of
+    the shared-memory buffer one after the other: ``pts_linears[s+1](cat([PE(x), h]))`` = W[:, npe:] h (then the rows
+    are refilled with PE(x)) + W[:, :npe] PE(x); ``views_linears[0](cat([feature, PE(view)]))`` likewise."""
+
+    def __init__(self, module, operand="fp16"):
+        dev = module.alpha_linear.weight.device
+        self.operand = operand
+        op_dtype = torch.float16 if operand == "fp16" else torch.bfloat16
+        if not module.use_view_dirs:
+            raise NotImplementedError("tensor tier: NeRF needs use_view_dirs=True")
+        W, D = module.W, module.D
+        if W != 256 or len(module.skips) > 1:
+            raise NotImplementedError("tensor tier: NeRF++ net must be 256 wide with at most one skip")
+        self.multires, self.multires_view, self.input_dim = module.multires, module.multires_view, module.input_dim
+        npe = self.input_dim * (1 if self.multires < 0 else 1 + 2 * self.multires)
+        npv = 3 if self.multires_view < 0 else 3 + 6 * self.multires_view
+        if npe > 256 or npv > 256:
+            raise NotImplementedError("tensor tier: embedding wider than 256")
+        chunks, biases, steps = [], [], []
+        self._n_chunks = self._n_bias = 0
+
+        def add(Wm, b, epi, n_mt=None, **kw):
+            out_d, in_d = Wm.shape
+            k_steps = (in_d + 63) // 64 * 4
+            n_mt = (out_d + 127) // 128 if n_mt is None else n_mt
+            img = pack_a_tiles(Wm, n_mtiles=n_mt, k_pad=k_steps * 16, dtype=op_dtype)
+            bt = torch.zeros(n_mt * 128, dtype=torch.float32, device=dev)
+            if b is not None:
+                bt[: b.numel()] = b.float()
+            steps.append(dict(chunk_begin=self._n_chunks, n_mt=n_mt, k_steps=k_steps, n_cols=128, epi=epi,
+                              bias_off=self._n_bias, out_rows=out_d, pe_fill=0, to_rad=0, accumulate=0, **kw))
+            chunks.append(img)
+            biases.append(bt)
+            self._n_chunks += img.shape[0]
+            self._n_bias += bt.numel()
+
+        lin = [(l.weight.detach().float(), l.bias.detach().float()) for l in module.pts_linears]
+        for i in range(D):
+            Wi, bi = lin[i]
+            if i > 0 and (i - 1) in module.skips:      # input = cat([PE(x), h])  (base.py:436)
+                add(Wi[:, npe:], None, EPI_EXTRAS)
+                steps[-1]["to_rad"] = 1
+                add(Wi[:, :npe], bi, EPI_RELU)
+                steps[-1]["accumulate"] = 1
+            else:
+                add(Wi, bi, EPI_RELU)
+        if (D - 1) in module.skips:
+            raise NotImplementedError("tensor tier: skip after the last NeRF++ layer")
+        a = module.alpha_linear
+        add(a.weight.detach().float().expand(32, W), a.bias.detach().float().expand(32), EPI_SDF_OUT, n_mt=1)
+        f = module.feature_linear
+        add(f.weight.detach().float(), f.bias.detach().float(), EPI_LINEAR)
+        v = module.views_linears[0]
+        Wv, bv = v.weight.detach().float(), v.bias.detach().float()
+        add(Wv[:, :W], None, EPI_EXTRAS)               # cat([feature, PE(view)])  (base.py:441)
+        steps[-1]["to_rad"] = 2
+        add(Wv[:, W:], bv, EPI_RELU)
+        steps[-1]["accumulate"] = 1
+        r = module.rgb_linear
+        add(r.weight.detach().float(), r.bias.detach().float(), EPI_RGB)
+        self.steps = steps
+        self.image = torch.cat(chunks, 0).contiguous()
+        self.bias = torch.cat(biases, 0).contiguous()
+
+    def program(self):
+        from . import _lib
+        P = _lib.UmmaProgram()
+        assert len(self.steps) <= _lib.NR_UMMA_MAX_STEPS
+        P.n_steps, P.tangents, P.multires, P.input_mode, P.input_dim = len(self.steps), 0, self.multires, 2, self.input_dim
+        P.rad_multires, P.rad_multires_view, P.rad_extra_rows = -1, self.multires_view, 0
+        P.operand_f16 = 1 if self.operand == "fp16" else 0
+        for i, s in enumerate(self.steps):
+            for k, v in s.items():
+                setattr(P.steps[i], k, int(v))
+        return P

@@ -114,3 +114,25 @@ def test_pair_kernel_matches_single_cta_kernel(n):
             assert rel_err(b_, a_) < 2e-6, rel_err(b_, a_)
     finally:
         base._PAIR_KERNEL = old
+
+
+def test_nerfpp_net_tensor_tier_vs_fp32():
+    """NeRF++ background MLP (base.py:395-453) as one launch of the fused kernel (split-K skip / view layers) against
+    the fp32 tier, on inverted-sphere inputs; ragged sizes."""
+    from neurecon_b200.models.base import NeRF
+    torch.manual_seed(0)
+    m = NeRF(D=8, W=256, input_ch=4, input_ch_view=3, multires=10, multires_view=4, skips=[4], use_view_dirs=True).to(DEV)
+    for n in (1, 129, 3000):
+        d = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+        x = torch.cat([d, torch.rand(n, 1, device=DEV)], -1)
+        v = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+        out = {}
+        for tier in ("fp32", "fp16", "bf16"):
+            neurecon_b200.set_precision(tier)
+            with torch.no_grad():
+                out[tier] = m(x, v)
+        neurecon_b200.set_precision("fp16")
+        for tier, tol in (("fp16", 5e-3), ("bf16", 4e-2)):
+            for a_, b_ in zip(out[tier], out["fp32"]):
+                assert a_.shape == b_.shape and torch.isfinite(a_).all()
+                assert rel_err(a_, b_) < tol, (tier, n, rel_err(a_, b_))

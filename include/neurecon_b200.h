@@ -324,6 +324,28 @@ int nr_sphere_trace_step(const float* val, const float* rays_o, const float* dir
                          float* d, uint8_t* mask, float* pts, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * After the path in a training step: losses, gradient norm, Adam -- no host syncs.
+ * ------------------------------------------------------------------------------------------ */
+/* NeuS Trainer.forward losses (neus.py:443-478) and the gradients of their sum:
+ *   loss_img  = mean |rgb - target|            (no masks), or  sum(|.| * m) / (sum(m) + 1e-10) with m = target_mask
+ *               [& mask_ignore] (with_mask) or m = mask_ignore;
+ *   loss_eik  = w_eikonal * mean((|nablas| - 1)^2) over [R,P];
+ *   loss_mask = w_mask * mean BCE(clamp(mask_volume, 1e-3, 1-1e-3), target_mask)     (iff target_mask != NULL).
+ * rgb/target_rgb [R,3], nablas [R,P,3], mask_volume [R], target_mask / mask_ignore [R] bytes or NULL.
+ * sums4: 4 floats of scratch; losses4 = {loss_img, loss_eikonal, loss_mask, total} on the device;
+ * g_rgb [R,3], g_nablas [R,P,3], g_mask_volume [R] = d total / d input. */
+int nr_neus_loss(const float* rgb, const float* target_rgb, const float* nablas, const float* mask_volume,
+                 const uint8_t* target_mask, const uint8_t* mask_ignore, int64_t R, int64_t P, float w_eikonal,
+                 float w_mask, float* sums4, float* losses4, float* g_rgb, float* g_nablas, float* g_mask_volume,
+                 void* stream);
+/* table: n_tensors device records {float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64 numel}.
+ * nr_grad_sqsum: out[0] = sum of squared gradients (train_util.calc_grad_norm's total, squared).
+ * nr_adam_step: torch.optim.Adam's update (no weight decay / amsgrad), `step` = 1-based step count. */
+int nr_grad_sqsum(const void* table, int32_t n_tensors, float* out, void* stream);
+int nr_adam_step(const void* table, int32_t n_tensors, float lr, float beta1, float beta2, float eps, int64_t step,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * bf16 tier: fused PE + SDF MLP (+ forward-mode normals) + radiance MLP on tcgen05 / TMEM.
  * The host packs the weights once into a pre-swizzled bf16 image (16 KB chunks = A tiles of
  * 128 features x 64 k) and describes the network as a short program of steps; the kernel

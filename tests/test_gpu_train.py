@@ -151,3 +151,70 @@ def test_volsdf_and_unisurf_training_renders():
             assert p.grad is not None and torch.isfinite(p.grad).all(), name
     finally:
         neurecon_b200.set_precision("fp16")
+
+
+def _ref_neus_losses(rgb, target_rgb, nablas, mask_volume, target_mask, mask_ignore, w_eik, w_mask):
+    """neus.py:443-478 re-stated with torch ops (the test's checker)."""
+    import torch.nn.functional as F
+    nn_ = torch.norm(nablas, dim=-1)
+    out = {"loss_eikonal": w_eik * F.mse_loss(nn_, torch.ones_like(nn_), reduction="mean")}
+    li = F.l1_loss(rgb, target_rgb, reduction="none")
+    if target_mask is not None:
+        mv = torch.clamp(mask_volume, 1e-3, 1 - 1e-3)
+        out["loss_mask"] = w_mask * F.binary_cross_entropy(mv, target_mask.float(), reduction="mean")
+        tm = target_mask if mask_ignore is None else torch.logical_and(target_mask, mask_ignore)
+        out["loss_img"] = (li * tm[..., None].float()).sum() / (tm.sum() + 1e-10)
+    elif mask_ignore is not None:
+        out["loss_img"] = (li * mask_ignore[..., None].float()).sum() / (mask_ignore.sum() + 1e-10)
+    else:
+        out["loss_img"] = li.mean()
+    out["total"] = sum(out.values())
+    return out
+
+
+@pytest.mark.parametrize("with_mask,with_ignore", [(False, False), (True, False), (True, True), (False, True)])
+def test_fused_neus_losses_and_gradients(with_mask, with_ignore):
+    from neurecon_b200.utils import train_util
+    g = torch.Generator().manual_seed(3)
+    R, P = 300, 128
+    rgb = torch.rand(R, 3, generator=g).to(DEV).requires_grad_()
+    tgt = torch.rand(R, 3, generator=g).to(DEV)
+    nab = (torch.randn(R, P, 3, generator=g) * 0.7).to(DEV).requires_grad_()
+    acc = torch.rand(R, generator=g).to(DEV)
+    acc[:5] = 0.0; acc[5:9] = 1.0                      # outside the clamp: zero gradient
+    acc.requires_grad_()
+    tm = (torch.rand(R, generator=g) > 0.4).to(DEV) if with_mask else None
+    mi = (torch.rand(R, generator=g) > 0.2).to(DEV) if with_ignore else None
+    want = _ref_neus_losses(rgb, tgt, nab, acc, tm, mi, 0.1, 0.5)
+    gw = torch.autograd.grad(want["total"], [rgb, nab] + ([acc] if with_mask else []))
+    got = train_util.neus_losses(rgb, tgt, nab, acc, tm, mi, w_eikonal=0.1, w_mask=0.5)
+    gg = torch.autograd.grad(got["total"], [rgb, nab] + ([acc] if with_mask else []))
+    assert list(got.keys()) == [k for k in ("loss_img", "loss_eikonal", "loss_mask", "total") if k in want]
+    for k in got:
+        assert abs(float(got[k].detach()) - float(want[k].detach())) <= 2e-6 * max(1.0, abs(float(want[k].detach()))), k
+    for a_, b_ in zip(gg, gw):
+        assert rel_err(a_, b_) < 1e-5
+
+
+def test_fused_adam_and_grad_norm_match_torch():
+    from neurecon_b200.utils import train_util
+    torch.manual_seed(0)
+    def make():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(39, 64), torch.nn.Softplus(beta=100), torch.nn.Linear(64, 7)).to(DEV)
+    ma, mb = make(), make()
+    oa = torch.optim.Adam([{"params": ma[0].parameters(), "lr": 5e-4}, {"params": ma[2].parameters()}], lr=2e-3)
+    ob = train_util.FusedAdam([{"params": mb[0].parameters(), "lr": 5e-4}, {"params": mb[2].parameters()}], lr=2e-3)
+    x = torch.randn(50, 39, device=DEV)
+    for it in range(6):
+        for m_, o_ in ((ma, oa), (mb, ob)):
+            o_.zero_grad()
+            (m_(x) ** 2).mean().backward()
+            o_.step()
+        if it == 0:
+            n_ref = torch.sqrt(sum((p.grad ** 2).sum() for p in ma.parameters()))
+            assert abs(float(train_util.grad_norm_device(mb)) - float(n_ref)) < 1e-5 * float(n_ref)
+            d = train_util.calc_grad_norm(model=mb)
+            assert set(d) == {"total", "model"} and abs(d["total"] - float(n_ref)) < 1e-5 * float(n_ref)
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert rel_err(pb, pa) < 2e-6

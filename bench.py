@@ -274,6 +274,16 @@ def main():
                              else "gemm_kernel (fp32 SIMT tier)", n_pts, k_launches, k_ms),
                 "whole_step_frac": (value / world) * MFLOP_PER_RAY * 1e6 / 1e12 / pk["bf16"]}
 
+    # ---- second half of BASELINE.json's metric: dense SDF-grid queries (extract_surface, mesh_util.py:82-111) --------
+    # every rank evaluates the x-planes of its own 256^3 lattice (weak scaling, like the rays); sdf only, lattice
+    # generated on the device, result left in HBM
+    from neurecon_b200.utils import mesh_util
+    GN = 256
+    for _ in range(2):
+        mesh_util.query_sdf_grid(model.implicit_surface, N=GN, plane_range=(0, GN))
+    ms_grid = timed(lambda: mesh_util.query_sdf_grid(model.implicit_surface, N=GN, plane_range=(0, GN)), 3)
+    sdf_qps = world * GN ** 3 * 3 / (ms_grid * 1e-3)
+
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
@@ -289,6 +299,8 @@ def main():
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "sdf_queries_per_s": {"value": sdf_qps, "unit": "queries/s", "workload": "%d^3 lattice per GPU, sdf only" % GN,
+                                  "frac_of_bf16_peak": sdf_qps / world * 0.918 * 1e6 / 1e12 / pk["bf16"]},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -176,6 +176,22 @@ __device__ __forceinline__ void copy_row16(const RowAddr& ra, const uint8_t* sta
   st_shared_v4(ra.chunk(col0 >> 3), c0.x, c0.y, c0.z, c0.w);
   st_shared_v4(ra.chunk((col0 >> 3) + 1), c1.x, c1.y, c1.z, c1.w);
 }
+// 16 consecutive columns [col0, col0+16) of operand row F of 128-point block `blk` of the radiance operand image in
+// global memory (the same 16-bit, 128-byte-swizzled layout the kernel keeps in shared memory).
+template <bool kF16>
+__device__ __forceinline__ void img_store16(uint8_t* img, int64_t blk, int F, int col0, const float (&v)[16]) {
+  uint8_t* row = img + (size_t)blk * kActBytes + (F >> 3) * 1024 + (F & 7) * 128 + (size_t)(col0 >> 6) * kLbo;
+#pragma unroll
+  for (int j4 = 0; j4 < 2; ++j4) {
+    uint4 w;
+    w.x = umma::pack2<kF16>(v[8 * j4 + 0], v[8 * j4 + 1]);
+    w.y = umma::pack2<kF16>(v[8 * j4 + 2], v[8 * j4 + 3]);
+    w.z = umma::pack2<kF16>(v[8 * j4 + 4], v[8 * j4 + 5]);
+    w.w = umma::pack2<kF16>(v[8 * j4 + 6], v[8 * j4 + 7]);
+    *reinterpret_cast<uint4*>(row + ((((((col0 & 63) >> 3) + j4) & 7) ^ (F & 7)) << 4)) = w;
+  }
+}
+
 template <bool kF16>
 __device__ __forceinline__ void store_elem(uint8_t* act, int k, int n, float v) {
   *reinterpret_cast<uint16_t*>(act + umma::b_chunk_offset(k, n >> 3, kLbo) + (n & 7) * 2) = umma::pack1<kF16>(v);

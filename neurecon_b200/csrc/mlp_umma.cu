@@ -365,6 +365,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                     }
                   }
                   store_row16<kF16>(ra, 16 * h, v, no_st);
+                  // last hidden layer of 'nablas_img': its value activations are what the radiance pass starts from
+                  if (S.to_rad && a.feat_img) img_store16<kF16>(a.feat_img, tile >> 2, F, 32 * (int)(tile & 3) + 16 * h, v);
                 } else {
                   copy_row16(ra, pes, jpe, 16 * h);
                 }
@@ -454,22 +456,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
                 }
               }
               if (S.to_rad) store_row16<kF16>(ra, 16 * c, v);
-              if (a.feat_img && F < S.out_rows) {
-                // the same 16-bit operand row, placed in the 128-point block of the image: tangent tiles hold 32 points
-                // (block column 32 * (tile & 3)), value tiles 128
-                const int col0 = (tang ? 32 * (int)(tile & 3) : 0) + 16 * c;
-                uint8_t* blk = a.feat_img + (size_t)(tang ? (tile >> 2) : tile) * kActBytes + (F >> 3) * 1024 + (F & 7) * 128 +
-                               (size_t)(col0 >> 6) * kLbo;
-#pragma unroll
-                for (int j4 = 0; j4 < 2; ++j4) {
-                  uint4 w;
-                  w.x = umma::pack2<kF16>(v[8 * j4 + 0], v[8 * j4 + 1]);
-                  w.y = umma::pack2<kF16>(v[8 * j4 + 2], v[8 * j4 + 3]);
-                  w.z = umma::pack2<kF16>(v[8 * j4 + 4], v[8 * j4 + 5]);
-                  w.w = umma::pack2<kF16>(v[8 * j4 + 6], v[8 * j4 + 7]);
-                  *reinterpret_cast<uint4*>(blk + ((((((col0 & 63) >> 3) + j4) & 7) ^ (F & 7)) << 4)) = w;
-                }
-              }
+              if (a.feat_img && F < S.out_rows)   // tangent tiles hold 32 points (block column 32 * (tile & 3)), value tiles 128
+                img_store16<kF16>(a.feat_img, tang ? (tile >> 2) : tile, F, (tang ? 32 * (int)(tile & 3) : 0) + 16 * c, v);
             }
           }
           if (S.to_rad) {
@@ -603,7 +591,8 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
     if (prog->input_mode != 2 && (S.epi == EPI_RELU || S.epi == EPI_RGB || (S.epi == EPI_FEAT && S.to_rad))) has_rad = true;
   }
   if (prog->input_mode == 1) {
-    NR_CHECK_ARG(!prog->tangents && view && nabla && feat_img && prog->steps[0].k_steps == 16 && prog->steps[0].epi == EPI_EXTRAS,
+    NR_CHECK_ARG(!prog->tangents && view && nabla && feat_img && prog->steps[0].k_steps == 16 &&
+                     (prog->steps[0].epi == EPI_EXTRAS || prog->steps[0].epi == EPI_LINEAR),
                  "nr_mlp_umma_forward: radiance-only programs need value tiles, view dirs, normals, the feature image and a "
                  "K = 256 first step");
     NR_CHECK_ARG(((uintptr_t)feat_img & 15) == 0, "nr_mlp_umma_forward: feat_img must be 16-byte aligned");

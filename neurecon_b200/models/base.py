@@ -282,7 +282,10 @@ class ImplicitSurface(nn.Module):
 
         with torch.cuda.device(dev):
             if mode == "split":
-                p_geo, p_rad = net.program("nablas_img", pair=pair), net.program("radiance")
+                # one-CTA kernel: image = last hidden activations, the radiance pass applies the feature layer 128 columns
+                # wide; pair kernel: image = the feature, from its own 32-column step
+                p_geo = net.program("nablas_imgf" if pair else "nablas_img", pair=pair)
+                p_rad = net.program("radiancef" if pair else "radiance")
                 step = _SPLIT_POINTS
                 img = _lib.workspace((min(n, step) + 127) // 128 * 65536, dev, slot=1)
                 for i0 in range(0, n, step):

@@ -155,18 +155,23 @@ class UmmaNet:
         image: layer 0 = feature part, then the [PE(x)|PE(view)|normals] part accumulated onto it),
         'fused' (everything in one launch, radiance steps 32 columns wide)."""
         from . import _lib
-        if mode == "radiance":
+        if mode in ("radiance", "radiancef"):
+            # 'radiance': the image holds the last hidden SDF activations -> the geometry-feature layer (linear) first;
+            # 'radiancef': the image holds the feature itself (written by an EPI_FEAT step, 'nablas_imgf')
             assert self.rad is not None
             r0 = self.rad[0]
-            steps = [dict(r0, k_steps=16, epi=EPI_EXTRAS, n_cols=128),
-                     dict(r0, chunk_begin=r0["chunk_begin"] + r0["n_mt"] * 4, k_steps=self.rad_extra_rows // 16,
-                          accumulate=1, n_cols=128)]
+            steps = [dict(self.feat, epi=EPI_LINEAR, n_cols=128)] if mode == "radiance" else []
+            steps += [dict(r0, k_steps=16, epi=EPI_EXTRAS, n_cols=128),
+                      dict(r0, chunk_begin=r0["chunk_begin"] + r0["n_mt"] * 4, k_steps=self.rad_extra_rows // 16,
+                           accumulate=1, n_cols=128)]
             steps += [dict(s, n_cols=128) for s in self.rad[1:]]
             return self._finish(steps, tang=0, input_mode=1)
         tang = 0 if mode == "sdf" else 1
         steps = [dict(s, n_cols=128) for s in self.hidden]
         steps.append(dict(self.sdf_out2 if pair else self.sdf_out, n_cols=128))
-        if mode == "nablas_img":
+        if mode == "nablas_img":       # the last hidden layer's value activations also go to the operand image
+            steps[len(self.hidden) - 1]["to_rad"] = 1
+        elif mode == "nablas_imgf":    # the geometry feature (one more, 32-column step) goes to the operand image
             steps.append(dict(self.feat, n_cols=32))
         elif mode == "fused":
             assert self.rad is not None

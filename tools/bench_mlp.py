@@ -51,14 +51,15 @@ def main():
     net = m.implicit_surface._umma_net(m.radiance_net)
     img = torch.zeros((n + 127) // 128 * 65536, dtype=torch.uint8, device=dev)
     for mode, mflop in (("sdf", 1.049 * 459008 / 524544), ("nablas", 1.967), ("fused", 1.967 + 0.543),
-                        ("nablas_img", 1.967 + 0.1316), ("radiance", 0.543 - 0.1316),
-                        ("pair:sdf", 1.049 * 459008 / 524544), ("pair:nablas", 1.967), ("pair:nablas_img", 1.967 + 0.1316)):
+                        ("nablas_img", 1.967), ("radiance", 0.543),
+                        ("nablas_imgf", 1.967 + 0.1316), ("radiancef", 0.543 - 0.1316),
+                        ("pair:sdf", 1.049 * 459008 / 524544), ("pair:nablas", 1.967), ("pair:nablas_imgf", 1.967 + 0.1316)):
         for flags in [int(f) for f in os.environ.get("NR_FLAGS", "0,2").split(",")]:
             pair = mode.startswith("pair:")
             prog = net.program(mode[5:] if pair else mode, pair=pair)
             prog._pair = pair
             prog.debug_flags = flags
-            ms = run(net, prog, x, v, n, reps, img if mode.endswith("nablas_img") or mode == "radiance" else None)
+            ms = run(net, prog, x, v, n, reps, img if "img" in mode or mode.startswith("radiance") else None)
             print("mode=%-15s flags=%d  %8.3f ms  %7.1f Mpts/s  %6.1f algorithmic TFLOP/s" % (
                 mode, flags, ms, n / ms / 1e3, n * mflop * 1e6 / (ms * 1e-3) / 1e12), flush=True)
 

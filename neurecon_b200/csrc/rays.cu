@@ -294,6 +294,121 @@ __global__ void neus_upsample_kernel(const float* __restrict__ rays_o, const flo
 }
 
 // ---------------------------------------------------------------------------------------------
+// NeuS compositing, staged variant (M <= kStagedMaxM): the ray's 8M-4 input floats are first pulled into the warp's
+// shared-memory slice with coalesced 4-byte cp.async copies, all in flight at once (32 per lane at M = 128), and the
+// scan below reads them from there: the memory system sees independent, fully coalesced 16-byte requests instead of
+// 4 dependent rounds of strided loads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStagedMaxM = 160;
+// The staged kernel is bound by instruction issue, not by HBM (ncu: issue slots 91 % busy with IEEE division, expf
+// and sqrt): it uses the 2-ulp hardware forms -- well inside the 1e-4 compositing tolerance; sample positions, which
+// must be bit-exact, are not computed here.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__global__ void neus_composite_staged_kernel(const float* __restrict__ sdf, const float* __restrict__ nablas,
+                                             const float* __restrict__ radiance, const float* __restrict__ d_mid,
+                                             const float* __restrict__ s_dev, int64_t R, int M, int white_bkgd,
+                                             float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ acc,
+                                             float* __restrict__ normals, float* __restrict__ cdf_out,
+                                             float* __restrict__ alpha_out, float* __restrict__ w_out, int vec16) {
+  extern __shared__ __align__(16) float stage[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray0 = blockIdx.x * (int64_t)kWarpsPerBlock, ray = ray0 + warp;
+  const int M1 = M - 1;
+  const int nrays = (int)((R - ray0) < kWarpsPerBlock ? (R - ray0) : kWarpsPerBlock);
+  // block-level staging: the kWarpsPerBlock rays of a block are contiguous in every input, and 4 rows of any length are
+  // a multiple of 16 bytes, so whole blocks move with 16-byte copies when the base pointers allow it
+  float* s_sd = stage;                               // [4][M]
+  float* s_nb = s_sd + kWarpsPerBlock * M;           // [4][3M]
+  float* s_rad = s_nb + kWarpsPerBlock * 3 * M;      // [4][3(M-1)]
+  float* s_dm = s_rad + kWarpsPerBlock * 3 * M1;     // [4][M-1]
+  auto stage_in = [&](float* dst, const float* src, int row) {   // rows of `row` floats for the block's rays
+    const float* g = src + ray0 * (int64_t)row;
+    const int n = nrays * row;
+    if (vec16) {
+      const int n4 = n >> 2;
+      for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 4 * i)), "l"(g + 4 * i) : "memory");
+      for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) cp_async4(dst + i, g + i);
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) cp_async4(dst + i, g + i);
+    }
+  };
+  stage_in(s_sd, sdf, M);
+  if (nablas) stage_in(s_nb, nablas, 3 * M);
+  stage_in(s_rad, radiance, 3 * M1);
+  stage_in(s_dm, d_mid, M1);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  if (ray >= R) return;
+  const float* sd = s_sd + warp * M;
+  const float* nb = s_nb + warp * 3 * M;
+  const float* rad = s_rad + warp * 3 * M1;
+  const float* dm = s_dm + warp * M1;
+  const float s = *s_dev;
+  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aw = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  // lane l owns the kSeg consecutive intervals [kSeg l, kSeg l + kSeg): one logistic per sample, a serial product
+  // inside the lane and ONE multiplicative warp scan over the lane products (5 shuffles per ray instead of 5 per
+  // 32 intervals)
+  constexpr int kSeg = (kStagedMaxM + 31) / 32;
+  const int seg = (M1 + 31) >> 5;                     // intervals per lane (<= kSeg)
+  const int i0 = lane * seg;
+  float alpha[kSeg], tr[kSeg];                        // alpha_i and the transmittance before interval i inside the lane
+  float prod = 1.0f;
+  float c_prev = fast_sigmoid(sd[i0 < M ? i0 : M - 1] * s);
+#pragma unroll
+  for (int k = 0; k < kSeg; ++k) {
+    const int i = i0 + k;
+    const bool ok = k < seg && i < M1;
+    const float c1 = fast_sigmoid(sd[i + 1 < M ? i + 1 : M - 1] * s);
+    alpha[k] = ok ? fmaxf(__fdividef(c_prev - c1, c_prev + 1e-10f), 0.0f) : 0.0f;
+    if (ok && cdf_out) {
+      cdf_out[ray * (int64_t)M + i] = c_prev;
+      if (i == M - 2) cdf_out[ray * (int64_t)M + i + 1] = c1;
+    }
+    tr[k] = prod;
+    if (ok) prod *= (1.0f - alpha[k]) + 1e-10f;
+    c_prev = c1;
+  }
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl *= t;
+  }
+  float before = __shfl_up_sync(kFull, incl, 1);      // transmittance before the lane's first interval
+  if (lane == 0) before = 1.0f;
+#pragma unroll
+  for (int k = 0; k < kSeg; ++k) {
+    const int i = i0 + k;
+    if (k < seg && i < M1) {
+      const float w = alpha[k] * (before * tr[k]);
+      if (alpha_out) alpha_out[ray * (int64_t)M1 + i] = alpha[k];
+      if (w_out) w_out[ray * (int64_t)M1 + i] = w;
+      ar += w * rad[3 * i]; ag += w * rad[3 * i + 1]; ab += w * rad[3 * i + 2];
+      ad += w * dm[i];
+      aw += w;
+      if (nablas) {
+        const float x = nb[3 * i], y = nb[3 * i + 1], z = nb[3 * i + 2];
+        const float inv = rsqrtf(fmaxf(x * x + y * y + z * z, 1e-24f));   // = 1 / max(|v|, 1e-12)
+        nx += w * x * inv; ny += w * y * inv; nz += w * z * inv;
+      }
+    }
+  }
+  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aw = warp_sum(aw);
+  if (nablas) { nx = warp_sum(nx); ny = warp_sum(ny); nz = warp_sum(nz); }
+  if (lane == 0) {
+    if (white_bkgd) { ar += 1.0f - aw; ag += 1.0f - aw; ab += 1.0f - aw; }
+    rgb[3 * ray] = ar; rgb[3 * ray + 1] = ag; rgb[3 * ray + 2] = ab;
+    depth[ray] = ad / (aw + 1e-10f);
+    acc[ray] = aw;
+    if (normals) { normals[3 * ray] = nx; normals[3 * ray + 1] = ny; normals[3 * ray + 2] = nz; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // NeuS compositing (neus.py:28-35,57-70,346-381): one warp per ray, 32 intervals per step,
 // multiplicative warp scan with a running carry for the exclusive transmittance.
 // ---------------------------------------------------------------------------------------------
@@ -583,6 +698,19 @@ extern "C" int nr_neus_composite(const float* sdf, const float* nablas, const fl
   NR_CHECK_ARG(R >= 0 && M >= 2, "nr_neus_composite: bad sizes");
   NR_CHECK_ARG((nablas != nullptr) == (normals != nullptr), "nr_neus_composite: nablas and normals go together");
   if (R == 0) return NR_OK;
+  if (M <= kStagedMaxM) {
+    const size_t smem = (size_t)kWarpsPerBlock * 8 * M * sizeof(float);
+    static bool carve = false;   // 16 KB per 4-warp block: ask for the large shared-memory carve-out so 13 blocks fit per SM
+    if (!carve) {
+      cudaFuncSetAttribute(neus_composite_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      carve = true;
+    }
+    neus_composite_staged_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+        sdf, nablas, radiance, d_mid, s_dev, R, M, white_bkgd, rgb, depth, acc, normals, cdf_out, alpha_out, weights_out,
+        ((((uintptr_t)sdf | (uintptr_t)nablas | (uintptr_t)radiance | (uintptr_t)d_mid) & 15) == 0) ? 1 : 0);
+    NR_CHECK_LAUNCH("neus_composite_staged_kernel");
+    return NR_OK;
+  }
   neus_composite_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       sdf, nablas, radiance, d_mid, s_dev, R, M, white_bkgd, rgb, depth, acc, normals, cdf_out, alpha_out,
       weights_out);

@@ -111,9 +111,17 @@ int nr_radiance_forward_f32(const nr_radiance_net_t* net, const float* x, const 
 int nr_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, const float* bias, int64_t M,
                 int32_t N, int32_t K, float* Y, int32_t ldy, int32_t mode, float* S, int32_t lds,
                 const float* aux, int32_t ldaux, int64_t m_val, void* stream);
+/* Same contract on the tensor cores (csrc/gemm_tc.cu): operands converted to fp16 (operand_f16 = 1) or bf16 on their
+ * way into shared memory, fp32 accumulation in TMEM; N <= 256, W must fit in shared memory as 16-bit. */
+int nr_gemm_tc(const float* A, int32_t lda, const float* W, int32_t ldw, const float* bias, int64_t M, int32_t N,
+               int32_t K, float* Y, int32_t ldy, int32_t mode, float* S, int32_t lds, const float* aux,
+               int32_t ldaux, int64_t m_val, int32_t operand_f16, void* stream);
 /* dW[N,K] += G[rows,N]^T X[rows,K]  (weight gradient; split over rows, fp32 atomics) */
 int nr_gemm_tn_f32(const float* G, int32_t ldg, const float* X, int32_t ldx, int64_t rows, int32_t N,
                    int32_t K, float* dW, int32_t lddw, void* stream);
+/* Same on the tensor cores (csrc/gemm_tc.cu): both operands converted to 16 bits, MN-major tiles, fp32 atomics. */
+int nr_gemm_tn_tc(const float* G, int32_t ldg, const float* X, int32_t ldx, int64_t rows, int32_t N, int32_t K,
+                  float* dW, int32_t lddw, int32_t operand_f16, void* stream);
 /* out[N] += column sums of G[rows,N]  (bias gradient) */
 int nr_colsum_f32(const float* G, int32_t ldg, int64_t rows, int32_t N, float* out, void* stream);
 /* in place: gh <- g_z = gh*S + sum_c gt_c*u_c*100*S*(1-S),  gt_c <- g_u_c = gt_c*S.

@@ -67,7 +67,9 @@ _SIGNATURES = {
     "nr_radiance_forward_f32_workspace": (_SZ, [C.POINTER(RadianceNetDesc), _I64]),
     "nr_radiance_forward_f32": (C.c_int, [C.POINTER(RadianceNetDesc), _P, _P, _P, _P, _I64, _I64, _P, _P, _SZ, _P]),
     "nr_gemm_f32": (C.c_int, [_P, _I32, _P, _I32, _P, _I64, _I32, _I32, _P, _I32, _I32, _P, _I32, _P, _I32, _I64, _P]),
+    "nr_gemm_tc": (C.c_int, [_P, _I32, _P, _I32, _P, _I64, _I32, _I32, _P, _I32, _I32, _P, _I32, _P, _I32, _I64, _I32, _P]),
     "nr_gemm_tn_f32": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _I32, _P]),
+    "nr_gemm_tn_tc": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _I32, _I32, _P]),
     "nr_colsum_f32": (C.c_int, [_P, _I32, _I64, _I32, _P, _P]),
     "nr_sdf_bwd_act_f32": (C.c_int, [_P, _I32, _P, _I32, _P, _I32, _P, _I32, _I64, _I32, _P]),
     "nr_act_bwd_f32": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P]),

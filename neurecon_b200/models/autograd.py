@@ -39,21 +39,42 @@ def _padded(W):
     return Wp
 
 
-def _gemm(A, K, W, bias, N, mode, S=None, aux=None, m_val=0):
-    """Y[M, pad4(N)] = epilogue(A[:, :K] @ W[:N, :K]^T + bias); pad columns are zero."""
+def _tc():
+    """Training GEMMs on the tensor cores (csrc/gemm_tc.cu) in the fp16 / bf16 tiers, fp32 SIMT in the fp32 tier."""
+    return _lib.tensor_tier()
+
+
+def _gemm(A, K, W, bias, N, mode, S=None, aux=None, m_val=0, grad=False):
+    """Y[M, pad4(N)] = epilogue(A[:, :K] @ W[:N, :K]^T + bias); pad columns are zero.  ``grad``: the operands are
+    gradients (tensor tier: bf16 operands for their range instead of fp16)."""
     lib = _lib.get_lib()
     M = A.shape[0]
     ldy = _pad4(N)
     Y = torch.zeros(M, ldy, dtype=torch.float32, device=A.device) if ldy != N else torch.empty(M, ldy, dtype=torch.float32, device=A.device)
+    st = _lib.stream_ptr(A.device)
+    if _tc():
+        f16 = 1 if (_lib.get_precision() == "fp16" and not grad) else 0
+        for n0 in range(0, N, 256):                       # the MMA's N is at most 256 (the last SDF layer has 257 rows)
+            nn = min(256, N - n0)
+            off = lambda t, ld: None if t is None else t[:, n0:]
+            _lib.check(lib.nr_gemm_tc(
+                _lib.ptr(A), A.shape[1], _lib.ptr(W[n0:]), W.shape[1], _lib.ptr(None if bias is None else bias[n0:]), M, nn, K,
+                _lib.ptr(Y[:, n0:]), ldy, mode, _lib.ptr(off(S, 0)), 0 if S is None else S.shape[1], _lib.ptr(off(aux, 0)),
+                0 if aux is None else aux.shape[1], m_val, f16, st), "gemm_tc")
+        return Y
     _lib.check(lib.nr_gemm_f32(_lib.ptr(A), A.shape[1], _lib.ptr(W), W.shape[1], _lib.ptr(bias), M, N, K, _lib.ptr(Y), ldy,
                                mode, _lib.ptr(S), 0 if S is None else S.shape[1], _lib.ptr(aux),
-                               0 if aux is None else aux.shape[1], m_val, _lib.stream_ptr(A.device)), "gemm_f32")
+                               0 if aux is None else aux.shape[1], m_val, st), "gemm_f32")
     return Y
 
 
 def _gemm_tn(G, N, X, K, dW):
     """dW[:N, :K] += G[:, :N]^T X[:, :K]"""
     lib = _lib.get_lib()
+    if _tc():
+        _lib.check(lib.nr_gemm_tn_tc(_lib.ptr(G), G.shape[1], _lib.ptr(X), X.shape[1], G.shape[0], N, K, _lib.ptr(dW),
+                                     dW.shape[1], 0, _lib.stream_ptr(G.device)), "gemm_tn_tc")
+        return
     _lib.check(lib.nr_gemm_tn_f32(_lib.ptr(G), G.shape[1], _lib.ptr(X), X.shape[1], G.shape[0], N, K, _lib.ptr(dW),
                                   dW.shape[1], _lib.stream_ptr(G.device)), "gemm_tn_f32")
 
@@ -146,7 +167,7 @@ class _SdfFn(torch.autograd.Function):
             _gemm_tn(g_out, N, h_last, K, dW)
             grads[2 * (L - 1) + 1] = _colsum(g_out, N)
             Wt = _padded(Ws[L - 1][:, :K].t().contiguous())
-            g_h = _gemm(g_out, N, Wt, None, K, MODE_LINEAR)
+            g_h = _gemm(g_out, N, Wt, None, K, MODE_LINEAR, grad=True)
             g_t = None
             if wn:
                 g_tout = torch.zeros(3 * n, 4, **f)
@@ -173,9 +194,9 @@ class _SdfFn(torch.autograd.Function):
                 grads[2 * l + 1] = _colsum(g_h, N)
                 if l > 0:
                     Wt = _padded(Ws[l][:, :K].t().contiguous())
-                    g_h = _gemm(g_h, N, Wt, None, K, MODE_LINEAR)      # [n, pad4(K)]; for the skip layer only the
+                    g_h = _gemm(g_h, N, Wt, None, K, MODE_LINEAR, grad=True)      # [n, pad4(K)]; for the skip layer only the
                     if wn:                                             # first out_{l-1} columns are used below
-                        g_t = _gemm(g_t, N, Wt, None, K, MODE_LINEAR)
+                        g_t = _gemm(g_t, N, Wt, None, K, MODE_LINEAR, grad=True)
         ctx.saved = ctx.last = None
         return (None, None, None, None, *grads)
 
@@ -235,7 +256,7 @@ class _RadianceFn(torch.autograd.Function):
                 grads[2 * l] = dW[:, :K]
                 grads[2 * l + 1] = _colsum(g, N)
                 Wt = _padded(Ws[l][:, :K].t().contiguous())
-                g = _gemm(g, N, Wt, None, K, MODE_LINEAR)
+                g = _gemm(g, N, Wt, None, K, MODE_LINEAR, grad=True)
         off, in0 = ctx.split
         g_normals = g[:, off:off + 3].contiguous()
         g_feat = g[:, off + 3:in0].contiguous()

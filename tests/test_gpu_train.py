@@ -25,7 +25,17 @@ def _cpu_clone(m):
     return sd, L, Lr
 
 
-def test_mlp_gradients_incl_second_order():
+@pytest.mark.parametrize("tier,tol_out,tol_grad", [("fp32", 1e-4, 1e-4), ("fp16", 5e-3, 2e-2), ("bf16", 4e-2, 1e-1)])
+def test_mlp_gradients_incl_second_order(tier, tol_out, tol_grad):
+    """fp32 tier: SIMT GEMMs; fp16 / bf16 tiers: the tcgen05 training GEMMs (16-bit operands, bf16 for gradients)."""
+    neurecon_b200.set_precision(tier)
+    try:
+        _mlp_gradients(tol_out, tol_grad)
+    finally:
+        neurecon_b200.set_precision("fp16")
+
+
+def _mlp_gradients(tol_out, tol_grad):
     m = build_neus(seed=1, device=DEV)
     n = 300
     x = synthetic.make_points(n, extent=0.9, seed=31)
@@ -50,19 +60,39 @@ def test_mlp_gradients_incl_second_order():
     orgb = nets.radiance_forward(x.double(), v.double(), onab, ofeat, Lr, -1, 4)
     oloss = loss_of(osdf, onab, ofeat, orgb)
     oloss.backward()
-    assert rel_err(loss, oloss) < 1e-5
-    assert rel_err(sdf, osdf) < 1e-5 and rel_err(nab, onab) < 1e-4 and rel_err(rgb, orgb) < 1e-5
+    assert rel_err(loss, oloss) < max(1e-5, tol_out)
+    assert rel_err(sdf, osdf) < max(1e-5, tol_out) and rel_err(nab, onab) < tol_out and rel_err(rgb, orgb) < max(1e-5, tol_out)
     worst = {}
     for name, p in m.named_parameters():
         if name == "ln_s":
             continue
         assert p.grad is not None, name
         worst[name] = rel_err(p.grad, sd[name].grad)
-    bad = {k: e for k, e in worst.items() if not e < 1e-4}
+    # the radiance net is ReLU: 16-bit rounding of the forward pass flips the mask of a few near-zero units, and with
+    # 300 points and random-sign upstream gradients one flip moves a bias gradient by ~1/sqrt(150) of its size
+    # (tools/dbg_grad_tiers.py: 8 % from the forward rounding alone, < 1.2 % from the backward GEMMs) -> for the
+    # 16-bit tiers those parameters are held to an L2-relative bound instead of the max-norm one
+    bad = {}
+    for k, e in worst.items():
+        if tol_grad > 1e-3 and k.startswith("radiance_net"):
+            a_, b_ = dict(m.named_parameters())[k].grad.double().cpu(), sd[k].grad.double()
+            l2 = ((a_ - b_).norm() / b_.norm()).item()
+            if not (l2 < 4 * tol_grad and e < 10 * tol_grad):
+                bad[k] = (e, l2)
+        elif not e < tol_grad:
+            bad[k] = e
     assert not bad, bad
 
 
 def test_sdf_only_forward_under_grad():
+    neurecon_b200.set_precision("fp32")
+    try:
+        _sdf_only_forward_under_grad()
+    finally:
+        neurecon_b200.set_precision("fp16")
+
+
+def _sdf_only_forward_under_grad():
     m = build_neus(seed=1, device=DEV)
     x = synthetic.make_points(64, extent=0.9, seed=33)
     sdf, feat = m.implicit_surface.forward(x.to(DEV), return_h=True)
@@ -218,3 +248,64 @@ def test_fused_adam_and_grad_norm_match_torch():
             assert set(d) == {"total", "model"} and abs(d["total"] - float(n_ref)) < 1e-5 * float(n_ref)
     for pa, pb in zip(ma.parameters(), mb.parameters()):
         assert rel_err(pb, pa) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(1000, 256, 256, 1), (300, 217, 39, 1), (129, 257, 256, 0), (5000, 256, 289, 2),
+                                        (777, 3, 256, 3), (640, 256, 256, 4), (513, 1, 256, 5), (2048, 39, 256, 5)])
+def test_gemm_tc_matches_fp32_gemm(M, N, K, mode):
+    """tcgen05 training GEMM (16-bit operands, fp32 accumulate, fused epilogues) against the fp32 SIMT GEMM."""
+    from neurecon_b200 import _lib
+    if N > 256:
+        pytest.skip("N > 256 stays on the fp32 GEMM")
+    lib = _lib.get_lib()
+    g = torch.Generator().manual_seed(M + N)
+    pad4 = lambda v: (v + 3) & ~3
+    A = torch.zeros(M, pad4(K)); A[:, :K] = torch.randn(M, K, generator=g) * 0.3
+    W = torch.zeros(N, pad4(K)); W[:, :K] = torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)
+    b = torch.randn(N, generator=g) * 0.1
+    m_val = 160
+    aux = torch.rand(m_val, pad4(N), generator=g)
+    A, W, b, aux = A.to(DEV), W.to(DEV), b.to(DEV), aux.to(DEV)
+    outs = []
+    for tc in (False, True):
+        Y = torch.full((M, pad4(N)), float("nan"), device=DEV)
+        S = torch.full((M, pad4(N)), float("nan"), device=DEV) if mode == 1 else None
+        args = [_lib.ptr(A), A.shape[1], _lib.ptr(W), W.shape[1], _lib.ptr(b), M, N, K, _lib.ptr(Y), Y.shape[1], mode,
+                _lib.ptr(S), 0 if S is None else S.shape[1], _lib.ptr(aux) if mode == 4 else None, aux.shape[1] if mode == 4 else 0,
+                m_val if mode == 4 else 0]
+        if tc:
+            _lib.check(lib.nr_gemm_tc(*args, 1, _lib.stream_ptr(torch.device(DEV))), "gemm_tc")
+        else:
+            _lib.check(lib.nr_gemm_f32(*args, _lib.stream_ptr(torch.device(DEV))), "gemm_f32")
+        torch.cuda.synchronize()
+        outs.append((Y[:, :N].clone(), None if S is None else S[:, :N].clone()))
+    assert torch.isfinite(outs[1][0]).all()
+    assert rel_err(outs[1][0], outs[0][0]) < 3e-3, rel_err(outs[1][0], outs[0][0])
+    if mode == 1:
+        assert rel_err(outs[1][1], outs[0][1]) < 2e-2
+
+
+@pytest.mark.parametrize("rows,N,K", [(4096, 256, 256), (1000, 217, 39), (333, 257, 256), (20000, 256, 289), (64, 3, 256), (129, 1, 256)])
+def test_gemm_tn_tc_matches_fp32(rows, N, K):
+    """tcgen05 weight-gradient GEMM dW += G^T X against the fp32 SIMT one (bf16 operands: gradients need the range)."""
+    from neurecon_b200 import _lib
+    lib = _lib.get_lib()
+    g = torch.Generator().manual_seed(rows + N)
+    pad4 = lambda v: (v + 3) & ~3
+    G = torch.zeros(rows, pad4(N)); G[:, :N] = torch.randn(rows, N, generator=g) * 1e-4
+    X = torch.zeros(rows, pad4(K)); X[:, :K] = torch.randn(rows, K, generator=g)
+    G, X = G.to(DEV), X.to(DEV)
+    outs = []
+    for tc in (False, True):
+        dW = torch.ones(N, pad4(K), device=DEV)          # += semantics
+        if tc:
+            _lib.check(lib.nr_gemm_tn_tc(_lib.ptr(G), G.shape[1], _lib.ptr(X), X.shape[1], rows, N, K, _lib.ptr(dW), dW.shape[1],
+                                         0, _lib.stream_ptr(torch.device(DEV))), "gemm_tn_tc")
+        else:
+            _lib.check(lib.nr_gemm_tn_f32(_lib.ptr(G), G.shape[1], _lib.ptr(X), X.shape[1], rows, N, K, _lib.ptr(dW), dW.shape[1],
+                                          _lib.stream_ptr(torch.device(DEV))), "gemm_tn_f32")
+        torch.cuda.synchronize()
+        outs.append(dW[:, :K] - 1.0)
+    want = G[:, :N].double().T @ X[:, :K].double()
+    assert rel_err(outs[0], want.float()) < 1e-3
+    assert rel_err(outs[1], want.float()) < 1.5e-2, rel_err(outs[1], want.float())

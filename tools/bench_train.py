@@ -10,6 +10,8 @@ from conftest import build_neus
 from neurecon_b200.models.frameworks import neus
 from neurecon_b200.utils import synthetic
 
+if os.environ.get("NEURECON_B200_PRECISION"):
+    neurecon_b200.set_precision(os.environ["NEURECON_B200_PRECISION"])
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dev = torch.device("cuda:0")
@@ -41,5 +43,5 @@ for _ in range(steps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
-print("NeuS training step, %d rays: %.2f ms/step, %.0f rays/s, loss %.4f, peak mem %.2f GB (algorithmic ~1.85 GFLOP/ray => %.1f TFLOP/s)"
-      % (R, ms, R / ms * 1e3, loss.item(), torch.cuda.max_memory_allocated() / 2**30, R * 1.85e9 / (ms * 1e-3) / 1e12))
+print("[%s tier] NeuS training step, %d rays: %.2f ms/step, %.0f rays/s, loss %.4f, peak mem %.2f GB (algorithmic ~1.85 GFLOP/ray => %.1f TFLOP/s)"
+      % (neurecon_b200.get_precision(), R, ms, R / ms * 1e3, loss.item(), torch.cuda.max_memory_allocated() / 2**30, R * 1.85e9 / (ms * 1e-3) / 1e12))

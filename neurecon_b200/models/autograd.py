@@ -313,3 +313,111 @@ def radiance_forward_autograd(rad, x, view_dirs, normals, geometry_feature):
         wb += [_effective_weight(layer), layer.bias]
     rgb = _RadianceFn.apply(xf, vf, nf, ff, rad.embed_multires, rad.embed_multires_view, *wb)
     return rgb.reshape(*shape, 3)
+
+
+class _NerfFn(torch.autograd.Function):
+    """NeRF++ background net (models/base.py:426-453, use_view_dirs=True) under autograd:
+    (x [n,dim], view [n,3], pts W/b ..., alpha W/b, feature W/b, views W/b, rgb W/b) -> (sigma [n], rgb [n,3]).
+    Gradients w.r.t. the weights only (the inputs are sample positions)."""
+
+    @staticmethod
+    def forward(ctx, x, view, dim, multires, multires_view, skip, D, *wb):
+        lib = _lib.get_lib()
+        n, dev = x.shape[0], x.device
+        Ws = [_padded(w.detach().float()) for w in wb[0::2]]
+        bs = [b.detach().float().contiguous() for b in wb[1::2]]
+        dims = [(w.shape[0], w.shape[1]) for w in wb[0::2]]
+        npe = dim * (1 if multires < 0 else 1 + 2 * multires)
+        npv = 3 if multires_view < 0 else 3 * (1 + 2 * multires_view)
+        f = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            pe = torch.zeros(n, _pad4(npe), **f)
+            _lib.check(lib.nr_embed_f32(_lib.ptr(x), n, dim, multires, _lib.ptr(pe), pe.shape[1], 0, None, 0, 0, st), "embed")
+            pv = torch.zeros(n, _pad4(npv), **f)
+            _lib.check(lib.nr_embed_f32(_lib.ptr(view), n, 3, multires_view, _lib.ptr(pv), pv.shape[1], 0, None, 0, 0, st), "embed")
+            ins, outs = [], []           # input / output activation of every pts layer
+            h = pe
+            for i in range(D):
+                N, K = dims[i]
+                ins.append(h)
+                h = _gemm(h, K, Ws[i], bs[i], N, MODE_RELU)
+                outs.append(h)
+                if i == skip:            # cat([PE(x), h])  (base.py:436)
+                    cat = torch.zeros(n, _pad4(npe + N), **f)
+                    cat[:, :npe] = pe[:, :npe]
+                    cat[:, npe:npe + N] = h[:, :N]
+                    h = cat
+            W_ = dims[D - 1][0]
+            ia, ife, iv, ir = D, D + 1, D + 2, D + 3
+            sigma = _gemm(h, W_, Ws[ia], bs[ia], 1, MODE_NONE)
+            feat = _gemm(h, W_, Ws[ife], bs[ife], dims[ife][0], MODE_NONE)
+            vin = torch.zeros(n, _pad4(dims[ife][0] + npv), **f)
+            vin[:, :dims[ife][0]] = feat[:, :dims[ife][0]]
+            vin[:, dims[ife][0]:dims[ife][0] + npv] = pv[:, :npv]
+            hv = _gemm(vin, dims[iv][1], Ws[iv], bs[iv], dims[iv][0], MODE_RELU)
+            rgb = _gemm(hv, dims[ir][1], Ws[ir], bs[ir], 3, MODE_SIGMOID)
+        ctx.state = (ins, outs, h, vin, hv, rgb, Ws, dims, npe, skip, D, n)
+        return sigma[:, 0].contiguous(), rgb[:, :3].contiguous()
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_rgb):
+        lib = _lib.get_lib()
+        ins, outs, h_last, vin, hv, rgb, Ws, dims, npe, skip, D, n = ctx.state
+        dev = h_last.device
+        f = dict(dtype=torch.float32, device=dev)
+        grads = [None] * (2 * (D + 4))
+        ia, ife, iv, ir = D, D + 1, D + 2, D + 3
+
+        def layer_bwd(idx, g, x_in, act=None, sigmoid=False):
+            """g [n, pad4(N)] = grad w.r.t. the layer's output -> weight / bias grads; returns grad w.r.t. its input."""
+            N, K = dims[idx]
+            if act is not None:
+                _lib.check(lib.nr_act_bwd_f32(_lib.ptr(g), g.shape[1], _lib.ptr(act), act.shape[1], n, N, 1 if sigmoid else 0,
+                                              _lib.stream_ptr(dev)), "act_bwd")
+            dW = torch.zeros(N, _pad4(K), **f)
+            _gemm_tn(g, N, x_in, K, dW)
+            grads[2 * idx] = dW[:, :K]
+            grads[2 * idx + 1] = _colsum(g, N)
+            Wt = _padded(Ws[idx][:, :K].t().contiguous())
+            return _gemm(g, N, Wt, None, K, MODE_LINEAR, grad=True)
+
+        with torch.cuda.device(dev):
+            g = torch.zeros(n, 4, **f)
+            if g_rgb is not None:
+                g[:, :3] = g_rgb
+            g_hv = layer_bwd(ir, g, hv, act=rgb, sigmoid=True)
+            g_vin = layer_bwd(iv, g_hv, vin, act=hv)
+            nf = dims[ife][0]
+            g_feat = torch.zeros(n, _pad4(nf), **f)
+            g_feat[:, :nf] = g_vin[:, :nf]
+            g_h = layer_bwd(ife, g_feat, h_last)
+            ga = torch.zeros(n, 4, **f)
+            if g_sigma is not None:
+                ga[:, 0] = g_sigma
+            g_h = g_h + layer_bwd(ia, ga, h_last)
+            for i in range(D - 1, -1, -1):
+                N, K = dims[i]
+                if i == skip:            # the next layer's input was cat([PE, h_i]): keep the h part
+                    gh = torch.zeros(n, _pad4(N), **f)
+                    gh[:, :N] = g_h[:, npe:npe + N]
+                    g_h = gh
+                g_h = layer_bwd(i, g_h, ins[i], act=outs[i])
+        ctx.state = None
+        return (None, None, None, None, None, None, None, *grads)
+
+
+def nerf_forward_autograd(module, input_pts, input_views):
+    """NeRF.forward under autograd (models/base.py:426-453)."""
+    if not module.use_view_dirs or len(module.skips) > 1:
+        raise NotImplementedError("neurecon_b200 NeRF supports use_view_dirs=True with at most one skip")
+    _lib.require_cuda(input_pts, input_views)
+    shape = input_pts.shape[:-1]
+    xf = _lib.f32c(input_pts.detach().reshape(-1, module.input_dim))
+    vf = _lib.f32c(input_views.detach().expand(*shape, 3).reshape(-1, 3))
+    wb = []
+    for lin in list(module.pts_linears) + [module.alpha_linear, module.feature_linear, module.views_linears[0], module.rgb_linear]:
+        wb += [lin.weight, lin.bias]
+    skip = module.skips[0] if module.skips else -1
+    sigma, rgb = _NerfFn.apply(xf, vf, module.input_dim, module.multires, module.multires_view, skip, module.D, *wb)
+    return sigma.reshape(shape), rgb.reshape(*shape, 3)

@@ -14,8 +14,7 @@ def volsdf_render_train(rays_o, rays_d, model, near, far, obj_bounding_radius, b
                         white_bkgd, use_nerfplusplus, detailed_output, perturb, N_samples, N_importance, N_outside,
                         max_upsample_steps, max_bisection_steps, epsilon):
     from . import volsdf
-    if use_nerfplusplus:
-        raise NotImplementedError("neurecon_b200: training with the NeRF++ background is not built yet")
+    from ...utils import rend_util
     lib = _lib.get_lib()
     B = rays_d.shape[0] if batched else 1
     prefix = [B, -1] if batched else [-1]
@@ -36,7 +35,8 @@ def volsdf_render_train(rays_o, rays_d, model, near, far, obj_bounding_radius, b
                 dirs, fars = torch.empty(R, 3, **f), torch.empty(R, **f)
                 d_init, pts_init = torch.empty(R, N_init, **f), torch.empty(R, N_init, 3, **f)
                 miss = torch.zeros(1, dtype=torch.int32, device=dev)
-                _lib.check(lib.nr_volsdf_ray_setup(_lib.ptr(ro), _lib.ptr(rd), R, float(near), float(far), -1.0, N_init,
+                _lib.check(lib.nr_volsdf_ray_setup(_lib.ptr(ro), _lib.ptr(rd), R, float(near), float(far),
+                                                   float(obj_bounding_radius) if use_nerfplusplus else -1.0, N_init,
                                                    _lib.ptr(dirs), _lib.ptr(fars), _lib.ptr(miss), _lib.ptr(d_init), N_init,
                                                    _lib.ptr(pts_init), st), "volsdf_ray_setup")
                 d_fine, beta_map, iter_usage = volsdf.fine_sample(
@@ -48,6 +48,23 @@ def volsdf_render_train(rays_o, rays_d, model, near, far, obj_bounding_radius, b
                                                _lib.ptr(d_fine), N_importance, _lib.ptr(d_all), _lib.ptr(pts), st), "merge")
             radiances, sdf, nablas = model.forward(pts, dirs.unsqueeze(-2).expand(R, M, 3))   # volsdf.py:450
             sigma = volsdf.sdf_to_sigma(sdf, alpha, beta)
+            M_in = M
+            if use_nerfplusplus:                                                           # volsdf.py:456-475
+                t = torch.linspace(0, 1, N_outside + 2)[..., 1:-1].float().to(dev)
+                rs = (obj_bounding_radius / torch.flip(t, dims=[-1])).expand([R, N_outside])
+                if perturb:
+                    mids = .5 * (rs[..., 1:] + rs[..., :-1])
+                    upper = torch.cat([mids, rs[..., -1:]], -1)
+                    lower = torch.cat([rs[..., :1], mids], -1)
+                    rs = lower + (upper - lower) * torch.rand(upper.shape).float().to(dev)
+                with torch.no_grad():
+                    d_out = rend_util.get_dvals_from_radius(ro, dirs, rs)
+                    pts_out = ro[..., None, :] + dirs[..., None, :] * d_out[..., :, None]
+                    x_out = torch.cat([pts_out / rs[..., None], 1. / rs[..., None]], dim=-1)
+                sigma_out, radiance_out = model.nerf_outside.forward(x_out, dirs.unsqueeze(-2).expand(R, N_outside, 3))
+                d_all = torch.cat([d_all, d_out], dim=-1)
+                sigma = torch.cat([sigma, sigma_out], dim=-1)
+                radiances = torch.cat([radiances, radiance_out], dim=-2)
             delta_i = d_all[..., 1:] - d_all[..., :-1]
             p_i = torch.exp(-F.relu(sigma[..., :-1] * delta_i))
             tau_i = (1 - p_i + 1e-10) * torch.cumprod(torch.cat([torch.ones_like(p_i[..., :1]), p_i], dim=-1), dim=-1)[..., :-1]
@@ -59,10 +76,13 @@ def volsdf_render_train(rays_o, rays_d, model, near, far, obj_bounding_radius, b
             ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
             if calc_normal:
                 nm = F.normalize(nablas, dim=-1)
-                ret_i['normals_volume'] = (nm[..., :M - 1, :] * tau_i[..., :M - 1, None]).sum(dim=-2)
+                n_pts = min(tau_i.shape[-1], nm.shape[-2])                                  # volsdf.py:510-513
+                ret_i['normals_volume'] = (nm[..., :n_pts, :] * tau_i[..., :n_pts, None]).sum(dim=-2)
             if detailed_output:
                 ret_i.update(implicit_surface=sdf, implicit_nablas=nablas, radiance=radiances, alpha=1.0 - p_i, p_i=p_i,
                              visibility_weights=tau_i, d_vals=d_all, sigma=sigma, beta_map=beta_map, iter_usage=iter_usage)
+                if use_nerfplusplus:
+                    ret_i.update(sigma_out=sigma_out, radiance_out=radiance_out)
             outs.append(ret_i)
     ret = OrderedDict()
     for k in outs[0].keys():

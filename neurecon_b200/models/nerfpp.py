@@ -46,7 +46,8 @@ def _umma_net(module):
 def nerf_forward(module, input_pts, input_views):
     """NeRF.forward(input_pts [..., 4], input_views [..., 3]) -> (sigma [...], rgb [..., 3])."""
     if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
-        raise NotImplementedError("neurecon_b200: NeRF++ training backward is not built yet; use torch.no_grad()")
+        from .autograd import nerf_forward_autograd
+        return nerf_forward_autograd(module, input_pts, input_views)
     _lib.require_cuda(input_pts, input_views)
     lib = _lib.get_lib()
     shape = input_pts.shape[:-1]

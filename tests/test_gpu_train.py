@@ -309,3 +309,81 @@ def test_gemm_tn_tc_matches_fp32(rows, N, K):
     want = G[:, :N].double().T @ X[:, :K].double()
     assert rel_err(outs[0], want.float()) < 1e-3
     assert rel_err(outs[1], want.float()) < 1.5e-2, rel_err(outs[1], want.float())
+
+
+def test_nerfpp_net_gradients_vs_torch_autograd():
+    """NeRF++ background net under autograd (hand-derived backward on the GEMM building blocks) against
+    torch autograd through a plain re-statement of base.py:426-453, fp32 tier."""
+    from neurecon_b200.models.base import NeRF
+    neurecon_b200.set_precision("fp32")
+    try:
+        torch.manual_seed(0)
+        m = NeRF(D=8, W=256, input_ch=4, input_ch_view=3, multires=10, multires_view=4, skips=[4], use_view_dirs=True).to(DEV)
+        n = 257
+        dvec = F.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+        x = torch.cat([dvec, torch.rand(n, 1, device=DEV)], -1)
+        v = F.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+        cs, cr = torch.randn(n, device=DEV), torch.randn(n, 3, device=DEV)
+        sigma, rgb = m(x, v)
+        assert sigma.requires_grad and rgb.requires_grad
+        ((sigma * cs).mean() + (rgb * cr).mean()).backward()
+        got = {k: p.grad.clone() for k, p in m.named_parameters()}
+        m.zero_grad()
+
+        def pe(t, L):
+            out = [t]
+            for k in range(L):
+                out += [torch.sin(t * 2.0 ** k), torch.cos(t * 2.0 ** k)]
+            return torch.cat(out, -1)
+        xe, ve = pe(x.double(), 10), pe(v.double(), 4)
+        md = {k: p.detach().double().requires_grad_() for k, p in m.named_parameters()}
+        h = xe
+        for i in range(8):
+            h = torch.relu(h @ md["pts_linears.%d.weight" % i].T + md["pts_linears.%d.bias" % i])
+            if i == 4:
+                h = torch.cat([xe, h], -1)
+        s2 = (h @ md["alpha_linear.weight"].T + md["alpha_linear.bias"])[:, 0]
+        ft = h @ md["feature_linear.weight"].T + md["feature_linear.bias"]
+        hv = torch.relu(torch.cat([ft, ve], -1) @ md["views_linears.0.weight"].T + md["views_linears.0.bias"])
+        r2 = torch.sigmoid(hv @ md["rgb_linear.weight"].T + md["rgb_linear.bias"])
+        ((s2 * cs.double()).mean() + (r2 * cr.double()).mean()).backward()
+        assert rel_err(sigma, s2) < 1e-4 and rel_err(rgb, r2) < 1e-4
+        bad = {k: rel_err(got[k], md[k].grad) for k in got if not rel_err(got[k], md[k].grad) < 2e-3}
+        assert not bad, bad
+    finally:
+        neurecon_b200.set_precision("fp16")
+
+
+def test_training_renders_with_nerfpp_background():
+    """NeuS (no mask) and VolSDF with the NeRF++ background under autograd: same values as the inference kernels,
+    gradients reach the background net."""
+    from test_oracle_golden import build_neus_bg, build_volsdf
+    from neurecon_b200.models.frameworks import neus, volsdf
+    neurecon_b200.set_precision("fp32")
+    try:
+        o, d = synthetic.make_rays(24, shell_radius=2.5, jitter=0.15, seed=5)
+        m = build_neus_bg(device=DEV)
+        with torch.no_grad():
+            want = neus.volume_render(o.to(DEV), d.to(DEV), m, calc_normal=True, detailed_output=True, perturb=False, N_outside=32)
+        rgb, depth, ret = neus.volume_render(o.to(DEV), d.to(DEV), m, calc_normal=True, detailed_output=True, perturb=False, N_outside=32)
+        assert rgb.requires_grad and rel_err(rgb, want[0]) < 1e-4 and rel_err(depth, want[1]) < 1e-4
+        assert rel_err(ret["normals_volume"], want[2]["normals_volume"]) < 1e-4
+        rgb.mean().backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.nerf_outside.parameters())
+        assert sum(float(p.grad.abs().sum()) for p in m.nerf_outside.parameters()) > 0
+        o, d = synthetic.make_rays(20, shell_radius=2.73, jitter=0.1, seed=6)
+        mv = build_volsdf(0.01, True, device=DEV)
+        kw = dict(near=0.0, far=6.0, obj_bounding_radius=3.0, max_upsample_steps=5, use_nerfplusplus=True, N_outside=32,
+                  calc_normal=True, detailed_output=True, perturb=False)
+        with torch.no_grad():
+            want = volsdf.volume_render(o.to(DEV), d.to(DEV), mv, **kw)
+        rgb, depth, ret = volsdf.volume_render(o.to(DEV), d.to(DEV), mv, **kw)
+        assert rgb.requires_grad and rel_err(rgb, want[0]) < 2e-4 and rel_err(depth, want[1]) < 2e-4
+        assert list(ret.keys())[-2:] == ["sigma_out", "radiance_out"] and ret["sigma"].shape == (20, 224)
+        (rgb.mean() + ret["implicit_nablas"].norm(dim=-1).mean()).backward()
+        # (the synthetic surface is opaque at beta = 0.01: the transmittance behind it underflows, so the background's
+        #  gradient may be exactly zero here -- it must exist and be finite; NeuS above checks a non-zero one)
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in mv.nerf_outside.parameters())
+        assert mv.ln_beta.grad is not None
+    finally:
+        neurecon_b200.set_precision("fp16")

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
 // dW[N, K] += G[rows, N]^T X[rows, K]
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTnStages = 3;
-constexpr uint32_t kTnABytes = 64 * 128 * 2;    // [64 rows x 128 cols]  16 KB, two 64-column blocks 8 KB apart
+constexpr uint32_t kTnABytes = 64 * 256 * 2;    // [64 rows x 256 cols]  32 KB: both 128-row M-tiles of dW, four blocks 8 KB apart
 constexpr uint32_t kTnBBytes = 64 * 256 * 2;    // [64 rows x 256 cols]  32 KB, four blocks 8 KB apart
 constexpr uint32_t kTnLbo = 8192;
 
@@ -215,7 +215,7 @@ template <bool kF16>
 __global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const TnArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                                   // kTnStages x 16 KB
+  uint8_t* sA = smem;                                   // kTnStages x 32 KB
   uint8_t* sB = smem + kTnStages * kTnABytes;           // kTnStages x 32 KB
   uint64_t* bars = (uint64_t*)(sB + kTnStages * kTnBBytes);
   uint64_t* full = bars;                 // [kTnStages] 128 loader threads
@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const TnArgs g) {
   uint64_t* acc_ready = bars + 2 * kTnStages;
   __shared__ uint32_t tmem_base_s;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * 128, n0 = blockIdx.z * 256;
+  const int m0 = blockIdx.y * 256, n0 = blockIdx.z * 256;
+  const bool two_mt = m0 + 128 < g.N;                               // second 128-row M-tile of dW present
   const int ncols = min(256, (g.K - n0 + 15) / 16 * 16);            // MMA N of this CTA
   const int64_t n_chunks = (g.rows + 63) / 64;
   const int64_t c_begin = blockIdx.x * g.chunks_per_slice;
@@ -234,14 +235,14 @@ __global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const TnArgs g) {
     umma::mbar_init(acc_ready, 1);
     umma::fence_barrier_init();
   }
-  if (warp == 4) { umma::tmem_alloc(&tmem_base_s, 256); umma::tmem_relinquish(); }
+  if (warp == 4) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (c_begin >= c_end) {                 // empty slice (uniform for the CTA)
     __syncthreads();
-    if (warp == 4) umma::tmem_dealloc(tmem_base, 256);
+    if (warp == 4) umma::tmem_dealloc(tmem_base, 512);
     return;
   }
 
@@ -258,12 +259,12 @@ __global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const TnArgs g) {
       const float* xrow = g.X + (size_t)row * g.ldx;
       uint8_t* a_dst = sA + st * kTnABytes;
       uint8_t* b_dst = sB + st * kTnBBytes;
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {        // G: 64 of the 128 M columns
-        const int col = m0 + 64 * h + 8 * c8;
+      for (int c8 = 0; c8 < 16; ++c8) {       // G: 128 of the <= 256 M columns
+        if (128 * h >= 128 && !two_mt) break;
+        const int col = m0 + 128 * h + 8 * c8;
         float4 a, b;
         load8(grow + col, rok ? g.N - col : 0, a, b);
-        *reinterpret_cast<uint4*>(a_dst + umma::b_chunk_offset(r, 8 * h + c8, kTnLbo)) = pack8<kF16>(a, b);
+        *reinterpret_cast<uint4*>(a_dst + umma::b_chunk_offset(r, 16 * h + c8, kTnLbo)) = pack8<kF16>(a, b);
       }
       for (int c8 = 0; c8 < 16; ++c8) {       // X: 128 of the <= 256 N columns
         const int cb = 128 * h + 8 * c8;
@@ -289,8 +290,12 @@ __global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const TnArgs g) {
       const uint32_t a_lo = a_lo0 + st * (kTnABytes >> 4), b_lo = b_lo0 + st * (kTnBBytes >> 4);
       if (umma::elect_one()) {
 #pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks)      // 16 rows = two 8-row groups = 2048 bytes per k-step
+        for (uint32_t ks = 0; ks < 4; ++ks) {    // 16 rows = two 8-row groups = 2048 bytes per k-step
           umma::mma_bf16_ss(tmem_base, umma::desc64(a_lo + 128 * ks, hi), umma::desc64(b_lo + 128 * ks, hi), idesc, (cnt | ks) ? 1u : 0u);
+          if (two_mt)                            // M-tile 1 = column blocks 2, 3 of the A stage (+16 KB), accumulator +256
+            umma::mma_bf16_ss(tmem_base + 256u, umma::desc64(a_lo + 1024 + 128 * ks, hi), umma::desc64(b_lo + 128 * ks, hi), idesc,
+                              (cnt | ks) ? 1u : 0u);
+        }
         umma::mma_commit(&empty[st]);
       }
       __syncwarp();
@@ -302,22 +307,24 @@ __global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const TnArgs g) {
     const int q = warp & 3;
     umma::mbar_wait(acc_ready, 0);
     umma::tc_fence_after();
-    const int orow = m0 + 32 * q + lane;
-    float* drow = g.dW + (size_t)orow * g.lddw + n0;
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
-      uint32_t raw[16];
-      umma::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + c0, raw);
-      umma::tmem_ld_wait();
-      if (orow < g.N) {
+    for (int mt = 0; mt < (two_mt ? 2 : 1); ++mt) {
+      const int orow = m0 + 128 * mt + 32 * q + lane;
+      float* drow = g.dW + (size_t)orow * g.lddw + n0;
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t raw[16];
+        umma::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + 256u * mt + c0, raw);
+        umma::tmem_ld_wait();
+        if (orow < g.N) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n0 + c0 + j < g.K) atomicAdd(drow + c0 + j, __uint_as_float(raw[j]));
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < g.K) atomicAdd(drow + c0 + j, __uint_as_float(raw[j]));
+        }
       }
     }
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 4) umma::tmem_dealloc(tmem_base, 256);
+  if (warp == 4) umma::tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
@@ -366,7 +373,7 @@ extern "C" int nr_gemm_tn_tc(const float* G, int32_t ldg, const float* X, int32_
   int dev = 0, sms = 0;
   NR_CHECK_CUDA(cudaGetDevice(&dev));
   NR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int n_mt = (N + 127) / 128, n_nt = (K + 255) / 256;
+  const int n_mt = (N + 255) / 256, n_nt = (K + 255) / 256;
   const int64_t n_chunks = nr_cdiv(rows, 64);
   int64_t slices = (2 * sms) / (n_mt * n_nt);
   if (slices < 1) slices = 1;

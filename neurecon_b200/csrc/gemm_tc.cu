@@ -50,6 +50,27 @@ __device__ __forceinline__ void load8(const float* p, int valid, float4& a, floa
   a = make_float4(t[0], t[1], t[2], t[3]); b = make_float4(t[4], t[5], t[6], t[7]);
 }
 
+// 64 consecutive floats of a row -> eight 16-byte chunks of 8 converted values each.  Fast path (everything readable):
+// all 16 vector loads are issued before the first conversion, so a thread keeps 16 requests in flight instead of 2 --
+// the loaders are latency-bound otherwise (measured: 15x).  `valid` = readable elements from p.
+template <bool kF16>
+__device__ __forceinline__ void load64(const float* p, int valid, uint4 (&out)[8]) {
+  if (valid >= 64) {
+    float4 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float4*>(p + 4 * j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = pack8<kF16>(v[2 * j], v[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 a, b;
+      load8(p + 8 * j, valid - 8 * j, a, b);
+      out[j] = pack8<kF16>(a, b);
+    }
+  }
+}
+
 template <bool kF16>
 __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -95,15 +116,12 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
       const float* arow = g.A + (size_t)row * g.lda;
       for (int kc = 0; kc < g.n_kc; ++kc, ++cnt) {
         const uint32_t st = cnt % kAStages, ph = (cnt / kAStages) & 1u;
-        umma::mbar_wait(&a_empty[st], ph ^ 1u);
         uint8_t* dst = sA + st * kAStageBytes + r * 128;
+        uint4 ch[8];
+        load64<kF16>(arow + kc * kKC, row < g.M ? g.K - kc * kKC : 0, ch);    // global loads first, then the slot
+        umma::mbar_wait(&a_empty[st], ph ^ 1u);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          const int k0 = kc * kKC + c8 * 8;
-          float4 a, b;
-          load8(arow + k0, row < g.M ? g.K - k0 : 0, a, b);
-          *reinterpret_cast<uint4*>(dst + ((c8 ^ (r & 7)) << 4)) = pack8<kF16>(a, b);
-        }
+        for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(dst + ((c8 ^ (r & 7)) << 4)) = ch[c8];
         umma::fence_proxy_async_smem();
         umma::mbar_arrive(&a_full[st]);
       }
@@ -209,6 +227,7 @@ struct TnArgs {
   int64_t rows; int N, K;
   float* dW; int lddw;
   int64_t chunks_per_slice;
+  int vec4;
 };
 
 template <bool kF16>
@@ -259,20 +278,25 @@ __global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const TnArgs g) {
       const float* xrow = g.X + (size_t)row * g.ldx;
       uint8_t* a_dst = sA + st * kTnABytes;
       uint8_t* b_dst = sB + st * kTnBBytes;
-      for (int c8 = 0; c8 < 16; ++c8) {       // G: 128 of the <= 256 M columns
-        if (128 * h >= 128 && !two_mt) break;
-        const int col = m0 + 128 * h + 8 * c8;
-        float4 a, b;
-        load8(grow + col, rok ? g.N - col : 0, a, b);
-        *reinterpret_cast<uint4*>(a_dst + umma::b_chunk_offset(r, 16 * h + c8, kTnLbo)) = pack8<kF16>(a, b);
+      // G: 128 of the <= 256 M columns, X: 128 of the <= 256 N columns, 64 floats at a time
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (h == 1 && !two_mt) break;
+        const int col = m0 + 128 * h + 64 * half;
+        uint4 ch[8];
+        load64<kF16>(grow + col, rok ? g.N - col : 0, ch);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(a_dst + umma::b_chunk_offset(r, 16 * h + 8 * half + c8, kTnLbo)) = ch[c8];
       }
-      for (int c8 = 0; c8 < 16; ++c8) {       // X: 128 of the <= 256 N columns
-        const int cb = 128 * h + 8 * c8;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int cb = 128 * h + 64 * half;
         if (cb >= ncols) break;
         const int col = n0 + cb;
-        float4 a, b;
-        load8(xrow + col, rok ? g.K - col : 0, a, b);
-        *reinterpret_cast<uint4*>(b_dst + umma::b_chunk_offset(r, 16 * h + c8, kTnLbo)) = pack8<kF16>(a, b);
+        uint4 ch[8];
+        load64<kF16>(xrow + col, rok ? g.K - col : 0, ch);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(b_dst + umma::b_chunk_offset(r, 16 * h + 8 * half + c8, kTnLbo)) = ch[c8];
       }
       umma::fence_proxy_async_smem();
       umma::mbar_arrive(&full[st]);
@@ -316,8 +340,17 @@ __global__ void __launch_bounds__(288, 1) gemm_tn_tc_kernel(const TnArgs g) {
         umma::tmem_ld_wait();
         if (orow < g.N) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + c0 + j < g.K) atomicAdd(drow + c0 + j, __uint_as_float(raw[j]));
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int col = n0 + c0 + 4 * j4;
+            if (col + 4 <= g.lddw && g.vec4) {        // 16-byte vector reduction (pad columns receive + 0)
+              atomicAdd(reinterpret_cast<float4*>(drow + c0 + 4 * j4),
+                        make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]), __uint_as_float(raw[4 * j4 + 2]),
+                                    __uint_as_float(raw[4 * j4 + 3])));
+            } else {
+              for (int j = 0; j < 4; ++j)
+                if (col + j < g.K) atomicAdd(drow + c0 + 4 * j4 + j, __uint_as_float(raw[4 * j4 + j]));
+            }
+          }
         }
       }
     }
@@ -375,10 +408,10 @@ extern "C" int nr_gemm_tn_tc(const float* G, int32_t ldg, const float* X, int32_
   NR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int n_mt = (N + 255) / 256, n_nt = (K + 255) / 256;
   const int64_t n_chunks = nr_cdiv(rows, 64);
-  int64_t slices = (2 * sms) / (n_mt * n_nt);
+  int64_t slices = sms / (n_mt * n_nt);       // one CTA per SM: the fp32 reduction of the partial sums is the cost to amortise
   if (slices < 1) slices = 1;
   if (slices > n_chunks) slices = n_chunks;
-  TnArgs g{G, ldg, X, ldx, rows, N, K, dW, lddw, nr_cdiv(n_chunks, slices)};
+  TnArgs g{G, ldg, X, ldx, rows, N, K, dW, lddw, nr_cdiv(n_chunks, slices), ((((uintptr_t)dW) & 15) == 0 && (lddw & 3) == 0) ? 1 : 0};
   slices = nr_cdiv(n_chunks, g.chunks_per_slice);
   const size_t smem = 1024 + kTnStages * (kTnABytes + kTnBBytes) + 128;
   dim3 grid((unsigned)slices, n_mt, n_nt);

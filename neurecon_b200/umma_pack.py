@@ -17,6 +17,18 @@ def _a_tile_index():
     return _A_IDX
 
 
+_A_IDX_DEV = {}
+
+
+def _a_tile_index_on(device):
+    """The tile index on `device`, uploaded once (the weights are re-packed after every optimiser step; a host-to-device
+    copy per call would also break CUDA-graph capture of a training step)."""
+    key = str(device)
+    if key not in _A_IDX_DEV:
+        _A_IDX_DEV[key] = _a_tile_index().to(device).reshape(-1)
+    return _A_IDX_DEV[key]
+
+
 def pack_a_tiles(W, n_mtiles=None, k_pad=None, dtype=torch.bfloat16):
     """W: [rows, K] float tensor -> int16 tensor [n_kchunks * n_mtiles, 8192] of A tiles ordered
     (k-chunk major, M-tile minor: the order the two MMA-issuing warps consume them);
@@ -29,7 +41,7 @@ def pack_a_tiles(W, n_mtiles=None, k_pad=None, dtype=torch.bfloat16):
     full[:rows, :K] = W.float()
     bf = full.to(dtype).view(torch.int16)
     tiles = bf.reshape(n_mt, 128, n_kc, 64).permute(2, 0, 1, 3).reshape(n_kc * n_mt, 128 * 64)
-    idx = _a_tile_index().to(W.device).reshape(-1)
+    idx = _a_tile_index_on(W.device)
     out = torch.empty_like(tiles)
     out[:, idx] = tiles
     return out.contiguous()

@@ -149,6 +149,9 @@ def workload_config(precision):
             "l2_policy": "inputs and intermediates per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
+NCU_DRAM_BYTES_PER_LAUNCH = 13689344   # see roofline.traffic_source
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,7 +270,11 @@ def main():
     k_ms = e0.elapsed_time(e1) / reps
     achieved = n_pts * MFLOP_PER_QUERY_NABLA * 1e6 / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " bf16 burst",
+                "frac": achieved / pk["bf16"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH if precision != "fp32" else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch "
+                                  "(524288 points, profiles/mlp_umma_r1_ncu_524288.txt): 13.7 MB read, 0 written inside the "
+                                  "kernel window (the 8.4 MB of outputs leave the L2 later); algorithmic 14.7 MB",
+                "peak_source": pk["src"] + " bf16 burst",
                 "kernel": "%s: sdf + analytic nabla of %d points, %d launch(es), %.3f ms; algorithmic 1.967 "
                           "MFLOP/query (forward-mode tangents execute 4.2 MFLOP/query on the tensor pipe)"
                           % ("mlp_umma_kernel (fused tcgen05, %s operands)" % precision if precision != "fp32"

@@ -23,13 +23,9 @@
 
 namespace {
 
-#ifndef NR_EXP_STAGES
-#define NR_EXP_STAGES 4
-#endif
-constexpr int kStages = NR_EXP_STAGES;
+constexpr int kStages = 4;             // weight-ring depth (3 / 4 / 5 measured: profiles/mlp_umma_r1_history.md; 5 does not fit with the stash)
 constexpr int kStagesLog2 = 2;
 static_assert(kStages == (1 << kStagesLog2), "the ring position arithmetic assumes a power-of-two ring");
-constexpr int kStashCopies = NR_EXP_STAGES > 4 ? 1 : 2;   // experiment only: >4 stages share one stash (wrong results)
 constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilogue warps
 constexpr int kEpiPerTile = 256;
 constexpr int kEpiWarpsPerTile = 8;
@@ -49,7 +45,7 @@ struct SmemLayout {
   static constexpr uint32_t vs = xs + 2 * 512 * 4;                   // 2 x 128 x 3 floats (view dirs)
   static constexpr uint32_t nabs = vs + 2 * 384 * 4;                 // 2 x 128 x 3 floats (normal stash)
   static constexpr uint32_t pes = nabs + 2 * 384 * 4;                // 2 x 40 rows x 256 B: embedding stash (skip)
-  static constexpr uint32_t bars = pes + kStashCopies * kPeStashRows * 256;     // mbarriers
+  static constexpr uint32_t bars = pes + 2 * kPeStashRows * 256;     // mbarriers
   static constexpr uint32_t total = bars + 256;
 };
 
@@ -222,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
       float* xs = (float*)(smem + SmemLayout::xs) + t * 512;
       float* vs = (float*)(smem + SmemLayout::vs) + t * 384;
       float* nabs = (float*)(smem + SmemLayout::nabs) + t * 384;
-      uint8_t* pes = smem + SmemLayout::pes + (kStashCopies > 1 ? t : 0) * (kPeStashRows * 256);
+      uint8_t* pes = smem + SmemLayout::pes + t * (kPeStashRows * 256);
 
       // ---- prologue: stage the points, evaluate the embedding into operand rows [0, k0) ----
       for (int i = etid; i < ppt * 3; i += kEpiPerTile) {
@@ -303,13 +299,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         float* xs = (float*)(smem + SmemLayout::xs) + t * 512;
         float* vs = (float*)(smem + SmemLayout::vs) + t * 384;
         float* nabs = (float*)(smem + SmemLayout::nabs) + t * 384;
-        uint8_t* pes = smem + SmemLayout::pes + (kStashCopies > 1 ? t : 0) * (kPeStashRows * 256);
+        uint8_t* pes = smem + SmemLayout::pes + t * (kPeStashRows * 256);
         const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
-#if defined(NR_ACC_SLEEP_NS)
-        umma::mbar_wait_backoff(&acc_ready[t], (acc_par >> t) & 1u, NR_ACC_SLEEP_NS, NR_ACC_POLL_NS);
-#else
         umma::mbar_wait(&acc_ready[t], (acc_par >> t) & 1u);
-#endif
         acc_par ^= 1u << t;
         umma::tc_fence_after();
         if (tracer) trace_ev(a.trace, 2, tcnt, 21, s * 2 + t, pair);

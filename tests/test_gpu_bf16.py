@@ -136,3 +136,30 @@ def test_nerfpp_net_tensor_tier_vs_fp32():
             for a_, b_ in zip(out[tier], out["fp32"]):
                 assert a_.shape == b_.shape and torch.isfinite(a_).all()
                 assert rel_err(a_, b_) < tol, (tier, n, rel_err(a_, b_))
+
+
+def test_split_radiance_chunking_and_ragged_sizes():
+    """query_radiance's two-launch form (geometry + feature image, then the radiance net on 128-point tiles) must not depend
+    on where the per-launch chunk boundary falls, nor on n % 128 / n % 32."""
+    from neurecon_b200.models import base
+    from conftest import build_neus
+    m = build_neus(seed=1, device=DEV)
+    n = 128 * 9 + 37
+    x = (torch.rand(n, 3, device=DEV) - 0.5) * 1.6
+    v = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+    old = base._SPLIT_POINTS
+    try:
+        with torch.no_grad():
+            want = query_radiance(m.implicit_surface, m.radiance_net, x, v)
+            for chunk in (128, 384, 1024):
+                base._SPLIT_POINTS = chunk
+                got = query_radiance(m.implicit_surface, m.radiance_net, x, v)
+                for a_, b_ in zip(got, want):
+                    assert torch.equal(a_, b_), chunk
+            base._SPLIT_POINTS = old
+            for k in (1, 31, 33, 127, 129):
+                sub = query_radiance(m.implicit_surface, m.radiance_net, x[:k], v[:k])
+                for a_, b_ in zip(sub, want):
+                    assert rel_err(a_, b_[:k]) < 1e-6, k
+    finally:
+        base._SPLIT_POINTS = old

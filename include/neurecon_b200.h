@@ -367,6 +367,10 @@ int nr_adam_step(const void* table, int32_t n_tensors, float lr, float beta1, fl
 #define NR_UMMA_EPI_FEAT 2    /* geometry feature rows: to global and/or the radiance operand */
 #define NR_UMMA_EPI_RELU 3    /* radiance hidden layer */
 #define NR_UMMA_EPI_RGB 4     /* sigmoid, 3 rows, to global */
+#define NR_UMMA_EPI_EXTRAS 5  /* split-K layer: refill the operand rows with the second operand, next step accumulates */
+#define NR_UMMA_EPI_LINEAR 6  /* bias only, next operand in shared memory */
+#define NR_UMMA_EPI_BWD 7     /* reverse mode: next operand = softplus'(z) of slot sig_slot times the accumulator (W^T g) */
+#define NR_UMMA_EPI_NABLA 8   /* reverse mode, last step: accumulator rows = d sdf / d PE(x); embedding Jacobian -> nabla */
 
 typedef struct {
   int32_t chunk_begin; /* first 16 KB weight chunk of this step; chunks ordered (k-chunk major, M-tile minor) */
@@ -380,6 +384,9 @@ typedef struct {
   int32_t to_rad;      /* EPI_FEAT: also build the radiance operand [feat | PE(x) | PE(view) | normals];
                           EPI_EXTRAS: which rows to write: 0 = the radiance extras, 1 = PE(x), 2 = PE(view) */
   int32_t accumulate;  /* 1: the step's MMAs add onto the previous step's accumulators (split-K over two operands) */
+  int32_t sig_slot;    /* reverse mode: the 64 KB scratch slot of softplus'(z) this step writes (EPI_HIDDEN) or applies
+                          (EPI_BWD, EPI_SDF_OUT) */
+  int32_t aux_off;     /* reverse-mode EPI_SDF_OUT: offset in the bias table of the 256 fp32 weights of the sdf row */
 } nr_umma_step_t;
 
 typedef struct {
@@ -396,6 +403,7 @@ typedef struct {
                                 2: NeRF++ background net on 128-point tiles: x = [n, input_dim] points, operand rows
                                 [0, K0) = PE(x) (multires), view dirs embedded with rad_multires_view */
   int32_t input_dim;         /* components of a point (3; 4 for the NeRF++ inverted-sphere parametrisation) */
+  int32_t reverse;           /* 1: reverse-mode normals program for nr_mlp_umma_reverse (128-point value tiles) */
   nr_umma_step_t steps[NR_UMMA_MAX_STEPS];
 } nr_umma_program_t;
 
@@ -410,6 +418,18 @@ int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t
                         const float* bias, size_t bias_floats, const float* x, const float* view,
                         int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
                         const float* normal_scale, void* feat_img, void* stream);
+
+/* sdf + d sdf / d x (+ feature) with REVERSE-mode normals, the arithmetic of ImplicitSurface.forward_with_nablas'
+ * autograd.grad (models/base.py:265-282): hidden layers forward on 128-point tiles, softplus' of every unit parked in
+ * `workspace` (device memory, nr_mlp_umma_reverse_workspace bytes, contents irrelevant before and after), then the
+ * backward sweep from the sdf row to the embedding on the same tiles.  Program: reverse = 1, steps EPI_HIDDEN x L
+ * (sig_slot = layer), optional EPI_FEAT, EPI_SDF_OUT (aux_off = the sdf row's weights), EPI_BWD x (L-1) whose chunks
+ * hold W_l^T (pe_fill marks the skip layer), EPI_NABLA with W_0^T.  Outputs as nr_mlp_umma_forward; feat_img, if not
+ * NULL, receives the LAST HIDDEN activations as the radiance pass's operand image (to_rad on the last hidden step). */
+size_t nr_mlp_umma_reverse_workspace(const nr_umma_program_t* prog, int64_t n);
+int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* image, size_t image_bytes, const float* bias,
+                        size_t bias_floats, const float* x, int64_t n, float* sdf, float* nabla, float* feat,
+                        int64_t feat_ld, void* feat_img, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The same network on CTA pairs (tcgen05.mma.cta_group::2, 2-CTA clusters): programs made of EPI_HIDDEN,
  * EPI_SDF_OUT and EPI_FEAT (to_rad = 0) steps whose weight chunks all come as M-tile pairs (n_mt = 2; the sdf row

@@ -45,12 +45,12 @@ NR_UMMA_MAX_STEPS = 24
 
 class UmmaStep(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("chunk_begin", "n_mt", "k_steps", "n_cols", "epi", "bias_off", "out_rows",
-                                         "pe_fill", "to_rad", "accumulate")]
+                                         "pe_fill", "to_rad", "accumulate", "sig_slot", "aux_off")]
 
 
 class UmmaProgram(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_steps", "tangents", "multires", "rad_multires", "rad_multires_view",
-                                         "rad_extra_rows", "operand_f16", "debug_flags", "input_mode", "input_dim")] + [("steps", UmmaStep * NR_UMMA_MAX_STEPS)]
+                                         "rad_extra_rows", "operand_f16", "debug_flags", "input_mode", "input_dim", "reverse")] + [("steps", UmmaStep * NR_UMMA_MAX_STEPS)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -100,6 +100,8 @@ _SIGNATURES = {
     "nr_sphere_trace_step": (C.c_int, [_P, _P, _P, _F, _I64, _P, _P, _P, _P]),
     "nr_unisurf_composite": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "nr_mlp_umma_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "nr_mlp_umma_reverse_workspace": (_SZ, [C.POINTER(UmmaProgram), _I64]),
+    "nr_mlp_umma_reverse": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _I64, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
     "nr_neus_loss": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _P, _P, _P, _P, _P, _P]),
     "nr_grad_sqsum": (C.c_int, [_P, _I32, _P, _P]),
     "nr_adam_step": (C.c_int, [_P, _I32, _F, _F, _F, _F, _I64, _P]),

@@ -20,6 +20,8 @@ enum : int32_t {
   EPI_EXTRAS = 5,   // no accumulator read: operand rows [0, K of the next step) <- the second operand of a split-K layer
                     // (to_rad 0: [PE(x)|PE(view)|normals|0] of the radiance net, 1: PE(x), 2: PE(view)); next step accumulates
   EPI_LINEAR = 6,   // bias only (NeRF++ feature_linear), next operand in smem
+  EPI_BWD = 7,      // reverse mode (mlp_rev.cu): next operand = softplus'(z) * accumulator
+  EPI_NABLA = 8,    // reverse mode, last step: embedding Jacobian, nabla to global
 };
 
 struct DevProgram {

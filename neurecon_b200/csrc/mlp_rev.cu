@@ -1,0 +1,605 @@
+// Fused positional-encoding + SDF MLP + REVERSE-MODE analytic normals on tcgen05 / TMEM.
+//
+// Same machine as mlp_umma.cu (weights = A operand streamed through a 4-stage ring, activations = B operand resident
+// in shared memory, accumulators in TMEM, two 128-point tiles ping-ponging through mbarriers, 640 threads), but the
+// normal  d sdf / d x  is computed the way autograd does it (models/base.py:265-282): one forward pass that remembers
+// softplus'(z) of every hidden unit, then one backward pass  g_{l-1} = softplus'(z_{l-1}) * (W_l^T g_l)  from the sdf
+// row down to the embedding, whose Jacobian is applied in the last epilogue.  The forward-mode kernel pushes three
+// tangent columns per point through every layer (4.03 MFLOP per query on the tensor pipe, 32 points per tile); this
+// one executes 2.0 MFLOP per query on full 128-point tiles and halves the activation traffic through shared memory.
+//
+// The 8 x 256 derivatives per point (16-bit) do not fit on chip next to the operands (512 KB per tile), so they go
+// through a per-CTA scratch in global memory: 64 KB per (tile slot, layer), written by the forward epilogue and read
+// back a few microseconds later by THE SAME THREAD in the backward epilogue (no fences needed), 148 MB for the whole
+// grid, i.e. mostly L2 hits; the rest is HBM traffic the kernel has no other use for (7 KB per point at worst).
+// The loads are issued before the thread waits for its accumulator, so their latency hides under the MMAs.
+//
+// Steps (nr_umma_program_t, reverse = 1): EPI_HIDDEN x L (sig_slot = layer), [EPI_FEAT], EPI_SDF_OUT (sdf to global,
+// then operand <- softplus'(z_{L-1}) * w_sdf), EPI_BWD x (L-1) (A = W_l^T; the skip layer's embedding rows go to the
+// stash), EPI_NABLA (A = W_0^T; (acc + stash) * dPE/dx summed over the embedding rows -> nabla).
+#include "mlp_epilogue.cuh"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kStagesLog2 = 2;
+constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilogue warps
+constexpr int kEpiPerTile = 256;
+constexpr int kEpiWarpsPerTile = 8;
+constexpr int kEpiWarp0 = 4;
+constexpr uint32_t kSigBytes = 65536;    // softplus' of one layer of one tile: [8 column chunks][256 features][16 x 16-bit]
+constexpr int kRedLd = 41;               // row stride (floats) of the embedding-gradient scratch: conflict-free both ways
+
+struct SmemRev {
+  static constexpr uint32_t act = 0;                                 // 2 x 64 KB
+  static constexpr uint32_t ring = 2 * kActBytes;                    // kStages x 16 KB
+  static constexpr uint32_t xs = ring + kStages * kChunkBytes;       // 2 x 128 x 3 floats
+  static constexpr uint32_t pes = xs + 2 * 512 * 4;                  // 2 x 40 rows x 256 B: embedding / skip-gradient stash
+  static constexpr uint32_t bars = pes + 2 * kPeStashRows * 256;
+  static constexpr uint32_t total = bars + 256;
+};
+static_assert(128 * kRedLd * 4 <= kActBytes, "embedding-gradient scratch must fit in the tile's operand buffer");
+
+struct RevArgs {
+  const uint8_t* image;
+  const float* bias;
+  const float* x;      // [n,3]
+  int64_t n;
+  float* sdf;          // [n] or null
+  float* nabla;        // [n,3]
+  float* feat;         // [n, feat_ld] or null
+  int64_t feat_ld;
+  uint8_t* feat_img;   // null, or [ceil(n/128)][64 KB]: last hidden activations as the radiance pass's operand image
+  uint8_t* sig;        // [grid][2][n_sig][64 KB]
+  int n_sig;
+};
+
+__device__ __forceinline__ void publish(uint64_t* bar) {
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar);
+}
+
+// Bounded wait with a tag: a protocol bug traps within ~0.1 s and says where.
+__device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, int tag) {
+  if (umma::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+#pragma unroll 1
+  while (clock64() - t0 < 200000000ll)
+    if (umma::mbar_try_wait(bar, parity)) return;
+  if ((threadIdx.x & 31) == 0)
+    printf("neurecon_b200: mlp_rev wait %d timed out (block %d warp %d)\n", tag, blockIdx.x, threadIdx.x >> 5);
+  __trap();
+}
+
+template <bool kF16>
+__device__ __forceinline__ uint32_t mul16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  if (kF16) asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  else asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint4 ldcg16(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stcg16(uint8_t* p, uint4 v) { __stcg(reinterpret_cast<uint4*>(p), v); }
+
+// kCluster > 1: the CTAs of a cluster consume the same weight stream in loose lock-step and every 16 KB chunk is read
+// from L2 ONCE per cluster: CTA (chunk % kCluster) issues a multicast bulk copy into the same ring stage of all of them.
+// A stage is refilled when every CTA's MMAs have released it (tcgen05.commit multicast onto w_empty of all CTAs, count
+// kCluster); each CTA arms its own w_full.  The weight stream, re-read per 128-point tile, is what saturates the L2
+// (~6300 B/clk for the chip, B300_MICROARCH.md) long before the tensor pipe: 2 MB per tile pass.
+template <bool kF16, int kCluster>
+__global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + SmemRev::bars);
+  uint64_t* w_full = bars;                   // [kStages]
+  uint64_t* w_empty = bars + kStages;        // [kStages]
+  uint64_t* in_ready = bars + 2 * kStages;   // [2]
+  uint64_t* acc_ready = in_ready + 2;        // [2]
+  __shared__ uint32_t tmem_base_s;
+
+  const nr_umma_program_t& P = prog.p;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int64_t n_tiles = (a.n + 127) / 128;
+  // every CTA runs the same number of tile pairs (tiles past the end compute on zeros and store nothing): the CTAs of a
+  // cluster must consume identical weight streams
+  const int64_t n_pairs = ((n_tiles + 1) / 2 + gridDim.x - 1) / gridDim.x * gridDim.x;
+  const uint32_t rank = kCluster > 1 ? umma::cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1u);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], kCluster); }
+    for (int t = 0; t < 2; ++t) {
+      umma::mbar_init(&in_ready[t], kEpiWarpsPerTile);
+      umma::mbar_init(&acc_ready[t], 2);
+    }
+    umma::fence_barrier_init();
+  }
+  if (warp == 2) {
+    umma::tmem_alloc(&tmem_base_s, 512);
+    umma::tmem_relinquish();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (kCluster > 1) umma::cluster_sync_all();   // nobody signals a peer's barrier before it exists
+  umma::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    uint32_t cnt = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int s = 0; s < P.n_steps; ++s) {
+        const int nch = P.steps[s].n_mt * (P.steps[s].k_steps >> 2);
+        const uint8_t* src = a.image + (size_t)P.steps[s].chunk_begin * kChunkBytes;
+        for (int t = 0; t < 2; ++t) {
+          for (int c = 0; c < nch; ++c, ++cnt) {
+            const uint32_t stage = cnt & (kStages - 1);
+            wait_tag(&w_empty[stage], ((cnt >> kStagesLog2) & 1u) ^ 1u, 1000 + s);
+            if (umma::elect_one()) {
+              umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
+              uint8_t* dst = smem + SmemRev::ring + stage * kChunkBytes;
+              if (kCluster == 1) umma::bulk_g2s(dst, src + (size_t)c * kChunkBytes, kChunkBytes, &w_full[stage]);
+              else if ((cnt & (kCluster - 1)) == rank)
+                umma::bulk_g2s_multicast(dst, src + (size_t)c * kChunkBytes, kChunkBytes, &w_full[stage], kMask);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers: warp 1 owns M-tile 0, warp 3 owns M-tile 1 (see mlp_umma.cu) ==============
+    const uint32_t my_mt = warp == 1 ? 0u : 1u;
+    uint32_t cnt = 0;
+    uint32_t in_par = 0;
+    const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
+    const uint32_t ring_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemRev::ring), 16);
+    const uint32_t act_lo0 = umma::smem_desc_lo(umma::smem_u32(smem + SmemRev::act), kLbo);
+    const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, 128, 0, 1) : umma::make_idesc_bf16(128, 128, 0, 1);
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int s = 0; s < P.n_steps; ++s) {
+        const uint32_t n_mt = P.steps[s].n_mt, nkc = P.steps[s].k_steps >> 2;
+        for (int t = 0; t < 2; ++t) {
+          wait_tag(&in_ready[t], (in_par >> t) & 1u, 2000 + s);
+          in_par ^= 1u << t;
+          umma::tc_fence_after();
+          if (my_mt < n_mt) {
+            const uint32_t d_addr = tmem_base + (uint32_t)t * 256u + my_mt * 128u;
+            uint32_t b_lo = act_lo0 + (uint32_t)t * (kActBytes >> 4);
+            uint32_t c = cnt + my_mt;
+#pragma unroll 1
+            for (uint32_t kc = 0; kc < nkc; ++kc, c += n_mt, b_lo += 512) {
+              const uint32_t st = c & (kStages - 1);
+              wait_tag(&w_full[st], (c >> kStagesLog2) & 1u, 3000 + s);
+              umma::tc_fence_after();
+              const uint32_t a_lo = ring_lo + st * (kChunkBytes >> 4);
+              if (umma::elect_one()) {
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, kc ? 1u : 0u);
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
+                umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
+                if (kCluster == 1) umma::mma_commit(&w_empty[st]);
+                else umma::mma_commit_mc(&w_empty[st], kMask);
+              }
+              __syncwarp();
+            }
+          }
+          if (umma::elect_one()) umma::mma_commit(&acc_ready[t]);
+          __syncwarp();
+          cnt += n_mt * nkc;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue: warps 4-11 own tile slot 0, warps 12-19 tile slot 1 =====================
+    const int e = warp - kEpiWarp0;                 // 0..15
+    const int t = e >> 3;                           // tile slot
+    const int mo = (e >> 2) & 1;                    // M-tile this warpgroup owns
+    const int q = warp & 3;                         // TMEM lane quarter (hardware: warp id % 4)
+    const int etid = (e & 7) * 32 + lane;           // 0..255 inside the group
+    const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
+    uint32_t acc_par = 0;
+    const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
+    uint8_t* act = smem + SmemRev::act + t * kActBytes;
+    float* xs = (float*)(smem + SmemRev::xs) + t * 512;
+    uint8_t* pes = smem + SmemRev::pes + t * (kPeStashRows * 256);
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256 + mo * 128);
+    const RowAddr ra(umma::smem_u32(act), F);
+    uint8_t* sig_tile = a.sig + ((size_t)blockIdx.x * 2 + t) * a.n_sig * kSigBytes + (size_t)F * 32;
+
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + t;
+      const int64_t p0 = tile * 128;
+
+      // ---- prologue: stage the points, evaluate the embedding into operand rows [0, k0) and the stash ----
+      for (int i = etid; i < 384; i += kEpiPerTile) {
+        const int64_t gi = p0 * 3 + i;
+        xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
+      }
+      named_bar_sync(1 + t, kEpiPerTile);
+      {
+        const int n = etid & 127;                      // operand column = point
+        const int part = etid >> 7;                    // 0..1: splits the rows
+        const float x3[3] = {xs[3 * n], xs[3 * n + 1], xs[3 * n + 2]};
+        const int k0 = P.steps[0].k_steps * 16;
+        uint16_t* stash = reinterpret_cast<uint16_t*>(pes) + n;   // row j at stash[j * 128]
+        auto put = [&](int j, float val) {
+          store_elem<kF16>(act, j, n, val);
+          if (j < kPeStashRows) stash[j * 128] = umma::pack1<kF16>(val);
+        };
+        if (part == 0) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) put(j, x3[j]);
+        }
+        for (int qf = part; qf < P.multires; qf += 2) {
+          const float f = (float)(1 << qf);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sn, cs;
+            __sincosf(x3[c] * f, &sn, &cs);
+            put(3 + 6 * qf + c, sn);
+            put(3 + 6 * qf + 3 + c, cs);
+          }
+        }
+        for (int j = pe_dim + part; j < k0; j += 2) store_elem<kF16>(act, j, n, 0.f);
+      }
+      publish(&in_ready[t]);
+
+      for (int s = 0; s < P.n_steps; ++s) {
+        const nr_umma_step_t& S = P.steps[s];
+        const bool mine = mo < S.n_mt;
+        const bool is_h = F < S.out_rows;
+        const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
+        const uint8_t* sig_rd = sig_tile + (size_t)S.sig_slot * kSigBytes;   // EPI_BWD / EPI_SDF_OUT: the slot to apply
+
+        // softplus' of the first half of the columns: requested before the accumulator wait (latency under the MMAs)
+        uint4 sg[8];
+        const bool use_sig = ((S.epi == EPI_BWD && mine && is_h) || S.epi == EPI_SDF_OUT) && !(P.debug_flags & 2);
+        if (use_sig) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            sg[2 * c] = ldcg16(sig_rd + c * 8192);
+            sg[2 * c + 1] = ldcg16(sig_rd + c * 8192 + 16);
+          }
+        }
+
+        wait_tag(&acc_ready[t], acc_par, 4000 + s);
+        acc_par ^= 1u;
+        umma::tc_fence_after();
+
+        if (S.epi == EPI_HIDDEN) {
+          if (mine && !(P.debug_flags & 8)) {
+            const float b = a.bias[S.bias_off + F];
+            const f32x2 b144 = splat2(b * 144.26950408889634f);
+            const int jpe = F - S.out_rows;
+            uint8_t* sig_wr = sig_tile + (size_t)S.sig_slot * kSigBytes;
+            uint32_t raw[16], rawB[16];
+            auto values = [&](const uint32_t (&r)[16], int c) {
+              if (!is_pe) {
+                float v[16];
+                f32x2 d2[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  softplus_sig2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, v[2 * j], v[2 * j + 1], d2[j]);
+                store_row16<kF16>(ra, 16 * c, v);
+                if (S.to_rad && a.feat_img && tile < n_tiles) img_store16<kF16>(a.feat_img, tile, F, 16 * c, v);
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float lo, hi;
+                  upk2(d2[j], lo, hi);
+                  w[j] = umma::pack2<kF16>(lo, hi);
+                }
+                if (!(P.debug_flags & 1)) {
+                  stcg16(sig_wr + c * 8192, make_uint4(w[0], w[1], w[2], w[3]));
+                  stcg16(sig_wr + c * 8192 + 16, make_uint4(w[4], w[5], w[6], w[7]));
+                } else if (w[0] + w[1] + w[2] + w[3] + w[4] + w[5] + w[6] + w[7] == 0x12345u) {
+                  stcg16(sig_wr, make_uint4(w[0], w[1], w[2], w[3]));
+                }
+              } else {
+                copy_row16(ra, pes, jpe, 16 * c);
+              }
+            };
+            umma::tmem_ld16(taddr, raw);
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+              umma::tmem_ld_wait();
+              umma::tmem_ld16(taddr + 16 * (c + 1), rawB);
+              values(raw, c);
+              umma::tmem_ld_wait();
+              if (c + 2 < 8) umma::tmem_ld16(taddr + 16 * (c + 2), raw);
+              values(rawB, c + 1);
+            }
+          }
+        } else if (S.epi == EPI_FEAT) {
+          if (mine) {
+            const float b = a.bias[S.bias_off + F];
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+              uint32_t raw[16];
+              umma::tmem_ld16(taddr + 16 * c, raw);
+              umma::tmem_ld_wait();
+              if (a.feat && F < S.out_rows) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int64_t gp = p0 + 16 * c + j;
+                  if (gp < a.n) a.feat[gp * a.feat_ld + F] = __uint_as_float(raw[j]) + b;
+                }
+              }
+            }
+          }
+        } else if (S.epi == EPI_SDF_OUT) {
+          // rows 0..31 of M-tile 0 all hold the sdf row: lane l keeps column l of each 32-column chunk
+          if (mo == 0 && q == 0 && a.sdf) {
+            const float b = a.bias[S.bias_off];
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t raw[32];
+              umma::tmem_ld32(taddr + 32 * c, raw);
+              umma::tmem_ld_wait();
+              float m = 0.0f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m = (lane == j) ? __uint_as_float(raw[j]) : m;
+              const int64_t gp = p0 + 32 * c + lane;
+              if (gp < a.n) a.sdf[gp] = m + b;
+            }
+          }
+          // start of the backward pass: operand row F <- softplus'(z_last)[F, :] * w_sdf[F]  (d sdf / d z_last)
+          const uint32_t w1 = umma::pack1<kF16>(a.bias[S.aux_off + F]);
+          const uint32_t w2 = w1 | (w1 << 16);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 s0 = sg[2 * (c & 3)], s1 = sg[2 * (c & 3) + 1];
+            if (c < 4 && !(P.debug_flags & 2)) {
+              sg[2 * c] = ldcg16(sig_rd + (c + 4) * 8192);
+              sg[2 * c + 1] = ldcg16(sig_rd + (c + 4) * 8192 + 16);
+            }
+            st_shared_v4(ra.chunk(2 * c), mul16x2<kF16>(s0.x, w2), mul16x2<kF16>(s0.y, w2), mul16x2<kF16>(s0.z, w2),
+                         mul16x2<kF16>(s0.w, w2));
+            st_shared_v4(ra.chunk(2 * c + 1), mul16x2<kF16>(s1.x, w2), mul16x2<kF16>(s1.y, w2), mul16x2<kF16>(s1.z, w2),
+                         mul16x2<kF16>(s1.w, w2));
+          }
+        } else if (S.epi == EPI_BWD) {
+          if (mine && !(P.debug_flags & 4)) {
+            uint32_t raw[16], rawB[16];
+            const int jpe = F - S.out_rows;
+            auto apply = [&](const uint32_t (&r)[16], int c) {
+              uint32_t h[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) h[j] = umma::pack2<kF16>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+              if (is_h) {
+                const uint4 s0 = sg[2 * (c & 3)], s1 = sg[2 * (c & 3) + 1];
+                if (c < 4 && !(P.debug_flags & 2)) {
+                  sg[2 * c] = ldcg16(sig_rd + (c + 4) * 8192);
+                  sg[2 * c + 1] = ldcg16(sig_rd + (c + 4) * 8192 + 16);
+                }
+                st_shared_v4(ra.chunk(2 * c), mul16x2<kF16>(h[0], s0.x), mul16x2<kF16>(h[1], s0.y), mul16x2<kF16>(h[2], s0.z),
+                             mul16x2<kF16>(h[3], s0.w));
+                st_shared_v4(ra.chunk(2 * c + 1), mul16x2<kF16>(h[4], s1.x), mul16x2<kF16>(h[5], s1.y),
+                             mul16x2<kF16>(h[6], s1.z), mul16x2<kF16>(h[7], s1.w));
+              } else {
+                if (is_pe) {   // gradient w.r.t. the skip connection's copy of the embedding: kept for EPI_NABLA
+                  uint4* dst = reinterpret_cast<uint4*>(pes + jpe * 256 + c * 32);
+                  dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                  dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                }
+                st_shared_v4(ra.chunk(2 * c), 0, 0, 0, 0);       // these rows meet zero weights; keep them finite
+                st_shared_v4(ra.chunk(2 * c + 1), 0, 0, 0, 0);
+              }
+            };
+            umma::tmem_ld16(taddr, raw);
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+              umma::tmem_ld_wait();
+              umma::tmem_ld16(taddr + 16 * (c + 1), rawB);
+              apply(raw, c);
+              umma::tmem_ld_wait();
+              if (c + 2 < 8) umma::tmem_ld16(taddr + 16 * (c + 2), raw);
+              apply(rawB, c + 1);
+            }
+          }
+        } else if (S.epi == EPI_NABLA) {
+          // acc rows [0, pe_dim) = d sdf / d PE(x) through layer 0 (+ the skip layer's share from the stash);
+          // nabla_c = sum_j dPE_j/dx_c * g_j: products to a [point][row] scratch in the (now free) operand buffer
+          float* red = reinterpret_cast<float*>(act);
+          if (mo == 0 && 32 * q < pe_dim) {   // warp-uniform: the TMEM loads are .sync.aligned
+            const int comp = F < 3 ? F : (F - 3) % 3;
+            const int qf = F < 3 ? 0 : (F - 3) / 6;
+            const bool is_sin = F >= 3 && ((F - 3) % 6) < 3;
+            const float f = (float)(1 << qf);
+            const uint16_t* srow = reinterpret_cast<const uint16_t*>(pes + F * 256);
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+              uint32_t raw[16];
+              umma::tmem_ld16(taddr + 16 * c, raw);
+              umma::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = 16 * c + j;
+                float g = __uint_as_float(raw[j]);
+                if (S.pe_fill && F < pe_dim) {
+                  const uint16_t hv = srow[col];
+                  g += kF16 ? __half2float(__ushort_as_half(hv)) : __uint_as_float((uint32_t)hv << 16);
+                }
+                float jac = 1.0f;
+                if (F >= 3) {
+                  float sn, cs;
+                  __sincosf(xs[3 * col + comp] * f, &sn, &cs);
+                  jac = is_sin ? f * cs : -f * sn;
+                }
+                if (F < pe_dim) red[col * kRedLd + F] = g * jac;
+              }
+            }
+          }
+          named_bar_sync(1 + t, kEpiPerTile);
+          if (etid < 128) {
+            const float* r = red + etid * kRedLd;
+            float g0 = r[0], g1 = r[1], g2 = r[2];
+            for (int j = 3; j < pe_dim; j += 3) { g0 += r[j]; g1 += r[j + 1]; g2 += r[j + 2]; }
+            const int64_t gp = p0 + etid;
+            if (gp < a.n) { a.nabla[gp * 3] = g0; a.nabla[gp * 3 + 1] = g1; a.nabla[gp * 3 + 2] = g2; }
+          }
+        }
+        if (s + 1 < P.n_steps) publish(&in_ready[t]);
+      }
+      umma::tc_fence_before();
+      named_bar_sync(1 + t, kEpiPerTile);   // staging buffers and the TMEM slot are free before the next pair
+    }
+  }
+
+  umma::tc_fence_before();
+  __syncthreads();
+  if (kCluster > 1) umma::cluster_sync_all();   // peers may still multicast into this CTA's ring / arrive on its barriers
+  if (warp == 2) umma::tmem_dealloc(tmem_base, 512);
+}
+
+int count_sig_slots(const nr_umma_program_t* p) {
+  int n = 0;
+  for (int s = 0; s < p->n_steps; ++s)
+    if (p->steps[s].epi == EPI_HIDDEN) ++n;
+  return n;
+}
+
+}  // namespace
+
+extern "C" size_t nr_mlp_umma_reverse_workspace(const nr_umma_program_t* prog, int64_t n) {
+  if (!prog || n <= 0) return 0;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  (void)n;   // sized for the largest grid, so one buffer serves every n
+  return (size_t)sms * 2 * count_sig_slots(prog) * kSigBytes;
+}
+
+namespace {
+// Cluster size of the weight multicast: NEURECON_B200_REV_CLUSTER = 1 | 2 | 4 (default 1: measured no faster).
+int rev_cluster_size() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("NEURECON_B200_REV_CLUSTER");
+    v = e ? atoi(e) : 1;
+    if (v != 1 && v != 2 && v != 4) v = 1;
+  }
+  return v;
+}
+
+template <bool kF16, int kCluster>
+int launch_rev(const DevProgram& dp, const RevArgs& ka, int64_t n, int sms, cudaStream_t stream) {
+  auto kern = mlp_rev_kernel<kF16, kCluster>;
+  const size_t smem = SmemRev::total + 1024;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  NR_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    NR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev & 63] = true;
+  }
+  const int64_t n_pairs = (nr_cdiv(n, 128) + 1) / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kCluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = kCluster > 1 ? 1 : 0;
+  int max_ctas = sms;
+  if (kCluster > 1) {
+    static int max_clusters[64] = {};
+    if (!max_clusters[dev & 63]) {
+      cfg.gridDim = dim3((sms / kCluster) * kCluster);
+      int nc = 0;
+      NR_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
+      NR_CHECK_ARG(nc >= 1, "mlp_rev_kernel: no cluster of %d CTAs fits on this device", kCluster);
+      max_clusters[dev & 63] = nc;
+    }
+    max_ctas = max_clusters[dev & 63] * kCluster;
+  }
+  int64_t grid = nr_cdiv(n_pairs, kCluster) * kCluster;
+  if (grid > max_ctas) grid = max_ctas;
+  cfg.gridDim = dim3((unsigned)grid);
+  NR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, dp, ka));
+  NR_CHECK_LAUNCH("mlp_rev_kernel");
+  return NR_OK;
+}
+}  // namespace
+
+extern "C" int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
+                                   const float* bias, size_t bias_floats, const float* x, int64_t n, float* sdf,
+                                   float* nabla, float* feat, int64_t feat_ld, void* feat_img, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  NR_CHECK_ARG(prog && image && bias && x && nabla, "nr_mlp_umma_reverse: null pointer");
+  NR_CHECK_ARG(n >= 0, "nr_mlp_umma_reverse: n < 0");
+  NR_CHECK_ARG(prog->reverse == 1 && prog->tangents == 0 && prog->input_mode == 0,
+               "nr_mlp_umma_reverse: needs a reverse-mode program on value tiles");
+  NR_CHECK_ARG(prog->n_steps >= 3 && prog->n_steps <= NR_UMMA_MAX_STEPS, "nr_mlp_umma_reverse: n_steps=%d", prog->n_steps);
+  NR_CHECK_ARG(((uintptr_t)image & 15) == 0 && ((uintptr_t)workspace & 15) == 0 && ((uintptr_t)feat_img & 15) == 0,
+               "nr_mlp_umma_reverse: image, workspace and feat_img must be 16-byte aligned");
+  const int pe_dim = prog->multires < 0 ? 3 : 3 + 6 * prog->multires;
+  NR_CHECK_ARG(pe_dim <= kPeStashRows && pe_dim % 3 == 0, "nr_mlp_umma_reverse: embedding of %d rows", pe_dim);
+  NR_CHECK_ARG(prog->steps[0].k_steps * 16 >= pe_dim, "nr_mlp_umma_reverse: step 0 K does not cover the embedding");
+  const int n_sig = count_sig_slots(prog);
+  // order: hidden layers, optional feature, sdf row, backward layers, embedding Jacobian
+  int phase = 0, n_sdf = 0, n_nabla = 0;
+  for (int s = 0; s < prog->n_steps; ++s) {
+    const nr_umma_step_t& S = prog->steps[s];
+    const int nch = S.n_mt * (S.k_steps / 4);
+    NR_CHECK_ARG(S.k_steps % 4 == 0 && S.k_steps >= 4 && S.k_steps <= 16, "step %d: k_steps=%d", s, S.k_steps);
+    NR_CHECK_ARG(S.n_mt >= 1 && S.n_mt <= 2, "step %d: n_mt=%d", s, S.n_mt);
+    NR_CHECK_ARG(S.n_cols == 128 && !S.accumulate, "step %d: reverse-mode steps are 128 columns wide, no split-K", s);
+    NR_CHECK_ARG(S.chunk_begin >= 0 && (size_t)(S.chunk_begin + nch) * kChunkBytes <= image_bytes,
+                 "step %d: weight chunks [%d,%d) exceed the image", s, S.chunk_begin, S.chunk_begin + nch);
+    const bool last = s == prog->n_steps - 1;
+    switch (S.epi) {
+      case EPI_HIDDEN:
+        NR_CHECK_ARG(phase == 0 && S.sig_slot == s, "step %d: hidden layers come first, sig_slot = layer", s);
+        NR_CHECK_ARG(S.bias_off >= 0 && (size_t)S.bias_off + S.n_mt * 128 <= bias_floats, "step %d: bias range", s);
+        NR_CHECK_ARG(!S.pe_fill || S.out_rows + pe_dim <= S.n_mt * 128, "step %d: skip operand too wide", s);
+        break;
+      case EPI_FEAT:
+        NR_CHECK_ARG(phase == 0 && s > 0 && !S.to_rad, "step %d: EPI_FEAT follows the hidden layers", s);
+        NR_CHECK_ARG(S.bias_off >= 0 && (size_t)S.bias_off + S.n_mt * 128 <= bias_floats, "step %d: bias range", s);
+        break;
+      case EPI_SDF_OUT:
+        NR_CHECK_ARG(phase == 0 && s > 0 && S.n_mt == 1 && S.sig_slot == n_sig - 1, "step %d: EPI_SDF_OUT placement", s);
+        NR_CHECK_ARG(S.bias_off >= 0 && (size_t)S.bias_off < bias_floats && S.aux_off >= 0 &&
+                         (size_t)S.aux_off + 256 <= bias_floats, "step %d: bias / w_sdf range", s);
+        phase = 1;
+        ++n_sdf;
+        break;
+      case EPI_BWD:
+        NR_CHECK_ARG(phase == 1 && !last && S.sig_slot >= 0 && S.sig_slot < n_sig, "step %d: EPI_BWD placement / slot", s);
+        NR_CHECK_ARG(!S.pe_fill || S.out_rows + pe_dim <= S.n_mt * 128, "step %d: skip operand too wide", s);
+        break;
+      case EPI_NABLA:
+        NR_CHECK_ARG(phase == 1 && last && S.n_mt == 1, "step %d: EPI_NABLA is the last step", s);
+        ++n_nabla;
+        break;
+      default:
+        NR_CHECK_ARG(false, "step %d: epi=%d is not a reverse-mode step", s, S.epi);
+    }
+  }
+  NR_CHECK_ARG(n_sdf == 1 && n_nabla == 1 && n_sig >= 1, "nr_mlp_umma_reverse: program needs one EPI_SDF_OUT and a final EPI_NABLA");
+  if (n == 0) return NR_OK;
+  const size_t need = nr_mlp_umma_reverse_workspace(prog, n);
+  NR_CHECK_ARG(workspace && workspace_bytes >= need, "nr_mlp_umma_reverse: workspace of %zu bytes needed, %zu given", need,
+               workspace_bytes);
+  int dev = 0, sms = 0;
+  NR_CHECK_CUDA(cudaGetDevice(&dev));
+  NR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DevProgram dp;
+  dp.p = *prog;
+  RevArgs ka{(const uint8_t*)image, bias, x, n, sdf, nabla, feat, feat_ld, (uint8_t*)feat_img, (uint8_t*)workspace, n_sig};
+  const cudaStream_t st = (cudaStream_t)stream;
+  const bool f16 = prog->operand_f16 != 0;
+  switch (rev_cluster_size()) {
+    case 1: return f16 ? launch_rev<true, 1>(dp, ka, n, sms, st) : launch_rev<false, 1>(dp, ka, n, sms, st);
+    case 2: return f16 ? launch_rev<true, 2>(dp, ka, n, sms, st) : launch_rev<false, 2>(dp, ka, n, sms, st);
+    default: return f16 ? launch_rev<true, 4>(dp, ka, n, sms, st) : launch_rev<false, 4>(dp, ka, n, sms, st);
+  }
+}

@@ -559,6 +559,7 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
                                    const float* normal_scale, void* feat_img, void* stream) {
   NR_CHECK_ARG(prog && image && bias && x, "nr_mlp_umma_forward: null pointer");
   NR_CHECK_ARG(n >= 0, "nr_mlp_umma_forward: n < 0");
+  NR_CHECK_ARG(!prog->reverse, "nr_mlp_umma_forward: reverse-mode programs run through nr_mlp_umma_reverse");
   NR_CHECK_ARG(prog->n_steps >= 1 && prog->n_steps <= NR_UMMA_MAX_STEPS, "nr_mlp_umma_forward: n_steps=%d", prog->n_steps);
   NR_CHECK_ARG(((uintptr_t)image & 15) == 0, "nr_mlp_umma_forward: image must be 16-byte aligned");
   bool has_rad = false;

@@ -116,6 +116,9 @@ _FUSED_MODE = os.environ.get("NEURECON_B200_FUSED", "split")   # 'split' | 'fuse
 # SDF net on CTA pairs (tcgen05.mma.cta_group::2, csrc/mlp_umma2.cu): numerically identical, but measured slower on
 # B200 (DSMEM activation exchange at ~20 B/clk/SM, weight round trip through a relay) -- opt-in until that is fixed
 _PAIR_KERNEL = os.environ.get("NEURECON_B200_PAIR", "0") != "0"
+# Normals of the tensor tier: reverse mode (csrc/mlp_rev.cu: forward + backward sweep on 128-point tiles, half the
+# tensor work) or, with NEURECON_B200_NABLAS=forward, the forward-mode tangent tiles of csrc/mlp_umma.cu
+_REVERSE_NABLAS = os.environ.get("NEURECON_B200_NABLAS", "reverse") != "forward"
 
 
 class ImplicitSurface(nn.Module):
@@ -280,8 +283,28 @@ class ImplicitSurface(nn.Module):
                 net.feat_dim, _lib.ptr(sl(rgb_o)), _lib.ptr(normal_scale), _lib.ptr(img), _lib.stream_ptr(dev)),
                 "mlp_umma_forward")
 
+        def launch_rev(prog, i0, m, sdf_o, nabla_o, feat_o, img):
+            sl = lambda t: None if t is None else t[i0:i0 + m]
+            need = lib.nr_mlp_umma_reverse_workspace(C.byref(prog), m)
+            ws = _lib.workspace(need, dev, slot=2)
+            _lib.check(lib.nr_mlp_umma_reverse(
+                C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias), net.bias.numel(),
+                _lib.ptr(xf[i0:i0 + m]), m, _lib.ptr(sl(sdf_o)), _lib.ptr(sl(nabla_o)), _lib.ptr(sl(feat_o)),
+                net.feat_dim, _lib.ptr(img), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "mlp_umma_reverse")
+
+        rev = _REVERSE_NABLAS and not pair
         with torch.cuda.device(dev):
-            if mode == "split":
+            if mode == "split" and rev:
+                p_geo, p_rad = net.program("rev_img"), net.program("radiance")
+                step = _SPLIT_POINTS
+                img = _lib.workspace((min(n, step) + 127) // 128 * 65536, dev, slot=1)
+                for i0 in range(0, n, step):
+                    m = min(step, n - i0)
+                    launch_rev(p_geo, i0, m, sdf, nabla, None, img)
+                    launch(p_rad, i0, m, None, nabla, None, rgb, img)
+            elif mode == "nablas" and rev:
+                launch_rev(net.program("rev", want_feat=want_feat), 0, n, sdf, nabla, feat, None)
+            elif mode == "split":
                 # one-CTA kernel: image = last hidden activations, the radiance pass applies the feature layer 128 columns
                 # wide; pair kernel: image = the feature, from its own 32-column step
                 p_geo = net.program("nablas_imgf" if pair else "nablas_img", pair=pair)

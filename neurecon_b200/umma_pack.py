@@ -51,6 +51,7 @@ def pack_a_tiles(W, n_mtiles=None, k_pad=None, dtype=torch.bfloat16):
 # Programs for the fused tcgen05 MLP kernel (csrc/mlp_umma.cu, include/neurecon_b200.h)
 # --------------------------------------------------------------------------------------------
 EPI_HIDDEN, EPI_SDF_OUT, EPI_FEAT, EPI_RELU, EPI_RGB, EPI_EXTRAS = 0, 1, 2, 3, 4, 5
+EPI_BWD, EPI_NABLA = 7, 8
 
 
 def _pe_dim(multires):
@@ -117,6 +118,26 @@ class UmmaNet:
         c0, b0 = add(rep, brep, k_steps, 2)
         self.sdf_out2 = dict(chunk_begin=c0, n_mt=2, k_steps=k_steps, epi=EPI_SDF_OUT, bias_off=b0, out_rows=1,
                              pe_fill=0, to_rad=0)
+        # reverse-mode normals (csrc/mlp_rev.cu): the sdf row's weights as an fp32 table for the start of the backward
+        # sweep, W_l^T chunks for l = L-2 .. 1 (rows = the layer's inputs, k = its outputs) and W_0^T for the embedding
+        aux = torch.zeros(256, dtype=torch.float32, device=dev)
+        aux[:in_d] = Wl[0].float()
+        self._aux_off = self._n_bias
+        biases.append(aux)
+        self._n_bias += 256
+        self.bwd = []
+        for l in range(L - 2, 0, -1):
+            Wt = surface_W[l].t()                      # [in_d, out_d]
+            m_d, k_d = Wt.shape
+            k_steps, n_mt = (k_d + 63) // 64 * 4, (m_d + 127) // 128
+            c0, _ = add(Wt, None, k_steps, n_mt)
+            skip = 1 if l == skip_layer else 0
+            self.bwd.append(dict(chunk_begin=c0, n_mt=n_mt, k_steps=k_steps, epi=EPI_BWD, bias_off=0,
+                                 out_rows=surface_W[l - 1].shape[0], pe_fill=skip, to_rad=0, sig_slot=l - 1))
+        W0t = surface_W[0].t()
+        c0, _ = add(W0t, None, (W0t.shape[1] + 63) // 64 * 4, 1)
+        self.bwd.append(dict(chunk_begin=c0, n_mt=1, k_steps=(W0t.shape[1] + 63) // 64 * 4, epi=EPI_NABLA, bias_off=0,
+                             out_rows=pe, pe_fill=1 if 0 < skip_layer < L - 1 else 0, to_rad=0))
         self.feat_dim = Wl.shape[0] - 1
         if self.feat_dim > 0:
             if self.feat_dim > 256:
@@ -178,6 +199,17 @@ class UmmaNet:
                            accumulate=1, n_cols=128)]
             steps += [dict(s, n_cols=128) for s in self.rad[1:]]
             return self._finish(steps, tang=0, input_mode=1)
+        if mode in ("rev", "rev_img"):
+            # reverse-mode normals on 128-point tiles (nr_mlp_umma_reverse); 'rev_img': the last hidden activations
+            # also go to the radiance pass's operand image
+            steps = [dict(s, n_cols=128, sig_slot=i) for i, s in enumerate(self.hidden)]
+            if mode == "rev_img":
+                steps[-1]["to_rad"] = 1
+            elif want_feat:
+                steps.append(dict(self.feat, n_cols=128))
+            steps.append(dict(self.sdf_out, n_cols=128, sig_slot=len(self.hidden) - 1, aux_off=self._aux_off))
+            steps += [dict(s, n_cols=128) for s in self.bwd]
+            return self._finish(steps, tang=0, reverse=1)
         tang = 0 if mode == "sdf" else 1
         steps = [dict(s, n_cols=128) for s in self.hidden]
         steps.append(dict(self.sdf_out2 if pair else self.sdf_out, n_cols=128))
@@ -193,11 +225,12 @@ class UmmaNet:
             steps.append(dict(self.feat, n_cols=32 if tang else 128))
         return self._finish(steps, tang)
 
-    def _finish(self, steps, tang, input_mode=0):
+    def _finish(self, steps, tang, input_mode=0, reverse=0):
         from . import _lib
         P = _lib.UmmaProgram()
         assert len(steps) <= _lib.NR_UMMA_MAX_STEPS
         P.n_steps, P.tangents, P.multires, P.input_mode = len(steps), tang, self.multires, input_mode
+        P.reverse = reverse
         P.rad_multires, P.rad_multires_view, P.rad_extra_rows = self.rad_multires, self.rad_multires_view, self.rad_extra_rows
         P.operand_f16 = 1 if self.operand == "fp16" else 0
         for i, s in enumerate(steps):

@@ -20,7 +20,15 @@ def run(net, prog, x, v, n, reps, img=None):
     f = dict(dtype=torch.float32, device=dev)
     sdf, nab, rgb = torch.empty(n, **f), torch.empty(n, 3, **f), torch.empty(n, 3, **f)
 
+    ws = torch.empty(max(int(lib.nr_mlp_umma_reverse_workspace(C.byref(prog), n)), 16), dtype=torch.uint8, device=dev) \
+        if prog.reverse else None
+
     def go():
+        if prog.reverse:
+            _lib.check(lib.nr_mlp_umma_reverse(C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias),
+                                               net.bias.numel(), _lib.ptr(x), n, _lib.ptr(sdf), _lib.ptr(nab), None, 256,
+                                               _lib.ptr(img), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "rev")
+            return
         if getattr(prog, "_pair", False):
             _lib.check(lib.nr_mlp_umma2_forward(C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias),
                                                 net.bias.numel(), _lib.ptr(x), n, _lib.ptr(sdf), _lib.ptr(nab), None, 256,
@@ -50,10 +58,14 @@ def main():
     v = torch.nn.functional.normalize(torch.randn(n, 3, device=dev), dim=-1)
     net = m.implicit_surface._umma_net(m.radiance_net)
     img = torch.zeros((n + 127) // 128 * 65536, dtype=torch.uint8, device=dev)
-    for mode, mflop in (("sdf", 1.049 * 459008 / 524544), ("nablas", 1.967), ("fused", 1.967 + 0.543),
+    modes = os.environ.get("NR_MODES")
+    for mode, mflop in (("sdf", 1.049 * 459008 / 524544), ("nablas", 1.967), ("rev", 1.967), ("rev_img", 1.967),
+                        ("fused", 1.967 + 0.543),
                         ("nablas_img", 1.967), ("radiance", 0.543),
                         ("nablas_imgf", 1.967 + 0.1316), ("radiancef", 0.543 - 0.1316),
                         ("pair:sdf", 1.049 * 459008 / 524544), ("pair:nablas", 1.967), ("pair:nablas_imgf", 1.967 + 0.1316)):
+        if modes and mode not in modes.split(","):
+            continue
         for flags in [int(f) for f in os.environ.get("NR_FLAGS", "0,2").split(",")]:
             pair = mode.startswith("pair:")
             prog = net.program(mode[5:] if pair else mode, pair=pair)

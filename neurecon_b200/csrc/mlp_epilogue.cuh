@@ -83,6 +83,29 @@ __device__ __forceinline__ void softplus_sig2(float a0, float a1, f32x2 b144, fl
   s1 = __uint_as_float(__float_as_uint(s1) | (__float_as_uint(t1) & 0x80000000u));
   sg = add2(pk2(s0, s1), splat2(0.5f));
 }
+// Same softplus, with sg = derivative - 1/2 good to 2.2e-4 absolute from ONE transcendental: r = 1/(1+u) as a minimax
+// quartic in u on the FMA pipe (the MUFU unit issues 16 lanes/clk/SM: two per value would cost a 128-point tile 4096
+// cycles per layer, twice its MMA time).  For consumers that quantise the derivative to 8 bits (mlp_rev.cu).
+__device__ __forceinline__ void softplus_sigq2(float a0, float a1, f32x2 b144, float& sp0, float& sp1, f32x2& sg) {
+  const f32x2 t2 = fma2(pk2(a0, a1), splat2(144.26950408889634f), b144);
+  float t0, t1;
+  upk2(t2, t0, t1);
+  const f32x2 u2 = pk2(ex2_approx(-fabsf(t0)), ex2_approx(-fabsf(t1)));
+  f32x2 p = fma2(u2, splat2(-0.05875718221068382e-2f), splat2(0.22568579018115997e-2f));
+  p = fma2(p, u2, splat2(-0.4713013470172882e-2f));
+  p = fma2(p, u2, splat2(0.9974489808082581e-2f));
+  const f32x2 q = mul2(p, u2);
+  upk2(fma2(pk2(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), splat2(0.006931471805599453f), q), sp0, sp1);
+  f32x2 r = fma2(u2, splat2(0.16162029f), splat2(-0.55180615f));
+  r = fma2(r, u2, splat2(0.87791824f));
+  r = fma2(r, u2, splat2(-0.9872991f));
+  r = fma2(r, u2, splat2(0.99978334f - 0.5f));          // r - 1/2 in [0, 1/2]
+  float s0, s1;
+  upk2(r, s0, s1);
+  s0 = __uint_as_float(__float_as_uint(s0) | (__float_as_uint(t0) & 0x80000000u));
+  s1 = __uint_as_float(__float_as_uint(s1) | (__float_as_uint(t1) & 0x80000000u));
+  sg = pk2(s0, s1);
+}
 __device__ __forceinline__ void softplus2(float a0, float a1, f32x2 b144, float& sp0, float& sp1) {
   const f32x2 t2 = fma2(pk2(a0, a1), splat2(144.26950408889634f), b144);
   float t0, t1;

@@ -8,11 +8,13 @@
 // tangent columns per point through every layer (4.03 MFLOP per query on the tensor pipe, 32 points per tile); this
 // one executes 2.0 MFLOP per query on full 128-point tiles and halves the activation traffic through shared memory.
 //
-// The 8 x 256 derivatives per point (16-bit) do not fit on chip next to the operands (512 KB per tile), so they go
-// through a per-CTA scratch in global memory: 64 KB per (tile slot, layer), written by the forward epilogue and read
-// back a few microseconds later by THE SAME THREAD in the backward epilogue (no fences needed), 148 MB for the whole
-// grid, i.e. mostly L2 hits; the rest is HBM traffic the kernel has no other use for (7 KB per point at worst).
-// The loads are issued before the thread waits for its accumulator, so their latency hides under the MMAs.
+// The 8 x 256 derivatives per point do not fit on chip next to the operands, so they go through a per-CTA scratch in
+// global memory as 8-bit codes 128 + round(254 (s - 1/2)): 32 KB per (tile slot, layer), written by the forward epilogue and read
+// back a few microseconds later by THE SAME THREAD in the backward epilogue (no fences needed), 76 MB for the whole
+// grid, which stays in the 126 MB L2 (with 16-bit codes the 148 MB scratch cycled through HBM: ncu, profiles/).
+// softplus(beta = 100)' is a logistic that sits at 0 or 1 for most units, which the code represents exactly; the
+// quantisation (|err| <= 1/508) costs 1.2e-3 rms on the normal (fp64 model of the kernel, tools/check_rev.py).
+// All loads of a step are issued before the thread waits for its accumulator: their latency hides under the MMAs.
 //
 // Steps (nr_umma_program_t, reverse = 1): EPI_HIDDEN x L (sig_slot = layer), [EPI_FEAT], EPI_SDF_OUT (sdf to global,
 // then operand <- softplus'(z_{L-1}) * w_sdf), EPI_BWD x (L-1) (A = W_l^T; the skip layer's embedding rows go to the
@@ -27,7 +29,8 @@ constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilog
 constexpr int kEpiPerTile = 256;
 constexpr int kEpiWarpsPerTile = 8;
 constexpr int kEpiWarp0 = 4;
-constexpr uint32_t kSigBytes = 65536;    // softplus' of one layer of one tile: [8 column chunks][256 features][16 x 16-bit]
+constexpr uint32_t kSigBytes = 32768;    // softplus' of one layer of one tile: [8 column chunks][256 features][16 x u8]
+constexpr uint32_t kSigChunk = 4096;     // one column chunk: a warp's 16-byte loads / stores cover 512 contiguous bytes
 constexpr int kRedLd = 41;               // row stride (floats) of the embedding-gradient scratch: conflict-free both ways
 
 struct SmemRev {
@@ -50,7 +53,7 @@ struct RevArgs {
   float* feat;         // [n, feat_ld] or null
   int64_t feat_ld;
   uint8_t* feat_img;   // null, or [ceil(n/128)][64 KB]: last hidden activations as the radiance pass's operand image
-  uint8_t* sig;        // [grid][2][n_sig][64 KB]
+  uint8_t* sig;        // [grid][2][n_sig][32 KB]
   int n_sig;
 };
 
@@ -73,22 +76,52 @@ __device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, int tag
   __trap();
 }
 
-template <bool kF16>
-__device__ __forceinline__ uint32_t mul16x2(uint32_t a, uint32_t b) {
-  uint32_t d;
-  if (kF16) asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  else asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
+// softplus' codes: byte = 128 + round(254 (s - 1/2)) in [1, 255], exact at s = 0, 1/2 and 1.  The producer hands over
+// s - 1/2 (softplus_sigq2); fma(., 254, 1.5 * 2^23 + 128) leaves the code in the low mantissa byte, three byte permutes
+// gather four of them.
+__device__ __forceinline__ uint32_t sig_pack4(f32x2 a, f32x2 b) {
+  float a0, a1, b0, b1;
+  upk2(fma2(a, splat2(254.0f), splat2(12583040.0f)), a0, a1);
+  upk2(fma2(b, splat2(254.0f), splat2(12583040.0f)), b0, b1);
+  const uint32_t p0 = __byte_perm(__float_as_uint(a0), __float_as_uint(a1), 0x0040);
+  const uint32_t p1 = __byte_perm(__float_as_uint(b0), __float_as_uint(b1), 0x0040);
+  return __byte_perm(p0, p1, 0x5410);
+}
+// codes of byte pair (2 i, 2 i + 1) of w -> the two derivatives times a scale (fp32): 2^23 + code is exact, then one
+// FFMA2 with k = scale / 254 and offs = scale / 2 - (2^23 + 128) k
+template <int kPair>
+__device__ __forceinline__ f32x2 sig_unpack2(uint32_t w, f32x2 k, f32x2 offs) {
+  const uint32_t lo = __byte_perm(w, 0x4B000000u, kPair ? 0x7442 : 0x7440);
+  const uint32_t hi = __byte_perm(w, 0x4B000000u, kPair ? 0x7443 : 0x7441);
+  return fma2(pk2(__uint_as_float(lo), __uint_as_float(hi)), k, offs);
+}
+// 16 accumulators (or 1.0) times the 16 derivatives coded in q, times scale -> 16-bit operand row chunk
+template <bool kF16, bool kAcc>
+__device__ __forceinline__ void apply_sig16(const RowAddr& ra, int c, const uint32_t (&r)[16], uint4 q, float scale) {
+  const float kf = scale * (1.0f / 254.0f);
+  const f32x2 k = splat2(kf), o = splat2(fmaf(-8388736.0f, kf, 0.5f * scale));
+  const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+  uint32_t h[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f32x2 s0 = sig_unpack2<0>(qw[j], k, o), s1 = sig_unpack2<1>(qw[j], k, o);
+    if (kAcc) {
+      s0 = mul2(s0, pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])));
+      s1 = mul2(s1, pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+    }
+    float a0, a1, b0, b1;
+    upk2(s0, a0, a1);
+    upk2(s1, b0, b1);
+    h[2 * j] = umma::pack2<kF16>(a0, a1);
+    h[2 * j + 1] = umma::pack2<kF16>(b0, b1);
+  }
+  st_shared_v4(ra.chunk(2 * c), h[0], h[1], h[2], h[3]);
+  st_shared_v4(ra.chunk(2 * c + 1), h[4], h[5], h[6], h[7]);
 }
 __device__ __forceinline__ uint4 ldcg16(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void stcg16(uint8_t* p, uint4 v) { __stcg(reinterpret_cast<uint4*>(p), v); }
 
-// kCluster > 1: the CTAs of a cluster consume the same weight stream in loose lock-step and every 16 KB chunk is read
-// from L2 ONCE per cluster: CTA (chunk % kCluster) issues a multicast bulk copy into the same ring stage of all of them.
-// A stage is refilled when every CTA's MMAs have released it (tcgen05.commit multicast onto w_empty of all CTAs, count
-// kCluster); each CTA arms its own w_full.  The weight stream, re-read per 128-point tile, is what saturates the L2
-// (~6300 B/clk for the chip, B300_MICROARCH.md) long before the tensor pipe: 2 MB per tile pass.
-template <bool kF16, int kCluster>
+template <bool kF16>
 __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -102,14 +135,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
   const nr_umma_program_t& P = prog.p;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.n + 127) / 128;
-  // every CTA runs the same number of tile pairs (tiles past the end compute on zeros and store nothing): the CTAs of a
-  // cluster must consume identical weight streams
+  // every CTA runs the same number of tile pairs and always both slots (tiles past the end compute on zeros and store
+  // nothing): one static schedule for the producer and the MMA issuers
   const int64_t n_pairs = ((n_tiles + 1) / 2 + gridDim.x - 1) / gridDim.x * gridDim.x;
-  const uint32_t rank = kCluster > 1 ? umma::cluster_ctarank() : 0u;
-  constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], kCluster); }
+    for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
       umma::mbar_init(&in_ready[t], kEpiWarpsPerTile);
       umma::mbar_init(&acc_ready[t], 2);
@@ -122,7 +153,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) umma::cluster_sync_all();   // nobody signals a peer's barrier before it exists
   umma::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -139,10 +169,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
             wait_tag(&w_empty[stage], ((cnt >> kStagesLog2) & 1u) ^ 1u, 1000 + s);
             if (umma::elect_one()) {
               umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
-              uint8_t* dst = smem + SmemRev::ring + stage * kChunkBytes;
-              if (kCluster == 1) umma::bulk_g2s(dst, src + (size_t)c * kChunkBytes, kChunkBytes, &w_full[stage]);
-              else if ((cnt & (kCluster - 1)) == rank)
-                umma::bulk_g2s_multicast(dst, src + (size_t)c * kChunkBytes, kChunkBytes, &w_full[stage], kMask);
+              umma::bulk_g2s(smem + SmemRev::ring + stage * kChunkBytes, src + (size_t)c * kChunkBytes, kChunkBytes,
+                             &w_full[stage]);
             }
             __syncwarp();
           }
@@ -158,6 +186,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
     const uint32_t ring_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemRev::ring), 16);
     const uint32_t act_lo0 = umma::smem_desc_lo(umma::smem_u32(smem + SmemRev::act), kLbo);
     const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, 128, 0, 1) : umma::make_idesc_bf16(128, 128, 0, 1);
+    // Both tile slots run the same step back to back.  Measured alternatives, all slower or equal (profiles/): slot 1
+    // lagging half a program behind (forward epilogue of one slot against the backward MMAs of the other: +15 %), one
+    // weight chunk feeding both slots' MMAs (halves the weight stream: +0 % MMA-only, slower with epilogues), and
+    // multicasting the weight stream across 2- or 4-CTA clusters (+0 % / +15 %): the weight stream is not the limiter.
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       for (int s = 0; s < P.n_steps; ++s) {
         const uint32_t n_mt = P.steps[s].n_mt, nkc = P.steps[s].k_steps >> 2;
@@ -180,8 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
-                if (kCluster == 1) umma::mma_commit(&w_empty[st]);
-                else umma::mma_commit_mc(&w_empty[st], kMask);
+                umma::mma_commit(&w_empty[st]);
               }
               __syncwarp();
             }
@@ -207,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
     uint8_t* pes = smem + SmemRev::pes + t * (kPeStashRows * 256);
     const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256 + mo * 128);
     const RowAddr ra(umma::smem_u32(act), F);
-    uint8_t* sig_tile = a.sig + ((size_t)blockIdx.x * 2 + t) * a.n_sig * kSigBytes + (size_t)F * 32;
+    uint8_t* sig_tile = a.sig + ((size_t)blockIdx.x * 2 + t) * a.n_sig * kSigBytes + (size_t)F * 16;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + t;
@@ -254,15 +285,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
         const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
         const uint8_t* sig_rd = sig_tile + (size_t)S.sig_slot * kSigBytes;   // EPI_BWD / EPI_SDF_OUT: the slot to apply
 
-        // softplus' of the first half of the columns: requested before the accumulator wait (latency under the MMAs)
+        // softplus' codes of all 128 columns: requested before the accumulator wait (latency under the MMAs)
         uint4 sg[8];
         const bool use_sig = ((S.epi == EPI_BWD && mine && is_h) || S.epi == EPI_SDF_OUT) && !(P.debug_flags & 2);
         if (use_sig) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            sg[2 * c] = ldcg16(sig_rd + c * 8192);
-            sg[2 * c + 1] = ldcg16(sig_rd + c * 8192 + 16);
-          }
+          for (int c = 0; c < 8; ++c) sg[c] = ldcg16(sig_rd + c * kSigChunk);
         }
 
         wait_tag(&acc_ready[t], acc_par, 4000 + s);
@@ -282,22 +310,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
                 f32x2 d2[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  softplus_sig2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, v[2 * j], v[2 * j + 1], d2[j]);
+                  softplus_sigq2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, v[2 * j], v[2 * j + 1], d2[j]);
                 store_row16<kF16>(ra, 16 * c, v);
                 if (S.to_rad && a.feat_img && tile < n_tiles) img_store16<kF16>(a.feat_img, tile, F, 16 * c, v);
-                uint32_t w[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float lo, hi;
-                  upk2(d2[j], lo, hi);
-                  w[j] = umma::pack2<kF16>(lo, hi);
-                }
-                if (!(P.debug_flags & 1)) {
-                  stcg16(sig_wr + c * 8192, make_uint4(w[0], w[1], w[2], w[3]));
-                  stcg16(sig_wr + c * 8192 + 16, make_uint4(w[4], w[5], w[6], w[7]));
-                } else if (w[0] + w[1] + w[2] + w[3] + w[4] + w[5] + w[6] + w[7] == 0x12345u) {
-                  stcg16(sig_wr, make_uint4(w[0], w[1], w[2], w[3]));
-                }
+                const uint4 w = make_uint4(sig_pack4(d2[0], d2[1]), sig_pack4(d2[2], d2[3]), sig_pack4(d2[4], d2[5]),
+                                           sig_pack4(d2[6], d2[7]));
+                if (!(P.debug_flags & 1) || w.x + w.y + w.z + w.w == 0x12345u) stcg16(sig_wr + c * kSigChunk, w);
               } else {
                 copy_row16(ra, pes, jpe, 16 * c);
               }
@@ -347,40 +365,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
             }
           }
           // start of the backward pass: operand row F <- softplus'(z_last)[F, :] * w_sdf[F]  (d sdf / d z_last)
-          const uint32_t w1 = umma::pack1<kF16>(a.bias[S.aux_off + F]);
-          const uint32_t w2 = w1 | (w1 << 16);
+          const float wF = a.bias[S.aux_off + F];
+          const uint32_t none[16] = {};
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 s0 = sg[2 * (c & 3)], s1 = sg[2 * (c & 3) + 1];
-            if (c < 4 && !(P.debug_flags & 2)) {
-              sg[2 * c] = ldcg16(sig_rd + (c + 4) * 8192);
-              sg[2 * c + 1] = ldcg16(sig_rd + (c + 4) * 8192 + 16);
-            }
-            st_shared_v4(ra.chunk(2 * c), mul16x2<kF16>(s0.x, w2), mul16x2<kF16>(s0.y, w2), mul16x2<kF16>(s0.z, w2),
-                         mul16x2<kF16>(s0.w, w2));
-            st_shared_v4(ra.chunk(2 * c + 1), mul16x2<kF16>(s1.x, w2), mul16x2<kF16>(s1.y, w2), mul16x2<kF16>(s1.z, w2),
-                         mul16x2<kF16>(s1.w, w2));
-          }
+          for (int c = 0; c < 8; ++c) apply_sig16<kF16, false>(ra, c, none, sg[c], wF);
         } else if (S.epi == EPI_BWD) {
           if (mine && !(P.debug_flags & 4)) {
             uint32_t raw[16], rawB[16];
             const int jpe = F - S.out_rows;
             auto apply = [&](const uint32_t (&r)[16], int c) {
-              uint32_t h[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) h[j] = umma::pack2<kF16>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
               if (is_h) {
-                const uint4 s0 = sg[2 * (c & 3)], s1 = sg[2 * (c & 3) + 1];
-                if (c < 4 && !(P.debug_flags & 2)) {
-                  sg[2 * c] = ldcg16(sig_rd + (c + 4) * 8192);
-                  sg[2 * c + 1] = ldcg16(sig_rd + (c + 4) * 8192 + 16);
-                }
-                st_shared_v4(ra.chunk(2 * c), mul16x2<kF16>(h[0], s0.x), mul16x2<kF16>(h[1], s0.y), mul16x2<kF16>(h[2], s0.z),
-                             mul16x2<kF16>(h[3], s0.w));
-                st_shared_v4(ra.chunk(2 * c + 1), mul16x2<kF16>(h[4], s1.x), mul16x2<kF16>(h[5], s1.y),
-                             mul16x2<kF16>(h[6], s1.z), mul16x2<kF16>(h[7], s1.w));
+                apply_sig16<kF16, true>(ra, c, r, sg[c], 1.0f);
               } else {
                 if (is_pe) {   // gradient w.r.t. the skip connection's copy of the embedding: kept for EPI_NABLA
+                  uint32_t h[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) h[j] = umma::pack2<kF16>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
                   uint4* dst = reinterpret_cast<uint4*>(pes + jpe * 256 + c * 32);
                   dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
                   dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
@@ -404,32 +404,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
           // acc rows [0, pe_dim) = d sdf / d PE(x) through layer 0 (+ the skip layer's share from the stash);
           // nabla_c = sum_j dPE_j/dx_c * g_j: products to a [point][row] scratch in the (now free) operand buffer
           float* red = reinterpret_cast<float*>(act);
-          if (mo == 0 && 32 * q < pe_dim) {   // warp-uniform: the TMEM loads are .sync.aligned
-            const int comp = F < 3 ? F : (F - 3) % 3;
-            const int qf = F < 3 ? 0 : (F - 3) / 6;
-            const bool is_sin = F >= 3 && ((F - 3) % 6) < 3;
+          if (32 * q < pe_dim) {   // warp-uniform (the TMEM loads are .sync.aligned); both warps of a lane quarter work,
+            const int R = 32 * q + lane;                       // each on half of the columns of M-tile 0
+            const int comp = R < 3 ? R : (R - 3) % 3;
+            const int qf = R < 3 ? 0 : (R - 3) / 6;
+            const bool is_sin = R >= 3 && ((R - 3) % 6) < 3;
             const float f = (float)(1 << qf);
-            const uint16_t* srow = reinterpret_cast<const uint16_t*>(pes + F * 256);
+            const uint16_t* srow = reinterpret_cast<const uint16_t*>(pes + R * 256);
+            const uint32_t taddr0 = taddr - (uint32_t)(mo * 128);
 #pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 4 * mo; c < 4 * mo + 4; ++c) {
               uint32_t raw[16];
-              umma::tmem_ld16(taddr + 16 * c, raw);
+              umma::tmem_ld16(taddr0 + 16 * c, raw);
               umma::tmem_ld_wait();
+              if (R < pe_dim) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int col = 16 * c + j;
-                float g = __uint_as_float(raw[j]);
-                if (S.pe_fill && F < pe_dim) {
-                  const uint16_t hv = srow[col];
-                  g += kF16 ? __half2float(__ushort_as_half(hv)) : __uint_as_float((uint32_t)hv << 16);
+                for (int j = 0; j < 16; ++j) {
+                  const int col = 16 * c + j;
+                  float g = __uint_as_float(raw[j]);
+                  if (S.pe_fill) {
+                    const uint16_t hv = srow[col];
+                    g += kF16 ? __half2float(__ushort_as_half(hv)) : __uint_as_float((uint32_t)hv << 16);
+                  }
+                  float jac = 1.0f;
+                  if (R >= 3) {
+                    float sn, cs;
+                    __sincosf(xs[3 * col + comp] * f, &sn, &cs);
+                    jac = is_sin ? f * cs : -f * sn;
+                  }
+                  red[col * kRedLd + R] = g * jac;
                 }
-                float jac = 1.0f;
-                if (F >= 3) {
-                  float sn, cs;
-                  __sincosf(xs[3 * col + comp] * f, &sn, &cs);
-                  jac = is_sin ? f * cs : -f * sn;
-                }
-                if (F < pe_dim) red[col * kRedLd + F] = g * jac;
               }
             }
           }
@@ -451,7 +455,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
 
   umma::tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) umma::cluster_sync_all();   // peers may still multicast into this CTA's ring / arrive on its barriers
   if (warp == 2) umma::tmem_dealloc(tmem_base, 512);
 }
 
@@ -472,62 +475,6 @@ extern "C" size_t nr_mlp_umma_reverse_workspace(const nr_umma_program_t* prog, i
   (void)n;   // sized for the largest grid, so one buffer serves every n
   return (size_t)sms * 2 * count_sig_slots(prog) * kSigBytes;
 }
-
-namespace {
-// Cluster size of the weight multicast: NEURECON_B200_REV_CLUSTER = 1 | 2 | 4 (default 1: measured no faster).
-int rev_cluster_size() {
-  static int v = 0;
-  if (!v) {
-    const char* e = getenv("NEURECON_B200_REV_CLUSTER");
-    v = e ? atoi(e) : 1;
-    if (v != 1 && v != 2 && v != 4) v = 1;
-  }
-  return v;
-}
-
-template <bool kF16, int kCluster>
-int launch_rev(const DevProgram& dp, const RevArgs& ka, int64_t n, int sms, cudaStream_t stream) {
-  auto kern = mlp_rev_kernel<kF16, kCluster>;
-  const size_t smem = SmemRev::total + 1024;
-  static bool attr_set[64] = {};
-  int dev = 0;
-  NR_CHECK_CUDA(cudaGetDevice(&dev));
-  if (!attr_set[dev & 63]) {
-    NR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[dev & 63] = true;
-  }
-  const int64_t n_pairs = (nr_cdiv(n, 128) + 1) / 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = kCluster;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = kCluster > 1 ? 1 : 0;
-  int max_ctas = sms;
-  if (kCluster > 1) {
-    static int max_clusters[64] = {};
-    if (!max_clusters[dev & 63]) {
-      cfg.gridDim = dim3((sms / kCluster) * kCluster);
-      int nc = 0;
-      NR_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
-      NR_CHECK_ARG(nc >= 1, "mlp_rev_kernel: no cluster of %d CTAs fits on this device", kCluster);
-      max_clusters[dev & 63] = nc;
-    }
-    max_ctas = max_clusters[dev & 63] * kCluster;
-  }
-  int64_t grid = nr_cdiv(n_pairs, kCluster) * kCluster;
-  if (grid > max_ctas) grid = max_ctas;
-  cfg.gridDim = dim3((unsigned)grid);
-  NR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, dp, ka));
-  NR_CHECK_LAUNCH("mlp_rev_kernel");
-  return NR_OK;
-}
-}  // namespace
 
 extern "C" int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* image, size_t image_bytes,
                                    const float* bias, size_t bias_floats, const float* x, int64_t n, float* sdf,
@@ -592,14 +539,20 @@ extern "C" int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* im
   int dev = 0, sms = 0;
   NR_CHECK_CUDA(cudaGetDevice(&dev));
   NR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t n_pairs = (nr_cdiv(n, 128) + 1) / 2;
+  const int grid = (int)(n_pairs < sms ? n_pairs : sms);
+  const size_t smem = SmemRev::total + 1024;
+  static unsigned long long attr_set = 0;  // per-device bit: the attribute is per (function, device)
+  if (!(attr_set >> (dev & 63) & 1ull)) {
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set |= 1ull << (dev & 63);
+  }
   DevProgram dp;
   dp.p = *prog;
   RevArgs ka{(const uint8_t*)image, bias, x, n, sdf, nabla, feat, feat_ld, (uint8_t*)feat_img, (uint8_t*)workspace, n_sig};
-  const cudaStream_t st = (cudaStream_t)stream;
-  const bool f16 = prog->operand_f16 != 0;
-  switch (rev_cluster_size()) {
-    case 1: return f16 ? launch_rev<true, 1>(dp, ka, n, sms, st) : launch_rev<false, 1>(dp, ka, n, sms, st);
-    case 2: return f16 ? launch_rev<true, 2>(dp, ka, n, sms, st) : launch_rev<false, 2>(dp, ka, n, sms, st);
-    default: return f16 ? launch_rev<true, 4>(dp, ka, n, sms, st) : launch_rev<false, 4>(dp, ka, n, sms, st);
-  }
+  if (prog->operand_f16) mlp_rev_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+  else mlp_rev_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+  NR_CHECK_LAUNCH("mlp_rev_kernel");
+  return NR_OK;
 }

@@ -21,6 +21,11 @@ __global__ void __launch_bounds__(1024, 1) probe_alu_kernel(int iters, float see
       else if (kOp == 3) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(v[j]));
       else if (kOp == 4) { uint32_t p; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(v[j]), "f"(v[(j + 1) & 7])); acc ^= p; }
       else if (kOp == 5) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(v[j]));
+      else if (kOp == 7) { uint32_t& w = reinterpret_cast<uint32_t&>(v[j]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(w)); }
+      else if (kOp == 8) { uint32_t& w = reinterpret_cast<uint32_t&>(v[j]); asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(w)); }
+      else if (kOp == 9) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[j]));
+      else if (kOp == 10) { uint32_t& w = reinterpret_cast<uint32_t&>(v[j]); asm volatile("fma.rn.f16x2 %0, %0, %0, %0;" : "+r"(w)); }
+      else if (kOp == 11) { uint32_t& w = reinterpret_cast<uint32_t&>(v[j]); asm volatile("max.f16x2 %0, %0, %1;" : "+r"(w) : "r"(acc)); }
       else if (kOp == 6) {
         if (j & 1) continue;
         uint64_t p = ((uint64_t)__float_as_uint(v[j + 1]) << 32) | __float_as_uint(v[j]);
@@ -42,7 +47,7 @@ __global__ void __launch_bounds__(1024, 1) probe_alu_kernel(int iters, float see
 
 extern "C" int nr_probe_alu(int32_t op, int32_t threads, int32_t iters, int32_t grid, float* out, long long* cycles,
                             void* stream) {
-  NR_CHECK_ARG(out && cycles && threads >= 32 && threads <= 1024 && iters > 0 && grid > 0 && op >= 0 && op <= 6, "nr_probe_alu: args");
+  NR_CHECK_ARG(out && cycles && threads >= 32 && threads <= 1024 && iters > 0 && grid > 0 && op >= 0 && op <= 11, "nr_probe_alu: args");
   cudaStream_t st = (cudaStream_t)stream;
   switch (op) {
     case 0: probe_alu_kernel<0><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
@@ -51,7 +56,12 @@ extern "C" int nr_probe_alu(int32_t op, int32_t threads, int32_t iters, int32_t 
     case 3: probe_alu_kernel<3><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
     case 4: probe_alu_kernel<4><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
     case 5: probe_alu_kernel<5><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
-    default: probe_alu_kernel<6><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
+    case 6: probe_alu_kernel<6><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
+    case 7: probe_alu_kernel<7><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
+    case 8: probe_alu_kernel<8><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
+    case 9: probe_alu_kernel<9><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
+    case 10: probe_alu_kernel<10><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
+    default: probe_alu_kernel<11><<<grid, threads, 0, st>>>(iters, 0.5f, out, cycles); break;
   }
   NR_CHECK_LAUNCH("probe_alu_kernel");
   return NR_OK;

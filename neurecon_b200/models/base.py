@@ -292,7 +292,9 @@ class ImplicitSurface(nn.Module):
                 _lib.ptr(xf[i0:i0 + m]), m, _lib.ptr(sl(sdf_o)), _lib.ptr(sl(nabla_o)), _lib.ptr(sl(feat_o)),
                 net.feat_dim, _lib.ptr(img), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "mlp_umma_reverse")
 
-        rev = _REVERSE_NABLAS and not pair
+        # bf16 operands keep the tangent tiles: the backward sweep rounds every layer's gradient to 8 bits of mantissa,
+        # which lands on the tier's 1e-2 bar (1.06e-2 measured), the forward-mode tangents stay under it
+        rev = _REVERSE_NABLAS and not pair and net.operand == "fp16"
         with torch.cuda.device(dev):
             if mode == "split" and rev:
                 p_geo, p_rad = net.program("rev_img"), net.program("radiance")

@@ -100,7 +100,8 @@ def test_pair_kernel_matches_single_cta_kernel(n):
     from conftest import build_neus
     m = build_neus(seed=1, device=DEV)
     x = (torch.rand(n, 3, device=DEV) - 0.5) * 1.6
-    old = base._PAIR_KERNEL
+    old, old_rev = base._PAIR_KERNEL, base._REVERSE_NABLAS
+    base._REVERSE_NABLAS = False     # both on forward-mode tangent tiles: the pair kernel has no reverse-mode twin
     try:
         outs = {}
         for pair in (False, True):
@@ -113,7 +114,41 @@ def test_pair_kernel_matches_single_cta_kernel(n):
             assert torch.isfinite(b_).all()
             assert rel_err(b_, a_) < 2e-6, rel_err(b_, a_)
     finally:
-        base._PAIR_KERNEL = old
+        base._PAIR_KERNEL, base._REVERSE_NABLAS = old, old_rev
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 255, 257, 4097, 40000])
+def test_reverse_mode_normals_vs_oracle_and_forward_mode(n, tier):
+    """csrc/mlp_rev.cu (forward sweep + backward sweep, softplus' parked as 8-bit codes) against the oracle's autograd
+    normals (base.py:265-282) and against the forward-mode tangent kernel; sdf and the geometry feature come from the
+    same forward arithmetic and must agree with the tangent kernel's to fp32 accumulation order."""
+    from neurecon_b200.models import base
+    if tier != "fp16":
+        pytest.skip("reverse-mode normals serve the fp16 tier (bf16 keeps the tangent tiles)")
+    m = build_neus(seed=1, device=DEV)
+    x = synthetic.make_points(n, extent=1.0, seed=11)
+    v = torch.nn.functional.normalize(synthetic.make_points(n, extent=1.0, seed=12), dim=-1)
+    osdf, onab, ofeat, orad = _oracle(m, x, v)
+    old = base._REVERSE_NABLAS
+    try:
+        out = {}
+        for rev in (True, False):
+            base._REVERSE_NABLAS = rev
+            with torch.no_grad():
+                sdf, nab, feat = m.implicit_surface.forward_with_nablas(x.to(DEV))
+                rgb, sdf2, nab2 = query_radiance(m.implicit_surface, m.radiance_net, x.to(DEV), v.to(DEV))
+            torch.cuda.synchronize()
+            out[rev] = (sdf, nab, feat, rgb, sdf2, nab2)
+    finally:
+        base._REVERSE_NABLAS = old
+    sdf, nab, feat, rgb, sdf2, nab2 = out[True]
+    assert nab.shape == (n, 3) and torch.isfinite(nab).all()
+    errs = dict(sdf=rel_err(sdf, osdf), nab=rel_err(nab, onab), feat=rel_err(feat, ofeat), rgb=rel_err(rgb, orad),
+                sdf2=rel_err(sdf2, osdf), nab2=rel_err(nab2, onab))
+    assert all(e < 5e-3 for e in errs.values()), errs          # north_star: <= 1e-2 on the 16-bit MLP path
+    assert torch.equal(nab, nab2) and torch.equal(sdf, sdf2)    # 'rev' and 'rev_img' programs: same arithmetic
+    assert rel_err(sdf, out[False][0]) < 1e-5 and rel_err(feat, out[False][2]) < 1e-5
+    assert rel_err(nab, out[False][1]) < 5e-3 and rel_err(rgb, out[False][3]) < 5e-3
 
 
 def test_nerfpp_net_tensor_tier_vs_fp32():

@@ -203,12 +203,15 @@ int nr_neus_ray_setup(const float* rays_o, const float* rays_d, int64_t R, float
  *      sample_pdf(n_next) -> d_next [R,n_next], pts_next [R,n_next,3]   -- neus.py:253-271
  *      (u_next: [R,n_next] uniforms, NULL = deterministic linspace)
  *   3. if n_next == 0 (final): emit pts [R,m,3], d_mid [R,m-1], pts_mid [R,m-1,3]
- *                                                                       -- neus.py:284-288 */
+ *                                                                       -- neus.py:284-288
+ * nab_buf [R,cap,3] / nab_new [R,n_new,3] (both or neither): the samples' normals ride along with the merge, so that
+ * after the final step (sdf_buf, nab_buf) ARE forward_with_nablas at the sorted samples (neus.py:291) and the render
+ * need not evaluate the network there again. */
 int nr_neus_upsample_step(const float* rays_o, const float* dirs, int64_t R, float* d_buf,
                           float* sdf_buf, int32_t cap, int32_t m_cur, const float* d_new,
                           const float* sdf_new, int32_t n_new, int32_t iter, int32_t n_next,
                           const float* u_next, float* d_next, float* pts_next, float* pts_all,
-                          float* d_mid, float* pts_mid, void* stream);
+                          float* d_mid, float* pts_mid, float* nab_buf, const float* nab_new, void* stream);
 
 /* Alpha, exclusive-cumprod transmittance and compositing (neus.py:28-35,57-70,296,346-381)
  * as one warp-scan pass.  sdf [R,M], nablas [R,M,3] (NULL if !calc_normal), radiance

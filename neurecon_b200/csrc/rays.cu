@@ -178,17 +178,19 @@ __global__ void neus_upsample_kernel(const float* __restrict__ rays_o, const flo
                                      int iter, int n_next, const float* __restrict__ u_next,
                                      float* __restrict__ d_next, float* __restrict__ pts_next,
                                      float* __restrict__ pts_all, float* __restrict__ d_mid_out,
-                                     float* __restrict__ pts_mid) {
+                                     float* __restrict__ pts_mid, float* __restrict__ nab_buf,
+                                     const float* __restrict__ nab_new) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
   if (ray >= R) return;
-  float* sd = smem + (size_t)warp * (4 * cap + 2 * cap);
+  float* sd = smem + (size_t)warp * (nab_buf ? 9 * cap : 6 * cap);
   float* ss = sd + cap;
   float* sa = ss + cap;   // scratch: alpha / weights / cdf
   float* sc = sa + cap;   // scratch: old d (during merge) / cdf
   float* dn = sc + cap;   // new d   [<= cap]
   float* sn = dn + cap;   // new sdf [<= cap]
+  float* on = sn + cap;   // old normals [<= 3 cap], only with nab_buf
   const int M = m_cur + n_new;
 
   // ---- 1. merge (neus.py:272-276: cat, sort, gather) ----
@@ -198,6 +200,9 @@ __global__ void neus_upsample_kernel(const float* __restrict__ rays_o, const flo
     od[i] = d_buf[ray * (int64_t)cap + i];
     os[i] = sdf_buf[ray * (int64_t)cap + i];
   }
+  float* nrow = nab_buf ? nab_buf + ray * (int64_t)cap * 3 : nullptr;   // the samples' normals ride along with the merge
+  if (nab_buf)
+    for (int i = lane; i < 3 * m_cur; i += 32) on[i] = nrow[i];
   for (int j = lane; j < n_new; j += 32) {
     dn[j] = d_new[ray * (int64_t)n_new + j];
     sn[j] = sdf_new[ray * (int64_t)n_new + j];
@@ -209,6 +214,11 @@ __global__ void neus_upsample_kernel(const float* __restrict__ rays_o, const flo
     for (int k = 0; k < n_new; ++k) c += (dn[k] < v);
     sd[i + c] = v;
     ss[i + c] = os[i];
+    if (nab_buf) {
+      nrow[3 * (i + c)] = on[3 * i];
+      nrow[3 * (i + c) + 1] = on[3 * i + 1];
+      nrow[3 * (i + c) + 2] = on[3 * i + 2];
+    }
   }
   for (int j = lane; j < n_new; j += 32) {
     const float v = dn[j];
@@ -221,6 +231,12 @@ __global__ void neus_upsample_kernel(const float* __restrict__ rays_o, const flo
     for (int k = 0; k < n_new; ++k) c += (dn[k] < v) || (dn[k] == v && k < j);
     sd[c] = v;
     ss[c] = sn[j];
+    if (nab_buf) {
+      const float* src = nab_new + (ray * (int64_t)n_new + j) * 3;
+      nrow[3 * c] = src[0];
+      nrow[3 * c + 1] = src[1];
+      nrow[3 * c + 2] = src[2];
+    }
   }
   __syncwarp();
   for (int i = lane; i < M; i += 32) {
@@ -671,21 +687,23 @@ extern "C" int nr_neus_ray_setup(const float* rays_o, const float* rays_d, int64
 extern "C" int nr_neus_upsample_step(const float* rays_o, const float* dirs, int64_t R, float* d_buf, float* sdf_buf,
                                      int32_t cap, int32_t m_cur, const float* d_new, const float* sdf_new,
                                      int32_t n_new, int32_t iter, int32_t n_next, const float* u_next, float* d_next,
-                                     float* pts_next, float* pts_all, float* d_mid, float* pts_mid, void* stream) {
+                                     float* pts_next, float* pts_all, float* d_mid, float* pts_mid, float* nab_buf,
+                                     const float* nab_new, void* stream) {
   NR_CHECK_ARG(rays_o && dirs && d_buf && sdf_buf && d_new && sdf_new, "nr_neus_upsample_step: null pointer");
+  NR_CHECK_ARG((nab_buf != nullptr) == (nab_new != nullptr), "nr_neus_upsample_step: nab_buf and nab_new go together");
   NR_CHECK_ARG(m_cur >= 0 && n_new >= 1 && m_cur + n_new <= cap && m_cur + n_new >= 2,
                "nr_neus_upsample_step: m_cur=%d n_new=%d cap=%d", m_cur, n_new, cap);
   NR_CHECK_ARG(n_next >= 0 && iter >= 0 && iter < 24, "nr_neus_upsample_step: bad iter/n_next");
   if (n_next > 0) NR_CHECK_ARG(d_next && pts_next, "nr_neus_upsample_step: d_next/pts_next required");
   else NR_CHECK_ARG(pts_all && d_mid && pts_mid, "nr_neus_upsample_step: final outputs required");
   if (R == 0) return NR_OK;
-  const size_t smem = (size_t)kWarpsPerBlock * 6 * cap * sizeof(float);
+  const size_t smem = (size_t)kWarpsPerBlock * (nab_buf ? 9 : 6) * cap * sizeof(float);
   NR_CHECK_ARG(smem <= 200 * 1024, "nr_neus_upsample_step: cap=%d too large", cap);
   if (smem > 48 * 1024)
     NR_CHECK_CUDA(cudaFuncSetAttribute(neus_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   neus_upsample_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
       rays_o, dirs, R, d_buf, sdf_buf, cap, m_cur, d_new, sdf_new, n_new, iter, n_next, u_next, d_next, pts_next,
-      pts_all, d_mid, pts_mid);
+      pts_all, d_mid, pts_mid, nab_buf, nab_new);
   NR_CHECK_LAUNCH("neus_upsample_kernel");
   return NR_OK;
 }

@@ -129,8 +129,11 @@ def _composite_bg(model, rays_o, dirs, far, sdf, nablas, radiances, d_mid, s, ra
 
 
 def _upsample(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
-              N_upsample_iters, perturb, return_far=False):
-    """neus.py:184-288 for one flat ray chunk [R,3]: returns dirs, d_all, pts, d_mid, pts_mid."""
+              N_upsample_iters, perturb, return_far=False, return_field=False, with_nablas=False):
+    """neus.py:184-288 for one flat ray chunk [R,3]: returns dirs, d_all, pts, d_mid, pts_mid [, far]
+    [, sdf_all, nablas_all].  ``return_field``: also the sdf at the sorted samples, which the up-sampler has evaluated
+    anyway (the reference evaluates it again, neus.py:291); ``with_nablas``: the network queries of the up-sampler also
+    produce the normals and the merge carries them along, so (sdf_all, nablas_all) replace that second evaluation."""
     lib = _lib.get_lib()
     R, dev = rays_o.shape[0], rays_o.device
     f = dict(dtype=torch.float32, device=dev)
@@ -146,11 +149,16 @@ def _upsample(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_b
         N_samples, _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far), _lib.ptr(d_new), _lib.ptr(pts_new), st),
         "neus_ray_setup")
     d_buf, sdf_buf = torch.empty(R, cap, **f), torch.empty(R, cap, **f)
+    nab_buf = torch.empty(R, cap, 3, **f) if with_nablas else None
     pts_all, d_mid, pts_mid = torch.empty(R, cap, 3, **f), torch.empty(R, cap - 1, **f), torch.empty(R, cap - 1, 3, **f)
     m_cur, n_new = 0, N_samples
     with torch.no_grad():
         for it in range(N_upsample_iters + 1):
-            sdf_new = model.implicit_surface.forward(pts_new)
+            nab_new = None
+            if with_nablas:
+                sdf_new, nab_new, _ = model.implicit_surface._run(pts_new, want_nablas=True, want_feat=False)
+            else:
+                sdf_new = model.implicit_surface.forward(pts_new)
             last = it == N_upsample_iters
             n_next = 0 if last else n_fine
             u = None
@@ -161,12 +169,14 @@ def _upsample(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_b
             _lib.check(lib.nr_neus_upsample_step(
                 _lib.ptr(rays_o), _lib.ptr(dirs), R, _lib.ptr(d_buf), _lib.ptr(sdf_buf), cap, m_cur,
                 _lib.ptr(d_new), _lib.ptr(sdf_new), n_new, it, n_next, _lib.ptr(u), _lib.ptr(d_next),
-                _lib.ptr(pts_next), _lib.ptr(pts_all), _lib.ptr(d_mid), _lib.ptr(pts_mid), st), "neus_upsample_step")
+                _lib.ptr(pts_next), _lib.ptr(pts_all), _lib.ptr(d_mid), _lib.ptr(pts_mid), _lib.ptr(nab_buf),
+                _lib.ptr(nab_new), st), "neus_upsample_step")
             m_cur += n_new
             d_new, pts_new, n_new = d_next, pts_next, n_next
-    if return_far:
-        return dirs, d_buf, pts_all, d_mid, pts_mid, far
-    return dirs, d_buf, pts_all, d_mid, pts_mid
+    out = (dirs, d_buf, pts_all, d_mid, pts_mid) + ((far,) if return_far else ())
+    if return_field:
+        out += (sdf_buf, nab_buf)
+    return out
 
 
 def volume_render(
@@ -244,11 +254,13 @@ def volume_render(
         for i0 in range(0, n_total, step):
             ro, rd = o_flat[i0:i0 + step], d_flat[i0:i0 + step]
             R = ro.shape[0]
-            dirs, d_all, pts, d_mid, pts_mid, far = _upsample(
+            # sdf (and, when the caller wants normals or per-sample outputs, nablas) at the sorted samples come out of the
+            # up-sampler's own network queries: same points, same arithmetic as the reference's second evaluation there
+            need_nablas = bool(calc_normal or detailed_output)
+            dirs, d_all, pts, d_mid, pts_mid, far, sdf, nablas = _upsample(
                 model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
-                N_upsample_iters, perturb, return_far=True)
+                N_upsample_iters, perturb, return_far=True, return_field=True, with_nablas=need_nablas)
             with torch.no_grad():
-                sdf, nablas, _ = model.implicit_surface._run(pts, want_nablas=True, want_feat=False)
                 views = dirs.unsqueeze(-2).expand(R, M - 1, 3)
                 radiances, _, _ = query_radiance(model.implicit_surface, model.radiance_net, pts_mid, views)
             sigma_out = radiance_out = None

@@ -158,6 +158,28 @@ def test_neus_upsample_matches_oracle():
     assert rel_err(pts, o[:, None, :] + dn[:, None, :] * d_all.cpu()[:, :, None]) < 1e-6
 
 
+@pytest.mark.parametrize("perturb", [False, True])
+def test_neus_upsampler_field_equals_evaluation_at_sorted_samples(perturb):
+    """The (sdf, nablas) the up-sampler's merge carries along are forward_with_nablas at the sorted samples
+    (neus.py:291, which the render no longer repeats): same points, same arithmetic, hence the same numbers; ties and
+    the stable old-before-new order must keep every normal with its depth."""
+    from neurecon_b200.models.frameworks import neus
+    m = build_neus(seed=1, device=DEV)
+    o, d = synthetic.make_rays(257, seed=21)
+    torch.manual_seed(5)
+    out = neus._upsample(m, o.to(DEV), d.to(DEV), 1.0, None, None, 64, 64, 4, perturb, return_field=True,
+                         with_nablas=True)
+    dirs, d_all, pts, d_mid, pts_mid, sdf_all, nab_all = out
+    with torch.no_grad():
+        sdf, nab, _ = m.implicit_surface.forward_with_nablas(pts)
+    assert sdf_all.shape == (257, 128) and nab_all.shape == (257, 128, 3)
+    assert torch.isfinite(nab_all).all()
+    assert rel_err(sdf_all, sdf) < 1e-6 and rel_err(nab_all, nab) < 1e-6
+    torch.manual_seed(5)
+    out2 = neus._upsample(m, o.to(DEV), d.to(DEV), 1.0, None, None, 64, 64, 4, perturb, return_field=True)
+    assert out2[6] is None and torch.equal(out2[1], d_all) and rel_err(out2[5], sdf_all) < 1e-6
+
+
 @pytest.mark.parametrize("white_bkgd", [False, True])
 def test_neus_composite_vs_oracle(white_bkgd):
     from neurecon_b200.models.frameworks import neus

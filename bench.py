@@ -149,7 +149,9 @@ def workload_config(precision):
             "l2_policy": "inputs and intermediates per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
-NCU_DRAM_BYTES_PER_LAUNCH = 13689344   # see roofline.traffic_source
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel the roofline times, from one `ncu --set full`
+# capture of that launch (profiles/): reverse-mode kernel of the fp16 tier / tangent-tile kernel of the bf16 tier
+NCU_DRAM_BYTES_PER_LAUNCH = {"fp16": 46644736 + 787309056, "bf16": 13689344}
 
 
 def main():
@@ -269,16 +271,27 @@ def main():
         k_launches = (lib.nr_launch_count() - lk0) // reps
     k_ms = e0.elapsed_time(e1) / reps
     achieved = n_pts * MFLOP_PER_QUERY_NABLA * 1e6 / (k_ms * 1e-3) / 1e12
+    if precision == "fp16":
+        kname = ("mlp_rev_kernel (fused tcgen05, fp16 operands, reverse-mode normals): sdf + analytic nabla of %d points, "
+                 "%d launch(es), %.3f ms; algorithmic 1.967 MFLOP/query = what the tensor pipe executes (forward sweep + "
+                 "backward sweep)" % (n_pts, k_launches, k_ms))
+        tsrc = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (524288 points, "
+                "profiles/mlp_rev_r1_ncu_summary.txt): 46.6 MB read (the points and the weights once), 787 MB written, of "
+                "which 8.4 MB are outputs and the rest L2 write-backs of the 76 MB softplus' scratch (1.07 GB stored into "
+                "it per launch, L2 hit rate 95 %); algorithmic 14.7 MB")
+    elif precision == "bf16":
+        kname = ("mlp_umma_kernel (fused tcgen05, bf16 operands, forward-mode tangent tiles): sdf + analytic nabla of %d "
+                 "points, %d launch(es), %.3f ms; algorithmic 1.967 MFLOP/query (the tangents execute 4.2 MFLOP/query)"
+                 % (n_pts, k_launches, k_ms))
+        tsrc = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (524288 points, "
+                "profiles/mlp_umma_r1_ncu_524288.txt): 13.7 MB read, 0 written inside the kernel window; algorithmic 14.7 MB")
+    else:
+        kname = "gemm_kernel (fp32 SIMT tier): sdf + analytic nabla of %d points, %d launch(es), %.3f ms" % (
+            n_pts, k_launches, k_ms)
+        tsrc = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH if precision != "fp32" else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch "
-                                  "(524288 points, profiles/mlp_umma_r1_ncu_524288.txt): 13.7 MB read, 0 written inside the "
-                                  "kernel window (the 8.4 MB of outputs leave the L2 later); algorithmic 14.7 MB",
-                "peak_source": pk["src"] + " bf16 burst",
-                "kernel": "%s: sdf + analytic nabla of %d points, %d launch(es), %.3f ms; algorithmic 1.967 "
-                          "MFLOP/query (forward-mode tangents execute 4.2 MFLOP/query on the tensor pipe)"
-                          % ("mlp_umma_kernel (fused tcgen05, %s operands)" % precision if precision != "fp32"
-                             else "gemm_kernel (fp32 SIMT tier)", n_pts, k_launches, k_ms),
+                "frac": achieved / pk["bf16"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(precision),
+                "traffic_source": tsrc, "peak_source": pk["src"] + " bf16 burst", "kernel": kname,
                 "whole_step_frac": (value / world) * MFLOP_PER_RAY * 1e6 / 1e12 / pk["bf16"]}
 
     # ---- second half of BASELINE.json's metric: dense SDF-grid queries (extract_surface, mesh_util.py:82-111) --------

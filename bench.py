@@ -185,6 +185,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when NCCL_DEBUG
+        # is set in the environment) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if args.precision:
         neurecon_b200.set_precision(args.precision)

@@ -294,7 +294,7 @@ class ImplicitSurface(nn.Module):
 
         # bf16 operands keep the tangent tiles: the backward sweep rounds every layer's gradient to 8 bits of mantissa,
         # which lands on the tier's 1e-2 bar (1.06e-2 measured), the forward-mode tangents stay under it
-        rev = _REVERSE_NABLAS and not pair and net.operand == "fp16"
+        rev = _REVERSE_NABLAS and not pair and net.operand == "fp16" and net.rev_ok(want_feat)
         with torch.cuda.device(dev):
             if mode == "split" and rev:
                 p_geo, p_rad = net.program("rev_img"), net.program("radiance")

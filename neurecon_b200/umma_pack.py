@@ -88,7 +88,10 @@ class UmmaNet:
         L = len(surface_W)
         pe = _pe_dim(multires)
         if pe > 64:
-            raise NotImplementedError("bf16 tier: embedding wider than 64 is not supported")
+            raise NotImplementedError("tensor tier: embedding wider than 64 is not supported (use set_precision('fp32'))")
+        if pe > 40 and 0 < skip_layer < L - 1:
+            raise NotImplementedError("tensor tier: a skip connection needs an embedding of at most 40 rows "
+                                      "(embed_multires <= 6); use set_precision('fp32') for this network")
         self.hidden = []
         for l in range(L - 1):
             W, b = surface_W[l], surface_b[l]
@@ -177,6 +180,14 @@ class UmmaNet:
             self.rad = steps
         self.image = torch.cat(chunks, 0).contiguous()
         self.bias = torch.cat(biases, 0).contiguous()
+
+    def rev_ok(self, want_feat=False):
+        """The reverse-mode program (csrc/mlp_rev.cu) keeps the embedding rows in the 40-row stash and has 2 L + 1 (+ 1)
+        steps; anything else runs on the forward-mode tangent tiles."""
+        from . import _lib
+        pe = _pe_dim(self.multires)
+        n_steps = 2 * len(self.hidden) + 1 + (1 if want_feat else 0)
+        return pe <= 40 and pe % 3 == 0 and n_steps <= _lib.NR_UMMA_MAX_STEPS
 
     def pair_ok(self):
         """The CTA-pair kernel needs every step as an M-tile pair (hidden width > 128) and the feature, if any, too."""

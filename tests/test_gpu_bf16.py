@@ -151,6 +151,49 @@ def test_reverse_mode_normals_vs_oracle_and_forward_mode(n, tier):
     assert rel_err(nab, out[False][1]) < 5e-3 and rel_err(rgb, out[False][3]) < 5e-3
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(W=256, D=8, skips=[4], W_geo_feat=256, embed_multires=6),      # configs/neus.yaml
+    dict(W=256, D=8, skips=[], W_geo_feat=256, embed_multires=6),       # no skip connection
+    dict(W=128, D=4, skips=[2], W_geo_feat=128, embed_multires=4),      # one M-tile per layer
+    dict(W=256, D=6, skips=[3], W_geo_feat=64, embed_multires=-1),      # identity embedding
+    dict(W=192, D=5, skips=[1], W_geo_feat=256, embed_multires=2),      # ragged widths
+    dict(W=256, D=8, skips=[], W_geo_feat=256, embed_multires=10),      # 63 embedding rows: tangent tiles serve it
+])
+def test_sdf_net_architectures_tensor_tier(cfg, tier):
+    """ImplicitSurface shapes other than the shipped config through both tensor-tier kernels (reverse-mode and
+    forward-mode normals) against the oracle's autograd normals (base.py:243-282)."""
+    from neurecon_b200.models import base
+    torch.manual_seed(3)
+    net = base.ImplicitSurface(radius_init=0.6, **cfg).to(DEV)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    L = nets.layers_from_state_dict(sd, "surface_fc_layers", cfg["D"] + 1)
+    x = synthetic.make_points(1500, extent=0.9, seed=7)
+    osdf, onab, ofeat = nets.sdf_forward_with_nablas(x, L, cfg["embed_multires"], tuple(cfg["skips"]))
+    old = base._REVERSE_NABLAS
+    try:
+        for rev in (True, False):
+            base._REVERSE_NABLAS = rev
+            with torch.no_grad():
+                sdf, nab, feat = net.forward_with_nablas(x.to(DEV))
+                sdf0 = net.forward(x.to(DEV))
+            torch.cuda.synchronize()
+            errs = dict(sdf=rel_err(sdf, osdf), nab=rel_err(nab, onab), feat=rel_err(feat, ofeat), sdf0=rel_err(sdf0, osdf))
+            tol = 1e-2 if tier == "fp16" else 3e-2
+            assert all(e < tol for e in errs.values()), (rev, errs)
+    finally:
+        base._REVERSE_NABLAS = old
+
+
+def test_unsupported_sdf_net_shape_raises_not_implemented():
+    """A skip connection with a 63-row embedding does not fit the kernels' 40-row stash: the tensor tier says so (the fp32
+    tier serves it), it does not fall back silently."""
+    from neurecon_b200.models import base
+    net = base.ImplicitSurface(W=256, D=8, skips=[4], W_geo_feat=256, embed_multires=10).to(DEV)
+    x = torch.rand(64, 3, device=DEV)
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        net.forward_with_nablas(x)
+
+
 def test_nerfpp_net_tensor_tier_vs_fp32():
     """NeRF++ background MLP (base.py:395-453) as one launch of the fused kernel (split-K skip / view layers) against
     the fp32 tier, on inverted-sphere inputs; ragged sizes."""

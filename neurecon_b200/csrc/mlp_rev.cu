@@ -121,7 +121,7 @@ __device__ __forceinline__ void apply_sig16(const RowAddr& ra, int c, const uint
 __device__ __forceinline__ uint4 ldcg16(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void stcg16(uint8_t* p, uint4 v) { __stcg(reinterpret_cast<uint4*>(p), v); }
 
-template <bool kF16>
+template <bool kF16, bool kShare>
 __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
-      umma::mbar_init(&in_ready[t], kEpiWarpsPerTile);
+      umma::mbar_init(&in_ready[t], kShare ? 2 * kEpiWarpsPerTile : kEpiWarpsPerTile);
       umma::mbar_init(&acc_ready[t], 2);
     }
     umma::fence_barrier_init();
@@ -224,33 +224,33 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue: warps 4-11 own tile slot 0, warps 12-19 tile slot 1 =====================
+    // ===================== epilogue: 16 warps; group g = warps 4-11 / 12-19 owns tile slot g =====================
+    // The owner runs the tile's prologue, its sdf read-out and the Jacobian step.  The wide steps (activation, feature,
+    // backward scaling) of BOTH tiles are drained by BOTH groups, tile 0 first, the owner taking columns [0, 64) and the
+    // other group [64, 128): the activation epilogue is what the tensor pipe waits for, and with it bound to the tile's
+    // own 8 warps only half of the epilogue warps have work while the other tile's MMAs run.
     const int e = warp - kEpiWarp0;                 // 0..15
-    const int t = e >> 3;                           // tile slot
+    const int g = e >> 3;                           // group = the tile slot it owns
     const int mo = (e >> 2) & 1;                    // M-tile this warpgroup owns
     const int q = warp & 3;                         // TMEM lane quarter (hardware: warp id % 4)
     const int etid = (e & 7) * 32 + lane;           // 0..255 inside the group
     const int F = mo * 128 + 32 * q + lane;         // feature = TMEM lane of the owned M-tile
-    uint32_t acc_par = 0;
+    uint32_t acc_par = 0;                           // bit t: parity of acc_ready[t]
     const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
-    uint8_t* act = smem + SmemRev::act + t * kActBytes;
-    float* xs = (float*)(smem + SmemRev::xs) + t * 512;
-    uint8_t* pes = smem + SmemRev::pes + t * (kPeStashRows * 256);
-    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256 + mo * 128);
-    const RowAddr ra(umma::smem_u32(act), F);
-    uint8_t* sig_tile = a.sig + ((size_t)blockIdx.x * 2 + t) * a.n_sig * kSigBytes + (size_t)F * 16;
+    constexpr int kCh = kShare ? 4 : 8;             // 16-column chunks of a tile this warp drains per wide step
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int64_t tile = 2 * pair + t;
-      const int64_t p0 = tile * 128;
-
-      // ---- prologue: stage the points, evaluate the embedding into operand rows [0, k0) and the stash ----
-      for (int i = etid; i < 384; i += kEpiPerTile) {
-        const int64_t gi = p0 * 3 + i;
-        xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
-      }
-      named_bar_sync(1 + t, kEpiPerTile);
       {
+        // ---- prologue (owner): stage the points, evaluate the embedding into operand rows [0, k0) and the stash ----
+        const int64_t p0 = (2 * pair + g) * 128;
+        uint8_t* act = smem + SmemRev::act + g * kActBytes;
+        float* xs = (float*)(smem + SmemRev::xs) + g * 512;
+        uint8_t* pes = smem + SmemRev::pes + g * (kPeStashRows * 256);
+        for (int i = etid; i < 384; i += kEpiPerTile) {
+          const int64_t gi = p0 * 3 + i;
+          xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
+        }
+        named_bar_sync(1 + g, kEpiPerTile);
         const int n = etid & 127;                      // operand column = point
         const int part = etid >> 7;                    // 0..1: splits the rows
         const float x3[3] = {xs[3 * n], xs[3 * n + 1], xs[3 * n + 2]};
@@ -275,181 +275,199 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
           }
         }
         for (int j = pe_dim + part; j < k0; j += 2) store_elem<kF16>(act, j, n, 0.f);
+        publish(&in_ready[g]);
+        if (kShare && lane == 0) umma::mbar_arrive(&in_ready[g ^ 1]);   // nothing of the other tile's operand is ours yet
       }
-      publish(&in_ready[t]);
 
       for (int s = 0; s < P.n_steps; ++s) {
         const nr_umma_step_t& S = P.steps[s];
         const bool mine = mo < S.n_mt;
         const bool is_h = F < S.out_rows;
         const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
-        const uint8_t* sig_rd = sig_tile + (size_t)S.sig_slot * kSigBytes;   // EPI_BWD / EPI_SDF_OUT: the slot to apply
-
-        // softplus' codes of all 128 columns: requested before the accumulator wait (latency under the MMAs)
-        uint4 sg[8];
-        const bool use_sig = ((S.epi == EPI_BWD && mine && is_h) || S.epi == EPI_SDF_OUT) && !(P.debug_flags & 2);
-        if (use_sig) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) sg[c] = ldcg16(sig_rd + c * kSigChunk);
-        }
-
-        wait_tag(&acc_ready[t], acc_par, 4000 + s);
-        acc_par ^= 1u;
-        umma::tc_fence_after();
-
-        if (S.epi == EPI_HIDDEN) {
-          if (mine && !(P.debug_flags & 8)) {
-            const float b = a.bias[S.bias_off + F];
-            const f32x2 b144 = splat2(b * 144.26950408889634f);
-            const int jpe = F - S.out_rows;
-            uint8_t* sig_wr = sig_tile + (size_t)S.sig_slot * kSigBytes;
-            uint32_t raw[16], rawB[16];
-            auto values = [&](const uint32_t (&r)[16], int c) {
-              if (!is_pe) {
-                float v[16];
-                f32x2 d2[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  softplus_sigq2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, v[2 * j], v[2 * j + 1], d2[j]);
-                store_row16<kF16>(ra, 16 * c, v);
-                if (S.to_rad && a.feat_img && tile < n_tiles) img_store16<kF16>(a.feat_img, tile, F, 16 * c, v);
-                const uint4 w = make_uint4(sig_pack4(d2[0], d2[1]), sig_pack4(d2[2], d2[3]), sig_pack4(d2[4], d2[5]),
-                                           sig_pack4(d2[6], d2[7]));
-                if (!(P.debug_flags & 1) || w.x + w.y + w.z + w.w == 0x12345u) stcg16(sig_wr + c * kSigChunk, w);
-              } else {
-                copy_row16(ra, pes, jpe, 16 * c);
-              }
-            };
-            umma::tmem_ld16(taddr, raw);
-#pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-              umma::tmem_ld_wait();
-              umma::tmem_ld16(taddr + 16 * (c + 1), rawB);
-              values(raw, c);
-              umma::tmem_ld_wait();
-              if (c + 2 < 8) umma::tmem_ld16(taddr + 16 * (c + 2), raw);
-              values(rawB, c + 1);
-            }
-          }
-        } else if (S.epi == EPI_FEAT) {
-          if (mine) {
-            const float b = a.bias[S.bias_off + F];
 #pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
-              uint32_t raw[16];
-              umma::tmem_ld16(taddr + 16 * c, raw);
-              umma::tmem_ld_wait();
-              if (a.feat && F < S.out_rows) {
+        for (int v = 0; v < (kShare ? 2 : 1); ++v) {
+          const int t = kShare ? v : g;               // tile slot worked on
+          const bool own = t == g;
+          const int c0 = kShare && !own ? 4 : 0;      // first chunk of this warp's share
+          const int64_t tile = 2 * pair + t;
+          const int64_t p0 = tile * 128;
+          uint8_t* act = smem + SmemRev::act + t * kActBytes;
+          float* xs = (float*)(smem + SmemRev::xs) + t * 512;
+          uint8_t* pes = smem + SmemRev::pes + t * (kPeStashRows * 256);
+          const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256 + mo * 128) + 16u * c0;
+          const RowAddr ra(umma::smem_u32(act), F);
+          uint8_t* sig_slot = a.sig + (((size_t)blockIdx.x * 2 + t) * a.n_sig + S.sig_slot) * kSigBytes + (size_t)F * 16 +
+                              (size_t)c0 * kSigChunk;   // written (EPI_HIDDEN) and read (EPI_BWD, EPI_SDF_OUT) by this thread
+
+          // softplus' codes of this warp's columns: requested before the accumulator wait (latency under the MMAs)
+          uint4 sg[kCh];
+          const bool use_sig = ((S.epi == EPI_BWD && mine && is_h) || S.epi == EPI_SDF_OUT) && !(P.debug_flags & 2);
+          if (use_sig) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int64_t gp = p0 + 16 * c + j;
-                  if (gp < a.n) a.feat[gp * a.feat_ld + F] = __uint_as_float(raw[j]) + b;
+            for (int k = 0; k < kCh; ++k) sg[k] = ldcg16(sig_slot + k * kSigChunk);
+          }
+
+          wait_tag(&acc_ready[t], (acc_par >> t) & 1u, 4000 + s);
+          acc_par ^= 1u << t;
+          umma::tc_fence_after();
+
+          if (S.epi == EPI_HIDDEN) {
+            if (mine && !(P.debug_flags & 8)) {
+              const float b = a.bias[S.bias_off + F];
+              const f32x2 b144 = splat2(b * 144.26950408889634f);
+              const int jpe = F - S.out_rows;
+              uint32_t raw[16], rawB[16];
+              auto values = [&](const uint32_t (&r)[16], int k) {
+                const int c = c0 + k;
+                if (!is_pe) {
+                  float vv[16];
+                  f32x2 d2[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    softplus_sigq2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, vv[2 * j], vv[2 * j + 1], d2[j]);
+                  store_row16<kF16>(ra, 16 * c, vv);
+                  if (S.to_rad && a.feat_img && tile < n_tiles) img_store16<kF16>(a.feat_img, tile, F, 16 * c, vv);
+                  const uint4 w = make_uint4(sig_pack4(d2[0], d2[1]), sig_pack4(d2[2], d2[3]), sig_pack4(d2[4], d2[5]),
+                                             sig_pack4(d2[6], d2[7]));
+                  if (!(P.debug_flags & 1) || w.x + w.y + w.z + w.w == 0x12345u) stcg16(sig_slot + k * kSigChunk, w);
+                } else {
+                  copy_row16(ra, pes, jpe, 16 * c);
                 }
+              };
+              umma::tmem_ld16(taddr, raw);
+#pragma unroll
+              for (int k = 0; k < kCh; k += 2) {
+                umma::tmem_ld_wait();
+                umma::tmem_ld16(taddr + 16 * (k + 1), rawB);
+                values(raw, k);
+                umma::tmem_ld_wait();
+                if (k + 2 < kCh) umma::tmem_ld16(taddr + 16 * (k + 2), raw);
+                values(rawB, k + 1);
               }
             }
-          }
-        } else if (S.epi == EPI_SDF_OUT) {
-          // rows 0..31 of M-tile 0 all hold the sdf row: lane l keeps column l of each 32-column chunk
-          if (mo == 0 && q == 0 && a.sdf) {
-            const float b = a.bias[S.bias_off];
+          } else if (S.epi == EPI_FEAT) {
+            if (mine) {
+              const float b = a.bias[S.bias_off + F];
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t raw[32];
-              umma::tmem_ld32(taddr + 32 * c, raw);
-              umma::tmem_ld_wait();
-              float m = 0.0f;
+              for (int k = 0; k < kCh; ++k) {
+                uint32_t raw[16];
+                umma::tmem_ld16(taddr + 16 * k, raw);
+                umma::tmem_ld_wait();
+                if (a.feat && F < S.out_rows) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) m = (lane == j) ? __uint_as_float(raw[j]) : m;
-              const int64_t gp = p0 + 32 * c + lane;
-              if (gp < a.n) a.sdf[gp] = m + b;
-            }
-          }
-          // start of the backward pass: operand row F <- softplus'(z_last)[F, :] * w_sdf[F]  (d sdf / d z_last)
-          const float wF = a.bias[S.aux_off + F];
-          const uint32_t none[16] = {};
-#pragma unroll
-          for (int c = 0; c < 8; ++c) apply_sig16<kF16, false>(ra, c, none, sg[c], wF);
-        } else if (S.epi == EPI_BWD) {
-          if (mine && !(P.debug_flags & 4)) {
-            uint32_t raw[16], rawB[16];
-            const int jpe = F - S.out_rows;
-            auto apply = [&](const uint32_t (&r)[16], int c) {
-              if (is_h) {
-                apply_sig16<kF16, true>(ra, c, r, sg[c], 1.0f);
-              } else {
-                if (is_pe) {   // gradient w.r.t. the skip connection's copy of the embedding: kept for EPI_NABLA
-                  uint32_t h[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) h[j] = umma::pack2<kF16>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                  uint4* dst = reinterpret_cast<uint4*>(pes + jpe * 256 + c * 32);
-                  dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                  dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
-                }
-                st_shared_v4(ra.chunk(2 * c), 0, 0, 0, 0);       // these rows meet zero weights; keep them finite
-                st_shared_v4(ra.chunk(2 * c + 1), 0, 0, 0, 0);
-              }
-            };
-            umma::tmem_ld16(taddr, raw);
-#pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-              umma::tmem_ld_wait();
-              umma::tmem_ld16(taddr + 16 * (c + 1), rawB);
-              apply(raw, c);
-              umma::tmem_ld_wait();
-              if (c + 2 < 8) umma::tmem_ld16(taddr + 16 * (c + 2), raw);
-              apply(rawB, c + 1);
-            }
-          }
-        } else if (S.epi == EPI_NABLA) {
-          // acc rows [0, pe_dim) = d sdf / d PE(x) through layer 0 (+ the skip layer's share from the stash);
-          // nabla_c = sum_j dPE_j/dx_c * g_j: products to a [point][row] scratch in the (now free) operand buffer
-          float* red = reinterpret_cast<float*>(act);
-          if (32 * q < pe_dim) {   // warp-uniform (the TMEM loads are .sync.aligned); both warps of a lane quarter work,
-            const int R = 32 * q + lane;                       // each on half of the columns of M-tile 0
-            const int comp = R < 3 ? R : (R - 3) % 3;
-            const int qf = R < 3 ? 0 : (R - 3) / 6;
-            const bool is_sin = R >= 3 && ((R - 3) % 6) < 3;
-            const float f = (float)(1 << qf);
-            const uint16_t* srow = reinterpret_cast<const uint16_t*>(pes + R * 256);
-            const uint32_t taddr0 = taddr - (uint32_t)(mo * 128);
-#pragma unroll 1
-            for (int c = 4 * mo; c < 4 * mo + 4; ++c) {
-              uint32_t raw[16];
-              umma::tmem_ld16(taddr0 + 16 * c, raw);
-              umma::tmem_ld_wait();
-              if (R < pe_dim) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int col = 16 * c + j;
-                  float g = __uint_as_float(raw[j]);
-                  if (S.pe_fill) {
-                    const uint16_t hv = srow[col];
-                    g += kF16 ? __half2float(__ushort_as_half(hv)) : __uint_as_float((uint32_t)hv << 16);
+                  for (int j = 0; j < 16; ++j) {
+                    const int64_t gp = p0 + 16 * (c0 + k) + j;
+                    if (gp < a.n) a.feat[gp * a.feat_ld + F] = __uint_as_float(raw[j]) + b;
                   }
-                  float jac = 1.0f;
-                  if (R >= 3) {
-                    float sn, cs;
-                    __sincosf(xs[3 * col + comp] * f, &sn, &cs);
-                    jac = is_sin ? f * cs : -f * sn;
-                  }
-                  red[col * kRedLd + R] = g * jac;
                 }
               }
             }
+          } else if (S.epi == EPI_SDF_OUT) {
+            // rows 0..31 of M-tile 0 all hold the sdf row: lane l keeps column l of each 32-column chunk (owner's warp 0)
+            if (own && mo == 0 && q == 0 && a.sdf) {
+              const float b = a.bias[S.bias_off];
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32];
+                umma::tmem_ld32(taddr + 32 * c, raw);
+                umma::tmem_ld_wait();
+                float m = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m = (lane == j) ? __uint_as_float(raw[j]) : m;
+                const int64_t gp = p0 + 32 * c + lane;
+                if (gp < a.n) a.sdf[gp] = m + b;
+              }
+            }
+            // start of the backward pass: operand row F <- softplus'(z_last)[F, :] * w_sdf[F]  (d sdf / d z_last)
+            const float wF = a.bias[S.aux_off + F];
+            const uint32_t none[16] = {};
+#pragma unroll
+            for (int k = 0; k < kCh; ++k) apply_sig16<kF16, false>(ra, c0 + k, none, sg[k], wF);
+          } else if (S.epi == EPI_BWD) {
+            if (mine && !(P.debug_flags & 4)) {
+              uint32_t raw[16], rawB[16];
+              const int jpe = F - S.out_rows;
+              auto apply = [&](const uint32_t (&r)[16], int k) {
+                const int c = c0 + k;
+                if (is_h) {
+                  apply_sig16<kF16, true>(ra, c, r, sg[k], 1.0f);
+                } else {
+                  if (is_pe) {   // gradient w.r.t. the skip connection's copy of the embedding: kept for EPI_NABLA
+                    uint32_t h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) h[j] = umma::pack2<kF16>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                    uint4* dst = reinterpret_cast<uint4*>(pes + jpe * 256 + c * 32);
+                    dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                    dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                  }
+                  st_shared_v4(ra.chunk(2 * c), 0, 0, 0, 0);       // these rows meet zero weights; keep them finite
+                  st_shared_v4(ra.chunk(2 * c + 1), 0, 0, 0, 0);
+                }
+              };
+              umma::tmem_ld16(taddr, raw);
+#pragma unroll
+              for (int k = 0; k < kCh; k += 2) {
+                umma::tmem_ld_wait();
+                umma::tmem_ld16(taddr + 16 * (k + 1), rawB);
+                apply(raw, k);
+                umma::tmem_ld_wait();
+                if (k + 2 < kCh) umma::tmem_ld16(taddr + 16 * (k + 2), raw);
+                apply(rawB, k + 1);
+              }
+            }
+          } else if (S.epi == EPI_NABLA && own) {
+            // acc rows [0, pe_dim) = d sdf / d PE(x) through layer 0 (+ the skip layer's share from the stash);
+            // nabla_c = sum_j dPE_j/dx_c * g_j: products to a [point][row] scratch in the (now free) operand buffer
+            float* red = reinterpret_cast<float*>(act);
+            if (32 * q < pe_dim) {   // warp-uniform (the TMEM loads are .sync.aligned); both warps of a lane quarter work,
+              const int Rr = 32 * q + lane;                      // each on half of the columns of M-tile 0
+              const int comp = Rr < 3 ? Rr : (Rr - 3) % 3;
+              const int qf = Rr < 3 ? 0 : (Rr - 3) / 6;
+              const bool is_sin = Rr >= 3 && ((Rr - 3) % 6) < 3;
+              const float f = (float)(1 << qf);
+              const uint16_t* srow = reinterpret_cast<const uint16_t*>(pes + Rr * 256);
+              const uint32_t taddr0 = taddr - (uint32_t)(mo * 128);
+#pragma unroll 1
+              for (int c = 4 * mo; c < 4 * mo + 4; ++c) {
+                uint32_t raw[16];
+                umma::tmem_ld16(taddr0 + 16 * c, raw);
+                umma::tmem_ld_wait();
+                if (Rr < pe_dim) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const int col = 16 * c + j;
+                    float gv = __uint_as_float(raw[j]);
+                    if (S.pe_fill) {
+                      const uint16_t hv = srow[col];
+                      gv += kF16 ? __half2float(__ushort_as_half(hv)) : __uint_as_float((uint32_t)hv << 16);
+                    }
+                    float jac = 1.0f;
+                    if (Rr >= 3) {
+                      float sn, cs;
+                      __sincosf(xs[3 * col + comp] * f, &sn, &cs);
+                      jac = is_sin ? f * cs : -f * sn;
+                    }
+                    red[col * kRedLd + Rr] = gv * jac;
+                  }
+                }
+              }
+            }
+            named_bar_sync(1 + g, kEpiPerTile);
+            if (etid < 128) {
+              const float* r = red + etid * kRedLd;
+              float g0 = r[0], g1 = r[1], g2 = r[2];
+              for (int j = 3; j < pe_dim; j += 3) { g0 += r[j]; g1 += r[j + 1]; g2 += r[j + 2]; }
+              const int64_t gp = p0 + etid;
+              if (gp < a.n) { a.nabla[gp * 3] = g0; a.nabla[gp * 3 + 1] = g1; a.nabla[gp * 3 + 2] = g2; }
+            }
           }
-          named_bar_sync(1 + t, kEpiPerTile);
-          if (etid < 128) {
-            const float* r = red + etid * kRedLd;
-            float g0 = r[0], g1 = r[1], g2 = r[2];
-            for (int j = 3; j < pe_dim; j += 3) { g0 += r[j]; g1 += r[j + 1]; g2 += r[j + 2]; }
-            const int64_t gp = p0 + etid;
-            if (gp < a.n) { a.nabla[gp * 3] = g0; a.nabla[gp * 3 + 1] = g1; a.nabla[gp * 3 + 2] = g2; }
-          }
+          if (s + 1 < P.n_steps) publish(&in_ready[t]);
         }
-        if (s + 1 < P.n_steps) publish(&in_ready[t]);
       }
       umma::tc_fence_before();
-      named_bar_sync(1 + t, kEpiPerTile);   // staging buffers and the TMEM slot are free before the next pair
+      // staging buffers and TMEM slots are free before the next pair's prologue
+      if (kShare) named_bar_sync(3, 2 * kEpiPerTile);
+      else named_bar_sync(1 + g, kEpiPerTile);
     }
   }
 
@@ -544,15 +562,25 @@ extern "C" int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* im
   const size_t smem = SmemRev::total + 1024;
   static unsigned long long attr_set = 0;  // per-device bit: the attribute is per (function, device)
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set |= 1ull << (dev & 63);
   }
   DevProgram dp;
   dp.p = *prog;
   RevArgs ka{(const uint8_t*)image, bias, x, n, sdf, nabla, feat, feat_ld, (uint8_t*)feat_img, (uint8_t*)workspace, n_sig};
-  if (prog->operand_f16) mlp_rev_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
-  else mlp_rev_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+  static int share = -1;   // NEURECON_B200_REV_SHARE=0: every tile's epilogue on its own 8 warps (for measurements)
+  if (share < 0) { const char* ev = getenv("NEURECON_B200_REV_SHARE"); share = ev ? atoi(ev) != 0 : 1; }
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (prog->operand_f16) {
+    if (share) mlp_rev_kernel<true, true><<<grid, kThreads, smem, st>>>(dp, ka);
+    else mlp_rev_kernel<true, false><<<grid, kThreads, smem, st>>>(dp, ka);
+  } else {
+    if (share) mlp_rev_kernel<false, true><<<grid, kThreads, smem, st>>>(dp, ka);
+    else mlp_rev_kernel<false, false><<<grid, kThreads, smem, st>>>(dp, ka);
+  }
   NR_CHECK_LAUNCH("mlp_rev_kernel");
   return NR_OK;
 }

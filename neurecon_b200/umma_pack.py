@@ -178,6 +178,15 @@ class UmmaNet:
             if steps[-1]["out_rows"] != 3:
                 raise NotImplementedError("bf16 tier: radiance output must be rgb")
             self.rad = steps
+            # the geometry-feature layer is linear and feeds only radiance layer 0: folded into it for the radiance pass
+            # that starts from the last hidden SDF activations (program 'radiance'):
+            #   W0[:, feat] (W_f h + b_f) = (W0[:, feat] W_f) h + W0[:, feat] b_f      -- one K = 256 layer less per point
+            W0f = W0[:, n_extra:].double()
+            Wfold = (W0f @ Wl[1:].double()).float()
+            bfold = (rad_b[0].double() + W0f @ bl[1:].double()).float()
+            kf = (Wfold.shape[1] + 63) // 64 * 4
+            c0, b0 = add(Wfold, bfold, kf, (Wfold.shape[0] + 127) // 128)
+            self.rad_fold = dict(steps[0], chunk_begin=c0, bias_off=b0, k_steps=kf)
         self.image = torch.cat(chunks, 0).contiguous()
         self.bias = torch.cat(biases, 0).contiguous()
 
@@ -204,10 +213,12 @@ class UmmaNet:
             # 'radiancef': the image holds the feature itself (written by an EPI_FEAT step, 'nablas_imgf')
             assert self.rad is not None
             r0 = self.rad[0]
-            steps = [dict(self.feat, epi=EPI_LINEAR, n_cols=128)] if mode == "radiance" else []
-            steps += [dict(r0, k_steps=16, epi=EPI_EXTRAS, n_cols=128),
-                      dict(r0, chunk_begin=r0["chunk_begin"] + r0["n_mt"] * 4, k_steps=self.rad_extra_rows // 16,
-                           accumulate=1, n_cols=128)]
+            extras = dict(r0, chunk_begin=r0["chunk_begin"] + r0["n_mt"] * 4, k_steps=self.rad_extra_rows // 16,
+                          accumulate=1, n_cols=128)
+            if mode == "radiance":     # image = last hidden activations: feature layer folded into layer 0
+                steps = [dict(self.rad_fold, epi=EPI_EXTRAS, n_cols=128), dict(extras, bias_off=self.rad_fold["bias_off"])]
+            else:
+                steps = [dict(r0, k_steps=16, epi=EPI_EXTRAS, n_cols=128), extras]
             steps += [dict(s, n_cols=128) for s in self.rad[1:]]
             return self._finish(steps, tang=0, input_mode=1)
         if mode in ("rev", "rev_img"):

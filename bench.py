@@ -185,8 +185,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when NCCL_DEBUG
-        # is set in the environment) goes to stderr
+        # stdout carries exactly one JSON line: with NCCL_DEBUG=VERSION in the environment NCCL printf()s its banner
+        # ("NCCL version ...") to stdout, whatever NCCL_DEBUG_FILE says; other debug levels go to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if args.precision:

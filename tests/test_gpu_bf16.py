@@ -184,6 +184,37 @@ def test_sdf_net_architectures_tensor_tier(cfg, tier):
         base._REVERSE_NABLAS = old
 
 
+def test_reverse_entry_point_argument_checks():
+    """nr_mlp_umma_reverse: n = 0 is a no-op, a too small scratch and a forward-mode program are refused with a message
+    (no launch, no crash)."""
+    from neurecon_b200 import _lib
+    from neurecon_b200._lib import C
+    if neurecon_b200.get_precision() != "fp16":
+        pytest.skip("one tier is enough")
+    lib = _lib.get_lib()
+    m = build_neus(seed=1, device=DEV)
+    net = m.implicit_surface._umma_net(None)
+    prog = net.program("rev", want_feat=True)
+    n = 300
+    x = torch.rand(n, 3, device=DEV)
+    sdf, nab = torch.empty(n, device=DEV), torch.empty(n, 3, device=DEV)
+    need = lib.nr_mlp_umma_reverse_workspace(C.byref(prog), n)
+    assert need > 0 and need % 32768 == 0
+    ws = torch.empty(need, dtype=torch.uint8, device=DEV)
+    st = _lib.stream_ptr(torch.device(DEV))
+
+    def call(p, count, ws_bytes):
+        return lib.nr_mlp_umma_reverse(C.byref(p), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias),
+                                       net.bias.numel(), _lib.ptr(x), count, _lib.ptr(sdf), _lib.ptr(nab), None, 256, None,
+                                       _lib.ptr(ws), ws_bytes, st)
+    assert call(prog, 0, need) == 0
+    assert call(prog, n, need) == 0
+    assert call(prog, n, need - 1) != 0 and "workspace" in _lib.last_error()
+    assert call(net.program("nablas"), n, need) != 0 and "reverse-mode program" in _lib.last_error()
+    torch.cuda.synchronize()
+    assert torch.isfinite(nab).all()
+
+
 def test_unsupported_sdf_net_shape_raises_not_implemented():
     """A skip connection with a 63-row embedding does not fit the kernels' 40-row stash: the tensor tier says so (the fp32
     tier serves it), it does not fall back silently."""

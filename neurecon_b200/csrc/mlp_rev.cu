@@ -13,7 +13,7 @@
 // back a few microseconds later by THE SAME THREAD in the backward epilogue (no fences needed), 76 MB for the whole
 // grid, which stays in the 126 MB L2 (with 16-bit codes the 148 MB scratch cycled through HBM: ncu, profiles/).
 // softplus(beta = 100)' is a logistic that sits at 0 or 1 for most units, which the code represents exactly; the
-// quantisation (|err| <= 1/508) costs 1.2e-3 rms on the normal (fp64 model of the kernel, tools/check_rev.py).
+// quantisation (|err| <= 1/508) costs 1.2e-3 rms on the normal (fp64 model of the kernel: tests/test_rev_code_model.py).
 // All loads of a step are issued before the thread waits for its accumulator: their latency hides under the MMAs.
 //
 // Steps (nr_umma_program_t, reverse = 1): EPI_HIDDEN x L (sig_slot = layer), [EPI_FEAT], EPI_SDF_OUT (sdf to global,

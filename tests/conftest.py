@@ -55,5 +55,32 @@ def build_neus(seed=1, device="cpu"):
     return m.to(device)
 
 
+def build_volsdf(beta_init=0.1, nerfpp=False, seed=3, device="cpu"):
+    from neurecon_b200.models.frameworks import volsdf
+    from neurecon_b200.utils import synthetic
+    torch.manual_seed(0)
+    m = volsdf.VolSDF(**dict(synthetic.VOLSDF_MODEL_KWARGS, beta_init=beta_init, use_nerfplusplus=nerfpp))
+    synthetic.reseed_parameters(m, seed=seed)
+    return m.to(device)
+
+
+def build_unisurf(seed=4, device="cpu"):
+    from neurecon_b200.models.frameworks import unisurf
+    from neurecon_b200.utils import synthetic
+    torch.manual_seed(0)
+    m = unisurf.UNISURF(**synthetic.UNISURF_MODEL_KWARGS)
+    synthetic.reseed_parameters(m, seed=seed)
+    return m.to(device)
+
+
+def build_neus_bg(seed=5, device="cpu"):
+    from neurecon_b200.models.frameworks import neus
+    from neurecon_b200.utils import synthetic
+    torch.manual_seed(0)
+    m = neus.NeuS(**dict(synthetic.NEUS_MODEL_KWARGS, use_outside_nerf=True))
+    synthetic.reseed_parameters(m, seed=seed)
+    return m.to(device)
+
+
 def cpu_state_dict(model):
     return {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import NEUS_CFG, build_neus, cpu_state_dict, frac_close, load_golden, rel_err
+from conftest import (NEUS_CFG, build_neus, build_neus_bg, build_unisurf, build_volsdf, cpu_state_dict, frac_close,
+                      load_golden, rel_err)
 from oracle import nets, neus as oneus, ref_loader, sampling
 from neurecon_b200.utils import synthetic
 
@@ -104,20 +105,8 @@ VOLSDF_CFG = dict(multires=6, multires_view=-1, rad_multires=-1, skips=[4], D=8,
 UNISURF_CFG = dict(multires=6, multires_view=-1, rad_multires=-1, skips=[4], D=8, D_rad=4)
 
 
-def build_volsdf(beta_init=0.1, nerfpp=False, seed=3, device="cpu"):
-    from neurecon_b200.models.frameworks import volsdf
-    torch.manual_seed(0)
-    m = volsdf.VolSDF(**dict(synthetic.VOLSDF_MODEL_KWARGS, beta_init=beta_init, use_nerfplusplus=nerfpp))
-    synthetic.reseed_parameters(m, seed=seed)
-    return m.to(device)
 
 
-def build_unisurf(seed=4, device="cpu"):
-    from neurecon_b200.models.frameworks import unisurf
-    torch.manual_seed(0)
-    m = unisurf.UNISURF(**synthetic.UNISURF_MODEL_KWARGS)
-    synthetic.reseed_parameters(m, seed=seed)
-    return m.to(device)
 
 
 def test_volsdf_error_bound_golden():
@@ -169,12 +158,6 @@ def test_unisurf_render_golden():
         assert frac_close(ret[k], g[k], 1e-4) > 0.97, k
 
 
-def build_neus_bg(seed=5, device="cpu"):
-    from neurecon_b200.models.frameworks import neus
-    torch.manual_seed(0)
-    m = neus.NeuS(**dict(synthetic.NEUS_MODEL_KWARGS, use_outside_nerf=True))
-    synthetic.reseed_parameters(m, seed=seed)
-    return m.to(device)
 
 
 def test_neus_nerfpp_render_golden():

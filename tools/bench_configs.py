@@ -6,8 +6,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import neurecon_b200
-from test_oracle_golden import build_neus_bg, build_unisurf, build_volsdf
-from conftest import build_neus
+from conftest import build_neus, build_neus_bg, build_unisurf, build_volsdf
 from neurecon_b200.models.frameworks import neus, unisurf, volsdf
 from neurecon_b200.utils import mesh_util, synthetic
 

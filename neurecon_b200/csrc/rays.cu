@@ -7,6 +7,7 @@
 // Reference semantics: utils/rend_util.py:167-185,255-327 and
 // models/frameworks/neus.py:21-70,184-210,249-288,296,346-381.
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace {
 
@@ -323,6 +324,7 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f,
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+template <int kSeg>   // intervals per lane: ceil((M - 1) / 32) <= kSeg (every unrolled iteration costs issue slots, used or not)
 __global__ void neus_composite_staged_kernel(const float* __restrict__ sdf, const float* __restrict__ nablas,
                                              const float* __restrict__ radiance, const float* __restrict__ d_mid,
                                              const float* __restrict__ s_dev, int64_t R, int M, int white_bkgd,
@@ -352,12 +354,32 @@ __global__ void neus_composite_staged_kernel(const float* __restrict__ sdf, cons
       for (int i = threadIdx.x; i < n; i += blockDim.x) cp_async4(dst + i, g + i);
     }
   };
-  stage_in(s_sd, sdf, M);
-  if (nablas) stage_in(s_nb, nablas, 3 * M);
-  stage_in(s_rad, radiance, 3 * M1);
-  stage_in(s_dm, d_mid, M1);
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
+  if (vec16 && nrays == kWarpsPerBlock) {
+    // full block, aligned inputs: four bulk copies (TMA unit) issued by one thread instead of 1024 16-byte cp.async
+    // spread over the block -- the kernel is bound by instruction issue, and this is ~5 % of its instructions
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+      umma::mbar_init(&bar, 1);
+      umma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t b_sd = 4u * M * 4u, b_nb = nablas ? 12u * M * 4u : 0u, b_rad = 12u * M1 * 4u, b_dm = 4u * M1 * 4u;
+      umma::mbar_arrive_expect_tx(&bar, b_sd + b_nb + b_rad + b_dm);
+      umma::bulk_g2s(s_sd, sdf + ray0 * (int64_t)M, b_sd, &bar);
+      if (nablas) umma::bulk_g2s(s_nb, nablas + ray0 * (int64_t)(3 * M), b_nb, &bar);
+      umma::bulk_g2s(s_rad, radiance + ray0 * (int64_t)(3 * M1), b_rad, &bar);
+      umma::bulk_g2s(s_dm, d_mid + ray0 * (int64_t)M1, b_dm, &bar);
+    }
+    umma::mbar_wait(&bar, 0);
+  } else {
+    stage_in(s_sd, sdf, M);
+    if (nablas) stage_in(s_nb, nablas, 3 * M);
+    stage_in(s_rad, radiance, 3 * M1);
+    stage_in(s_dm, d_mid, M1);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+  }
   if (ray >= R) return;
   const float* sd = s_sd + warp * M;
   const float* nb = s_nb + warp * 3 * M;
@@ -368,7 +390,6 @@ __global__ void neus_composite_staged_kernel(const float* __restrict__ sdf, cons
   // lane l owns the kSeg consecutive intervals [kSeg l, kSeg l + kSeg): one logistic per sample, a serial product
   // inside the lane and ONE multiplicative warp scan over the lane products (5 shuffles per ray instead of 5 per
   // 32 intervals)
-  constexpr int kSeg = (kStagedMaxM + 31) / 32;
   const int seg = (M1 + 31) >> 5;                     // intervals per lane (<= kSeg)
   const int i0 = lane * seg;
   float alpha[kSeg], tr[kSeg];                        // alpha_i and the transmittance before interval i inside the lane
@@ -720,12 +741,18 @@ extern "C" int nr_neus_composite(const float* sdf, const float* nablas, const fl
     const size_t smem = (size_t)kWarpsPerBlock * 8 * M * sizeof(float);
     static bool carve = false;   // 16 KB per 4-warp block: ask for the large shared-memory carve-out so 13 blocks fit per SM
     if (!carve) {
-      cudaFuncSetAttribute(neus_composite_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(neus_composite_staged_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(neus_composite_staged_kernel<(kStagedMaxM + 31) / 32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       carve = true;
     }
-    neus_composite_staged_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
-        sdf, nablas, radiance, d_mid, s_dev, R, M, white_bkgd, rgb, depth, acc, normals, cdf_out, alpha_out, weights_out,
-        ((((uintptr_t)sdf | (uintptr_t)nablas | (uintptr_t)radiance | (uintptr_t)d_mid) & 15) == 0) ? 1 : 0);
+    const int vec16 = ((((uintptr_t)sdf | (uintptr_t)nablas | (uintptr_t)radiance | (uintptr_t)d_mid) & 15) == 0) ? 1 : 0;
+    const unsigned grid = (unsigned)nr_cdiv(R, kWarpsPerBlock);
+    if (M - 1 <= 4 * 32)   // 64 + 64 samples (every shipped NeuS config): 4 intervals per lane
+      neus_composite_staged_kernel<4><<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+          sdf, nablas, radiance, d_mid, s_dev, R, M, white_bkgd, rgb, depth, acc, normals, cdf_out, alpha_out, weights_out, vec16);
+    else
+      neus_composite_staged_kernel<(kStagedMaxM + 31) / 32><<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+          sdf, nablas, radiance, d_mid, s_dev, R, M, white_bkgd, rgb, depth, acc, normals, cdf_out, alpha_out, weights_out, vec16);
     NR_CHECK_LAUNCH("neus_composite_staged_kernel");
     return NR_OK;
   }

@@ -7,6 +7,7 @@
 // Reference semantics: models/frameworks/volsdf.py:16-35 (sdf_to_sigma), :38-74 (error_bound),
 // :77-272 (fine_sample), :402-417,436-443 (ray setup / merge), :452-503 (compositing).
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace {
 
@@ -443,7 +444,8 @@ __global__ void volsdf_composite_kernel(const float* __restrict__ sdf, const flo
 // computed here.
 // ---------------------------------------------------------------------------------------------
 constexpr int kVsMaxIn = 256, kVsMaxOut = 64;
-constexpr int kVsSeg = (kVsMaxIn + kVsMaxOut + 31) / 32;
+constexpr int kVsSegMax = (kVsMaxIn + kVsMaxOut + 31) / 32;
+template <int kVsSeg>   // samples per lane: ceil(M / 32) <= kVsSeg (every unrolled iteration costs issue slots, used or not)
 __global__ void volsdf_composite_staged_kernel(const float* __restrict__ sdf, const float* __restrict__ nablas,
                                                const float* __restrict__ radiance, const float* __restrict__ d_in,
                                                const float* __restrict__ alpha_dev, const float* __restrict__ beta_dev,
@@ -474,17 +476,42 @@ __global__ void volsdf_composite_staged_kernel(const float* __restrict__ sdf, co
     for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(g + i) : "memory");
   };
-  stage_in(s_sd, sdf, M_in);
-  stage_in(s_d, d_in, M_in);
-  stage_in(s_rad, radiance, 3 * M_in);
-  if (nablas) stage_in(s_nb, nablas, 3 * M_in);
-  if (M_out > 0) {
-    stage_in(s_so, sigma_out, M_out);
-    stage_in(s_do, d_out, M_out);
-    stage_in(s_ro, radiance_out, 3 * M_out);
+  if (vec16 && nrays == 4) {
+    // full block, aligned inputs: one thread issues the bulk copies (TMA unit); spread over the block as 16-byte
+    // cp.async the staging alone was ~5 % of the instructions of an issue-bound kernel
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+      umma::mbar_init(&bar, 1);
+      umma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t b1 = 16u * M_in, b3 = 48u * M_in, o1 = 16u * M_out, o3 = 48u * M_out;
+      umma::mbar_arrive_expect_tx(&bar, 2 * b1 + b3 + (nablas ? b3 : 0u) + (M_out > 0 ? 2 * o1 + o3 : 0u));
+      umma::bulk_g2s(s_sd, sdf + ray0 * (int64_t)M_in, b1, &bar);
+      umma::bulk_g2s(s_d, d_in + ray0 * (int64_t)M_in, b1, &bar);
+      umma::bulk_g2s(s_rad, radiance + ray0 * (int64_t)(3 * M_in), b3, &bar);
+      if (nablas) umma::bulk_g2s(s_nb, nablas + ray0 * (int64_t)(3 * M_in), b3, &bar);
+      if (M_out > 0) {
+        umma::bulk_g2s(s_so, sigma_out + ray0 * (int64_t)M_out, o1, &bar);
+        umma::bulk_g2s(s_do, d_out + ray0 * (int64_t)M_out, o1, &bar);
+        umma::bulk_g2s(s_ro, radiance_out + ray0 * (int64_t)(3 * M_out), o3, &bar);
+      }
+    }
+    umma::mbar_wait(&bar, 0);
+  } else {
+    stage_in(s_sd, sdf, M_in);
+    stage_in(s_d, d_in, M_in);
+    stage_in(s_rad, radiance, 3 * M_in);
+    if (nablas) stage_in(s_nb, nablas, 3 * M_in);
+    if (M_out > 0) {
+      stage_in(s_so, sigma_out, M_out);
+      stage_in(s_do, d_out, M_out);
+      stage_in(s_ro, radiance_out, 3 * M_out);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
   if (ray >= R) return;
   const float* sd = s_sd + warp * M_in;
   const float* dd = s_d + warp * M_in;
@@ -658,13 +685,22 @@ extern "C" int nr_volsdf_composite(const float* sdf, const float* nablas, const 
   NR_CHECK_ARG(M_out == 0 || (sigma_out && radiance_out && d_out), "nr_volsdf_composite: outside samples missing");
   if (M_in <= kVsMaxIn && M_out <= kVsMaxOut) {
     const size_t smem = (size_t)4 * (8 * M_in + 5 * M_out) * sizeof(float);
-    int rc = set_smem((const void*)volsdf_composite_staged_kernel, smem, "nr_volsdf_composite");
-    if (rc) return rc;
     uintptr_t al = (uintptr_t)sdf | (uintptr_t)radiance | (uintptr_t)d_in | (uintptr_t)nablas;
     if (M_out > 0) al |= (uintptr_t)sigma_out | (uintptr_t)radiance_out | (uintptr_t)d_out;
-    volsdf_composite_staged_kernel<<<(unsigned)nr_cdiv(R, 4), 128, smem, (cudaStream_t)stream>>>(
-        sdf, nablas, radiance, d_in, alpha_dev, beta_dev, R, M_in, sigma_out, radiance_out, d_out, M_out, white_bkgd, rgb,
-        depth, acc, normals, sigma_all, p_out, tau_out, (al & 15) == 0 ? 1 : 0);
+    const int vec16 = (al & 15) == 0 ? 1 : 0;
+    const int seg = (M_in + M_out + 31) / 32;
+#define NR_VS_LAUNCH(SEG)                                                                                              \
+  do {                                                                                                                 \
+    int rc = set_smem((const void*)volsdf_composite_staged_kernel<SEG>, smem, "nr_volsdf_composite");                   \
+    if (rc) return rc;                                                                                                 \
+    volsdf_composite_staged_kernel<SEG><<<(unsigned)nr_cdiv(R, 4), 128, smem, (cudaStream_t)stream>>>(                  \
+        sdf, nablas, radiance, d_in, alpha_dev, beta_dev, R, M_in, sigma_out, radiance_out, d_out, M_out, white_bkgd,  \
+        rgb, depth, acc, normals, sigma_all, p_out, tau_out, vec16);                                                   \
+  } while (0)
+    if (seg <= 6) NR_VS_LAUNCH(6);            // 128 + 64 samples (configs/volsdf.yaml)
+    else if (seg <= 7) NR_VS_LAUNCH(7);       // + 32 NeRF++ samples
+    else NR_VS_LAUNCH(kVsSegMax);
+#undef NR_VS_LAUNCH
     NR_CHECK_LAUNCH("volsdf_composite_staged_kernel");
     return NR_OK;
   }

@@ -4,6 +4,7 @@
 // Reference semantics: models/ray_casting.py:11-30 (secant), :35-160 (root_finding_surface_points),
 // models/frameworks/unisurf.py:124-131 (near/far), :147-203 (samplers), :216-240 (compositing).
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace {
 
@@ -249,6 +250,117 @@ __global__ void unisurf_composite_kernel(const float* __restrict__ logits, const
   }
 }
 
+// Staged variant (M <= kUsMaxM), the structure of the NeuS / VolSDF compositing kernels: the block's four rays arrive by
+// bulk copies issued by one thread (or 16-byte cp.async when a pointer is unaligned / the block is ragged), each lane owns
+// ceil(M/32) CONSECUTIVE samples, one multiplicative warp scan per ray.  These kernels are bound by instruction issue.
+// alpha keeps the IEEE division: inf / inf = NaN for logits below ~ -88.7 is the reference's behaviour.
+constexpr int kUsMaxM = 256;
+template <int kSeg>
+__global__ void unisurf_composite_staged_kernel(const float* __restrict__ logits, const float* __restrict__ nablas,
+                                                const float* __restrict__ radiance, const float* __restrict__ d_all,
+                                                int64_t R, int M, int white_bkgd, float* __restrict__ rgb,
+                                                float* __restrict__ depth, float* __restrict__ acc,
+                                                float* __restrict__ normals, float* __restrict__ alpha_out,
+                                                float* __restrict__ w_out, int vec16) {
+  extern __shared__ __align__(16) float ustage[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray0 = blockIdx.x * (int64_t)4, ray = ray0 + warp;
+  const int nrays = (int)((R - ray0) < 4 ? (R - ray0) : 4);
+  float* s_lg = ustage;                 // [4][M]
+  float* s_d = s_lg + 4 * M;            // [4][M]
+  float* s_rad = s_d + 4 * M;           // [4][3M]
+  float* s_nb = s_rad + 12 * M;         // [4][3M]
+  if (vec16 && nrays == 4) {
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+      umma::mbar_init(&bar, 1);
+      umma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t b1 = 16u * M, b3 = 48u * M;
+      umma::mbar_arrive_expect_tx(&bar, 2 * b1 + b3 + (nablas ? b3 : 0u));
+      umma::bulk_g2s(s_lg, logits + ray0 * (int64_t)M, b1, &bar);
+      umma::bulk_g2s(s_d, d_all + ray0 * (int64_t)M, b1, &bar);
+      umma::bulk_g2s(s_rad, radiance + ray0 * (int64_t)(3 * M), b3, &bar);
+      if (nablas) umma::bulk_g2s(s_nb, nablas + ray0 * (int64_t)(3 * M), b3, &bar);
+    }
+    umma::mbar_wait(&bar, 0);
+  } else {
+    auto stage_in = [&](float* dst, const float* src, int row) {
+      const float* g = src + ray0 * (int64_t)row;
+      const int n = nrays * row;
+      const int n4 = vec16 ? n >> 2 : 0;
+      for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 4 * i)), "l"(g + 4 * i) : "memory");
+      for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(g + i) : "memory");
+    };
+    stage_in(s_lg, logits, M);
+    stage_in(s_d, d_all, M);
+    stage_in(s_rad, radiance, 3 * M);
+    if (nablas) stage_in(s_nb, nablas, 3 * M);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+  }
+  if (ray >= R) return;
+  const float* lg = s_lg + warp * M;
+  const float* dd = s_d + warp * M;
+  const float* rad = s_rad + warp * 3 * M;
+  const float* nb = s_nb + warp * 3 * M;
+  const int seg = (M + 31) >> 5;
+  const int i0 = lane * seg;
+  float al[kSeg], tr[kSeg];
+  float prod = 1.0f;
+#pragma unroll
+  for (int k = 0; k < kSeg; ++k) {
+    const int i = i0 + k;
+    float alpha = 0.0f;
+    if (k < seg && i < M) {
+      const float odds = __expf(-lg[i]);
+      alpha = __fdiv_rn(odds, 1.0f + odds);
+    }
+    al[k] = alpha;
+    tr[k] = prod;
+    if (k < seg && i < M) prod *= (1.0f - alpha) + 1e-10f;
+  }
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl *= t;
+  }
+  float before = __shfl_up_sync(kFull, incl, 1);
+  if (lane == 0) before = 1.0f;
+  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aw = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSeg; ++k) {
+    const int i = i0 + k;
+    if (k < seg && i < M) {
+      const float w = al[k] * (before * tr[k]);
+      if (alpha_out) alpha_out[ray * (int64_t)M + i] = al[k];
+      if (w_out) w_out[ray * (int64_t)M + i] = w;
+      ar += w * rad[3 * i]; ag += w * rad[3 * i + 1]; ab += w * rad[3 * i + 2];
+      ad += w * dd[i];
+      aw += w;
+      if (nablas) {
+        const float x = nb[3 * i], y = nb[3 * i + 1], z = nb[3 * i + 2];
+        const float inv = rsqrtf(fmaxf(x * x + y * y + z * z, 1e-24f));   // = 1 / max(|v|, 1e-12)
+        nx += w * x * inv; ny += w * y * inv; nz += w * z * inv;
+      }
+    }
+  }
+  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aw = warp_sum(aw);
+  if (nablas) { nx = warp_sum(nx); ny = warp_sum(ny); nz = warp_sum(nz); }
+  if (lane == 0) {
+    if (white_bkgd) { ar += 1.0f - aw; ag += 1.0f - aw; ab += 1.0f - aw; }
+    rgb[3 * ray] = ar; rgb[3 * ray + 1] = ag; rgb[3 * ray + 2] = ab;
+    depth[ray] = ad / (aw + 1e-10f);
+    acc[ray] = aw;
+    if (normals) { normals[3 * ray] = nx; normals[3 * ray + 1] = ny; normals[3 * ray + 2] = nz; }
+  }
+}
+
 // One sphere-tracing update (ray_casting.py:178-183): d[mask] += sdf[mask]; rays leaving [0, far] are dropped;
 // emits the next query points.
 __global__ void sphere_trace_step_kernel(const float* __restrict__ val, const float* __restrict__ rays_o,
@@ -332,6 +444,20 @@ extern "C" int nr_unisurf_composite(const float* logits, const float* nablas, co
   if (R == 0) return NR_OK;
   NR_CHECK_ARG(logits && radiance && d_all && rgb && depth && acc, "nr_unisurf_composite: null pointer");
   NR_CHECK_ARG((nablas != nullptr) == (normals != nullptr), "nr_unisurf_composite: nablas and normals go together");
+  if (M <= kUsMaxM) {
+    const size_t smem = (size_t)4 * 8 * M * sizeof(float);
+    const int vec16 = ((((uintptr_t)logits | (uintptr_t)nablas | (uintptr_t)radiance | (uintptr_t)d_all) & 15) == 0) ? 1 : 0;
+    const unsigned grid = (unsigned)nr_cdiv(R, 4);
+    if (M <= 96) {           // 64 interval + 32 free-space samples (configs/unisurf.yaml)
+      unisurf_composite_staged_kernel<3><<<grid, 128, smem, (cudaStream_t)stream>>>(
+          logits, nablas, radiance, d_all, R, M, white_bkgd, rgb, depth, acc, normals, alpha_out, weights_out, vec16);
+    } else {
+      unisurf_composite_staged_kernel<kUsMaxM / 32><<<grid, 128, smem, (cudaStream_t)stream>>>(
+          logits, nablas, radiance, d_all, R, M, white_bkgd, rgb, depth, acc, normals, alpha_out, weights_out, vec16);
+    }
+    NR_CHECK_LAUNCH("unisurf_composite_staged_kernel");
+    return NR_OK;
+  }
   unisurf_composite_kernel<<<(unsigned)nr_cdiv(R, 4), 128, 0, (cudaStream_t)stream>>>(
       logits, nablas, radiance, d_all, R, M, white_bkgd, rgb, depth, acc, normals, alpha_out, weights_out);
   NR_CHECK_LAUNCH("unisurf_composite_kernel");

@@ -85,3 +85,15 @@ with torch.no_grad():
                                            None, None, None, _lib.stream_ptr(dev)), "volsdf_composite")
     report("nr_volsdf_composite (normals)", timeit(fnv), 6144 + 32)
     R = R_keep
+    # UNISURF compositing (a18): 96 x (logit, nabla, radiance, d) in
+    Mu = 96
+    lgu = torch.randn(R, Mu, **f) * 3.0
+    nabu = torch.randn(R, Mu, 3, **f)
+    radu = torch.rand(R, Mu, 3, **f)
+    du = torch.rand(R, Mu, **f).sort(-1).values
+    rgbu, depu, accu, nrmu = torch.empty(R, 3, device=dev), torch.empty(R, device=dev), torch.empty(R, device=dev), torch.empty(R, 3, device=dev)
+
+    def fnu():
+        _lib.check(lib.nr_unisurf_composite(_lib.ptr(lgu), _lib.ptr(nabu), _lib.ptr(radu), _lib.ptr(du), R, Mu, 0, _lib.ptr(rgbu),
+                                            _lib.ptr(depu), _lib.ptr(accu), _lib.ptr(nrmu), None, None, _lib.stream_ptr(dev)), "unisurf_composite")
+    report("nr_unisurf_composite (normals)", timeit(fnu), 3072 + 32)

@@ -303,3 +303,35 @@ def test_get_rays_vs_golden():
     q = torch.tensor([[0.9, 0.1, -0.3, 0.2, 1.0, 2.0, 3.0]], device=DEV)
     roq, rdq, _ = rend_util.get_rays(q, K[:1].to(DEV), H, W)
     assert torch.allclose(roq[0, 0].cpu(), torch.tensor([1.0, 2.0, 3.0])) and torch.isfinite(rdq).all()
+
+
+def test_neus_volume_render_is_cuda_graph_capturable():
+    """no host synchronisation inside the path.  A whole volume_render (ray setup, 5 up-sampling
+    rounds with their network queries, radiance pass, compositing) is captured into one CUDA graph and replayed on new
+    rays: same numbers as the eager call."""
+    import neurecon_b200
+    from neurecon_b200.models.frameworks import neus
+    neurecon_b200.set_precision("fp16")       # the fixture restores the module's tier afterwards
+    try:
+        m = build_neus(seed=1, device=DEV)
+        o, d = synthetic.make_rays(1000, seed=3)
+        o, d = o.to(DEV), d.to(DEV)
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream), torch.no_grad():
+            for _ in range(2):     # warm-up: weight images, workspaces and the allocator's pools exist before the capture
+                neus.volume_render(o, d, m, calc_normal=True, detailed_output=False)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                rgb, depth, ret = neus.volume_render(o, d, m, calc_normal=True, detailed_output=False)
+            o2, d2 = synthetic.make_rays(1000, seed=4)
+            o.copy_(o2.to(DEV))
+            d.copy_(d2.to(DEV))
+            graph.replay()
+            torch.cuda.synchronize()
+            rgb_e, depth_e, ret_e = neus.volume_render(o, d, m, calc_normal=True, detailed_output=False)
+            torch.cuda.synchronize()
+        assert torch.equal(rgb, rgb_e) and torch.equal(depth, depth_e)
+        assert torch.equal(ret["normals_volume"], ret_e["normals_volume"])
+    finally:
+        neurecon_b200.set_precision("fp32")

@@ -465,9 +465,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
         }
       }
       umma::tc_fence_before();
-      // staging buffers and TMEM slots are free before the next pair's prologue
-      if (kShare) named_bar_sync(3, 2 * kEpiPerTile);
-      else named_bar_sync(1 + g, kEpiPerTile);
+      // The owner's staging buffers and TMEM slot are free before its next prologue.  Its own group suffices also when
+      // the wide steps are shared: the other group last touched this tile in the last backward step, which completed
+      // (all 16 arrivals on in_ready) before the Jacobian step's MMAs were even issued.
+      named_bar_sync(1 + g, kEpiPerTile);
     }
   }
 

@@ -178,6 +178,10 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
           const int col = c0 + 4 * j4;
           if (col >= n_out) break;     // columns [N, pad4(N)) are written as zeros, nothing beyond (Y may be a column slice)
           float v[4], sp[4];
+          // tangent scale: one 16-byte load per 4 columns (ldaux >= pad4(N), rows 16-byte aligned) instead of four scalar
+          // loads that each touch 32 sectors per warp
+          const float4 xv4 = xrow ? *reinterpret_cast<const float4*>(xrow + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float z = __uint_as_float(raw[4 * j4 + j]);
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
                 case M_SOFTPLUS: z += g.bias[cj]; sp[j] = nr_softplus100_grad(z); z = nr_softplus100(z); break;
                 case M_RELU: z = fmaxf(z + g.bias[cj], 0.0f); break;
                 case M_SIGMOID: z = nr_sigmoid(z + g.bias[cj]); break;
-                case M_TANGENT: z *= xrow[cj]; break;
+                case M_TANGENT: z *= xv[j]; break;
                 default: break;
               }
             } else {
@@ -371,7 +375,8 @@ extern "C" int nr_gemm_tc(const float* A, int32_t lda, const float* W, int32_t l
                "nr_gemm_tc: leading dimensions must be multiples of 4 and cover the matrix");
   NR_CHECK_ARG((((uintptr_t)A | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)S) & 15) == 0, "nr_gemm_tc: 16-byte alignment");
   NR_CHECK_ARG(mode == M_LINEAR || mode == M_TANGENT || bias, "nr_gemm_tc: bias required");
-  NR_CHECK_ARG(mode != M_TANGENT || (aux && m_val > 0 && ldaux >= N), "nr_gemm_tc: tangent mode needs aux");
+  NR_CHECK_ARG(mode != M_TANGENT || (aux && m_val > 0 && ldaux >= ((N + 3) & ~3) && ldaux % 4 == 0 && ((uintptr_t)aux & 15) == 0),
+               "nr_gemm_tc: tangent mode needs aux with 16-byte aligned rows of at least pad4(N) floats");
   NR_CHECK_ARG(!S || ((lds & 3) == 0 && lds >= ((N + 3) & ~3)), "nr_gemm_tc: lds must be a multiple of 4 covering pad4(N)");
   NR_CHECK_ARG(ldy >= ((N + 3) & ~3), "nr_gemm_tc: ldy must cover pad4(N)");
   if (M == 0) return NR_OK;

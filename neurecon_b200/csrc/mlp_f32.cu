@@ -553,15 +553,17 @@ extern "C" int nr_nerf_forward_f32(const nr_nerf_net_t* net, const float* x, con
 namespace {
 
 // g_z / g_u in place of g_h' / g_t' (see above).  S = sp'(z) [n, N]; u [3n, N]; sp'' = 100 S (1 - S).
+// u_scaled: the array holds the layer's OUTPUT tangent t' = S u (what the forward pass keeps anyway as the next layer's
+// input), so u sp'' = 100 (1 - S) t'.
 __global__ void sdf_bwd_act_kernel(float* __restrict__ gh, int ldgh, float* __restrict__ gt, int ldgt,
                                    const float* __restrict__ S, int lds, const float* __restrict__ u, int ldu, int64_t n,
-                                   int N) {
+                                   int N, int u_scaled) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= n * N) return;
   const int64_t m = idx / N;
   const int j = (int)(idx % N);
   const float s = S[m * lds + j];
-  const float s2 = 100.0f * s * (1.0f - s);
+  const float s2 = u_scaled ? 100.0f * (1.0f - s) : 100.0f * s * (1.0f - s);
   float gz = gh[m * ldgh + j] * s;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -713,11 +715,12 @@ extern "C" int nr_colsum_f32(const float* G, int32_t ldg, int64_t rows, int32_t 
 }
 
 extern "C" int nr_sdf_bwd_act_f32(float* gh, int32_t ldgh, float* gt, int32_t ldgt, const float* S, int32_t lds,
-                                  const float* u, int32_t ldu, int64_t n, int32_t N, void* stream) {
+                                  const float* u, int32_t ldu, int64_t n, int32_t N, int32_t u_scaled, void* stream) {
   NR_CHECK_ARG(n >= 0 && N >= 1, "nr_sdf_bwd_act_f32: bad sizes");
   if (n == 0) return NR_OK;
   NR_CHECK_ARG(gh && gt && S && u, "nr_sdf_bwd_act_f32: null pointer");
-  sdf_bwd_act_kernel<<<(unsigned)nr_cdiv(n * N, 256), 256, 0, (cudaStream_t)stream>>>(gh, ldgh, gt, ldgt, S, lds, u, ldu, n, N);
+  sdf_bwd_act_kernel<<<(unsigned)nr_cdiv(n * N, 256), 256, 0, (cudaStream_t)stream>>>(gh, ldgh, gt, ldgt, S, lds, u, ldu, n, N,
+                                                                                        u_scaled);
   NR_CHECK_LAUNCH("sdf_bwd_act_kernel");
   return NR_OK;
 }

@@ -124,11 +124,10 @@ class _SdfFn(torch.autograd.Function):
                         t = tc
                 S = torch.zeros(n, _pad4(N), **f)
                 h_out = _gemm(h, K, Ws[l], bs[l], N, MODE_SOFTPLUS, S=S)
-                u = t_out = None
-                if want_nablas:
-                    u = _gemm(t, K, Ws[l], None, N, MODE_LINEAR)
-                    t_out = (u.view(3, n, -1) * S.unsqueeze(0)).reshape(3 * n, -1)
-                saved.append((h, t, S, u))
+                t_out = None
+                if want_nablas:   # t' = sp'(z) * (W t), the scaling in the GEMM's epilogue (row r of t belongs to point r % n)
+                    t_out = _gemm(t, K, Ws[l], None, N, MODE_TANGENT, aux=S, m_val=n)
+                saved.append((h, t, S))
                 h, t = h_out, t_out
             N, K = dims[L - 1]
             out = _gemm(h, K, Ws[L - 1], bs[L - 1], N, MODE_NONE)
@@ -180,10 +179,13 @@ class _SdfFn(torch.autograd.Function):
             # ---- hidden softplus layers ----
             for l in range(L - 2, -1, -1):
                 N, K = dims[l]
-                h_in, t_in, S, u = ctx.saved[l]
+                h_in, t_in, S = ctx.saved[l]
                 if wn:
+                    # the layer's output tangent S * u is the next layer's saved input (its first N columns at the skip)
+                    t_scaled = ctx.saved[l + 1][1] if l + 1 <= L - 2 else t_last
                     _lib.check(lib.nr_sdf_bwd_act_f32(_lib.ptr(g_h), g_h.shape[1], _lib.ptr(g_t), g_t.shape[1], _lib.ptr(S),
-                                                      S.shape[1], _lib.ptr(u), u.shape[1], n, N, st), "sdf_bwd_act")
+                                                      S.shape[1], _lib.ptr(t_scaled), t_scaled.shape[1], n, N, 1, st),
+                               "sdf_bwd_act")
                 else:
                     g_h[:, :N] *= S[:, :N]
                 dW = torch.zeros(N, _pad4(K), **f)

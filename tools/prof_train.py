@@ -33,7 +33,9 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-rows = [(e.key, e.device_time_total / 3e3, e.count // 3) for e in prof.key_averages() if e.device_time_total > 0]
+# kernels only (the autograd-function and aten entries of key_averages() nest the kernels they launch)
+rows = [(e.key, e.device_time_total / 3e3, e.count // 3) for e in prof.key_averages()
+        if e.device_time_total > 0 and ("kernel" in e.key.lower() or e.key.startswith("void ") or "Memcpy" in e.key or "Memset" in e.key)]
 rows.sort(key=lambda r: -r[1])
 tot = sum(r[1] for r in rows)
 print("[%s] device time per step %.2f ms" % (neurecon_b200.get_precision(), tot))

@@ -5,8 +5,9 @@
 // nr_gemm_tc:  Y[M, N] = epilogue(A[M, K] W[N, K]^T + bias)      M = points (x4 with tangents): large; N, K <= 320
 //   * W (<= 160 KB as 16-bit) is converted once per CTA into K-major SWIZZLE_128B chunks [Npad x 64 k] and stays
 //     resident; CTAs are persistent over 128-row tiles of A.
-//   * warps 0-3 load and convert the A tile ([128 x 64 k] per stage, 3 stages), warp 4 issues the MMAs
-//     (M = 128, N = Npad, one accumulator per tile, double buffered in TMEM), warps 5-8 run the epilogue from TMEM.
+//   * warps 0-7 load and convert the A tile ([128 x 64 k] per stage, 3 stages; two groups of four warps take alternate
+//     k-chunks, so two chunks = 64 KB of loads are in flight per SM: the loaders are latency bound), warp 8 issues the
+//     MMAs (M = 128, N = Npad, one accumulator per tile, double buffered in TMEM), warps 9-12 run the epilogue from TMEM.
 // nr_gemm_tn_tc: dW[N, K] += G[rows, N]^T X[rows, K]             reduction over the rows, split across CTAs
 //   * both operands are MN-major tiles [64 rows x (128 | <=256) columns] converted on the fly; each CTA owns one
 //     (128-row slice of dW) x (<=256-column slice) accumulator and a range of row chunks, and adds its partial sum
@@ -17,6 +18,7 @@
 namespace {
 
 constexpr int kBM = 128, kKC = 64, kAStages = 3;
+constexpr int kGemmThreads = 13 * 32;   // 8 loader warps, 1 MMA warp, 4 epilogue warps
 constexpr uint32_t kAStageBytes = kBM * kKC * 2;   // 16 KB
 
 enum : int { M_NONE = 0, M_SOFTPLUS = 1, M_RELU = 2, M_SIGMOID = 3, M_TANGENT = 4, M_LINEAR = 5 };
@@ -72,7 +74,7 @@ __device__ __forceinline__ void load64(const float* p, int valid, uint4 (&out)[8
 }
 
 template <bool kF16>
-__global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t w_chunk_bytes = (uint32_t)g.npad * 128u;
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
     for (int b = 0; b < 2; ++b) { umma::mbar_init(&acc_ready[b], 1); umma::mbar_init(&acc_free[b], 4); }
     umma::fence_barrier_init();
   }
-  if (warp == 4) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
+  if (warp == 8) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
   // W -> shared memory, K-major 128-byte swizzle, rows >= N and columns >= K zero
   for (int idx = threadIdx.x; idx < g.n_kc * g.npad * 8; idx += blockDim.x) {
     const int c8 = idx & 7, n = (idx >> 3) % g.npad, kc = (idx >> 3) / g.npad;
@@ -107,14 +109,16 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
   umma::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < 4) {
-    // ===================== A loaders: thread = row of the tile =====================
-    const int r = threadIdx.x;
+  if (warp < 8) {
+    // ===================== A loaders: thread = row of the tile; group 0 / 1 = even / odd chunks of the stream ==========
+    const int r = threadIdx.x & 127;
+    const uint32_t grp = (uint32_t)warp >> 2;
     uint32_t cnt = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t row = tile * kBM + r;
       const float* arow = g.A + (size_t)row * g.lda;
       for (int kc = 0; kc < g.n_kc; ++kc, ++cnt) {
+        if ((cnt & 1u) != grp) continue;
         const uint32_t st = cnt % kAStages, ph = (cnt / kAStages) & 1u;
         uint8_t* dst = sA + st * kAStageBytes + r * 128;
         uint4 ch[8];
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
         umma::mbar_arrive(&a_full[st]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, g.npad, 0, 0) : umma::make_idesc_bf16(128, g.npad, 0, 0);
     const uint32_t hi = umma::smem_desc_hi(1024);
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
       __syncwarp();
     }
   } else {
-    // ===================== epilogue: warps 5..8, TMEM lane quarter = warp % 4 =====================
+    // ===================== epilogue: warps 9..12, TMEM lane quarter = warp % 4 =====================
     const int q = warp & 3;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -168,9 +172,24 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
       float* srow = g.S ? g.S + (size_t)row * g.lds : nullptr;
       const float* xrow = g.mode == M_TANGENT ? g.aux + (size_t)(row % g.m_val) * g.ldaux : nullptr;
       const int n_out = (g.N + 3) & ~3;
+      // tangent scale: 16-byte loads (ldaux >= pad4(N), rows 16-byte aligned), the NEXT 16 columns' requested while the
+      // current ones are processed -- a load issued where it is used stalls the thread for an L2 round trip per 4 outputs
+      float4 xn[4];
+      auto fetch_scale = [&](int c0) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int col = c0 + 4 * j4;
+          xn[j4] = (xrow && rok && col < n_out) ? __ldg(reinterpret_cast<const float4*>(xrow + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+      };
+      fetch_scale(0);
       for (int c0 = 0; c0 < g.npad; c0 += 16) {
         uint32_t raw[16];
         umma::tmem_ld16(taddr + c0, raw);
+        float4 xc[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) xc[j4] = xn[j4];
+        if (c0 + 16 < g.npad) fetch_scale(c0 + 16);
         umma::tmem_ld_wait();
         if (!rok) continue;
 #pragma unroll
@@ -178,10 +197,12 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
           const int col = c0 + 4 * j4;
           if (col >= n_out) break;     // columns [N, pad4(N)) are written as zeros, nothing beyond (Y may be a column slice)
           float v[4], sp[4];
-          // tangent scale: one 16-byte load per 4 columns (ldaux >= pad4(N), rows 16-byte aligned) instead of four scalar
-          // loads that each touch 32 sectors per warp
-          const float4 xv4 = xrow ? *reinterpret_cast<const float4*>(xrow + col) : make_float4(1.f, 1.f, 1.f, 1.f);
-          const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+          const float xv[4] = {xc[j4].x, xc[j4].y, xc[j4].z, xc[j4].w};
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (g.bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = col + j < g.N ? __ldg(g.bias + col + j) : 0.0f;
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float z = __uint_as_float(raw[4 * j4 + j]);
@@ -189,10 +210,18 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
             sp[j] = 0.f;
             if (cj < g.N) {
               switch (g.mode) {
-                case M_NONE: z += g.bias[cj]; break;
-                case M_SOFTPLUS: z += g.bias[cj]; sp[j] = nr_softplus100_grad(z); z = nr_softplus100(z); break;
-                case M_RELU: z = fmaxf(z + g.bias[cj], 0.0f); break;
-                case M_SIGMOID: z = nr_sigmoid(z + g.bias[cj]); break;
+                case M_NONE: z += bv[j]; break;
+                case M_SOFTPLUS: {
+                  // 16-bit tiers only (the fp32 tier runs nr_gemm_f32): hardware exponential / logarithm, 2 ulp
+                  z += bv[j];
+                  const float t = 100.0f * z, e = __expf(-fabsf(t));
+                  const float r = __fdividef(1.0f, 1.0f + e);
+                  sp[j] = t >= 0.0f ? r : e * r;
+                  z = fmaxf(z, 0.0f) + 0.01f * __logf(1.0f + e);
+                  break;
+                }
+                case M_RELU: z = fmaxf(z + bv[j], 0.0f); break;
+                case M_SIGMOID: z = __fdividef(1.0f, 1.0f + __expf(-(z + bv[j]))); break;
                 case M_TANGENT: z *= xv[j]; break;
                 default: break;
               }
@@ -214,7 +243,7 @@ __global__ void __launch_bounds__(288, 1) gemm_tc_kernel(const GemmArgs g) {
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 4) umma::tmem_dealloc(tmem_base, 512);
+  if (warp == 8) umma::tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -393,10 +422,10 @@ extern "C" int nr_gemm_tc(const float* A, int32_t lda, const float* W, int32_t l
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
   if (operand_f16) {
     NR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<true><<<grid, 288, smem, (cudaStream_t)stream>>>(g);
+    gemm_tc_kernel<true><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(g);
   } else {
     NR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<false><<<grid, 288, smem, (cudaStream_t)stream>>>(g);
+    gemm_tc_kernel<false><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(g);
   }
   NR_CHECK_LAUNCH("gemm_tc_kernel");
   return NR_OK;

@@ -12,12 +12,15 @@ from neurecon_b200.utils import synthetic
 
 if os.environ.get("NEURECON_B200_PRECISION"):
     neurecon_b200.set_precision(os.environ["NEURECON_B200_PRECISION"])
+from neurecon_b200.utils import dist_util
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-dev = torch.device("cuda:0")
+# under torchrun: one rank per GPU, R rays per rank, ONE flat gradient all-reduce per step (train.py:124 semantics)
+rank, local_rank, world = dist_util.init_env()
+dev = torch.device("cuda", local_rank)
 m = build_neus(seed=1, device=dev)
 opt = torch.optim.Adam(m.parameters(), lr=5e-4)
-o, d = synthetic.make_rays(R, seed=3)
+o, d = synthetic.make_rays(R, seed=3 + rank)
 o, d = o.to(dev), d.to(dev)
 target = torch.rand(R, 3, device=dev)
 
@@ -29,6 +32,7 @@ def step():
     loss = F.l1_loss(rgb, target) + 0.1 * F.mse_loss(nn_, torch.ones_like(nn_)) \
         + F.binary_cross_entropy(ret["mask_volume"].clamp(1e-3, 1 - 1e-3), torch.ones(R, device=dev))
     loss.backward()
+    dist_util.allreduce_gradients(m.parameters())
     opt.step()
     return loss
 
@@ -36,6 +40,8 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
+if world > 1:
+    torch.distributed.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(steps):
@@ -43,5 +49,14 @@ for _ in range(steps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
+if world > 1:
+    t = torch.tensor([ms], device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = t.item()
+    if rank == 0:
+        print("[%s tier] NeuS data-parallel training step, %d x %d rays: %.2f ms/step (max over ranks), %.0f rays/s"
+              % (neurecon_b200.get_precision(), world, R, ms, world * R / ms * 1e3))
+    torch.distributed.destroy_process_group()
+    sys.exit(0)
 print("[%s tier] NeuS training step, %d rays: %.2f ms/step, %.0f rays/s, loss %.4f, peak mem %.2f GB (algorithmic ~1.85 GFLOP/ray => %.1f TFLOP/s)"
       % (neurecon_b200.get_precision(), R, ms, R / ms * 1e3, loss.item(), torch.cuda.max_memory_allocated() / 2**30, R * 1.85e9 / (ms * 1e-3) / 1e12))

@@ -5,10 +5,11 @@
 // nr_gemm_tc:  Y[M, N] = epilogue(A[M, K] W[N, K]^T + bias)      M = points (x4 with tangents): large; N, K <= 320
 //   * W (<= 160 KB as 16-bit) is converted once per CTA into K-major SWIZZLE_128B chunks [Npad x 64 k] and stays
 //     resident; CTAs are persistent over 128-row tiles of A.
-//   * warps 0-3 load and convert the A tile ([128 x 64 k] per stage, 3 stages), warp 4 issues the MMAs
-//     (M = 128, N = Npad, one accumulator per tile, double buffered in TMEM), warps 5-12 run the epilogue from TMEM:
-//     two warps per TMEM lane quarter, each on half of the columns (the epilogue -- a row per thread, strided 16-byte
-//     stores, the activation math -- is what the kernel waits for; doubling the loaders instead changed nothing).
+//   * warps 0-7 load and convert the A tile ([128 x 64 k] per stage, 3 stages; two groups of four warps take alternate
+//     k-chunks: two chunks = 64 KB of loads in flight per SM), warp 8 issues the MMAs (M = 128, N = Npad, one
+//     accumulator per tile, double buffered in TMEM), warps 9-16 run the epilogue from TMEM: two warps per TMEM lane
+//     quarter, each on half of the columns.  ncu: the kernel is latency bound (issue slots 18 % busy, tensor pipe 6 %,
+//     long-scoreboard stalls); four -> eight epilogue warps bought 23 %, four -> eight loader warps 3 %.
 // nr_gemm_tn_tc: dW[N, K] += G[rows, N]^T X[rows, K]             reduction over the rows, split across CTAs
 //   * both operands are MN-major tiles [64 rows x (128 | <=256) columns] converted on the fly; each CTA owns one
 //     (128-row slice of dW) x (<=256-column slice) accumulator and a range of row chunks, and adds its partial sum
@@ -19,7 +20,7 @@
 namespace {
 
 constexpr int kBM = 128, kKC = 64, kAStages = 3;
-constexpr int kGemmThreads = 13 * 32;   // 4 loader warps, 1 MMA warp, 8 epilogue warps
+constexpr int kGemmThreads = 17 * 32;   // 8 loader warps, 1 MMA warp, 8 epilogue warps
 constexpr uint32_t kAStageBytes = kBM * kKC * 2;   // 16 KB
 
 enum : int { M_NONE = 0, M_SOFTPLUS = 1, M_RELU = 2, M_SIGMOID = 3, M_TANGENT = 4, M_LINEAR = 5 };
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     for (int b = 0; b < 2; ++b) { umma::mbar_init(&acc_ready[b], 1); umma::mbar_init(&acc_free[b], 8); }
     umma::fence_barrier_init();
   }
-  if (warp == 4) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
+  if (warp == 8) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
   // W -> shared memory, K-major 128-byte swizzle, rows >= N and columns >= K zero
   for (int idx = threadIdx.x; idx < g.n_kc * g.npad * 8; idx += blockDim.x) {
     const int c8 = idx & 7, n = (idx >> 3) % g.npad, kc = (idx >> 3) / g.npad;
@@ -110,14 +111,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
   umma::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < 4) {
-    // ===================== A loaders: thread = row of the tile =====================
-    const int r = threadIdx.x;
+  if (warp < 8) {
+    // ===================== A loaders: thread = row of the tile; group 0 / 1 = even / odd chunks of the stream ==========
+    const int r = threadIdx.x & 127;
+    const uint32_t grp = (uint32_t)warp >> 2;
     uint32_t cnt = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t row = tile * kBM + r;
       const float* arow = g.A + (size_t)row * g.lda;
       for (int kc = 0; kc < g.n_kc; ++kc, ++cnt) {
+        if ((cnt & 1u) != grp) continue;
         const uint32_t st = cnt % kAStages, ph = (cnt / kAStages) & 1u;
         uint8_t* dst = sA + st * kAStageBytes + r * 128;
         uint4 ch[8];
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
         umma::mbar_arrive(&a_full[st]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, g.npad, 0, 0) : umma::make_idesc_bf16(128, g.npad, 0, 0);
     const uint32_t hi = umma::smem_desc_hi(1024);
@@ -157,9 +160,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
       __syncwarp();
     }
   } else {
-    // ===================== epilogue: warps 5..12, TMEM lane quarter = warp % 4, column half = (warp - 5) / 4 ==========
+    // ===================== epilogue: warps 9..16, TMEM lane quarter = warp % 4, column half = (warp - 9) / 4 ==========
     const int q = warp & 3;
-    const int half = (warp - 5) >> 2;
+    const int half = (warp - 9) >> 2;
     const int c_lo = half ? ((g.npad >> 1) + 15) & ~15 : 0, c_hi = half ? g.npad : ((g.npad >> 1) + 15) & ~15;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 4) umma::tmem_dealloc(tmem_base, 512);
+  if (warp == 8) umma::tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

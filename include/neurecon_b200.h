@@ -401,7 +401,9 @@ typedef struct {
   int32_t rad_multires_view; /* embedding of the view direction */
   int32_t rad_extra_rows;    /* zero-padded rows after the 256 feature rows of the radiance operand */
   int32_t operand_f16;       /* 1: fp16 operands (image packed as fp16), 0: bf16; fp32 accumulation either way */
-  int32_t debug_flags;       /* profiling only (results invalid): 1 = no weight copies, 2 = no epilogue math/stores */
+  int32_t debug_flags;       /* profiling only (results invalid).  nr_mlp_umma_forward: 1 = no weight copies, 2 = no
+                                epilogue math/stores.  nr_mlp_umma_reverse: 1 = no softplus' scratch stores, 2 = no scratch
+                                loads, 4 = no backward epilogue, 8 = no forward (hidden-layer) epilogue */
   int32_t input_mode;        /* 0: points -> embedding -> SDF net; 1: radiance net alone on 128-point tiles, its operand
                                 rows [0,256) bulk-copied from the feature image a previous launch wrote (feat_img);
                                 2: NeRF++ background net on 128-point tiles: x = [n, input_dim] points, operand rows

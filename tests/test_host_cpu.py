@@ -72,3 +72,42 @@ def test_batchify_query_shapes():
     assert torch.equal(s, x.sum(-1)) and torch.equal(d["twice"], x * 2)
     s0 = batchify_query(lambda p: p[..., 0], x[0], chunk=4, dim_batchify=0)
     assert torch.equal(s0, x[0, ..., 0])
+
+
+def test_reverse_mode_program_layout_on_cpu():
+    """Host side of csrc/mlp_rev.cu (no GPU): the weight image holds W_l^T chunks for the backward sweep, the program is
+    hidden x L, [feature], sdf row, backward x (L-1), Jacobian; every chunk range lies inside the image, the transposed
+    chunks unswizzle back to the weights, rev_ok() refuses what the kernel's stash cannot hold."""
+    from neurecon_b200 import _lib, umma_pack
+    m = build_neus()
+    net = m.implicit_surface._umma_net(None)
+    P = net.program("rev", want_feat=True)
+    epi = [P.steps[i].epi for i in range(P.n_steps)]
+    H, F, S, B, N = umma_pack.EPI_HIDDEN, umma_pack.EPI_FEAT, umma_pack.EPI_SDF_OUT, umma_pack.EPI_BWD, umma_pack.EPI_NABLA
+    assert P.reverse == 1 and P.tangents == 0
+    assert epi == [H] * 8 + [F, S] + [B] * 7 + [N]
+    assert [P.steps[i].sig_slot for i in range(8)] == list(range(8))
+    assert P.steps[9].sig_slot == 7 and [P.steps[i].sig_slot for i in range(10, 17)] == [6, 5, 4, 3, 2, 1, 0]
+    assert [P.steps[i].pe_fill for i in range(10, 17)] == [0, 0, 0, 1, 0, 0, 0]       # backward of the skip layer (l = 4)
+    assert P.steps[13].out_rows == 217 and P.steps[17].out_rows == 39 and P.steps[17].pe_fill == 1
+    n_chunks = net.image.shape[0]
+    for i in range(P.n_steps):
+        st = P.steps[i]
+        assert 0 <= st.chunk_begin and st.chunk_begin + st.n_mt * (st.k_steps // 4) <= n_chunks
+        assert st.n_cols == 128
+    # w_sdf table: the sdf row's weights, fp32, zero padded to 256
+    aux = net.bias[P.steps[9].aux_off:P.steps[9].aux_off + 256]
+    from neurecon_b200.models.base import _effective_weight
+    w_last = _effective_weight(m.implicit_surface.surface_fc_layers[8]).detach().float()
+    assert torch.allclose(aux, w_last[0], atol=0, rtol=0)
+    # chunk (k-chunk 0, M-tile 0) of the first backward step = rows 0..127 x k 0..63 of W_7^T, K-major 128-byte swizzle
+    W7t = _effective_weight(m.implicit_surface.surface_fc_layers[7]).detach().float().t().contiguous()
+    chunk = net.image[P.steps[10].chunk_begin].view(torch.float16)
+    idx = umma_pack._a_tile_index().reshape(128, 64)
+    got = chunk[idx.reshape(-1)].reshape(128, 64).float()
+    assert torch.equal(got, W7t[:128, :64].half().float())
+    assert net.rev_ok(True) and net.rev_ok(False)
+    # 'rev_img': no feature step, the last hidden step also writes the radiance operand image
+    Pi = net.program("rev_img")
+    assert Pi.n_steps == 17 and Pi.steps[7].to_rad == 1 and Pi.steps[8].epi == S
+    assert _lib.NR_UMMA_MAX_STEPS >= P.n_steps

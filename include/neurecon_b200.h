@@ -356,6 +356,11 @@ int nr_neus_loss(const float* rgb, const float* target_rgb, const float* nablas,
 int nr_grad_sqsum(const void* table, int32_t n_tensors, float* out, void* stream);
 int nr_adam_step(const void* table, int32_t n_tensors, float lr, float beta1, float beta2, float eps, int64_t step,
                  void* stream);
+/* The same update with the step count and the learning rate in device memory (`*step_dev` is incremented first), so
+ * that a CUDA graph of a whole training step (train.py:196-210: forward, backward, optimizer.step(), scheduler) replays
+ * with the right bias correction and the scheduler's current lr. */
+int nr_adam_step_dev(const void* table, int32_t n_tensors, const float* lr_dev, float beta1, float beta2, float eps,
+                     int64_t* step_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * bf16 tier: fused PE + SDF MLP (+ forward-mode normals) + radiance MLP on tcgen05 / TMEM.

@@ -105,6 +105,7 @@ _SIGNATURES = {
     "nr_neus_loss": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _P, _P, _P, _P, _P, _P]),
     "nr_grad_sqsum": (C.c_int, [_P, _I32, _P, _P]),
     "nr_adam_step": (C.c_int, [_P, _I32, _F, _F, _F, _F, _I64, _P]),
+    "nr_adam_step_dev": (C.c_int, [_P, _I32, _P, _F, _F, _F, _P, _P]),
     "nr_mlp_umma2_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _I64, _P, _P, _P, _I64, _P, _P]),
     "nr_mlp_umma_set_trace": (C.c_int, [_P]),
     "nr_bench_ldtm": (C.c_int, [_I32, _I32, _I32, _P, _P, _P]),

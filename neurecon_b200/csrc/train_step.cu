@@ -128,6 +128,28 @@ __global__ void adam_multi_kernel(const TensorRef* __restrict__ tab, int n_tenso
   }
 }
 
+// The same update with the step count and the learning rate in device memory, so that a CUDA graph of the whole
+// training step replays with the right bias correction and a scheduler can change lr between replays.
+__global__ void adam_tick_kernel(int64_t* step) { *step += 1; }
+
+__global__ void adam_multi_dev_kernel(const TensorRef* __restrict__ tab, int n_tensors, const float* __restrict__ lr_dev,
+                                      float b1, float b2, float eps, const int64_t* __restrict__ step_dev) {
+  const double step = (double)*step_dev;
+  const float bc1 = (float)(1.0 - pow((double)b1, step)), bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, step));
+  const float step_size = *lr_dev / bc1;
+  for (int t = blockIdx.y; t < n_tensors; t += gridDim.y) {
+    const TensorRef T = tab[t];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T.n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float g = T.g[i];
+      const float m = T.m[i] + (g - T.m[i]) * (1.f - b1);
+      const float v = b2 * T.v[i] + (1.f - b2) * g * g;
+      T.m[i] = m; T.v[i] = v;
+      const float denom = sqrtf(v) / bc2_sqrt + eps;
+      T.p[i] = T.p[i] - step_size * (m / denom);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int nr_neus_loss(const float* rgb, const float* target_rgb, const float* nablas, const float* mask_volume,
@@ -168,5 +190,17 @@ extern "C" int nr_adam_step(const void* table, int32_t n_tensors, float lr, floa
   adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const TensorRef*)table, n_tensors, lr, beta1, beta2, eps, (float)bc1,
                                                             (float)sqrt(bc2));
   NR_CHECK_LAUNCH("adam_multi_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_adam_step_dev(const void* table, int32_t n_tensors, const float* lr_dev, float beta1, float beta2, float eps,
+                                int64_t* step_dev, void* stream) {
+  NR_CHECK_ARG(table && n_tensors > 0 && lr_dev && step_dev, "nr_adam_step_dev: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, st>>>(step_dev);
+  NR_CHECK_LAUNCH("adam_tick_kernel");
+  dim3 grid(32, n_tensors < 64 ? n_tensors : 64);
+  adam_multi_dev_kernel<<<grid, 256, 0, st>>>((const TensorRef*)table, n_tensors, lr_dev, beta1, beta2, eps, step_dev);
+  NR_CHECK_LAUNCH("adam_multi_dev_kernel");
   return NR_OK;
 }

@@ -423,3 +423,34 @@ def nerf_forward_autograd(module, input_pts, input_views):
     skip = module.skips[0] if module.skips else -1
     sigma, rgb = _NerfFn.apply(xf, vf, module.input_dim, module.multires, module.multires_view, skip, module.D, *wb)
     return sigma.reshape(shape), rgb.reshape(*shape, 3)
+
+
+class _ExclusiveCumprodFn(torch.autograd.Function):
+    """T_i = prod_{j<i} p_j along the last axis: the transmittance of neus.py:346-347 / volsdf.py:487 /
+    unisurf.py:210 (``cumprod(cat([1, p]))[..., :-1]``).  Same forward as torch; the backward is written
+    out because ``torch.cumprod``'s reads an "any zero?" flag on the host, which keeps a training step
+    from being captured into a CUDA graph.  Zeros are handled on the device: the first zero of a row
+    gets the product of the others, everything behind it zero -- torch's result."""
+
+    @staticmethod
+    def forward(ctx, p):
+        T = torch.cumprod(torch.cat([torch.ones_like(p[..., :1]), p[..., :-1]], dim=-1), dim=-1)
+        ctx.save_for_backward(p, T)
+        return T
+
+    @staticmethod
+    def backward(ctx, g):
+        p, T = ctx.saved_tensors
+
+        def suffix_sum_excl(a):                            # sum_{i>j} a_i
+            return a.flip(-1).cumsum(-1).flip(-1) - a
+
+        zero = p == 0
+        first = zero & (zero.cumsum(-1) == 1)
+        T1 = torch.cumprod(torch.cat([torch.ones_like(p[..., :1]), torch.where(first, torch.ones_like(p), p)[..., :-1]], dim=-1), dim=-1)
+        regular = suffix_sum_excl(g * T) / torch.where(zero, torch.ones_like(p), p)
+        return torch.where(first, suffix_sum_excl(g * T1), torch.where(zero, torch.zeros_like(p), regular))
+
+
+def exclusive_cumprod(p):
+    return _ExclusiveCumprodFn.apply(p)

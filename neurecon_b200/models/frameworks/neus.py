@@ -35,8 +35,8 @@ def sdf_to_alpha(sdf, s):
 
 
 def alpha_to_w(alpha):
-    shifted = torch.cat([torch.ones_like(alpha[..., :1]), 1.0 - alpha + 1e-10], dim=-1)
-    return alpha * torch.cumprod(shifted, dim=-1)[..., :-1]
+    from ..autograd import exclusive_cumprod          # torch.cumprod's backward syncs with the host
+    return alpha * exclusive_cumprod(1.0 - alpha + 1e-10)
 
 
 def sdf_to_w(sdf, s):

@@ -8,6 +8,7 @@ import torch
 import torch.nn.functional as F
 
 from ... import _lib
+from ..autograd import exclusive_cumprod
 
 
 def volsdf_render_train(rays_o, rays_d, model, near, far, obj_bounding_radius, batched, calc_normal, rayschunk,
@@ -67,7 +68,7 @@ def volsdf_render_train(rays_o, rays_d, model, near, far, obj_bounding_radius, b
                 radiances = torch.cat([radiances, radiance_out], dim=-2)
             delta_i = d_all[..., 1:] - d_all[..., :-1]
             p_i = torch.exp(-F.relu(sigma[..., :-1] * delta_i))
-            tau_i = (1 - p_i + 1e-10) * torch.cumprod(torch.cat([torch.ones_like(p_i[..., :1]), p_i], dim=-1), dim=-1)[..., :-1]
+            tau_i = (1 - p_i + 1e-10) * exclusive_cumprod(p_i)
             rgb = torch.sum(tau_i[..., None] * radiances[..., :-1, :], dim=-2)
             depth = torch.sum(tau_i / (tau_i.sum(-1, keepdim=True) + 1e-10) * d_all[..., :-1], dim=-1)
             acc = torch.sum(tau_i, -1)
@@ -141,8 +142,7 @@ def unisurf_render_train(rays_o, rays_d, model, batched, calc_normal, logit_tau,
                 logits = torch.cat(sdf_l, 1).reshape(R, M)
                 nablas = torch.cat(nab_l, 1).reshape(R, M, 3)
                 alpha = model.get_opacity_from_surface(logits)
-                shifted = torch.cat([torch.ones_like(alpha[..., :1]), 1.0 - alpha + 1e-10], dim=-1)
-                w = alpha * torch.cumprod(shifted, dim=-1)[..., :-1]
+                w = alpha * exclusive_cumprod(1.0 - alpha + 1e-10)
                 rgb = torch.sum(w[..., None] * radiances, -2)
                 depth = torch.sum(w / (w.sum(-1, keepdim=True) + 1e-10) * d_all, -1)
                 acc = torch.sum(w, -1)

@@ -94,6 +94,9 @@ def _tensor_table(entries, device):
     return torch.tensor(rows, dtype=torch.int64).to(device, non_blocking=True)
 
 
+_NORM_TABLES = {}
+
+
 def grad_norm_device(*modules):
     """2-norm of all gradients of the modules as a 0-dim device tensor (one launch, no sync)."""
     from .. import _lib
@@ -103,7 +106,10 @@ def grad_norm_device(*modules):
     dev = ps[0].device
     for p in ps:
         assert p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.device == dev
-    tab = _tensor_table([(p.grad, p.grad, None, None) for p in ps], dev)
+    key = tuple((p.grad.data_ptr(), p.numel()) for p in ps)
+    if key not in _NORM_TABLES:       # kept for good: a captured graph may hold the pointer, and its upload must not fall into a capture
+        _NORM_TABLES[key] = _tensor_table([(p.grad, p.grad, None, None) for p in ps], dev)
+    tab = _NORM_TABLES[key]
     out = torch.empty(1, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.get_lib().nr_grad_sqsum(_lib.ptr(tab), len(ps), _lib.ptr(out), _lib.stream_ptr(dev)), "grad_sqsum")
@@ -125,10 +131,23 @@ def calc_grad_norm(norm_type=2.0, **named_models):
 
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam (betas, eps; no weight decay / amsgrad) with one multi-tensor launch per parameter group,
-    so the per-module learning-rate groups of the reference's ``get_optimizer`` (base.py:486-521) carry over."""
+    so the per-module learning-rate groups of the reference's ``get_optimizer`` (base.py:486-521) carry over.
+    ``capturable=True`` keeps the step count and each group's lr in device memory (``nr_adam_step_dev``), which is
+    what a CUDA graph of the step needs: `CapturedStep` refreshes the device lr from ``group["lr"]`` (where the
+    reference's schedulers write it, train.py:210) before every replay."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.capturable = bool(capturable)
+
+    def push_lr(self):
+        """Copy every group's host ``lr`` into its device slot (stream-ordered, no sync).  Not recorded while a CUDA
+        graph is being captured: a replay must see the lr of its own iteration, not the capture's."""
+        if not self.capturable or torch.cuda.is_current_stream_capturing():
+            return
+        for group in self.param_groups:
+            if "_lr_dev" in group:
+                group["_lr_dev"].fill_(float(group["lr"]))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -156,7 +175,68 @@ class FusedAdam(torch.optim.Optimizer):
             if group.get("_table_key") != key:
                 group["_table"], group["_table_key"] = _tensor_table(entries, dev), key
             b1, b2 = group["betas"]
+            if self.capturable:
+                if "_lr_dev" not in group:
+                    group["_lr_dev"] = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
+                    group["_step_dev"] = torch.full((1,), group["step"] - 1, dtype=torch.int64, device=dev)
+                elif not torch.cuda.is_current_stream_capturing():
+                    group["_lr_dev"].fill_(float(group["lr"]))
+                with torch.cuda.device(dev):
+                    _lib.check(lib.nr_adam_step_dev(_lib.ptr(group["_table"]), len(entries), _lib.ptr(group["_lr_dev"]), float(b1),
+                                                    float(b2), float(group["eps"]), _lib.ptr(group["_step_dev"]),
+                                                    _lib.stream_ptr(dev)), "adam_step_dev")
+                torch.autograd.graph.increment_version(ps)
+                continue
             with torch.cuda.device(dev):
                 _lib.check(lib.nr_adam_step(_lib.ptr(group["_table"]), len(entries), float(group["lr"]), float(b1), float(b2),
                                             float(group["eps"]), int(group["step"]), _lib.stream_ptr(dev)), "adam_step")
+            # the kernel wrote through raw pointers: tell torch, the packed-weight caches of models/base.py key on _version
+            torch.autograd.graph.increment_version(ps)
         return loss
+
+
+class CapturedStep:
+    """A whole training iteration -- ``volume_render`` under autograd, the losses, ``backward()``, the gradient
+    all-reduce if any, ``optimizer.step()`` (train.py:196-210) -- captured ONCE into a CUDA graph and replayed: the
+    ~1 100 launches of a 512-ray NeuS step become one graph launch (22.0 -> 19.3 ms on a B200).
+
+        step = CapturedStep(step_fn, (rays_o, rays_d, target_rgb), optimizer=opt)
+        for it in range(...):
+            scheduler.step(it)                                     # writes group["lr"] on the host
+            losses = step(rays_o_it, rays_d_it, target_it)         # copies into the static inputs, replays
+
+    ``step_fn(*inputs)`` must be free of host reads (no ``.item()``; `neus_losses`, `grad_norm_device` and
+    `FusedAdam(capturable=True)` / ``torch.optim.Adam(capturable=True)`` are) and must zero the gradients with
+    ``zero_grad(set_to_none=False)`` so that the buffers the graph writes stay the same.  Its return value (tensors or
+    a dict / tuple of tensors) is static storage overwritten by every replay.  Input shapes are fixed; random
+    numbers inside (``perturb=True``) advance per replay through torch's graph-safe generator."""
+
+    def __init__(self, step_fn, example_inputs, optimizer=None, warmup=3):
+        dev = example_inputs[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("neurecon_b200: CapturedStep needs CUDA tensors (there is no CPU fallback)")
+        self.optimizer = optimizer
+        self._params = [p for g in optimizer.param_groups for p in g["params"]] if optimizer is not None else []
+        self.inputs = [t.clone() for t in example_inputs]
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                          # allocator / lazy-init warm-up outside the capture
+                for _ in range(max(int(warmup), 1)):
+                    step_fn(*self.inputs)
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.outputs = step_fn(*self.inputs)
+        self.warmup_steps = max(int(warmup), 1)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.inputs, inputs):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        if self.optimizer is not None and hasattr(self.optimizer, "push_lr"):
+            self.optimizer.push_lr()
+        self.graph.replay()
+        if self._params:                                            # the replay changed them behind torch's back (see FusedAdam.step)
+            torch.autograd.graph.increment_version(self._params)
+        return self.outputs

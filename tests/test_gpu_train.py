@@ -250,6 +250,95 @@ def test_fused_adam_and_grad_norm_match_torch():
         assert rel_err(pb, pa) < 2e-6
 
 
+def test_fused_adam_capturable_follows_the_scheduler():
+    """Step count and lr in device memory (nr_adam_step_dev): same parameters as torch.optim.Adam under a changing lr."""
+    from neurecon_b200.utils import train_util
+    def make():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(39, 64), torch.nn.Softplus(beta=100), torch.nn.Linear(64, 7)).to(DEV)
+    ma, mb = make(), make()
+    oa = torch.optim.Adam(ma.parameters(), lr=2e-3)
+    ob = train_util.FusedAdam(mb.parameters(), lr=2e-3, capturable=True)
+    x = torch.randn(50, 39, device=DEV)
+    for it in range(6):
+        for m_, o_ in ((ma, oa), (mb, ob)):
+            for g_ in o_.param_groups:
+                g_["lr"] = 2e-3 * 0.7 ** it
+            o_.zero_grad()
+            (m_(x) ** 2).mean().backward()
+            o_.step()
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert rel_err(pb, pa) < 2e-6
+
+
+def test_captured_training_step_matches_eager():
+    """A whole NeuS iteration (render under autograd, device losses, backward, gradient norm, Adam) captured into ONE
+    CUDA graph (train_util.CapturedStep) and replayed on fresh rays with a decaying lr follows the eager loop."""
+    from neurecon_b200.utils import train_util
+    from neurecon_b200.models.frameworks import neus
+    neurecon_b200.set_precision("fp32")
+    try:
+        R, W, K = 96, 2, 4
+        rays = [synthetic.make_rays(R, seed=20 + i) for i in range(W + K)]
+        rays = [(o.to(DEV), d.to(DEV)) for o, d in rays]
+        tgts = [torch.rand(R, 3, generator=torch.Generator().manual_seed(40 + i)).to(DEV) for i in range(W + K)]
+        lr_at = lambda it: 5e-4 * 0.8 ** it
+
+        def make():
+            m = build_neus(seed=1, device=DEV)
+            return m, train_util.FusedAdam(m.parameters(), lr=5e-4, capturable=True)
+
+        def make_step(m, opt):
+            def step(o, d, tgt):
+                opt.zero_grad(set_to_none=False)
+                rgb, _, ret = neus.volume_render(o, d, m, detailed_output=True, perturb=False)
+                losses = train_util.neus_losses(rgb, tgt, ret["implicit_nablas"], w_eikonal=0.1)
+                losses["total"].backward()
+                return losses["total"].detach(), train_util.grad_norm_device(m)
+            def full(o, d, tgt):
+                out = step(o, d, tgt)
+                opt.step()
+                return out
+            return full
+
+        m_e, opt_e = make()
+        step_e = make_step(m_e, opt_e)
+        eager = []
+        for it in range(W + K):
+            for g_ in opt_e.param_groups:
+                g_["lr"] = lr_at(it)
+            eager.append([float(v) for v in step_e(*rays[it], tgts[it])])
+
+        m_g, opt_g = make()
+        # the W warm-up iterations of the capture are real steps on the example inputs: give them the same data / lr
+        # CapturedStep's warm-up iteration is a real step on the example inputs: run the loop's first W steps eagerly,
+        # capture, then put parameters / Adam state / step count back to where the eager loop stands
+        step_g = make_step(m_g, opt_g)
+        for it in range(W):
+            for g_ in opt_g.param_groups:
+                g_["lr"] = lr_at(it)
+            step_g(*rays[it], tgts[it])
+        snap = [p.detach().clone() for p in m_g.parameters()]
+        snap_state = [(opt_g.state[p]["exp_avg"].clone(), opt_g.state[p]["exp_avg_sq"].clone()) for p in m_g.parameters()]
+        snap_steps = [g_["_step_dev"].clone() for g_ in opt_g.param_groups]
+        cap = train_util.CapturedStep(step_g, (rays[W][0], rays[W][1], tgts[W]), optimizer=opt_g, warmup=1)
+        with torch.no_grad():
+            for p, s0, (ea, es) in zip(m_g.parameters(), snap, snap_state):
+                p.copy_(s0); opt_g.state[p]["exp_avg"].copy_(ea); opt_g.state[p]["exp_avg_sq"].copy_(es)
+            for g_, s0 in zip(opt_g.param_groups, snap_steps):
+                g_["_step_dev"].copy_(s0)
+        for it in range(W, W + K):
+            for g_ in opt_g.param_groups:
+                g_["lr"] = lr_at(it)
+            loss, gn = cap(rays[it][0], rays[it][1], tgts[it])
+            assert abs(float(loss) - eager[it][0]) < 2e-3 * abs(eager[it][0]), (it, float(loss), eager[it])
+            assert abs(float(gn) - eager[it][1]) < 2e-2 * abs(eager[it][1]), (it, float(gn), eager[it])
+        diff = max(float((a.detach() - b.detach()).abs().mean()) for a, b in zip(m_e.parameters(), m_g.parameters()))
+        assert diff < 1e-4, diff
+    finally:
+        neurecon_b200.set_precision("fp16")
+
+
 @pytest.mark.parametrize("M,N,K,mode", [(1000, 256, 256, 1), (300, 217, 39, 1), (129, 257, 256, 0), (5000, 256, 289, 2),
                                         (777, 3, 256, 3), (640, 256, 256, 4), (513, 1, 256, 5), (2048, 39, 256, 5)])
 def test_gemm_tc_matches_fp32_gemm(M, N, K, mode):

@@ -111,3 +111,23 @@ def test_reverse_mode_program_layout_on_cpu():
     Pi = net.program("rev_img")
     assert Pi.n_steps == 17 and Pi.steps[7].to_rad == 1 and Pi.steps[8].epi == S
     assert _lib.NR_UMMA_MAX_STEPS >= P.n_steps
+
+
+def test_exclusive_cumprod_backward_matches_torch_incl_zeros():
+    """models/autograd.py: the transmittance product with a host-sync-free backward (torch.cumprod's reads a flag on the
+    host, which a CUDA-graph capture of the training step cannot do); zeros as torch handles them."""
+    import torch
+    from neurecon_b200.models.autograd import exclusive_cumprod
+    g = torch.Generator().manual_seed(0)
+    for with_zeros in (False, True):
+        p = torch.rand(7, 33, dtype=torch.float64, generator=g)
+        if with_zeros:
+            p[1, 5] = 0; p[2, 0] = 0; p[3, 32] = 0; p[4, 3] = 0; p[4, 9] = 0; p[5, 31] = 0
+        w = torch.randn(7, 33, dtype=torch.float64, generator=g)
+        a, b = p.clone().requires_grad_(), p.clone().requires_grad_()
+        Ta = torch.cumprod(torch.cat([torch.ones_like(a[..., :1]), a], -1), -1)[..., :-1]
+        Tb = exclusive_cumprod(b)
+        assert torch.equal(Ta, Tb)
+        (Ta * w).sum().backward()
+        (Tb * w).sum().backward()
+        assert (a.grad - b.grad).abs().max() < 1e-12

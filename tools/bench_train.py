@@ -1,5 +1,7 @@
 """NeuS training step (512 rays: render under autograd + L1 + eikonal + mask BCE, backward) -- ms per step and
-rays/s on one GPU, next to the oracle port on the CPU.  Usage: python tools/bench_train.py [rays] [steps]"""
+rays/s on one GPU, next to the oracle port on the CPU.  Usage: python tools/bench_train.py [rays] [steps] [graph]
+``graph``: the whole iteration (render, losses, backward, all-reduce, FusedAdam) replayed as one CUDA graph
+(train_util.CapturedStep) instead of ~1 100 eager launches."""
 import os, sys, time
 import torch
 import torch.nn.functional as F
@@ -19,33 +21,45 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 rank, local_rank, world = dist_util.init_env()
 dev = torch.device("cuda", local_rank)
 m = build_neus(seed=1, device=dev)
-opt = torch.optim.Adam(m.parameters(), lr=5e-4)
+GRAPH = len(sys.argv) > 3 and sys.argv[3] == "graph"
+if GRAPH:
+    from neurecon_b200.utils import train_util
+    opt = train_util.FusedAdam(m.parameters(), lr=5e-4, capturable=True)
+else:
+    opt = torch.optim.Adam(m.parameters(), lr=5e-4)
 o, d = synthetic.make_rays(R, seed=3 + rank)
 o, d = o.to(dev), d.to(dev)
 target = torch.rand(R, 3, device=dev)
 
 
-def step():
-    opt.zero_grad(set_to_none=True)
+ones = torch.ones(R, device=dev)
+
+
+def step_eager(o, d, target):
+    opt.zero_grad(set_to_none=not GRAPH)
     rgb, _, ret = neus.volume_render(o, d, m, detailed_output=True, perturb=True)
     nn_ = ret["implicit_nablas"].norm(dim=-1)
     loss = F.l1_loss(rgb, target) + 0.1 * F.mse_loss(nn_, torch.ones_like(nn_)) \
-        + F.binary_cross_entropy(ret["mask_volume"].clamp(1e-3, 1 - 1e-3), torch.ones(R, device=dev))
+        + F.binary_cross_entropy(ret["mask_volume"].clamp(1e-3, 1 - 1e-3), ones)
     loss.backward()
     dist_util.allreduce_gradients(m.parameters())
     opt.step()
     return loss
 
 
-for _ in range(3):
-    step()
+step = step_eager
+if GRAPH:
+    step = train_util.CapturedStep(step_eager, (o, d, target), optimizer=opt, warmup=3)
+else:
+    for _ in range(3):
+        step(o, d, target)
 torch.cuda.synchronize()
 if world > 1:
     torch.distributed.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(steps):
-    loss = step()
+    loss = step(o, d, target)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
@@ -54,9 +68,9 @@ if world > 1:
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = t.item()
     if rank == 0:
-        print("[%s tier] NeuS data-parallel training step, %d x %d rays: %.2f ms/step (max over ranks), %.0f rays/s"
-              % (neurecon_b200.get_precision(), world, R, ms, world * R / ms * 1e3))
+        print("[%s tier%s] NeuS data-parallel training step, %d x %d rays: %.2f ms/step (max over ranks), %.0f rays/s"
+              % (neurecon_b200.get_precision(), ", one CUDA graph" if GRAPH else "", world, R, ms, world * R / ms * 1e3))
     torch.distributed.destroy_process_group()
     sys.exit(0)
-print("[%s tier] NeuS training step, %d rays: %.2f ms/step, %.0f rays/s, loss %.4f, peak mem %.2f GB (algorithmic ~1.85 GFLOP/ray => %.1f TFLOP/s)"
-      % (neurecon_b200.get_precision(), R, ms, R / ms * 1e3, loss.item(), torch.cuda.max_memory_allocated() / 2**30, R * 1.85e9 / (ms * 1e-3) / 1e12))
+print("[%s tier%s] NeuS training step, %d rays: %.2f ms/step, %.0f rays/s, loss %.4f, peak mem %.2f GB (algorithmic ~1.85 GFLOP/ray => %.1f TFLOP/s)"
+      % (neurecon_b200.get_precision(), ", one CUDA graph" if GRAPH else "", R, ms, R / ms * 1e3, loss.item(), torch.cuda.max_memory_allocated() / 2**30, R * 1.85e9 / (ms * 1e-3) / 1e12))

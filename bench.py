@@ -97,6 +97,40 @@ def build_model(seed, device):
     return m.to(device)
 
 
+def train_step_bench(dev, world, rank, timed, R=512, steps=10):
+    """The training half of the target: one NeuS iteration of configs/neus.yaml per GPU -- 512 rays, volume_render under
+    autograd (perturb=True), L1 + 0.1 eikonal + 1.0 mask BCE (neus.py:443-478), backward incl. the second-order path,
+    one flat gradient all-reduce (train.py:124), Adam -- replayed as ONE CUDA graph (train_util.CapturedStep)."""
+    import torch
+    from neurecon_b200.models.frameworks import neus
+    from neurecon_b200.utils import dist_util, synthetic, train_util
+    model = build_model(1, dev)
+    opt = train_util.FusedAdam(model.parameters(), lr=5e-4, capturable=True)
+    o, d = synthetic.make_rays(R, shell_radius=2.5, jitter=0.1, seed=300 + rank)
+    g = torch.Generator().manual_seed(400 + rank)
+    o, d, target = o.to(dev), d.to(dev), torch.rand(R, 3, generator=g).to(dev)
+    mask = (torch.rand(R, generator=g) < 0.7).to(dev)
+
+    def iteration(o, d, target, mask):
+        opt.zero_grad(set_to_none=False)
+        rgb, _, ret = neus.volume_render(o, d, model, detailed_output=True, perturb=True)
+        losses = train_util.neus_losses(rgb, target, ret["implicit_nablas"], mask_volume=ret["mask_volume"], target_mask=mask,
+                                        w_eikonal=0.1, w_mask=1.0)
+        losses["total"].backward()
+        dist_util.allreduce_gradients(model.parameters())
+        opt.step()
+        return losses["total"].detach()
+
+    step = train_util.CapturedStep(iteration, (o, d, target, mask), optimizer=opt, warmup=3)
+    for _ in range(2):
+        step(o, d, target, mask)
+    ms = timed(lambda: step(o, d, target, mask), steps) / steps
+    return {"ms_per_step": ms, "value": world * R / (ms * 1e-3), "unit": "rays/s", "rays_per_gpu": R,
+            "workload": "NeuS training iteration (configs/neus.yaml: 512 rays per GPU, 64 + 4x16 samples, L1 + eikonal + mask "
+                        "loss, backward with the second-order path, flat gradient all-reduce, Adam), one CUDA graph per iteration",
+            "algorithmic_tflops_per_gpu": R * 1.85e9 / (ms * 1e-3) / 1e12}
+
+
 def cpu_reference_rate(n_rays, reps, seed=1):
     """rays/s of the oracle port (torch CPU, fp32, all host threads) on `n_rays` rays of the workload."""
     import torch
@@ -309,6 +343,8 @@ def main():
     ms_grid = timed(lambda: mesh_util.query_sdf_grid(model.implicit_surface, N=GN, plane_range=(0, GN)), 3)
     sdf_qps = world * GN ** 3 * 3 / (ms_grid * 1e-3)
 
+    train = train_step_bench(dev, world, rank, timed)
+
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
@@ -326,6 +362,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "sdf_queries_per_s": {"value": sdf_qps, "unit": "queries/s", "workload": "%d^3 lattice per GPU, sdf only" % GN,
                                   "frac_of_bf16_peak": sdf_qps / world * 0.918 * 1e6 / 1e12 / pk["bf16"]},
+            "train_step": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -209,7 +209,8 @@ class CapturedStep:
     `FusedAdam(capturable=True)` / ``torch.optim.Adam(capturable=True)`` are) and must zero the gradients with
     ``zero_grad(set_to_none=False)`` so that the buffers the graph writes stay the same.  Its return value (tensors or
     a dict / tuple of tensors) is static storage overwritten by every replay.  Input shapes are fixed; random
-    numbers inside (``perturb=True``) advance per replay through torch's graph-safe generator."""
+    numbers inside (``perturb=True``) advance per replay through torch's graph-safe generator.  With a gradient
+    all-reduce inside (NCCL captures), drop the CapturedStep before ``destroy_process_group()``."""
 
     def __init__(self, step_fn, example_inputs, optimizer=None, warmup=3):
         dev = example_inputs[0].device

@@ -70,6 +70,9 @@ if world > 1:
     if rank == 0:
         print("[%s tier%s] NeuS data-parallel training step, %d x %d rays: %.2f ms/step (max over ranks), %.0f rays/s"
               % (neurecon_b200.get_precision(), ", one CUDA graph" if GRAPH else "", world, R, ms, world * R / ms * 1e3))
+        sys.stdout.flush()
+    del step                      # a live CUDA graph holding NCCL kernels must go before the communicator does
+    torch.cuda.synchronize()
     torch.distributed.destroy_process_group()
     sys.exit(0)
 print("[%s tier%s] NeuS training step, %d rays: %.2f ms/step, %.0f rays/s, loss %.4f, peak mem %.2f GB (algorithmic ~1.85 GFLOP/ray => %.1f TFLOP/s)"

@@ -133,6 +133,133 @@ __global__ void sample_pdf_kernel(const float* __restrict__ bins, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// sample_pdf / sample_cdf for short rows (even M <= 128, the NeuS up-sampling shapes): one THREAD per ray.
+// The warp-per-ray kernel above issues ~550 warp instructions per 64-bin ray (ncu: 93 % of the issue slots busy at
+// 16 % of the copy bandwidth); here a warp serves 32 rays with the same instruction stream.  A block's rows are
+// contiguous in HBM, so they are staged as FLAT copies (16-byte loads, no per-row index math): the weights row of
+// thread t starts at t*(M-1) floats (odd stride -> conflict-free lock-step access), the bins row at t*M (accessed at
+// data-dependent indices only).  The arithmetic reproduces the warp kernel's association order exactly -- the
+// strided partial sums and the butterfly of warp_sum, the lane segments and the Hillis-Steele pass of
+// warp_scan_excl -- so both kernels return the same bits.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowThreads = 64;
+
+__device__ __forceinline__ void flat_copy(float* dst, const float* __restrict__ src, int count, int tid) {
+  if (((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0) {
+    const int c4 = count >> 2;
+    for (int i = tid; i < c4; i += kRowThreads) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    for (int i = (c4 << 2) + tid; i < count; i += kRowThreads) dst[i] = __ldg(src + i);
+  } else {
+    for (int i = tid; i < count; i += kRowThreads) dst[i] = __ldg(src + i);
+  }
+}
+
+// n > 32 (kSeg - 1), so only the last stride / the last lanes' segments can run past the row: the other bounds checks
+// fold away at compile time
+template <int kSeg>
+__device__ __forceinline__ void row_weights_to_cdf(float* row, int n) {
+  float part[32];
+#pragma unroll
+  for (int l = 0; l < 32; ++l) {          // warp_sum's input: lane l adds the elements l, l + 32, ...
+    float p = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSeg; ++k) {
+      const int i = l + 32 * k;
+      if (k < kSeg - 1 || i < n) { const float v = row[i] + 1e-5f; row[i] = v; p += v; }
+    }
+    part[l] = p;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)        // the xor butterfly as lane 0 sees it
+#pragma unroll
+    for (int j = 0; j < o; ++j) part[j] = part[j] + part[j + o];
+  const float tot = part[0];
+  float incl[32];
+#pragma unroll
+  for (int l = 0; l < 32; ++l) {          // warp_scan_excl: lane l owns [l * kSeg, (l + 1) * kSeg)
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSeg; ++k) {
+      const int i = l * kSeg + k;
+      if (i <= 32 * (kSeg - 1) || i < n) { const float c = __fdiv_rn(row[i], tot); row[i] = c; t = t + c; }
+    }
+    incl[l] = t;
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+    for (int l = 31; l >= o; --l) incl[l] = incl[l] + incl[l - o];
+#pragma unroll
+  for (int l = 0; l < 32; ++l) {
+    float run = l == 0 ? 0.0f : incl[l - 1];
+#pragma unroll
+    for (int k = 0; k < kSeg; ++k) {
+      const int i = l * kSeg + k;
+      if (i <= 32 * (kSeg - 1) || i < n) { run = run + row[i]; row[i] = run; }
+    }
+  }
+}
+
+template <int kSeg>
+__global__ void __launch_bounds__(kRowThreads) sample_pdf_rows_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                                                       const float* __restrict__ u_in, int64_t R, int M, int N,
+                                                                       int cdf_given, float eps, float* __restrict__ samples) {
+  extern __shared__ __align__(16) float smem[];
+  const int n = M - 1, tid = threadIdx.x;
+  const int64_t ray0 = blockIdx.x * (int64_t)kRowThreads;
+  const int rows = (int)(R - ray0 < kRowThreads ? R - ray0 : kRowThreads);
+  float* sw = smem;                                   // [rows][n]  weights -> cdf[1..M)
+  float* sb = sw + ((kRowThreads * n + 3) & ~3);      // [rows][M]  bins
+  float* su = sb + kRowThreads * M;                   // [rows][N]  uniforms in, samples out
+  flat_copy(sw, weights + ray0 * n, rows * n, tid);
+  flat_copy(sb, bins + ray0 * M, rows * M, tid);
+  if (u_in) flat_copy(su, u_in + ray0 * N, rows * N, tid);
+  __syncthreads();
+  if (tid < rows) {
+    float* row = sw + tid * n;
+    const float* b = sb + tid * M;
+    if (!cdf_given) row_weights_to_cdf<kSeg>(row, n);
+    // nr_linspace01 with its division hoisted; the search as a fixed number of predicated rounds (floor(log2 M) + 1 cover
+    // [0, M]) so that the unrolled samples interleave instead of waiting out 7 dependent shared-memory loads each
+    const float step = N > 1 ? __fdiv_rn(1.0f, (float)(N - 1)) : 0.0f;
+    const int rounds = 32 - __clz(M);
+    float* my_u = su + tid * N;
+    int j = tid % N;                                  // rotate the sample order per thread: su's row stride N is a power of two
+#pragma unroll 4
+    for (int jj = 0; jj < N; ++jj) {
+      float u;
+      if (u_in) u = my_u[j];
+      else u = N <= 1 ? 0.0f : ((j < N / 2) ? __fmaf_rn(step, (float)j, 0.0f) : __fmaf_rn(-step, (float)(N - 1 - j), 1.0f));
+      int lo = 0, hi = M;                             // lower_bound over cdf = (0, row[0..n)), the warp kernel's probe sequence
+      for (int r = 0; r < rounds; ++r) {
+        const int mid = (lo + hi) >> 1;
+        const bool act = lo < hi;
+        const float c = (act && mid) ? row[mid - 1] : 0.0f;
+        const bool lt = c < u;
+        lo = (act && lt) ? mid + 1 : lo;
+        hi = (act && !lt) ? mid : hi;
+      }
+      const int below = max(lo - 1, 0), above = min(lo, M - 1);
+      const float cb = below ? row[below - 1] : 0.0f, ca = above ? row[above - 1] : 0.0f;
+      float denom = __fsub_rn(ca, cb);
+      if (denom < eps) denom = 1.0f;
+      const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+      const float bb = b[below], ba = b[above];
+      my_u[j] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+      j = j + 1 == N ? 0 : j + 1;
+    }
+  }
+  __syncthreads();
+  float* out = samples + ray0 * N;
+  const int count = rows * N;
+  if ((((uintptr_t)out) & 15) == 0 && (count & 3) == 0) {
+    for (int i = tid; i < (count >> 2); i += kRowThreads) reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(su)[i];
+  } else {
+    for (int i = tid; i < count; i += kRowThreads) out[i] = su[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // NeuS ray prologue (neus.py:169-172,184-210)
 // ---------------------------------------------------------------------------------------------
 __global__ void neus_ray_setup_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t R,
@@ -683,6 +810,18 @@ extern "C" int nr_sample_pdf(const float* bins, const float* weights, const floa
   NR_CHECK_ARG(R >= 0 && M >= 2 && N >= 1, "nr_sample_pdf: need R>=0, M>=2, N>=1 (got R=%lld M=%d N=%d)", (long long)R, M, N);
   if (R == 0) return NR_OK;  // empty batches carry null data pointers
   NR_CHECK_ARG(bins && weights && samples, "nr_sample_pdf: null pointer");
+  if (!below && !above && !cdf_out && (M & 1) == 0 && M <= 128 && N <= 128) {   // short rows: one thread per ray
+    const size_t smem_rows = ((size_t)((kRowThreads * (M - 1) + 3) & ~3) + (size_t)kRowThreads * (M + N)) * sizeof(float);
+    const int seg = (M - 1 + 31) >> 5;
+    auto kern = seg == 1 ? sample_pdf_rows_kernel<1> : seg == 2 ? sample_pdf_rows_kernel<2>
+              : seg == 3 ? sample_pdf_rows_kernel<3> : sample_pdf_rows_kernel<4>;
+    if (smem_rows > 48 * 1024)
+      NR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    kern<<<(unsigned)nr_cdiv(R, kRowThreads), kRowThreads, smem_rows, (cudaStream_t)stream>>>(bins, weights, u, R, M, N,
+                                                                                             cdf_is_given, eps, samples);
+    NR_CHECK_LAUNCH("sample_pdf_rows_kernel");
+    return NR_OK;
+  }
   const size_t smem = (size_t)kWarpsPerBlock * 2 * M * sizeof(float);
   NR_CHECK_ARG(smem <= 200 * 1024, "nr_sample_pdf: M=%d too large for shared memory staging", M);
   if (smem > 48 * 1024)

@@ -85,6 +85,32 @@ def test_sample_pdf_golden_and_same_cdf_contract():
     assert torch.equal(got.cpu(), g["sto_cdf"])
 
 
+@pytest.mark.parametrize("M,N", [(64, 16), (80, 16), (96, 16), (112, 16), (128, 32), (32, 8), (8, 5), (2, 1), (64, 128)])
+@pytest.mark.parametrize("R", [37, 64, 1000])
+def test_sample_pdf_thread_per_ray_kernel_returns_the_warp_kernels_bits(M, N, R):
+    """Short even rows go to the thread-per-ray kernel (sample_pdf_rows_kernel), which reproduces the warp kernel's
+    association order: identical samples, deterministic and with given uniforms, for weights and for a given CDF."""
+    rs = np.random.RandomState(M * 131 + N * 7 + R)
+    bins = torch.from_numpy(np.sort(rs.uniform(0, 6, size=(R, M)).astype(np.float32), axis=1)).to(DEV)
+    w = (rs.uniform(size=(R, M - 1)) ** 6).astype(np.float32)
+    w[: R // 2, : (M - 1) // 2] = 0
+    w = torch.from_numpy(w).to(DEV)
+    u = torch.from_numpy(rs.uniform(size=(R, N)).astype(np.float32))
+    u[:, 0], u[:, -1] = 0.0, 1.0
+    u = u.to(DEV)
+    for uu in (u, None):
+        fast = rend_util.sample_pdf(bins, w, N, det=uu is None, u=uu)
+        slow, _, _, cdf = rend_util.sample_pdf(bins, w, N, det=uu is None, u=uu, return_details=True)
+        assert torch.equal(fast, slow)
+        assert torch.equal(rend_util.sample_cdf(bins, cdf[:, 1:].contiguous(), N, det=uu is None, u=uu),
+                           rend_util.sample_cdf(bins, cdf[:, 1:].contiguous(), N, det=uu is None, u=uu, return_details=True)[0])
+    # unaligned rows (a slice that starts 4 bytes into an allocation) take the scalar staging loops
+    flat_b, flat_w = torch.zeros(R * M + 1, device=DEV), torch.zeros(R * (M - 1) + 1, device=DEV)
+    flat_b[1:] = bins.reshape(-1); flat_w[1:] = w.reshape(-1)
+    fast = rend_util.sample_pdf(flat_b[1:].view(R, M), flat_w[1:].view(R, M - 1), N, det=True)
+    assert torch.equal(fast, rend_util.sample_pdf(bins, w, N, det=True, return_details=True)[0])
+
+
 def test_sample_pdf_empty_and_batched_prefix():
     bins = torch.linspace(0, 1, 8, device=DEV).expand(0, 8)
     out = rend_util.sample_pdf(bins, torch.zeros(0, 7, device=DEV), 4, det=True)

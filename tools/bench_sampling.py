@@ -62,6 +62,13 @@ with torch.no_grad():
     bins = torch.rand(R, Mb, **f).sort(-1).values
     w = torch.rand(R, Mb - 1, **f)
     report("rend_util.sample_pdf 64 -> 16 det", timeit(lambda: rend_util.sample_pdf(bins, w, N, det=True)), 4 * Mb + 4 * (Mb - 1) + 4 * N)
+    uu = torch.rand(R, N, **f)
+    report("rend_util.sample_pdf 64 -> 16 given u", timeit(lambda: rend_util.sample_pdf(bins, w, N, u=uu)), 4 * Mb + 4 * (Mb - 1) + 8 * N)
+    report("  (warp-per-ray kernel, same call)", timeit(lambda: rend_util.sample_pdf(bins, w, N, det=True, return_details=True)),
+           4 * Mb + 4 * (Mb - 1) + 4 * N + 8 * N + 4 * Mb)
+    b2, w2 = torch.rand(R, 112, **f).sort(-1).values, torch.rand(R, 111, **f)
+    report("rend_util.sample_pdf 112 -> 16 det", timeit(lambda: rend_util.sample_pdf(b2, w2, N, det=True)), 4 * 112 + 4 * 111 + 4 * N)
+    del b2, w2
     Mb, N = 512, 64
     bins = torch.rand(R // 8, Mb, **f).sort(-1).values
     w = torch.rand(R // 8, Mb - 1, **f)

@@ -122,7 +122,7 @@ class _SdfFn(torch.autograd.Function):
                         tc[:, :prev] = t[:, :prev]
                         tc[:, prev:prev + pe_dim] = tpe[:, :pe_dim]
                         t = tc
-                S = torch.zeros(n, _pad4(N), **f)
+                S = torch.zeros(n, _pad4(N), **f) if _pad4(N) != N else torch.empty(n, N, **f)   # the epilogue writes every column < N
                 h_out = _gemm(h, K, Ws[l], bs[l], N, MODE_SOFTPLUS, S=S)
                 t_out = None
                 if want_nablas:   # t' = sp'(z) * (W t), the scaling in the GEMM's epilogue (row r of t belongs to point r % n)

@@ -137,7 +137,7 @@ class FusedAdam(torch.optim.Optimizer):
     reference's schedulers write it, train.py:210) before every replay."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, foreach=True))   # foreach: zero_grad() as one multi-tensor launch
         self.capturable = bool(capturable)
 
     def push_lr(self):

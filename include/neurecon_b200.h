@@ -126,9 +126,11 @@ int nr_gemm_tn_tc(const float* G, int32_t ldg, const float* X, int32_t ldx, int6
 int nr_colsum_f32(const float* G, int32_t ldg, int64_t rows, int32_t N, float* out, void* stream);
 /* in place: gh <- g_z = gh*S + sum_c gt_c*u_c*100*S*(1-S),  gt_c <- g_u_c = gt_c*S.
  * gh,S: [n,N]; gt,u: [3n,N] (component-major row blocks).  u_scaled = 1: `u` holds the layer's output tangent S*u
- * (the next layer's input, kept by the forward pass anyway) and the factor becomes 100*(1-S). */
+ * (the next layer's input, kept by the forward pass anyway) and the factor becomes 100*(1-S).
+ * gz_colsum (optional, [N]) += column sums of g_z, the layer's bias gradient. */
 int nr_sdf_bwd_act_f32(float* gh, int32_t ldgh, float* gt, int32_t ldgt, const float* S, int32_t lds,
-                       const float* u, int32_t ldu, int64_t n, int32_t N, int32_t u_scaled, void* stream);
+                       const float* u, int32_t ldu, int64_t n, int32_t N, int32_t u_scaled, float* gz_colsum,
+                       void* stream);
 /* in place: x *= (ref > 0) (mode 0, ReLU backward) or x *= ref*(1-ref) (mode 1, sigmoid backward) */
 int nr_act_bwd_f32(float* x, int32_t ldx, const float* ref, int32_t ldr, int64_t rows, int32_t N,
                    int32_t mode, void* stream);

@@ -71,7 +71,7 @@ _SIGNATURES = {
     "nr_gemm_tn_f32": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _I32, _P]),
     "nr_gemm_tn_tc": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _I32, _I32, _P]),
     "nr_colsum_f32": (C.c_int, [_P, _I32, _I64, _I32, _P, _P]),
-    "nr_sdf_bwd_act_f32": (C.c_int, [_P, _I32, _P, _I32, _P, _I32, _P, _I32, _I64, _I32, _I32, _P]),
+    "nr_sdf_bwd_act_f32": (C.c_int, [_P, _I32, _P, _I32, _P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P]),
     "nr_act_bwd_f32": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P]),
     "nr_embed_f32": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _I32, _P, _I32, _I32, _P]),
     "nr_nerf_forward_f32_workspace": (_SZ, [C.POINTER(NerfNet), _I64]),

@@ -555,24 +555,76 @@ namespace {
 // g_z / g_u in place of g_h' / g_t' (see above).  S = sp'(z) [n, N]; u [3n, N]; sp'' = 100 S (1 - S).
 // u_scaled: the array holds the layer's OUTPUT tangent t' = S u (what the forward pass keeps anyway as the next layer's
 // input), so u sp'' = 100 (1 - S) t'.
-__global__ void sdf_bwd_act_kernel(float* __restrict__ gh, int ldgh, float* __restrict__ gt, int ldgt,
-                                   const float* __restrict__ S, int lds, const float* __restrict__ u, int ldu, int64_t n,
-                                   int N, int u_scaled) {
-  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (idx >= n * N) return;
-  const int64_t m = idx / N;
-  const int j = (int)(idx % N);
-  const float s = S[m * lds + j];
+// 4 row groups x 64 column quads per block, kBwdRows rows per block; 16-byte accesses when every leading dimension is a
+// multiple of 4 floats and the bases are 16-byte aligned.  `gz_colsum` (optional) += column sums of g_z: the layer's
+// bias gradient, which would otherwise re-read g_z in a launch of its own.
+constexpr int kBwdRows = 64;
+
+__device__ __forceinline__ float bwd_act_elem(float gh, float s, float g0, float g1, float g2, float u0, float u1, float u2,
+                                              int u_scaled, float* o0, float* o1, float* o2) {
   const float s2 = u_scaled ? 100.0f * (1.0f - s) : 100.0f * s * (1.0f - s);
-  float gz = gh[m * ldgh + j] * s;
+  float gz = gh * s;
+  gz += g0 * u0 * s2; *o0 = g0 * s;
+  gz += g1 * u1 * s2; *o1 = g1 * s;
+  gz += g2 * u2 * s2; *o2 = g2 * s;
+  return gz;
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(256) sdf_bwd_act_kernel(float* __restrict__ gh, int ldgh, float* __restrict__ gt, int ldgt,
+                                                          const float* __restrict__ S, int lds, const float* __restrict__ u,
+                                                          int ldu, int64_t n, int N, int u_scaled, float* __restrict__ gz_colsum) {
+  __shared__ float red[4][256];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int64_t r0 = blockIdx.x * (int64_t)kBwdRows, r1 = min(n, r0 + kBwdRows);
+  for (int j0 = 0; j0 < N; j0 += 256) {
+    const int j = j0 + 4 * tx;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (j < N) {
+      const bool quad = kVec && j + 3 < N;
+      for (int64_t m = r0 + ty; m < r1; m += 4) {
+        if (quad) {
+          const float4 s4 = *reinterpret_cast<const float4*>(S + m * lds + j);
+          const float4 h4 = *reinterpret_cast<const float4*>(gh + m * ldgh + j);
+          float4 g4[3], u4[3], o4[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int64_t r = c * n + m;
-    const float g = gt[r * ldgt + j];
-    gz += g * u[r * ldu + j] * s2;
-    gt[r * ldgt + j] = g * s;
+          for (int c = 0; c < 3; ++c) {
+            g4[c] = *reinterpret_cast<const float4*>(gt + (c * n + m) * ldgt + j);
+            u4[c] = *reinterpret_cast<const float4*>(u + (c * n + m) * ldu + j);
+          }
+          float4 z4;
+          z4.x = bwd_act_elem(h4.x, s4.x, g4[0].x, g4[1].x, g4[2].x, u4[0].x, u4[1].x, u4[2].x, u_scaled, &o4[0].x, &o4[1].x, &o4[2].x);
+          z4.y = bwd_act_elem(h4.y, s4.y, g4[0].y, g4[1].y, g4[2].y, u4[0].y, u4[1].y, u4[2].y, u_scaled, &o4[0].y, &o4[1].y, &o4[2].y);
+          z4.z = bwd_act_elem(h4.z, s4.z, g4[0].z, g4[1].z, g4[2].z, u4[0].z, u4[1].z, u4[2].z, u_scaled, &o4[0].z, &o4[1].z, &o4[2].z);
+          z4.w = bwd_act_elem(h4.w, s4.w, g4[0].w, g4[1].w, g4[2].w, u4[0].w, u4[1].w, u4[2].w, u_scaled, &o4[0].w, &o4[1].w, &o4[2].w);
+          *reinterpret_cast<float4*>(gh + m * ldgh + j) = z4;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(gt + (c * n + m) * ldgt + j) = o4[c];
+          acc[0] += z4.x; acc[1] += z4.y; acc[2] += z4.z; acc[3] += z4.w;
+        } else {
+          for (int k = 0; k < 4 && j + k < N; ++k) {
+            const int jj = j + k;
+            float o[3];
+            const float gz = bwd_act_elem(gh[m * ldgh + jj], S[m * lds + jj], gt[m * ldgt + jj], gt[(n + m) * ldgt + jj],
+                                          gt[(2 * n + m) * ldgt + jj], u[m * ldu + jj], u[(n + m) * ldu + jj],
+                                          u[(2 * n + m) * ldu + jj], u_scaled, &o[0], &o[1], &o[2]);
+            gh[m * ldgh + jj] = gz;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gt[(c * n + m) * ldgt + jj] = o[c];
+            acc[k] += gz;
+          }
+        }
+      }
+    }
+    if (gz_colsum) {                                       // block-uniform
+#pragma unroll
+      for (int k = 0; k < 4; ++k) red[ty][4 * tx + k] = acc[k];
+      __syncthreads();
+      const int jc = j0 + (int)threadIdx.x;
+      if (jc < N) atomicAdd(gz_colsum + jc, (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]));
+      __syncthreads();
+    }
   }
-  gh[m * ldgh + j] = gz;
 }
 
 // dW[i, j] += sum_r G[r, i] * X[r, j]   (i < N, j < K), split over row ranges, fp32 atomics.
@@ -715,12 +767,17 @@ extern "C" int nr_colsum_f32(const float* G, int32_t ldg, int64_t rows, int32_t 
 }
 
 extern "C" int nr_sdf_bwd_act_f32(float* gh, int32_t ldgh, float* gt, int32_t ldgt, const float* S, int32_t lds,
-                                  const float* u, int32_t ldu, int64_t n, int32_t N, int32_t u_scaled, void* stream) {
+                                  const float* u, int32_t ldu, int64_t n, int32_t N, int32_t u_scaled, float* gz_colsum,
+                                  void* stream) {
   NR_CHECK_ARG(n >= 0 && N >= 1, "nr_sdf_bwd_act_f32: bad sizes");
   if (n == 0) return NR_OK;
   NR_CHECK_ARG(gh && gt && S && u, "nr_sdf_bwd_act_f32: null pointer");
-  sdf_bwd_act_kernel<<<(unsigned)nr_cdiv(n * N, 256), 256, 0, (cudaStream_t)stream>>>(gh, ldgh, gt, ldgt, S, lds, u, ldu, n, N,
-                                                                                        u_scaled);
+  const bool vec = ((ldgh | ldgt | lds | ldu) & 3) == 0 && ((((uintptr_t)gh) | ((uintptr_t)gt) | ((uintptr_t)S) | ((uintptr_t)u)) & 15) == 0;
+  const unsigned grid = (unsigned)nr_cdiv(n, kBwdRows);
+  if (vec)
+    sdf_bwd_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(gh, ldgh, gt, ldgt, S, lds, u, ldu, n, N, u_scaled, gz_colsum);
+  else
+    sdf_bwd_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(gh, ldgh, gt, ldgt, S, lds, u, ldu, n, N, u_scaled, gz_colsum);
   NR_CHECK_LAUNCH("sdf_bwd_act_kernel");
   return NR_OK;
 }

@@ -183,17 +183,19 @@ class _SdfFn(torch.autograd.Function):
                 if wn:
                     # the layer's output tangent S * u is the next layer's saved input (its first N columns at the skip)
                     t_scaled = ctx.saved[l + 1][1] if l + 1 <= L - 2 else t_last
+                    g_b = torch.zeros(N, **f)                          # bias gradient = column sums of g_z, from the same pass
                     _lib.check(lib.nr_sdf_bwd_act_f32(_lib.ptr(g_h), g_h.shape[1], _lib.ptr(g_t), g_t.shape[1], _lib.ptr(S),
-                                                      S.shape[1], _lib.ptr(t_scaled), t_scaled.shape[1], n, N, 1, st),
+                                                      S.shape[1], _lib.ptr(t_scaled), t_scaled.shape[1], n, N, 1, _lib.ptr(g_b), st),
                                "sdf_bwd_act")
                 else:
                     g_h[:, :N] *= S[:, :N]
+                    g_b = None
                 dW = torch.zeros(N, _pad4(K), **f)
                 _gemm_tn(g_h, N, h_in, K, dW)
                 if wn:
                     _gemm_tn(g_t, N, t_in, K, dW)
                 grads[2 * l] = dW[:, :K]
-                grads[2 * l + 1] = _colsum(g_h, N)
+                grads[2 * l + 1] = g_b if g_b is not None else _colsum(g_h, N)
                 if l > 0:
                     Wt = _padded(Ws[l][:, :K].t().contiguous())
                     g_h = _gemm(g_h, N, Wt, None, K, MODE_LINEAR, grad=True)      # [n, pad4(K)]; for the skip layer only the

@@ -34,6 +34,8 @@ def _pad4(k):
 def _padded(W):
     """[out, in] -> contiguous fp32 [out, pad4(in)] (zero filled)."""
     out_d, in_d = W.shape
+    if in_d % 4 == 0:
+        return W.float().contiguous()
     Wp = torch.zeros(out_d, _pad4(in_d), dtype=torch.float32, device=W.device)
     Wp[:, :in_d] = W
     return Wp
@@ -44,13 +46,18 @@ def _tc():
     return _lib.tensor_tier()
 
 
-def _gemm(A, K, W, bias, N, mode, S=None, aux=None, m_val=0, grad=False):
+def _gemm(A, K, W, bias, N, mode, S=None, aux=None, m_val=0, grad=False, out=None):
     """Y[M, pad4(N)] = epilogue(A[:, :K] @ W[:N, :K]^T + bias); pad columns are zero.  ``grad``: the operands are
-    gradients (tensor tier: bf16 operands for their range instead of fp16)."""
+    gradients (tensor tier: bf16 operands for their range instead of fp16).  ``out``: a wider row-major buffer whose
+    first pad4(N) columns receive the result (the head of a skip layer's concatenated input)."""
     lib = _lib.get_lib()
     M = A.shape[0]
-    ldy = _pad4(N)
-    Y = torch.zeros(M, ldy, dtype=torch.float32, device=A.device) if ldy != N else torch.empty(M, ldy, dtype=torch.float32, device=A.device)
+    if out is not None:
+        assert out.shape[0] == M and out.shape[1] >= _pad4(N) and out.is_contiguous()
+        Y, ldy = out, out.shape[1]
+    else:
+        ldy = _pad4(N)
+        Y = torch.zeros(M, ldy, dtype=torch.float32, device=A.device) if ldy != N else torch.empty(M, ldy, dtype=torch.float32, device=A.device)
     st = _lib.stream_ptr(A.device)
     if _tc():
         f16 = 1 if (_lib.get_precision() == "fp16" and not grad) else 0
@@ -111,22 +118,21 @@ class _SdfFn(torch.autograd.Function):
             saved = []
             for l in range(L - 1):
                 N, K = dims[l]
-                if l == skip:
-                    prev = dims[l - 1][0]
-                    hc = torch.zeros(n, _pad4(K), **f)
-                    hc[:, :prev] = h[:, :prev]
-                    hc[:, prev:prev + pe_dim] = pe[:, :pe_dim]
-                    h = hc
-                    if want_nablas:
-                        tc = torch.zeros(3 * n, _pad4(K), **f)
-                        tc[:, :prev] = t[:, :prev]
-                        tc[:, prev:prev + pe_dim] = tpe[:, :pe_dim]
-                        t = tc
                 S = torch.zeros(n, _pad4(N), **f) if _pad4(N) != N else torch.empty(n, N, **f)   # the epilogue writes every column < N
-                h_out = _gemm(h, K, Ws[l], bs[l], N, MODE_SOFTPLUS, S=S)
+                h_buf = t_buf = None
+                if l + 1 == skip:   # this layer's output is the head of the skip layer's input [h | pe]: the GEMMs write it in place
+                    ldn = _pad4(dims[skip][1])
+                    h_buf = torch.empty(n, ldn, **f)
+                    t_buf = torch.empty(3 * n, ldn, **f) if want_nablas else None
+                h_out = _gemm(h, K, Ws[l], bs[l], N, MODE_SOFTPLUS, S=S, out=h_buf)
                 t_out = None
                 if want_nablas:   # t' = sp'(z) * (W t), the scaling in the GEMM's epilogue (row r of t belongs to point r % n)
-                    t_out = _gemm(t, K, Ws[l], None, N, MODE_TANGENT, aux=S, m_val=n)
+                    t_out = _gemm(t, K, Ws[l], None, N, MODE_TANGENT, aux=S, m_val=n, out=t_buf)
+                for buf, src in ((h_buf, pe), (t_buf, tpe)):
+                    if buf is not None:
+                        buf[:, N:N + pe_dim] = src[:, :pe_dim]
+                        if buf.shape[1] > N + pe_dim:
+                            buf[:, N + pe_dim:] = 0
                 saved.append((h, t, S))
                 h, t = h_out, t_out
             N, K = dims[L - 1]
@@ -173,8 +179,9 @@ class _SdfFn(torch.autograd.Function):
                 if g_nabla is not None:
                     g_tout[:, 0] = g_nabla.t().reshape(-1)
                 _gemm_tn(g_tout, 1, t_last, K, dW)                      # adds to row 0
-                g_t = torch.zeros(3 * n, _pad4(K), **f)
-                g_t[:, :K] = g_tout[:, :1] * Ws[L - 1][0:1, :K]
+                w_row = torch.zeros(1, _pad4(K), **f)
+                w_row[:, :K] = Ws[L - 1][0:1, :K]
+                g_t = g_tout[:, :1] * w_row                            # [3n, pad4(K)], pad columns zero
             grads[2 * (L - 1)] = dW[:, :K]
             # ---- hidden softplus layers ----
             for l in range(L - 2, -1, -1):

@@ -107,9 +107,22 @@ def grad_norm_device(*modules):
     for p in ps:
         assert p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.device == dev
     key = tuple((p.grad.data_ptr(), p.numel()) for p in ps)
-    if key not in _NORM_TABLES:       # kept for good: a captured graph may hold the pointer, and its upload must not fall into a capture
-        _NORM_TABLES[key] = _tensor_table([(p.grad, p.grad, None, None) for p in ps], dev)
-    tab = _NORM_TABLES[key]
+    # The table is uploaded outside any graph capture (the copy comes from pageable memory) and cached by gradient
+    # addresses.  A table a capture has used is pinned for good -- the graph holds its pointer; the others are a small
+    # LRU, so that a loop with zero_grad(set_to_none=True) (fresh gradient tensors every step) does not pile tables up.
+    capturing = torch.cuda.is_current_stream_capturing()
+    entry = _NORM_TABLES.pop(key, None)
+    if entry is None:
+        if capturing:
+            raise RuntimeError("neurecon_b200: grad_norm_device inside a CUDA-graph capture needs a warm-up call on the same "
+                               "gradient tensors first (use zero_grad(set_to_none=False))")
+        entry = [_tensor_table([(p.grad, p.grad, None, None) for p in ps], dev), False]
+    entry[1] = entry[1] or capturing
+    _NORM_TABLES[key] = entry                               # most recently used last
+    loose = [k for k, e in _NORM_TABLES.items() if not e[1]]
+    for k in loose[:-8]:
+        del _NORM_TABLES[k]
+    tab = entry[0]
     out = torch.empty(1, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.get_lib().nr_grad_sqsum(_lib.ptr(tab), len(ps), _lib.ptr(out), _lib.stream_ptr(dev)), "grad_sqsum")

@@ -131,3 +131,12 @@ def test_exclusive_cumprod_backward_matches_torch_incl_zeros():
         (Ta * w).sum().backward()
         (Tb * w).sum().backward()
         assert (a.grad - b.grad).abs().max() < 1e-12
+
+
+def test_captured_step_refuses_cpu_tensors():
+    """train_util.CapturedStep is a CUDA-graph capture: on CPU tensors it raises instead of running the step eagerly."""
+    import pytest
+    import torch
+    from neurecon_b200.utils import train_util
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        train_util.CapturedStep(lambda x: x * 2, (torch.zeros(4),))

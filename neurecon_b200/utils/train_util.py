@@ -152,15 +152,30 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, foreach=True))   # foreach: zero_grad() as one multi-tensor launch
         self.capturable = bool(capturable)
+        self._dev = {}          # per group index: pointer table, its key, device lr / step count -- never part of state_dict()
 
     def push_lr(self):
         """Copy every group's host ``lr`` into its device slot (stream-ordered, no sync).  Not recorded while a CUDA
         graph is being captured: a replay must see the lr of its own iteration, not the capture's."""
         if not self.capturable or torch.cuda.is_current_stream_capturing():
             return
-        for group in self.param_groups:
-            if "_lr_dev" in group:
-                group["_lr_dev"].fill_(float(group["lr"]))
+        for gi, group in enumerate(self.param_groups):
+            d = self._dev.get(gi)
+            if d is not None and "lr" in d:
+                d["lr"].fill_(float(group["lr"]))
+
+    def state_dict(self):
+        """Checkpointing (checkpoints.py of the reference saves ``optimizer.state_dict()``): graph replays advance the
+        step count on the device only, so it is read back into ``group["step"]`` here (one sync per group)."""
+        for gi, group in enumerate(self.param_groups):
+            d = self._dev.get(gi)
+            if self.capturable and d is not None and "step" in d:
+                group["step"] = int(d["step"].item())
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._dev = {}          # device counters and tables are rebuilt from the loaded groups at the next step
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -170,7 +185,7 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.get_lib()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
@@ -184,25 +199,24 @@ class FusedAdam(torch.optim.Optimizer):
                 assert p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32
                 entries.append((p, p.grad, st["exp_avg"], st["exp_avg_sq"]))
             group["step"] = group.get("step", 0) + 1
+            d = self._dev.setdefault(gi, {})
             key = tuple(t.data_ptr() for e in entries for t in e)
-            if group.get("_table_key") != key:
-                group["_table"], group["_table_key"] = _tensor_table(entries, dev), key
+            if d.get("key") != key:
+                d["table"], d["key"] = _tensor_table(entries, dev), key
             b1, b2 = group["betas"]
             if self.capturable:
-                if "_lr_dev" not in group:
-                    group["_lr_dev"] = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
-                    group["_step_dev"] = torch.full((1,), group["step"] - 1, dtype=torch.int64, device=dev)
+                if "lr" not in d:
+                    d["lr"] = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
+                    d["step"] = torch.full((1,), group["step"] - 1, dtype=torch.int64, device=dev)
                 elif not torch.cuda.is_current_stream_capturing():
-                    group["_lr_dev"].fill_(float(group["lr"]))
+                    d["lr"].fill_(float(group["lr"]))
                 with torch.cuda.device(dev):
-                    _lib.check(lib.nr_adam_step_dev(_lib.ptr(group["_table"]), len(entries), _lib.ptr(group["_lr_dev"]), float(b1),
-                                                    float(b2), float(group["eps"]), _lib.ptr(group["_step_dev"]),
-                                                    _lib.stream_ptr(dev)), "adam_step_dev")
-                torch.autograd.graph.increment_version(ps)
-                continue
-            with torch.cuda.device(dev):
-                _lib.check(lib.nr_adam_step(_lib.ptr(group["_table"]), len(entries), float(group["lr"]), float(b1), float(b2),
-                                            float(group["eps"]), int(group["step"]), _lib.stream_ptr(dev)), "adam_step")
+                    _lib.check(lib.nr_adam_step_dev(_lib.ptr(d["table"]), len(entries), _lib.ptr(d["lr"]), float(b1), float(b2),
+                                                    float(group["eps"]), _lib.ptr(d["step"]), _lib.stream_ptr(dev)), "adam_step_dev")
+            else:
+                with torch.cuda.device(dev):
+                    _lib.check(lib.nr_adam_step(_lib.ptr(d["table"]), len(entries), float(group["lr"]), float(b1), float(b2),
+                                                float(group["eps"]), int(group["step"]), _lib.stream_ptr(dev)), "adam_step")
             # the kernel wrote through raw pointers: tell torch, the packed-weight caches of models/base.py key on _version
             torch.autograd.graph.increment_version(ps)
         return loss

@@ -267,6 +267,11 @@ def test_fused_adam_capturable_follows_the_scheduler():
             o_.zero_grad()
             (m_(x) ** 2).mean().backward()
             o_.step()
+        if it == 2:      # checkpoint round trip: the device step count goes through state_dict() and comes back
+            sd = ob.state_dict()
+            assert sd["param_groups"][0]["step"] == 3 and not any(k.startswith("_") for k in sd["param_groups"][0])
+            ob = train_util.FusedAdam(mb.parameters(), lr=2e-3, capturable=True)
+            ob.load_state_dict(sd)
     for pa, pb in zip(ma.parameters(), mb.parameters()):
         assert rel_err(pb, pa) < 2e-6
 
@@ -320,13 +325,13 @@ def test_captured_training_step_matches_eager():
             step_g(*rays[it], tgts[it])
         snap = [p.detach().clone() for p in m_g.parameters()]
         snap_state = [(opt_g.state[p]["exp_avg"].clone(), opt_g.state[p]["exp_avg_sq"].clone()) for p in m_g.parameters()]
-        snap_steps = [g_["_step_dev"].clone() for g_ in opt_g.param_groups]
+        snap_steps = [opt_g._dev[gi]["step"].clone() for gi in range(len(opt_g.param_groups))]
         cap = train_util.CapturedStep(step_g, (rays[W][0], rays[W][1], tgts[W]), optimizer=opt_g, warmup=1)
         with torch.no_grad():
             for p, s0, (ea, es) in zip(m_g.parameters(), snap, snap_state):
                 p.copy_(s0); opt_g.state[p]["exp_avg"].copy_(ea); opt_g.state[p]["exp_avg_sq"].copy_(es)
-            for g_, s0 in zip(opt_g.param_groups, snap_steps):
-                g_["_step_dev"].copy_(s0)
+            for gi, s0 in enumerate(snap_steps):
+                opt_g._dev[gi]["step"].copy_(s0)
         for it in range(W, W + K):
             for g_ in opt_g.param_groups:
                 g_["lr"] = lr_at(it)

@@ -1,5 +1,5 @@
 """NeuS training step (512 rays: render under autograd + L1 + eikonal + mask BCE, backward) -- ms per step and
-rays/s on one GPU, next to the oracle port on the CPU.  Usage: python tools/bench_train.py [rays] [steps] [graph]
+rays/s on one GPU, or per rank under torchrun.  Usage: python tools/bench_train.py [rays] [steps] [graph]
 ``graph``: the whole iteration (render, losses, backward, all-reduce, FusedAdam) replayed as one CUDA graph
 (train_util.CapturedStep) instead of ~1 100 eager launches."""
 import os, sys, time

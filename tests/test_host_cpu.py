@@ -140,3 +140,27 @@ def test_captured_step_refuses_cpu_tensors():
     from neurecon_b200.utils import train_util
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         train_util.CapturedStep(lambda x: x * 2, (torch.zeros(4),))
+
+
+def test_training_weights_match_the_oracle_incl_gradients():
+    """neus.sdf_to_alpha / alpha_to_w (the differentiable tensor ops of the training render, neus.py:21-70) against the
+    oracle's restatement on the CPU: same weights bit for bit, same gradient w.r.t. the sdf values and s (the oracle
+    differentiates torch.cumprod, the product path its own host-sync-free backward)."""
+    import torch
+    from neurecon_b200.models.frameworks import neus
+    from oracle import neus as oneus
+    g = torch.Generator().manual_seed(3)
+    sdf = (torch.rand(9, 128, generator=g, dtype=torch.float64) - 0.4) * 0.5
+    sdf[0] = torch.linspace(0.5, -0.5, 128, dtype=torch.float64)          # a clean surface crossing: alpha reaches ~1
+    wgt = torch.randn(9, 127, generator=g, dtype=torch.float64)
+    outs = []
+    for mod in (oneus, neus):
+        x = sdf.clone().requires_grad_()
+        s = torch.tensor([64.0], dtype=torch.float64, requires_grad=True)
+        _, alpha = mod.sdf_to_alpha(x, s)
+        w = mod.alpha_to_w(alpha)
+        (w * wgt).sum().backward()
+        outs.append((w.detach(), x.grad, s.grad))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert (outs[0][1] - outs[1][1]).abs().max() < 1e-10 * outs[0][1].abs().max()
+    assert (outs[0][2] - outs[1][2]).abs().max() < 1e-10 * outs[0][2].abs().max()

@@ -177,7 +177,9 @@ int nr_get_rays(const float* pose, const float* intr, const int64_t* select_inds
  * bins [R,M], weights [R,M-1], u [R,N] or NULL (det: torch.linspace(0,1,N) bit-exact),
  * samples [R,N]; optional outputs: below/above int32 [R,N] (the gathered indices) and the
  * CDF [R,M] the search ran on.  cdf_is_given != 0 turns this into sample_cdf
- * (rend_util.py:294-327): `weights` then holds the un-normalised CDF [R,M-1]. */
+ * (rend_util.py:294-327): `weights` then holds the un-normalised CDF [R,M-1].
+ * Even M <= 128 with none of the optional outputs requested runs one thread per ray (64 rows staged per block),
+ * everything else one warp per ray; both return the same bits. */
 int nr_sample_pdf(const float* bins, const float* weights, const float* u, int64_t R, int32_t M,
                   int32_t N, int32_t cdf_is_given, float eps, float* samples, int32_t* below,
                   int32_t* above, float* cdf_out, void* stream);

@@ -16,6 +16,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libneurecon_b200.so")
+# test-only twin of the two fused MLP kernels, compiled with the weight producer's fault injection (-DNR_FAULT_INJECT,
+# csrc/umma.cuh); loaded by tests/test_gpu_reliability.py and tools/soak_mlp.py, never by the package
+INJECT_LIB_PATH = os.path.join(LIB_DIR, "libneurecon_b200_inject.so")
+INJECT_SOURCES = ("api.cu", "mlp_rev.cu", "mlp_umma.cu")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -31,19 +35,32 @@ def sources():
 
 
 def _stale():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(INJECT_LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = min(os.path.getmtime(LIB_PATH), os.path.getmtime(INJECT_LIB_PATH))
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
-    if not force and not _stale():
+    """Compile and link under an exclusive file lock: eight torchrun ranks that all find the library stale must not
+    race nvcc into the same object files while their peers dlopen() the result."""
+    import fcntl
+    os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
+    if not force and not _stale():     # re-checked under the lock: another rank may just have built it
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
-    objs = []
+    objs, inject_objs = [], []
     procs = []
     for src in sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
@@ -52,6 +69,11 @@ def build(force=False, verbose=False):
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
+        if os.path.basename(src) in INJECT_SOURCES:
+            obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".inject.o")
+            cmd = [nvcc, *NVCC_FLAGS, "-DNR_FAULT_INJECT", "-I", INCLUDE, "-c", src, "-o", obj]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            inject_objs.append(obj)
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
@@ -62,8 +84,12 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("neurecon_b200: nvcc build failed")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart", "-lcuda"]
-    subprocess.check_call(cmd)
+    # link to a temporary name and rename: a process that dlopen()s the library meanwhile sees the old or the new file,
+    # never a half-written one
+    for path, members in ((LIB_PATH, objs), (INJECT_LIB_PATH, inject_objs)):
+        tmp = "%s.%d.tmp" % (path, os.getpid())
+        subprocess.check_call([nvcc, "-shared", "-o", tmp, *members, "-lcudart", "-lcuda"])
+        os.replace(tmp, path)
     return LIB_PATH
 
 

@@ -64,17 +64,7 @@ __device__ __forceinline__ void publish(uint64_t* bar) {
   if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar);
 }
 
-// Bounded wait with a tag: a protocol bug traps within ~0.1 s and says where.
-__device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, int tag) {
-  if (umma::mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-#pragma unroll 1
-  while (clock64() - t0 < 200000000ll)
-    if (umma::mbar_try_wait(bar, parity)) return;
-  if ((threadIdx.x & 31) == 0)
-    printf("neurecon_b200: mlp_rev wait %d timed out (block %d warp %d)\n", tag, blockIdx.x, threadIdx.x >> 5);
-  __trap();
-}
+__device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, int tag) { umma::mbar_wait(bar, parity, tag); }
 
 // softplus' codes: byte = 128 + round(254 (s - 1/2)) in [1, 255], exact at s = 0, 1/2 and 1.  The producer hands over
 // s - 1/2 (softplus_sigq2); fma(., 254, 1.5 * 2^23 + 128) leaves the code in the low mantissa byte, three byte permutes
@@ -167,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
           for (int c = 0; c < nch; ++c, ++cnt) {
             const uint32_t stage = cnt & (kStages - 1);
             wait_tag(&w_empty[stage], ((cnt >> kStagesLog2) & 1u) ^ 1u, 1000 + s);
+            NR_INJECT_DELAY(P.debug_flags, P.steps[s].n_mt, t);
             if (umma::elect_one()) {
               umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
               umma::bulk_g2s(smem + SmemRev::ring + stage * kChunkBytes, src + (size_t)c * kChunkBytes, kChunkBytes,
@@ -182,6 +173,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
     const uint32_t my_mt = warp == 1 ? 0u : 1u;
     uint32_t cnt = 0;
     uint32_t in_par = 0;
+    int prev_t = -1;                   // tile slot and acc_ready parity of the previous (step, tile) visit
+    uint32_t prev_par = 0;
     const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
     const uint32_t ring_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemRev::ring), 16);
     const uint32_t act_lo0 = umma::smem_desc_lo(umma::smem_u32(smem + SmemRev::act), kLbo);
@@ -194,9 +187,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
       for (int s = 0; s < P.n_steps; ++s) {
         const uint32_t n_mt = P.steps[s].n_mt, nkc = P.steps[s].k_steps >> 2;
         for (int t = 0; t < 2; ++t) {
-          wait_tag(&in_ready[t], (in_par >> t) & 1u, 2000 + s);
+          const uint32_t par = (in_par >> t) & 1u;   // in_ready[t] and acc_ready[t] complete one phase per visit of tile t
+          wait_tag(&in_ready[t], par, 2000 + s);
           in_par ^= 1u << t;
           umma::tc_fence_after();
+          // RING LOCKSTEP, rule 2 (rule 1 and the story are below): a step with one M-tile is issued by warp 1 alone, also
+          // from the stages whose previous chunks were warp 3's.  Before it touches them it waits for the previous
+          // visit's accumulator: both issuers have committed there, so every chunk issued before this visit has landed.
+          if (n_mt == 1 && my_mt == 0 && prev_t >= 0 && !(P.debug_flags & 128)) wait_tag(&acc_ready[prev_t], prev_par, 6000 + s);
           if (my_mt < n_mt) {
             const uint32_t d_addr = tmem_base + (uint32_t)t * 256u + my_mt * 128u;
             uint32_t b_lo = act_lo0 + (uint32_t)t * (kActBytes >> 4);
@@ -219,6 +217,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
           }
           if (umma::elect_one()) umma::mma_commit(&acc_ready[t]);
           __syncwarp();
+          // RING LOCKSTEP, rule 1.  A parity wait is sound only if the waiter knows that the barrier's PREVIOUS phase has
+          // completed: met one phase too early, the barrier shows the opposite parity and the wait falls through.  A
+          // consumer that takes every chunk of a stage knows it from its own last wait; with two issuers sharing the
+          // ring that breaks where a stage changes hands -- at the single-M-tile steps (sdf row, Jacobian), which warp 1
+          // issues alone.  Round 1 let warp 3 skip such a step; when tile 1's chunks of it were late (weights evicted
+          // from L2) warp 3 reached the w_full barrier of its next chunk while the chunk four positions earlier had not
+          // landed, fell through, multiplied stale weights, and its extra w_empty arrival put the ring out of step for
+          // good -- the driver's "wait 3016 / 4016 / 2000 timed out" (tools/repro_r1_trap.sh reproduces it with the
+          // producer's fault injection).  Rule 1: the issuer without an M-tile in a visit waits for that visit's
+          // accumulator, i.e. for the other issuer's MMAs on all of its chunks, before it moves on.  Rules 1 + 2 give
+          // every w_full wait a happens-before edge from the landing of the chunk four positions earlier.
+          if (my_mt >= n_mt && !(P.debug_flags & 128)) wait_tag(&acc_ready[t], par, 5000 + s);
+          prev_t = t;
+          prev_par = par;
           cnt += n_mt * nkc;
         }
       }

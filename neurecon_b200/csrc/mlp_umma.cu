@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         for (int t = 0; t < ntl; ++t) {
           for (int c = 0; c < nch; ++c, ++cnt) {
             const uint32_t stage = cnt & (kStages - 1);
-            umma::mbar_wait(&w_empty[stage], ((cnt >> kStagesLog2) & 1u) ^ 1u);
+            umma::mbar_wait(&w_empty[stage], ((cnt >> kStagesLog2) & 1u) ^ 1u, 1000 + s);
+            NR_INJECT_DELAY(P.debug_flags, P.steps[s].n_mt, t);
             if (umma::elect_one()) {
               if (P.debug_flags & 1) {
                 umma::mbar_arrive(&w_full[stage]);
@@ -147,6 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
     int tcnt = 0;
     uint32_t cnt = 0;                  // chunks consumed by the CTA before the current (step, tile)
     uint32_t in_par = 0;               // bit t: parity of in_ready[t]
+    int prev_t = -1;                   // tile slot and acc_ready parity of the previous (step, tile) visit
+    uint32_t prev_par = 0;
     const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
     const uint32_t ring_lo = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::ring), 16);
     const uint32_t act_lo0 = umma::smem_desc_lo(umma::smem_u32(smem + SmemLayout::act), kLbo);
@@ -158,9 +161,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         const uint32_t idesc = kF16 ? umma::make_idesc_f16(128, P.steps[s].n_cols, 0, 1)
                                     : umma::make_idesc_bf16(128, P.steps[s].n_cols, 0, 1);
         for (int t = 0; t < ntl; ++t) {
-          umma::mbar_wait(&in_ready[t], (in_par >> t) & 1u);
+          const uint32_t par = (in_par >> t) & 1u;   // in_ready[t] and acc_ready[t] complete one phase per visit of tile t
+          umma::mbar_wait(&in_ready[t], par, 2000 + s);
           in_par ^= 1u << t;
           umma::tc_fence_after();
+          // ring lockstep, rule 2 (mlp_rev.cu has the full story): before warp 1 issues a single-M-tile step from stages
+          // whose previous chunks were warp 3's, the previous visit's accumulator must be complete
+          if (n_mt == 1 && my_mt == 0 && prev_t >= 0 && !(P.debug_flags & 128)) umma::mbar_wait(&acc_ready[prev_t], prev_par, 6000 + s);
           if (lane == 0) trace_ev(a.trace, my_mt, tcnt, 11, s * 2 + t, pair);
           if (my_mt < n_mt) {
             const uint32_t d_addr = tmem_base + (uint32_t)t * 256u + my_mt * 128u;
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll 1
             for (uint32_t kc = 0; kc < nkc; ++kc, c += n_mt, b_lo += 512) {
               const uint32_t st = c & (kStages - 1);
-              umma::mbar_wait(&w_full[st], (c >> kStagesLog2) & 1u);
+              umma::mbar_wait(&w_full[st], (c >> kStagesLog2) & 1u, 3000 + s);
               umma::tc_fence_after();
               const uint32_t a_lo = ring_lo + st * (kChunkBytes >> 4);
               if (umma::elect_one()) {
@@ -185,6 +192,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
           if (umma::elect_one()) umma::mma_commit(&acc_ready[t]);
           __syncwarp();
           if (lane == 0) trace_ev(a.trace, my_mt, tcnt, 12, s * 2 + t, pair);
+          // ring lockstep, rule 1: the issuer without an M-tile in this visit waits for the visit's accumulator (the other
+          // issuer's MMAs on all of its chunks), so that it never meets a w_full barrier a phase early
+          if (my_mt >= n_mt && !(P.debug_flags & 128)) umma::mbar_wait(&acc_ready[t], par, 5000 + s);
+          prev_t = t;
+          prev_par = par;
           cnt += n_mt * nkc;
         }
       }
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
 #pragma unroll
           for (int c = 0; c < 4; ++c) umma::bulk_g2s(act + c * kChunkBytes, src + c * kChunkBytes, kChunkBytes, &feat_full[t]);
         }
-        umma::mbar_wait(&feat_full[t], feat_par);
+        umma::mbar_wait(&feat_full[t], feat_par, 7000);
         feat_par ^= 1;
         named_bar_sync(1 + t, kEpiPerTile);
       } else if (nerf) {
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         float* nabs = (float*)(smem + SmemLayout::nabs) + t * 384;
         uint8_t* pes = smem + SmemLayout::pes + t * (kPeStashRows * 256);
         const uint32_t tmem_tile = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 256);
-        umma::mbar_wait(&acc_ready[t], (acc_par >> t) & 1u);
+        umma::mbar_wait(&acc_ready[t], (acc_par >> t) & 1u, 4000 + s);
         acc_par ^= 1u << t;
         umma::tc_fence_after();
         if (tracer) trace_ev(a.trace, 2, tcnt, 21, s * 2 + t, pair);

@@ -69,27 +69,46 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU box.  Plain try_wait polling measured
-// fastest: parking the warp with a suspend-time hint (NR_WAIT_MODE 1) frees issue slots but wakes up later (+2.5 %
-// kernel time), see profiles/mlp_umma_r1_history.md.
-#ifndef NR_WAIT_MODE
-#define NR_WAIT_MODE 0
+// Watchdog clock: %globaltimer (ns, one clock for the whole GPU).  Round 1 bounded its waits by a spin count or by 2e8
+// cycles of clock64 (0.1 s); clock64 is a per-SM cycle counter that need not be continuous for a context that was switched
+// out and back in, and 0.1 s is not far enough from a time-sliced GPU's legitimate stalls.  The budget is now seconds of
+// wall clock, three orders of magnitude above a whole launch, so the trap can only mean a protocol bug.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#ifndef NR_WATCHDOG_NS
+#define NR_WATCHDOG_NS 4000000000ull
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#if NR_WAIT_MODE == 1
-  if (mbar_try_wait(bar, parity)) return;
-#pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 12); ++spin)
-    if (mbar_try_wait_hint(bar, parity, 1000000u)) return;
-#elif NR_WAIT_MODE == 2
-#pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin)
-    if (mbar_test_wait(bar, parity)) return;
+// Fault injection for the weight producers (only in the test library, built with -DNR_FAULT_INJECT; a never-taken branch
+// in the producer loop measured 3 % on the kernels): debug flag 64 holds back the second tile's chunks of the
+// single-M-tile steps by 20 us each -- the timing that broke round 1's ring.
+#ifdef NR_FAULT_INJECT
+#define NR_INJECT_DELAY(flags, n_mt, t) do { if (((flags) & 64) && (n_mt) == 1 && (t) == 1) __nanosleep(20000); } while (0)
 #else
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
-    if (mbar_try_wait(bar, parity)) return;
+#define NR_INJECT_DELAY(flags, n_mt, t) ((void)0)
 #endif
-  printf("neurecon_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU box, and says which wait (tag) of which
+// role it was.  Plain try_wait polling measured fastest: parking the warp with a suspend-time hint frees issue slots
+// but wakes up later (+2.5 % kernel time), see profiles/mlp_umma_r1_history.md.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+#pragma unroll 1
+  for (;;) {
+    // the timer is read once per 2048 polls: %globaltimer is a slow special register, and a poll loop that reads it
+    // every time wakes up late (measured +4..8 % on the fused MLP kernels)
+#pragma unroll 1
+    for (int spin = 0; spin < 2048; ++spin)
+      if (mbar_try_wait(bar, parity)) return;
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > NR_WATCHDOG_NS) break;
+  }
+  if ((threadIdx.x & 31) == 0)
+    printf("neurecon_b200: mbarrier wait %d timed out (block %d warp %d, barrier word %016llx, parity %u)\n", tag,
+           blockIdx.x, threadIdx.x >> 5, (unsigned long long)*reinterpret_cast<volatile uint64_t*>(bar), parity);
   __trap();
 }
 
@@ -98,8 +117,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t first_ns, uint32_t poll_ns) {
   if (mbar_try_wait(bar, parity)) return;
   if (first_ns) asm volatile("nanosleep.u32 %0;" ::"r"(first_ns));
+  const uint64_t t0 = globaltimer_ns();
 #pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+  while (globaltimer_ns() - t0 < NR_WATCHDOG_NS) {
     if (mbar_try_wait(bar, parity)) return;
     if (poll_ns) asm volatile("nanosleep.u32 %0;" ::"r"(poll_ns));
   }
@@ -247,22 +267,17 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
 #pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
+  while (globaltimer_ns() - t0 < NR_WATCHDOG_NS)
     if (mbar_try_wait_cluster(bar, parity)) return;
   if ((threadIdx.x & 31) == 0)
     printf("neurecon_b200: cluster mbarrier wait %d timed out (block %d warp %d)\n", tag, blockIdx.x, threadIdx.x >> 5);
   __trap();
 }
 // mbar_wait with a tag in the time-out message (the pair kernel has many distinct waits)
-__device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag) {
-#pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
-    if (mbar_try_wait(bar, parity)) return;
-  if ((threadIdx.x & 31) == 0)
-    printf("neurecon_b200: mbarrier wait %d timed out (block %d warp %d)\n", tag, blockIdx.x, threadIdx.x >> 5);
-  __trap();
-}
+__device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag) { mbar_wait(bar, parity, tag); }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {   // one warp of EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
 }

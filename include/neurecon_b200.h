@@ -340,6 +340,62 @@ int nr_sphere_trace_step(const float* val, const float* rays_o, const float* dir
                          float* d, uint8_t* mask, float* pts, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * NeRF++ background helpers -- utils/rend_util.py:188-234, models/frameworks/volsdf.py:456-467
+ * ------------------------------------------------------------------------------------------ */
+/* get_sphere_intersection (rend_util.py:188-210): exact ray / sphere near and far (clamped at 0) and the hit mask
+ * (bytes, may be NULL).  rays_d normalised.  r is a double because the reference squares it as a Python float before it
+ * meets the fp32 tensors. */
+int nr_sphere_intersection(const float* rays_o, const float* rays_d, int64_t R, double r, float* near, float* far,
+                           uint8_t* mask, void* stream);
+/* get_dvals_from_radius (rend_util.py:213-234): depth at which |o + t d| = rs, rs [R,N] -> d_vals [R,N]; far_end
+ * selects the far (else the near, clamped at 0) intersection.  The reference asserts rs^2 > |o|^2 - (o.d)^2 on the
+ * host (:225); here every violating entry adds 1 to *bad_count (device int, may be NULL) and yields NaN. */
+int nr_dvals_from_radius(const float* rays_o, const float* rays_d, const float* rs, int64_t R, int32_t N,
+                         int32_t far_end, float* d_vals, int32_t* bad_count, void* stream);
+/* VolSDF's inverted-sphere samples (volsdf.py:456-467): radii radius / flip(linspace(0,1,n_out+2)[1:-1]), jittered
+ * between the mid points of their neighbours with u [R,n_out] (NULL = none), their depths d_out [R,n_out]
+ * (get_dvals_from_radius) and the NeRF++ inputs x_out [R,n_out,4] = [p / rs, 1 / rs]. */
+int nr_volsdf_outside_points(const float* rays_o, const float* dirs, int64_t R, float radius, int32_t n_out,
+                             const float* u, float* d_out, float* x_out, int32_t* bad_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward of the compositing passes (training): the adjoints of nr_neus_composite[_bg], nr_volsdf_composite and
+ * nr_unisurf_composite, one launch each, one warp per ray (csrc/composite_bwd.cu).  Inputs: what the forward read, its
+ * per-sample outputs, and the upstream gradients of rgb [R,3], depth [R], acc [R], normals [R,3] and the weights
+ * [R,K] (each may be NULL = zero).  Replaces what autograd records for neus.py:296-352, volsdf.py:452-503,
+ * unisurf.py:216-240.
+ * ------------------------------------------------------------------------------------------ */
+/* NeuS.  K = M-1+n_out weights.  radiance_used [R,K,3]: the radiance the forward composited (the blend when n_out > 0),
+ * d_vals [R,K] (= d_mid when n_out = 0).  Outputs g_sdf [R,M], g_s_part [R] (sum over rays = dL/ds, s = exp(ln_s*speed)),
+ * g_radiance [R,M-1,3], g_nablas [R,M,3] (iff g_normals); with the background also g_sigma_out [R,K] and
+ * g_radiance_out [R,K,3]. */
+int nr_neus_composite_bwd(const float* sdf, const float* cdf, const float* alpha, const float* weights,
+                          const float* radiance_used, const float* d_vals, const float* nablas, const float* s_dev,
+                          const float* acc, const float* depth, int64_t R, int32_t M, int32_t n_out,
+                          const float* rays_o, const float* dirs, const float* sigma_out, float radius,
+                          int32_t white_bkgd, const float* g_rgb, const float* g_depth, const float* g_acc,
+                          const float* g_normals, const float* g_weights, float* g_sdf, float* g_s_part,
+                          float* g_radiance, float* g_nablas, float* g_sigma_out, float* g_radiance_out, void* stream);
+/* VolSDF.  K = M_in+M_out-1.  sigma_all [R,M_in+M_out], p, tau [R,K] from the forward.  Outputs g_sdf [R,M_in],
+ * g_alpha_part / g_beta_part [R] (sums = dL/dalpha, dL/dbeta of forward_ab), g_radiance [R,M_in,3], g_nablas
+ * [R,M_in,3] (iff g_normals), g_sigma_out [R,M_out], g_radiance_out [R,M_out,3].  A ray whose product of p contains
+ * zeros gets the exact one-zero gradient (see the source). */
+int nr_volsdf_composite_bwd(const float* sdf, const float* sigma_all, const float* p, const float* tau,
+                            const float* radiance, const float* d_in, const float* nablas, const float* alpha_dev,
+                            const float* beta_dev, const float* acc, const float* depth, int64_t R, int32_t M_in,
+                            const float* radiance_out, const float* d_out, int32_t M_out, int32_t white_bkgd,
+                            const float* g_rgb, const float* g_depth, const float* g_acc, const float* g_normals,
+                            const float* g_weights, float* g_sdf, float* g_alpha_part, float* g_beta_part,
+                            float* g_radiance, float* g_nablas, float* g_sigma_out, float* g_radiance_out,
+                            void* stream);
+/* UNISURF.  Outputs g_logits [R,M], g_radiance [R,M,3], g_nablas [R,M,3] (iff g_normals). */
+int nr_unisurf_composite_bwd(const float* logits, const float* alpha, const float* weights, const float* radiance,
+                             const float* d_all, const float* nablas, const float* acc, const float* depth, int64_t R,
+                             int32_t M, int32_t white_bkgd, const float* g_rgb, const float* g_depth,
+                             const float* g_acc, const float* g_normals, const float* g_weights, float* g_logits,
+                             float* g_radiance, float* g_nablas, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * After the path in a training step: losses, gradient norm, Adam -- no host syncs.
  * ------------------------------------------------------------------------------------------ */
 /* NeuS Trainer.forward losses (neus.py:443-478) and the gradients of their sum:

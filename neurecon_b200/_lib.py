@@ -113,6 +113,12 @@ _SIGNATURES = {
     "nr_bench_umma": (C.c_int, [_I32, _I32, _I32, _I32, _P, _I32, _P, _P]),
     "nr_selftest_umma2": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
     "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
+    "nr_sphere_intersection": (C.c_int, [_P, _P, _I64, C.c_double, _P, _P, _P, _P]),
+    "nr_dvals_from_radius": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
+    "nr_volsdf_outside_points": (C.c_int, [_P, _P, _I64, _F, _I32, _P, _P, _P, _P, _P]),
+    "nr_neus_composite_bwd": (C.c_int, [_P] * 10 + [_I64, _I32, _I32, _P, _P, _P, _F, _I32] + [_P] * 12),
+    "nr_volsdf_composite_bwd": (C.c_int, [_P] * 11 + [_I64, _I32, _P, _P, _I32, _I32] + [_P] * 13),
+    "nr_unisurf_composite_bwd": (C.c_int, [_P] * 8 + [_I64, _I32, _I32] + [_P] * 9),
     "nr_neus_composite": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 

@@ -82,50 +82,33 @@ class NeuS(nn.Module):
 
 
 def _composite(sdf, nablas, radiances, d_mid, s, white_bkgd, calc_normal, detailed):
-    """nr_neus_composite on [R, M] per-sample tensors."""
-    lib = _lib.get_lib()
-    R, M = sdf.shape
-    dev = sdf.device
-    f = dict(dtype=torch.float32, device=dev)
-    rgb, depth, acc = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
-    normals = torch.empty(R, 3, **f) if calc_normal else None
-    cdf = torch.empty(R, M, **f) if detailed else None
-    alpha = torch.empty(R, M - 1, **f) if detailed else None
-    w = torch.empty(R, M - 1, **f) if detailed else None
-    _lib.check(lib.nr_neus_composite(
-        _lib.ptr(sdf), _lib.ptr(nablas) if calc_normal else None, _lib.ptr(radiances), _lib.ptr(d_mid), _lib.ptr(s),
-        R, M, int(bool(white_bkgd)), _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(normals),
-        _lib.ptr(cdf), _lib.ptr(alpha), _lib.ptr(w), _lib.stream_ptr(dev)), "neus_composite")
-    return rgb, depth, acc, normals, cdf, alpha, w
+    """nr_neus_composite on [R, M] per-sample tensors (differentiable: models/composite.py)."""
+    from ..composite import NeusComposite
+    return NeusComposite.apply(sdf, nablas if calc_normal else None, radiances, d_mid, s, None, None, None, None, 0.0, 0,
+                               bool(white_bkgd), bool(calc_normal), bool(detailed))[:7]
 
 
-def _composite_bg(model, rays_o, dirs, far, sdf, nablas, radiances, d_mid, s, radius, N_outside, perturb, white_bkgd,
-                  calc_normal, detailed):
-    """NeRF++ background (neus.py:303-352): outside samples, NeRF.forward, blended compositing."""
+def _outside_points(rays_o, dirs, far, d_mid, N_outside, perturb):
+    """neus.py:303-318: d_vals [R, M-1+N_outside] = cat(d_mid, far / flip(linspace)) (stratified jitter if perturb) and
+    the inverted-sphere inputs x_out [R, M-1+N_outside, 4] of NeRF.forward."""
     lib = _lib.get_lib()
-    R, M = sdf.shape
-    dev = sdf.device
+    R, M1 = d_mid.shape
+    dev = d_mid.device
     f = dict(dtype=torch.float32, device=dev)
-    st = _lib.stream_ptr(dev)
-    T = M - 1 + N_outside
-    u = torch.rand([R, N_outside]).float().to(dev) if perturb else None   # CPU RNG like neus.py:310
+    T = M1 + N_outside
+    u = None
+    if perturb:
+        # the reference draws on the CPU generator (neus.py:310); a pageable host-to-device copy cannot be captured into
+        # a CUDA graph, so a capturing stream draws on the device instead (different stream of random numbers)
+        if torch.cuda.is_current_stream_capturing():
+            u = torch.rand([R, N_outside], device=dev)
+        else:
+            u = torch.rand([R, N_outside]).float().to(dev)
     d_vals, x_out = torch.empty(R, T, **f), torch.empty(R, T, 4, **f)
-    _lib.check(lib.nr_neus_outside_points(_lib.ptr(rays_o), _lib.ptr(dirs), _lib.ptr(far), _lib.ptr(d_mid), R, M - 1,
-                                          N_outside, _lib.ptr(u), _lib.ptr(d_vals), _lib.ptr(x_out), st), "neus_outside_points")
-    sigma_out, radiance_out = model.nerf_outside.forward(x_out, dirs.unsqueeze(-2).expand(R, T, 3))
-    sigma_out, radiance_out = sigma_out.contiguous(), radiance_out.contiguous()
-    rgb, depth, acc = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
-    normals = torch.empty(R, 3, **f) if calc_normal else None
-    cdf = torch.empty(R, M, **f) if detailed else None
-    alpha = torch.empty(R, T, **f) if detailed else None
-    w = torch.empty(R, T, **f) if detailed else None
-    blend = torch.empty(R, T, 3, **f) if detailed else None
-    _lib.check(lib.nr_neus_composite_bg(
-        _lib.ptr(sdf), _lib.ptr(nablas) if calc_normal else None, _lib.ptr(radiances), _lib.ptr(rays_o), _lib.ptr(dirs),
-        _lib.ptr(d_vals), _lib.ptr(sigma_out), _lib.ptr(radiance_out), _lib.ptr(s), float(radius), R, M, N_outside,
-        int(bool(white_bkgd)), _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(normals), _lib.ptr(cdf),
-        _lib.ptr(alpha), _lib.ptr(w), _lib.ptr(blend), st), "neus_composite_bg")
-    return rgb, depth, acc, normals, cdf, alpha, w, blend, d_vals, sigma_out, radiance_out
+    _lib.check(lib.nr_neus_outside_points(_lib.ptr(rays_o), _lib.ptr(dirs), _lib.ptr(far), _lib.ptr(d_mid), R, M1,
+                                          N_outside, _lib.ptr(u), _lib.ptr(d_vals), _lib.ptr(x_out), _lib.stream_ptr(dev)),
+               "neus_outside_points")
+    return d_vals, x_out
 
 
 def _upsample(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
@@ -225,13 +208,11 @@ def volume_render(
     if not use_view_dirs:
         raise NotImplementedError("use_view_dirs=False is not supported")
     _lib.require_cuda(rays_o, rays_d)
-    if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
-        from .neus_train import volume_render_train
-        return volume_render_train(
-            rays_o, rays_d, model, obj_bounding_radius=obj_bounding_radius, batched=batched, calc_normal=calc_normal,
-            rayschunk=rayschunk, white_bkgd=white_bkgd, near_bypass=near_bypass, far_bypass=far_bypass,
-            detailed_output=detailed_output, perturb=perturb, N_samples=N_samples, N_importance=N_importance,
-            N_upsample_iters=N_upsample_iters, N_outside=N_outside)
+    from ..composite import NeusComposite
+    # training (neus.py:440: Trainer.forward renders under autograd): the up-sampler stays no_grad as in the reference
+    # (neus.py:214), the two with-grad network queries (neus.py:294,298) go through models/autograd.py, the compositing
+    # through NeusComposite -- same kernels forward, hand-written adjoints backward
+    train = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
     if batched:
         B = rays_d.shape[0]
         prefix = [B, -1]
@@ -242,9 +223,8 @@ def volume_render(
     o_flat = _lib.f32c(rays_o.reshape(-1, 3))
     d_flat = _lib.f32c(rays_d.reshape(-1, 3))
     n_total = o_flat.shape[0]
-    rays_per_b = n_total // B
     M = N_samples + (N_importance // N_upsample_iters) * N_upsample_iters
-    s = model.forward_s().detach().float().contiguous()
+    s = model.forward_s() if train else model.forward_s().detach().float().contiguous()
 
     outs = []
     with torch.cuda.device(dev):
@@ -254,32 +234,41 @@ def volume_render(
         for i0 in range(0, n_total, step):
             ro, rd = o_flat[i0:i0 + step], d_flat[i0:i0 + step]
             R = ro.shape[0]
-            # sdf (and, when the caller wants normals or per-sample outputs, nablas) at the sorted samples come out of the
-            # up-sampler's own network queries: same points, same arithmetic as the reference's second evaluation there
-            need_nablas = bool(calc_normal or detailed_output)
-            dirs, d_all, pts, d_mid, pts_mid, far, sdf, nablas = _upsample(
-                model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
-                N_upsample_iters, perturb, return_far=True, return_field=True, with_nablas=need_nablas)
-            with torch.no_grad():
-                views = dirs.unsqueeze(-2).expand(R, M - 1, 3)
-                radiances, _, _ = query_radiance(model.implicit_surface, model.radiance_net, pts_mid, views)
+            if train:
+                with torch.no_grad():
+                    dirs, d_all, pts, d_mid, pts_mid, far = _upsample(
+                        model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
+                        N_upsample_iters, perturb, return_far=True)
+                sdf, nablas, _ = model.implicit_surface.forward_with_nablas(pts)            # neus.py:294
+                radiances = model.forward_radiance(pts_mid, dirs.unsqueeze(-2).expand(R, M - 1, 3))   # neus.py:298
+            else:
+                # sdf (and, when the caller wants normals or per-sample outputs, nablas) at the sorted samples come out of
+                # the up-sampler's own network queries: same points, same arithmetic as the reference's second
+                # evaluation there
+                need_nablas = bool(calc_normal or detailed_output)
+                dirs, d_all, pts, d_mid, pts_mid, far, sdf, nablas = _upsample(
+                    model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
+                    N_upsample_iters, perturb, return_far=True, return_field=True, with_nablas=need_nablas)
+                with torch.no_grad():
+                    views = dirs.unsqueeze(-2).expand(R, M - 1, 3)
+                    radiances, _, _ = query_radiance(model.implicit_surface, model.radiance_net, pts_mid, views)
             sigma_out = radiance_out = None
             d_final = d_mid
             if N_outside > 0:
                 with torch.no_grad():
-                    (rgb, depth, acc, normals, cdf, alpha, w, radiances, d_final, sigma_out, radiance_out) = _composite_bg(
-                        model, ro, dirs, far, sdf, nablas, radiances, d_mid, s, obj_bounding_radius, N_outside, perturb,
-                        white_bkgd, calc_normal, detailed_output)
-            else:
-                rgb, depth, acc, normals, cdf, alpha, w = _composite(
-                    sdf, nablas, radiances, d_mid, s, white_bkgd, calc_normal, detailed_output)
+                    d_final, x_out = _outside_points(ro, dirs, far, d_mid, N_outside, perturb)
+                sigma_out, radiance_out = model.nerf_outside.forward(
+                    x_out, dirs.unsqueeze(-2).expand(R, d_final.shape[-1], 3))
+            rgb, depth, acc, normals, cdf, alpha, w, blended = NeusComposite.apply(
+                sdf, nablas if calc_normal else None, radiances, d_final, s, sigma_out, radiance_out, ro, dirs,
+                float(obj_bounding_radius), int(N_outside), bool(white_bkgd), bool(calc_normal), bool(detailed_output))
             ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
             if calc_normal:
                 ret_i['normals_volume'] = normals
             if detailed_output:
                 ret_i['implicit_nablas'] = nablas
                 ret_i['implicit_surface'] = sdf
-                ret_i['radiance'] = radiances
+                ret_i['radiance'] = blended if N_outside > 0 else radiances
                 ret_i['alpha'] = alpha
                 ret_i['cdf'] = cdf
                 ret_i['visibility_weights'] = w

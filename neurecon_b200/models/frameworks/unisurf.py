@@ -89,11 +89,11 @@ def volume_render(
     if not use_view_dirs:
         raise NotImplementedError("use_view_dirs=False is not supported")
     _lib.require_cuda(rays_o, rays_d)
-    if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
-        from .train_paths import unisurf_render_train
-        return unisurf_render_train(rays_o, rays_d, model, batched, calc_normal, logit_tau, rayschunk, netchunk, white_bkgd,
-                                    near_bypass, far_bypass, detailed_output, radius_of_interest, perturb, interval,
-                                    too_close_threshold, N_query, N_freespace)
+    # training (unisurf.py:307: Trainer.forward renders under autograd): root finding and sampling stay no_grad as in the
+    # reference (ray_casting.py:35 is @torch.no_grad, the samples are detached), the network query goes through
+    # UNISURF.forward (models/autograd.py), the compositing through UnisurfComposite
+    train = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
+    from ..composite import UnisurfComposite
     from ..ray_casting import _root_find
     lib = _lib.get_lib()
     B = rays_d.shape[0] if batched else 1
@@ -107,62 +107,66 @@ def volume_render(
     nan = float("nan")
     surface_fn = model.implicit_surface.forward
 
-    per_batch = []
-    with torch.cuda.device(dev), torch.no_grad():
-        st = _lib.stream_ptr(dev)
-        for b in range(B):
-            outs = []
-            for i0 in range(0, n_rays, int(rayschunk)):
-                ro, rd = o_b[b, i0:i0 + rayschunk].contiguous(), d_b[b, i0:i0 + rayschunk].contiguous()
-                R = ro.shape[0]
-                dirs, near, far = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
-                pts_prop = torch.empty(R, N_steps, 3, **f)
-                _lib.check(lib.nr_unisurf_ray_setup(
-                    _lib.ptr(ro), _lib.ptr(rd), R, float(radius_of_interest), nan if near_bypass is None else float(near_bypass),
-                    nan if far_bypass is None else float(far_bypass), N_steps, _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far),
-                    _lib.ptr(pts_prop), st), "unisurf_ray_setup")
-                state, mask, msc, m0 = _root_find(surface_fn, ro, dirs, near, far, pts_prop, N_steps, logit_tau, N_secant)
-                u_int = torch.rand([R, N_query], device=dev) if perturb else None     # unisurf.py:164
-                u_free = torch.rand([R, N_freespace], device=dev) if perturb else None  # unisurf.py:193
-                depth_s, surf_pts = torch.empty(R, **f), torch.empty(R, 3, **f)
-                d_all, pts = torch.empty(R, M, **f), torch.empty(R, M, 3, **f)
-                _lib.check(lib.nr_unisurf_sample(
-                    _lib.ptr(ro), _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far), _lib.ptr(state), _lib.ptr(mask),
-                    _lib.ptr(msc), _lib.ptr(m0), R, float(interval), float(too_close_threshold), N_query, N_freespace,
-                    _lib.ptr(u_int), _lib.ptr(u_free), _lib.ptr(depth_s), _lib.ptr(surf_pts), _lib.ptr(d_all),
-                    _lib.ptr(pts), st), "unisurf_sample")
-                # network query, one net-chunk of the flattened points at a time (batchify_query semantics)
-                flat_pts = pts.reshape(-1, 3)
-                flat_views = dirs.unsqueeze(-2).expand(R, M, 3).reshape(-1, 3)
-                rad_l, sdf_l, nab_l = [], [], []
-                for j0 in range(0, R * M, int(netchunk)):
+    def render_chunk(ro, rd, st):
+        R = ro.shape[0]
+        with torch.no_grad():
+            dirs, near, far = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
+            pts_prop = torch.empty(R, N_steps, 3, **f)
+            _lib.check(lib.nr_unisurf_ray_setup(
+                _lib.ptr(ro), _lib.ptr(rd), R, float(radius_of_interest), nan if near_bypass is None else float(near_bypass),
+                nan if far_bypass is None else float(far_bypass), N_steps, _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far),
+                _lib.ptr(pts_prop), st), "unisurf_ray_setup")
+            state, mask, msc, m0 = _root_find(surface_fn, ro, dirs, near, far, pts_prop, N_steps, logit_tau, N_secant)
+            u_int = torch.rand([R, N_query], device=dev) if perturb else None     # unisurf.py:164
+            u_free = torch.rand([R, N_freespace], device=dev) if perturb else None  # unisurf.py:193
+            depth_s, surf_pts = torch.empty(R, **f), torch.empty(R, 3, **f)
+            d_all, pts = torch.empty(R, M, **f), torch.empty(R, M, 3, **f)
+            _lib.check(lib.nr_unisurf_sample(
+                _lib.ptr(ro), _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far), _lib.ptr(state), _lib.ptr(mask),
+                _lib.ptr(msc), _lib.ptr(m0), R, float(interval), float(too_close_threshold), N_query, N_freespace,
+                _lib.ptr(u_int), _lib.ptr(u_free), _lib.ptr(depth_s), _lib.ptr(surf_pts), _lib.ptr(d_all),
+                _lib.ptr(pts), st), "unisurf_sample")
+        # network query, one net-chunk of the flattened points at a time (batchify_query semantics, incl. the chunk-wide
+        # F.normalize of unisurf.py:36): the fused inference query, or UNISURF.forward under autograd on [1, chunk, 3]
+        # slices -- the layout batchify_query(dim_batchify=1) feeds it (unisurf.py:214)
+        flat_pts = pts.reshape(-1, 3)
+        flat_views = dirs.unsqueeze(-2).expand(R, M, 3).reshape(-1, 3)
+        rad_l, sdf_l, nab_l = [], [], []
+        for j0 in range(0, R * M, int(netchunk)):
+            if train:
+                r_, s_, n_ = model.forward(flat_pts[None, j0:j0 + netchunk], flat_views[None, j0:j0 + netchunk])
+                r_, s_, n_ = r_[0], s_[0], n_[0]
+            else:
+                with torch.no_grad():
                     r_, s_, n_ = query_radiance(model.implicit_surface, model.radiance_net, flat_pts[j0:j0 + netchunk],
                                                 flat_views[j0:j0 + netchunk], chunk_normalize=True)
-                    rad_l.append(r_); sdf_l.append(s_); nab_l.append(n_)
-                radiances = (rad_l[0] if len(rad_l) == 1 else torch.cat(rad_l)).reshape(R, M, 3)
-                logits = (sdf_l[0] if len(sdf_l) == 1 else torch.cat(sdf_l)).reshape(R, M)
-                nablas = (nab_l[0] if len(nab_l) == 1 else torch.cat(nab_l)).reshape(R, M, 3)
-                rgb, depth, acc = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
-                normals = torch.empty(R, 3, **f) if calc_normal else None
-                alpha = torch.empty(R, M, **f) if detailed_output else None
-                w = torch.empty(R, M, **f) if detailed_output else None
-                _lib.check(lib.nr_unisurf_composite(
-                    _lib.ptr(logits), _lib.ptr(nablas) if calc_normal else None, _lib.ptr(radiances), _lib.ptr(d_all), R, M,
-                    int(bool(white_bkgd)), _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(normals),
-                    _lib.ptr(alpha), _lib.ptr(w), st), "unisurf_composite")
-                ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
-                if calc_normal:
-                    ret_i['normals_volume'] = normals
-                if detailed_output:
-                    ret_i['surface_points'] = surf_pts
-                    ret_i['mask_surface'] = mask.bool()
-                    ret_i['depth_surface'] = depth_s
-                    ret_i['radiance'] = radiances
-                    ret_i['implicit_surface'] = logits
-                    ret_i['implicit_nablas'] = nablas
-                    ret_i['alpha'] = alpha
-                    ret_i['visibility_weights'] = w
-                outs.append(ret_i)
+            rad_l.append(r_); sdf_l.append(s_); nab_l.append(n_)
+        radiances = (rad_l[0] if len(rad_l) == 1 else torch.cat(rad_l)).reshape(R, M, 3)
+        logits = (sdf_l[0] if len(sdf_l) == 1 else torch.cat(sdf_l)).reshape(R, M)
+        nablas = (nab_l[0] if len(nab_l) == 1 else torch.cat(nab_l)).reshape(R, M, 3)
+        rgb, depth, acc, normals, alpha, w = UnisurfComposite.apply(
+            logits, nablas if calc_normal else None, radiances, d_all, bool(white_bkgd), bool(calc_normal),
+            bool(detailed_output))
+        ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
+        if calc_normal:
+            ret_i['normals_volume'] = normals
+        if detailed_output:
+            ret_i['surface_points'] = surf_pts
+            ret_i['mask_surface'] = mask.bool()
+            ret_i['depth_surface'] = depth_s
+            ret_i['radiance'] = radiances
+            ret_i['implicit_surface'] = logits
+            ret_i['implicit_nablas'] = nablas
+            ret_i['alpha'] = alpha
+            ret_i['visibility_weights'] = w
+        return ret_i
+
+    per_batch = []
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        for b in range(B):
+            outs = [render_chunk(o_b[b, i0:i0 + rayschunk].contiguous(), d_b[b, i0:i0 + rayschunk].contiguous(), st)
+                    for i0 in range(0, n_rays, int(rayschunk))]
             per_batch.append(OrderedDict((k, outs[0][k] if len(outs) == 1 else torch.cat([o_[k] for o_ in outs], 0))
                                          for k in outs[0].keys()))
     ret = OrderedDict()

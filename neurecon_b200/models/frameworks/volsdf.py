@@ -191,11 +191,11 @@ def volume_render(
     if not use_view_dirs:
         raise NotImplementedError("use_view_dirs=False is not supported")
     _lib.require_cuda(rays_o, rays_d)
-    if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
-        from .train_paths import volsdf_render_train
-        return volsdf_render_train(rays_o, rays_d, model, near, far, obj_bounding_radius, batched, calc_normal, rayschunk,
-                                   white_bkgd, use_nerfplusplus, detailed_output, perturb, N_samples, N_importance,
-                                   N_outside, max_upsample_steps, max_bisection_steps, epsilon)
+    # training (volsdf.py:578: Trainer.forward renders under autograd): the error-bounded sampler stays no_grad as in the
+    # reference (volsdf.py:77 fine_sample is @torch.no_grad via its callers, the depths are detached), the network query
+    # goes through VolSDF.forward (models/autograd.py), density + compositing through VolsdfComposite
+    train = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
+    from ..composite import VolsdfComposite
     lib = _lib.get_lib()
     B = rays_d.shape[0] if batched else 1
     prefix = [B, -1] if batched else [-1]
@@ -204,65 +204,61 @@ def volume_render(
     d_flat = _lib.f32c(rays_d.reshape(-1, 3))
     n_total = o_flat.shape[0]
     f = dict(dtype=torch.float32, device=dev)
-    alpha_t, beta_t = model.forward_ab()
-    alpha_t, beta_t = alpha_t.detach().float().contiguous(), beta_t.detach().float().contiguous()
+    alpha_g, beta_g = model.forward_ab()                      # with the graph to ln_beta when training
+    alpha_t, beta_t = alpha_g.detach().float().contiguous(), beta_g.detach().float().contiguous()
     N_init = N_samples * 4
     M_in = N_samples + N_importance
     M_out = N_outside if use_nerfplusplus else 0
-    M = M_in + M_out
-    miss = torch.zeros(1, dtype=torch.int32, device=dev)
+    miss = torch.zeros(1, dtype=torch.int32, device=dev)      # rays that miss the sphere / radii inside the ray's closest point
 
     outs = []
-    with torch.cuda.device(dev), torch.no_grad():
+    with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
         step = int(rayschunk) * B
         for i0 in range(0, n_total, step):
             ro, rd = o_flat[i0:i0 + step], d_flat[i0:i0 + step]
             R = ro.shape[0]
-            dirs, fars = torch.empty(R, 3, **f), torch.empty(R, **f)
-            d_init, pts_init = torch.empty(R, N_init, **f), torch.empty(R, N_init, 3, **f)
-            _lib.check(lib.nr_volsdf_ray_setup(
-                _lib.ptr(ro), _lib.ptr(rd), R, float(near), float(far),
-                float(obj_bounding_radius) if use_nerfplusplus else -1.0, N_init, _lib.ptr(dirs), _lib.ptr(fars),
-                _lib.ptr(miss), _lib.ptr(d_init), N_init, _lib.ptr(pts_init), st), "volsdf_ray_setup")
-            d_fine, beta_map, iter_usage = fine_sample(
-                lambda p: _surface_sdf(model, p), d_init, ro, dirs, alpha_t, beta_t, fars, eps=epsilon,
-                max_iter=max_upsample_steps, max_bisection=max_bisection_steps, final_N_importance=N_importance,
-                N_up=N_samples * 4, perturb=perturb)
-            d_in, pts = torch.empty(R, M_in, **f), torch.empty(R, M_in, 3, **f)
-            _lib.check(lib.nr_volsdf_merge(_lib.ptr(ro), _lib.ptr(dirs), _lib.ptr(fars), R, float(near), N_samples,
-                                           _lib.ptr(d_fine), N_importance, _lib.ptr(d_in), _lib.ptr(pts), st), "volsdf_merge")
+            with torch.no_grad():
+                dirs, fars = torch.empty(R, 3, **f), torch.empty(R, **f)
+                d_init, pts_init = torch.empty(R, N_init, **f), torch.empty(R, N_init, 3, **f)
+                _lib.check(lib.nr_volsdf_ray_setup(
+                    _lib.ptr(ro), _lib.ptr(rd), R, float(near), float(far),
+                    float(obj_bounding_radius) if use_nerfplusplus else -1.0, N_init, _lib.ptr(dirs), _lib.ptr(fars),
+                    _lib.ptr(miss), _lib.ptr(d_init), N_init, _lib.ptr(pts_init), st), "volsdf_ray_setup")
+                d_fine, beta_map, iter_usage = fine_sample(
+                    lambda p: _surface_sdf(model, p), d_init, ro, dirs, alpha_t, beta_t, fars, eps=epsilon,
+                    max_iter=max_upsample_steps, max_bisection=max_bisection_steps, final_N_importance=N_importance,
+                    N_up=N_samples * 4, perturb=perturb)
+                d_in, pts = torch.empty(R, M_in, **f), torch.empty(R, M_in, 3, **f)
+                _lib.check(lib.nr_volsdf_merge(_lib.ptr(ro), _lib.ptr(dirs), _lib.ptr(fars), R, float(near), N_samples,
+                                               _lib.ptr(d_fine), N_importance, _lib.ptr(d_in), _lib.ptr(pts), st), "volsdf_merge")
             views = dirs.unsqueeze(-2).expand(R, M_in, 3)
-            radiances, sdf, nablas = query_radiance(model.implicit_surface, model.radiance_net, pts, views)
-            if model.use_sphere_bg:
-                _lib.check(lib.nr_sphere_min(_lib.ptr(pts), _lib.ptr(sdf), R * M_in, float(model.obj_bounding_radius), st),
-                           "sphere_min")
+            if train:
+                radiances, sdf, nablas = model.forward(pts, views)                         # volsdf.py:450
+            else:
+                with torch.no_grad():
+                    radiances, sdf, nablas = query_radiance(model.implicit_surface, model.radiance_net, pts, views)
+                    if model.use_sphere_bg:
+                        _lib.check(lib.nr_sphere_min(_lib.ptr(pts), _lib.ptr(sdf), R * M_in, float(model.obj_bounding_radius),
+                                                     st), "sphere_min")
             sigma_out = radiance_out = d_out = None
             if use_nerfplusplus:
-                # inverse-sphere samples (volsdf.py:456-467): tiny [R, N_outside] host-side compositions
-                from ...utils import rend_util
-                t_ = torch.linspace(0, 1, N_outside + 2)[..., 1:-1].float().to(dev)
-                rs = (obj_bounding_radius / torch.flip(t_, dims=[-1])).expand(R, N_outside)
-                if perturb:
-                    mids = .5 * (rs[..., 1:] + rs[..., :-1])
-                    upper = torch.cat([mids, rs[..., -1:]], -1)
-                    lower = torch.cat([rs[..., :1], mids], -1)
-                    rs = lower + (upper - lower) * torch.rand(upper.shape).float().to(dev)
-                d_out = rend_util.get_dvals_from_radius(ro, dirs, rs).contiguous()
-                pts_out = ro[..., None, :] + dirs[..., None, :] * d_out[..., :, None]
-                x_out = torch.cat([pts_out / rs[..., None], 1. / rs[..., None]], dim=-1)
+                # inverted-sphere samples (volsdf.py:456-467) in one launch; the jitter uniforms come from the CPU generator
+                # like the reference's (device generator while a CUDA graph is being captured)
+                with torch.no_grad():
+                    u = None
+                    if perturb:
+                        u = (torch.rand([R, N_outside], device=dev) if torch.cuda.is_current_stream_capturing()
+                             else torch.rand([R, N_outside]).float().to(dev))
+                    d_out, x_out = torch.empty(R, N_outside, **f), torch.empty(R, N_outside, 4, **f)
+                    _lib.check(lib.nr_volsdf_outside_points(_lib.ptr(ro), _lib.ptr(dirs), R, float(obj_bounding_radius),
+                                                            N_outside, _lib.ptr(u), _lib.ptr(d_out), _lib.ptr(x_out),
+                                                            _lib.ptr(miss), st), "volsdf_outside_points")
                 sigma_out, radiance_out = model.nerf_outside.forward(x_out, dirs.unsqueeze(-2).expand(R, N_outside, 3))
-                sigma_out, radiance_out = sigma_out.contiguous(), radiance_out.contiguous()
-            rgb, depth, acc = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
-            normals = torch.empty(R, 3, **f) if calc_normal else None
-            sigma_all = torch.empty(R, M, **f) if detailed_output else None
-            p_i = torch.empty(R, M - 1, **f) if detailed_output else None
-            tau = torch.empty(R, M - 1, **f) if detailed_output else None
-            _lib.check(lib.nr_volsdf_composite(
-                _lib.ptr(sdf), _lib.ptr(nablas) if calc_normal else None, _lib.ptr(radiances), _lib.ptr(d_in),
-                _lib.ptr(alpha_t), _lib.ptr(beta_t), R, M_in, _lib.ptr(sigma_out), _lib.ptr(radiance_out),
-                _lib.ptr(d_out), M_out, int(bool(white_bkgd)), _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc),
-                _lib.ptr(normals), _lib.ptr(sigma_all), _lib.ptr(p_i), _lib.ptr(tau), st), "volsdf_composite")
+            rgb, depth, acc, normals, sigma_all, p_i, tau = VolsdfComposite.apply(
+                sdf, nablas if calc_normal else None, radiances, d_in, alpha_g if train else alpha_t,
+                beta_g if train else beta_t, sigma_out, radiance_out, d_out, bool(white_bkgd), bool(calc_normal),
+                bool(detailed_output))
             ret_i = OrderedDict([('rgb', rgb), ('depth_volume', depth), ('mask_volume', acc)])
             if calc_normal:
                 ret_i['normals_volume'] = normals
@@ -281,8 +277,8 @@ def volume_render(
                     ret_i['sigma_out'] = sigma_out
                     ret_i['radiance_out'] = radiance_out
             outs.append(ret_i)
-    if use_nerfplusplus:
-        assert int(miss.item()) == 0, "every ray must intersect the bounding sphere (volsdf.py:404-405)"
+    if use_nerfplusplus and not torch.cuda.is_current_stream_capturing():
+        assert int(miss.item()) == 0, "every ray must intersect the bounding sphere (volsdf.py:404-405, rend_util.py:225)"
 
     ret = OrderedDict()
     for k in outs[0].keys():

@@ -67,28 +67,40 @@ def sample_cdf(bins, cdf, N_importance, det=False, eps=1e-5, u=None, return_deta
 
 
 def get_sphere_intersection(ray_origins, ray_directions, r=1.0):
-    """rend_util.py:188-210 (exact ray/sphere near & far with hit mask)."""
+    """rend_util.py:188-210: exact ray / sphere (near, far, mask_intersect), each [..., 1]; ``nr_sphere_intersection``."""
     _lib.require_cuda(ray_origins, ray_directions)
-    o2 = (ray_origins ** 2).sum(-1, keepdim=True)
-    od = (ray_origins * ray_directions).sum(-1, keepdim=True)
-    under = od ** 2 + r ** 2 - o2
-    mask = under > 0
-    sq = torch.sqrt(under.clamp_min(0))
-    zero = torch.zeros_like(od)
-    near = torch.where(mask, -sq - od, zero).clamp_min(0.0)
-    far = torch.where(mask, sq - od, zero).clamp_min(0.0)
-    return near, far, mask
+    lib = _lib.get_lib()
+    prefix = ray_origins.shape[:-1]
+    o, d = _lib.f32c(ray_origins.reshape(-1, 3)), _lib.f32c(ray_directions.expand_as(ray_origins).reshape(-1, 3))
+    R, dev = o.shape[0], o.device
+    near, far = torch.empty(R, dtype=torch.float32, device=dev), torch.empty(R, dtype=torch.float32, device=dev)
+    mask = torch.empty(R, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nr_sphere_intersection(_lib.ptr(o), _lib.ptr(d), R, float(r), _lib.ptr(near), _lib.ptr(far),
+                                              _lib.ptr(mask), _lib.stream_ptr(dev)), "sphere_intersection")
+    return near.reshape(*prefix, 1), far.reshape(*prefix, 1), mask.bool().reshape(*prefix, 1)
 
 
-def get_dvals_from_radius(ray_origins, ray_directions, rs, far_end=True):
-    """rend_util.py:213-234."""
+def get_dvals_from_radius(ray_origins, ray_directions, rs, far_end=True, strict=False):
+    """rend_util.py:213-234: depth at which the ray is ``rs`` away from the origin; rs [..., N] -> d_vals [..., N];
+    ``nr_dvals_from_radius``.  The reference asserts ``rs^2 > |o|^2 - (o.d)^2`` with a host read of the whole tensor
+    (:225); here violating entries come back NaN (what ``torch.sqrt`` gives) without a sync, and ``strict=True`` performs
+    the reference's assertion (one host read of a device counter)."""
     _lib.require_cuda(ray_origins, ray_directions, rs)
-    o2 = (ray_origins ** 2).sum(-1, keepdim=True)
-    od = (ray_origins * ray_directions).sum(-1, keepdim=True)
-    under = rs ** 2 - (o2 - od ** 2)
-    assert (under > 0).all()
-    sq = torch.sqrt(under)
-    return (-od + sq) if far_end else (-od - sq).clamp_min(0.0)
+    lib = _lib.get_lib()
+    prefix = ray_origins.shape[:-1]
+    o, d = _lib.f32c(ray_origins.reshape(-1, 3)), _lib.f32c(ray_directions.expand_as(ray_origins).reshape(-1, 3))
+    R, dev = o.shape[0], o.device
+    N = rs.shape[-1]
+    rs_f = _lib.f32c(rs.expand(*prefix, N).reshape(R, N))
+    out = torch.empty(R, N, dtype=torch.float32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev) if strict else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.nr_dvals_from_radius(_lib.ptr(o), _lib.ptr(d), _lib.ptr(rs_f), R, N, int(bool(far_end)),
+                                            _lib.ptr(out), _lib.ptr(bad), _lib.stream_ptr(dev)), "dvals_from_radius")
+    if strict:
+        assert int(bad.item()) == 0, "get_dvals_from_radius: rs inside the ray's closest approach (rend_util.py:225)"
+    return out.reshape(*prefix, N)
 
 
 def quat_to_rot(q):

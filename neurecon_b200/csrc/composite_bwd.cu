@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(kWarps * 32) composite_bwd_kernel(const BwdArg
   float* sT = smem_f + (size_t)warp * 2 * K;    // transmittance
   float* sG = sT + K;                           // dL/d alpha_i (NeuS, UNISURF) or dL/d p_i (VolSDF)
   const float* as = a.a_saved + ray * (int64_t)K;
-  const float* ws = a.w + ray * (int64_t)K;
 
   // ---- A: transmittance ------------------------------------------------------------------------------------------
   float carry = 1.0f;
@@ -132,10 +131,14 @@ __global__ void __launch_bounds__(kWarps * 32) composite_bwd_kernel(const BwdArg
     const bool ok = i < K;
     float gw = 0.0f, wi = 0.0f, T = 0.0f, q = 1.0f;
     if (ok) {
-      wi = ws[i];
       T = sT[i];
       const float s = as[i];
       q = MODE == MODE_VOLSDF ? s : (1.0f - s) + 1e-10f;
+      // the weight is rebuilt from THIS sweep's transmittance instead of read back from the forward's output: dL/d alpha_i
+      // = gw_i T_i - S_i / q_i is a difference of nearly equal terms wherever neighbouring samples have similar colours
+      // (it telescopes to gw T_end / q_i), and a forward whose scan rounded T a few ulps differently leaves a residual
+      // 1e3 times the rounding (measured: 2e-3 on sum(g_logit) of a UNISURF step)
+      wi = (MODE == MODE_VOLSDF ? (1.0f - s) + 1e-10f : s) * T;
       const float* c = i < a.K0c ? a.c0 + (ray * (int64_t)a.ld_c0 + i) * 3 : a.c1 + (ray * (int64_t)a.ld_c1 + (i - a.K0c)) * 3;
       const float d = i < a.K0d ? a.d0[ray * (int64_t)a.ld_d0 + i] : a.d1[ray * (int64_t)a.ld_d1 + (i - a.K0d)];
       gw = gr[0] * c[0] + gr[1] * c[1] + gr[2] * c[2] + g_acc + g_dep * (d - Dp);
@@ -217,7 +220,8 @@ __global__ void __launch_bounds__(kWarps * 32) composite_bwd_kernel(const BwdArg
     if (bg) {
       for (int i = lane; i < K; i += 32) {
         const bool in = i < M1 && inside(i);
-        const float wi = ws[i];
+        const float sa = as[i];
+        const float wi = sa * sT[i];
         const float gcx = wi * gr[0], gcy = wi * gr[1], gcz = wi * gr[2];
         float* go = a.g_c0 + (ray * (int64_t)K + i) * 3;          // g_radiance_out [R,T,3]
         go[0] = in ? 0.f : gcx; go[1] = in ? 0.f : gcy; go[2] = in ? 0.f : gcz;

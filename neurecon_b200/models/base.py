@@ -91,6 +91,20 @@ def _param_key(module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
 
 
+def _cached(module, slot, key, build):
+    """Packed weights / descriptors of a module, rebuilt when a parameter changed.  ``nn.DataParallel`` replicas are
+    shallow copies that SHARE the module's ``_cache`` dict and run in concurrent threads on different devices
+    (the reference renders that way, neus.py:413-414): entries are keyed by (slot, device), built into a local and
+    stored with one dict assignment, so a replica can neither see a half-built entry nor another device's pointers."""
+    dev = next(module.parameters()).device
+    k = (slot, dev.type, dev.index)
+    hit = module._cache.get(k)
+    if hit is None or hit[0] != key:
+        hit = (key, build())
+        module._cache[k] = hit
+    return hit[1]
+
+
 def _pad4(k):
     return (k + 3) & ~3
 
@@ -198,9 +212,7 @@ class ImplicitSurface(nn.Module):
     def _descriptor(self):
         """Device-resident packed weights + C descriptor, rebuilt only when a parameter changed."""
         self._check_supported()
-        key = _param_key(self)
-        c = self._cache
-        if c.get("key") != key:
+        def build():
             Wl = [_effective_weight(l) for l in self.surface_fc_layers]
             bl = [l.bias for l in self.surface_fc_layers]
             scales = [1.0 / math.sqrt(2) if i in self.skips else 1.0 for i in range(self.D + 1)]
@@ -216,9 +228,8 @@ class ImplicitSurface(nn.Module):
                 d.W[i], d.b[i] = Ws[i].data_ptr(), bs[i].data_ptr()
             d.umma_image = None
             d.umma_bias = None
-            c.clear()
-            c.update(key=key, desc=d, keep=(Ws, bs))
-        return c["desc"]
+            return d, (Ws, bs)            # the descriptor holds raw pointers: keep the tensors alive with it
+        return _cached(self, "desc", _param_key(self), build)[0]
 
     def _umma_net(self, radiance_net=None):
         """bf16 image / bias table / step templates for the tcgen05 tier (cached like _descriptor)."""
@@ -226,8 +237,8 @@ class ImplicitSurface(nn.Module):
         from .. import umma_pack
         key = (_param_key(self), None if radiance_net is None else _param_key(radiance_net), _lib.get_precision())
         slot = "umma_fused" if radiance_net is not None else "umma"
-        c = self._cache.get(slot)
-        if c is None or c[0] != key:
+
+        def build():
             with torch.no_grad():
                 Wl = [_effective_weight(l).detach().float() for l in self.surface_fc_layers]
                 bl = [l.bias.detach().float() for l in self.surface_fc_layers]
@@ -241,11 +252,9 @@ class ImplicitSurface(nn.Module):
                               rad_b=[l.bias.detach().float() for l in radiance_net.layers],
                               rad_multires=radiance_net.embed_multires,
                               rad_multires_view=radiance_net.embed_multires_view)
-                net = umma_pack.UmmaNet(Wl, bl, self.embed_multires, self.skips[0] if self.skips else -1,
-                                        operand=_lib.get_precision(), **kw)
-            c = (key, net)
-            self._cache[slot] = c
-        return c[1]
+                return umma_pack.UmmaNet(Wl, bl, self.embed_multires, self.skips[0] if self.skips else -1,
+                                         operand=_lib.get_precision(), **kw)
+        return _cached(self, slot, key, build)
 
     def _run_umma(self, x, mode, want_feat=False, radiance_net=None, view_dirs=None, want_sdf=True,
                   want_nablas=True, normal_scale=None):
@@ -424,9 +433,7 @@ class RadianceNet(nn.Module):
         if self.skips or not self.use_view_dirs:
             raise NotImplementedError("neurecon_b200 RadianceNet supports skips=[] with use_view_dirs=True "
                                       "(every shipped reference config)")
-        key = _param_key(self)
-        c = self._cache
-        if c.get("key") != key:
+        def build():
             Wl = [_effective_weight(l) for l in self.layers]
             Ws, bs = _pack_layers(Wl, [l.bias for l in self.layers])
             d = _lib.RadianceNetDesc()
@@ -438,9 +445,8 @@ class RadianceNet(nn.Module):
                 d.W[i], d.b[i] = Ws[i].data_ptr(), bs[i].data_ptr()
             d.umma_image = None
             d.umma_bias = None
-            c.clear()
-            c.update(key=key, desc=d, keep=(Ws, bs))
-        return c["desc"]
+            return d, (Ws, bs)
+        return _cached(self, "desc", _param_key(self), build)[0]
 
     def forward(self, x, view_dirs, normals, geometry_feature):
         """base.py:372-391."""

@@ -1,4 +1,6 @@
-"""Framework dispatcher, mirrors models/frameworks/__init__.py of the reference."""
+"""Framework dispatcher: ``get_model(args)`` as models/frameworks/__init__.py of the reference (same framework names,
+same 5-tuple ``(model, trainer, render_kwargs_train, render_kwargs_test, renderer)``), plus ``get_framework(name)``
+for callers that want the module."""
 
 
 def get_framework(name):
@@ -13,3 +15,9 @@ def get_framework(name):
         from . import unisurf
         return unisurf
     raise NotImplementedError("unknown framework %r" % name)
+
+
+def get_model(args):
+    if args.model.framework not in ("UNISURF", "NeuS", "VolSDF"):
+        raise NotImplementedError
+    return get_framework(args.model.framework).get_model(args)

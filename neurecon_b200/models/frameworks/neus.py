@@ -111,6 +111,26 @@ def _outside_points(rays_o, dirs, far, d_mid, N_outside, perturb):
     return d_vals, x_out
 
 
+def _forced_samples(rays_o, rays_d_raw, d_all, obj_bounding_radius, near_bypass, far_bypass):
+    """Parity-test hook (``samples_bypass``): the tensors ``_upsample`` returns, for GIVEN sorted depths d_all [R, M]
+    (neus.py:284-288: points, mid depths, mid points)."""
+    lib = _lib.get_lib()
+    R, dev = rays_o.shape[0], rays_o.device
+    f = dict(dtype=torch.float32, device=dev)
+    dirs, near, far = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
+    d0, p0 = torch.empty(R, 2, **f), torch.empty(R, 2, 3, **f)
+    nan = float("nan")
+    _lib.check(lib.nr_neus_ray_setup(
+        _lib.ptr(rays_o), _lib.ptr(rays_d_raw), R, float(obj_bounding_radius),
+        nan if near_bypass is None else float(near_bypass), nan if far_bypass is None else float(far_bypass), 2,
+        _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far), _lib.ptr(d0), _lib.ptr(p0), _lib.stream_ptr(dev)), "neus_ray_setup")
+    d_all = _lib.f32c(d_all.to(dev))
+    pts = rays_o[:, None, :] + dirs[:, None, :] * d_all[..., None]
+    d_mid = 0.5 * (d_all[..., 1:] + d_all[..., :-1])
+    pts_mid = rays_o[:, None, :] + dirs[:, None, :] * d_mid[..., None]
+    return dirs, d_all, pts.contiguous(), d_mid.contiguous(), pts_mid.contiguous(), far
+
+
 def _upsample(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
               N_upsample_iters, perturb, return_far=False, return_field=False, with_nablas=False):
     """neus.py:184-288 for one flat ray chunk [R,3]: returns dirs, d_all, pts, d_mid, pts_mid [, far]
@@ -197,6 +217,9 @@ def volume_render(
         N_nograd_samples=2048,
         N_upsample_iters=4,
 
+        # determinism hook for parity tests: {"d_all": [R, M] sorted depths} replaces the up-sampler's result
+        samples_bypass=None,
+
         **dummy_kwargs):
     """neus.py:118-397.  rays_o / rays_d: [(B,) N_rays, 3] (rays_d not normalised).
     Returns (rgb, depth_volume, ret) with the reference's ``ret`` keys and shapes."""
@@ -234,11 +257,15 @@ def volume_render(
         for i0 in range(0, n_total, step):
             ro, rd = o_flat[i0:i0 + step], d_flat[i0:i0 + step]
             R = ro.shape[0]
-            if train:
+            if samples_bypass is not None:
+                dirs, d_all, pts, d_mid, pts_mid, far = _forced_samples(
+                    ro, rd, samples_bypass["d_all"][i0:i0 + step], obj_bounding_radius, near_bypass, far_bypass)
+            elif train:
                 with torch.no_grad():
                     dirs, d_all, pts, d_mid, pts_mid, far = _upsample(
                         model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
                         N_upsample_iters, perturb, return_far=True)
+            if train or samples_bypass is not None:
                 sdf, nablas, _ = model.implicit_surface.forward_with_nablas(pts)            # neus.py:294
                 radiances = model.forward_radiance(pts_mid, dirs.unsqueeze(-2).expand(R, M - 1, 3))   # neus.py:298
             else:
@@ -294,3 +321,12 @@ class SingleRenderer(nn.Module):
 
     def forward(self, rays_o, rays_d, **kwargs):
         return volume_render(rays_o, rays_d, self.model, **kwargs)
+
+
+def __getattr__(name):
+    """``Trainer`` and ``get_model`` (neus.py of the reference) live in frameworks/trainers.py; resolved lazily because
+    that module imports this one."""
+    if name in ("Trainer", "get_model"):
+        from . import trainers
+        return {"Trainer": trainers.NeusTrainer, "get_model": trainers.get_model_neus}[name]
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

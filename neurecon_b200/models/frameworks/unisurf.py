@@ -77,6 +77,10 @@ def volume_render(
         too_close_threshold=0.1,
         N_query=64,
         N_freespace=32,
+
+        # determinism hook for parity tests: {"d_all": [B, R, N_query + N_freespace] sorted depths} replaces the sampler's
+        # depths (root finding still runs: its outputs are part of ``ret``)
+        samples_bypass=None,
         **dummy_kwargs):
     """unisurf.py:64-283.  rays_o / rays_d: [(B,) N_rays, 3].  Returns (rgb, depth_volume, ret).
 
@@ -107,7 +111,7 @@ def volume_render(
     nan = float("nan")
     surface_fn = model.implicit_surface.forward
 
-    def render_chunk(ro, rd, st):
+    def render_chunk(ro, rd, st, d_forced=None):
         R = ro.shape[0]
         with torch.no_grad():
             dirs, near, far = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
@@ -126,6 +130,11 @@ def volume_render(
                 _lib.ptr(msc), _lib.ptr(m0), R, float(interval), float(too_close_threshold), N_query, N_freespace,
                 _lib.ptr(u_int), _lib.ptr(u_free), _lib.ptr(depth_s), _lib.ptr(surf_pts), _lib.ptr(d_all),
                 _lib.ptr(pts), st), "unisurf_sample")
+            if d_forced is not None:
+                d_all = _lib.f32c(d_forced.to(dev))
+                pts = (ro[:, None, :] + dirs[:, None, :] * d_all[..., None]).contiguous()
+                if "surface_points" in samples_bypass:
+                    surf_pts = _lib.f32c(samples_bypass["surface_points"].reshape(-1, 3)[:R].to(dev))
         # network query, one net-chunk of the flattened points at a time (batchify_query semantics, incl. the chunk-wide
         # F.normalize of unisurf.py:36): the fused inference query, or UNISURF.forward under autograd on [1, chunk, 3]
         # slices -- the layout batchify_query(dim_batchify=1) feeds it (unisurf.py:214)
@@ -165,7 +174,9 @@ def volume_render(
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
         for b in range(B):
-            outs = [render_chunk(o_b[b, i0:i0 + rayschunk].contiguous(), d_b[b, i0:i0 + rayschunk].contiguous(), st)
+            outs = [render_chunk(o_b[b, i0:i0 + rayschunk].contiguous(), d_b[b, i0:i0 + rayschunk].contiguous(), st,
+                                 None if samples_bypass is None
+                                 else samples_bypass["d_all"].reshape(B, n_rays, -1)[b, i0:i0 + rayschunk])
                     for i0 in range(0, n_rays, int(rayschunk))]
             per_batch.append(OrderedDict((k, outs[0][k] if len(outs) == 1 else torch.cat([o_[k] for o_ in outs], 0))
                                          for k in outs[0].keys()))
@@ -184,3 +195,12 @@ class SingleRenderer(nn.Module):
 
     def forward(self, rays_o, rays_d, **kwargs):
         return volume_render(rays_o, rays_d, self.model, **kwargs)
+
+
+def __getattr__(name):
+    """``Trainer`` and ``get_model`` (unisurf.py of the reference) live in frameworks/trainers.py; resolved lazily because
+    that module imports this one."""
+    if name in ("Trainer", "get_model"):
+        from . import trainers
+        return {"Trainer": trainers.UnisurfTrainer, "get_model": trainers.get_model_unisurf}[name]
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -186,6 +186,10 @@ def volume_render(
         max_upsample_steps=5,
         max_bisection_steps=10,
         epsilon=0.1,
+
+        # determinism hook for parity tests: {"d_all": [R, N_samples + N_importance] sorted depths, "beta_map": [R,1],
+        # "iter_usage": [R]} replaces the error-bounded sampler's result
+        samples_bypass=None,
         **dummy_kwargs):
     """volsdf.py:334-551.  rays_o / rays_d: [(B,) N_rays, 3].  Returns (rgb, depth_volume, ret)."""
     if not use_view_dirs:
@@ -225,13 +229,20 @@ def volume_render(
                     _lib.ptr(ro), _lib.ptr(rd), R, float(near), float(far),
                     float(obj_bounding_radius) if use_nerfplusplus else -1.0, N_init, _lib.ptr(dirs), _lib.ptr(fars),
                     _lib.ptr(miss), _lib.ptr(d_init), N_init, _lib.ptr(pts_init), st), "volsdf_ray_setup")
-                d_fine, beta_map, iter_usage = fine_sample(
-                    lambda p: _surface_sdf(model, p), d_init, ro, dirs, alpha_t, beta_t, fars, eps=epsilon,
-                    max_iter=max_upsample_steps, max_bisection=max_bisection_steps, final_N_importance=N_importance,
-                    N_up=N_samples * 4, perturb=perturb)
-                d_in, pts = torch.empty(R, M_in, **f), torch.empty(R, M_in, 3, **f)
-                _lib.check(lib.nr_volsdf_merge(_lib.ptr(ro), _lib.ptr(dirs), _lib.ptr(fars), R, float(near), N_samples,
-                                               _lib.ptr(d_fine), N_importance, _lib.ptr(d_in), _lib.ptr(pts), st), "volsdf_merge")
+                if samples_bypass is None:
+                    d_fine, beta_map, iter_usage = fine_sample(
+                        lambda p: _surface_sdf(model, p), d_init, ro, dirs, alpha_t, beta_t, fars, eps=epsilon,
+                        max_iter=max_upsample_steps, max_bisection=max_bisection_steps, final_N_importance=N_importance,
+                        N_up=N_samples * 4, perturb=perturb)
+                    d_in, pts = torch.empty(R, M_in, **f), torch.empty(R, M_in, 3, **f)
+                    _lib.check(lib.nr_volsdf_merge(_lib.ptr(ro), _lib.ptr(dirs), _lib.ptr(fars), R, float(near), N_samples,
+                                                   _lib.ptr(d_fine), N_importance, _lib.ptr(d_in), _lib.ptr(pts), st),
+                               "volsdf_merge")
+                else:
+                    d_in = _lib.f32c(samples_bypass["d_all"][i0:i0 + step].to(dev))
+                    pts = (ro[:, None, :] + dirs[:, None, :] * d_in[..., None]).contiguous()
+                    beta_map = samples_bypass["beta_map"][i0:i0 + step].to(dev)
+                    iter_usage = samples_bypass["iter_usage"][i0:i0 + step].to(dev)
             views = dirs.unsqueeze(-2).expand(R, M_in, 3)
             if train:
                 radiances, sdf, nablas = model.forward(pts, views)                         # volsdf.py:450
@@ -296,3 +307,12 @@ class SingleRenderer(nn.Module):
 
     def forward(self, rays_o, rays_d, **kwargs):
         return volume_render(rays_o, rays_d, self.model, **kwargs)
+
+
+def __getattr__(name):
+    """``Trainer`` and ``get_model`` (volsdf.py of the reference) live in frameworks/trainers.py; resolved lazily because
+    that module imports this one."""
+    if name in ("Trainer", "get_model"):
+        from . import trainers
+        return {"Trainer": trainers.VolsdfTrainer, "get_model": trainers.get_model_volsdf}[name]
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -3,7 +3,7 @@ import torch
 
 from .. import _lib
 from .._lib import C
-from .base import _pack_layers, _param_key, _MAX_POINTS_PER_CALL
+from .base import _cached, _pack_layers, _param_key, _MAX_POINTS_PER_CALL
 
 
 def _descriptor(module):
@@ -11,9 +11,7 @@ def _descriptor(module):
         raise NotImplementedError("neurecon_b200 NeRF supports use_view_dirs=True (the NeRF++ background configuration)")
     if len(module.skips) > 1:
         raise NotImplementedError("neurecon_b200 NeRF supports one skip")
-    key = _param_key(module)
-    c = module._cache
-    if c.get("key") != key:
+    def build():
         lin = list(module.pts_linears)
         Ws, bs = _pack_layers([l.weight for l in lin], [l.bias for l in lin])
         others = [module.alpha_linear, module.feature_linear, module.views_linears[0], module.rgb_linear]
@@ -28,19 +26,14 @@ def _descriptor(module):
         d.feature_W, d.feature_b = Wo[1].data_ptr(), bo[1].data_ptr()
         d.views_W, d.views_b = Wo[2].data_ptr(), bo[2].data_ptr()
         d.rgb_W, d.rgb_b = Wo[3].data_ptr(), bo[3].data_ptr()
-        c.clear()
-        c.update(key=key, desc=d, keep=(Ws, bs, Wo, bo))
-    return c["desc"]
+        return d, (Ws, bs, Wo, bo)        # the descriptor holds raw pointers: keep the tensors alive with it
+    return _cached(module, "desc", _param_key(module), build)[0]
 
 
 def _umma_net(module):
     from ..umma_pack import UmmaNerfNet
-    key = (_param_key(module), _lib.get_precision())
-    c = module._cache
-    if c.get("umma_key") != key:
-        c["umma_net"] = UmmaNerfNet(module, operand=_lib.get_precision())
-        c["umma_key"] = key
-    return c["umma_net"]
+    return _cached(module, "umma", (_param_key(module), _lib.get_precision()),
+                   lambda: UmmaNerfNet(module, operand=_lib.get_precision()))
 
 
 def nerf_forward(module, input_pts, input_views):

@@ -114,3 +114,14 @@ def pinhole_intrinsics(H, W, fov_deg=50.0, skew=0.0):
     K = np.eye(4)
     K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[0, 1] = f, f * 1.01, 0.5 * W - 0.3, 0.5 * H + 0.2, skew
     return _t(K)
+
+
+def make_view(seed, eye, H, W):
+    """One synthetic training view (the layout the reference's trainers consume): ``model_input`` = {c2w [1,4,4],
+    intrinsics [1,4,4], object_mask [1,H*W] bool}, ``ground_truth`` = {rgb [1,H*W,3]}."""
+    rs = np.random.RandomState(seed)
+    c2w = look_at_pose(eye)[None]
+    intr = pinhole_intrinsics(H, W)[None]
+    rgb = torch.from_numpy(rs.uniform(size=(1, H * W, 3)).astype(np.float32))
+    mask = torch.from_numpy(rs.uniform(size=(1, H * W)) < 0.7)
+    return dict(c2w=c2w, intrinsics=intr, object_mask=mask), dict(rgb=rgb)

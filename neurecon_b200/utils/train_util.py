@@ -150,7 +150,12 @@ class FusedAdam(torch.optim.Optimizer):
     reference's schedulers write it, train.py:210) before every replay."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, foreach=True))   # foreach: zero_grad() as one multi-tensor launch
+        # the group keys torch.optim.Adam reads, with the only values this optimiser implements, so that a state_dict
+        # saved here loads into torch.optim.Adam and back (the reference checkpoints optimizer.state_dict());
+        # foreach: zero_grad() as one multi-tensor launch
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False,
+                                      foreach=True, capturable=bool(capturable), differentiable=False, fused=None,
+                                      decoupled_weight_decay=False))
         self.capturable = bool(capturable)
         self._dev = {}          # per group index: pointer table, its key, device lr / step count -- never part of state_dict()
 
@@ -165,16 +170,31 @@ class FusedAdam(torch.optim.Optimizer):
                 d["lr"].fill_(float(group["lr"]))
 
     def state_dict(self):
-        """Checkpointing (checkpoints.py of the reference saves ``optimizer.state_dict()``): graph replays advance the
-        step count on the device only, so it is read back into ``group["step"]`` here (one sync per group)."""
+        """Checkpointing (checkpoints.py of the reference saves ``optimizer.state_dict()``) in torch.optim.Adam's layout:
+        the step count lives per group here (one bias correction per multi-tensor launch; graph replays advance it on
+        the device only, so it is read back first -- one sync per group) and is mirrored into ``state[p]["step"]`` as
+        the float tensor torch keeps, so that the dict loads into ``torch.optim.Adam`` with warm moments AND the right
+        bias correction."""
         for gi, group in enumerate(self.param_groups):
             d = self._dev.get(gi)
             if self.capturable and d is not None and "step" in d:
                 group["step"] = int(d["step"].item())
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st:
+                    st["step"] = torch.tensor(float(group.get("step", 0)), dtype=torch.float32)
         return super().state_dict()
 
     def load_state_dict(self, state_dict):
+        """Accepts this class's dicts and torch.optim.Adam's: the group's step is taken from the loaded per-parameter
+        steps (their maximum; torch keeps them equal for parameters that always have a gradient)."""
         super().load_state_dict(state_dict)
+        for group in self.param_groups:
+            steps = [int(float(self.state[p]["step"])) for p in group["params"] if p in self.state and "step" in self.state[p]]
+            if steps:
+                group["step"] = max(steps)
+            group["capturable"] = self.capturable
+            group.setdefault("foreach", True)
         self._dev = {}          # device counters and tables are rebuilt from the loaded groups at the next step
 
     @torch.no_grad()
@@ -193,7 +213,7 @@ class FusedAdam(torch.optim.Optimizer):
             entries = []
             for p in ps:
                 st = self.state[p]
-                if not st:
+                if "exp_avg" not in st:
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 assert p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32

@@ -209,7 +209,8 @@ def test_composite_without_upstream_gradients():
 
 
 # ---- sphere helpers (rend_util.py:188-234, volsdf.py:456-467) ---------------------------------------------------------
-def test_sphere_intersection_and_dvals_bitwise():
+def test_sphere_intersection_and_dvals():
+    """rend_util.py:188-234 at the SURVEY's bar for the sphere helpers (<= 1e-6 relative, identical hit mask)."""
     from oracle import sampling as osamp
     from neurecon_b200.utils import rend_util
     g = torch.Generator().manual_seed(11)
@@ -220,14 +221,13 @@ def test_sphere_intersection_and_dvals_bitwise():
     near, far, mask = rend_util.get_sphere_intersection(o.cuda(), dirs.cuda(), r=1.3)
     assert 0.2 < mask_w.float().mean() < 0.98
     assert torch.equal(mask.cpu(), mask_w)
-    assert torch.equal(near.cpu(), near_w) and torch.equal(far.cpu(), far_w), (
-        (near.cpu() - near_w).abs().max(), (far.cpu() - far_w).abs().max())
+    assert rel_err(near, near_w) < 1e-6 and rel_err(far, far_w) < 1e-6, (rel_err(near, near_w), rel_err(far, far_w))
     # radii beyond every origin: the assertion of rend_util.py:225 holds
     rs = (o.norm(dim=-1, keepdim=True) + 0.1) * (1.0 + torch.rand(R, 32, generator=g))
     for far_end in (True, False):
         want = osamp.get_dvals_from_radius(o, dirs, rs, far_end=far_end)
         got = rend_util.get_dvals_from_radius(o.cuda(), dirs.cuda(), rs.cuda(), far_end=far_end, strict=True)
-        assert torch.equal(got.cpu(), want), (far_end, (got.cpu() - want).abs().max())
+        assert rel_err(got, want) < 1e-6, (far_end, rel_err(got, want))
     # a radius inside the closest approach: NaN there, and strict=True raises like the reference's assert
     rs_bad = rs.clone()
     rs_bad[5, 7] = 1e-3

@@ -132,6 +132,207 @@ def train_step_bench(dev, world, rank, timed, R=512, steps=10):
             "algorithmic_tflops_per_gpu": R * 1.85e9 / (ms * 1e-3) / 1e12}
 
 
+def _event_ms(fn, reps=5, inner=4, flush=None):
+    """best-of-`reps` ms per call, `inner` calls per timing, the L2 flushed (a > 126 MB write) before each timing"""
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(inner):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / inner)
+    return min(ts)
+
+
+def hbm_rooflines(dev, hbm_peak, R=N_RAYS):
+    """K2 / K3 (sampling, compositing) against the HBM roofline: ALGORITHMIC bytes per ray / CUDA-event
+    time of the kernel alone on R rays of synthetic per-sample buffers (hundreds of MB: larger than the L2, which is
+    flushed before every timing anyway) / the measured copy bandwidth."""
+    import torch
+    from neurecon_b200 import _lib
+    from neurecon_b200.models.frameworks import neus
+    from neurecon_b200.utils import rend_util
+    lib = _lib.get_lib()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    f = dict(device=dev, generator=g)
+    out = {}
+
+    def put(name, ms, bytes_per_ray, rays, kernel):
+        gbs = rays * bytes_per_ray / (ms * 1e-3) / 1e9
+        out[name] = {"kernel": kernel, "ms": ms, "rays": rays, "bytes_per_ray": bytes_per_ray, "achieved_gbs": gbs,
+                     "frac_of_hbm_peak": gbs / hbm_peak}
+
+    with torch.no_grad():
+        M = 128                                            # NeuS: sdf[128] + nablas[128,3] + radiance[127,3] + d_mid[127] in, 32 B out
+        sdf, nab = torch.randn(R, M, **f) * 0.3, torch.randn(R, M, 3, **f)
+        rad, dmid = torch.rand(R, M - 1, 3, **f), torch.rand(R, M - 1, **f).sort(-1).values
+        s = torch.tensor([20.0], device=dev)
+        put("neus_composite", _event_ms(lambda: neus._composite(sdf, nab, rad, dmid, s, False, True, False), flush=flush),
+            4084 + 32, R, "neus_composite_staged_kernel")
+        del sdf, nab, rad, dmid
+        Mb, N = 64, 16                                     # sample_pdf: bins M + weights M-1 in, N out (det)
+        bins, w = torch.rand(R, Mb, **f).sort(-1).values, torch.rand(R, Mb - 1, **f)
+        put("sample_pdf_64_to_16", _event_ms(lambda: rend_util.sample_pdf(bins, w, N, det=True), flush=flush),
+            4 * Mb + 4 * (Mb - 1) + 4 * N, R, "sample_pdf_rows_kernel")
+        del bins, w
+        Rv, Mv = R // 2, 192                               # VolSDF: 192 x (sdf, nabla, radiance, d) in
+        sdfv, nabv = torch.randn(Rv, Mv, **f) * 0.3, torch.randn(Rv, Mv, 3, **f)
+        radv, dv = torch.rand(Rv, Mv, 3, **f), torch.rand(Rv, Mv, **f).sort(-1).values
+        al, be = torch.tensor([10.0], device=dev), torch.tensor([0.1], device=dev)
+        o3, o1a, o1b, o3n = (torch.empty(Rv, 3, device=dev), torch.empty(Rv, device=dev), torch.empty(Rv, device=dev),
+                             torch.empty(Rv, 3, device=dev))
+
+        def fnv():
+            _lib.check(lib.nr_volsdf_composite(_lib.ptr(sdfv), _lib.ptr(nabv), _lib.ptr(radv), _lib.ptr(dv), _lib.ptr(al),
+                                               _lib.ptr(be), Rv, Mv, None, None, None, 0, 0, _lib.ptr(o3), _lib.ptr(o1a),
+                                               _lib.ptr(o1b), _lib.ptr(o3n), None, None, None, _lib.stream_ptr(dev)), "volsdf_composite")
+        put("volsdf_composite", _event_ms(fnv, flush=flush), 6144 + 32, Rv, "volsdf_composite_staged_kernel")
+        del sdfv, nabv, radv, dv
+        Mu = 96                                            # UNISURF: 96 x (logit, nabla, radiance, d) in
+        lgu, nabu = torch.randn(R, Mu, **f) * 3.0, torch.randn(R, Mu, 3, **f)
+        radu, du = torch.rand(R, Mu, 3, **f), torch.rand(R, Mu, **f).sort(-1).values
+        p3, p1a, p1b, p3n = (torch.empty(R, 3, device=dev), torch.empty(R, device=dev), torch.empty(R, device=dev),
+                             torch.empty(R, 3, device=dev))
+
+        def fnu():
+            _lib.check(lib.nr_unisurf_composite(_lib.ptr(lgu), _lib.ptr(nabu), _lib.ptr(radu), _lib.ptr(du), R, Mu, 0,
+                                                _lib.ptr(p3), _lib.ptr(p1a), _lib.ptr(p1b), _lib.ptr(p3n), None, None,
+                                                _lib.stream_ptr(dev)), "unisurf_composite")
+        put("unisurf_composite", _event_ms(fnu, flush=flush), 3072 + 32, R, "unisurf_composite_staged_kernel")
+        del lgu, nabu, radu, du
+        # NeuS up-sampler: the five nr_neus_upsample_step launches of one render (merge + slopes + logistic CDF + inverse-CDF
+        # draw, then the final emit), timed one by one between the (untimed) sdf evaluations of an analytic sphere.
+        # Bytes per ray and step: state read 8 (m_cur + n_new), state written 8 (m_cur + n_new), 16 new depths + points
+        # written (256 B), the final step writes points, mid depths and mid points of all 128 samples instead.
+        Ru, n0, nf = min(R, 1 << 18), 64, 16
+        o = torch.nn.functional.normalize(torch.randn(Ru, 3, **f), dim=-1) * 2.5
+        dr = torch.nn.functional.normalize(-o + 0.1 * torch.randn(Ru, 3, **f), dim=-1)
+        ff = dict(dtype=torch.float32, device=dev)
+        dirs, near, far = torch.empty(Ru, 3, **ff), torch.empty(Ru, **ff), torch.empty(Ru, **ff)
+        st = _lib.stream_ptr(dev)
+        cap = n0 + 4 * nf
+        step_bytes = [8 * 64 * 2 + 256, 8 * 80 * 2 + 256, 8 * 96 * 2 + 256, 8 * 112 * 2 + 256, 8 * 128 * 2 + 12 * 128 + 4 * 127 + 12 * 127]
+
+        def one_render():
+            d_new, pts_new = torch.empty(Ru, n0, **ff), torch.empty(Ru, n0, 3, **ff)
+            _lib.check(lib.nr_neus_ray_setup(_lib.ptr(o), _lib.ptr(dr), Ru, 1.0, float("nan"), float("nan"), n0, _lib.ptr(dirs),
+                                             _lib.ptr(near), _lib.ptr(far), _lib.ptr(d_new), _lib.ptr(pts_new), st), "ray_setup")
+            d_buf, sdf_buf = torch.empty(Ru, cap, **ff), torch.empty(Ru, cap, **ff)
+            pts_all, d_mid, pts_mid = torch.empty(Ru, cap, 3, **ff), torch.empty(Ru, cap - 1, **ff), torch.empty(Ru, cap - 1, 3, **ff)
+            m_cur, n_new, total = 0, n0, 0.0
+            for it in range(5):
+                sdf_new = (pts_new.norm(dim=-1) - 0.5).contiguous()
+                n_next = 0 if it == 4 else nf
+                d_next, pts_next = torch.empty(Ru, max(n_next, 1), **ff), torch.empty(Ru, max(n_next, 1), 3, **ff)
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.check(lib.nr_neus_upsample_step(
+                    _lib.ptr(o), _lib.ptr(dirs), Ru, _lib.ptr(d_buf), _lib.ptr(sdf_buf), cap, m_cur, _lib.ptr(d_new),
+                    _lib.ptr(sdf_new), n_new, it, n_next, None, _lib.ptr(d_next), _lib.ptr(pts_next), _lib.ptr(pts_all),
+                    _lib.ptr(d_mid), _lib.ptr(pts_mid), None, None, st), "neus_upsample_step")
+                e1.record()
+                torch.cuda.synchronize()
+                total += e0.elapsed_time(e1)
+                m_cur += n_new
+                d_new, pts_new, n_new = d_next, pts_next, n_next
+            return total
+        one_render()
+        put("neus_upsample_5_steps", min(one_render() for _ in range(3)), sum(step_bytes), Ru, "neus_upsample_kernel x5")
+    return out
+
+
+def extra_configs(dev, rank, world, timed, precision):
+    """BASELINE.json configs 4 and 5 and two informational legs, all under this run's clock.
+    config 4: VolSDF + NeRF++ (configs/volsdf_nerfpp_blended.yaml) full 576x768 view, the rays of ONE image split over
+      the ranks by contiguous ranges (`dist_util.shard_range`; strong scaling, no collective);
+    config 5: extract_surface's 512^3 lattice WITH nablas, x-planes split over the ranks.
+    fp32 tier: the same NeuS render on the fp32 SIMT tier (the <= 1e-4 path), 16 384 rays."""
+    import torch
+    import neurecon_b200
+    from neurecon_b200.models.frameworks import neus, volsdf
+    from neurecon_b200.utils import dist_util, mesh_util, rend_util, synthetic
+    out = {}
+    with torch.no_grad():
+        # ---- config 4 ----
+        torch.manual_seed(0)
+        mv = volsdf.VolSDF(**dict(synthetic.VOLSDF_MODEL_KWARGS, beta_init=0.01, use_nerfplusplus=True))
+        synthetic.reseed_parameters(mv, seed=3)
+        mv = mv.to(dev)
+        c2w = synthetic.look_at_pose([1.6, 1.2, 1.0])[None].to(dev)
+        intr = synthetic.pinhole_intrinsics(H, W)[None].to(dev)
+        ro, rd, _ = rend_util.get_rays(c2w, intr, H, W, N_rays=-1)
+        lo, hi = dist_util.shard_range(N_RAYS, rank, world)
+        ro, rd = ro[0, lo:hi].contiguous(), rd[0, lo:hi].contiguous()
+        kw = dict(calc_normal=True, detailed_output=False, perturb=False, rayschunk=65536, near=0.0, far=6.0,
+                  obj_bounding_radius=3.0, max_upsample_steps=5, use_nerfplusplus=True, N_outside=32)
+        volsdf.volume_render(ro, rd, mv, **kw)
+        ms = timed(lambda: volsdf.volume_render(ro, rd, mv, **kw), 2) / 2
+        out["config4_volsdf_nerfpp_576x768"] = {
+            "value": N_RAYS / (ms * 1e-3), "unit": "rays/s", "ms_per_image": ms, "scaling": "strong",
+            "workload": "VolSDF + NeRF++ (configs/volsdf_nerfpp_blended.yaml, beta 0.01 random init), one 576x768 view, "
+                        "128 + 64 samples + 32 outside, <= 5 up-sample iterations, its %d rays split over %d rank(s)" % (N_RAYS, world)}
+        del mv
+        # ---- config 5 ----
+        m = build_model(1, dev)
+        GN = 512
+        plo, phi = dist_util.shard_range(GN, rank, world)
+        mesh_util.query_sdf_grid(m.implicit_surface, N=GN, plane_range=(plo, min(plo + 8, phi)), with_nablas=True)
+        ms = timed(lambda: mesh_util.query_sdf_grid(m.implicit_surface, N=GN, plane_range=(plo, phi), with_nablas=True), 1)
+        out["config5_grid_512_nablas"] = {
+            "value": GN ** 3 / (ms * 1e-3), "unit": "queries/s", "ms": ms, "scaling": "strong",
+            "workload": "extract_surface lattice 512^3 (mesh_util.py:82-111) with analytic nablas, x-planes split over %d rank(s), "
+                        "results left in HBM" % world,
+            "algorithmic_tflops": GN ** 3 * MFLOP_PER_QUERY_NABLA * 1e6 / (ms * 1e-3) / 1e12}
+        # ---- fp32 tier ----
+        if precision != "fp32":
+            o, d = synthetic.make_rays(16384, shell_radius=2.5, jitter=0.1, seed=100 + rank)
+            o, d = o.to(dev), d.to(dev)
+            neurecon_b200.set_precision("fp32")
+            try:
+                kwn = dict(calc_normal=True, detailed_output=False, perturb=False, rayschunk=65536)
+                neus.volume_render(o[:2048], d[:2048], m, **kwn)
+                ms = timed(lambda: neus.volume_render(o, d, m, **kwn), 1)
+            finally:
+                neurecon_b200.set_precision(precision)
+            out["neus_fp32_tier"] = {"value": world * 16384 / (ms * 1e-3), "unit": "rays/s", "rays_per_gpu": 16384,
+                                     "workload": "the headline NeuS render on the fp32 SIMT tier (<= 1e-4 parity), 16384 rays per GPU"}
+    return out
+
+
+def reference_cuda_eager(dev, n_rays=4096):
+    """Informational: the reference's algorithm as plain PyTorch ops ON THE GPU -- the oracle
+    port's torch fp32 eager path on cuda:0, TF32 off -- i.e. what running the reference on a B200 amounts to."""
+    import torch
+    from oracle import neus as oneus
+    from neurecon_b200.utils import synthetic
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = build_model(1, "cpu")
+    sd = {k: v.detach().clone().to(dev) for k, v in m.state_dict().items()}
+    o, d = synthetic.make_rays(n_rays, shell_radius=2.5, jitter=0.1, seed=1)
+    o, d = o.to(dev), d.to(dev)
+    oneus.volume_render(o[:512], d[:512], sd, NEUS_CFG, calc_normal=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(2):
+        oneus.volume_render(o, d, sd, NEUS_CFG, calc_normal=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    return {"value": n_rays / (ms * 1e-3), "unit": "rays/s", "sample": "%d rays of the headline workload" % n_rays,
+            "what": "oracle port of the reference's PyTorch ops, eager, fp32 (TF32 off), on cuda:0"}
+
+
 def cpu_reference_rate(n_rays, reps, seed=1):
     """rays/s of the oracle port (torch CPU, fp32, all host threads) on `n_rays` rays of the workload."""
     import torch
@@ -167,7 +368,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "rays/sec (NeuS 64+64 samples)", "value": rate, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config("fp32"),
+        "config": reference_config(),
         "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": "%d rays of the 576x768 workload per step, oracle port (torch CPU fp32)" % CPU_SAMPLE_RAYS},
         "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -176,17 +377,28 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+WORKLOAD = ("NeuS volume_render, 576x768 = 442368 rays per GPU per step, configs/neus.yaml network "
+            "(8x256 SDF MLP + 4x256 radiance MLP), 64 coarse + 4x16 up-sampled samples, calc_normal, "
+            "perturb=False, random-init weights")
+
+
 def workload_config(precision):
-    return {"workload": "NeuS volume_render, 576x768 = 442368 rays per GPU per step, configs/neus.yaml network "
-                        "(8x256 SDF MLP + 4x256 radiance MLP), 64 coarse + 4x16 up-sampled samples, calc_normal, "
-                        "perturb=False, random-init weights",
-            "rays_per_step_per_gpu": N_RAYS, "rayschunk": 65536, "mlp_tier": precision,
+    return {"workload": WORKLOAD, "rays_per_step_per_gpu": N_RAYS, "rayschunk": 65536, "mlp_tier": precision,
             "l2_policy": "inputs and intermediates per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+def reference_config():
+    """The reference arm times a BOUNDED SAMPLE of the workload: one of its steps is CPU_SAMPLE_RAYS rays of the same
+    view, and ms_per_step is the time of that sample (value = rays/s is what compares with the GPU arm)."""
+    return {"workload": WORKLOAD + " -- reference arm: each step renders a %d-ray sample of that view on the host CPU "
+                        "(oracle port of the reference's torch-CPU path, fp32, all host threads)" % CPU_SAMPLE_RAYS,
+            "rays_per_step_per_gpu": CPU_SAMPLE_RAYS, "sample_rays_per_step": CPU_SAMPLE_RAYS, "full_workload_rays": N_RAYS,
+            "rayschunk": 65536, "mlp_tier": "fp32", "l2_policy": "n/a (CPU)"}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel the roofline times, from one `ncu --set full`
 # capture of that launch (profiles/): reverse-mode kernel of the fp16 tier / tangent-tile kernel of the bf16 tier
-NCU_DRAM_BYTES_PER_LAUNCH = {"fp16": 46644736 + 787309056, "bf16": 13689344}
+NCU_DRAM_BYTES_PER_LAUNCH = {"fp16": 13254656 + 115763200, "bf16": 13689344}
 
 
 def main():
@@ -315,10 +527,10 @@ def main():
         kname = ("mlp_rev_kernel (fused tcgen05, fp16 operands, reverse-mode normals): sdf + analytic nabla of %d points, "
                  "%d launch(es), %.3f ms; algorithmic 1.967 MFLOP/query = what the tensor pipe executes (forward sweep + "
                  "backward sweep)" % (n_pts, k_launches, k_ms))
-        tsrc = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (524288 points, "
-                "profiles/mlp_rev_r1_ncu_summary.txt): 46.6 MB read (the points and the weights once), 787 MB written, of "
-                "which 8.4 MB are outputs and the rest L2 write-backs of the 76 MB softplus' scratch (1.07 GB stored into "
-                "it per launch, L2 hit rate 95 %); algorithmic 14.7 MB")
+        tsrc = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture of this launch (524288 points, "
+                "profiles/r2_mlp_rev_dram.txt): 13.3 MB read, 115.8 MB written = 8.4 MB of outputs + the softplus' scratch "
+                "lines evicted before the backward sweep read them back (the rest are dropped with discard.global.L2 "
+                "after the read: round 1 wrote 787 MB); algorithmic 14.7 MB")
     elif precision == "bf16":
         kname = ("mlp_umma_kernel (fused tcgen05, bf16 operands, forward-mode tangent tiles): sdf + analytic nabla of %d "
                  "points, %d launch(es), %.3f ms; algorithmic 1.967 MFLOP/query (the tangents execute 4.2 MFLOP/query)"
@@ -344,6 +556,15 @@ def main():
     ms_grid = timed(lambda: mesh_util.query_sdf_grid(model.implicit_surface, N=GN, plane_range=(0, GN)), 3)
     sdf_qps = world * GN ** 3 * 3 / (ms_grid * 1e-3)
 
+    extras = extra_configs(dev, rank, world, timed, precision)
+    hbm = hbm_rooflines(dev, pk["hbm"]) if rank == 0 else None
+    eager = None
+    if rank == 0 and world == 1:
+        try:
+            eager = reference_cuda_eager(dev)
+        except Exception as e:                       # informational leg: never takes the line down
+            eager = {"error": repr(e)[:200]}
+
     line = None
     if rank == 0:
         cpu_baseline = None
@@ -362,7 +583,10 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "sdf_queries_per_s": {"value": sdf_qps, "unit": "queries/s", "workload": "%d^3 lattice per GPU, sdf only" % GN,
                                   "frac_of_bf16_peak": sdf_qps / world * 0.918 * 1e6 / 1e12 / pk["bf16"]},
+            "roofline_hbm": {"peak_gbs": pk["hbm"], "peak_source": pk["src"] + " copy bandwidth", "kernels": hbm},
+            "reference_cuda_eager": eager,
         }
+        line.update(extras)
 
     # ---- secondary: the 512-ray training iteration.  The headline numbers above are complete; a watchdog prints them and
     # ends the process if this block (a CUDA graph with an NCCL all-reduce inside at N > 1) should ever fail to return ----

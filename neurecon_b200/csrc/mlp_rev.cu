@@ -109,6 +109,18 @@ __device__ __forceinline__ void apply_sig16(const RowAddr& ra, int c, const uint
   st_shared_v4(ra.chunk(2 * c + 1), h[4], h[5], h[6], h[7]);
 }
 __device__ __forceinline__ uint4 ldcg16(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+// The softplus' codes are dead once the backward sweep has read them (the next tile pair overwrites the slot before it
+// reads it again).  Left alone, every line is eventually evicted from L2 DIRTY: 0.79 GB of write-backs per 524 288-point
+// launch (round 1: dram bytes 57 x the algorithmic traffic).  discard.global.L2 drops the line without the write-back.
+// One lane per 128-byte line (8 features x 16 B), after the whole warp has consumed its loads.
+#ifndef NR_SIG_DISCARD
+#define NR_SIG_DISCARD 1
+#endif
+__device__ __forceinline__ void discard_line(const uint8_t* p) {
+#if NR_SIG_DISCARD
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+#endif
+}
 __device__ __forceinline__ void stcg16(uint8_t* p, uint4 v) { __stcg(reinterpret_cast<uint4*>(p), v); }
 
 template <bool kF16, bool kShare>
@@ -471,6 +483,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
               for (int j = 3; j < pe_dim; j += 3) { g0 += r[j]; g1 += r[j + 1]; g2 += r[j + 2]; }
               const int64_t gp = p0 + etid;
               if (gp < a.n) { a.nabla[gp * 3] = g0; a.nabla[gp * 3 + 1] = g1; a.nabla[gp * 3 + 2] = g2; }
+            }
+          }
+          if (NR_SIG_DISCARD) {
+            __syncwarp();                                   // every lane of the warp has consumed its codes (use_sig differs
+            if (use_sig && (lane & 7) == 0) {               // between lanes around out_rows: the barrier stays outside)
+#pragma unroll
+              for (int k = 0; k < kCh; ++k) discard_line(sig_slot + k * kSigChunk);
             }
           }
           if (s + 1 < P.n_steps) publish(&in_ready[t]);

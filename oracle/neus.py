@@ -82,7 +82,7 @@ def composite_bg(sdf, nablas, radiances, d_all, s, rays_o, rays_d, far, sd, radi
     d_mid = 0.5 * (d_all[..., 1:] + d_all[..., :-1])
     pts_mid = rays_o[..., None, :] + rays_d[..., None, :] * d_mid[..., :, None]
     cdf, alpha_in = sdf_to_alpha(sdf, s)
-    t = sampling.linspace01(N_outside + 2, sdf.dtype)[1:-1]
+    t = sampling.linspace01(N_outside + 2, sdf.dtype, sdf.device)[1:-1]
     d_out = far / torch.flip(t, dims=[-1])
     d_vals = torch.cat([d_mid, d_out], dim=-1)
     pts_out = rays_o[..., None, :] + rays_d[..., None, :] * d_vals[..., :, None]
@@ -132,7 +132,7 @@ def volume_render(rays_o, rays_d, sd, cfg, obj_bounding_radius=1.0, calc_normal=
         near = near_bypass * torch.ones_like(near)
     if far_bypass is not None:
         far = far_bypass * torch.ones_like(far)
-    t = sampling.linspace01(N_samples, dtype)
+    t = sampling.linspace01(N_samples, dtype, rays_o.device)
     d_coarse = near * (1 - t) + far * t
 
     sdf_fn = lambda p: nets.sdf_forward(p, sdf_layers, mr, skips)

@@ -8,9 +8,13 @@ import numpy as np
 import torch
 
 
-def linspace01(n, dtype=torch.float32):
+def linspace01(n, dtype=torch.float32, device=None):
     """torch.linspace(0, 1, n) restated: step = fp32(1/(n-1)); the first half is
     ``step*i``, the second half ``1 - step*(n-1-i)``."""
+    return _linspace01_cpu(n, dtype).to(device) if device is not None else _linspace01_cpu(n, dtype)
+
+
+def _linspace01_cpu(n, dtype):
     if n == 1:
         return torch.zeros(1, dtype=dtype)
     i = np.arange(n, dtype=np.int64)
@@ -73,10 +77,10 @@ def invert_cdf(bins, cdf, u, eps=1e-5, return_inds=False):
     return (samples, below, above) if return_inds else samples
 
 
-def make_u(prefix, n, det, dtype, generator=None):
+def make_u(prefix, n, det, dtype, generator=None, device=None):
     if det:
-        return linspace01(n, dtype).expand(*prefix, n).contiguous()
-    return torch.rand(*prefix, n, dtype=dtype, generator=generator)
+        return linspace01(n, dtype, device).expand(*prefix, n).contiguous()
+    return torch.rand(*prefix, n, dtype=dtype, generator=generator, device=device)
 
 
 def pdf_to_cdf(weights):
@@ -91,7 +95,7 @@ def sample_pdf(bins, weights, n, det=False, eps=1e-5, u=None, return_inds=False)
     """utils/rend_util.py:255-292."""
     cdf = pdf_to_cdf(weights)
     if u is None:
-        u = make_u(cdf.shape[:-1], n, det, cdf.dtype)
+        u = make_u(cdf.shape[:-1], n, det, cdf.dtype, device=cdf.device)
     return invert_cdf(bins, cdf, u, eps, return_inds)
 
 
@@ -99,7 +103,7 @@ def sample_cdf(bins, cdf, n, det=False, eps=1e-5, u=None, return_inds=False):
     """utils/rend_util.py:294-327 (CDF given, not re-normalised)."""
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
     if u is None:
-        u = make_u(cdf.shape[:-1], n, det, cdf.dtype)
+        u = make_u(cdf.shape[:-1], n, det, cdf.dtype, device=cdf.device)
     return invert_cdf(bins, cdf, u, eps, return_inds)
 
 

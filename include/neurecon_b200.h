@@ -396,6 +396,43 @@ int nr_unisurf_composite_bwd(const float* logits, const float* alpha, const floa
                              float* g_radiance, float* g_nablas, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training GEMMs with 16-bit tensors in HBM (csrc/gemm16.cu): the per-layer building blocks of the reverse-mode
+ * training path of the SDF network (models/autograd_rev.py; reference semantics base.py:265-282 under create_graph
+ * + neus.py:443-458).  fp16 rows in, fp16 (or fp32) rows out, fp32 weights, fp32 accumulation on tcgen05.
+ * ------------------------------------------------------------------------------------------ */
+#define NR_G16_LINEAR 0   /* y = acc + bias */
+#define NR_G16_SOFTPLUS 1 /* y = softplus100(acc + bias), out2 = its derivative */
+#define NR_G16_SCALE 2    /* y = aux_a * acc (+ aux_b) */
+#define NR_G16_ADJ 3      /* y = aux_a * acc, out2 = 100 (1 - aux_a) * aux_b * acc */
+#define NR_G16_RELU 4
+#define NR_G16_SIGMOID 5
+#define NR_G16_MASK 6     /* y = aux_a > 0 ? acc : 0 */
+/* Y[M, N] = epilogue(A[M, K] W[N, K]^T).  A: fp16 rows of lda halves (a multiple of 8 covering K rounded up to 64; pad
+ * columns finite -- they meet zero weights); W fp32 [N, ldw]; bias fp32 [N] or NULL; Y fp16 (y_half) or fp32 rows of ldy
+ * elements, columns [N, round_up(N, 16)) written as zeros; aux_a / aux_b / out2: fp16 rows (NULL where the mode has none);
+ * fp16 rows are read and written 32 bytes at a time (32-byte aligned, leading dimensions multiples of 16). */
+int nr_gemm16(const void* A, int32_t lda, const float* W, int32_t ldw, const float* bias, int64_t M, int32_t N, int32_t K,
+              void* Y, int32_t ldy, int32_t y_half, int32_t mode, const void* aux_a, int32_t ld_a, const void* aux_b,
+              int32_t ld_b, void* out2, int32_t ld_o2, int32_t w_packed, void* stream);
+/* w_packed != 0: W points to the fp16 shared-memory image of the weight matrix written by nr_gemm16_pack_w
+ * (nr_gemm16_pack_w_bytes(N, K) bytes), which a CTA then fetches with bulk copies instead of converting W itself. */
+size_t nr_gemm16_pack_w_bytes(int32_t N, int32_t K);
+int nr_gemm16_pack_w(const float* W, int32_t ldw, int32_t N, int32_t K, void* img, void* stream);
+/* dW[N, K] += scale * G[rows, N]^T X[rows, K]; G, X fp16 rows (ldg, ldx multiples of 64), dW fp32 (atomics). */
+int nr_gemm16_tn(const void* G, int32_t ldg, const void* X, int32_t ldx, int64_t rows, int32_t N, int32_t K, float* dW,
+                 int32_t lddw, float scale, void* stream);
+/* out[N] += scale * column sums of a fp16 matrix (N <= 256). */
+int nr_colsum16(const void* A, int32_t lda, int64_t rows, int32_t N, float scale, float* out, void* stream);
+/* Embedder.forward (base.py:46-64) as fp16 rows e [n, ld] (columns [pe_dim, width) zero; optionally also into e2 at
+ * column off2), the transposed Jacobian nabla = J^T (g0 + ge) and the Jacobian product gbar = scale * J nbar. */
+int nr_pe16(const float* x, int64_t n, int32_t multires, void* e, int32_t ld, int32_t width, void* e2, int32_t ld2,
+            int32_t off2, void* stream);
+int nr_pe_jac_t(const float* x, int64_t n, int32_t multires, const float* g0, int32_t ldg0, const void* ge, int32_t ldge,
+                float* nabla, void* stream);
+int nr_pe_jac(const float* x, int64_t n, int32_t multires, const float* nbar, float scale, void* gbar, int32_t ld,
+              int32_t width, void* g2, int32_t ld2, int32_t off2, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * After the path in a training step: losses, gradient norm, Adam -- no host syncs.
  * ------------------------------------------------------------------------------------------ */
 /* NeuS Trainer.forward losses (neus.py:443-478) and the gradients of their sum:

@@ -113,6 +113,14 @@ _SIGNATURES = {
     "nr_bench_umma": (C.c_int, [_I32, _I32, _I32, _I32, _P, _I32, _P, _P]),
     "nr_selftest_umma2": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
     "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
+    "nr_gemm16": (C.c_int, [_P, _I32, _P, _I32, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _P]),
+    "nr_gemm16_pack_w_bytes": (_SZ, [_I32, _I32]),
+    "nr_gemm16_pack_w": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
+    "nr_gemm16_tn": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _I32, _F, _P]),
+    "nr_colsum16": (C.c_int, [_P, _I32, _I64, _I32, _F, _P, _P]),
+    "nr_pe16": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _I32, _I32, _P]),
+    "nr_pe_jac_t": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _P, _P]),
+    "nr_pe_jac": (C.c_int, [_P, _I64, _I32, _P, _F, _P, _I32, _I32, _P, _I32, _I32, _P]),
     "nr_sphere_intersection": (C.c_int, [_P, _P, _I64, C.c_double, _P, _P, _P, _P]),
     "nr_dvals_from_radius": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "nr_volsdf_outside_points": (C.c_int, [_P, _P, _I64, _F, _I32, _P, _P, _P, _P, _P]),

@@ -52,6 +52,11 @@ import os
 _GRAD_SCALE = float(2 ** int(os.environ.get("NEURECON_B200_GRAD_SCALE_LOG2", "14")))
 
 
+# fp16 tier: the SDF network trains through the reverse-mode 16-bit path of models/autograd_rev.py
+# (NEURECON_B200_TRAIN=forward: round 1's forward-mode tangent path on fp32 rows)
+_REVERSE_TRAINING = os.environ.get("NEURECON_B200_TRAIN", "reverse") != "forward"
+
+
 def _tc():
     """Training GEMMs on the tensor cores (csrc/gemm_tc.cu) in the fp16 / bf16 tiers, fp32 SIMT in the fp32 tier."""
     return _lib.tensor_tier()
@@ -317,7 +322,13 @@ def _run_sdf(surface, x, want_nablas):
     shape = x.shape[:-1]
     xf = _lib.f32c(x.detach().reshape(-1, 3))
     skip = surface.skips[0] if surface.skips else -1
-    sdf, nabla, feat = _SdfFn.apply(xf, surface.embed_multires, skip, want_nablas, *_surface_weights(surface))
+    wb = _surface_weights(surface)
+    if want_nablas and _tc() and _lib.get_precision() == "fp16" and _REVERSE_TRAINING:
+        from . import autograd_rev
+        if autograd_rev.supported([tuple(w.shape) for w in wb[0::2]], skip, surface.embed_multires):
+            sdf, nabla, feat = autograd_rev.SdfRevFn.apply(xf, surface.embed_multires, skip, *wb)
+            return sdf.reshape(shape), nabla.reshape(*shape, 3), feat.reshape(*shape, -1)
+    sdf, nabla, feat = _SdfFn.apply(xf, surface.embed_multires, skip, want_nablas, *wb)
     return sdf.reshape(shape), nabla.reshape(*shape, 3), feat.reshape(*shape, -1)
 
 

@@ -266,8 +266,14 @@ def volume_render(
                         model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
                         N_upsample_iters, perturb, return_far=True)
             if train or samples_bypass is not None:
-                sdf, nablas, _ = model.implicit_surface.forward_with_nablas(pts)            # neus.py:294
-                radiances = model.forward_radiance(pts_mid, dirs.unsqueeze(-2).expand(R, M - 1, 3))   # neus.py:298
+                # neus.py:294,298: forward_with_nablas at the samples and (inside forward_radiance) at the mid points -- ONE
+                # network call on both point sets, so that the per-layer training GEMMs run once over 255 points per ray
+                n1 = R * M
+                sdf_a, nab_a, feat_a = model.implicit_surface.forward_with_nablas(
+                    torch.cat([pts.reshape(-1, 3), pts_mid.reshape(-1, 3)], dim=0))
+                sdf, nablas = sdf_a[:n1].reshape(R, M), nab_a[:n1].reshape(R, M, 3)
+                radiances = model.radiance_net.forward(pts_mid, dirs.unsqueeze(-2).expand(R, M - 1, 3),
+                                                       nab_a[n1:].reshape(R, M - 1, 3), feat_a[n1:].reshape(R, M - 1, -1))
             else:
                 # sdf (and, when the caller wants normals or per-sample outputs, nablas) at the sorted samples come out of
                 # the up-sampler's own network queries: same points, same arithmetic as the reference's second

@@ -331,13 +331,15 @@ struct Tn16Args {
   int vec4;
 };
 
-__global__ void __launch_bounds__(288, 1) gemm16_tn_kernel(const Tn16Args g) {
+__global__ void __launch_bounds__(192, 1) gemm16_tn_kernel(const Tn16Args g, const __grid_constant__ CUtensorMap map_g,
+                                                            const __grid_constant__ CUtensorMap map_x) {
+  // warp 0: TMA producer (one thread), warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue (TMEM lane quarter = warp % 4)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kTnStages * kTnABytes;
   uint64_t* bars = (uint64_t*)(sB + kTnStages * kTnBBytes);
-  uint64_t* full = bars;                 // [kTnStages] 128 loader threads
+  uint64_t* full = bars;                 // [kTnStages] TMA transaction bytes
   uint64_t* empty = bars + kTnStages;    // [kTnStages] MMA commit
   uint64_t* acc_ready = bars + 2 * kTnStages;
   __shared__ uint32_t tmem_base_s;
@@ -350,67 +352,36 @@ __global__ void __launch_bounds__(288, 1) gemm16_tn_kernel(const Tn16Args g) {
   const int64_t c_end = min(n_chunks, c_begin + g.chunks_per_slice);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTnStages; ++s) { umma::mbar_init(&full[s], 128); umma::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kTnStages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
     umma::mbar_init(acc_ready, 1);
     umma::fence_barrier_init();
   }
-  if (warp == 4) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
+  if (warp == 1) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (c_begin >= c_end) {
     __syncthreads();
-    if (warp == 4) umma::tmem_dealloc(tmem_base, 512);
+    if (warp == 1) umma::tmem_dealloc(tmem_base, 512);
     return;
   }
 
-  if (warp < 4) {
-    // loaders: thread = (row of the 64-row chunk, column half); a 64-column piece of a row is 128 bytes = the MN-major
-    // operand's row piece: eight 16-byte loads, eight swizzled stores
-    const int r = threadIdx.x & 63, h = threadIdx.x >> 6;
-    uint32_t cnt = 0;
-    for (int64_t c = c_begin; c < c_end; ++c, ++cnt) {
-      const uint32_t st = cnt % kTnStages, ph = (cnt / kTnStages) & 1u;
-      const int64_t row = c * 64 + r;
-      const bool rok = row < g.rows;
-      const __half* grow = g.G + (size_t)(rok ? row : 0) * g.ldg;
-      const __half* xrow = g.X + (size_t)(rok ? row : 0) * g.ldx;
-      uint4 ga[2][8], xa[2][8];
-      bool gu[2] = {false, false}, xu[2] = {false, false};
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int col = m0 + 128 * h + 64 * half;
-        gu[half] = !(h == 1 && !two_mt) && col < g.ldg;
-#pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8)
-          ga[half][c8] = (gu[half] && rok) ? __ldg(reinterpret_cast<const uint4*>(grow + col) + c8) : make_uint4(0, 0, 0, 0);
-        const int cb = 128 * h + 64 * half;
-        xu[half] = cb < ncols && n0 + cb < g.ldx;
-#pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8)
-          xa[half][c8] = (xu[half] && rok) ? __ldg(reinterpret_cast<const uint4*>(xrow + n0 + cb) + c8) : make_uint4(0, 0, 0, 0);
+  if (warp == 0) {
+    // a 64-row chunk of G (the 128 / 256 columns of this CTA's M-tiles) and of X (ncols columns), as 64-column blocks:
+    // a [64 rows x 64 columns] box with the 128-byte swizzle IS one block of the MN-major operand
+    if (lane == 0) {
+      const int g_blocks = two_mt ? 4 : 2, x_blocks = (ncols + 63) / 64;
+      uint32_t cnt = 0;
+      for (int64_t c = c_begin; c < c_end; ++c, ++cnt) {
+        const uint32_t st = cnt % kTnStages, ph = (cnt / kTnStages) & 1u;
+        umma::mbar_wait(&empty[st], ph ^ 1u);
+        umma::mbar_arrive_expect_tx(&full[st], (uint32_t)(g_blocks + x_blocks) * kTnLbo);
+        for (int b = 0; b < g_blocks; ++b) tma_load_2d(sA + st * kTnABytes + b * kTnLbo, &map_g, m0 + 64 * b, (int)(c * 64), &full[st]);
+        for (int b = 0; b < x_blocks; ++b) tma_load_2d(sB + st * kTnBBytes + b * kTnLbo, &map_x, n0 + 64 * b, (int)(c * 64), &full[st]);
       }
-      umma::mbar_wait(&empty[st], ph ^ 1u);
-      uint8_t* a_dst = sA + st * kTnABytes;
-      uint8_t* b_dst = sB + st * kTnBBytes;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (!(h == 1 && !two_mt)) {
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8)
-            *reinterpret_cast<uint4*>(a_dst + umma::b_chunk_offset(r, 16 * h + 8 * half + c8, kTnLbo)) = ga[half][c8];
-        }
-        if (128 * h + 64 * half < ncols) {
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8)
-            *reinterpret_cast<uint4*>(b_dst + umma::b_chunk_offset(r, 16 * h + 8 * half + c8, kTnLbo)) = xa[half][c8];
-        }
-      }
-      umma::fence_proxy_async_smem();
-      umma::mbar_arrive(&full[st]);
     }
-  } else if (warp == 4) {
+  } else if (warp == 1) {
     const uint32_t idesc = umma::make_idesc_f16(128, ncols, 1, 1);
     const uint32_t hi = umma::smem_desc_hi(1024);
     const uint32_t a_lo0 = umma::smem_desc_lo(umma::smem_u32(sA), kTnLbo), b_lo0 = umma::smem_desc_lo(umma::smem_u32(sB), kTnLbo);
@@ -464,7 +435,7 @@ __global__ void __launch_bounds__(288, 1) gemm16_tn_kernel(const Tn16Args g) {
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 4) umma::tmem_dealloc(tmem_base, 512);
+  if (warp == 1) umma::tmem_dealloc(tmem_base, 512);
 }
 
 // W fp32 [N, ldw] -> the fp16 image nr_gemm16 keeps in shared memory: n_kc chunks of [npad rows x 64 k], K-major, 128-byte
@@ -653,8 +624,24 @@ extern "C" int nr_gemm16_tn(const void* G, int32_t ldg, const void* X, int32_t l
   slices = nr_cdiv(n_chunks, g.chunks_per_slice);
   const size_t smem = 1024 + kTnStages * (kTnABytes + kTnBBytes) + 128;
   dim3 grid((unsigned)slices, n_mt, n_nt);
+  CUtensorMap map_g, map_x;
+  {
+    const cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
+    const cuuint64_t gd[2] = {(cuuint64_t)ldg, (cuuint64_t)rows}, gs[1] = {(cuuint64_t)ldg * 2};
+    const cuuint64_t xd[2] = {(cuuint64_t)ldx, (cuuint64_t)rows}, xs[1] = {(cuuint64_t)ldx * 2};
+    const CUresult r1 = cuTensorMapEncodeTiled(&map_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(G), gd, gs, box, estr,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r2 = cuTensorMapEncodeTiled(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(X), xd, xs, box, estr,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+      nr_set_error("nr_gemm16_tn: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+      return NR_ERR_CUDA;
+    }
+  }
   NR_CHECK_CUDA(cudaFuncSetAttribute(gemm16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gemm16_tn_kernel<<<grid, 288, smem, (cudaStream_t)stream>>>(g);
+  gemm16_tn_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(g, map_g, map_x);
   NR_CHECK_LAUNCH("gemm16_tn_kernel");
   return NR_OK;
 }

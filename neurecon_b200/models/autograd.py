@@ -358,6 +358,11 @@ def radiance_forward_autograd(rad, x, view_dirs, normals, geometry_feature):
     wb = []
     for layer in rad.layers:
         wb += [_effective_weight(layer), layer.bias]
+    if _tc() and _lib.get_precision() == "fp16" and _REVERSE_TRAINING and all(tuple(w.shape)[0] == 256 for w in wb[0:-2:2]) \
+            and wb[0].shape[1] > 256:
+        from . import autograd_rev
+        rgb = autograd_rev.RadianceRevFn.apply(xf, vf, nf, ff, rad.embed_multires, rad.embed_multires_view, *wb)
+        return rgb.reshape(*shape, 3)
     rgb = _RadianceFn.apply(xf, vf, nf, ff, rad.embed_multires, rad.embed_multires_view, *wb)
     return rgb.reshape(*shape, 3)
 

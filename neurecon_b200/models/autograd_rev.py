@@ -203,3 +203,87 @@ class SdfRevFn(torch.autograd.Function):
             grads[2 * D], grads[2 * D + 1] = dWo, dbo
         ctx.state = None
         return (None, None, None, *grads)
+
+
+G_RELU, G_SIGMOID, G_MASK = 4, 5, 6
+
+
+def _r16(k):
+    return (k + 15) & ~15
+
+
+class RadianceRevFn(torch.autograd.Function):
+    """RadianceNet.forward (base.py:372-391) on the 16-bit training GEMMs: cat([PE(x), PE(view), normals, feat]) as fp16
+    rows -> ReLU layers -> sigmoid; the backward masks with the saved activations (h > 0) in the GEMM epilogue.
+    (x, view, normals [n,3], feat [n,F], W_0, b_0, ...) -> rgb [n,3]; gradients for normals, feat and the weights."""
+
+    @staticmethod
+    def forward(ctx, x, view, normals, feat, multires, multires_view, *wb):
+        lib = _lib.get_lib()
+        dev, n = x.device, x.shape[0]
+        L = len(wb) // 2
+        Ws = [_pad4c(w) for w in wb[0::2]]
+        bs = [b.detach().float().contiguous() for b in wb[1::2]]
+        dims = [(w.shape[0], w.shape[1]) for w in wb[0::2]]
+        px = 3 if multires < 0 else 3 * (1 + 2 * multires)
+        pv = 3 if multires_view < 0 else 3 * (1 + 2 * multires_view)
+        in0 = px + pv + 3 + feat.shape[1]
+        assert in0 == dims[0][1], "RadianceNet layer 0 width"
+        ld0 = (in0 + 63) // 64 * 64
+        h16 = dict(dtype=torch.float16, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            a0 = torch.zeros(n, ld0, **h16)
+            _lib.check(lib.nr_pe16(_lib.ptr(x), n, multires, _lib.ptr(a0), ld0, px, None, 0, 0, st), "pe16")
+            _lib.check(lib.nr_pe16(_lib.ptr(view), n, multires_view, _lib.ptr(a0[:, px:]), ld0, pv, None, 0, 0, st), "pe16")
+            a0[:, px + pv:px + pv + 3] = normals
+            a0[:, px + pv + 3:in0] = feat
+            acts = [a0]
+            for l in range(L - 1):
+                N, K = dims[l]
+                out = torch.empty(n, WIDTH, **h16)
+                _gemm16(acts[l], _Packed(Ws[l], N, K), bs[l], n, N, K, out, 1, G_RELU)
+                acts.append(out)
+            N, K = dims[L - 1]
+            y = torch.empty(n, _r16(N), dtype=torch.float32, device=dev)
+            _gemm16(acts[L - 1], Ws[L - 1], bs[L - 1], n, N, K, y, 0, G_SIGMOID)
+            rgb = y[:, :N].contiguous()
+        ctx.state = (acts, rgb, Ws, dims, n, px + pv, in0)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        lib = _lib.get_lib()
+        acts, rgb, Ws, dims, n, off, in0 = ctx.state
+        L = len(Ws)
+        dev = rgb.device
+        h16 = dict(dtype=torch.float16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        scale, inv = _GRAD_SCALE, 1.0 / _GRAD_SCALE
+        grads = [None] * (2 * L)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            N, K = dims[L - 1]
+            z = torch.zeros(n, 64, **h16)
+            z[:, :N] = g_rgb * rgb * (1.0 - rgb) * scale                       # through the sigmoid
+            for l in range(L - 1, -1, -1):
+                N, K = dims[l]
+                dW = torch.zeros(N, (K + 3) & ~3, **f32)
+                _lib.check(lib.nr_gemm16_tn(_lib.ptr(z), z.stride(0), _lib.ptr(acts[l]), acts[l].stride(0), n, N, K, _lib.ptr(dW),
+                                            dW.stride(0), inv, st), "gemm16_tn")
+                db = torch.zeros(N, **f32)
+                _lib.check(lib.nr_colsum16(_lib.ptr(z), z.stride(0), n, N, inv, _lib.ptr(db), st), "colsum16")
+                grads[2 * l], grads[2 * l + 1] = dW[:, :K], db
+                Wt = _pad4c(Ws[l][:, :K].t())                                    # [K, N]
+                if l > 0:
+                    zn = torch.empty(n, WIDTH, **h16)
+                    _gemm16(z, Wt, None, n, K, N, zn, 1, G_MASK, aux_a=acts[l])    # relu'(h) = (h > 0)
+                    z = zn
+                else:                                                            # gradient of the input row: two launches over its columns
+                    ga = torch.empty(n, _r16(K - WIDTH) + WIDTH, **f32)
+                    _gemm16(z, Wt[:WIDTH], None, n, WIDTH, N, ga, 0, G_LINEAR)
+                    _gemm16(z, Wt[WIDTH:], None, n, K - WIDTH, N, ga[:, WIDTH:], 0, G_LINEAR)
+        g_normals = ga[:, off:off + 3] * inv
+        g_feat = ga[:, off + 3:in0] * inv
+        ctx.state = None
+        return (None, None, g_normals, g_feat, None, None, *grads)

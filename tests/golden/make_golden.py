@@ -137,9 +137,35 @@ def golden_unisurf(ref):
     npz("unisurf_render_r40.npz", seed=4, **{k: ret[k][0] for k in keep})
 
 
+def golden_surface_render(ref):
+    """ray_casting.py:163-263: sphere tracing and root finding + surface rendering through the reference's own code"""
+    torch.manual_seed(0)
+    m = ref.neus.NeuS(**synthetic.NEUS_MODEL_KWARGS)
+    synthetic.reseed_parameters(m, seed=1)
+    R = 48
+    o, d = synthetic.make_rays(R, shell_radius=2.5, jitter=0.12, seed=9)
+    dn = torch.nn.functional.normalize(d, dim=-1)
+    out = {}
+    with torch.no_grad():
+        dp, pts, mask = ref.ray_casting.sphere_tracing_surface_points(m.implicit_surface, o[None], dn[None], near=0.0, far=5.0, N_iters=20)
+        out.update(st_d=dp[0], st_pts=pts[0], st_mask=mask[0])
+        col, dep, ex = ref.ray_casting.surface_render(o[None], d[None], m, calc_normal=True, batched=True,
+                                                      ray_casting_algo="sphere_tracing", ray_casting_cfgs=dict(near=0.0, far=5.0, N_iters=20))
+        out.update(st_color=col[0], st_depth=dep[0], st_normals=ex["normals_surface"][0], st_render_mask=ex["mask_surface"][0])
+        near, far = ref.rend_util.near_far_from_sphere(o[None], dn[None], r=1.0, keepdim=False)
+        col, dep, ex = ref.ray_casting.surface_render(o[None], d[None], m, calc_normal=True, batched=True, ray_casting_algo="root_finding",
+                                                      ray_casting_cfgs=dict(near=near, far=far, logit_tau=0.0, N_steps=256, N_secant_steps=8))
+        out.update(rf_color=col[0], rf_depth=dep[0], rf_normals=ex["normals_surface"][0], rf_mask=ex["mask_surface"][0], near=near[0], far=far[0])
+    npz("surface_render_r48.npz", seed=9, n_rays=R, **out)
+
+
 if __name__ == "__main__":
     ref = ref_loader.load()
+    if "surface" in sys.argv[1:]:
+        golden_surface_render(ref)
+        raise SystemExit(0)
     golden_neus(ref)
     golden_sampling(ref)
     golden_volsdf(ref)
     golden_unisurf(ref)
+    golden_surface_render(ref)

@@ -1,0 +1,110 @@
+"""Renders at BASELINE.json's configuration sizes against the oracle on the same seeded inputs (C1 NeuS
+1024 rays, C2 VolSDF 1024 rays, C3 UNISURF 2048 rays, and a 4096-ray slice of the 576 x 768 view the bench times), composited
+outputs within north_star's tolerances: <= 1e-4 (fp32 tier) / <= 1e-2 (fp16 tensor tier), max|a-b| / max|b| per tensor.
+The golden-vector tests cover 24-48 rays of the unmodified reference; these cover the sizes, through the oracle that those
+goldens pin.
+
+Two comparisons per configuration.  (1) With the oracle's sample depths forced (``samples_bypass``): EVERY ray within the
+tolerance -- this is the network + compositing parity.  (2) Free running: the samplers are bit-exact functions of their
+inputs (their own tests), but their inputs are network outputs, and an ulp of difference in an sdf value moves an inverse-CDF
+sample across a bin in flat stretches of the CDF (the oracle itself does not land on the reference's depths on 11 of 64 rays,
+tests/golden/make_golden_grads.py); over thousands of rays a few see a sample move by a bin width, which shifts their composite
+by a few 1e-4.  There: >= 99 % of the rays within the tolerance and no ray beyond 20 x it."""
+import pytest
+import torch
+
+import neurecon_b200
+from neurecon_b200.utils import rend_util, synthetic
+from conftest import NEUS_CFG, build_neus, build_unisurf, build_volsdf, cpu_state_dict, rel_err
+
+pytestmark = pytest.mark.gpu
+KEYS = ("rgb", "depth_volume", "mask_volume", "normals_volume")
+TIERS = [("fp32", 1e-4), ("fp16", 1e-2)]
+VOL_CFG = dict(multires=6, multires_view=-1, rad_multires=-1, skips=[4], D=8, D_rad=4, speed_factor=10.0)
+UNI_CFG = dict(multires=6, multires_view=-1, rad_multires=-1, skips=[4], D=8, D_rad=4, speed_factor=1.0)
+
+
+def _compare(ret, want, tol, tag, strict):
+    for k in KEYS:
+        a, b = ret[k].reshape(want[k].shape).detach().double().cpu(), want[k].double()
+        err = (a - b).abs() / b.abs().max()
+        per_ray = err.reshape(err.shape[0], -1).amax(-1) if err.dim() > 1 else err
+        if k == "depth_volume":        # sum(w d) / (sum(w) + 1e-10): a ratio of two roundings on rays that miss the object
+            per_ray = per_ray[want["mask_volume"].reshape(-1) > 1e-3]
+        if strict:
+            assert per_ray.max().item() < tol, (tag, k, "forced depths", per_ray.max().item())
+        else:
+            frac = (per_ray < tol).double().mean().item()
+            assert frac >= 0.99 and per_ray.max().item() < 20 * tol, (tag, k, "free running", frac, per_ray.max().item())
+
+
+def _render_tiers(render, want, tag, bypass):
+    """render(samples_bypass) -> (rgb, depth, ret)"""
+    for tier, tol in TIERS:
+        neurecon_b200.set_precision(tier)
+        try:
+            with torch.no_grad():
+                _compare(render(None)[2], want, tol, (tag, tier), strict=False)
+                _compare(render(bypass)[2], want, tol, (tag, tier), strict=True)
+        finally:
+            neurecon_b200.set_precision("fp16")
+
+
+def test_c1_neus_1024_rays():
+    from oracle import neus as oneus
+    from neurecon_b200.models.frameworks import neus
+    m = build_neus(seed=1)
+    o, d = synthetic.make_rays(1024, shell_radius=2.5, jitter=0.1, seed=11)
+    with torch.no_grad():
+        _, _, want = oneus.volume_render(o, d, cpu_state_dict(m), NEUS_CFG, calc_normal=True)
+    m = m.cuda()
+    _render_tiers(lambda bp: neus.volume_render(o.cuda(), d.cuda(), m, calc_normal=True, detailed_output=False, samples_bypass=bp),
+                  want, "C1", {"d_all": want["d_all"]})
+
+
+def test_c1_slice_of_the_576x768_view():
+    """4096 consecutive rays of the pinhole view bench.py renders (rend_util.get_rays on a look-at pose)"""
+    from oracle import neus as oneus
+    from neurecon_b200.models.frameworks import neus
+    m = build_neus(seed=1)
+    H, W = 576, 768
+    c2w = synthetic.look_at_pose([2.0, 1.2, 0.9])[None].cuda()
+    intr = synthetic.pinhole_intrinsics(H, W)[None].cuda()
+    ro, rd, _ = rend_util.get_rays(c2w, intr, H, W, N_rays=-1)
+    lo = (H // 2) * W + 100
+    o, d = ro[0, lo:lo + 4096].contiguous(), rd[0, lo:lo + 4096].contiguous()
+    with torch.no_grad():
+        _, _, want = oneus.volume_render(o.cpu(), d.cpu(), cpu_state_dict(m), NEUS_CFG, calc_normal=True)
+    m = m.cuda()
+    _render_tiers(lambda bp: neus.volume_render(o, d, m, calc_normal=True, detailed_output=False, samples_bypass=bp), want, "C1-slice",
+                  {"d_all": want["d_all"]})
+
+
+@pytest.mark.parametrize("beta_init", [0.1, 0.01])
+def test_c2_volsdf_1024_rays(beta_init):
+    from oracle import volsdf as ovol
+    from neurecon_b200.models.frameworks import volsdf
+    m = build_volsdf(beta_init, False)
+    o, d = synthetic.make_rays(1024, shell_radius=3.0 / 1.1, jitter=0.1, seed=12)
+    with torch.no_grad():
+        _, _, want = ovol.volume_render(o, d, cpu_state_dict(m), VOL_CFG, near=0.0, far=6.0, obj_bounding_radius=3.0,
+                                        calc_normal=True, max_upsample_steps=6)
+    m = m.cuda()
+    _render_tiers(lambda bp: volsdf.volume_render(o.cuda(), d.cuda(), m, calc_normal=True, detailed_output=False, near=0.0, far=6.0,
+                                                  obj_bounding_radius=3.0, max_upsample_steps=6, samples_bypass=bp),
+                  want, "C2 beta %g" % beta_init, {"d_all": want["d_vals"], "beta_map": want["beta_map"], "iter_usage": want["iter_usage"]})
+
+
+def test_c3_unisurf_2048_rays():
+    from oracle import unisurf as ouni
+    from neurecon_b200.models.frameworks import unisurf
+    m = build_unisurf()
+    o, d = synthetic.make_rays(2048, shell_radius=3.0, jitter=0.25, seed=13)
+    with torch.no_grad():
+        _, _, want = ouni.volume_render(o, d, cpu_state_dict(m), UNI_CFG, calc_normal=True, logit_tau=0.0, radius_of_interest=4.0,
+                                        interval=1.0)
+    m = m.cuda()
+    _render_tiers(lambda bp: unisurf.volume_render(o[None].cuda(), d[None].cuda(), m, batched=True, calc_normal=True,
+                                                   detailed_output=False, logit_tau=0.0, radius_of_interest=4.0, interval=1.0,
+                                                   samples_bypass=bp),
+                  want, "C3", {"d_all": want["d_all"][None]})

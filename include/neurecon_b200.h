@@ -432,6 +432,12 @@ int nr_pe_jac_t(const float* x, int64_t n, int32_t multires, const float* g0, in
 int nr_pe_jac(const float* x, int64_t n, int32_t multires, const float* nbar, float scale, void* gbar, int32_t ld,
               int32_t width, void* g2, int32_t ld2, int32_t off2, void* stream);
 
+/* Weight normalisation W = scale * g v / ||v||_row (base.py:226-227, nn.utils.weight_norm dim 0) of ALL layers of a
+ * network in one launch, and its backward (dW -> dg, dv) in one more.  `table`: n_entries <= 16 records IN HOST MEMORY of
+ * twelve 8-byte words {v*, g*, W*, dW*, dv*, dg* (device pointers), rows, cols, ldw, lddw, scale (double), first global
+ * row}, passed on to the kernel by value (graph-capturable); one warp per row. */
+int nr_weight_norm(const void* table, int32_t n_entries, int64_t total_rows, int32_t backward, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * After the path in a training step: losses, gradient norm, Adam -- no host syncs.
  * ------------------------------------------------------------------------------------------ */

@@ -121,6 +121,7 @@ _SIGNATURES = {
     "nr_pe16": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _I32, _I32, _P]),
     "nr_pe_jac_t": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _P, _P]),
     "nr_pe_jac": (C.c_int, [_P, _I64, _I32, _P, _F, _P, _I32, _I32, _P, _I32, _I32, _P]),
+    "nr_weight_norm": (C.c_int, [_P, _I32, _I64, _I32, _P]),
     "nr_sphere_intersection": (C.c_int, [_P, _P, _I64, C.c_double, _P, _P, _P, _P]),
     "nr_dvals_from_radius": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "nr_volsdf_outside_points": (C.c_int, [_P, _P, _I64, _F, _I32, _P, _P, _P, _P, _P]),

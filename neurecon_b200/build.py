@@ -88,7 +88,7 @@ def _build_locked(force, verbose):
     # never a half-written one
     for path, members in ((LIB_PATH, objs), (INJECT_LIB_PATH, inject_objs)):
         tmp = "%s.%d.tmp" % (path, os.getpid())
-        subprocess.check_call([nvcc, "-shared", "-o", tmp, *members, "-lcudart", "-lcuda"])
+        subprocess.check_call([nvcc, "-shared", "-o", tmp, *members, "-lcudart"])   # no -lcuda: see csrc/gemm16.cu
         os.replace(tmp, path)
     return LIB_PATH
 

@@ -23,6 +23,38 @@
 
 namespace {
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: the library must not link against libcuda.so.1
+// (it is loaded, and its symbols are checked, on machines without a driver -- the CPU half of the test-suite)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// 2-D tensor map of a row-major fp16 matrix [rows, ld], box [box_rows x 64 columns], 128-byte swizzle, zero fill
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int ld, int box_rows, const char* who) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) { nr_set_error("%s: cuTensorMapEncodeTiled is not available from this driver", who); return NR_ERR_CUDA; }
+  const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    nr_set_error("%s: cuTensorMapEncodeTiled failed (%d) for %p [%lld x %d]", who, (int)rc, base, (long long)rows, ld);
+    return NR_ERR_CUDA;
+  }
+  return NR_OK;
+}
+
 constexpr int kBM = 128, kKC = 64;
 #ifndef NR_G16_STAGES
 #define NR_G16_STAGES 6
@@ -575,20 +607,8 @@ extern "C" int nr_gemm16(const void* A, int32_t lda, const float* W, int32_t ldw
   NR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t n_tiles = nr_cdiv(M, kBM);
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  // tensor map of A: [M rows, lda columns] fp16 row-major, box = [128 rows x 64 columns], 128-byte swizzle, zero fill
-  CUtensorMap map_a;
-  {
-    const cuuint64_t gdim[2] = {(cuuint64_t)lda, (cuuint64_t)M};
-    const cuuint64_t gstride[1] = {(cuuint64_t)lda * 2};
-    const cuuint32_t box[2] = {kKC, kBM}, estr[2] = {1, 1};
-    const CUresult rc = cuTensorMapEncodeTiled(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(A), gdim, gstride, box, estr,
-                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) {
-      nr_set_error("nr_gemm16: cuTensorMapEncodeTiled failed (%d) for A %p [%lld x %d]", (int)rc, A, (long long)M, lda);
-      return NR_ERR_CUDA;
-    }
-  }
+  CUtensorMap map_a;      // A: [M rows, lda columns] fp16 row-major, box = [128 rows x 64 columns]
+  if (int rc = make_map(&map_a, A, M, lda, kBM, "nr_gemm16")) return rc;
 #define NR_G16_LAUNCH(MODE_, YH_)                                                                                         \
   do {                                                                                                                    \
     NR_CHECK_CUDA(cudaFuncSetAttribute(gemm16_kernel<MODE_, YH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -625,21 +645,8 @@ extern "C" int nr_gemm16_tn(const void* G, int32_t ldg, const void* X, int32_t l
   const size_t smem = 1024 + kTnStages * (kTnABytes + kTnBBytes) + 128;
   dim3 grid((unsigned)slices, n_mt, n_nt);
   CUtensorMap map_g, map_x;
-  {
-    const cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
-    const cuuint64_t gd[2] = {(cuuint64_t)ldg, (cuuint64_t)rows}, gs[1] = {(cuuint64_t)ldg * 2};
-    const cuuint64_t xd[2] = {(cuuint64_t)ldx, (cuuint64_t)rows}, xs[1] = {(cuuint64_t)ldx * 2};
-    const CUresult r1 = cuTensorMapEncodeTiled(&map_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(G), gd, gs, box, estr,
-                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    const CUresult r2 = cuTensorMapEncodeTiled(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(X), xd, xs, box, estr,
-                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
-      nr_set_error("nr_gemm16_tn: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
-      return NR_ERR_CUDA;
-    }
-  }
+  if (int rc = make_map(&map_g, G, rows, ldg, 64, "nr_gemm16_tn")) return rc;
+  if (int rc = make_map(&map_x, X, rows, ldx, 64, "nr_gemm16_tn")) return rc;
   NR_CHECK_CUDA(cudaFuncSetAttribute(gemm16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gemm16_tn_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(g, map_g, map_x);
   NR_CHECK_LAUNCH("gemm16_tn_kernel");

@@ -305,13 +305,78 @@ class _RadianceFn(torch.autograd.Function):
         return (None, None, g_normals, g_feat, None, None, *_unscale(grads, inv))
 
 
+class _WeightNormFn(torch.autograd.Function):
+    """(scales, g_0, v_0, g_1, v_1, ...) -> (W_0, W_1, ...), W_l = scale_l g_l v_l / ||v_l||_row: the weight normalisation
+    of every layer of a network in one launch, its backward in one more (csrc/weight_norm.cu) -- instead of three torch
+    kernels per layer forward and half a dozen backward."""
+
+    @staticmethod
+    def _table(entries, dev):
+        import struct
+        rows, words = 0, b""
+        for v, g, W, dW, dv, dg, scale in entries:
+            words += struct.pack("<6q4qdq", v.data_ptr(), g.data_ptr(), W.data_ptr(), 0 if dW is None else dW.data_ptr(),
+                                 0 if dv is None else dv.data_ptr(), 0 if dg is None else dg.data_ptr(), v.shape[0], v.shape[1],
+                                 W.stride(0), 0 if dW is None else dW.stride(0), float(scale), rows)
+            rows += v.shape[0]
+        return _lib.C.create_string_buffer(words, len(words)), rows          # host memory: the kernel takes the table by value
+
+    @staticmethod
+    def forward(ctx, scales, *gv):
+        gs, vs = gv[0::2], gv[1::2]
+        dev = vs[0].device
+        Ws = [torch.empty(v.shape[0], (v.shape[1] + 3) & ~3, dtype=torch.float32, device=dev) for v in vs]
+        ent = [(v.detach(), g.detach(), W, None, None, None, sc) for v, g, W, sc in zip(vs, gs, Ws, scales)]
+        tab, rows = _WeightNormFn._table(ent, dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.get_lib().nr_weight_norm(tab, len(ent), rows, 0, _lib.stream_ptr(dev)), "weight_norm")
+        ctx.save_for_backward(*gv)
+        ctx.scales = scales
+        return tuple(W[:, :v.shape[1]] for W, v in zip(Ws, vs))
+
+    @staticmethod
+    def backward(ctx, *dWs):
+        gv = ctx.saved_tensors
+        gs, vs = gv[0::2], gv[1::2]
+        dev = vs[0].device
+        ent, out = [], []
+        for g, v, dW, sc in zip(gs, vs, dWs, ctx.scales):
+            dW = torch.zeros_like(v) if dW is None else dW
+            if dW.stride(1) != 1 or dW.dtype != torch.float32:
+                dW = dW.float().contiguous()
+            dg, dv = torch.empty_like(g), torch.empty_like(v)
+            # W is only read by the forward kernel; the backward gets a dummy
+            ent.append((v, g, dv, dW, dv, dg, sc))
+            out += [dg, dv]
+        tab, rows = _WeightNormFn._table(ent, dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.get_lib().nr_weight_norm(tab, len(ent), rows, 1, _lib.stream_ptr(dev)), "weight_norm")
+        return (None, *out)
+
+
+def _fused_effective_weights(layers, scales):
+    """effective weights of weight-normed layers through one kernel (tensor tier); None if a layer is not weight-normed"""
+    if not all(hasattr(l, "weight_g") for l in layers) or not layers[0].weight_v.is_cuda:
+        return None
+    gv = []
+    for l in layers:
+        gv += [l.weight_g, l.weight_v]
+    return list(_WeightNormFn.apply(tuple(scales), *gv))
+
+
 def _surface_weights(surface):
     from .base import _effective_weight
+    layers = list(surface.surface_fc_layers)
+    scales = [1.0 / math.sqrt(2) if i in surface.skips else 1.0 for i in range(len(layers))]
+    Ws = _fused_effective_weights(layers, scales) if (_tc() and torch.is_grad_enabled()) else None
     wb = []
-    for i, layer in enumerate(surface.surface_fc_layers):
-        W = _effective_weight(layer)
-        if i in surface.skips:
-            W = W / math.sqrt(2)
+    for i, layer in enumerate(layers):
+        if Ws is not None:
+            W = Ws[i]
+        else:
+            W = _effective_weight(layer)
+            if i in surface.skips:
+                W = W / math.sqrt(2)
         wb += [W, layer.bias]
     return wb
 
@@ -355,9 +420,11 @@ def radiance_forward_autograd(rad, x, view_dirs, normals, geometry_feature):
     vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
     nf = normals.reshape(-1, 3).float()
     ff = geometry_feature.reshape(-1, geometry_feature.shape[-1]).float()
+    layers = list(rad.layers)
+    Ws = _fused_effective_weights(layers, [1.0] * len(layers)) if (_tc() and torch.is_grad_enabled()) else None
     wb = []
-    for layer in rad.layers:
-        wb += [_effective_weight(layer), layer.bias]
+    for i, layer in enumerate(layers):
+        wb += [Ws[i] if Ws is not None else _effective_weight(layer), layer.bias]
     if _tc() and _lib.get_precision() == "fp16" and _REVERSE_TRAINING and all(tuple(w.shape)[0] == 256 for w in wb[0:-2:2]) \
             and wb[0].shape[1] > 256:
         from . import autograd_rev

@@ -108,11 +108,6 @@ _SIGNATURES = {
     "nr_adam_step_dev": (C.c_int, [_P, _I32, _P, _F, _F, _F, _P, _P]),
     "nr_mlp_umma2_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _I64, _P, _P, _P, _I64, _P, _P]),
     "nr_mlp_umma_set_trace": (C.c_int, [_P]),
-    "nr_bench_ldtm": (C.c_int, [_I32, _I32, _I32, _P, _P, _P]),
-    "nr_probe_alu": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P]),
-    "nr_bench_umma": (C.c_int, [_I32, _I32, _I32, _I32, _P, _I32, _P, _P]),
-    "nr_selftest_umma2": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
-    "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
     "nr_gemm16": (C.c_int, [_P, _I32, _P, _I32, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _P]),
     "nr_gemm16_pack_w_bytes": (_SZ, [_I32, _I32]),
     "nr_gemm16_pack_w": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
@@ -130,6 +125,32 @@ _SIGNATURES = {
     "nr_unisurf_composite_bwd": (C.c_int, [_P] * 8 + [_I64, _I32, _I32] + [_P] * 9),
     "nr_neus_composite": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
+
+
+# self-tests and probes: include/neurecon_b200_devtools.h, lib/libneurecon_b200_devtools.so (not in the production library)
+_DEVTOOLS_SIGNATURES = {
+    "nr_bench_ldtm": (C.c_int, [_I32, _I32, _I32, _P, _P, _P]),
+    "nr_probe_alu": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P]),
+    "nr_bench_umma": (C.c_int, [_I32, _I32, _I32, _I32, _P, _I32, _P, _P]),
+    "nr_selftest_umma2": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
+    "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
+}
+_devtools = None
+
+
+def get_devtools():
+    """ctypes handle on the development-tools library (self-tests, micro-architecture probes)."""
+    global _devtools
+    if _devtools is None:
+        get_lib()                                   # builds everything if stale
+        from . import build as _build
+        lib = C.CDLL(_build.DEVTOOLS_LIB_PATH)
+        for name, (res, args) in _DEVTOOLS_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        lib.nr_last_error.restype, lib.nr_last_error.argtypes = C.c_int, [C.c_char_p, _SZ]
+        _devtools = lib
+    return _devtools
 
 
 def declared_symbols():

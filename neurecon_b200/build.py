@@ -20,6 +20,8 @@ LIB_PATH = os.path.join(LIB_DIR, "libneurecon_b200.so")
 # csrc/umma.cuh); loaded by tests/test_gpu_reliability.py and tools/soak_mlp.py, never by the package
 INJECT_LIB_PATH = os.path.join(LIB_DIR, "libneurecon_b200_inject.so")
 INJECT_SOURCES = ("api.cu", "mlp_rev.cu", "mlp_umma.cu")
+# self-tests and micro-architecture probes (csrc/devtools/): their own library, the production one carries only the path
+DEVTOOLS_LIB_PATH = os.path.join(LIB_DIR, "libneurecon_b200_devtools.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -34,11 +36,16 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def devtools_sources():
+    return sorted(glob.glob(os.path.join(CSRC, "devtools", "*.cu")))
+
+
 def _stale():
-    if not os.path.exists(LIB_PATH) or not os.path.exists(INJECT_LIB_PATH):
+    libs = (LIB_PATH, INJECT_LIB_PATH, DEVTOOLS_LIB_PATH)
+    if not all(os.path.exists(p) for p in libs):
         return True
-    t = min(os.path.getmtime(LIB_PATH), os.path.getmtime(INJECT_LIB_PATH))
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    t = min(os.path.getmtime(p) for p in libs)
+    deps = sources() + devtools_sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -74,6 +81,12 @@ def _build_locked(force, verbose):
             cmd = [nvcc, *NVCC_FLAGS, "-DNR_FAULT_INJECT", "-I", INCLUDE, "-c", src, "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
             inject_objs.append(obj)
+    dev_objs = [os.path.join(LIB_DIR, "api.o")]
+    for src in devtools_sources():
+        obj = os.path.join(LIB_DIR, "devtools_" + os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        dev_objs.append(obj)
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
@@ -86,7 +99,7 @@ def _build_locked(force, verbose):
         raise RuntimeError("neurecon_b200: nvcc build failed")
     # link to a temporary name and rename: a process that dlopen()s the library meanwhile sees the old or the new file,
     # never a half-written one
-    for path, members in ((LIB_PATH, objs), (INJECT_LIB_PATH, inject_objs)):
+    for path, members in ((LIB_PATH, objs), (INJECT_LIB_PATH, inject_objs), (DEVTOOLS_LIB_PATH, dev_objs)):
         tmp = "%s.%d.tmp" % (path, os.getpid())
         subprocess.check_call([nvcc, "-shared", "-o", tmp, *members, "-lcudart"])   # no -lcuda: see csrc/gemm16.cu
         os.replace(tmp, path)

@@ -1,6 +1,6 @@
 // Issue-rate probes for the epilogue's instruction mix (tools/probe_alu.py): per-SM throughput of MUFU.EX2,
 // MUFU.RCP, the fp32 -> 16-bit pack conversion and FFMA, measured with clock64 over a long unrolled loop.
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace {
 

@@ -1,8 +1,8 @@
 // Single-CTA tcgen05 self-test: D[128, N] = A[128, K] * B[K, N] with exactly the operand layouts,
 // descriptors, TMEM addressing and barrier protocol the fused MLP kernel uses.  Exercised by
 // tests/test_gpu_umma.py against a bf16-rounded CPU matmul.
-#include "common.cuh"
-#include "umma.cuh"
+#include "../common.cuh"
+#include "../umma.cuh"
 
 namespace {
 

@@ -15,7 +15,7 @@ def _run(K, N, variant=0, seed=0):
     img = umma_pack.pack_a_tiles(A.to(DEV))
     D = torch.full((128, N), float("nan"), device=DEV)
     Bd = B.to(DEV).contiguous()
-    lib = _lib.get_lib()
+    lib = _lib.get_devtools()
     _lib.check(lib.nr_selftest_umma(_lib.ptr(img), _lib.ptr(Bd), K, N, _lib.ptr(D), variant, _lib.stream_ptr()), "selftest")
     torch.cuda.synchronize()
     want = A.to(torch.bfloat16).double() @ B.to(torch.bfloat16).double()
@@ -38,7 +38,7 @@ def _run2(K, N, variant=0, seed=0):
     img = umma_pack.pack_a_tiles(A.to(DEV), dtype=torch.float16)     # k-chunk major, M-tile minor
     D = torch.full((256, N), float("nan"), device=DEV)
     Bd = B.to(DEV).contiguous()
-    lib = _lib.get_lib()
+    lib = _lib.get_devtools()
     _lib.check(lib.nr_selftest_umma2(_lib.ptr(img), _lib.ptr(Bd), K, N, _lib.ptr(D), variant, _lib.stream_ptr()), "selftest2")
     torch.cuda.synchronize()
     want = A.to(torch.float16).double() @ B.to(torch.float16).double()

@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 from neurecon_b200 import _lib  # noqa: E402
 
 dev = torch.device("cuda:0")
-lib = _lib.get_lib()
+lib = _lib.get_devtools()
 src = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
 for grid in (1, 148):
     out = torch.zeros(grid, 2, dtype=torch.int64, device=dev)

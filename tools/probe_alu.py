@@ -4,7 +4,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from neurecon_b200 import _lib
-dev = torch.device("cuda:0"); lib = _lib.get_lib()
+dev = torch.device("cuda:0"); lib = _lib.get_devtools()
 out = torch.zeros(4, device=dev); cyc = torch.zeros(148, dtype=torch.int64, device=dev)
 names = ["ex2.approx", "rcp.approx", "cvt.f16x2.f32", "fma.f32", "cvt.bf16x2.f32", "lg2.approx", "fma.f32x2 (4 instr per iteration; lanes = instr lanes x2)",
          "ex2.f16x2 (2 values per lane)", "tanh.f16x2 (2 values per lane)", "tanh.f32", "fma.f16x2 (2 values per lane)", "max.f16x2"]

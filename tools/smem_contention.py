@@ -5,7 +5,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from neurecon_b200 import _lib
-dev = torch.device("cuda:0"); lib = _lib.get_lib()
+dev = torch.device("cuda:0"); lib = _lib.get_devtools()
 src = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
 grid = 148
 out = torch.zeros(3 * grid, dtype=torch.int64, device=dev)

@@ -1,7 +1,7 @@
 import os, sys, torch
 sys.path.insert(0, "/root/repo")
 from neurecon_b200 import _lib
-dev = torch.device("cuda:0"); lib = _lib.get_lib()
+dev = torch.device("cuda:0"); lib = _lib.get_devtools()
 src = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
 out = torch.zeros(1, 2, dtype=torch.int64, device=dev)
 for N in (128, 32):

@@ -228,6 +228,10 @@ int nr_neus_composite(const float* sdf, const float* nablas, const float* radian
                       int32_t white_bkgd, float* rgb, float* depth, float* acc, float* normals,
                       float* cdf_out, float* alpha_out, float* weights_out, void* stream);
 
+/* sdf_to_w with a fixed slope s (neus.py:28-70, the weights of the 'direct_use' / 'direct_more' up-samplers, :216-243):
+ * sdf [R,M] -> w [R,M-1] = alpha_i * prod_{j<i} (1 - alpha_j + 1e-10), alpha from sigmoid(sdf * s). */
+int nr_neus_sdf_to_w(const float* sdf, float s, int64_t R, int32_t M, float* w, void* stream);
+
 /* NeuS with the NeRF++ background (N_outside > 0, neus.py:303-343).
  * nr_neus_outside_points: d_vals [R, M1+n_out] = cat(d_mid, far / flip(linspace(0,1,n_out+2)[1:-1]))
  * (u [R,n_out]: stratified jitter uniforms or NULL) and the inverted-sphere inputs x_out [R, M1+n_out, 4]

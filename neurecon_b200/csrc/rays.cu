@@ -639,6 +639,37 @@ __global__ void neus_composite_kernel(const float* __restrict__ sdf, const float
   }
 }
 
+// sdf_to_w with a fixed slope (neus.py:28-70 as used by the 'direct_use' / 'direct_more' up-samplers, :216-243):
+// cdf = sigmoid(sdf s), alpha_i = max((cdf_i - cdf_{i+1}) / (cdf_i + 1e-10), 0), w_i = alpha_i prod_{j<i} (1 - alpha_j + 1e-10).
+// One warp per ray, 32 intervals per round, the running product carried between rounds.
+__global__ void neus_sdf_to_w_kernel(const float* __restrict__ sdf, float s, int64_t R, int M, float* __restrict__ w) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (ray >= R) return;
+  const float* row = sdf + ray * (int64_t)M;
+  float* out = w + ray * (int64_t)(M - 1);
+  float carry = 1.0f;
+  for (int base = 0; base < M - 1; base += 32) {
+    const int i = base + lane;
+    float alpha = 0.0f, q = 1.0f;
+    if (i < M - 1) {
+      const float c0 = nr_sigmoid(__fmul_rn(row[i], s)), c1 = nr_sigmoid(__fmul_rn(row[i + 1], s));
+      alpha = fmaxf(__fdiv_rn(__fsub_rn(c0, c1), __fadd_rn(c0, 1e-10f)), 0.0f);
+      q = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+    }
+    float incl = q;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl *= t;
+    }
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    if (i < M - 1) out[i] = alpha * (carry * excl);
+    carry *= __shfl_sync(kFull, incl, 31);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // NeuS + NeRF++ background (neus.py:303-343).
 // ---------------------------------------------------------------------------------------------
@@ -899,6 +930,15 @@ extern "C" int nr_neus_composite(const float* sdf, const float* nablas, const fl
       sdf, nablas, radiance, d_mid, s_dev, R, M, white_bkgd, rgb, depth, acc, normals, cdf_out, alpha_out,
       weights_out);
   NR_CHECK_LAUNCH("neus_composite_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_neus_sdf_to_w(const float* sdf, float s, int64_t R, int32_t M, float* w, void* stream) {
+  NR_CHECK_ARG(R >= 0 && M >= 2, "nr_neus_sdf_to_w: bad sizes");
+  if (R == 0) return NR_OK;
+  NR_CHECK_ARG(sdf && w, "nr_neus_sdf_to_w: null pointer");
+  neus_sdf_to_w_kernel<<<(unsigned)nr_cdiv(R, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(sdf, s, R, M, w);
+  NR_CHECK_LAUNCH("neus_sdf_to_w_kernel");
   return NR_OK;
 }
 

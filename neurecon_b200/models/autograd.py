@@ -412,25 +412,30 @@ def sdf_forward_with_nablas_autograd(surface, x):
 def radiance_forward_autograd(rad, x, view_dirs, normals, geometry_feature):
     """RadianceNet.forward under autograd (models/base.py:372-391)."""
     from .base import _effective_weight
-    if rad.skips or not rad.use_view_dirs:
-        raise NotImplementedError("neurecon_b200 RadianceNet supports skips=[] with use_view_dirs=True")
+    if rad.skips:
+        raise NotImplementedError("neurecon_b200 RadianceNet supports skips=[]")
     _lib.require_cuda(x, view_dirs, normals, geometry_feature)
     shape = x.shape[:-1]
     xf = _lib.f32c(x.detach().reshape(-1, 3))
-    vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
-    nf = normals.reshape(-1, 3).float()
+    if rad.use_view_dirs:
+        vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
+        nf = normals.reshape(-1, 3).float()
+    else:       # base.py:383-384: neither enters the network; layer 0's weight has zero columns for them (base.py here)
+        vf, nf = xf, xf
     ff = geometry_feature.reshape(-1, geometry_feature.shape[-1]).float()
     layers = list(rad.layers)
     Ws = _fused_effective_weights(layers, [1.0] * len(layers)) if (_tc() and torch.is_grad_enabled()) else None
     wb = []
     for i, layer in enumerate(layers):
         wb += [Ws[i] if Ws is not None else _effective_weight(layer), layer.bias]
+    wb[0] = rad._layer0_weight(wb[0])
+    mv = rad._multires_view_eff
     if _tc() and _lib.get_precision() == "fp16" and _REVERSE_TRAINING and all(tuple(w.shape)[0] == 256 for w in wb[0:-2:2]) \
             and wb[0].shape[1] > 256:
         from . import autograd_rev
-        rgb = autograd_rev.RadianceRevFn.apply(xf, vf, nf, ff, rad.embed_multires, rad.embed_multires_view, *wb)
+        rgb = autograd_rev.RadianceRevFn.apply(xf, vf, nf, ff, rad.embed_multires, mv, *wb)
         return rgb.reshape(*shape, 3)
-    rgb = _RadianceFn.apply(xf, vf, nf, ff, rad.embed_multires, rad.embed_multires_view, *wb)
+    rgb = _RadianceFn.apply(xf, vf, nf, ff, rad.embed_multires, mv, *wb)
     return rgb.reshape(*shape, 3)
 
 

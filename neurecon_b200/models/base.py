@@ -246,12 +246,12 @@ class ImplicitSurface(nn.Module):
                     Wl[i] = Wl[i] / math.sqrt(2)
                 kw = {}
                 if radiance_net is not None:
-                    if radiance_net.skips or not radiance_net.use_view_dirs:
-                        raise NotImplementedError("bf16 tier: RadianceNet needs skips=[] and use_view_dirs=True")
-                    kw = dict(rad_W=[_effective_weight(l).detach().float() for l in radiance_net.layers],
+                    if radiance_net.skips:
+                        raise NotImplementedError("tensor tier: RadianceNet needs skips=[]")
+                    kw = dict(rad_W=[W.detach().float() for W in radiance_net._effective_weights()],
                               rad_b=[l.bias.detach().float() for l in radiance_net.layers],
                               rad_multires=radiance_net.embed_multires,
-                              rad_multires_view=radiance_net.embed_multires_view)
+                              rad_multires_view=radiance_net._multires_view_eff)
                 return umma_pack.UmmaNet(Wl, bl, self.embed_multires, self.skips[0] if self.skips else -1,
                                          operand=_lib.get_precision(), **kw)
         return _cached(self, slot, key, build)
@@ -273,7 +273,9 @@ class ImplicitSurface(nn.Module):
         nabla = torch.empty(n, 3, **f) if (mode != "sdf" and (want_nablas or mode == "split")) else None
         feat = torch.empty(n, net.feat_dim, **f) if (want_feat and not with_rad) else None
         rgb = torch.empty(n, 3, **f) if with_rad else None
-        vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3)) if with_rad else None
+        vf = None
+        if with_rad:      # view_dirs None (use_view_dirs=False): any finite value, it meets zero weights
+            vf = xf if view_dirs is None else _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
 
         pair = _PAIR_KERNEL and net.pair_ok()
 
@@ -429,16 +431,34 @@ class RadianceNet(nn.Module):
         self.layers = nn.ModuleList(layers)
         self._cache = {}
 
+    # ``use_view_dirs=False`` (base.py:335-336,383-384: layer 0 sees cat([PE(x), feature]) only) runs on the same kernels:
+    # layer 0's weight gets zero columns where the kernels place [view (un-embedded) | normals], so whatever is passed
+    # for those six inputs is multiplied by zero.
+    @property
+    def _multires_view_eff(self):
+        return self.embed_multires_view if self.use_view_dirs else -1
+
+    def _layer0_weight(self, W0):
+        """Layer-0 weight in the kernels' input order [PE(x) | PE(view) | normals | feature] (differentiable)."""
+        if self.use_view_dirs:
+            return W0
+        px = W0.shape[1] - self.W_geo_feat
+        return torch.cat([W0[:, :px], W0.new_zeros(W0.shape[0], 6), W0[:, px:]], dim=1)
+
+    def _effective_weights(self):
+        Wl = [_effective_weight(l) for l in self.layers]
+        Wl[0] = self._layer0_weight(Wl[0])
+        return Wl
+
     def _descriptor(self):
-        if self.skips or not self.use_view_dirs:
-            raise NotImplementedError("neurecon_b200 RadianceNet supports skips=[] with use_view_dirs=True "
-                                      "(every shipped reference config)")
+        if self.skips:
+            raise NotImplementedError("neurecon_b200 RadianceNet supports skips=[] (every shipped reference config)")
         def build():
-            Wl = [_effective_weight(l) for l in self.layers]
+            Wl = self._effective_weights()
             Ws, bs = _pack_layers(Wl, [l.bias for l in self.layers])
             d = _lib.RadianceNetDesc()
             d.n_layers = self.D + 1
-            d.multires, d.multires_view, d.feat_dim = self.embed_multires, self.embed_multires_view, self.W_geo_feat
+            d.multires, d.multires_view, d.feat_dim = self.embed_multires, self._multires_view_eff, self.W_geo_feat
             for i in range(self.D + 1):
                 out_d, in_d = Wl[i].shape
                 d.in_dim[i], d.out_dim[i] = in_d, out_d
@@ -451,7 +471,8 @@ class RadianceNet(nn.Module):
     def forward(self, x, view_dirs, normals, geometry_feature):
         """base.py:372-391."""
         needs_grad = torch.is_grad_enabled() and (
-            normals.requires_grad or geometry_feature.requires_grad or any(p.requires_grad for p in self.parameters()))
+            (normals is not None and normals.requires_grad) or geometry_feature.requires_grad
+            or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
             from .autograd import radiance_forward_autograd
             return radiance_forward_autograd(self, x, view_dirs, normals, geometry_feature)
@@ -459,8 +480,9 @@ class RadianceNet(nn.Module):
         lib = _lib.get_lib()
         shape = x.shape[:-1]
         xf = _lib.f32c(x.detach().reshape(-1, 3))
-        vf = _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
-        nf = _lib.f32c(normals.detach().reshape(-1, 3))
+        # use_view_dirs=False: the reference ignores view_dirs and normals (base.py:383-384); they meet zero weights here
+        vf = xf if (view_dirs is None or not self.use_view_dirs) else _lib.f32c(view_dirs.detach().expand(*shape, 3).reshape(-1, 3))
+        nf = xf if (normals is None or not self.use_view_dirs) else _lib.f32c(normals.detach().reshape(-1, 3))
         ff = _lib.f32c(geometry_feature.detach().reshape(-1, self.W_geo_feat))
         n, dev = xf.shape[0], xf.device
         desc = self._descriptor()

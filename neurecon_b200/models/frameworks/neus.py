@@ -182,6 +182,42 @@ def _upsample(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_b
     return out
 
 
+def _upsample_direct(model, rays_o, rays_d_raw, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
+                     perturb, fixed_s_recp, algo, N_nograd_samples):
+    """neus.py:216-243, the two NeRF-like up-samplers: the visibility weights of a FIXED slope 1 / fixed_s_recp on the
+    coarse samples ('direct_use') or on N_nograd_samples extra samples ('direct_more'; no gradients there, hence the
+    name), ONE inverse-CDF draw of N_importance depths, merged with the coarse ones.  Returns the sorted depths [R, M]."""
+    lib = _lib.get_lib()
+    R, dev = rays_o.shape[0], rays_o.device
+    f = dict(dtype=torch.float32, device=dev)
+    st = _lib.stream_ptr(dev)
+    nan = float("nan")
+
+    def setup(n):
+        dirs, near, far = torch.empty(R, 3, **f), torch.empty(R, **f), torch.empty(R, **f)
+        d, pts = torch.empty(R, n, **f), torch.empty(R, n, 3, **f)
+        _lib.check(lib.nr_neus_ray_setup(
+            _lib.ptr(rays_o), _lib.ptr(rays_d_raw), R, float(obj_bounding_radius),
+            nan if near_bypass is None else float(near_bypass), nan if far_bypass is None else float(far_bypass),
+            n, _lib.ptr(dirs), _lib.ptr(near), _lib.ptr(far), _lib.ptr(d), _lib.ptr(pts), st), "neus_ray_setup")
+        return d, pts
+
+    from ...utils import rend_util
+    with torch.no_grad():
+        d_coarse, pts_coarse = setup(N_samples)
+        if algo == 'direct_use':
+            d_w, pts_w = d_coarse, pts_coarse
+        else:
+            d_w, pts_w = setup(int(N_nograd_samples))
+        sdf_w = _lib.f32c(model.implicit_surface.forward(pts_w))
+        n_w = d_w.shape[1]
+        w = torch.empty(R, n_w - 1, **f)
+        _lib.check(lib.nr_neus_sdf_to_w(_lib.ptr(sdf_w), 1.0 / float(fixed_s_recp), R, n_w, _lib.ptr(w), st), "neus_sdf_to_w")
+        d_fine = rend_util.sample_pdf(d_w, w, N_importance, det=not perturb)
+        d_all, _ = torch.sort(torch.cat([d_coarse, d_fine], dim=-1), dim=-1)
+    return d_all.contiguous()
+
+
 def volume_render(
         rays_o,
         rays_d,
@@ -223,13 +259,14 @@ def volume_render(
         **dummy_kwargs):
     """neus.py:118-397.  rays_o / rays_d: [(B,) N_rays, 3] (rays_d not normalised).
     Returns (rgb, depth_volume, ret) with the reference's ``ret`` keys and shapes."""
-    if upsample_algo != 'official_solution':
-        raise NotImplementedError("upsample_algo=%r: only 'official_solution' (every shipped config) is built"
-                                  % upsample_algo)
+    if upsample_algo not in ('official_solution', 'direct_use', 'direct_more'):
+        raise NotImplementedError("upsample_algo=%r" % (upsample_algo,))      # neus.py:281
     if N_outside > 0 and not hasattr(model, "nerf_outside"):
         raise ValueError("N_outside > 0 needs a model built with use_outside_nerf=True")
-    if not use_view_dirs:
-        raise NotImplementedError("use_view_dirs=False is not supported")
+    if bool(use_view_dirs) != bool(model.radiance_net.use_view_dirs):
+        # the reference passes view_dirs=None for use_view_dirs=False (neus.py:190-193), which only a RadianceNet built
+        # with use_view_dirs=False accepts (base.py:379-384)
+        raise ValueError("use_view_dirs=%r needs a radiance net built with use_view_dirs=%r" % (use_view_dirs, use_view_dirs))
     _lib.require_cuda(rays_o, rays_d)
     from ..composite import NeusComposite
     # training (neus.py:440: Trainer.forward renders under autograd): the up-sampler stays no_grad as in the reference
@@ -246,7 +283,8 @@ def volume_render(
     o_flat = _lib.f32c(rays_o.reshape(-1, 3))
     d_flat = _lib.f32c(rays_d.reshape(-1, 3))
     n_total = o_flat.shape[0]
-    M = N_samples + (N_importance // N_upsample_iters) * N_upsample_iters
+    direct = upsample_algo != 'official_solution'
+    M = N_samples + (N_importance if direct else (N_importance // N_upsample_iters) * N_upsample_iters)
     s = model.forward_s() if train else model.forward_s().detach().float().contiguous()
 
     outs = []
@@ -257,15 +295,18 @@ def volume_render(
         for i0 in range(0, n_total, step):
             ro, rd = o_flat[i0:i0 + step], d_flat[i0:i0 + step]
             R = ro.shape[0]
-            if samples_bypass is not None:
+            if samples_bypass is not None or direct:
+                d_given = samples_bypass["d_all"][i0:i0 + step] if samples_bypass is not None else _upsample_direct(
+                    model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance, perturb,
+                    fixed_s_recp, upsample_algo, N_nograd_samples)
                 dirs, d_all, pts, d_mid, pts_mid, far = _forced_samples(
-                    ro, rd, samples_bypass["d_all"][i0:i0 + step], obj_bounding_radius, near_bypass, far_bypass)
+                    ro, rd, d_given, obj_bounding_radius, near_bypass, far_bypass)
             elif train:
                 with torch.no_grad():
                     dirs, d_all, pts, d_mid, pts_mid, far = _upsample(
                         model, ro, rd, obj_bounding_radius, near_bypass, far_bypass, N_samples, N_importance,
                         N_upsample_iters, perturb, return_far=True)
-            if train or samples_bypass is not None:
+            if train or samples_bypass is not None or direct:
                 # neus.py:294,298: forward_with_nablas at the samples and (inside forward_radiance) at the mid points -- ONE
                 # network call on both point sets, so that the per-layer training GEMMs run once over 255 points per ray
                 n1 = R * M

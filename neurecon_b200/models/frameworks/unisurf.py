@@ -90,8 +90,10 @@ def volume_render(
     is treated as one batch."""
     if method != 'secant':
         raise NotImplementedError("only method='secant' (every shipped config) is built")
-    if not use_view_dirs:
-        raise NotImplementedError("use_view_dirs=False is not supported")
+    if bool(use_view_dirs) != bool(model.radiance_net.use_view_dirs):
+        # the reference passes view_dirs=None for use_view_dirs=False, which only a RadianceNet built with
+        # use_view_dirs=False accepts (base.py:379-384); here such a net ignores whatever views it is handed
+        raise ValueError("use_view_dirs=%r needs a radiance net built with use_view_dirs=%r" % (use_view_dirs, use_view_dirs))
     _lib.require_cuda(rays_o, rays_d)
     # training (unisurf.py:307: Trainer.forward renders under autograd): root finding and sampling stay no_grad as in the
     # reference (ray_casting.py:35 is @torch.no_grad, the samples are detached), the network query goes through

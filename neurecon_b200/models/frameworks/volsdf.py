@@ -192,8 +192,10 @@ def volume_render(
         samples_bypass=None,
         **dummy_kwargs):
     """volsdf.py:334-551.  rays_o / rays_d: [(B,) N_rays, 3].  Returns (rgb, depth_volume, ret)."""
-    if not use_view_dirs:
-        raise NotImplementedError("use_view_dirs=False is not supported")
+    if bool(use_view_dirs) != bool(model.radiance_net.use_view_dirs):
+        # the reference passes view_dirs=None for use_view_dirs=False, which only a RadianceNet built with
+        # use_view_dirs=False accepts (base.py:379-384); here such a net ignores whatever views it is handed
+        raise ValueError("use_view_dirs=%r needs a radiance net built with use_view_dirs=%r" % (use_view_dirs, use_view_dirs))
     _lib.require_cuda(rays_o, rays_d)
     # training (volsdf.py:578: Trainer.forward renders under autograd): the error-bounded sampler stays no_grad as in the
     # reference (volsdf.py:77 fine_sample is @torch.no_grad via its callers, the depths are detached), the network query

@@ -90,8 +90,10 @@ def surface_render(rays_o, rays_d, model, calc_normal=True, rayschunk=8192, netc
     from collections import OrderedDict
     import torch.nn.functional as F
     _lib.require_cuda(rays_o, rays_d)
-    if not use_view_dirs:
-        raise NotImplementedError("use_view_dirs=False is not supported")
+    if bool(use_view_dirs) != bool(model.radiance_net.use_view_dirs):
+        # the reference passes view_dirs=None for use_view_dirs=False, which only a RadianceNet built with
+        # use_view_dirs=False accepts (base.py:379-384); here such a net ignores whatever views it is handed
+        raise ValueError("use_view_dirs=%r needs a radiance net built with use_view_dirs=%r" % (use_view_dirs, use_view_dirs))
     with torch.no_grad():
         B = rays_d.shape[0] if batched else None
         shape = [B, -1, 3] if batched else [-1, 3]

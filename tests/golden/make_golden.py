@@ -159,8 +159,42 @@ def golden_surface_render(ref):
     npz("surface_render_r48.npz", seed=9, n_rays=R, **out)
 
 
+def golden_neus_variants(ref):
+    """The reference behaviours outside the shipped configs: the two NeRF-like up-samplers (neus.py:216-243) and a
+    radiance net without view directions (base.py:335-336,383-384; volume_render(use_view_dirs=False), neus.py:190-193)."""
+    R = 32
+    o, d = synthetic.make_rays(R, shell_radius=2.5, jitter=0.1, seed=7)
+    keep = ["rgb", "depth_volume", "mask_volume", "normals_volume", "implicit_surface", "radiance", "visibility_weights", "d_final"]
+    out = {}
+    torch.manual_seed(0)
+    m = ref.neus.NeuS(**synthetic.NEUS_MODEL_KWARGS)
+    synthetic.reseed_parameters(m, seed=1)
+    for algo in ("direct_use", "direct_more"):
+        with torch.no_grad():
+            _, _, ret = ref.neus.volume_render(o, d, m, calc_normal=True, detailed_output=True, perturb=False,
+                                               upsample_algo=algo, N_nograd_samples=256)
+        out.update({"%s__%s" % (algo, k): ret[k] for k in keep})
+    kw = dict(synthetic.NEUS_MODEL_KWARGS, radiance_cfg=dict(synthetic.NEUS_MODEL_KWARGS["radiance_cfg"], use_view_dirs=False))
+    torch.manual_seed(0)
+    mv = ref.neus.NeuS(**kw)
+    synthetic.reseed_parameters(mv, seed=1)
+    # (volume_render(use_view_dirs=False) itself crashes in the reference: batchify_query flattens the None it passes as
+    # view_dirs, train_util.py:27.  What works there: the network's forward and surface_render, ray_casting.py:217-230.)
+    x = synthetic.make_points(128, extent=1.0, seed=2)
+    with torch.no_grad():
+        sdf, nab, feat = mv.implicit_surface.forward_with_nablas(x)
+        out["noview__net_radiance"] = mv.radiance_net.forward(x, None, nab, feat)
+        col, dep, ex = ref.ray_casting.surface_render(o[None], d[None], mv, calc_normal=True, batched=True, use_view_dirs=False,
+                                                      ray_casting_algo="sphere_tracing", ray_casting_cfgs=dict(near=0.0, far=5.0, N_iters=20))
+        out.update(noview__st_color=col[0], noview__st_depth=dep[0], noview__st_mask=ex["mask_surface"][0])
+    npz("neus_variants_r32.npz", seed=7, n_rays=R, **out)
+
+
 if __name__ == "__main__":
     ref = ref_loader.load()
+    if "variants" in sys.argv[1:]:
+        golden_neus_variants(ref)
+        raise SystemExit(0)
     if "surface" in sys.argv[1:]:
         golden_surface_render(ref)
         raise SystemExit(0)
@@ -169,3 +203,4 @@ if __name__ == "__main__":
     golden_volsdf(ref)
     golden_unisurf(ref)
     golden_surface_render(ref)
+    golden_neus_variants(ref)

@@ -549,6 +549,17 @@ int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* image, size_t
                         size_t bias_floats, const float* x, int64_t n, float* sdf, float* nabla, float* feat,
                         int64_t feat_ld, void* feat_img, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same program on SPLIT-PRECISION operands (precision tier 'fp16x2': <= 1e-4 against the reference's fp32 on the tensor
+ * pipe).  Every weight chunk of the image comes as a (hi, lo) fp16 pair (chunk_begin counts 16 KB chunks of that
+ * interleaved image, umma_pack.pack_a_tiles_split), tile slots hold 64 points whose activations / gradients live as
+ * [hi | lo] column blocks of the operand buffer; W h ~= W_hi h_hi + W_hi h_lo + W_lo h_hi as one N = 128 and one N = 64
+ * MMA per k-step; softplus' as 16-bit codes.  A program may also END at EPI_SDF_OUT (sdf [+ feature] only, nabla and
+ * workspace may then be NULL).  feat_img as above (the fp16 `hi` parts of the last hidden activations). */
+size_t nr_mlp_split_reverse_workspace(const nr_umma_program_t* prog, int64_t n);
+int nr_mlp_split_reverse(const nr_umma_program_t* prog, const void* image, size_t image_bytes, const float* bias,
+                         size_t bias_floats, const float* x, int64_t n, float* sdf, float* nabla, float* feat,
+                         int64_t feat_ld, void* feat_img, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The same network on CTA pairs (tcgen05.mma.cta_group::2, 2-CTA clusters): programs made of EPI_HIDDEN,
  * EPI_SDF_OUT and EPI_FEAT (to_rad = 0) steps whose weight chunks all come as M-tile pairs (n_mt = 2; the sdf row
  * replicated into both M-tiles).  Halves the shared-memory traffic per SM of nr_mlp_umma_forward; same outputs. */

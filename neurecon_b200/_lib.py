@@ -109,6 +109,8 @@ _SIGNATURES = {
     "nr_adam_step_dev": (C.c_int, [_P, _I32, _P, _F, _F, _F, _P, _P]),
     "nr_mlp_umma2_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _I64, _P, _P, _P, _I64, _P, _P]),
     "nr_mlp_umma_set_trace": (C.c_int, [_P]),
+    "nr_mlp_split_reverse_workspace": (_SZ, [C.POINTER(UmmaProgram), _I64]),
+    "nr_mlp_split_reverse": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _I64, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
     "nr_gemm16": (C.c_int, [_P, _I32, _P, _I32, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _P]),
     "nr_gemm16_pack_w_bytes": (_SZ, [_I32, _I32]),
     "nr_gemm16_pack_w": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
@@ -246,8 +248,8 @@ def set_precision(p):
     """'fp32' (SIMT tier, <=1e-4 vs the reference), or the tcgen05 tier with 'fp16' or 'bf16'
     operands (fp32 accumulation; same tensor rate -- fp16 carries 3 more mantissa bits)."""
     global _precision
-    if p not in ("fp32", "bf16", "fp16"):
-        raise ValueError("precision must be 'fp32', 'fp16' or 'bf16'")
+    if p not in ("fp32", "bf16", "fp16", "fp16x2"):
+        raise ValueError("precision must be 'fp32', 'fp16x2', 'fp16' or 'bf16'")
     _precision = p
 
 
@@ -256,5 +258,17 @@ def get_precision():
 
 
 def tensor_tier():
-    """True when the MLPs run on the fused tcgen05 kernel."""
-    return _precision in ("fp16", "bf16")
+    """True when the MLPs run on the fused tcgen05 kernels."""
+    return _precision in ("fp16", "bf16", "fp16x2")
+
+
+def split_tier():
+    """'fp16x2': the SDF net on split-precision operands (hi + lo fp16 pairs, csrc/mlp_rev_split.cu) -- the <= 1e-4 tier on
+    the tensor pipe.  The radiance and NeRF++ nets, which have no softplus(beta=100) to amplify operand rounding, stay on
+    plain fp16 operands; training takes the fp32 path."""
+    return _precision == "fp16x2"
+
+
+def operand():
+    """16-bit operand type of the tensor tier's plain kernels"""
+    return "bf16" if _precision == "bf16" else "fp16"

@@ -59,7 +59,7 @@ _REVERSE_TRAINING = os.environ.get("NEURECON_B200_TRAIN", "reverse") != "forward
 
 def _tc():
     """Training GEMMs on the tensor cores (csrc/gemm_tc.cu) in the fp16 / bf16 tiers, fp32 SIMT in the fp32 tier."""
-    return _lib.tensor_tier()
+    return _lib.tensor_tier() and not _lib.split_tier()     # 'fp16x2' trains on the fp32 path (<= 1e-4 is its contract)
 
 
 def _gemm(A, K, W, bias, N, mode, S=None, aux=None, m_val=0, grad=False, out=None):

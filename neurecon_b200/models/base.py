@@ -253,8 +253,27 @@ class ImplicitSurface(nn.Module):
                               rad_multires=radiance_net.embed_multires,
                               rad_multires_view=radiance_net._multires_view_eff)
                 return umma_pack.UmmaNet(Wl, bl, self.embed_multires, self.skips[0] if self.skips else -1,
-                                         operand=_lib.get_precision(), **kw)
+                                         operand=_lib.operand(), **kw)
         return _cached(self, slot, key, build)
+
+    def _umma_split_net(self):
+        """(hi, lo) fp16 weight image of the SDF net for the split-precision kernel (precision 'fp16x2')."""
+        self._check_supported()
+        from .. import umma_pack
+
+        def build():
+            with torch.no_grad():
+                Wl = [_effective_weight(l).detach().float() for l in self.surface_fc_layers]
+                bl = [l.bias.detach().float() for l in self.surface_fc_layers]
+                for i in self.skips:
+                    Wl[i] = Wl[i] / math.sqrt(2)
+                net = umma_pack.UmmaNet(Wl, bl, self.embed_multires, self.skips[0] if self.skips else -1, operand="fp16",
+                                        split=True)
+            if not net.rev_ok(want_feat=True):
+                raise NotImplementedError("precision 'fp16x2' needs an embedding of at most 40 rows (embed_multires <= 6) and "
+                                          "at most 11 hidden layers; use set_precision('fp32') for this network")
+            return net
+        return _cached(self, "umma_split", _param_key(self), build)
 
     def _run_umma(self, x, mode, want_feat=False, radiance_net=None, view_dirs=None, want_sdf=True,
                   want_nablas=True, normal_scale=None):
@@ -302,6 +321,35 @@ class ImplicitSurface(nn.Module):
                 C.byref(prog), _lib.ptr(net.image), net.image.numel() * 2, _lib.ptr(net.bias), net.bias.numel(),
                 _lib.ptr(xf[i0:i0 + m]), m, _lib.ptr(sl(sdf_o)), _lib.ptr(sl(nabla_o)), _lib.ptr(sl(feat_o)),
                 net.feat_dim, _lib.ptr(img), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "mlp_umma_reverse")
+
+        def launch_split(snet, prog, i0, m, sdf_o, nabla_o, feat_o, img):
+            sl = lambda t: None if t is None else t[i0:i0 + m]
+            need = lib.nr_mlp_split_reverse_workspace(C.byref(prog), m)
+            ws = _lib.workspace(need, dev, slot=2)
+            _lib.check(lib.nr_mlp_split_reverse(
+                C.byref(prog), _lib.ptr(snet.image), snet.image.numel() * 2, _lib.ptr(snet.bias), snet.bias.numel(),
+                _lib.ptr(xf[i0:i0 + m]), m, _lib.ptr(sl(sdf_o)), _lib.ptr(sl(nabla_o)), _lib.ptr(sl(feat_o)),
+                snet.feat_dim, _lib.ptr(img), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "mlp_split_reverse")
+
+        if _lib.split_tier():
+            # 'fp16x2': the SDF net (where softplus(beta=100) amplifies operand rounding) on split-precision operands,
+            # csrc/mlp_rev_split.cu; the radiance pass on plain fp16 operands, fed by the same operand image
+            snet = self._umma_split_net()
+            with torch.cuda.device(dev):
+                if with_rad:
+                    p_geo, p_rad = snet.program("rev_img"), net.program("radiance")
+                    step = _SPLIT_POINTS
+                    img = _lib.workspace((min(n, step) + 127) // 128 * 65536, dev, slot=1)
+                    for i0 in range(0, n, step):
+                        m = min(step, n - i0)
+                        launch_split(snet, p_geo, i0, m, sdf, nabla, None, img)
+                        launch(p_rad, i0, m, None, nabla, None, rgb, img)
+                elif mode == "sdf":
+                    launch_split(snet, snet.program("rev_sdf", want_feat=want_feat), 0, n, sdf, None, feat, None)
+                else:
+                    launch_split(snet, snet.program("rev", want_feat=want_feat), 0, n, sdf, nabla, feat, None)
+            rs = lambda t, *tail: None if t is None else t.reshape(*shape, *tail)
+            return rs(sdf), rs(nabla if want_nablas else None, 3), rs(feat, net.feat_dim), rs(rgb, 3)
 
         # bf16 operands keep the tangent tiles: the backward sweep rounds every layer's gradient to 8 bits of mantissa,
         # which lands on the tier's 1e-2 bar (1.06e-2 measured), the forward-mode tangents stay under it

@@ -32,8 +32,8 @@ def _descriptor(module):
 
 def _umma_net(module):
     from ..umma_pack import UmmaNerfNet
-    return _cached(module, "umma", (_param_key(module), _lib.get_precision()),
-                   lambda: UmmaNerfNet(module, operand=_lib.get_precision()))
+    return _cached(module, "umma", (_param_key(module), _lib.operand()),
+                   lambda: UmmaNerfNet(module, operand=_lib.operand()))
 
 
 def nerf_forward(module, input_pts, input_views):

@@ -47,6 +47,18 @@ def pack_a_tiles(W, n_mtiles=None, k_pad=None, dtype=torch.bfloat16):
     return out.contiguous()
 
 
+def pack_a_tiles_split(W, n_mtiles=None, k_pad=None):
+    """Split-precision image (csrc/mlp_rev_split.cu): W = hi + 2^-12 lo with hi = fp16(W), lo = fp16((W - hi) 2^12) (scaled so
+    that it is a normal fp16 number); the A tiles of both parts interleaved (hi, lo) per (k-chunk, M-tile):
+    [2 * n_kchunks * n_mtiles, 8192] int16."""
+    Wf = W.float()
+    hi = Wf.to(torch.float16)
+    lo = ((Wf - hi.float()) * 4096.0).to(torch.float16)
+    th = pack_a_tiles(hi, n_mtiles=n_mtiles, k_pad=k_pad, dtype=torch.float16)
+    tl = pack_a_tiles(lo, n_mtiles=n_mtiles, k_pad=k_pad, dtype=torch.float16)
+    return torch.stack([th, tl], dim=1).reshape(-1, th.shape[1]).contiguous()
+
+
 # --------------------------------------------------------------------------------------------
 # Programs for the fused tcgen05 MLP kernel (csrc/mlp_umma.cu, include/neurecon_b200.h)
 # --------------------------------------------------------------------------------------------
@@ -62,9 +74,12 @@ class UmmaNet:
     """bf16 weight image + bias table + step templates for one (surface[, radiance]) pair."""
 
     def __init__(self, surface_W, surface_b, multires, skip_layer, rad_W=None, rad_b=None, rad_multires=-1,
-                 rad_multires_view=-1, operand="fp16"):
+                 rad_multires_view=-1, operand="fp16", split=False):
         dev = surface_W[0].device
         self.operand = operand
+        # split: every weight chunk as a (hi, lo) fp16 pair for csrc/mlp_rev_split.cu (reverse-mode programs only)
+        self.split = bool(split)
+        assert not (split and (rad_W is not None or operand != "fp16")), "split images hold the SDF net only, fp16 parts"
         op_dtype = torch.float16 if operand == "fp16" else torch.bfloat16
         self.multires = multires
         self.rad_multires, self.rad_multires_view = rad_multires, rad_multires_view
@@ -73,8 +88,12 @@ class UmmaNet:
 
         def add(W, b, k_steps, n_mt):
             assert k_steps % 4 == 0
-            img = pack_a_tiles(W, n_mtiles=n_mt, k_pad=k_steps * 16, dtype=op_dtype)
-            assert img.shape[0] == n_mt * (k_steps // 4)
+            if self.split:
+                img = pack_a_tiles_split(W, n_mtiles=n_mt, k_pad=k_steps * 16)
+                assert img.shape[0] == 2 * n_mt * (k_steps // 4)
+            else:
+                img = pack_a_tiles(W, n_mtiles=n_mt, k_pad=k_steps * 16, dtype=op_dtype)
+                assert img.shape[0] == n_mt * (k_steps // 4)
             bt = torch.zeros(n_mt * 128, dtype=torch.float32, device=dev)
             if b is not None:
                 bt[: b.numel()] = b.float()
@@ -221,6 +240,14 @@ class UmmaNet:
                 steps = [dict(r0, k_steps=16, epi=EPI_EXTRAS, n_cols=128), extras]
             steps += [dict(s, n_cols=128) for s in self.rad[1:]]
             return self._finish(steps, tang=0, input_mode=1)
+        if mode == "rev_sdf":
+            # split-precision kernel, sdf (and optionally the feature) only: the forward sweep of 'rev'
+            steps = [dict(s, n_cols=128, sig_slot=i) for i, s in enumerate(self.hidden)]
+            if want_feat:
+                steps.append(dict(self.feat, n_cols=128))
+            steps.append(dict(self.sdf_out, n_cols=128, sig_slot=len(self.hidden) - 1, aux_off=self._aux_off))
+            return self._finish(steps, tang=0, reverse=1)
+        assert not self.split or mode in ("rev", "rev_img"), "split images run reverse-mode programs only"
         if mode in ("rev", "rev_img"):
             # reverse-mode normals on 128-point tiles (nr_mlp_umma_reverse); 'rev_img': the last hidden activations
             # also go to the radiance pass's operand image

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(params=["fp32", "fp16"])
+@pytest.fixture(params=["fp32", "fp16", "fp16x2"])
 def tier(request):
     neurecon_b200.set_precision(request.param)
     yield request.param
@@ -87,10 +87,12 @@ def test_volsdf_render_vs_golden(tier, tag, beta_init, nerfpp):
     Mtot = 224 if nerfpp else 192
     assert ret["d_vals"].shape == (24, Mtot) and ret["visibility_weights"].shape == (24, Mtot - 1)
     assert ret["beta_map"].shape == (24, 1) and ret["iter_usage"].shape == (24,)
-    tol = 1e-4 if tier == "fp32" else 1e-2
+    tol = 1e-2 if tier == "fp16" else 1e-4      # 'fp16x2' (split-precision tensor tier) is held to the fp32 bar
     if tier == "fp32":
         assert torch.equal(ret["iter_usage"].cpu(), g["iter_usage"])
         assert rel_err(ret["beta_map"], g["beta_map"]) < 1e-5
+    elif tier == "fp16x2":
+        assert (ret["iter_usage"].cpu() == g["iter_usage"]).float().mean() > 0.95
     else:
         # the tensor tier's sdf differs by ~1e-3, which may move a ray across the eps threshold
         assert (ret["iter_usage"].cpu() == g["iter_usage"]).float().mean() > 0.8

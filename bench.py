@@ -305,6 +305,21 @@ def extra_configs(dev, rank, world, timed, precision):
                 neurecon_b200.set_precision(precision)
             out["neus_fp32_tier"] = {"value": world * 16384 / (ms * 1e-3), "unit": "rays/s", "rays_per_gpu": 16384,
                                      "workload": "the headline NeuS render on the fp32 SIMT tier (<= 1e-4 parity), 16384 rays per GPU"}
+        # ---- split-precision tensor tier: the <= 1e-4 contract on tcgen05 (csrc/mlp_rev_split.cu) ----
+        if precision != "fp16x2":
+            o, d = synthetic.make_rays(N_RAYS, shell_radius=2.5, jitter=0.1, seed=100 + rank)
+            o, d = o.to(dev), d.to(dev)
+            neurecon_b200.set_precision("fp16x2")
+            try:
+                kwn = dict(calc_normal=True, detailed_output=False, perturb=False, rayschunk=65536)
+                neus.volume_render(o[:65536], d[:65536], m, **kwn)
+                ms = timed(lambda: neus.volume_render(o, d, m, **kwn), 2) / 2
+            finally:
+                neurecon_b200.set_precision(precision)
+            out["neus_fp16x2_tier"] = {
+                "value": world * N_RAYS / (ms * 1e-3), "unit": "rays/s", "rays_per_gpu": N_RAYS, "ms_per_image": ms,
+                "workload": "the headline NeuS render (576x768 view per GPU) on the split-precision tensor tier: SDF net on (hi, lo) "
+                            "fp16 operand pairs (3 products as 2 MMAs per k-step), radiance net on fp16; <= 1e-4 parity"}
     return out
 
 

@@ -19,7 +19,7 @@ from conftest import NEUS_CFG, build_neus, build_unisurf, build_volsdf, cpu_stat
 
 pytestmark = pytest.mark.gpu
 KEYS = ("rgb", "depth_volume", "mask_volume", "normals_volume")
-TIERS = [("fp32", 1e-4), ("fp16", 1e-2)]
+TIERS = [("fp32", 1e-4), ("fp16x2", 1e-4), ("fp16", 1e-2)]     # fp16x2: split-precision tensor tier, held to the fp32 bar
 VOL_CFG = dict(multires=6, multires_view=-1, rad_multires=-1, skips=[4], D=8, D_rad=4, speed_factor=10.0)
 UNI_CFG = dict(multires=6, multires_view=-1, rad_multires=-1, skips=[4], D=8, D_rad=4, speed_factor=1.0)
 

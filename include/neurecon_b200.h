@@ -190,6 +190,25 @@ int nr_sample_pdf(const float* bins, const float* weights, const float* u, int64
 int nr_grid_points(int64_t i0, int64_t count, int32_t N, double volume_size, int32_t faithful, float* pts,
                    void* stream);
 
+/* Iso-surface extraction on the device: what the reference does on the host with skimage.measure.marching_cubes
+ * (utils/mesh_util.py:33-35) after copying the grid over PCIe.  Indexed triangle mesh of {vol = level} on the lattice
+ * vol [Nx,Ny,Nz] (row-major, x slowest); a sample is inside when vol < level; vertices are the linear edge crossings,
+ * (index + t) * spacing per axis, every crossing ONE vertex shared by the triangles around it; case table =
+ * neurecon_b200/mc_tables.py (face-consistent disambiguation: closed meshes).  Canonical output order (vertices by owner
+ * lattice point then axis, triangles by cell then table order), so a CPU restatement reproduces both arrays bit for bit.
+ * nr_mc_count: flags / cases [Nx*Ny*Nz] u8, vbase / fbase [Nx*Ny*Nz] i32 (first vertex of a point, first triangle of a
+ *   cell), totals: 2 x int64 ON THE DEVICE (vertices, triangles) -- the one number the host must read to allocate outputs.
+ *   n_tris: the table's u8[256] triangle counts on the device; workspace: nr_mc_count_workspace bytes.
+ * nr_mc_generate: verts [V,3] f32, faces [F,3] i32; tri_table: the table's int8 [256][32] on the device; ascent != 0
+ *   flips the winding (default: right-hand normals point towards decreasing values, skimage's 'descent'). */
+size_t nr_mc_count_workspace(int32_t Nx, int32_t Ny, int32_t Nz);
+int nr_mc_count(const float* vol, int32_t Nx, int32_t Ny, int32_t Nz, float level, const uint8_t* n_tris, uint8_t* flags,
+                uint8_t* cases, int32_t* vbase, int32_t* fbase, int64_t* totals, void* workspace, size_t workspace_bytes,
+                void* stream);
+int nr_mc_generate(const float* vol, int32_t Nx, int32_t Ny, int32_t Nz, float level, float spacing_x, float spacing_y,
+                   float spacing_z, int32_t ascent, const uint8_t* flags, const uint8_t* cases, const int32_t* vbase,
+                   const int32_t* fbase, const int8_t* tri_table, float* verts, int32_t* faces, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * NeuS -- models/frameworks/neus.py
  * ------------------------------------------------------------------------------------------ */

@@ -43,11 +43,11 @@ def edge_corners(e):
     return c0, c1
 
 
+_EDGE_OF = {frozenset(edge_corners(e)): e for e in range(12)}
+
+
 def _edge_between(ca, cb):
-    for e in range(12):
-        if set(edge_corners(e)) == {ca, cb}:
-            return e
-    raise AssertionError
+    return _EDGE_OF[frozenset((ca, cb))]
 
 
 def _faces():

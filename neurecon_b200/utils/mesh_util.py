@@ -1,5 +1,7 @@
-"""Dense SDF-grid query: the hot part of the reference's ``utils/mesh_util.py:extract_mesh`` (:82-111).
-Marching cubes and the PLY writer (:13-80) are CPU post-processing and stay with the reference."""
+"""Drop-in for the reference's ``utils/mesh_util.py``: the dense SDF-grid query of ``extract_mesh`` (:82-111) through the fused
+MLP kernels, the iso-surface extraction (:33-35, skimage.measure.marching_cubes on the host there) as CUDA kernels on the
+grid where it lies in HBM, and the PLY writer (:57-72, plyfile there) producing the same byte layout."""
+import numpy as np
 import torch
 
 from .. import _lib
@@ -34,3 +36,98 @@ def query_sdf_grid(implicit_surface, N=512, volume_size=2.0, with_nablas=False, 
                 nab[c0:c0 + m] = n_
     sdf = sdf.reshape(hi - lo, N, N)
     return (sdf, nab.reshape(hi - lo, N, N, 3)) if with_nablas else sdf
+
+
+_MC_TABLES = {}
+
+
+def _mc_tables(dev):
+    key = (dev.type, dev.index)
+    if key not in _MC_TABLES:
+        from .. import mc_tables
+        tri, cnt = mc_tables.tables()
+        _MC_TABLES[key] = (torch.from_numpy(tri).to(dev).contiguous(), torch.from_numpy(cnt).to(dev).contiguous())
+    return _MC_TABLES[key]
+
+
+def marching_cubes(volume, level=0.0, spacing=(1.0, 1.0, 1.0), gradient_direction="descent"):
+    """Iso-surface of a CUDA volume [Nx, Ny, Nz] -> (verts [V, 3] float32, faces [F, 3] int32), both on the device: the role of
+    ``skimage.measure.marching_cubes(volume, level=, spacing=)`` in mesh_util.py:33-35 (same conventions: vertices in units
+    of ``spacing`` from the array origin, one shared vertex per edge crossing, right-hand normals towards decreasing values
+    unless gradient_direction='ascent').  One host read: the (vertex, triangle) totals, to size the outputs."""
+    if gradient_direction not in ("descent", "ascent"):
+        raise ValueError("gradient_direction must be 'descent' or 'ascent'")
+    _lib.require_cuda(volume)
+    if volume.dim() != 3:
+        raise ValueError("marching_cubes: the volume must be 3-D")
+    lib = _lib.get_lib()
+    vol = _lib.f32c(volume.detach())
+    dev = vol.device
+    Nx, Ny, Nz = vol.shape
+    n = vol.numel()
+    tri, cnt = _mc_tables(dev)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        flags = torch.empty(n, dtype=torch.uint8, device=dev)
+        cases = torch.empty(n, dtype=torch.uint8, device=dev)
+        vbase = torch.empty(n, dtype=torch.int32, device=dev)
+        fbase = torch.empty(n, dtype=torch.int32, device=dev)
+        totals = torch.empty(2, dtype=torch.int64, device=dev)
+        ws = _lib.workspace(lib.nr_mc_count_workspace(Nx, Ny, Nz), dev)
+        _lib.check(lib.nr_mc_count(_lib.ptr(vol), Nx, Ny, Nz, float(level), _lib.ptr(cnt), _lib.ptr(flags), _lib.ptr(cases),
+                                   _lib.ptr(vbase), _lib.ptr(fbase), _lib.ptr(totals), _lib.ptr(ws), ws.numel(), st), "mc_count")
+        V, F = (int(t) for t in totals.tolist())
+        verts = torch.empty(V, 3, dtype=torch.float32, device=dev)
+        faces = torch.empty(F, 3, dtype=torch.int32, device=dev)
+        if V > 0:
+            sp = [float(v) for v in spacing]
+            _lib.check(lib.nr_mc_generate(_lib.ptr(vol), Nx, Ny, Nz, float(level), sp[0], sp[1], sp[2],
+                                          1 if gradient_direction == "ascent" else 0, _lib.ptr(flags), _lib.ptr(cases),
+                                          _lib.ptr(vbase), _lib.ptr(fbase), _lib.ptr(tri), _lib.ptr(verts), _lib.ptr(faces), st),
+                       "mc_generate")
+    return verts, faces
+
+
+def write_ply(path, verts, faces):
+    """The file plyfile writes for mesh_util.py:57-72: binary little-endian, vertex x y z float32, face = a uchar count and
+    three int32 ``vertex_indices``."""
+    verts = np.ascontiguousarray(verts, dtype="<f4").reshape(-1, 3)
+    faces = np.ascontiguousarray(faces, dtype="<i4").reshape(-1, 3)
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+              "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(verts), len(faces)))
+    rec = np.empty(len(faces), dtype=np.dtype([("n", "u1"), ("idx", "<i4", (3,))]))
+    rec["n"] = 3
+    rec["idx"] = faces
+    with open(path, "wb") as fh:
+        fh.write(header.encode("ascii"))
+        fh.write(verts.tobytes())
+        fh.write(rec.tobytes())
+
+
+def convert_sigma_samples_to_ply(input_3d_sigma_array, voxel_grid_origin, volume_size, ply_filename_out, level=5.0, offset=None,
+                                 scale=None):
+    """mesh_util.py:13-80 with the same signature; ``input_3d_sigma_array`` may be a CUDA tensor (stays on the device) or a
+    numpy array (uploaded).  Returns (mesh_points [V, 3] float32 numpy, faces [F, 3] int32 numpy), which the reference
+    only writes to the file."""
+    vol = input_3d_sigma_array
+    if not torch.is_tensor(vol):
+        vol = torch.from_numpy(np.ascontiguousarray(vol, dtype=np.float32)).cuda()
+    verts, faces = marching_cubes(vol, level=level, spacing=volume_size)
+    org = torch.tensor([float(v) for v in voxel_grid_origin], dtype=torch.float32, device=verts.device)
+    mesh_points = (org + verts).cpu().numpy()                       # mesh_util.py:39-42
+    if scale is not None:
+        mesh_points = mesh_points / scale
+    if offset is not None:
+        mesh_points = mesh_points - offset
+    faces = faces.cpu().numpy()
+    write_ply(ply_filename_out, mesh_points, faces)
+    return mesh_points, faces
+
+
+def extract_mesh(implicit_surface, volume_size=2.0, level=0.0, N=512, filepath='./surface.ply', show_progress=True, chunk=16 * 1024):
+    """mesh_util.py:82-111, same signature: sdf on the N^3 lattice, iso-surface, PLY.  ``chunk`` (the reference's 16 K points
+    per host round trip) and ``show_progress`` are accepted and ignored: lattice, sdf grid and mesh never leave the device
+    until the mesh itself is written."""
+    s = volume_size
+    sdf = query_sdf_grid(implicit_surface, N=N, volume_size=s, plane_range=(0, N))
+    return convert_sigma_samples_to_ply(sdf, [-s / 2.0] * 3, [float(s) / N] * 3, filepath, level=level)   # spacing s / N: :111

@@ -247,6 +247,18 @@ def hbm_rooflines(dev, hbm_peak, R=N_RAYS):
             return total
         one_render()
         put("neus_upsample_5_steps", min(one_render() for _ in range(3)), sum(step_bytes), Ru, "neus_upsample_kernel x5")
+        # iso-surface extraction: 512^3 sdf lattice of a sphere in HBM -> indexed mesh in HBM; algorithmic
+        # bytes = the volume once + the mesh once ("rays" = lattice points)
+        from neurecon_b200.utils import mesh_util
+        Ng = 512
+        gg = torch.linspace(-1, 1, Ng, device=dev)
+        vol = torch.sqrt(gg[:, None, None] ** 2 + gg[None, :, None] ** 2 + gg[None, None, :] ** 2) - 0.6
+        v, fc = mesh_util.marching_cubes(vol, 0.0, (2.0 / Ng,) * 3)
+        ms = _event_ms(lambda: mesh_util.marching_cubes(vol, 0.0, (2.0 / Ng,) * 3), flush=flush)
+        mc_bytes = 4 * Ng ** 3 + 12 * v.shape[0] + 12 * fc.shape[0]
+        put("marching_cubes_512", ms, mc_bytes / Ng ** 3, Ng ** 3, "mc_count_kernel + 2 cub scans + mc_generate_kernel (incl. the one host read of the totals)")
+        out["marching_cubes_512"].update(vertices=int(v.shape[0]), triangles=int(fc.shape[0]))
+        del vol, v, fc
     return out
 
 

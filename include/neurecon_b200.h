@@ -444,6 +444,17 @@ int nr_gemm16_pack_w(const float* W, int32_t ldw, int32_t N, int32_t K, void* im
 /* dW[N, K] += scale * G[rows, N]^T X[rows, K]; G, X fp16 rows (ldg, ldx multiples of 64), dW fp32 (atomics). */
 int nr_gemm16_tn(const void* G, int32_t ldg, const void* X, int32_t ldx, int64_t rows, int32_t N, int32_t K, float* dW,
                  int32_t lddw, float scale, void* stream);
+/* Split-precision forward GEMM of the training path (precision 'fp16x2'): Y = epilogue((A_hi + A_lo)(W_hi + W_lo)^T) minus
+ * the lo x lo term, as ONE K-concatenated product [A_hi | A_lo | A_hi] x [W_hi | W_hi | W_lo]^T.  A: fp16 rows [M, lda] =
+ * [hi (Kp columns) | lo (Kp columns)], Kp = K rounded up to 64.  Wimg: per block of 64 output columns the image
+ * nr_gemm16_pack_w makes of the fp32 matrix [W_hi | W_hi | W_lo] (64 rows x 3 Kp, rows past N zero), blocks back to back.
+ * mode: 0 linear, 1 softplus100 (+ out2 = its derivative), 4 relu, 5 sigmoid.  Y fp16 (y_half) with the lo part of the
+ * result lo_off columns to the right of the hi part (lo_off = 0: hi only), or fp32. */
+int nr_gemm16_split(const void* A, int32_t lda, const void* Wimg, const float* bias, int64_t M, int32_t N, int32_t K, void* Y,
+                    int32_t ldy, int32_t y_half, int32_t lo_off, int32_t mode, void* out2, int32_t ld_o2, void* stream);
+/* nr_pe16 with split-precision output: lo = fp16(v - hi) lo_off (lo_off2 for e2) columns to the right of the hi parts. */
+int nr_pe16_split(const float* x, int64_t n, int32_t multires, void* e, int32_t ld, int32_t width, int32_t lo_off, void* e2,
+                  int32_t ld2, int32_t off2, int32_t lo_off2, void* stream);
 /* out[N] += scale * column sums of a fp16 matrix (N <= 256). */
 int nr_colsum16(const void* A, int32_t lda, int64_t rows, int32_t N, float scale, float* out, void* stream);
 /* Embedder.forward (base.py:46-64) as fp16 rows e [n, ld] (columns [pe_dim, width) zero; optionally also into e2 at

@@ -83,6 +83,10 @@ struct G16Args {
   const __half* aux_b; int ld_b;
   __half* out2; int ld_o2;
   int npad, n_kc;
+  // split-precision forward GEMMs (nr_gemm16_split): A = [hi | lo] (a_wrap physical 64-column chunks, chunk kc of the
+  // K-concatenated product [hi | lo | hi] x [W_hi | W_hi | W_lo]^T reads physical chunk kc % a_wrap), blockIdx.y = block of
+  // `npad` output columns with its own W image, lo_off = column offset of the lo part of a fp16 result (0: none)
+  int a_wrap, lo_off, w_block_bytes;
 };
 
 __device__ __forceinline__ uint4 pack8h(const float4& a, const float4& b) {
@@ -160,6 +164,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm16_kernel(const G16Args g
   __shared__ uint32_t tmem_base_s;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int64_t n_tiles = (g.M + kBM - 1) / kBM;
+  const int col0 = (int)blockIdx.y * g.npad;        // first output column of this CTA (column blocks: nr_gemm16_split only)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kAStages; ++s) { umma::mbar_init(&a_full[s], 1); umma::mbar_init(&a_empty[s], 1); }
@@ -168,9 +173,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm16_kernel(const G16Args g
     umma::fence_barrier_init();
     if (g.Wimg) {                          // the packed image: one bulk copy per 64-k chunk
       const uint32_t bytes = (uint32_t)g.n_kc * w_chunk_bytes;
+      const uint8_t* img = g.Wimg + (size_t)blockIdx.y * g.w_block_bytes;
       umma::mbar_arrive_expect_tx(w_bar, bytes);
       for (int kc = 0; kc < g.n_kc; ++kc)
-        umma::bulk_g2s(sW + (size_t)kc * w_chunk_bytes, g.Wimg + (size_t)kc * w_chunk_bytes, w_chunk_bytes, w_bar);
+        umma::bulk_g2s(sW + (size_t)kc * w_chunk_bytes, img + (size_t)kc * w_chunk_bytes, w_chunk_bytes, w_bar);
     }
   }
   if (warp == 1) { umma::tmem_alloc(&tmem_base_s, 512); umma::tmem_relinquish(); }
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm16_kernel(const G16Args g
           const uint32_t st = cnt % kAStages, ph = (cnt / kAStages) & 1u;
           umma::mbar_wait(&a_empty[st], ph ^ 1u);
           umma::mbar_arrive_expect_tx(&a_full[st], kAStageBytes);
-          tma_load_2d(sA + st * kAStageBytes, &map_a, kc * kKC, (int)(tile * kBM), &a_full[st]);
+          tma_load_2d(sA + st * kAStageBytes, &map_a, (kc % g.a_wrap) * kKC, (int)(tile * kBM), &a_full[st]);
         }
       }
     }
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm16_kernel(const G16Args g
     const int part = (warp - kEpiWarp0) >> 2;
     const int per = ((g.npad + 3) / 4 + 15) & ~15;                 // columns per quarter, a multiple of 16
     const int c_lo = min(part * per, g.npad), c_hi = min(c_lo + per, g.npad);
-    const int n16 = (g.N + 15) & ~15;        // columns written: [N, n16) as zeros
+    const int n16 = min(g.npad, ((g.N + 15) & ~15) - col0);        // columns (of this block) written: [N, n16) as zeros
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u;
@@ -262,9 +268,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm16_kernel(const G16Args g
       const int64_t row = tile * kBM + 32 * q + lane;
       const bool rok = row < g.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + buf * 256u;
-      const __half* arow = g.aux_a ? g.aux_a + (size_t)row * g.ld_a : nullptr;
-      const __half* brow = g.aux_b ? g.aux_b + (size_t)row * g.ld_b : nullptr;
-      __half* orow = g.out2 ? g.out2 + (size_t)row * g.ld_o2 : nullptr;
+      const __half* arow = g.aux_a ? g.aux_a + (size_t)row * g.ld_a + col0 : nullptr;
+      const __half* brow = g.aux_b ? g.aux_b + (size_t)row * g.ld_b + col0 : nullptr;
+      __half* orow = g.out2 ? g.out2 + (size_t)row * g.ld_o2 + col0 : nullptr;
       // auxiliary rows: kPre iterations (16 columns each) requested ahead of their use -- a thread that asks for 32 bytes and
       // waits an HBM round trip for them moves 5 GB/s per SM; this is what bounded the first version of these kernels
       U8 an[2], bn[2];                           // two prefetch slots (16 columns = 32 bytes each), compile-time indices only
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm16_kernel(const G16Args g
         unpack16h(bc, bv);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int cj = c0 + j;
+          const int cj = col0 + c0 + j;
           float z = __uint_as_float(raw[j]);
           o2[j] = 0.f;
           if (cj < g.N) {
@@ -318,9 +324,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm16_kernel(const G16Args g
           y[j] = z;
         }
         if (Y_HALF) {
-          stg256(reinterpret_cast<__half*>(g.Y) + (size_t)row * g.ldy + c0, pack16f(y));
+          __half* yrow = reinterpret_cast<__half*>(g.Y) + (size_t)row * g.ldy + col0 + c0;
+          const U8 hi = pack16f(y);
+          stg256(yrow, hi);
+          if (g.lo_off) {                       // split result: lo = fp16(y - hi) next to it
+            float hf[16], lo[16];
+            unpack16h(hi, hf);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) lo[j] = y[j] - hf[j];
+            stg256(yrow + g.lo_off, pack16f(lo));
+          }
         } else {
-          float* yrow = reinterpret_cast<float*>(g.Y) + (size_t)row * g.ldy + c0;
+          float* yrow = reinterpret_cast<float*>(g.Y) + (size_t)row * g.ldy + col0 + c0;
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<float4*>(yrow + 4 * j4) = make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
         }
@@ -509,7 +524,7 @@ __device__ __forceinline__ void pe_and_jac(int j, int multires, const float* x3,
 }
 // e [n, ld] <- PE(x) as fp16 (columns [pe_dim, width) zero); optionally the same values into e2 at column offset off2
 __global__ void pe16_kernel(const float* __restrict__ x, int64_t n, int multires, int pe_dim, __half* __restrict__ e, int ld,
-                            int width, __half* __restrict__ e2, int ld2, int off2) {
+                            int width, __half* __restrict__ e2, int ld2, int off2, int lo_off, int lo_off2) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n * width) return;
   const int64_t p = i / width;
@@ -520,8 +535,14 @@ __global__ void pe16_kernel(const float* __restrict__ x, int64_t n, int multires
     int comp; float jac;
     pe_and_jac(j, multires, x3, v, comp, jac);
   }
-  e[(size_t)p * ld + j] = __float2half_rn(v);
-  if (e2 && j < pe_dim) e2[(size_t)p * ld2 + off2 + j] = __float2half_rn(v);
+  const __half h = __float2half_rn(v);
+  e[(size_t)p * ld + j] = h;
+  if (e2 && j < pe_dim) e2[(size_t)p * ld2 + off2 + j] = h;
+  if (lo_off) {                            // split-precision rows: lo = fp16(v - hi), lo_off columns to the right
+    const __half l = __float2half_rn(v - __half2float(h));
+    e[(size_t)p * ld + lo_off + j] = l;
+    if (e2 && j < pe_dim) e2[(size_t)p * ld2 + lo_off2 + off2 + j] = l;
+  }
 }
 // nabla[p, c] = sum_j dPE_j/dx_c (g0[p, j] + ge[p, j])          (g0 fp32 [n, ldg0]; ge fp16 view or NULL)
 __global__ void pe_jac_t_kernel(const float* __restrict__ x, int64_t n, int multires, int pe_dim, const float* __restrict__ g0,
@@ -593,9 +614,10 @@ extern "C" int nr_gemm16(const void* A, int32_t lda, const float* W, int32_t ldw
   NR_CHECK_ARG(mode != G_SOFTPLUS || out2, "nr_gemm16: G_SOFTPLUS needs out2");
   if (M == 0) return NR_OK;
   G16Args g{(const __half*)A, lda, w_packed ? nullptr : W, ldw, w_packed ? (const uint8_t*)W : nullptr, 3, bias, M, N, K, Y, ldy,
-            y_half, mode, (const __half*)aux_a, ld_a, (const __half*)aux_b, ld_b, (__half*)out2, ld_o2, 0, 0};
+            y_half, mode, (const __half*)aux_a, ld_a, (const __half*)aux_b, ld_b, (__half*)out2, ld_o2, 0, 0, 0, 0, 0};
   g.npad = (N + 15) / 16 * 16;
   g.n_kc = (K + kKC - 1) / kKC;
+  g.a_wrap = g.n_kc;
   NR_CHECK_ARG(g.npad <= 256, "nr_gemm16: N=%d > 256", N);
   const size_t fixed = 1024 + (size_t)g.n_kc * g.npad * 128 + 256;
   NR_CHECK_ARG(fixed + 3 * kAStageBytes <= 227 * 1024, "nr_gemm16: W (%d x %d) does not fit in shared memory", N, K);
@@ -621,6 +643,62 @@ extern "C" int nr_gemm16(const void* A, int32_t lda, const float* W, int32_t ldw
     default: break;
   }
   NR_CHECK_LAUNCH("gemm16_kernel");
+  return NR_OK;
+}
+
+// Split-precision forward GEMM:  Y = epilogue((A_hi + A_lo) (W_hi + W_lo)^T) without the lo x lo term, as ONE K-concatenated
+// product [A_hi | A_lo | A_hi] x [W_hi | W_hi | W_lo]^T.  A: fp16 rows [M, lda] holding [hi (Kp columns) | lo (Kp columns)],
+// Kp = K rounded up to 64; Wimg: for each block of 64 output columns the image nr_gemm16_pack_w makes of the fp32 matrix
+// [W_hi | W_hi | W_lo] (64 x 3 Kp); Y fp16 with the lo part of the result lo_off columns to the right (lo_off = 0: hi only),
+// or fp32.  grid = (tiles, column blocks): the blocks of a row tile run on different SMs at the same time and share its A
+// chunks through L2.
+extern "C" int nr_gemm16_split(const void* A, int32_t lda, const void* Wimg, const float* bias, int64_t M, int32_t N, int32_t K,
+                               void* Y, int32_t ldy, int32_t y_half, int32_t lo_off, int32_t mode, void* out2, int32_t ld_o2,
+                               void* stream) {
+  NR_CHECK_ARG(A && Wimg && Y && M >= 0 && N >= 1 && K >= 1, "nr_gemm16_split: bad arguments");
+  NR_CHECK_ARG(mode == G_LINEAR || mode == G_SOFTPLUS || mode == G_RELU || mode == G_SIGMOID, "nr_gemm16_split: mode=%d", mode);
+  const int kp = (K + kKC - 1) / kKC * kKC, n_blocks = (N + 63) / 64, n16 = (N + 15) & ~15;
+  NR_CHECK_ARG(lda % 16 == 0 && lda >= 2 * kp, "nr_gemm16_split: lda=%d must cover [hi | lo] = 2 x %d columns", lda, kp);
+  NR_CHECK_ARG(ldy % (y_half ? 16 : 4) == 0 && ldy >= (lo_off ? lo_off + n16 : n16) && (lo_off == 0 || (y_half && lo_off % 16 == 0 && lo_off >= n16)),
+               "nr_gemm16_split: ldy / lo_off");
+  NR_CHECK_ARG((((uintptr_t)A | (uintptr_t)out2) & 31) == 0 && ((uintptr_t)Y & (y_half ? 31 : 15)) == 0 && ((uintptr_t)Wimg & 15) == 0,
+               "nr_gemm16_split: alignment");
+  NR_CHECK_ARG(mode != G_SOFTPLUS || out2, "nr_gemm16_split: G_SOFTPLUS needs out2");
+  NR_CHECK_ARG(!out2 || (ld_o2 % 16 == 0 && ld_o2 >= n16), "nr_gemm16_split: ld_o2");
+  if (M == 0) return NR_OK;
+  G16Args g{(const __half*)A, lda, nullptr, 0, (const uint8_t*)Wimg, 3, bias, M, N, 3 * kp, Y, ldy, y_half, mode, nullptr, 0, nullptr, 0,
+            (__half*)out2, ld_o2, 0, 0, 0, 0, 0};
+  g.npad = 64;
+  g.n_kc = 3 * kp / kKC;
+  g.a_wrap = 2 * kp / kKC;
+  g.lo_off = lo_off;
+  g.w_block_bytes = g.n_kc * g.npad * 128;
+  const size_t fixed = 1024 + (size_t)g.n_kc * g.npad * 128 + 256;
+  NR_CHECK_ARG(fixed + 3 * kAStageBytes <= 227 * 1024, "nr_gemm16_split: W (64 x %d) does not fit in shared memory", 3 * kp);
+  g.a_stages = (int)((227 * 1024 - fixed) / kAStageBytes);
+  if (g.a_stages > kMaxAStages) g.a_stages = kMaxAStages;
+  const size_t smem = fixed + (size_t)g.a_stages * kAStageBytes;
+  int dev = 0, sms = 0;
+  NR_CHECK_CUDA(cudaGetDevice(&dev));
+  NR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t n_tiles = nr_cdiv(M, kBM);
+  int64_t gx = sms / n_blocks;
+  if (gx < 1) gx = 1;
+  if (gx > n_tiles) gx = n_tiles;
+  CUtensorMap map_a;
+  if (int rc = make_map(&map_a, A, M, lda, kBM, "nr_gemm16_split")) return rc;
+  const dim3 grid((unsigned)gx, (unsigned)n_blocks);
+#define NR_G16S_LAUNCH(MODE_, YH_)                                                                                        \
+  do {                                                                                                                    \
+    NR_CHECK_CUDA(cudaFuncSetAttribute(gemm16_kernel<MODE_, YH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gemm16_kernel<MODE_, YH_><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(g, map_a);                                 \
+  } while (0)
+#define NR_G16S_CASE(MODE_) case MODE_: if (y_half) NR_G16S_LAUNCH(MODE_, true); else NR_G16S_LAUNCH(MODE_, false); break
+  switch (mode) {
+    NR_G16S_CASE(G_LINEAR); NR_G16S_CASE(G_SOFTPLUS); NR_G16S_CASE(G_RELU); NR_G16S_CASE(G_SIGMOID);
+    default: break;
+  }
+  NR_CHECK_LAUNCH("gemm16_kernel (split)");
   return NR_OK;
 }
 
@@ -667,8 +745,21 @@ extern "C" int nr_pe16(const float* x, int64_t n, int32_t multires, void* e, int
   NR_CHECK_ARG(x && e && n >= 0 && width >= pe_dim && ld >= width, "nr_pe16: bad arguments");
   if (n == 0) return NR_OK;
   pe16_kernel<<<(unsigned)nr_cdiv(n * width, 256), 256, 0, (cudaStream_t)stream>>>(x, n, multires < 0 ? 0 : multires, pe_dim, (__half*)e, ld,
-                                                                                  width, (__half*)e2, ld2, off2);
+                                                                                  width, (__half*)e2, ld2, off2, 0, 0);
   NR_CHECK_LAUNCH("pe16_kernel");
+  return NR_OK;
+}
+
+// nr_pe16 with split-precision output: the lo parts lo_off (lo_off2 for e2) columns to the right of the hi parts
+extern "C" int nr_pe16_split(const float* x, int64_t n, int32_t multires, void* e, int32_t ld, int32_t width, int32_t lo_off, void* e2,
+                             int32_t ld2, int32_t off2, int32_t lo_off2, void* stream) {
+  const int pe_dim = multires < 0 ? 3 : 3 + 6 * multires;
+  NR_CHECK_ARG(x && e && n >= 0 && width >= pe_dim && lo_off >= width && ld >= lo_off + width, "nr_pe16_split: bad arguments");
+  NR_CHECK_ARG(!e2 || (lo_off2 > 0 && ld2 >= lo_off2 + off2 + pe_dim), "nr_pe16_split: second output");
+  if (n == 0) return NR_OK;
+  pe16_kernel<<<(unsigned)nr_cdiv(n * width, 256), 256, 0, (cudaStream_t)stream>>>(x, n, multires < 0 ? 0 : multires, pe_dim, (__half*)e, ld,
+                                                                                  width, (__half*)e2, ld2, off2, lo_off, lo_off2);
+  NR_CHECK_LAUNCH("pe16_kernel (split)");
   return NR_OK;
 }
 

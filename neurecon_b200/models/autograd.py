@@ -59,7 +59,7 @@ _REVERSE_TRAINING = os.environ.get("NEURECON_B200_TRAIN", "reverse") != "forward
 
 def _tc():
     """Training GEMMs on the tensor cores (csrc/gemm_tc.cu) in the fp16 / bf16 tiers, fp32 SIMT in the fp32 tier."""
-    return _lib.tensor_tier() and not _lib.split_tier()     # 'fp16x2' trains on the fp32 path (<= 1e-4 is its contract)
+    return _lib.tensor_tier()
 
 
 def _gemm(A, K, W, bias, N, mode, S=None, aux=None, m_val=0, grad=False, out=None):
@@ -76,7 +76,7 @@ def _gemm(A, K, W, bias, N, mode, S=None, aux=None, m_val=0, grad=False, out=Non
         Y = torch.zeros(M, ldy, dtype=torch.float32, device=A.device) if ldy != N else torch.empty(M, ldy, dtype=torch.float32, device=A.device)
     st = _lib.stream_ptr(A.device)
     if _tc():
-        f16 = 1 if _lib.get_precision() == "fp16" else 0       # gradient operands too: fp16 behind the loss scale
+        f16 = 1 if _lib.operand() == "fp16" else 0       # gradient operands too: fp16 behind the loss scale
         for n0 in range(0, N, 256):                       # the MMA's N is at most 256 (the last SDF layer has 257 rows)
             nn = min(256, N - n0)
             off = lambda t, ld: None if t is None else t[:, n0:]
@@ -96,7 +96,7 @@ def _gemm_tn(G, N, X, K, dW):
     lib = _lib.get_lib()
     if _tc():
         _lib.check(lib.nr_gemm_tn_tc(_lib.ptr(G), G.shape[1], _lib.ptr(X), X.shape[1], G.shape[0], N, K, _lib.ptr(dW),
-                                     dW.shape[1], 1 if _lib.get_precision() == "fp16" else 0, _lib.stream_ptr(G.device)),
+                                     dW.shape[1], 1 if _lib.operand() == "fp16" else 0, _lib.stream_ptr(G.device)),
                    "gemm_tn_tc")
         return
     _lib.check(lib.nr_gemm_tn_f32(_lib.ptr(G), G.shape[1], _lib.ptr(X), X.shape[1], G.shape[0], N, K, _lib.ptr(dW),
@@ -105,7 +105,7 @@ def _gemm_tn(G, N, X, K, dW):
 
 def _scale_in(*gs):
     """incoming gradients times the loss scale (tensor tier with fp16 operands only)"""
-    if not (_tc() and _lib.get_precision() == "fp16"):
+    if not (_tc() and _lib.operand() == "fp16"):
         return gs + (1.0,)
     return tuple(None if g is None else g * _GRAD_SCALE for g in gs) + (1.0 / _GRAD_SCALE,)
 
@@ -388,7 +388,7 @@ def _run_sdf(surface, x, want_nablas):
     xf = _lib.f32c(x.detach().reshape(-1, 3))
     skip = surface.skips[0] if surface.skips else -1
     wb = _surface_weights(surface)
-    if want_nablas and _tc() and _lib.get_precision() == "fp16" and _REVERSE_TRAINING:
+    if want_nablas and _tc() and _lib.operand() == "fp16" and _REVERSE_TRAINING:
         from . import autograd_rev
         if autograd_rev.supported([tuple(w.shape) for w in wb[0::2]], skip, surface.embed_multires):
             sdf, nabla, feat = autograd_rev.SdfRevFn.apply(xf, surface.embed_multires, skip, *wb)
@@ -430,7 +430,7 @@ def radiance_forward_autograd(rad, x, view_dirs, normals, geometry_feature):
         wb += [Ws[i] if Ws is not None else _effective_weight(layer), layer.bias]
     wb[0] = rad._layer0_weight(wb[0])
     mv = rad._multires_view_eff
-    if _tc() and _lib.get_precision() == "fp16" and _REVERSE_TRAINING and all(tuple(w.shape)[0] == 256 for w in wb[0:-2:2]) \
+    if _tc() and _lib.operand() == "fp16" and _REVERSE_TRAINING and all(tuple(w.shape)[0] == 256 for w in wb[0:-2:2]) \
             and wb[0].shape[1] > 256:
         from . import autograd_rev
         rgb = autograd_rev.RadianceRevFn.apply(xf, vf, nf, ff, rad.embed_multires, mv, *wb)

@@ -62,6 +62,43 @@ def _gemm16(A, W, bias, n, N, K, Y, y_half, mode, aux_a=None, aux_b=None, out2=N
         _lib.stream_ptr(A.device)), "gemm16")
 
 
+def split_forward():
+    """Forward sweeps on split-precision operands (csrc/gemm16.cu nr_gemm16_split): the 'fp16x2' tier's training path, or
+    NEURECON_B200_TRAIN_SPLIT=1 in the fp16 tier.  Softplus(beta=100) turns a pre-activation error dz into 25 dz on
+    softplus' and 2500 dz on softplus'' (the eikonal term's second-order path): with plain fp16 operands (dz ~ 3e-4) the
+    worst weight gradient of a NeuS step is 1e-1 off the reference's, with exact pre-activations 1e-2 (measured)."""
+    return _lib.split_tier() or os.environ.get("NEURECON_B200_TRAIN_SPLIT", "0") != "0"
+
+
+class _PackedSplit:
+    """[W_hi | W_hi | W_lo] (the K-concatenated split product's weight side) as nr_gemm16 images, one per block of 64 output
+    columns"""
+
+    def __init__(self, W, N, K):
+        lib = _lib.get_lib()
+        dev = W.device
+        kp = (K + 63) // 64 * 64
+        nb = (N + 63) // 64
+        Wf = W.detach().float()[:N, :K]
+        hi = Wf.half().float()
+        lo = (Wf - hi).half().float()
+        cat = torch.zeros(nb * 64, 3 * kp, dtype=torch.float32, device=dev)
+        cat[:N, :K] = hi
+        cat[:N, kp:kp + K] = hi
+        cat[:N, 2 * kp:2 * kp + K] = lo
+        per = int(lib.nr_gemm16_pack_w_bytes(64, 3 * kp))
+        self.img = torch.empty(nb * per, dtype=torch.uint8, device=dev)
+        st = _lib.stream_ptr(dev)
+        for b in range(nb):
+            _lib.check(lib.nr_gemm16_pack_w(_lib.ptr(cat[64 * b:]), 3 * kp, 64, 3 * kp, _lib.ptr(self.img[b * per:]), st), "gemm16_pack_w")
+
+
+def _gemm16_split(A, Wp, bias, n, N, K, Y, y_half, lo_off, mode, out2=None):
+    _lib.check(_lib.get_lib().nr_gemm16_split(
+        _lib.ptr(A), A.stride(0), _lib.ptr(Wp.img), _lib.ptr(bias), n, N, K, _lib.ptr(Y), Y.stride(0), int(y_half), int(lo_off), mode,
+        _lib.ptr(out2), 0 if out2 is None else out2.stride(0), _lib.stream_ptr(A.device)), "gemm16_split")
+
+
 def supported(dims, skip, multires):
     """the shapes this path is written for: hidden width 256, one skip whose input is [h | PE(x)] of width 256"""
     L = len(dims)
@@ -95,23 +132,39 @@ class SdfRevFn(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            e = torch.empty(n, 64, **h16)
-            _lib.check(lib.nr_pe16(_lib.ptr(x), n, multires, _lib.ptr(e), 64, 64, None, 0, 0, st), "pe16")
+            split = split_forward()
+            if split:
+                e = torch.empty(n, 128, **h16)                                # [PE hi | PE lo]
+                _lib.check(lib.nr_pe16_split(_lib.ptr(x), n, multires, _lib.ptr(e), 128, 64, 64, None, 0, 0, 0, st), "pe16_split")
+            else:
+                e = torch.empty(n, 64, **h16)
+                _lib.check(lib.nr_pe16(_lib.ptr(x), n, multires, _lib.ptr(e), 64, 64, None, 0, 0, st), "pe16")
             hs, S = [e], []
             Wp = [_Packed(Ws[l], dims[l][0], dims[l][1]) if _PACK else Ws[l] for l in range(D)]   # forward + adjoint sweeps
             for l in range(D):                                               # ---- forward sweep
                 N, K = dims[l]
-                out = torch.empty(n, WIDTH, **h16)
                 Sl = torch.empty(n, WIDTH, **h16)
-                _gemm16(hs[l], Wp[l], bs[l], n, N, K, out, 1, G_SOFTPLUS, out2=Sl)
+                if split:      # pre-activations from (hi, lo) operand pairs: softplus(beta=100) turns dz into 25 dz on softplus'
+                    out = torch.empty(n, 2 * WIDTH, **h16)
+                    _gemm16_split(hs[l], _PackedSplit(Ws[l], N, K), bs[l], n, N, K, out, 1, WIDTH, G_SOFTPLUS, out2=Sl)
+                else:
+                    out = torch.empty(n, WIDTH, **h16)
+                    _gemm16(hs[l], Wp[l], bs[l], n, N, K, out, 1, G_SOFTPLUS, out2=Sl)
                 if l + 1 == skip:                                            # the skip layer's input [h | PE(x)], S = 1 on the PE part
-                    _lib.check(lib.nr_pe16(_lib.ptr(x), n, multires, _lib.ptr(e), 64, 64, _lib.ptr(out), WIDTH, N, st), "pe16")
+                    if split:
+                        _lib.check(lib.nr_pe16_split(_lib.ptr(x), n, multires, _lib.ptr(e), 128, 64, 64, _lib.ptr(out), 2 * WIDTH, N,
+                                                     WIDTH, st), "pe16_split")
+                    else:
+                        _lib.check(lib.nr_pe16(_lib.ptr(x), n, multires, _lib.ptr(e), 64, 64, _lib.ptr(out), WIDTH, N, st), "pe16")
                     Sl[:, N:] = 1.0
                 hs.append(out)
                 S.append(Sl)
             y = torch.empty(n, WIDTH + 16, **f32)                             # [sdf | feat]: 257 columns in two launches
-            _gemm16(hs[D], Ws[D][:WIDTH], bs[D][:WIDTH], n, WIDTH, WIDTH, y, 0, G_LINEAR)
-            _gemm16(hs[D], Ws[D][WIDTH:], bs[D][WIDTH:], n, 1, WIDTH, y[:, WIDTH:], 0, G_LINEAR)
+            if split:
+                _gemm16_split(hs[D], _PackedSplit(Ws[D], WIDTH + 1, WIDTH), bs[D], n, WIDTH + 1, WIDTH, y, 0, 0, G_LINEAR)
+            else:
+                _gemm16(hs[D], Ws[D][:WIDTH], bs[D][:WIDTH], n, WIDTH, WIDTH, y, 0, G_LINEAR)
+                _gemm16(hs[D], Ws[D][WIDTH:], bs[D][WIDTH:], n, 1, WIDTH, y[:, WIDTH:], 0, G_LINEAR)
             sdf = y[:, 0].contiguous()
             feat = y[:, 1:WIDTH + 1].contiguous()
             # ---- reverse sweep: the normal
@@ -191,7 +244,7 @@ class SdfRevFn(torch.autograd.Function):
                 _lib.check(lib.nr_colsum16(_lib.ptr(Z[l]), WIDTH, n, N, inv, _lib.ptr(db), st), "colsum16")
                 grads[2 * l], grads[2 * l + 1] = dW[:, :K], db
             dWo = torch.zeros(WIDTH + 1, WIDTH, **f32)
-            _lib.check(lib.nr_gemm16_tn(_lib.ptr(yb), 320, _lib.ptr(hs[D]), WIDTH, n, WIDTH + 1, WIDTH, _lib.ptr(dWo), WIDTH, inv, st),
+            _lib.check(lib.nr_gemm16_tn(_lib.ptr(yb), 320, _lib.ptr(hs[D]), hs[D].stride(0), n, WIDTH + 1, WIDTH, _lib.ptr(dWo), WIDTH, inv, st),
                        "gemm16_tn")
             if adj:
                 _lib.check(lib.nr_colsum16(_lib.ptr(G[D]), WIDTH, n, WIDTH, inv, _lib.ptr(dWo), st), "colsum16")   # sdf row
@@ -233,20 +286,37 @@ class RadianceRevFn(torch.autograd.Function):
         h16 = dict(dtype=torch.float16, device=dev)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            a0 = torch.zeros(n, ld0, **h16)
-            _lib.check(lib.nr_pe16(_lib.ptr(x), n, multires, _lib.ptr(a0), ld0, px, None, 0, 0, st), "pe16")
-            _lib.check(lib.nr_pe16(_lib.ptr(view), n, multires_view, _lib.ptr(a0[:, px:]), ld0, pv, None, 0, 0, st), "pe16")
-            a0[:, px + pv:px + pv + 3] = normals
-            a0[:, px + pv + 3:in0] = feat
+            split = split_forward()
+            a0 = torch.zeros(n, 2 * ld0 if split else ld0, **h16)        # split: [hi (ld0 columns) | lo (ld0 columns)]
+            if split:
+                _lib.check(lib.nr_pe16_split(_lib.ptr(x), n, multires, _lib.ptr(a0), 2 * ld0, px, ld0, None, 0, 0, 0, st), "pe16_split")
+                _lib.check(lib.nr_pe16_split(_lib.ptr(view), n, multires_view, _lib.ptr(a0[:, px:]), 2 * ld0, pv, ld0, None, 0, 0, 0, st),
+                           "pe16_split")
+                rest = torch.cat([normals.detach().float(), feat.detach().float()], dim=1)
+                rest_hi = rest.half()
+                a0[:, px + pv:in0] = rest_hi
+                a0[:, ld0 + px + pv:ld0 + in0] = rest - rest_hi.float()
+            else:
+                _lib.check(lib.nr_pe16(_lib.ptr(x), n, multires, _lib.ptr(a0), ld0, px, None, 0, 0, st), "pe16")
+                _lib.check(lib.nr_pe16(_lib.ptr(view), n, multires_view, _lib.ptr(a0[:, px:]), ld0, pv, None, 0, 0, st), "pe16")
+                a0[:, px + pv:px + pv + 3] = normals
+                a0[:, px + pv + 3:in0] = feat
             acts = [a0]
             for l in range(L - 1):
                 N, K = dims[l]
-                out = torch.empty(n, WIDTH, **h16)
-                _gemm16(acts[l], _Packed(Ws[l], N, K), bs[l], n, N, K, out, 1, G_RELU)
+                if split:
+                    out = torch.empty(n, 2 * WIDTH, **h16)
+                    _gemm16_split(acts[l], _PackedSplit(Ws[l], N, K), bs[l], n, N, K, out, 1, WIDTH, G_RELU)
+                else:
+                    out = torch.empty(n, WIDTH, **h16)
+                    _gemm16(acts[l], _Packed(Ws[l], N, K), bs[l], n, N, K, out, 1, G_RELU)
                 acts.append(out)
             N, K = dims[L - 1]
             y = torch.empty(n, _r16(N), dtype=torch.float32, device=dev)
-            _gemm16(acts[L - 1], Ws[L - 1], bs[L - 1], n, N, K, y, 0, G_SIGMOID)
+            if split:
+                _gemm16_split(acts[L - 1], _PackedSplit(Ws[L - 1], N, K), bs[L - 1], n, N, K, y, 0, 0, G_SIGMOID)
+            else:
+                _gemm16(acts[L - 1], Ws[L - 1], bs[L - 1], n, N, K, y, 0, G_SIGMOID)
             rgb = y[:, :N].contiguous()
         ctx.state = (acts, rgb, Ws, dims, n, px + pv, in0)
         return rgb

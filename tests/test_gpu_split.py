@@ -97,19 +97,24 @@ def test_split_neus_nerfpp_background_vs_golden():
         assert rel_err(ret[k], g[k]) < 5e-3, (k, rel_err(ret[k], g[k]))
 
 
-def test_split_training_takes_the_fp32_path():
-    """'fp16x2' is an inference tier: under autograd the networks run the fp32 kernels (gradient parity of that tier)"""
-    from neurecon_b200.models import autograd
-    assert _lib.tensor_tier() and _lib.split_tier() and not autograd._tc()
+def test_split_training_gradients_vs_fp32_tier():
+    """'fp16x2' under autograd: the reverse-mode training GEMMs with split-precision FORWARD sweeps (nr_gemm16_split).  Weight
+    gradients of sdf + eikonal + feature losses within 1e-2 of the fp32 tier's (plain fp16 operands: ~1e-1)."""
+    from neurecon_b200.models import autograd, autograd_rev
+    assert _lib.tensor_tier() and _lib.split_tier() and autograd._tc() and autograd_rev.split_forward()
     m = build_neus(seed=1, device=DEV)
-    x = (torch.rand(500, 3, device=DEV) - 0.5).requires_grad_(False)
-    sdf, nab, feat = m.implicit_surface.forward_with_nablas(x)
-    loss = (sdf ** 2).mean() + ((nab.norm(dim=-1) - 1) ** 2).mean()
-    loss.backward()
-    g1 = [p.grad.clone() for p in m.implicit_surface.parameters()]
+    x = (torch.rand(4000, 3, device=DEV) - 0.5) * 1.6
+
+    def grads():
+        m.zero_grad()
+        sdf, nab, feat = m.implicit_surface.forward_with_nablas(x)
+        loss = (sdf ** 2).mean() + ((nab.norm(dim=-1) - 1) ** 2).mean() + 1e-2 * (feat ** 2).mean()
+        loss.backward()
+        return float(loss), [p.grad.clone() for p in m.implicit_surface.parameters()]
+
+    l2, g2 = grads()
     neurecon_b200.set_precision("fp32")
-    m.zero_grad()
-    sdf, nab, feat = m.implicit_surface.forward_with_nablas(x)
-    ((sdf ** 2).mean() + ((nab.norm(dim=-1) - 1) ** 2).mean()).backward()
-    for a, p in zip(g1, m.implicit_surface.parameters()):
-        assert rel_err(a, p.grad) < 1e-5        # same kernels; the dW partial sums meet in atomics, hence not bit-equal
+    l1, g1 = grads()
+    assert abs(l1 - l2) < 1e-4 * abs(l1)
+    worst = max(rel_err(a, b) for a, b in zip(g2, g1))
+    assert worst < 1e-2, worst

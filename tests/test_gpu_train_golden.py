@@ -11,7 +11,8 @@ generator also ran the unmodified reference in float64 on the same step, and the
 up to 3.0e-4 (NeuS), 2.1e-3 (VolSDF), 5e-5 (UNISURF) away from those; torch's own float32 autograd of the UNISURF
 compositing is 1.1e-4 .. 2e-4 away from its float64 result on these rays (tools/dbg/dbg_uni2.py on a B200).  The bar
 per tensor is therefore max(5e-4, 4 x that tensor's reference fp32-vs-fp64 distance); how many tensors exceed the plain
-1e-4 is printed.  Gradients, 16-bit tier: see TIER16_GRAD_BAR below.
+1e-4 is printed.  Gradients, tensor tiers: 'fp16x2' (split-precision forward sweeps) meets north_star's 1e-2 on every tensor;
+plain 'fp16' does not, see TIER16_GRAD_BAR below.
 """
 import numpy as np
 import pytest
@@ -23,7 +24,7 @@ from conftest import load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 H, W = 24, 32
-TIERS = (("fp32", 1e-4), ("fp16", 1e-2))
+TIERS = (("fp32", 1e-4), ("fp16", 1e-2), ("fp16x2", 1e-2))
 # Weight gradients of the 16-bit tensor tier.  Measured against the reference: 8.6e-2 (NeuS), 3.0e-1 (VolSDF, a bias whose
 # entries are sums with heavy cancellation), 1.6e-1 (UNISURF) on the worst
 # tensor -- NOT north_star's 1e-2.  The cause is the activation, not the gradient GEMMs (fp16 gradient operands behind a
@@ -32,6 +33,10 @@ TIERS = (("fp32", 1e-4), ("fp16", 1e-2))
 # pre-activations good to ~3e-5, i.e. split-precision operands in the forward GEMMs.  Until then the
 # tier's training accuracy is what this bar says, and the fp32 tier is the one that matches the reference.
 TIER16_GRAD_BAR = 0.35
+# 'fp16x2': the same reverse-mode training GEMMs with the FORWARD sweeps on split-precision operands (hi + lo fp16 pairs, one
+# K-concatenated product, csrc/gemm16.cu nr_gemm16_split): every parameter gradient of all three frameworks within
+# north_star's 1e-2 of the reference's (measured worst tensors: 4.0e-3 NeuS, 2.7e-3 VolSDF, 5.9e-3 UNISURF).
+TIER16X2_GRAD_BAR = 1e-2
 
 
 class AttrDict(dict):
@@ -58,6 +63,8 @@ def _assert_grads(model, z, tol, tier):
     worst = _check_grads(model, z, tol, tier)
     if tier == "fp32":
         bad = [(e, nz, n) for e, nz, n in worst if e > max(5e-4, 4.0 * nz)]
+    elif tier == "fp16x2":
+        bad = [(e, nz, n) for e, nz, n in worst if e > TIER16X2_GRAD_BAR]
     else:
         bad = [(e, nz, n) for e, nz, n in worst if e > TIER16_GRAD_BAR]
     print("%s: %d tensors, worst (err, reference fp32-vs-fp64 noise, name): %s" % (tier, len(worst), worst[:4]))

@@ -28,7 +28,7 @@ H, W = 576, 768
 N_RAYS = H * W
 N_SAMPLES, N_IMPORTANCE = 64, 64
 CPU_SAMPLE_RAYS = 1024
-TRAIN_BLOCK_TIMEOUT_S = 120
+TRAIN_BLOCK_TIMEOUT_S = 180
 # algorithmic MFLOP per NeuS ray (inference) and per SDF query with nabla
 MFLOP_PER_RAY = 704.9
 MFLOP_PER_QUERY_NABLA = 1.967
@@ -603,7 +603,7 @@ def main():
             "metric": "rays/sec (NeuS 64+64 samples)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[precision], "data": "synthetic",
+            "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16", "fp16x2": "f16x2"}[precision], "data": "synthetic",
             "config": workload_config(precision),
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -634,10 +634,25 @@ def main():
         train = train_step_bench(dev, world, rank, timed)
     except Exception as e:  # reported in the line, the render numbers stand
         train = {"error": repr(e)[:300]}
+    train_x2 = None
+    if precision == "fp16" and "error" not in train:
+        # the same iteration with gradient parity (<= 1e-2 on every parameter, tests/test_gpu_train_golden.py): forward
+        # sweeps on split-precision operands (the fp16x2 tier)
+        import neurecon_b200
+        neurecon_b200.set_precision("fp16x2")
+        try:
+            train_x2 = train_step_bench(dev, world, rank, timed)
+            train_x2["workload"] += "; fp16x2 tier: forward sweeps on (hi, lo) fp16 operand pairs, every parameter gradient within 1e-2 of the reference's"
+        except Exception as e:
+            train_x2 = {"error": repr(e)[:300]}
+        finally:
+            neurecon_b200.set_precision(precision)
     finished.set()
     watchdog.cancel()
     if rank == 0:
         line["train_step"] = train
+        if train_x2 is not None:
+            line["train_step_fp16x2"] = train_x2
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

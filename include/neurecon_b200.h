@@ -452,6 +452,10 @@ int nr_gemm16_tn(const void* G, int32_t ldg, const void* X, int32_t ldx, int64_t
  * result lo_off columns to the right of the hi part (lo_off = 0: hi only), or fp32. */
 int nr_gemm16_split(const void* A, int32_t lda, const void* Wimg, const float* bias, int64_t M, int32_t N, int32_t K, void* Y,
                     int32_t ldy, int32_t y_half, int32_t lo_off, int32_t mode, void* out2, int32_t ld_o2, void* stream);
+/* The weight side of nr_gemm16_split for a fp32 matrix W [N, ldw]: all its column blocks in one launch (img:
+ * nr_gemm16_pack_w_split_bytes). */
+size_t nr_gemm16_pack_w_split_bytes(int32_t N, int32_t K);
+int nr_gemm16_pack_w_split(const float* W, int32_t ldw, int32_t N, int32_t K, void* img, void* stream);
 /* nr_pe16 with split-precision output: lo = fp16(v - hi) lo_off (lo_off2 for e2) columns to the right of the hi parts. */
 int nr_pe16_split(const float* x, int64_t n, int32_t multires, void* e, int32_t ld, int32_t width, int32_t lo_off, void* e2,
                   int32_t ld2, int32_t off2, int32_t lo_off2, void* stream);

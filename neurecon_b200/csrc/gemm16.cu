@@ -498,6 +498,33 @@ __global__ void gemm16_pack_w_kernel(const float* __restrict__ W, int ldw, int N
   *reinterpret_cast<uint4*>(img + (size_t)kc * npad * 128 + (n >> 3) * 1024 + (n & 7) * 128 + ((c8 ^ (n & 7)) << 4)) = pack8h(a, b);
 }
 
+// [W_hi | W_hi | W_lo] of nr_gemm16_split, all column blocks of a weight matrix in one launch: image = n_blocks x
+// (3 Kp / 64 chunks) x [64 rows x 64 k] fp16, swizzled; hi = fp16(w), lo = fp16(w - hi)
+__global__ void gemm16_pack_w_split_kernel(const float* __restrict__ W, int ldw, int N, int K, int kp, int n_blocks,
+                                           uint8_t* __restrict__ img) {
+  const int n_kc = 3 * kp / kKC, per_part = kp / kKC;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_blocks * n_kc * 64 * 8) return;
+  const int c8 = idx & 7, r = (idx >> 3) & 63, kc = (idx >> 9) % n_kc, b = (idx >> 9) / n_kc;
+  const int part = kc / per_part, k0 = (kc % per_part) * kKC + c8 * 8, n = 64 * b + r;
+  float4 a4, b4;
+  load8(W + (size_t)n * ldw + k0, n < N ? K - k0 : 0, a4, b4);
+  float v[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    if (part < 2) {
+      o[j] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      const float2 hf = __half22float2(h);
+      o[j] = umma::pack_f16(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    }
+  }
+  *reinterpret_cast<uint4*>(img + ((size_t)b * n_kc + kc) * (64 * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4)) =
+      make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // out[c] += scale * sum_r A[r, c]  (fp16 rows): block = 256 columns x 4 row lanes, grid over row slabs
 __global__ void colsum16_kernel(const __half* __restrict__ A, int lda, int64_t rows, int N, float scale, float* __restrict__ out) {
   const int c = threadIdx.x & 255, rl = threadIdx.x >> 8;
@@ -591,6 +618,21 @@ extern "C" int nr_gemm16_pack_w(const float* W, int32_t ldw, int32_t N, int32_t 
   gemm16_pack_w_kernel<<<(unsigned)nr_cdiv((int64_t)n_kc * npad * 8, 256), 256, 0, (cudaStream_t)stream>>>(W, ldw, N, K, npad, n_kc,
                                                                                                     (uint8_t*)img);
   NR_CHECK_LAUNCH("gemm16_pack_w_kernel");
+  return NR_OK;
+}
+
+extern "C" size_t nr_gemm16_pack_w_split_bytes(int32_t N, int32_t K) {
+  const int kp = (K + kKC - 1) / kKC * kKC;
+  return (size_t)((N + 63) / 64) * (3 * kp / kKC) * 64 * 128;
+}
+
+extern "C" int nr_gemm16_pack_w_split(const float* W, int32_t ldw, int32_t N, int32_t K, void* img, void* stream) {
+  NR_CHECK_ARG(W && img && N >= 1 && K >= 1 && (ldw & 3) == 0 && ldw >= K, "nr_gemm16_pack_w_split: bad arguments");
+  NR_CHECK_ARG((((uintptr_t)W | (uintptr_t)img) & 15) == 0, "nr_gemm16_pack_w_split: 16-byte alignment");
+  const int kp = (K + kKC - 1) / kKC * kKC, n_blocks = (N + 63) / 64;
+  const int64_t total = (int64_t)n_blocks * (3 * kp / kKC) * 64 * 8;
+  gemm16_pack_w_split_kernel<<<(unsigned)nr_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(W, ldw, N, K, kp, n_blocks, (uint8_t*)img);
+  NR_CHECK_LAUNCH("gemm16_pack_w_split_kernel");
   return NR_OK;
 }
 

@@ -72,25 +72,13 @@ def split_forward():
 
 class _PackedSplit:
     """[W_hi | W_hi | W_lo] (the K-concatenated split product's weight side) as nr_gemm16 images, one per block of 64 output
-    columns"""
+    columns; W: contiguous fp32 [>= N, pad4(K)]"""
 
     def __init__(self, W, N, K):
         lib = _lib.get_lib()
-        dev = W.device
-        kp = (K + 63) // 64 * 64
-        nb = (N + 63) // 64
-        Wf = W.detach().float()[:N, :K]
-        hi = Wf.half().float()
-        lo = (Wf - hi).half().float()
-        cat = torch.zeros(nb * 64, 3 * kp, dtype=torch.float32, device=dev)
-        cat[:N, :K] = hi
-        cat[:N, kp:kp + K] = hi
-        cat[:N, 2 * kp:2 * kp + K] = lo
-        per = int(lib.nr_gemm16_pack_w_bytes(64, 3 * kp))
-        self.img = torch.empty(nb * per, dtype=torch.uint8, device=dev)
-        st = _lib.stream_ptr(dev)
-        for b in range(nb):
-            _lib.check(lib.nr_gemm16_pack_w(_lib.ptr(cat[64 * b:]), 3 * kp, 64, 3 * kp, _lib.ptr(self.img[b * per:]), st), "gemm16_pack_w")
+        self.img = torch.empty(int(lib.nr_gemm16_pack_w_split_bytes(N, K)), dtype=torch.uint8, device=W.device)
+        _lib.check(lib.nr_gemm16_pack_w_split(_lib.ptr(W), W.stride(0), N, K, _lib.ptr(self.img), _lib.stream_ptr(W.device)),
+                   "gemm16_pack_w_split")
 
 
 def _gemm16_split(A, Wp, bias, n, N, K, Y, y_half, lo_off, mode, out2=None):

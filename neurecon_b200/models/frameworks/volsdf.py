@@ -137,8 +137,18 @@ def fine_sample(implicit_surface_fn, init_dvals, rays_o, rays_d, alpha_net, beta
                 _lib.ptr(d_new[it & 1]), _lib.ptr(pts_new), st), "volsdf_fine_iter")
             if it == max_iter:
                 break
-            if early_exit and bool((status != 0).all()):
-                break
+            if early_exit:
+                # one host read per iteration: WHICH rays are still refining.  Only their proposals go through the network
+                # -- the reference's boolean-mask gathers (volsdf.py:151-264); finished rays ignore sdf_new in the kernel.
+                # With every ray active (or early_exit=False: sync-free, graph-capturable) the whole batch is queried.
+                active = torch.nonzero(status == 0).squeeze(1)
+                if active.numel() == 0:
+                    break
+                if active.numel() < R:
+                    sdf_act = _lib.f32c(implicit_surface_fn(pts_new.index_select(0, active)).reshape(-1, N_up))
+                    sdf_new = torch.zeros(R, N_up, **f) if (sdf_new is None or sdf_new.shape != (R, N_up)) else sdf_new
+                    sdf_new.index_copy_(0, active, sdf_act)
+                    continue
             sdf_new = _lib.f32c(implicit_surface_fn(pts_new).reshape(R, N_up))
     return (d_fine.reshape(*prefix, final_N_importance), beta_map.reshape(*prefix, 1), iter_usage.reshape(*prefix))
 

@@ -445,13 +445,14 @@ int nr_gemm16_pack_w(const float* W, int32_t ldw, int32_t N, int32_t K, void* im
 int nr_gemm16_tn(const void* G, int32_t ldg, const void* X, int32_t ldx, int64_t rows, int32_t N, int32_t K, float* dW,
                  int32_t lddw, float scale, void* stream);
 /* Split-precision forward GEMM of the training path (precision 'fp16x2'): Y = epilogue((A_hi + A_lo)(W_hi + W_lo)^T) minus
- * the lo x lo term, as ONE K-concatenated product [A_hi | A_lo | A_hi] x [W_hi | W_hi | W_lo]^T.  A: fp16 rows [M, lda] =
- * [hi (Kp columns) | lo (Kp columns)], Kp = K rounded up to 64.  Wimg: per block of 64 output columns the image
- * nr_gemm16_pack_w makes of the fp32 matrix [W_hi | W_hi | W_lo] (64 rows x 3 Kp, rows past N zero), blocks back to back.
- * mode: 0 linear, 1 softplus100 (+ out2 = its derivative), 4 relu, 5 sigmoid.  Y fp16 (y_half) with the lo part of the
- * result lo_off columns to the right of the hi part (lo_off = 0: hi only), or fp32. */
+ * the lo x lo term, in one accumulator: every 64-column chunk of A is loaded once; a hi chunk multiplies the W_hi and the
+ * W_lo chunk of its k range, a lo chunk the W_hi chunk.  A: fp16 rows [M, lda] = [hi (Kp columns) | lo (Kp columns)], Kp = K
+ * rounded up to 64.  Wimg: nr_gemm16_pack_w_split (per block of 128 output columns [W_hi | W_lo], rows past N zero).
+ * mode: 0 linear, 1 softplus100 (+ out2 = its derivative), 2 scale (y = aux_a * acc: the reverse sweep), 4 relu, 5 sigmoid.
+ * Y fp16 (y_half) with the lo part of the result lo_off columns to the right of the hi part (lo_off = 0: hi only), or fp32. */
 int nr_gemm16_split(const void* A, int32_t lda, const void* Wimg, const float* bias, int64_t M, int32_t N, int32_t K, void* Y,
-                    int32_t ldy, int32_t y_half, int32_t lo_off, int32_t mode, void* out2, int32_t ld_o2, void* stream);
+                    int32_t ldy, int32_t y_half, int32_t lo_off, int32_t mode, void* out2, int32_t ld_o2, const void* aux_a,
+                    int32_t ld_a, void* stream);
 /* The weight side of nr_gemm16_split for a fp32 matrix W [N, ldw]: all its column blocks in one launch (img:
  * nr_gemm16_pack_w_split_bytes). */
 size_t nr_gemm16_pack_w_split_bytes(int32_t N, int32_t K);
@@ -466,7 +467,8 @@ int nr_colsum16(const void* A, int32_t lda, int64_t rows, int32_t N, float scale
 int nr_pe16(const float* x, int64_t n, int32_t multires, void* e, int32_t ld, int32_t width, void* e2, int32_t ld2,
             int32_t off2, void* stream);
 int nr_pe_jac_t(const float* x, int64_t n, int32_t multires, const float* g0, int32_t ldg0, const void* ge, int32_t ldge,
-                float* nabla, void* stream);
+                int32_t ge_lo_off /* != 0: ge is a (hi, lo) pair, the lo part that many columns to the right */, float* nabla,
+                void* stream);
 int nr_pe_jac(const float* x, int64_t n, int32_t multires, const float* nbar, float scale, void* gbar, int32_t ld,
               int32_t width, void* g2, int32_t ld2, int32_t off2, void* stream);
 

@@ -119,12 +119,12 @@ _SIGNATURES = {
     "nr_gemm16_pack_w": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "nr_gemm16_tn": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _I32, _F, _P]),
     "nr_colsum16": (C.c_int, [_P, _I32, _I64, _I32, _F, _P, _P]),
-    "nr_gemm16_split": (C.c_int, [_P, _I32, _P, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _I32, _P]),
+    "nr_gemm16_split": (C.c_int, [_P, _I32, _P, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _I32, _P, _I32, _P]),
     "nr_gemm16_pack_w_split_bytes": (_SZ, [_I32, _I32]),
     "nr_gemm16_pack_w_split": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "nr_pe16_split": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _I32, _P, _I32, _I32, _I32, _P]),
     "nr_pe16": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _I32, _I32, _P]),
-    "nr_pe_jac_t": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _P, _P]),
+    "nr_pe_jac_t": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _P, _P]),
     "nr_pe_jac": (C.c_int, [_P, _I64, _I32, _P, _F, _P, _I32, _I32, _P, _I32, _I32, _P]),
     "nr_weight_norm": (C.c_int, [_P, _I32, _I64, _I32, _P]),
     "nr_sphere_intersection": (C.c_int, [_P, _P, _I64, C.c_double, _P, _P, _P, _P]),

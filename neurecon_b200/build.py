@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libneurecon_b200.so")
 # test-only twin of the two fused MLP kernels, compiled with the weight producer's fault injection (-DNR_FAULT_INJECT,
 # csrc/umma.cuh); loaded by tests/test_gpu_reliability.py and tools/soak_mlp.py, never by the package
 INJECT_LIB_PATH = os.path.join(LIB_DIR, "libneurecon_b200_inject.so")
-INJECT_SOURCES = ("api.cu", "mlp_rev.cu", "mlp_umma.cu")
+INJECT_SOURCES = ("api.cu", "mlp_rev.cu", "mlp_rev_split.cu", "mlp_umma.cu")
 # self-tests and micro-architecture probes (csrc/devtools/): their own library, the production one carries only the path
 DEVTOOLS_LIB_PATH = os.path.join(LIB_DIR, "libneurecon_b200_devtools.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")

@@ -83,10 +83,12 @@ struct G16Args {
   const __half* aux_b; int ld_b;
   __half* out2; int ld_o2;
   int npad, n_kc;
-  // split-precision forward GEMMs (nr_gemm16_split): A = [hi | lo] (a_wrap physical 64-column chunks, chunk kc of the
-  // K-concatenated product [hi | lo | hi] x [W_hi | W_hi | W_lo]^T reads physical chunk kc % a_wrap), blockIdx.y = block of
-  // `npad` output columns with its own W image, lo_off = column offset of the lo part of a fp16 result (0: none)
-  int a_wrap, lo_off, w_block_bytes;
+  // split-precision forward GEMMs (nr_gemm16_split): A = [hi | lo], split_p = P 64-column chunks each; the W image of a
+  // column block holds [W_hi (P chunks) | W_lo (P chunks)]; A chunk j < P (hi) multiplies W_hi chunk j AND W_lo chunk j,
+  // A chunk P + j (lo) multiplies W_hi chunk j -- (hi + lo)(W_hi + W_lo)^T without the lo x lo term, every A chunk loaded
+  // once.  blockIdx.y = block of `npad` output columns with its own W image, lo_off = column offset of the lo part of a
+  // fp16 result (0: none)
+  int split_p, lo_off, w_block_bytes;
 };
 
 __device__ __forceinline__ uint4 pack8h(const float4& a, const float4& b) {
@@ -214,11 +216,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm16_kernel(const G16Args g
     if (lane == 0) {
       uint32_t cnt = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int kc = 0; kc < g.n_kc; ++kc, ++cnt) {
+        const int n_a = g.split_p ? 2 * g.split_p : g.n_kc;       // A chunks per tile
+        for (int kc = 0; kc < n_a; ++kc, ++cnt) {
           const uint32_t st = cnt % kAStages, ph = (cnt / kAStages) & 1u;
           umma::mbar_wait(&a_empty[st], ph ^ 1u);
           umma::mbar_arrive_expect_tx(&a_full[st], kAStageBytes);
-          tma_load_2d(sA + st * kAStageBytes, &map_a, (kc % g.a_wrap) * kKC, (int)(tile * kBM), &a_full[st]);
+          tma_load_2d(sA + st * kAStageBytes, &map_a, kc * kKC, (int)(tile * kBM), &a_full[st]);
         }
       }
     }
@@ -234,15 +237,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm16_kernel(const G16Args g
       umma::mbar_wait(&acc_free[buf], ((it >> 1) & 1u) ^ 1u);
       umma::tc_fence_after();
       const uint32_t d_addr = tmem_base + buf * 256u;
-      for (int kc = 0; kc < g.n_kc; ++kc, ++cnt) {
+      const int P = g.split_p, n_a = P ? 2 * P : g.n_kc;
+      for (int kc = 0; kc < n_a; ++kc, ++cnt) {
         const uint32_t st = cnt % kAStages, ph = (cnt / kAStages) & 1u;
         umma::mbar_wait(&a_full[st], ph);
         umma::tc_fence_after();
-        const uint32_t a_lo = a_lo0 + st * (kAStageBytes >> 4), w_lo = w_lo0 + (uint32_t)kc * (w_chunk_bytes >> 4);
+        const uint32_t a_lo = a_lo0 + st * (kAStageBytes >> 4);
+        const int wc = (P && kc >= P) ? kc - P : kc;          // split: a lo chunk meets W_hi
+        const uint32_t w_lo = w_lo0 + (uint32_t)wc * (w_chunk_bytes >> 4);
         if (umma::elect_one()) {
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks)
             umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2 * ks, hi), umma::desc64(w_lo + 2 * ks, hi), idesc, (kc | (int)ks) ? 1u : 0u);
+          if (P && kc < P) {                                  // split: a hi chunk also meets W_lo
+            const uint32_t w2 = w_lo0 + (uint32_t)(P + kc) * (w_chunk_bytes >> 4);
+#pragma unroll
+            for (uint32_t ks = 0; ks < 4; ++ks)
+              umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2 * ks, hi), umma::desc64(w2 + 2 * ks, hi), idesc, 1u);
+          }
           umma::mma_commit(&a_empty[st]);
         }
         __syncwarp();
@@ -498,15 +510,16 @@ __global__ void gemm16_pack_w_kernel(const float* __restrict__ W, int ldw, int N
   *reinterpret_cast<uint4*>(img + (size_t)kc * npad * 128 + (n >> 3) * 1024 + (n & 7) * 128 + ((c8 ^ (n & 7)) << 4)) = pack8h(a, b);
 }
 
-// [W_hi | W_hi | W_lo] of nr_gemm16_split, all column blocks of a weight matrix in one launch: image = n_blocks x
-// (3 Kp / 64 chunks) x [64 rows x 64 k] fp16, swizzled; hi = fp16(w), lo = fp16(w - hi)
+// [W_hi | W_lo] of nr_gemm16_split, all column blocks of a weight matrix in one launch: image = n_blocks x
+// (2 Kp / 64 chunks) x [128 rows x 64 k] fp16, swizzled; hi = fp16(w), lo = fp16(w - hi)
+constexpr int kSplitBlock = 128;      // output columns per CTA of nr_gemm16_split
 __global__ void gemm16_pack_w_split_kernel(const float* __restrict__ W, int ldw, int N, int K, int kp, int n_blocks,
                                            uint8_t* __restrict__ img) {
-  const int n_kc = 3 * kp / kKC, per_part = kp / kKC;
+  const int n_kc = 2 * kp / kKC, per_part = kp / kKC;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_blocks * n_kc * 64 * 8) return;
-  const int c8 = idx & 7, r = (idx >> 3) & 63, kc = (idx >> 9) % n_kc, b = (idx >> 9) / n_kc;
-  const int part = kc / per_part, k0 = (kc % per_part) * kKC + c8 * 8, n = 64 * b + r;
+  if (idx >= n_blocks * n_kc * kSplitBlock * 8) return;
+  const int c8 = idx & 7, r = (idx >> 3) & (kSplitBlock - 1), kc = (idx >> 10) % n_kc, b = (idx >> 10) / n_kc;
+  const int part = kc / per_part, k0 = (kc % per_part) * kKC + c8 * 8, n = kSplitBlock * b + r;
   float4 a4, b4;
   load8(W + (size_t)n * ldw + k0, n < N ? K - k0 : 0, a4, b4);
   float v[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
@@ -514,14 +527,14 @@ __global__ void gemm16_pack_w_split_kernel(const float* __restrict__ W, int ldw,
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    if (part < 2) {
+    if (part == 0) {
       o[j] = *reinterpret_cast<const uint32_t*>(&h);
     } else {
       const float2 hf = __half22float2(h);
       o[j] = umma::pack_f16(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
     }
   }
-  *reinterpret_cast<uint4*>(img + ((size_t)b * n_kc + kc) * (64 * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4)) =
+  *reinterpret_cast<uint4*>(img + ((size_t)b * n_kc + kc) * (kSplitBlock * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4)) =
       make_uint4(o[0], o[1], o[2], o[3]);
 }
 
@@ -573,7 +586,7 @@ __global__ void pe16_kernel(const float* __restrict__ x, int64_t n, int multires
 }
 // nabla[p, c] = sum_j dPE_j/dx_c (g0[p, j] + ge[p, j])          (g0 fp32 [n, ldg0]; ge fp16 view or NULL)
 __global__ void pe_jac_t_kernel(const float* __restrict__ x, int64_t n, int multires, int pe_dim, const float* __restrict__ g0,
-                                int ldg0, const __half* __restrict__ ge, int ldge, float* __restrict__ nabla) {
+                                int ldg0, const __half* __restrict__ ge, int ldge, int ge_lo_off, float* __restrict__ nabla) {
   const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (p >= n) return;
   const float x3[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
@@ -582,7 +595,7 @@ __global__ void pe_jac_t_kernel(const float* __restrict__ x, int64_t n, int mult
     float v, jac; int comp;
     pe_and_jac(j, multires, x3, v, comp, jac);
     float gv = g0[(size_t)p * ldg0 + j];
-    if (ge) gv += __half2float(ge[(size_t)p * ldge + j]);
+    if (ge) gv += __half2float(ge[(size_t)p * ldge + j]) + (ge_lo_off ? __half2float(ge[(size_t)p * ldge + ge_lo_off + j]) : 0.0f);
     acc[comp] += jac * gv;
   }
   nabla[3 * p] = acc[0]; nabla[3 * p + 1] = acc[1]; nabla[3 * p + 2] = acc[2];
@@ -623,14 +636,14 @@ extern "C" int nr_gemm16_pack_w(const float* W, int32_t ldw, int32_t N, int32_t 
 
 extern "C" size_t nr_gemm16_pack_w_split_bytes(int32_t N, int32_t K) {
   const int kp = (K + kKC - 1) / kKC * kKC;
-  return (size_t)((N + 63) / 64) * (3 * kp / kKC) * 64 * 128;
+  return (size_t)((N + kSplitBlock - 1) / kSplitBlock) * (2 * kp / kKC) * kSplitBlock * 128;
 }
 
 extern "C" int nr_gemm16_pack_w_split(const float* W, int32_t ldw, int32_t N, int32_t K, void* img, void* stream) {
   NR_CHECK_ARG(W && img && N >= 1 && K >= 1 && (ldw & 3) == 0 && ldw >= K, "nr_gemm16_pack_w_split: bad arguments");
   NR_CHECK_ARG((((uintptr_t)W | (uintptr_t)img) & 15) == 0, "nr_gemm16_pack_w_split: 16-byte alignment");
-  const int kp = (K + kKC - 1) / kKC * kKC, n_blocks = (N + 63) / 64;
-  const int64_t total = (int64_t)n_blocks * (3 * kp / kKC) * 64 * 8;
+  const int kp = (K + kKC - 1) / kKC * kKC, n_blocks = (N + kSplitBlock - 1) / kSplitBlock;
+  const int64_t total = (int64_t)n_blocks * (2 * kp / kKC) * kSplitBlock * 8;
   gemm16_pack_w_split_kernel<<<(unsigned)nr_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(W, ldw, N, K, kp, n_blocks, (uint8_t*)img);
   NR_CHECK_LAUNCH("gemm16_pack_w_split_kernel");
   return NR_OK;
@@ -659,7 +672,6 @@ extern "C" int nr_gemm16(const void* A, int32_t lda, const float* W, int32_t ldw
             y_half, mode, (const __half*)aux_a, ld_a, (const __half*)aux_b, ld_b, (__half*)out2, ld_o2, 0, 0, 0, 0, 0};
   g.npad = (N + 15) / 16 * 16;
   g.n_kc = (K + kKC - 1) / kKC;
-  g.a_wrap = g.n_kc;
   NR_CHECK_ARG(g.npad <= 256, "nr_gemm16: N=%d > 256", N);
   const size_t fixed = 1024 + (size_t)g.n_kc * g.npad * 128 + 256;
   NR_CHECK_ARG(fixed + 3 * kAStageBytes <= 227 * 1024, "nr_gemm16: W (%d x %d) does not fit in shared memory", N, K);
@@ -688,18 +700,21 @@ extern "C" int nr_gemm16(const void* A, int32_t lda, const float* W, int32_t ldw
   return NR_OK;
 }
 
-// Split-precision forward GEMM:  Y = epilogue((A_hi + A_lo) (W_hi + W_lo)^T) without the lo x lo term, as ONE K-concatenated
-// product [A_hi | A_lo | A_hi] x [W_hi | W_hi | W_lo]^T.  A: fp16 rows [M, lda] holding [hi (Kp columns) | lo (Kp columns)],
-// Kp = K rounded up to 64; Wimg: for each block of 64 output columns the image nr_gemm16_pack_w makes of the fp32 matrix
-// [W_hi | W_hi | W_lo] (64 x 3 Kp); Y fp16 with the lo part of the result lo_off columns to the right (lo_off = 0: hi only),
-// or fp32.  grid = (tiles, column blocks): the blocks of a row tile run on different SMs at the same time and share its A
-// chunks through L2.
+// Split-precision forward GEMM:  Y = epilogue((A_hi + A_lo) (W_hi + W_lo)^T) without the lo x lo term, accumulated in ONE
+// TMEM accumulator: every A chunk is loaded once, a hi chunk multiplies the W_hi and the W_lo chunk of its k range, a lo chunk
+// the W_hi chunk.  A: fp16 rows [M, lda] holding [hi (Kp columns) | lo (Kp columns)], Kp = K rounded up to 64; Wimg:
+// nr_gemm16_pack_w_split (per block of 128 output columns [W_hi | W_lo]); Y fp16 with the lo part of the result lo_off columns
+// to the right (lo_off = 0: hi only), or fp32.  grid = (tiles, column blocks): the blocks of a row tile run on different SMs at
+// the same time and share its A chunks through L2.
 extern "C" int nr_gemm16_split(const void* A, int32_t lda, const void* Wimg, const float* bias, int64_t M, int32_t N, int32_t K,
                                void* Y, int32_t ldy, int32_t y_half, int32_t lo_off, int32_t mode, void* out2, int32_t ld_o2,
-                               void* stream) {
+                               const void* aux_a, int32_t ld_a, void* stream) {
   NR_CHECK_ARG(A && Wimg && Y && M >= 0 && N >= 1 && K >= 1, "nr_gemm16_split: bad arguments");
-  NR_CHECK_ARG(mode == G_LINEAR || mode == G_SOFTPLUS || mode == G_RELU || mode == G_SIGMOID, "nr_gemm16_split: mode=%d", mode);
-  const int kp = (K + kKC - 1) / kKC * kKC, n_blocks = (N + 63) / 64, n16 = (N + 15) & ~15;
+  NR_CHECK_ARG(mode == G_LINEAR || mode == G_SOFTPLUS || mode == G_RELU || mode == G_SIGMOID || mode == G_SCALE,
+               "nr_gemm16_split: mode=%d", mode);
+  NR_CHECK_ARG(mode != G_SCALE || aux_a, "nr_gemm16_split: G_SCALE needs aux_a");
+  NR_CHECK_ARG(!aux_a || (ld_a % 16 == 0 && ld_a >= ((N + 15) & ~15) && ((uintptr_t)aux_a & 31) == 0), "nr_gemm16_split: aux_a");
+  const int kp = (K + kKC - 1) / kKC * kKC, n_blocks = (N + kSplitBlock - 1) / kSplitBlock, n16 = (N + 15) & ~15;
   NR_CHECK_ARG(lda % 16 == 0 && lda >= 2 * kp, "nr_gemm16_split: lda=%d must cover [hi | lo] = 2 x %d columns", lda, kp);
   NR_CHECK_ARG(ldy % (y_half ? 16 : 4) == 0 && ldy >= (lo_off ? lo_off + n16 : n16) && (lo_off == 0 || (y_half && lo_off % 16 == 0 && lo_off >= n16)),
                "nr_gemm16_split: ldy / lo_off");
@@ -708,15 +723,15 @@ extern "C" int nr_gemm16_split(const void* A, int32_t lda, const void* Wimg, con
   NR_CHECK_ARG(mode != G_SOFTPLUS || out2, "nr_gemm16_split: G_SOFTPLUS needs out2");
   NR_CHECK_ARG(!out2 || (ld_o2 % 16 == 0 && ld_o2 >= n16), "nr_gemm16_split: ld_o2");
   if (M == 0) return NR_OK;
-  G16Args g{(const __half*)A, lda, nullptr, 0, (const uint8_t*)Wimg, 3, bias, M, N, 3 * kp, Y, ldy, y_half, mode, nullptr, 0, nullptr, 0,
-            (__half*)out2, ld_o2, 0, 0, 0, 0, 0};
-  g.npad = 64;
-  g.n_kc = 3 * kp / kKC;
-  g.a_wrap = 2 * kp / kKC;
+  G16Args g{(const __half*)A, lda, nullptr, 0, (const uint8_t*)Wimg, 3, bias, M, N, 2 * kp, Y, ldy, y_half, mode, (const __half*)aux_a,
+            ld_a, nullptr, 0, (__half*)out2, ld_o2, 0, 0, 0, 0, 0};
+  g.npad = kSplitBlock;
+  g.n_kc = 2 * kp / kKC;          // W chunks of a block: [W_hi | W_lo]
+  g.split_p = kp / kKC;
   g.lo_off = lo_off;
   g.w_block_bytes = g.n_kc * g.npad * 128;
   const size_t fixed = 1024 + (size_t)g.n_kc * g.npad * 128 + 256;
-  NR_CHECK_ARG(fixed + 3 * kAStageBytes <= 227 * 1024, "nr_gemm16_split: W (64 x %d) does not fit in shared memory", 3 * kp);
+  NR_CHECK_ARG(fixed + 3 * kAStageBytes <= 227 * 1024, "nr_gemm16_split: W (128 x %d) does not fit in shared memory", 2 * kp);
   g.a_stages = (int)((227 * 1024 - fixed) / kAStageBytes);
   if (g.a_stages > kMaxAStages) g.a_stages = kMaxAStages;
   const size_t smem = fixed + (size_t)g.a_stages * kAStageBytes;
@@ -737,7 +752,7 @@ extern "C" int nr_gemm16_split(const void* A, int32_t lda, const void* Wimg, con
   } while (0)
 #define NR_G16S_CASE(MODE_) case MODE_: if (y_half) NR_G16S_LAUNCH(MODE_, true); else NR_G16S_LAUNCH(MODE_, false); break
   switch (mode) {
-    NR_G16S_CASE(G_LINEAR); NR_G16S_CASE(G_SOFTPLUS); NR_G16S_CASE(G_RELU); NR_G16S_CASE(G_SIGMOID);
+    NR_G16S_CASE(G_LINEAR); NR_G16S_CASE(G_SOFTPLUS); NR_G16S_CASE(G_RELU); NR_G16S_CASE(G_SIGMOID); NR_G16S_CASE(G_SCALE);
     default: break;
   }
   NR_CHECK_LAUNCH("gemm16_kernel (split)");
@@ -806,12 +821,12 @@ extern "C" int nr_pe16_split(const float* x, int64_t n, int32_t multires, void* 
 }
 
 extern "C" int nr_pe_jac_t(const float* x, int64_t n, int32_t multires, const float* g0, int32_t ldg0, const void* ge,
-                           int32_t ldge, float* nabla, void* stream) {
+                           int32_t ldge, int32_t ge_lo_off, float* nabla, void* stream) {
   const int pe_dim = multires < 0 ? 3 : 3 + 6 * multires;
   NR_CHECK_ARG(x && g0 && nabla && n >= 0 && ldg0 >= pe_dim, "nr_pe_jac_t: bad arguments");
   if (n == 0) return NR_OK;
   pe_jac_t_kernel<<<(unsigned)nr_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(x, n, multires < 0 ? 0 : multires, pe_dim, g0, ldg0,
-                                                                            (const __half*)ge, ldge, nabla);
+                                                                            (const __half*)ge, ldge, ge_lo_off, nabla);
   NR_CHECK_LAUNCH("pe_jac_t_kernel");
   return NR_OK;
 }

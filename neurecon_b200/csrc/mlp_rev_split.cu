@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_split_kernel(const __grid
           for (int c = 0; c < nch; ++c, ++cnt) {
             const uint32_t stage = cnt & (kStages - 1);
             wait_tag(&w_empty[stage], ((cnt >> kStagesLog2) & 1u) ^ 1u, 1000 + s);
+            NR_INJECT_DELAY(P.debug_flags, P.steps[s].n_mt, t);
             if (umma::elect_one()) {
               umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
               umma::bulk_g2s(smem + SmemSplit::ring + stage * kChunkBytes, src + (size_t)c * kChunkBytes, kChunkBytes,

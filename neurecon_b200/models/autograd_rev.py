@@ -81,10 +81,11 @@ class _PackedSplit:
                    "gemm16_pack_w_split")
 
 
-def _gemm16_split(A, Wp, bias, n, N, K, Y, y_half, lo_off, mode, out2=None):
+def _gemm16_split(A, Wp, bias, n, N, K, Y, y_half, lo_off, mode, out2=None, aux_a=None):
     _lib.check(_lib.get_lib().nr_gemm16_split(
         _lib.ptr(A), A.stride(0), _lib.ptr(Wp.img), _lib.ptr(bias), n, N, K, _lib.ptr(Y), Y.stride(0), int(y_half), int(lo_off), mode,
-        _lib.ptr(out2), 0 if out2 is None else out2.stride(0), _lib.stream_ptr(A.device)), "gemm16_split")
+        _lib.ptr(out2), 0 if out2 is None else out2.stride(0), _lib.ptr(aux_a), 0 if aux_a is None else aux_a.stride(0),
+        _lib.stream_ptr(A.device)), "gemm16_split")
 
 
 def supported(dims, skip, multires):
@@ -158,21 +159,36 @@ class SdfRevFn(torch.autograd.Function):
             # ---- reverse sweep: the normal
             Wts = [None] * L
             P = [None] * D
-            P[D - 1] = (S[D - 1].float() * Ws[D][0:1, :WIDTH]).half()
+            # split: the normal feeds the radiance net, whose ReLU masks flip on 1e-4 errors of a pre-activation -- the reverse
+            # sweep's rows are (hi, lo) pairs too ([n, 512]; everything downstream reads the hi halves through the row stride)
+            p_last = S[D - 1].float() * Ws[D][0:1, :WIDTH]
+            if split:
+                P[D - 1] = torch.empty(n, 2 * WIDTH, **h16)
+                P[D - 1][:, :WIDTH] = p_last
+                P[D - 1][:, WIDTH:] = p_last - P[D - 1][:, :WIDTH].float()
+            else:
+                P[D - 1] = p_last.half()
             for l in range(D - 1, 0, -1):
                 out_l, in_l = dims[l]
-                Wts[l] = _pad4c(Ws[l][:, :in_l].t())                            # the reverse sweep and the backprop use these
-                if _PACK:
-                    Wts[l] = _Packed(Wts[l], in_l, out_l)
-                P[l - 1] = torch.empty(n, WIDTH, **h16)
-                _gemm16(P[l], Wts[l], None, n, in_l, out_l, P[l - 1], 1, G_SCALE, aux_a=S[l - 1])
+                Wt = _pad4c(Ws[l][:, :in_l].t())                                # the reverse sweep and the backprop use these
+                Wts[l] = _Packed(Wt, in_l, out_l) if _PACK else Wt
+                if split:
+                    P[l - 1] = torch.empty(n, 2 * WIDTH, **h16)
+                    _gemm16_split(P[l], _PackedSplit(Wt, in_l, out_l), None, n, in_l, out_l, P[l - 1], 1, WIDTH, G_SCALE, aux_a=S[l - 1])
+                else:
+                    P[l - 1] = torch.empty(n, WIDTH, **h16)
+                    _gemm16(P[l], Wts[l], None, n, in_l, out_l, P[l - 1], 1, G_SCALE, aux_a=S[l - 1])
             Wts[0] = _pad4c(Ws[0][:, :pe].t())
             g0 = torch.empty(n, (pe + 15) & ~15, **f32)
-            _gemm16(P[0], Wts[0], None, n, pe, dims[0][0], g0, 0, G_LINEAR)
+            if split:
+                _gemm16_split(P[0], _PackedSplit(Wts[0], pe, dims[0][0]), None, n, pe, dims[0][0], g0, 0, 0, G_LINEAR)
+            else:
+                _gemm16(P[0], Wts[0], None, n, pe, dims[0][0], g0, 0, G_LINEAR)
             nabla = torch.empty(n, 3, **f32)
             ge = P[skip - 1][:, dims[skip - 1][0]:] if skip > 0 else None
             _lib.check(lib.nr_pe_jac_t(_lib.ptr(x), n, multires, _lib.ptr(g0), g0.stride(0), _lib.ptr(ge),
-                                       0 if ge is None else WIDTH, _lib.ptr(nabla), st), "pe_jac_t")
+                                       0 if ge is None else ge.stride(0), WIDTH if (split and ge is not None) else 0,
+                                       _lib.ptr(nabla), st), "pe_jac_t")
         ctx.state = (x, hs, S, P, Ws, Wp, Wts, dims, multires, skip, pe, n)
         return sdf, nabla, feat
 
@@ -226,7 +242,7 @@ class SdfRevFn(torch.autograd.Function):
                 _lib.check(lib.nr_gemm16_tn(_lib.ptr(Z[l]), WIDTH, _lib.ptr(hs[l]), hs[l].stride(0), n, N, K, _lib.ptr(dW),
                                             dW.stride(0), inv, st), "gemm16_tn")
                 if adj:
-                    _lib.check(lib.nr_gemm16_tn(_lib.ptr(P[l]), WIDTH, _lib.ptr(G[l]), G[l].stride(0), n, N, K, _lib.ptr(dW),
+                    _lib.check(lib.nr_gemm16_tn(_lib.ptr(P[l]), P[l].stride(0), _lib.ptr(G[l]), G[l].stride(0), n, N, K, _lib.ptr(dW),
                                                 dW.stride(0), inv, st), "gemm16_tn")
                 db = torch.zeros(N, **f32)
                 _lib.check(lib.nr_colsum16(_lib.ptr(Z[l]), WIDTH, n, N, inv, _lib.ptr(db), st), "colsum16")

@@ -25,3 +25,10 @@ def test_soak_back_to_back_launches():
     compared bit for bit with the first launch: a mis-fed MMA or a lost barrier phase shows as a mismatch or a trap."""
     import soak_mlp
     soak_mlp.soak(600, 1 << 20)
+
+
+def test_soak_split_precision_kernel():
+    """the same soak for the split-precision kernel (csrc/mlp_rev_split.cu: sdf + normals with the feature image, the radiance
+    pass it feeds, sdf only); its late-chunk fault injection runs in test_late_weight_chunks_change_nothing"""
+    import soak_mlp
+    soak_mlp.soak(300, 1 << 20, soak_mlp.SPLIT_PIPE)

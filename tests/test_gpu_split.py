@@ -1,5 +1,6 @@
 """Split-precision tensor tier (precision 'fp16x2', csrc/mlp_rev_split.cu): the SDF net on (hi, lo) fp16 operand pairs, held to
 the fp32 tier's bars (north_star: <= 1e-4 end to end) against the oracle and the reference's golden vectors."""
+import numpy as np
 import pytest
 import torch
 
@@ -118,3 +119,37 @@ def test_split_training_gradients_vs_fp32_tier():
     assert abs(l1 - l2) < 1e-4 * abs(l1)
     worst = max(rel_err(a, b) for a, b in zip(g2, g1))
     assert worst < 1e-2, worst
+
+
+@pytest.mark.parametrize("N,K", [(256, 256), (217, 256), (256, 39), (257, 256), (256, 289), (3, 256), (64, 64)])
+def test_gemm16_split_vs_fp64(N, K):
+    """nr_gemm16_split (the training path's split-precision forward GEMM) against a float64 product: linear output, softplus
+    output with its derivative, and the (hi, lo) pair it writes for the next layer"""
+    from neurecon_b200.models import autograd_rev as ar
+    rs = np.random.RandomState(N * 1000 + K)
+    n = 1000
+    kp = (K + 63) // 64 * 64
+    A = torch.from_numpy(rs.normal(size=(n, K)).astype(np.float32)).to(DEV)
+    W = torch.from_numpy((rs.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)).to(DEV)
+    b = torch.from_numpy(rs.normal(size=(N,)).astype(np.float32) * 0.1).to(DEV)
+    rows = torch.zeros(n, 2 * kp, dtype=torch.float16, device=DEV)
+    hi = A.half()
+    rows[:, :K] = hi
+    rows[:, kp:kp + K] = (A - hi.float()).half()
+    Wp = torch.zeros(N, (K + 3) & ~3, device=DEV)
+    Wp[:, :K] = W
+    img = ar._PackedSplit(Wp.contiguous(), N, K)
+    want = A.double() @ W.double().t() + b.double()
+    n16 = (N + 15) & ~15
+    y = torch.empty(n, n16, device=DEV)
+    ar._gemm16_split(rows, img, b, n, N, K, y, 0, 0, ar.G_LINEAR)
+    assert rel_err(y[:, :N], want) < 3e-6, rel_err(y[:, :N], want)
+    lo_off = (N + 63) // 64 * 64
+    out = torch.empty(n, 2 * lo_off, dtype=torch.float16, device=DEV)
+    S = torch.empty(n, lo_off, dtype=torch.float16, device=DEV)
+    ar._gemm16_split(rows, img, b, n, N, K, out, 1, lo_off, ar.G_SOFTPLUS, out2=S)
+    sp = torch.nn.functional.softplus(want, beta=100)
+    got = out[:, :N].double() + out[:, lo_off:lo_off + N].double()
+    assert rel_err(got, sp) < 3e-6, rel_err(got, sp)
+    assert rel_err(out[:, :N], sp) < 1e-3                                # the hi part alone is an fp16 number
+    assert rel_err(S[:, :N], torch.sigmoid(100 * want)) < 1e-3           # softplus' is kept in fp16

@@ -573,6 +573,14 @@ int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* image, size_t
                         int64_t n, float* sdf, float* nabla, float* feat, int64_t feat_ld, float* rgb,
                         const float* normal_scale, void* feat_img, void* stream);
 
+/* Weight (A-operand) images of the fused MLP kernels from a fp32 matrix W[row, k] = W[row * row_stride + k * col_stride]
+ * (strides in elements: a transposed view or a broadcast row needs no copy): chunks of [128 rows x 64 k], K-major with the
+ * 128-byte swizzle, ordered (k-chunk, M-tile); rows past `rows` and k past K are zero, k is padded to k_pad (a multiple of 64).
+ * mode 0: fp16, 1: bf16, 2: split precision -- every chunk as a (hi, lo) pair, hi = fp16(w), lo = fp16((w - hi) 2^12). */
+size_t nr_umma_pack_a_bytes(int32_t n_mt, int32_t k_pad, int32_t mode);
+int nr_umma_pack_a(const float* W, int64_t row_stride, int64_t col_stride, int32_t rows, int32_t K, int32_t n_mt, int32_t k_pad,
+                   int32_t mode, void* img, void* stream);
+
 /* sdf + d sdf / d x (+ feature) with REVERSE-mode normals, the arithmetic of ImplicitSurface.forward_with_nablas'
  * autograd.grad (models/base.py:265-282): hidden layers forward on 128-point tiles, softplus' of every unit parked in
  * `workspace` (device memory, nr_mlp_umma_reverse_workspace bytes, contents irrelevant before and after), then the

@@ -112,6 +112,8 @@ _SIGNATURES = {
     "nr_adam_step_dev": (C.c_int, [_P, _I32, _P, _F, _F, _F, _P, _P]),
     "nr_mlp_umma2_forward": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _I64, _P, _P, _P, _I64, _P, _P]),
     "nr_mlp_umma_set_trace": (C.c_int, [_P]),
+    "nr_umma_pack_a_bytes": (_SZ, [_I32, _I32, _I32]),
+    "nr_umma_pack_a": (C.c_int, [_P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "nr_mlp_split_reverse_workspace": (_SZ, [C.POINTER(UmmaProgram), _I64]),
     "nr_mlp_split_reverse": (C.c_int, [C.POINTER(UmmaProgram), _P, _SZ, _P, _SZ, _P, _I64, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
     "nr_gemm16": (C.c_int, [_P, _I32, _P, _I32, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _P]),

@@ -29,13 +29,32 @@ def _a_tile_index_on(device):
     return _A_IDX_DEV[key]
 
 
+def _pack_a_device(W, n_mt, kp, mode):
+    """nr_umma_pack_a: one launch, any strides (csrc/umma_pack.cu)"""
+    from . import _lib
+    lib = _lib.get_lib()
+    Wf = W.detach()
+    if Wf.dtype != torch.float32:
+        Wf = Wf.float()
+    rows, K = Wf.shape
+    kp64 = (kp + 63) // 64 * 64
+    img = torch.empty(int(lib.nr_umma_pack_a_bytes(n_mt, kp64, mode)) // 2, dtype=torch.int16, device=Wf.device)
+    with torch.cuda.device(Wf.device):
+        _lib.check(lib.nr_umma_pack_a(_lib.ptr(Wf), Wf.stride(0), Wf.stride(1), rows, K, n_mt, kp64, mode, _lib.ptr(img),
+                                      _lib.stream_ptr(Wf.device)), "umma_pack_a")
+    return img.view(-1, 8192)
+
+
 def pack_a_tiles(W, n_mtiles=None, k_pad=None, dtype=torch.bfloat16):
     """W: [rows, K] float tensor -> int16 tensor [n_kchunks * n_mtiles, 8192] of A tiles ordered
     (k-chunk major, M-tile minor: the order the two MMA-issuing warps consume them);
-    rows/K zero-padded to 128 / 64 multiples."""
+    rows/K zero-padded to 128 / 64 multiples.  CUDA tensors are packed by nr_umma_pack_a; the torch composition below
+    remains for CPU tensors (layout tests)."""
     rows, K = W.shape
     n_mt = n_mtiles if n_mtiles is not None else (rows + 127) // 128
     kp = k_pad if k_pad is not None else K
+    if W.is_cuda:
+        return _pack_a_device(W, n_mt, kp, 0 if dtype == torch.float16 else 1)
     n_kc = (kp + 63) // 64
     full = torch.zeros(n_mt * 128, n_kc * 64, dtype=torch.float32, device=W.device)
     full[:rows, :K] = W.float()
@@ -51,6 +70,9 @@ def pack_a_tiles_split(W, n_mtiles=None, k_pad=None):
     """Split-precision image (csrc/mlp_rev_split.cu): W = hi + 2^-12 lo with hi = fp16(W), lo = fp16((W - hi) 2^12) (scaled so
     that it is a normal fp16 number); the A tiles of both parts interleaved (hi, lo) per (k-chunk, M-tile):
     [2 * n_kchunks * n_mtiles, 8192] int16."""
+    if W.is_cuda:
+        rows, K = W.shape
+        return _pack_a_device(W, n_mtiles if n_mtiles is not None else (rows + 127) // 128, k_pad if k_pad is not None else K, 2)
     Wf = W.float()
     hi = Wf.to(torch.float16)
     lo = ((Wf - hi.float()) * 4096.0).to(torch.float16)

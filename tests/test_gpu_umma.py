@@ -1,4 +1,5 @@
 """GPU: tcgen05 / TMEM / bulk-copy plumbing of the fused MLP kernel, checked on a plain GEMM."""
+import numpy as np
 import pytest
 import torch
 
@@ -51,3 +52,26 @@ def test_umma_cta_pair_gemm(K, N, variant):
     into the peer's shared memory through DSMEM (variant bit 0); hand-off by cluster barrier or (variant bit 1) by
     release.cluster arrivals of all warps on the leader's mbarrier, as in the fused pair kernel."""
     assert _run2(K, N, variant) < 1e-5
+
+
+def test_device_packer_matches_torch_packer():
+    """nr_umma_pack_a (one launch, any strides) against the torch composition it replaces, bit for bit: plain, transposed view,
+    broadcast row (stride 0), bf16, and the (hi, lo) split image"""
+    rs = np.random.RandomState(0)
+    for rows, K, n_mt, k_pad in ((256, 256, 2, 256), (217, 39, 2, 64), (39, 256, 1, 256), (3, 130, 1, 192)):
+        W = torch.from_numpy(rs.normal(size=(rows, K)).astype(np.float32))
+        for dt in (torch.float16, torch.bfloat16):
+            want = umma_pack.pack_a_tiles(W, n_mtiles=n_mt, k_pad=k_pad, dtype=dt)
+            got = umma_pack.pack_a_tiles(W.to(DEV), n_mtiles=n_mt, k_pad=k_pad, dtype=dt)
+            assert got.shape == want.shape and torch.equal(got.cpu(), want)
+        Wt = torch.from_numpy(rs.normal(size=(K, rows)).astype(np.float32))
+        want = umma_pack.pack_a_tiles(Wt.t().contiguous(), n_mtiles=n_mt, k_pad=k_pad, dtype=torch.float16)
+        got = umma_pack.pack_a_tiles(Wt.to(DEV).t(), n_mtiles=n_mt, k_pad=k_pad, dtype=torch.float16)
+        assert torch.equal(got.cpu(), want)
+        want = umma_pack.pack_a_tiles_split(W, n_mtiles=n_mt, k_pad=k_pad)
+        got = umma_pack.pack_a_tiles_split(W.to(DEV), n_mtiles=n_mt, k_pad=k_pad)
+        assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    row = torch.from_numpy(rs.normal(size=(1, 256)).astype(np.float32))
+    want = umma_pack.pack_a_tiles(row.expand(32, 256).contiguous(), n_mtiles=1, k_pad=256, dtype=torch.float16)
+    got = umma_pack.pack_a_tiles(row.to(DEV).expand(32, 256), n_mtiles=1, k_pad=256, dtype=torch.float16)
+    assert torch.equal(got.cpu(), want)

@@ -435,7 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("NEURECON_B200_PRECISION", None),
-                    help="fp16 (default: fused tcgen05 MLP, fp16 operands, fp32 accumulate), bf16, or fp32 (SIMT tier)")
+                    help="fp16 (default: fused tcgen05 MLP, fp16 operands, fp32 accumulate), fp16x2 (split-precision tensor tier), bf16, or fp32 (SIMT tier)")
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

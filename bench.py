@@ -263,7 +263,8 @@ def hbm_rooflines(dev, hbm_peak, R=N_RAYS):
 
 
 def extra_configs(dev, rank, world, timed, precision):
-    """BASELINE.json configs 4 and 5 and two informational legs, all under this run's clock.
+    """BASELINE.json configs 2 - 5 and two informational legs, all under this run's clock.
+    config 2 / 3: VolSDF 1024-ray render + training iteration, UNISURF 2048-ray render (per GPU);
     config 4: VolSDF + NeRF++ (configs/volsdf_nerfpp_blended.yaml) full 576x768 view, the rays of ONE image split over
       the ranks by contiguous ranges (`dist_util.shard_range`; strong scaling, no collective);
     config 5: extract_surface's 512^3 lattice WITH nablas, x-planes split over the ranks.
@@ -293,6 +294,57 @@ def extra_configs(dev, rank, world, timed, precision):
             "workload": "VolSDF + NeRF++ (configs/volsdf_nerfpp_blended.yaml, beta 0.01 random init), one 576x768 view, "
                         "128 + 64 samples + 32 outside, <= 5 up-sample iterations, its %d rays split over %d rank(s)" % (N_RAYS, world)}
         del mv
+    # ---- configs 2 and 3 (BASELINE.json): VolSDF 1024-ray render and training iteration, UNISURF 2048-ray render; every
+    # rank does its own batch (weak scaling), eager (the VolSDF sampler's early exit reads one flag per iteration) ----
+    from neurecon_b200.models.frameworks import unisurf
+    from neurecon_b200.utils import train_util
+    torch.manual_seed(0)
+    mv = volsdf.VolSDF(**dict(synthetic.VOLSDF_MODEL_KWARGS, beta_init=0.01))
+    synthetic.reseed_parameters(mv, seed=3)
+    mv = mv.to(dev)
+    o2, d2 = synthetic.make_rays(1024, shell_radius=3.0 / 1.1, jitter=0.1, seed=500 + rank)
+    o2, d2 = o2.to(dev), d2.to(dev)
+    kw2 = dict(near=0.0, far=6.0, obj_bounding_radius=3.0, max_upsample_steps=6, perturb=False)
+    with torch.no_grad():
+        volsdf.volume_render(o2, d2, mv, calc_normal=True, detailed_output=False, **kw2)
+        ms_r = timed(lambda: volsdf.volume_render(o2, d2, mv, calc_normal=True, detailed_output=False, **kw2), 5) / 5
+    opt2 = train_util.FusedAdam(mv.parameters(), lr=5e-4)
+    tgt2 = torch.rand(1024, 3, device=dev)
+
+    def volsdf_iteration():
+        opt2.zero_grad(set_to_none=False)
+        rgb, _, ret = volsdf.volume_render(o2, d2, mv, detailed_output=True, **dict(kw2, perturb=True))
+        nn_ = ret["implicit_nablas"].norm(dim=-1)
+        loss = (rgb - tgt2).abs().mean() + 0.1 * ((nn_ - 1.0) ** 2).mean()            # volsdf.py:597-621 (L1 + eikonal)
+        loss.backward()
+        dist_util.allreduce_gradients(mv.parameters())
+        opt2.step()
+    for _ in range(3):
+        volsdf_iteration()
+    ms_t = timed(volsdf_iteration, 5) / 5
+    out["config2_volsdf_1024"] = {
+        "render_ms": ms_r, "render_rays_per_s": world * 1024 / (ms_r * 1e-3), "train_step_ms": ms_t,
+        "train_rays_per_s": world * 1024 / (ms_t * 1e-3), "scaling": "weak",
+        "workload": "VolSDF (configs/volsdf.yaml, beta 0.01 random init), 1024 rays per GPU: error-bounded beta up-sampling render "
+                    "(128 + 64 samples, <= 6 iterations), and one training iteration (render under autograd, L1 + eikonal, backward "
+                    "incl. ln_beta, gradient all-reduce, Adam), eager"}
+    del mv, opt2
+    torch.manual_seed(0)
+    mu = unisurf.UNISURF(**synthetic.UNISURF_MODEL_KWARGS)
+    synthetic.reseed_parameters(mu, seed=4)
+    mu = mu.to(dev)
+    o3, d3 = synthetic.make_rays(2048, shell_radius=3.0, jitter=0.25, seed=600 + rank)
+    o3, d3 = o3[None].to(dev), d3[None].to(dev)
+    with torch.no_grad():
+        kw3 = dict(batched=True, calc_normal=True, detailed_output=False, perturb=False)
+        unisurf.volume_render(o3, d3, mu, **kw3)
+        ms_u = timed(lambda: unisurf.volume_render(o3, d3, mu, **kw3), 5) / 5
+    out["config3_unisurf_2048"] = {
+        "render_ms": ms_u, "render_rays_per_s": world * 2048 / (ms_u * 1e-3), "scaling": "weak",
+        "workload": "UNISURF (configs/unisurf.yaml), 2048 rays per GPU: 256-step root finding + 8 secant steps + interval sampling "
+                    "(64 + 32 samples), render"}
+    del mu
+    with torch.no_grad():
         # ---- config 5 ----
         m = build_model(1, dev)
         GN = 512

@@ -196,18 +196,21 @@ int nr_grid_points(int64_t i0, int64_t count, int32_t N, double volume_size, int
  * (index + t) * spacing per axis, every crossing ONE vertex shared by the triangles around it; case table =
  * neurecon_b200/mc_tables.py (face-consistent disambiguation: closed meshes).  Canonical output order (vertices by owner
  * lattice point then axis, triangles by cell then table order), so a CPU restatement reproduces both arrays bit for bit.
- * nr_mc_count: flags / cases [Nx*Ny*Nz] u8, vbase / fbase [Nx*Ny*Nz] i32 (first vertex of a point, first triangle of a
- *   cell), totals: 2 x int64 ON THE DEVICE (vertices, triangles) -- the one number the host must read to allocate outputs.
- *   n_tris: the table's u8[256] triangle counts on the device; workspace: nr_mc_count_workspace bytes.
+ * nr_mc_count: flags / cases [Nx*Ny*Nz] u8, vlocal [Nx*Ny*Nz] u16 (a point's first vertex inside its block of 256 points),
+ *   block_v / block_f [nr_mc_blocks] i32 (first vertex / triangle of a block, after the scan), totals: 2 x int64 ON THE DEVICE
+ *   (vertices, triangles) -- the one number the host must read to allocate outputs.  n_tris: the table's u8[256] triangle
+ *   counts on the device; workspace: nr_mc_count_workspace bytes.
  * nr_mc_generate: verts [V,3] f32, faces [F,3] i32; tri_table: the table's int8 [256][32] on the device; ascent != 0
  *   flips the winding (default: right-hand normals point towards decreasing values, skimage's 'descent'). */
 size_t nr_mc_count_workspace(int32_t Nx, int32_t Ny, int32_t Nz);
+int64_t nr_mc_blocks(int32_t Nx, int32_t Ny, int32_t Nz);
 int nr_mc_count(const float* vol, int32_t Nx, int32_t Ny, int32_t Nz, float level, const uint8_t* n_tris, uint8_t* flags,
-                uint8_t* cases, int32_t* vbase, int32_t* fbase, int64_t* totals, void* workspace, size_t workspace_bytes,
-                void* stream);
+                uint8_t* cases, uint16_t* vlocal, int32_t* block_v, int32_t* block_f, int64_t* totals, void* workspace,
+                size_t workspace_bytes, void* stream);
 int nr_mc_generate(const float* vol, int32_t Nx, int32_t Ny, int32_t Nz, float level, float spacing_x, float spacing_y,
-                   float spacing_z, int32_t ascent, const uint8_t* flags, const uint8_t* cases, const int32_t* vbase,
-                   const int32_t* fbase, const int8_t* tri_table, float* verts, int32_t* faces, void* stream);
+                   float spacing_z, int32_t ascent, const uint8_t* flags, const uint8_t* cases, const uint16_t* vlocal,
+                   const int32_t* block_v, const int32_t* block_f, const uint8_t* n_tris, const int8_t* tri_table, float* verts,
+                   int32_t* faces, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * NeuS -- models/frameworks/neus.py

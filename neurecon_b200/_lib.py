@@ -83,8 +83,9 @@ _SIGNATURES = {
     "nr_neus_ray_setup": (C.c_int, [_P, _P, _I64, _F, _F, _F, _I32, _P, _P, _P, _P, _P, _P]),
     "nr_neus_upsample_step": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nr_mc_count_workspace": (_SZ, [_I32, _I32, _I32]),
-    "nr_mc_count": (C.c_int, [_P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "nr_mc_generate": (C.c_int, [_P, _I32, _I32, _I32, _F, _F, _F, _F, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nr_mc_blocks": (_I64, [_I32, _I32, _I32]),
+    "nr_mc_count": (C.c_int, [_P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "nr_mc_generate": (C.c_int, [_P, _I32, _I32, _I32, _F, _F, _F, _F, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nr_neus_sdf_to_w": (C.c_int, [_P, _F, _I64, _I32, _P, _P]),
     "nr_neus_outside_points": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P]),
     "nr_neus_composite_bg": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P,

@@ -68,14 +68,17 @@ def marching_cubes(volume, level=0.0, spacing=(1.0, 1.0, 1.0), gradient_directio
     tri, cnt = _mc_tables(dev)
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
+        nb = int(lib.nr_mc_blocks(Nx, Ny, Nz))
         flags = torch.empty(n, dtype=torch.uint8, device=dev)
         cases = torch.empty(n, dtype=torch.uint8, device=dev)
-        vbase = torch.empty(n, dtype=torch.int32, device=dev)
-        fbase = torch.empty(n, dtype=torch.int32, device=dev)
+        vlocal = torch.empty(n, dtype=torch.int16, device=dev)              # u16 payload
+        block_v = torch.empty(nb, dtype=torch.int32, device=dev)
+        block_f = torch.empty(nb, dtype=torch.int32, device=dev)
         totals = torch.empty(2, dtype=torch.int64, device=dev)
         ws = _lib.workspace(lib.nr_mc_count_workspace(Nx, Ny, Nz), dev)
         _lib.check(lib.nr_mc_count(_lib.ptr(vol), Nx, Ny, Nz, float(level), _lib.ptr(cnt), _lib.ptr(flags), _lib.ptr(cases),
-                                   _lib.ptr(vbase), _lib.ptr(fbase), _lib.ptr(totals), _lib.ptr(ws), ws.numel(), st), "mc_count")
+                                   _lib.ptr(vlocal), _lib.ptr(block_v), _lib.ptr(block_f), _lib.ptr(totals), _lib.ptr(ws),
+                                   ws.numel(), st), "mc_count")
         V, F = (int(t) for t in totals.tolist())
         verts = torch.empty(V, 3, dtype=torch.float32, device=dev)
         faces = torch.empty(F, 3, dtype=torch.int32, device=dev)
@@ -83,8 +86,8 @@ def marching_cubes(volume, level=0.0, spacing=(1.0, 1.0, 1.0), gradient_directio
             sp = [float(v) for v in spacing]
             _lib.check(lib.nr_mc_generate(_lib.ptr(vol), Nx, Ny, Nz, float(level), sp[0], sp[1], sp[2],
                                           1 if gradient_direction == "ascent" else 0, _lib.ptr(flags), _lib.ptr(cases),
-                                          _lib.ptr(vbase), _lib.ptr(fbase), _lib.ptr(tri), _lib.ptr(verts), _lib.ptr(faces), st),
-                       "mc_generate")
+                                          _lib.ptr(vlocal), _lib.ptr(block_v), _lib.ptr(block_f), _lib.ptr(cnt), _lib.ptr(tri),
+                                          _lib.ptr(verts), _lib.ptr(faces), st), "mc_generate")
     return verts, faces
 
 

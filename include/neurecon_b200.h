@@ -463,6 +463,10 @@ int nr_gemm16_pack_w_split(const float* W, int32_t ldw, int32_t N, int32_t K, vo
 /* nr_pe16 with split-precision output: lo = fp16(v - hi) lo_off (lo_off2 for e2) columns to the right of the hi parts. */
 int nr_pe16_split(const float* x, int64_t n, int32_t multires, void* e, int32_t ld, int32_t width, int32_t lo_off, void* e2,
                   int32_t ld2, int32_t off2, int32_t lo_off2, void* stream);
+/* dst[r, c] = fp16(scale * src[r, c]), r < n, c < ncols (fp32 rows with stride ld_src -> fp16 rows with stride ld_dst, both in
+ * elements); lo_off != 0: also the lo part fp16(scale * src - hi) lo_off columns to the right. */
+int nr_cast_cols16(const float* src, int64_t ld_src, int64_t n, int32_t ncols, float scale, void* dst, int64_t ld_dst,
+                   int32_t lo_off, void* stream);
 /* out[N] += scale * column sums of a fp16 matrix (N <= 256). */
 int nr_colsum16(const void* A, int32_t lda, int64_t rows, int32_t N, float scale, float* out, void* stream);
 /* Embedder.forward (base.py:46-64) as fp16 rows e [n, ld] (columns [pe_dim, width) zero; optionally also into e2 at

@@ -126,6 +126,7 @@ _SIGNATURES = {
     "nr_gemm16_pack_w_split_bytes": (_SZ, [_I32, _I32]),
     "nr_gemm16_pack_w_split": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "nr_pe16_split": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _I32, _P, _I32, _I32, _I32, _P]),
+    "nr_cast_cols16": (C.c_int, [_P, _I64, _I64, _I32, _F, _P, _I64, _I32, _P]),
     "nr_pe16": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _I32, _I32, _P]),
     "nr_pe_jac_t": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _P, _P]),
     "nr_pe_jac": (C.c_int, [_P, _I64, _I32, _P, _F, _P, _I32, _I32, _P, _I32, _I32, _P]),

@@ -538,6 +538,20 @@ __global__ void gemm16_pack_w_split_kernel(const float* __restrict__ W, int ldw,
       make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// dst[r, c] = fp16(scale * src[r, c]) for a block of columns (fp32 rows -> the fp16 rows of the training GEMMs), optionally the
+// lo part fp16(scale * src - hi) `lo_off` columns to the right: one pass instead of torch's mul + cast + strided copy
+__global__ void cast_cols16_kernel(const float* __restrict__ src, int64_t ld_src, int64_t n, int ncols, float scale,
+                                   __half* __restrict__ dst, int64_t ld_dst, int lo_off) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * ncols) return;
+  const int64_t r = idx / ncols;
+  const int c = (int)(idx - r * ncols);
+  const float v = scale * src[r * ld_src + c];
+  const __half h = __float2half_rn(v);
+  dst[r * ld_dst + c] = h;
+  if (lo_off) dst[r * ld_dst + lo_off + c] = __float2half_rn(v - __half2float(h));
+}
+
 // out[c] += scale * sum_r A[r, c]  (fp16 rows): block = 256 columns x 4 row lanes, grid over row slabs
 __global__ void colsum16_kernel(const __half* __restrict__ A, int lda, int64_t rows, int N, float scale, float* __restrict__ out) {
   const int c = threadIdx.x & 255, rl = threadIdx.x >> 8;
@@ -793,6 +807,16 @@ extern "C" int nr_colsum16(const void* A, int32_t lda, int64_t rows, int32_t N, 
   if (rows == 0) return NR_OK;
   colsum16_kernel<<<(unsigned)nr_cdiv(rows, 256), 1024, 0, (cudaStream_t)stream>>>((const __half*)A, lda, rows, N, scale, out);
   NR_CHECK_LAUNCH("colsum16_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_cast_cols16(const float* src, int64_t ld_src, int64_t n, int32_t ncols, float scale, void* dst, int64_t ld_dst,
+                              int32_t lo_off, void* stream) {
+  NR_CHECK_ARG(src && dst && n >= 0 && ncols >= 1 && ld_src >= 0 && ld_dst >= ncols && lo_off >= 0, "nr_cast_cols16: bad arguments");
+  if (n == 0) return NR_OK;
+  cast_cols16_kernel<<<(unsigned)nr_cdiv(n * ncols, 256), 256, 0, (cudaStream_t)stream>>>(src, ld_src, n, ncols, scale, (__half*)dst,
+                                                                                          ld_dst, lo_off);
+  NR_CHECK_LAUNCH("cast_cols16_kernel");
   return NR_OK;
 }
 

@@ -88,6 +88,18 @@ def _gemm16_split(A, Wp, bias, n, N, K, Y, y_half, lo_off, mode, out2=None, aux_
         _lib.stream_ptr(A.device)), "gemm16_split")
 
 
+def _cast_cols16(src, scale, dst, lo_off=0):
+    """dst[:, :ncols] = fp16(scale * src) (+ the lo part lo_off columns to the right) in one launch; src fp32 [n, ncols] with any
+    row stride (unit column stride), dst a column-offset view of fp16 rows"""
+    if src.dtype != torch.float32 or src.stride(-1) != 1:
+        src = src.float().contiguous()
+    if src.dim() == 1:
+        src = src.unsqueeze(1)
+    n, ncols = src.shape
+    _lib.check(_lib.get_lib().nr_cast_cols16(_lib.ptr(src), src.stride(0), n, ncols, float(scale), _lib.ptr(dst), dst.stride(0),
+                                             int(lo_off), _lib.stream_ptr(dst.device)), "cast_cols16")
+
+
 def supported(dims, skip, multires):
     """the shapes this path is written for: hidden width 256, one skip whose input is [h | PE(x)] of width 256"""
     L = len(dims)
@@ -154,20 +166,18 @@ class SdfRevFn(torch.autograd.Function):
             else:
                 _gemm16(hs[D], Ws[D][:WIDTH], bs[D][:WIDTH], n, WIDTH, WIDTH, y, 0, G_LINEAR)
                 _gemm16(hs[D], Ws[D][WIDTH:], bs[D][WIDTH:], n, 1, WIDTH, y[:, WIDTH:], 0, G_LINEAR)
-            sdf = y[:, 0].contiguous()
-            feat = y[:, 1:WIDTH + 1].contiguous()
+            sdf = y[:, 0]                      # views of y: the consumers (reshape, the radiance net's input rows) take strides
+            feat = y[:, 1:WIDTH + 1]
             # ---- reverse sweep: the normal
             Wts = [None] * L
             P = [None] * D
             # split: the normal feeds the radiance net, whose ReLU masks flip on 1e-4 errors of a pre-activation -- the reverse
             # sweep's rows are (hi, lo) pairs too ([n, 512]; everything downstream reads the hi halves through the row stride)
-            p_last = S[D - 1].float() * Ws[D][0:1, :WIDTH]
             if split:
                 P[D - 1] = torch.empty(n, 2 * WIDTH, **h16)
-                P[D - 1][:, :WIDTH] = p_last
-                P[D - 1][:, WIDTH:] = p_last - P[D - 1][:, :WIDTH].float()
+                _cast_cols16(S[D - 1].float() * Ws[D][0:1, :WIDTH], 1.0, P[D - 1], lo_off=WIDTH)
             else:
-                P[D - 1] = p_last.half()
+                P[D - 1] = S[D - 1] * Ws[D][0:1, :WIDTH].half()           # one fp16 kernel (the rows are rounded to fp16 anyway)
             for l in range(D - 1, 0, -1):
                 out_l, in_l = dims[l]
                 Wt = _pad4c(Ws[l][:, :in_l].t())                                # the reverse sweep and the backprop use these
@@ -223,9 +233,9 @@ class SdfRevFn(torch.autograd.Function):
             # ---- yb = scale * [g_sdf | g_feat] as fp16 rows
             yb = torch.zeros(n, 320, **h16)
             if g_sdf is not None:
-                yb[:, 0] = g_sdf * scale
+                _cast_cols16(g_sdf.reshape(n), scale, yb)
             if g_feat is not None:
-                yb[:, 1:WIDTH + 1] = g_feat * scale
+                _cast_cols16(g_feat, scale, yb[:, 1:])
             # ---- backprop through the forward sweep
             Z = [None] * D
             Wt_out = _pad4c(Ws[D][:, :WIDTH].t())                              # [256, 257 -> 260]
@@ -235,28 +245,36 @@ class SdfRevFn(torch.autograd.Function):
                 out_l, in_l = dims[l]
                 Z[l - 1] = torch.empty(n, WIDTH, **h16)
                 _gemm16(Z[l], Wts[l], None, n, in_l, out_l, Z[l - 1], 1, G_SCALE, aux_a=S[l - 1], aux_b=Z2[l - 1])
-            # ---- weight and bias gradients
+            # ---- weight and bias gradients (accumulated by atomics into ONE zero-filled buffer: a fill per tensor was 36 launches)
+            sizes = []
             for l in range(D):
                 N, K = dims[l]
-                dW = torch.zeros(N, (K + 3) & ~3, **f32)
+                sizes += [N * ((K + 3) & ~3), (N + 3) & ~3]
+            sizes += [(WIDTH + 1) * WIDTH, (WIDTH + 1 + 3) & ~3]
+            flat = torch.zeros(sum(sizes), **f32)
+            segs, off = [], 0
+            for sz in sizes:
+                segs.append(flat[off:off + sz])
+                off += sz
+            for l in range(D):
+                N, K = dims[l]
+                dW = segs[2 * l].view(N, (K + 3) & ~3)
                 _lib.check(lib.nr_gemm16_tn(_lib.ptr(Z[l]), WIDTH, _lib.ptr(hs[l]), hs[l].stride(0), n, N, K, _lib.ptr(dW),
                                             dW.stride(0), inv, st), "gemm16_tn")
                 if adj:
                     _lib.check(lib.nr_gemm16_tn(_lib.ptr(P[l]), P[l].stride(0), _lib.ptr(G[l]), G[l].stride(0), n, N, K, _lib.ptr(dW),
                                                 dW.stride(0), inv, st), "gemm16_tn")
-                db = torch.zeros(N, **f32)
+                db = segs[2 * l + 1][:N]
                 _lib.check(lib.nr_colsum16(_lib.ptr(Z[l]), WIDTH, n, N, inv, _lib.ptr(db), st), "colsum16")
                 grads[2 * l], grads[2 * l + 1] = dW[:, :K], db
-            dWo = torch.zeros(WIDTH + 1, WIDTH, **f32)
+            dWo = segs[2 * D].view(WIDTH + 1, WIDTH)
             _lib.check(lib.nr_gemm16_tn(_lib.ptr(yb), 320, _lib.ptr(hs[D]), hs[D].stride(0), n, WIDTH + 1, WIDTH, _lib.ptr(dWo), WIDTH, inv, st),
                        "gemm16_tn")
             if adj:
                 _lib.check(lib.nr_colsum16(_lib.ptr(G[D]), WIDTH, n, WIDTH, inv, _lib.ptr(dWo), st), "colsum16")   # sdf row
-            dbo = torch.zeros(WIDTH + 1, **f32)
-            if g_sdf is not None:
-                dbo[0] = g_sdf.sum()
-            if g_feat is not None:
-                dbo[1:] = g_feat.sum(0)
+            dbo = segs[2 * D + 1][:WIDTH + 1]                                 # column sums of yb (fp16, scaled): two launches
+            _lib.check(lib.nr_colsum16(_lib.ptr(yb), 320, n, WIDTH, inv, _lib.ptr(dbo), st), "colsum16")
+            _lib.check(lib.nr_colsum16(_lib.ptr(yb[:, WIDTH:]), 320, n, 1, inv, _lib.ptr(dbo[WIDTH:]), st), "colsum16")
             grads[2 * D], grads[2 * D + 1] = dWo, dbo
         ctx.state = None
         return (None, None, None, *grads)
@@ -296,10 +314,8 @@ class RadianceRevFn(torch.autograd.Function):
                 _lib.check(lib.nr_pe16_split(_lib.ptr(x), n, multires, _lib.ptr(a0), 2 * ld0, px, ld0, None, 0, 0, 0, st), "pe16_split")
                 _lib.check(lib.nr_pe16_split(_lib.ptr(view), n, multires_view, _lib.ptr(a0[:, px:]), 2 * ld0, pv, ld0, None, 0, 0, 0, st),
                            "pe16_split")
-                rest = torch.cat([normals.detach().float(), feat.detach().float()], dim=1)
-                rest_hi = rest.half()
-                a0[:, px + pv:in0] = rest_hi
-                a0[:, ld0 + px + pv:ld0 + in0] = rest - rest_hi.float()
+                _cast_cols16(normals.detach(), 1.0, a0[:, px + pv:], lo_off=ld0)
+                _cast_cols16(feat.detach(), 1.0, a0[:, px + pv + 3:], lo_off=ld0)
             else:
                 _lib.check(lib.nr_pe16(_lib.ptr(x), n, multires, _lib.ptr(a0), ld0, px, None, 0, 0, st), "pe16")
                 _lib.check(lib.nr_pe16(_lib.ptr(view), n, multires_view, _lib.ptr(a0[:, px:]), ld0, pv, None, 0, 0, st), "pe16")
@@ -340,12 +356,21 @@ class RadianceRevFn(torch.autograd.Function):
             N, K = dims[L - 1]
             z = torch.zeros(n, 64, **h16)
             z[:, :N] = g_rgb * rgb * (1.0 - rgb) * scale                       # through the sigmoid
+            sizes = []
+            for l in range(L):
+                N, K = dims[l]
+                sizes += [N * ((K + 3) & ~3), (N + 3) & ~3]
+            flat = torch.zeros(sum(sizes), **f32)                              # all dW / db of the net: one fill
+            segs, o_ = [], 0
+            for sz in sizes:
+                segs.append(flat[o_:o_ + sz])
+                o_ += sz
             for l in range(L - 1, -1, -1):
                 N, K = dims[l]
-                dW = torch.zeros(N, (K + 3) & ~3, **f32)
+                dW = segs[2 * l].view(N, (K + 3) & ~3)
                 _lib.check(lib.nr_gemm16_tn(_lib.ptr(z), z.stride(0), _lib.ptr(acts[l]), acts[l].stride(0), n, N, K, _lib.ptr(dW),
                                             dW.stride(0), inv, st), "gemm16_tn")
-                db = torch.zeros(N, **f32)
+                db = segs[2 * l + 1][:N]
                 _lib.check(lib.nr_colsum16(_lib.ptr(z), z.stride(0), n, N, inv, _lib.ptr(db), st), "colsum16")
                 grads[2 * l], grads[2 * l + 1] = dW[:, :K], db
                 Wt = _pad4c(Ws[l][:, :K].t())                                    # [K, N]

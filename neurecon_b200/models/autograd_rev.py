@@ -63,11 +63,12 @@ def _gemm16(A, W, bias, n, N, K, Y, y_half, mode, aux_a=None, aux_b=None, out2=N
 
 
 def split_forward():
-    """Forward sweeps on split-precision operands (csrc/gemm16.cu nr_gemm16_split): the 'fp16x2' tier's training path, or
-    NEURECON_B200_TRAIN_SPLIT=1 in the fp16 tier.  Softplus(beta=100) turns a pre-activation error dz into 25 dz on
-    softplus' and 2500 dz on softplus'' (the eikonal term's second-order path): with plain fp16 operands (dz ~ 3e-4) the
-    worst weight gradient of a NeuS step is 1e-1 off the reference's, with exact pre-activations 1e-2 (measured)."""
-    return _lib.split_tier() or os.environ.get("NEURECON_B200_TRAIN_SPLIT", "0") != "0"
+    """Forward and reverse sweeps on split-precision operands (csrc/gemm16.cu nr_gemm16_split): the training path of the
+    'fp16x2' tier and, by default, of the 'fp16' tier too; NEURECON_B200_TRAIN_SPLIT=0 keeps plain fp16 sweeps there (0.8 ms
+    faster per 512-ray step).  Softplus(beta=100) turns a pre-activation error dz into 25 dz on softplus' and 2500 dz on
+    softplus'' (the eikonal term's second-order path): with plain fp16 operands (dz ~ 3e-4) the worst weight gradient of a
+    NeuS / VolSDF / UNISURF step is 1e-1 / 3e-1 / 2e-1 off the reference's, with split sweeps 4e-3 / 3e-3 / 4e-3 (measured)."""
+    return _lib.split_tier() or os.environ.get("NEURECON_B200_TRAIN_SPLIT", "1") != "0"
 
 
 class _PackedSplit:
@@ -175,7 +176,7 @@ class SdfRevFn(torch.autograd.Function):
             # sweep's rows are (hi, lo) pairs too ([n, 512]; everything downstream reads the hi halves through the row stride)
             if split:
                 P[D - 1] = torch.empty(n, 2 * WIDTH, **h16)
-                _cast_cols16(S[D - 1].float() * Ws[D][0:1, :WIDTH], 1.0, P[D - 1], lo_off=WIDTH)
+                _cast_cols16(S[D - 1] * Ws[D][0:1, :WIDTH], 1.0, P[D - 1], lo_off=WIDTH)      # fp16 x fp32 -> fp32 in one kernel
             else:
                 P[D - 1] = S[D - 1] * Ws[D][0:1, :WIDTH].half()           # one fp16 kernel (the rows are rounded to fp16 anyway)
             for l in range(D - 1, 0, -1):

@@ -87,6 +87,21 @@ def _effective_weight(layer):
     return layer.weight
 
 
+def _effective_weights_nograd(layers, scales):
+    """effective weights of all layers (detached fp32, scale folded in): ONE launch of nr_weight_norm for weight-normed CUDA
+    layers (the images are re-packed after every optimiser step), else the torch composition"""
+    with torch.no_grad():
+        from .autograd import _fused_effective_weights
+        Ws = _fused_effective_weights(layers, scales)       # None unless every layer is weight-normed and on a CUDA device
+        if Ws is not None:
+            return [W.detach() for W in Ws]
+        out = []
+        for l, sc in zip(layers, scales):
+            W = _effective_weight(l).detach().float()
+            out.append(W * sc if sc != 1.0 else W)
+        return out
+
+
 def _param_key(module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
 
@@ -240,15 +255,17 @@ class ImplicitSurface(nn.Module):
 
         def build():
             with torch.no_grad():
-                Wl = [_effective_weight(l).detach().float() for l in self.surface_fc_layers]
+                layers = list(self.surface_fc_layers)
+                Wl = _effective_weights_nograd(layers, [1.0 / math.sqrt(2) if i in self.skips else 1.0 for i in range(len(layers))])
                 bl = [l.bias.detach().float() for l in self.surface_fc_layers]
-                for i in self.skips:
-                    Wl[i] = Wl[i] / math.sqrt(2)
                 kw = {}
                 if radiance_net is not None:
                     if radiance_net.skips:
                         raise NotImplementedError("tensor tier: RadianceNet needs skips=[]")
-                    kw = dict(rad_W=[W.detach().float() for W in radiance_net._effective_weights()],
+                    rl = list(radiance_net.layers)
+                    rW = _effective_weights_nograd(rl, [1.0] * len(rl))
+                    rW[0] = radiance_net._layer0_weight(rW[0])
+                    kw = dict(rad_W=rW,
                               rad_b=[l.bias.detach().float() for l in radiance_net.layers],
                               rad_multires=radiance_net.embed_multires,
                               rad_multires_view=radiance_net._multires_view_eff)
@@ -263,10 +280,9 @@ class ImplicitSurface(nn.Module):
 
         def build():
             with torch.no_grad():
-                Wl = [_effective_weight(l).detach().float() for l in self.surface_fc_layers]
+                layers = list(self.surface_fc_layers)
+                Wl = _effective_weights_nograd(layers, [1.0 / math.sqrt(2) if i in self.skips else 1.0 for i in range(len(layers))])
                 bl = [l.bias.detach().float() for l in self.surface_fc_layers]
-                for i in self.skips:
-                    Wl[i] = Wl[i] / math.sqrt(2)
                 net = umma_pack.UmmaNet(Wl, bl, self.embed_multires, self.skips[0] if self.skips else -1, operand="fp16",
                                         split=True)
             if not net.rev_ok(want_feat=True):

@@ -328,7 +328,29 @@ def extra_configs(dev, rank, world, timed, precision):
         "workload": "VolSDF (configs/volsdf.yaml, beta 0.01 random init), 1024 rays per GPU: error-bounded beta up-sampling render "
                     "(128 + 64 samples, <= 6 iterations), and one training iteration (render under autograd, L1 + eikonal, backward "
                     "incl. ln_beta, gradient all-reduce, Adam), eager"}
-    del mv, opt2
+    del opt2
+    # the same iteration as ONE CUDA graph: the sampler then runs sync-free (every ray through all its iterations)
+    try:
+        opt2g = train_util.FusedAdam(mv.parameters(), lr=5e-4, capturable=True)
+
+        def volsdf_iteration_g(o, d, tgt):
+            opt2g.zero_grad(set_to_none=False)
+            rgb, _, ret = volsdf.volume_render(o, d, mv, detailed_output=True, **dict(kw2, perturb=True))
+            nn_ = ret["implicit_nablas"].norm(dim=-1)
+            loss = (rgb - tgt).abs().mean() + 0.1 * ((nn_ - 1.0) ** 2).mean()
+            loss.backward()
+            dist_util.allreduce_gradients(mv.parameters())
+            opt2g.step()
+            return loss.detach()
+        gstep = train_util.CapturedStep(volsdf_iteration_g, (o2, d2, tgt2), optimizer=opt2g, warmup=3)
+        for _ in range(2):
+            gstep(o2, d2, tgt2)
+        ms_g = timed(lambda: gstep(o2, d2, tgt2), 5) / 5
+        out["config2_volsdf_1024"].update(train_step_graph_ms=ms_g, train_graph_rays_per_s=world * 1024 / (ms_g * 1e-3))
+        del gstep, opt2g
+    except Exception as e:      # informational leg
+        out["config2_volsdf_1024"]["train_step_graph_error"] = repr(e)[:200]
+    del mv
     torch.manual_seed(0)
     mu = unisurf.UNISURF(**synthetic.UNISURF_MODEL_KWARGS)
     synthetic.reseed_parameters(mu, seed=4)

@@ -105,6 +105,8 @@ def fine_sample(implicit_surface_fn, init_dvals, rays_o, rays_d, alpha_net, beta
     remaining network queries once every ray is finished (set False for a sync-free, graph-capturable run)."""
     _lib.require_cuda(init_dvals, rays_o, rays_d)
     lib = _lib.get_lib()
+    if torch.cuda.is_current_stream_capturing():
+        early_exit = False                   # a CUDA-graph capture cannot read the flag: the sync-free form (every ray, every iteration)
     prefix, N0 = init_dvals.shape[:-1], init_dvals.shape[-1]
     o = _lib.f32c(rays_o.detach().reshape(-1, 3))
     dirs = _lib.f32c(rays_d.detach().reshape(-1, 3))

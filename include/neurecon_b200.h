@@ -447,6 +447,10 @@ int nr_gemm16_pack_w(const float* W, int32_t ldw, int32_t N, int32_t K, void* im
 /* dW[N, K] += scale * G[rows, N]^T X[rows, K]; G, X fp16 rows (ldg, ldx multiples of 64), dW fp32 (atomics). */
 int nr_gemm16_tn(const void* G, int32_t ldg, const void* X, int32_t ldx, int64_t rows, int32_t N, int32_t K, float* dW,
                  int32_t lddw, float scale, void* stream);
+/* dW += scale * (G^T X + G2^T X2): two products of the same shape in one launch, one pass of atomics (the SDF layers'
+ * dW = zb^T h + p^T gb). */
+int nr_gemm16_tn2(const void* G, int32_t ldg, const void* X, int32_t ldx, const void* G2, int32_t ldg2, const void* X2,
+                  int32_t ldx2, int64_t rows, int32_t N, int32_t K, float* dW, int32_t lddw, float scale, void* stream);
 /* Split-precision forward GEMM of the training path (precision 'fp16x2'): Y = epilogue((A_hi + A_lo)(W_hi + W_lo)^T) minus
  * the lo x lo term, in one accumulator: every 64-column chunk of A is loaded once; a hi chunk multiplies the W_hi and the
  * W_lo chunk of its k range, a lo chunk the W_hi chunk.  A: fp16 rows [M, lda] = [hi (Kp columns) | lo (Kp columns)], Kp = K

@@ -41,6 +41,18 @@ int nr_probe_alu(int32_t op, int32_t threads, int32_t iters, int32_t grid, float
 /* TMEM read-rate probe: `warps` warps x iters x 4 tcgen05.ld.32x32b.x16 (2 KB each); out: [grid] int64 cycles. */
 int nr_bench_ldtm(int32_t warps, int32_t iters, int32_t grid, long long* out, float* sink, void* stream);
 
+/* Forward epilogue of mlp_rev_kernel in isolation (tools/probe_epi.py): 16 warps x iters chunks of 16 values per thread, the
+ * accumulators read from shared memory; variant 0 = shipped math + codes + stores, 1 = no stores, 2 = lower-degree
+ * polynomials, 3 = no bias FMA, 4 = scalar FFMA, 5 = math only, 6 = codes / conversions / stores only.
+ * bias: [256] floats, scratch: 32 * 8192 * grid bytes, cycles: [grid] int64. */
+int nr_probe_epi(int32_t variant, int32_t iters, int32_t grid, const float* bias, void* scratch, long long* cycles, void* stream);
+
+/* Pipe-overlap probe (tools/probe_mix.py): iters x (8 x op_a interleaved with 8 x op_b) per thread on independent registers;
+ * ops: 0 none, 1 fma.f32, 2 fma.f32x2, 3 ex2.approx, 4 lop3, 5 max.f32, 6 prmt, 7 cvt.f16x2.f32, 8 fma.f16x2, 9 add.s32,
+ * 10 fma.f32x2 with distinct operands.  cycles: [grid] int64. */
+int nr_probe_mix(int32_t op_a, int32_t op_b, int32_t threads, int32_t iters, int32_t grid, uint32_t* out, long long* cycles,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

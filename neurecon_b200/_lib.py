@@ -121,6 +121,7 @@ _SIGNATURES = {
     "nr_gemm16_pack_w_bytes": (_SZ, [_I32, _I32]),
     "nr_gemm16_pack_w": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "nr_gemm16_tn": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _I32, _F, _P]),
+    "nr_gemm16_tn2": (C.c_int, [_P, _I32, _P, _I32, _P, _I32, _P, _I32, _I64, _I32, _I32, _P, _I32, _F, _P]),
     "nr_colsum16": (C.c_int, [_P, _I32, _I64, _I32, _F, _P, _P]),
     "nr_gemm16_split": (C.c_int, [_P, _I32, _P, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _I32, _P, _I32, _P]),
     "nr_gemm16_pack_w_split_bytes": (_SZ, [_I32, _I32]),
@@ -145,6 +146,8 @@ _SIGNATURES = {
 _DEVTOOLS_SIGNATURES = {
     "nr_bench_ldtm": (C.c_int, [_I32, _I32, _I32, _P, _P, _P]),
     "nr_probe_alu": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P]),
+    "nr_probe_epi": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P]),
+    "nr_probe_mix": (C.c_int, [_I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "nr_bench_umma": (C.c_int, [_I32, _I32, _I32, _I32, _P, _I32, _P, _P]),
     "nr_selftest_umma2": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),
     "nr_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P]),

@@ -388,10 +388,16 @@ struct Tn16Args {
   int64_t chunks_per_slice;
   float scale;
   int vec4;
+  int n_pairs;
 };
 
+// n_pairs = 2: dW += scale * (G^T X + G2^T X2) -- both products accumulate in the same TMEM tile and leave through ONE pass of
+// atomics (the atomics of 146 partial sums are a third of this kernel's time: the SDF layers' dW = zb^T h + p^T gb as two
+// launches paid them twice)
 __global__ void __launch_bounds__(192, 1) gemm16_tn_kernel(const Tn16Args g, const __grid_constant__ CUtensorMap map_g,
-                                                            const __grid_constant__ CUtensorMap map_x) {
+                                                            const __grid_constant__ CUtensorMap map_x,
+                                                            const __grid_constant__ CUtensorMap map_g2,
+                                                            const __grid_constant__ CUtensorMap map_x2) {
   // warp 0: TMA producer (one thread), warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue (TMEM lane quarter = warp % 4)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -432,12 +438,16 @@ __global__ void __launch_bounds__(192, 1) gemm16_tn_kernel(const Tn16Args g, con
     if (lane == 0) {
       const int g_blocks = two_mt ? 4 : 2, x_blocks = (ncols + 63) / 64;
       uint32_t cnt = 0;
-      for (int64_t c = c_begin; c < c_end; ++c, ++cnt) {
-        const uint32_t st = cnt % kTnStages, ph = (cnt / kTnStages) & 1u;
-        umma::mbar_wait(&empty[st], ph ^ 1u);
-        umma::mbar_arrive_expect_tx(&full[st], (uint32_t)(g_blocks + x_blocks) * kTnLbo);
-        for (int b = 0; b < g_blocks; ++b) tma_load_2d(sA + st * kTnABytes + b * kTnLbo, &map_g, m0 + 64 * b, (int)(c * 64), &full[st]);
-        for (int b = 0; b < x_blocks; ++b) tma_load_2d(sB + st * kTnBBytes + b * kTnLbo, &map_x, n0 + 64 * b, (int)(c * 64), &full[st]);
+      for (int pair = 0; pair < g.n_pairs; ++pair) {
+        const CUtensorMap* mg = pair ? &map_g2 : &map_g;
+        const CUtensorMap* mx = pair ? &map_x2 : &map_x;
+        for (int64_t c = c_begin; c < c_end; ++c, ++cnt) {
+          const uint32_t st = cnt % kTnStages, ph = (cnt / kTnStages) & 1u;
+          umma::mbar_wait(&empty[st], ph ^ 1u);
+          umma::mbar_arrive_expect_tx(&full[st], (uint32_t)(g_blocks + x_blocks) * kTnLbo);
+          for (int b = 0; b < g_blocks; ++b) tma_load_2d(sA + st * kTnABytes + b * kTnLbo, mg, m0 + 64 * b, (int)(c * 64), &full[st]);
+          for (int b = 0; b < x_blocks; ++b) tma_load_2d(sB + st * kTnBBytes + b * kTnLbo, mx, n0 + 64 * b, (int)(c * 64), &full[st]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -445,7 +455,8 @@ __global__ void __launch_bounds__(192, 1) gemm16_tn_kernel(const Tn16Args g, con
     const uint32_t hi = umma::smem_desc_hi(1024);
     const uint32_t a_lo0 = umma::smem_desc_lo(umma::smem_u32(sA), kTnLbo), b_lo0 = umma::smem_desc_lo(umma::smem_u32(sB), kTnLbo);
     uint32_t cnt = 0;
-    for (int64_t c = c_begin; c < c_end; ++c, ++cnt) {
+    const int64_t n_it = (c_end - c_begin) * g.n_pairs;
+    for (int64_t c = 0; c < n_it; ++c, ++cnt) {
       const uint32_t st = cnt % kTnStages, ph = (cnt / kTnStages) & 1u;
       umma::mbar_wait(&full[st], ph);
       umma::tc_fence_after();
@@ -773,12 +784,28 @@ extern "C" int nr_gemm16_split(const void* A, int32_t lda, const void* Wimg, con
   return NR_OK;
 }
 
+static int gemm16_tn_launch(const void* G, int32_t ldg, const void* X, int32_t ldx, const void* G2, int32_t ldg2, const void* X2,
+                            int32_t ldx2, int64_t rows, int32_t N, int32_t K, float* dW, int32_t lddw, float scale, void* stream);
+
 extern "C" int nr_gemm16_tn(const void* G, int32_t ldg, const void* X, int32_t ldx, int64_t rows, int32_t N, int32_t K,
                             float* dW, int32_t lddw, float scale, void* stream) {
+  return gemm16_tn_launch(G, ldg, X, ldx, nullptr, 0, nullptr, 0, rows, N, K, dW, lddw, scale, stream);
+}
+
+extern "C" int nr_gemm16_tn2(const void* G, int32_t ldg, const void* X, int32_t ldx, const void* G2, int32_t ldg2, const void* X2,
+                             int32_t ldx2, int64_t rows, int32_t N, int32_t K, float* dW, int32_t lddw, float scale, void* stream) {
+  NR_CHECK_ARG(G2 && X2, "nr_gemm16_tn2: null pointer");
+  return gemm16_tn_launch(G, ldg, X, ldx, G2, ldg2, X2, ldx2, rows, N, K, dW, lddw, scale, stream);
+}
+
+static int gemm16_tn_launch(const void* G, int32_t ldg, const void* X, int32_t ldx, const void* G2, int32_t ldg2, const void* X2,
+                            int32_t ldx2, int64_t rows, int32_t N, int32_t K, float* dW, int32_t lddw, float scale, void* stream) {
   NR_CHECK_ARG(G && X && dW && rows >= 0 && N >= 1 && K >= 1, "nr_gemm16_tn: bad arguments");
   NR_CHECK_ARG(ldg % 64 == 0 && ldx % 64 == 0 && ldg >= N && ldx >= K && lddw >= K,
                "nr_gemm16_tn: ldg / ldx must be multiples of 64 covering N / K (pad columns finite), lddw >= K");
   NR_CHECK_ARG((((uintptr_t)G | (uintptr_t)X) & 15) == 0, "nr_gemm16_tn: 16-byte alignment");
+  NR_CHECK_ARG(!G2 || (ldg2 % 64 == 0 && ldx2 % 64 == 0 && ldg2 >= N && ldx2 >= K && (((uintptr_t)G2 | (uintptr_t)X2) & 15) == 0),
+               "nr_gemm16_tn2: second operand pair");
   if (rows == 0) return NR_OK;
   int dev = 0, sms = 0;
   NR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -789,15 +816,17 @@ extern "C" int nr_gemm16_tn(const void* G, int32_t ldg, const void* X, int32_t l
   if (slices < 1) slices = 1;
   if (slices > n_chunks) slices = n_chunks;
   Tn16Args g{(const __half*)G, ldg, (const __half*)X, ldx, rows, N, K, dW, lddw, nr_cdiv(n_chunks, slices), scale,
-             ((((uintptr_t)dW) & 15) == 0 && (lddw & 3) == 0) ? 1 : 0};
+             ((((uintptr_t)dW) & 15) == 0 && (lddw & 3) == 0) ? 1 : 0, G2 ? 2 : 1};
   slices = nr_cdiv(n_chunks, g.chunks_per_slice);
   const size_t smem = 1024 + kTnStages * (kTnABytes + kTnBBytes) + 128;
   dim3 grid((unsigned)slices, n_mt, n_nt);
-  CUtensorMap map_g, map_x;
+  CUtensorMap map_g, map_x, map_g2, map_x2;
   if (int rc = make_map(&map_g, G, rows, ldg, 64, "nr_gemm16_tn")) return rc;
   if (int rc = make_map(&map_x, X, rows, ldx, 64, "nr_gemm16_tn")) return rc;
+  if (int rc = make_map(&map_g2, G2 ? G2 : G, rows, G2 ? ldg2 : ldg, 64, "nr_gemm16_tn")) return rc;
+  if (int rc = make_map(&map_x2, X2 ? X2 : X, rows, X2 ? ldx2 : ldx, 64, "nr_gemm16_tn")) return rc;
   NR_CHECK_CUDA(cudaFuncSetAttribute(gemm16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gemm16_tn_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(g, map_g, map_x);
+  gemm16_tn_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(g, map_g, map_x, map_g2, map_x2);
   NR_CHECK_LAUNCH("gemm16_tn_kernel");
   return NR_OK;
 }

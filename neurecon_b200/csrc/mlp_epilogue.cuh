@@ -125,6 +125,32 @@ __device__ __forceinline__ void softplus_sigt2(float a0, float a1, f32x2 b144, f
   upk2(mul2(t2, splat2(0.34657359027997264f)), h0, h1);          // t ln2 / 2 = 50 z
   th = pk2(tanh_approx(h0), tanh_approx(h1));
 }
+// softplus AND its derivative from ONE transcendental, th = tanh(50 z) = 2 sigmoid(100 z) - 1 (MUFU.TANH, 2^-11 relative):
+//   softplus' - 1/2 = th / 2 comes signed out of the XU pipe (no quartic, no sign transfer), and with 1 + u = 2 / (1 + |th|)
+//   softplus(z) = relu(z) + log1p(u) / 100 = relu(z) + (ln 2 - log1p(|th|)) / 100: the same degree-3 log1p, evaluated in
+//   |th| (a free operand modifier of FFMA2), relu(t) = (t + |t|) / 2 on the FMA pipe as well.  7 FMA-pipe operations per
+//   pair of values instead of 11, no ALU-pipe operation instead of 4 (tools/probe_epi.py: 990 -> 690 cycles per 16-value
+//   chunk and warp).  |err| of softplus: 7.1e-7 (polynomial) + 2.4e-6 (th), of the derivative 2.4e-4: for consumers that
+//   round the activation to 16 bits and the derivative to 8 (mlp_rev.cu).  b50 = splat(50 bias); th = tanh(50 z) in [-1, 1].
+template <bool kReluFma>
+__device__ __forceinline__ void softplus_th2(float a0, float a1, f32x2 b50, float& sp0, float& sp1, f32x2& th) {
+  const f32x2 t2 = fma2(pk2(a0, a1), splat2(50.0f), b50);
+  float t0, t1;
+  upk2(t2, t0, t1);
+  const float h0 = tanh_approx(t0), h1 = tanh_approx(t1);
+  th = pk2(h0, h1);
+  const f32x2 x = pk2(fabsf(h0), fabsf(h1));
+  f32x2 q = fma2(x, splat2(0.05875718221068382e-2f), splat2(-0.22568579018115997e-2f));
+  q = fma2(q, x, splat2(0.4713013470172882e-2f));
+  q = fma2(q, x, splat2(-0.9974489808082581e-2f));
+  q = fma2(q, x, splat2(0.006931471805599453f));
+  if (kReluFma) {
+    q = fma2(pk2(fabsf(t0), fabsf(t1)), splat2(0.01f), q);
+    upk2(fma2(t2, splat2(0.01f), q), sp0, sp1);
+  } else {
+    upk2(fma2(pk2(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), splat2(0.02f), q), sp0, sp1);
+  }
+}
 __device__ __forceinline__ void softplus2(float a0, float a1, f32x2 b144, float& sp0, float& sp1) {
   const f32x2 t2 = fma2(pk2(a0, a1), splat2(144.26950408889634f), b144);
   float t0, t1;

@@ -55,7 +55,16 @@ struct RevArgs {
   uint8_t* feat_img;   // null, or [ceil(n/128)][64 KB]: last hidden activations as the radiance pass's operand image
   uint8_t* sig;        // [grid][2][n_sig][32 KB]
   int n_sig;
+  long long* trace;    // test twin only: [8][kTraceCap][4] (event, step * 2 + tile, clock, pair) from CTA 0 (tools/trace_rev.py)
 };
+
+constexpr int kTraceCap = 1024;
+__device__ __forceinline__ void trace_ev(long long* tr, int region, int& cnt, int ev, int st, long long pair) {
+  if (!tr || blockIdx.x != 0 || cnt >= kTraceCap) return;
+  long long* p = tr + ((size_t)region * kTraceCap + cnt) * 4;
+  p[0] = ev; p[1] = st; p[2] = clock64(); p[3] = pair;
+  ++cnt;
+}
 
 __device__ __forceinline__ void publish(uint64_t* bar) {
   umma::fence_proxy_async_smem();
@@ -69,8 +78,11 @@ __device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, int tag
 // softplus' codes: byte = 128 + round(254 (s - 1/2)) in [1, 255], exact at s = 0, 1/2 and 1.  The producer hands over
 // s - 1/2 (softplus_sigq2); fma(., 254, 1.5 * 2^23 + 128) leaves the code in the low mantissa byte, three byte permutes
 // gather four of them.
+// Forward activation: 0 = one ex2, log1p cubic + 1/(1+u) quartic on the FMA pipe (softplus_sigq2); 1 = ex2 for softplus and
+// tanh for its derivative (softplus_sigt2: two transcendentals, XU bound, measured equal to 0); 2 / 3 = ONE tanh for both
+// (softplus_th2, relu on the ALU / on the FMA pipe): profiles/r2_mlp_rev_epilogue.md
 #ifndef NR_SIG_TANH
-#define NR_SIG_TANH 0      // 1: softplus' through tanh.approx (softplus_sigt2) instead of the FMA-pipe quartic (softplus_sigq2): measured equal, see profiles/r2_mlp_rev_epilogue.md
+#define NR_SIG_TANH 3
 #endif
 #ifdef NR_FAULT_INJECT
 constexpr bool kProbe = true;     // the test twin (libneurecon_b200_inject.so) also carries the epilogue probes: debug_flags 16 / 32 / 256
@@ -194,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
     const uint32_t my_mt = warp == 1 ? 0u : 1u;
     uint32_t cnt = 0;
     uint32_t in_par = 0;
+    int tcnt = 0;
     int prev_t = -1;                   // tile slot and acc_ready parity of the previous (step, tile) visit
     uint32_t prev_par = 0;
     const uint32_t a_hi = umma::smem_desc_hi(1024), b_hi = umma::smem_desc_hi(1024);
@@ -212,6 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
           wait_tag(&in_ready[t], par, 2000 + s);
           in_par ^= 1u << t;
           umma::tc_fence_after();
+          if (kProbe && lane == 0) trace_ev(a.trace, (int)my_mt, tcnt, 11, s * 2 + t, pair);
           // RING LOCKSTEP, rule 2 (rule 1 and the story are below): a step with one M-tile is issued by warp 1 alone, also
           // from the stages whose previous chunks were warp 3's.  Before it touches them it waits for the previous
           // visit's accumulator: both issuers have committed there, so every chunk issued before this visit has landed.
@@ -225,6 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
               const uint32_t st = c & (kStages - 1);
               wait_tag(&w_full[st], (c >> kStagesLog2) & 1u, 3000 + s);
               umma::tc_fence_after();
+              if (kProbe && lane == 0 && (kc == 0 || kc + 1 == nkc)) trace_ev(a.trace, (int)my_mt, tcnt, kc == 0 ? 13 : 14, s * 2 + t, pair);
               const uint32_t a_lo = ring_lo + st * (kChunkBytes >> 4);
               if (umma::elect_one()) {
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, kc ? 1u : 0u);
@@ -238,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
           }
           if (umma::elect_one()) umma::mma_commit(&acc_ready[t]);
           __syncwarp();
+          if (kProbe && lane == 0) trace_ev(a.trace, (int)my_mt, tcnt, 12, s * 2 + t, pair);
           // RING LOCKSTEP, rule 1.  A parity wait is sound only if the waiter knows that the barrier's PREVIOUS phase has
           // completed: met one phase too early, the barrier shows the opposite parity and the wait falls through.  A
           // consumer that takes every chunk of a stage knows it from its own last wait; with two issuers sharing the
@@ -271,6 +287,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
     uint32_t acc_par = 0;                           // bit t: parity of acc_ready[t]
     const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
     constexpr int kCh = kShare ? 4 : 8;             // 16-column chunks of a tile this warp drains per wide step
+    int tcnt = 0;
+    const int treg = e == 0 ? 2 : e == 3 ? 3 : e == 8 ? 4 : e == 15 ? 5 : e == 5 ? 6 : -1;   // traced warps (test twin)
+    const bool tracer = kProbe && lane == 0 && treg >= 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       {
@@ -343,11 +362,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
           wait_tag(&acc_ready[t], (acc_par >> t) & 1u, 4000 + s);
           acc_par ^= 1u << t;
           umma::tc_fence_after();
+          if (tracer) trace_ev(a.trace, treg, tcnt, 21, s * 2 + t, pair);
 
           if (S.epi == EPI_HIDDEN) {
             if (mine && !(P.debug_flags & 8)) {
               const float b = a.bias[S.bias_off + F];
-              const f32x2 b144 = splat2(b * 144.26950408889634f);
+              const f32x2 b144 = splat2(b * (NR_SIG_TANH >= 2 ? 50.0f : 144.26950408889634f));
               const int jpe = F - S.out_rows;
               // loop-invariant decisions and addresses, taken out of the per-chunk code (it costs issue slots there: the
               // forward epilogue is bound by what its FMA / ALU pipes and issue port can take, profiles/r2_mlp_rev_epilogue.md)
@@ -366,7 +386,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
                   } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                      if (NR_SIG_TANH) softplus_sigt2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, vv[2 * j], vv[2 * j + 1], d2[j]);
+                      if (NR_SIG_TANH >= 2) softplus_th2<NR_SIG_TANH == 3>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, vv[2 * j], vv[2 * j + 1], d2[j]);
+                      else if (NR_SIG_TANH) softplus_sigt2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, vv[2 * j], vv[2 * j + 1], d2[j]);
                       else softplus_sigq2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b144, vv[2 * j], vv[2 * j + 1], d2[j]);
                   }
                   store_row16<kF16>(ra, 16 * c, vv, kProbe && (P.debug_flags & 16));   // probe: no operand stores
@@ -388,10 +409,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
               for (int k = 0; k < kCh; k += 2) {
                 umma::tmem_ld_wait();
                 if (!no_ld) umma::tmem_ld16(taddr + 16 * (k + 1), rawB);
+                if (tracer && k == 0) trace_ev(a.trace, treg, tcnt, 24, s * 2 + t, pair);
                 values(raw, k);
                 umma::tmem_ld_wait();
                 if (k + 2 < kCh && !no_ld) umma::tmem_ld16(taddr + 16 * (k + 2), raw);
                 values(rawB, k + 1);
+                if (tracer && k == 0) trace_ev(a.trace, treg, tcnt, 25, s * 2 + t, pair);
               }
             }
           } else if (S.epi == EPI_FEAT) {
@@ -517,7 +540,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
               for (int k = 0; k < kCh; ++k) discard_line(sig_slot + k * kSigChunk);
             }
           }
+          if (tracer) trace_ev(a.trace, treg, tcnt, 22, s * 2 + t, pair);
           if (s + 1 < P.n_steps) publish(&in_ready[t]);
+          if (tracer) trace_ev(a.trace, treg, tcnt, 23, s * 2 + t, pair);
         }
       }
       umma::tc_fence_before();
@@ -541,6 +566,14 @@ int count_sig_slots(const nr_umma_program_t* p) {
 }
 
 }  // namespace
+
+#ifdef NR_FAULT_INJECT
+static long long* g_rev_trace = nullptr;
+// test twin only: timestamps of the MMA <-> epilogue hand-offs of CTA 0 ([8][1024][4] int64, device memory)
+extern "C" int nr_mlp_rev_set_trace(void* buf) { g_rev_trace = (long long*)buf; return NR_OK; }
+#else
+static long long* const g_rev_trace = nullptr;
+#endif
 
 extern "C" size_t nr_mlp_umma_reverse_workspace(const nr_umma_program_t* prog, int64_t n) {
   if (!prog || n <= 0) return 0;
@@ -627,7 +660,7 @@ extern "C" int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* im
   }
   DevProgram dp;
   dp.p = *prog;
-  RevArgs ka{(const uint8_t*)image, bias, x, n, sdf, nabla, feat, feat_ld, (uint8_t*)feat_img, (uint8_t*)workspace, n_sig};
+  RevArgs ka{(const uint8_t*)image, bias, x, n, sdf, nabla, feat, feat_ld, (uint8_t*)feat_img, (uint8_t*)workspace, n_sig, g_rev_trace};
   static int share = -1;   // NEURECON_B200_REV_SHARE=0: every tile's epilogue on its own 8 warps (for measurements)
   if (share < 0) { const char* ev = getenv("NEURECON_B200_REV_SHARE"); share = ev ? atoi(ev) != 0 : 1; }
   const cudaStream_t st = (cudaStream_t)stream;

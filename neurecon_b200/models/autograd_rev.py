@@ -260,10 +260,11 @@ class SdfRevFn(torch.autograd.Function):
             for l in range(D):
                 N, K = dims[l]
                 dW = segs[2 * l].view(N, (K + 3) & ~3)
-                _lib.check(lib.nr_gemm16_tn(_lib.ptr(Z[l]), WIDTH, _lib.ptr(hs[l]), hs[l].stride(0), n, N, K, _lib.ptr(dW),
-                                            dW.stride(0), inv, st), "gemm16_tn")
-                if adj:
-                    _lib.check(lib.nr_gemm16_tn(_lib.ptr(P[l]), P[l].stride(0), _lib.ptr(G[l]), G[l].stride(0), n, N, K, _lib.ptr(dW),
+                if adj:      # zb^T h + p^T gb: one launch, one pass of atomics
+                    _lib.check(lib.nr_gemm16_tn2(_lib.ptr(Z[l]), WIDTH, _lib.ptr(hs[l]), hs[l].stride(0), _lib.ptr(P[l]), P[l].stride(0),
+                                                 _lib.ptr(G[l]), G[l].stride(0), n, N, K, _lib.ptr(dW), dW.stride(0), inv, st), "gemm16_tn2")
+                else:
+                    _lib.check(lib.nr_gemm16_tn(_lib.ptr(Z[l]), WIDTH, _lib.ptr(hs[l]), hs[l].stride(0), n, N, K, _lib.ptr(dW),
                                                 dW.stride(0), inv, st), "gemm16_tn")
                 db = segs[2 * l + 1][:N]
                 _lib.check(lib.nr_colsum16(_lib.ptr(Z[l]), WIDTH, n, N, inv, _lib.ptr(db), st), "colsum16")

@@ -120,8 +120,10 @@ def test_pair_kernel_matches_single_cta_kernel(n):
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 255, 257, 4097, 40000])
 def test_reverse_mode_normals_vs_oracle_and_forward_mode(n, tier):
     """csrc/mlp_rev.cu (forward sweep + backward sweep, softplus' parked as 8-bit codes) against the oracle's autograd
-    normals (base.py:265-282) and against the forward-mode tangent kernel; sdf and the geometry feature come from the
-    same forward arithmetic and must agree with the tangent kernel's to fp32 accumulation order."""
+    normals (base.py:265-282) and against the forward-mode tangent kernel.  The two kernels evaluate softplus differently
+    (one tanh for value and derivative here, ex2 + polynomials there: 2.4e-6 apart before the fp16 rounding of every
+    activation), so their sdf / feature differ by what either differs from the oracle (tools/check_rev_err.py: 6e-4 max,
+    1.2e-4 rms, both), not by accumulation order only."""
     from neurecon_b200.models import base
     if tier != "fp16":
         pytest.skip("reverse-mode normals serve the fp16 tier (bf16 keeps the tangent tiles)")
@@ -147,7 +149,7 @@ def test_reverse_mode_normals_vs_oracle_and_forward_mode(n, tier):
                 sdf2=rel_err(sdf2, osdf), nab2=rel_err(nab2, onab))
     assert all(e < 5e-3 for e in errs.values()), errs          # north_star: <= 1e-2 on the 16-bit MLP path
     assert torch.equal(nab, nab2) and torch.equal(sdf, sdf2)    # 'rev' and 'rev_img' programs: same arithmetic
-    assert rel_err(sdf, out[False][0]) < 1e-5 and rel_err(feat, out[False][2]) < 1e-5
+    assert rel_err(sdf, out[False][0]) < 2e-3 and rel_err(feat, out[False][2]) < 2e-3
     assert rel_err(nab, out[False][1]) < 5e-3 and rel_err(rgb, out[False][3]) < 5e-3
 
 

@@ -153,3 +153,32 @@ def test_gemm16_split_vs_fp64(N, K):
     assert rel_err(got, sp) < 3e-6, rel_err(got, sp)
     assert rel_err(out[:, :N], sp) < 1e-3                                # the hi part alone is an fp16 number
     assert rel_err(S[:, :N], torch.sigmoid(100 * want)) < 1e-3           # softplus' is kept in fp16
+
+
+@pytest.mark.parametrize("rows,N,K", [(1000, 256, 256), (4096, 217, 256), (70000, 256, 39), (513, 256, 295), (64, 3, 256)])
+def test_gemm16_tn_and_tn2_vs_fp64(rows, N, K):
+    """nr_gemm16_tn (dW += scale G^T X on fp16 rows) and nr_gemm16_tn2 (two such products through one accumulator and one
+    pass of atomics: the SDF layers' dW = zb^T h + p^T gb) against float64 products of the same fp16 operands"""
+    lib = _lib.get_lib()
+    rs = np.random.RandomState(rows + 7 * N + K)
+    ldg, ldx = (N + 63) // 64 * 64, (K + 63) // 64 * 64
+
+    def operand(cols, ld):
+        t = torch.zeros(rows, ld, dtype=torch.float16, device=DEV)
+        t[:, :cols] = torch.from_numpy(rs.normal(size=(rows, cols)).astype(np.float32)).to(DEV).half()
+        return t
+
+    G, X, G2, X2 = operand(N, ldg), operand(K, ldx), operand(N, ldg), operand(K, ldx)
+    ldw = (K + 3) & ~3
+    st = torch.cuda.current_stream().cuda_stream
+    base = torch.from_numpy(rs.normal(size=(N, ldw)).astype(np.float32)).to(DEV)
+    one = G[:, :N].double().t() @ X[:, :K].double()
+    two = one + G2[:, :N].double().t() @ X2[:, :K].double()
+    dW = base.clone()
+    _lib.check(lib.nr_gemm16_tn(_lib.ptr(G), ldg, _lib.ptr(X), ldx, rows, N, K, _lib.ptr(dW), ldw, 0.5, st), "gemm16_tn")
+    assert rel_err(dW[:, :K], base[:, :K].double() + 0.5 * one) < 2e-6
+    dW2 = base.clone()
+    _lib.check(lib.nr_gemm16_tn2(_lib.ptr(G), ldg, _lib.ptr(X), ldx, _lib.ptr(G2), ldg, _lib.ptr(X2), ldx, rows, N, K,
+                                 _lib.ptr(dW2), ldw, 0.5, st), "gemm16_tn2")
+    assert rel_err(dW2[:, :K], base[:, :K].double() + 0.5 * two) < 2e-6
+    assert torch.equal(dW2[:, K:], base[:, K:])                          # pad columns of dW untouched

@@ -192,9 +192,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
             wait_tag(&w_empty[stage], ((cnt >> kStagesLog2) & 1u) ^ 1u, 1000 + s);
             NR_INJECT_DELAY(P.debug_flags, P.steps[s].n_mt, t);
             if (umma::elect_one()) {
-              umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
-              umma::bulk_g2s(smem + SmemRev::ring + stage * kChunkBytes, src + (size_t)c * kChunkBytes, kChunkBytes,
-                             &w_full[stage]);
+              if (kProbe && (P.debug_flags & 1024)) {      // probe: no weight stream (the MMAs run on whatever the ring holds)
+                umma::mbar_arrive(&w_full[stage]);
+              } else {
+                umma::mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
+                umma::bulk_g2s(smem + SmemRev::ring + stage * kChunkBytes, src + (size_t)c * kChunkBytes, kChunkBytes,
+                               &w_full[stage]);
+              }
             }
             __syncwarp();
           }
@@ -242,10 +246,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
               if (kProbe && lane == 0 && (kc == 0 || kc + 1 == nkc)) trace_ev(a.trace, (int)my_mt, tcnt, kc == 0 ? 13 : 14, s * 2 + t, pair);
               const uint32_t a_lo = ring_lo + st * (kChunkBytes >> 4);
               if (umma::elect_one()) {
+                if (!(kProbe && (P.debug_flags & 512))) {  // probe 512: no MMAs (the commits still arrive)
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo, a_hi), umma::desc64(b_lo, b_hi), idesc, kc ? 1u : 0u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 2, a_hi), umma::desc64(b_lo + 128, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 4, a_hi), umma::desc64(b_lo + 256, b_hi), idesc, 1u);
                 umma::mma_bf16_ss(d_addr, umma::desc64(a_lo + 6, a_hi), umma::desc64(b_lo + 384, b_hi), idesc, 1u);
+                }
                 umma::mma_commit(&w_empty[st]);
               }
               __syncwarp();

@@ -646,7 +646,11 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(precision),
                 "traffic_source": tsrc, "peak_source": pk["src"] + " bf16 burst", "kernel": kname,
-                "whole_step_frac": (value / world) * MFLOP_PER_RAY * 1e6 / 1e12 / pk["bf16"]}
+                "whole_step_frac": (value / world) * MFLOP_PER_RAY * 1e6 / 1e12 / pk["bf16"],
+                # the launches above run right after the timed render loop, at its power-capped clocks: next to the burst
+                # peak (a GEMM timed alone on an idle GPU) the figure against the peak of a GEMM run back to back for seconds
+                "peak_sustained": pk["bf16_sustained"],
+                "frac_of_sustained_peak": (achieved / pk["bf16_sustained"]) if pk["bf16_sustained"] else None}
 
     # ---- second half of BASELINE.json's metric: dense SDF-grid queries (extract_surface, mesh_util.py:82-111) --------
     # every rank evaluates the x-planes of its own 256^3 lattice (weak scaling, like the rays); sdf only, lattice

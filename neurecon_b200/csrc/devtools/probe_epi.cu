@@ -174,12 +174,96 @@ __global__ void __launch_bounds__(640, 1) probe_epi_kernel(int iters, const floa
   if (warp == 16) umma::tmem_dealloc(tmem_base, 512);
 }
 
+// The same chunk on EIGHT fat epilogue warps (384 threads: 168 registers each, two warps per scheduler) instead of sixteen:
+// kWide = 0: 16-column chunks as above; 1: two 16-column chunks in flight per warp (16 value pairs of ILP)
+template <int kWide>
+__global__ void __launch_bounds__(384, 1) probe_epi8_kernel(int iters, const float* bias, uint8_t* scratch, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* act = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 8) {
+    umma::tmem_alloc(&tmem_base_s, 512);
+    umma::tmem_relinquish();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (warp < 8) {
+    const int q = warp & 3, mo = warp >> 2;
+    const int F = mo * 128 + 32 * q + (tid & 31);
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(mo * 128);
+    for (int c = 0; c < 8; ++c) {
+      uint32_t v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(0.004f * (float)(((F * 64 + c * 16 + j) * 37) % 121 - 60));
+      tmem_st16(taddr + 16 * c, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    const RowAddr ra(umma::smem_u32(act), F);
+    const f32x2 b50 = splat2(bias[F] * 50.0f);
+    uint8_t* dst = scratch + ((size_t)blockIdx.x * 512 + tid) * 16;
+    asm volatile("bar.sync 1, 256;");
+    const long long t0 = clock64();
+    auto values = [&](const uint32_t (&r)[16], int c, int it) {
+      float vv[16];
+      f32x2 d2[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        softplus_th2<true>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), b50, vv[2 * j], vv[2 * j + 1], d2[j]);
+      const uint4 w = make_uint4(code_pack4(d2[0], d2[1], 127.0f), code_pack4(d2[2], d2[3], 127.0f), code_pack4(d2[4], d2[5], 127.0f),
+                                 code_pack4(d2[6], d2[7], 127.0f));
+      store_row16<true>(ra, 16 * c, vv);
+      __stcg(reinterpret_cast<uint4*>(dst + (size_t)(c + 8 * (it & 3)) * 8192 * 148), w);
+    };
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+      if (kWide == 0) {
+        uint32_t raw[16], rawB[16];
+        umma::tmem_ld16(taddr, raw);
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          umma::tmem_ld_wait();
+          umma::tmem_ld16(taddr + 16 * (k + 1), rawB);
+          values(raw, k, it);
+          umma::tmem_ld_wait();
+          if (k + 2 < 8) umma::tmem_ld16(taddr + 16 * (k + 2), raw);
+          values(rawB, k + 1, it);
+        }
+      } else {
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        umma::tmem_ld16(taddr, r0);
+        umma::tmem_ld16(taddr + 16, r1);
+#pragma unroll
+        for (int k = 0; k < 8; k += 4) {
+          umma::tmem_ld_wait();
+          umma::tmem_ld16(taddr + 16 * (k + 2), r2);
+          umma::tmem_ld16(taddr + 16 * (k + 3), r3);
+          values(r0, k, it);
+          values(r1, k + 1, it);
+          umma::tmem_ld_wait();
+          if (k + 4 < 8) { umma::tmem_ld16(taddr + 16 * (k + 4), r0); umma::tmem_ld16(taddr + 16 * (k + 5), r1); }
+          values(r2, k + 2, it);
+          values(r3, k + 3, it);
+        }
+      }
+    }
+    const long long t1 = clock64();
+    asm volatile("bar.sync 1, 256;");
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) umma::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 // scratch: 32 * 8192 * grid bytes; cycles: [grid]; iters = tile steps of 4 chunks per warp
 extern "C" int nr_probe_epi(int32_t variant, int32_t iters, int32_t grid, const float* bias, void* scratch, long long* cycles,
                             void* stream) {
-  NR_CHECK_ARG(bias && scratch && cycles && iters > 0 && grid > 0 && variant >= 0 && variant <= 11, "nr_probe_epi: args");
+  NR_CHECK_ARG(bias && scratch && cycles && iters > 0 && grid > 0 && variant >= 0 && variant <= 21, "nr_probe_epi: args");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = 65536 + 1024;
 #define NR_PE(V)                                                                                                        \
@@ -187,6 +271,14 @@ extern "C" int nr_probe_epi(int32_t variant, int32_t iters, int32_t grid, const 
     NR_CHECK_CUDA(cudaFuncSetAttribute(probe_epi_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     probe_epi_kernel<V><<<grid, 640, smem, st>>>(iters, bias, (uint8_t*)scratch, cycles);                                \
     break;
+  if (variant >= 20) {
+    NR_CHECK_CUDA(cudaFuncSetAttribute(probe_epi8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(probe_epi8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (variant == 20) probe_epi8_kernel<0><<<grid, 384, smem, st>>>(iters, bias, (uint8_t*)scratch, cycles);
+    else probe_epi8_kernel<1><<<grid, 384, smem, st>>>(iters, bias, (uint8_t*)scratch, cycles);
+    NR_CHECK_LAUNCH("probe_epi8_kernel");
+    return NR_OK;
+  }
   switch (variant) { NR_PE(0) NR_PE(1) NR_PE(2) NR_PE(3) NR_PE(4) NR_PE(5) NR_PE(6) NR_PE(7) NR_PE(8) NR_PE(9) NR_PE(10) NR_PE(11) }
 #undef NR_PE
   NR_CHECK_LAUNCH("probe_epi_kernel");

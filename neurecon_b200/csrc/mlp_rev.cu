@@ -26,6 +26,10 @@ namespace {
 constexpr int kStages = 4;
 constexpr int kStagesLog2 = 2;
 constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilogue warps
+#ifndef NR_REV_DEFAULT_MODE
+#define NR_REV_DEFAULT_MODE 1
+#endif
+constexpr int kThreadsFat = 384;         // 4 control warps + 8 epilogue warps of 168 registers (kMode 2)
 constexpr int kEpiPerTile = 256;
 constexpr int kEpiWarpsPerTile = 8;
 constexpr int kEpiWarp0 = 4;
@@ -144,8 +148,16 @@ __device__ __forceinline__ void discard_line(const uint8_t* p) {
 }
 __device__ __forceinline__ void stcg16(uint8_t* p, uint4 v) { __stcg(reinterpret_cast<uint4*>(p), v); }
 
-template <bool kF16, bool kShare>
-__global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
+// kMode 0: every tile slot's epilogue on its own 8 warps (measurements); 1: both 8-warp groups drain every tile, 64 columns
+// each; 2: EIGHT epilogue warps in all, every one draining its 32 features x 128 columns of both tiles -- 384 threads, so 168
+// registers per thread instead of 96: the sweep's per-thread invariants stay in registers next to the accumulator chunks, and a
+// (layer, slot) visit's bookkeeping is paid by 8 warps per tile instead of 16 (two warps per scheduler keep the activation's
+// instruction rate: tools/probe_epi.py variants 20 / 21).
+template <bool kF16, int kMode>
+__global__ void __launch_bounds__(kMode == 2 ? kThreadsFat : kThreads, 1)
+mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
+  constexpr bool kShare = kMode == 1;
+  constexpr bool kFat = kMode == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + SmemRev::bars);
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
-      umma::mbar_init(&in_ready[t], kShare ? 2 * kEpiWarpsPerTile : kEpiWarpsPerTile);
+      umma::mbar_init(&in_ready[t], kShare ? 2 * kEpiWarpsPerTile : kEpiWarpsPerTile);   // kFat: its 8 warps
       umma::mbar_init(&acc_ready[t], 2);
     }
     umma::fence_barrier_init();
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
     // other group [64, 128): the activation epilogue is what the tensor pipe waits for, and with it bound to the tile's
     // own 8 warps only half of the epilogue warps have work while the other tile's MMAs run.
     const int e = warp - kEpiWarp0;                 // 0..15
-    const int g = e >> 3;                           // group = the tile slot it owns
+    const int g = kFat ? 0 : e >> 3;                // group = the tile slot it owns (kFat: one group owns both)
     const int mo = (e >> 2) & 1;                    // M-tile this warpgroup owns
     const int q = warp & 3;                         // TMEM lane quarter (hardware: warp id % 4)
     const int etid = (e & 7) * 32 + lane;           // 0..255 inside the group
@@ -293,17 +305,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
     uint32_t acc_par = 0;                           // bit t: parity of acc_ready[t]
     const int pe_dim = P.multires < 0 ? 3 : 3 + 6 * P.multires;
     constexpr int kCh = kShare ? 4 : 8;             // 16-column chunks of a tile this warp drains per wide step
+    constexpr int kVisits = (kShare || kFat) ? 2 : 1;   // tile slots a warp visits per step
     int tcnt = 0;
     const int treg = e == 0 ? 2 : e == 3 ? 3 : e == 8 ? 4 : e == 15 ? 5 : e == 5 ? 6 : -1;   // traced warps (test twin)
     const bool tracer = kProbe && lane == 0 && treg >= 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      {
+#pragma unroll 1
+      for (int pg = g; pg < (kFat ? 2 : g + 1); ++pg) {
         // ---- prologue (owner): stage the points, evaluate the embedding into operand rows [0, k0) and the stash ----
-        const int64_t p0 = (2 * pair + g) * 128;
-        uint8_t* act = smem + SmemRev::act + g * kActBytes;
-        float* xs = (float*)(smem + SmemRev::xs) + g * 512;
-        uint8_t* pes = smem + SmemRev::pes + g * (kPeStashRows * 256);
+        const int64_t p0 = (2 * pair + pg) * 128;
+        uint8_t* act = smem + SmemRev::act + pg * kActBytes;
+        float* xs = (float*)(smem + SmemRev::xs) + pg * 512;
+        uint8_t* pes = smem + SmemRev::pes + pg * (kPeStashRows * 256);
         for (int i = etid; i < 384; i += kEpiPerTile) {
           const int64_t gi = p0 * 3 + i;
           xs[i] = gi < a.n * 3 ? a.x[gi] : 0.0f;
@@ -333,8 +347,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
           }
         }
         for (int j = pe_dim + part; j < k0; j += 2) store_elem<kF16>(act, j, n, 0.f);
-        publish(&in_ready[g]);
-        if (kShare && lane == 0) umma::mbar_arrive(&in_ready[g ^ 1]);   // nothing of the other tile's operand is ours yet
+        publish(&in_ready[pg]);
+        if (kShare && lane == 0) umma::mbar_arrive(&in_ready[pg ^ 1]);   // nothing of the other tile's operand is ours yet
       }
 
       for (int s = 0; s < P.n_steps; ++s) {
@@ -343,9 +357,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
         const bool is_h = F < S.out_rows;
         const bool is_pe = S.pe_fill && F >= S.out_rows && F < S.out_rows + pe_dim;
 #pragma unroll 1
-        for (int v = 0; v < (kShare ? 2 : 1); ++v) {
-          const int t = kShare ? v : g;               // tile slot worked on
-          const bool own = t == g;
+        for (int v = 0; v < kVisits; ++v) {
+          const int t = kVisits == 2 ? v : g;         // tile slot worked on
+          const bool own = kFat || t == g;
           const int c0 = kShare && !own ? 4 : 0;      // first chunk of this warp's share
           const int64_t tile = 2 * pair + t;
           const int64_t p0 = tile * 128;
@@ -495,15 +509,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
             }
           } else if (S.epi == EPI_NABLA && own) {
             // acc rows [0, pe_dim) = d sdf / d PE(x) through layer 0 (+ the skip layer's share from the stash);
-            // nabla_c = sum_j dPE_j/dx_c * g_j: products to a [point][row] scratch in the (now free) operand buffer
+            // nabla_c = sum_j dPE_j/dx_c * g_j over a [point][row] scratch in the (now free) operand buffer.
+            // Phase A, all 256 threads: the Jacobian dPE_j/dx of every row and point, one sincos per (point, frequency,
+            // component).  (Until late in round 2 every (row, point) element evaluated its own sincos and read its stash value
+            // through a 32-way bank conflict, on four warps: 18 - 23 k cycles per tile pair, a seventh of the kernel.)
             float* red = reinterpret_cast<float*>(act);
-            if (32 * q < pe_dim) {   // warp-uniform (the TMEM loads are .sync.aligned); both warps of a lane quarter work,
-              const int Rr = 32 * q + lane;                      // each on half of the columns of M-tile 0
-              const int comp = Rr < 3 ? Rr : (Rr - 3) % 3;
-              const int qf = Rr < 3 ? 0 : (Rr - 3) / 6;
-              const bool is_sin = Rr >= 3 && ((Rr - 3) % 6) < 3;
-              const float f = (float)(1 << qf);
-              const uint16_t* srow = reinterpret_cast<const uint16_t*>(pes + Rr * 256);
+            {
+              const int n = etid & 127, part = etid >> 7;
+              const float x3[3] = {xs[3 * n], xs[3 * n + 1], xs[3 * n + 2]};
+              float* rn = red + n * kRedLd;
+              if (part == 0) rn[0] = rn[1] = rn[2] = 1.0f;
+              for (int qf = part; qf < P.multires; qf += 2) {
+                const float f = (float)(1 << qf);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  float sn, cs;
+                  __sincosf(x3[c] * f, &sn, &cs);
+                  rn[3 + 6 * qf + c] = f * cs;
+                  rn[3 + 6 * qf + 3 + c] = -f * sn;
+                }
+              }
+            }
+            named_bar_sync(1 + g, kEpiPerTile);
+            // Phase B: scale by the gradient rows (TMEM lane = row; both warps of a lane quarter work, each on half of the columns)
+            if (32 * q < pe_dim) {   // warp-uniform (the TMEM loads are .sync.aligned)
+              const int Rr = 32 * q + lane;
               const uint32_t taddr0 = taddr - (uint32_t)(mo * 128);
 #pragma unroll 1
               for (int c = 4 * mo; c < 4 * mo + 4; ++c) {
@@ -511,21 +541,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const __grid_const
                 umma::tmem_ld16(taddr0 + 16 * c, raw);
                 umma::tmem_ld_wait();
                 if (Rr < pe_dim) {
+                  uint32_t hv[8] = {};
+                  if (S.pe_fill) {   // 16 stash values as two 16-byte loads
+                    const uint4* sp = reinterpret_cast<const uint4*>(pes + Rr * 256 + c * 32);
+                    const uint4 s0 = sp[0], s1 = sp[1];
+                    hv[0] = s0.x; hv[1] = s0.y; hv[2] = s0.z; hv[3] = s0.w; hv[4] = s1.x; hv[5] = s1.y; hv[6] = s1.z; hv[7] = s1.w;
+                  }
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
                     const int col = 16 * c + j;
                     float gv = __uint_as_float(raw[j]);
                     if (S.pe_fill) {
-                      const uint16_t hv = srow[col];
-                      gv += kF16 ? __half2float(__ushort_as_half(hv)) : __uint_as_float((uint32_t)hv << 16);
+                      const uint16_t h16 = (uint16_t)(hv[j >> 1] >> (16 * (j & 1)));
+                      gv += kF16 ? __half2float(__ushort_as_half(h16)) : __uint_as_float((uint32_t)h16 << 16);
                     }
-                    float jac = 1.0f;
-                    if (Rr >= 3) {
-                      float sn, cs;
-                      __sincosf(xs[3 * col + comp] * f, &sn, &cs);
-                      jac = is_sin ? f * cs : -f * sn;
-                    }
-                    red[col * kRedLd + Rr] = gv * jac;
+                    red[col * kRedLd + Rr] *= gv;
                   }
                 }
               }
@@ -658,24 +688,30 @@ extern "C" int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* im
   const size_t smem = SmemRev::total + 1024;
   static unsigned long long attr_set = 0;  // per-device bit: the attribute is per (function, device)
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_rev_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set |= 1ull << (dev & 63);
   }
   DevProgram dp;
   dp.p = *prog;
   RevArgs ka{(const uint8_t*)image, bias, x, n, sdf, nabla, feat, feat_ld, (uint8_t*)feat_img, (uint8_t*)workspace, n_sig, g_rev_trace};
-  static int share = -1;   // NEURECON_B200_REV_SHARE=0: every tile's epilogue on its own 8 warps (for measurements)
-  if (share < 0) { const char* ev = getenv("NEURECON_B200_REV_SHARE"); share = ev ? atoi(ev) != 0 : 1; }
+  // NEURECON_B200_REV_SHARE (measurements): 0 = every tile's epilogue on its own 8 warps, 1 = both 8-warp groups on every tile,
+  // 2 = eight 168-register epilogue warps in all
+  static int mode = -1;
+  if (mode < 0) { const char* ev = getenv("NEURECON_B200_REV_SHARE"); mode = ev ? atoi(ev) : NR_REV_DEFAULT_MODE; if (mode < 0 || mode > 2) mode = NR_REV_DEFAULT_MODE; }
   const cudaStream_t st = (cudaStream_t)stream;
   if (prog->operand_f16) {
-    if (share) mlp_rev_kernel<true, true><<<grid, kThreads, smem, st>>>(dp, ka);
-    else mlp_rev_kernel<true, false><<<grid, kThreads, smem, st>>>(dp, ka);
+    if (mode == 2) mlp_rev_kernel<true, 2><<<grid, kThreadsFat, smem, st>>>(dp, ka);
+    else if (mode == 1) mlp_rev_kernel<true, 1><<<grid, kThreads, smem, st>>>(dp, ka);
+    else mlp_rev_kernel<true, 0><<<grid, kThreads, smem, st>>>(dp, ka);
   } else {
-    if (share) mlp_rev_kernel<false, true><<<grid, kThreads, smem, st>>>(dp, ka);
-    else mlp_rev_kernel<false, false><<<grid, kThreads, smem, st>>>(dp, ka);
+    if (mode == 2) mlp_rev_kernel<false, 2><<<grid, kThreadsFat, smem, st>>>(dp, ka);
+    else if (mode == 1) mlp_rev_kernel<false, 1><<<grid, kThreads, smem, st>>>(dp, ka);
+    else mlp_rev_kernel<false, 0><<<grid, kThreads, smem, st>>>(dp, ka);
   }
   NR_CHECK_LAUNCH("mlp_rev_kernel");
   return NR_OK;

@@ -26,3 +26,9 @@ for pollers in (1, 2, 3, 4):
     torch.cuda.synchronize()
     c = cyc.float().mean().item() / (4 * iters)
     print("shipped, %d warps polling an mbarrier (try_wait loop): %.0f cycles per chunk and warp" % (pollers, c), flush=True)
+for v, nm in ((20, "8 fat warps (168 registers), 16-column chunks"), (21, "8 fat warps, two chunks in flight")):
+    for _ in range(2):
+        _lib.check(lib.nr_probe_epi(v, iters, grid, _lib.ptr(bias), _lib.ptr(scratch), _lib.ptr(cyc), _lib.stream_ptr(dev)), "probe_epi")
+    torch.cuda.synchronize()
+    c = cyc.float().mean().item() / (8 * iters)
+    print("variant %d %-44s %.0f cycles per chunk and warp (2 warps per scheduler: %.0f per chunk-slot)" % (v, nm, c, c / 2), flush=True)

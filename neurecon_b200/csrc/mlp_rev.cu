@@ -455,17 +455,28 @@ mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
               }
             }
           } else if (S.epi == EPI_SDF_OUT) {
-            // rows 0..31 of M-tile 0 all hold the sdf row: lane l keeps column l of each 32-column chunk (owner's warp 0)
-            if (own && mo == 0 && q == 0 && a.sdf) {
+            // rows 0..31 of M-tile 0 all hold the sdf row: lane l keeps column l of a 32-column chunk.  The four chunks are split
+            // over the warps of lane quarter 0 that visit this tile (one warp did all four, with a 32-deep select chain each: 2.7 k
+            // cycles on the critical path of the tile's first backward step)
+            if (q == 0 && a.sdf) {
+              constexpr int kQ0 = kShare ? 4 : 2;                      // warps of quarter 0 visiting the tile
+              const int iq = kShare ? (e >> 2) : ((e & 7) >> 2);
               const float b = a.bias[S.bias_off];
 #pragma unroll 1
-              for (int c = 0; c < 4; ++c) {
+              for (int c = iq * (4 / kQ0); c < (iq + 1) * (4 / kQ0); ++c) {
                 uint32_t raw[32];
-                umma::tmem_ld32(taddr + 32 * c, raw);
+                umma::tmem_ld32(tmem_base + (uint32_t)(t * 256 + 32 * c), raw);
                 umma::tmem_ld_wait();
-                float m = 0.0f;
+                uint32_t s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) m = (lane == j) ? __uint_as_float(raw[j]) : m;
+                for (int j = 0; j < 16; ++j) s16[j] = (lane & 1) ? raw[2 * j + 1] : raw[2 * j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s8[j] = (lane & 2) ? s16[2 * j + 1] : s16[2 * j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s4[j] = (lane & 4) ? s8[2 * j + 1] : s8[2 * j];
+                s2[0] = (lane & 8) ? s4[1] : s4[0];
+                s2[1] = (lane & 8) ? s4[3] : s4[2];
+                const float m = __uint_as_float((lane & 16) ? s2[1] : s2[0]);
                 const int64_t gp = p0 + 32 * c + lane;
                 if (gp < a.n) a.sdf[gp] = m + b;
               }

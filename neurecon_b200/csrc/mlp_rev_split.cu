@@ -468,32 +468,46 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_split_kernel(const __grid
           } else if (S.epi == EPI_NABLA && own) {
             // acc rows [0, pe_dim) = d sdf / d PE(x) through layer 0 (+ the skip layer's share from the stash);
             // nabla_c = sum_j dPE_j/dx_c * g_j: products to a [point][row] scratch in the (now free) operand buffer
+            // Phase A, all 256 threads: the Jacobian dPE_j/dx of every row and point, one sincosf per (point, frequency, component)
+            // (it was evaluated per (row, point) element, with the stash read through a 32-way bank conflict: see mlp_rev.cu)
             float* red = reinterpret_cast<float*>(act);
-            if (32 * q < pe_dim) {   // warp-uniform; the two warps of a lane quarter take 32 columns each
+            {
+              const int n = etid & (kPts - 1), part = etid >> 6;
+              const float x3[3] = {xs[3 * n], xs[3 * n + 1], xs[3 * n + 2]};
+              float* rn = red + n * kRedLd;
+              if (part == 0) rn[0] = rn[1] = rn[2] = 1.0f;
+              for (int qf = part; qf < P.multires; qf += 4) {
+                const float f = (float)(1 << qf);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  float sn, cs;
+                  sincosf(x3[c] * f, &sn, &cs);
+                  rn[3 + 6 * qf + c] = f * cs;
+                  rn[3 + 6 * qf + 3 + c] = -f * sn;
+                }
+              }
+            }
+            named_bar_sync(1 + g, kEpiPerTile);
+            // Phase B: scale by the gradient rows (TMEM lane = row; the two warps of a lane quarter take 32 columns each)
+            if (32 * q < pe_dim) {   // warp-uniform
               const int Rr = 32 * q + lane;
-              const int comp = Rr < 3 ? Rr : (Rr - 3) % 3;
-              const int qf = Rr < 3 ? 0 : (Rr - 3) / 6;
-              const bool is_sin = Rr >= 3 && ((Rr - 3) % 6) < 3;
-              const float f = (float)(1 << qf);
               const float* srow = pes + Rr * kPts;
 #pragma unroll 1
               for (int c = 2 * mo; c < 2 * mo + 2; ++c) {
                 float z[16];
                 ld_sum16(tslot + 16 * c, z);
                 if (Rr < pe_dim) {
+                  float sv[16] = {};
+                  if (S.pe_fill) {   // 16 stash values as four 16-byte loads
+                    const float4* sp = reinterpret_cast<const float4*>(srow + 16 * c);
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const int col = 16 * c + j;
-                    float gv = z[j];
-                    if (S.pe_fill) gv += srow[col];
-                    float jac = 1.0f;
-                    if (Rr >= 3) {
-                      float sn, cs;
-                      sincosf(xs[3 * col + comp] * f, &sn, &cs);
-                      jac = is_sin ? f * cs : -f * sn;
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                      const float4 w = sp[j4];
+                      sv[4 * j4] = w.x; sv[4 * j4 + 1] = w.y; sv[4 * j4 + 2] = w.z; sv[4 * j4 + 3] = w.w;
                     }
-                    red[col * kRedLd + Rr] = gv * jac;
                   }
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) red[(16 * c + j) * kRedLd + Rr] *= z[j] + sv[j];
                 }
               }
             }

@@ -499,7 +499,7 @@ def reference_config():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel the roofline times, from one `ncu --set full`
 # capture of that launch (profiles/): reverse-mode kernel of the fp16 tier / tangent-tile kernel of the bf16 tier
-NCU_DRAM_BYTES_PER_LAUNCH = {"fp16": 17637376 + 223073280, "bf16": 13689344}
+NCU_DRAM_BYTES_PER_LAUNCH = {"fp16": 17855232 + 212988160, "bf16": 13689344}
 
 
 def main():
@@ -629,7 +629,7 @@ def main():
                  "%d launch(es), %.3f ms; algorithmic 1.967 MFLOP/query = what the tensor pipe executes (forward sweep + "
                  "backward sweep)" % (n_pts, k_launches, k_ms))
         tsrc = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (524288 points, "
-                "profiles/r2_ncu_mlp_rev_tanh_raw.csv.gz): 17.6 MB read, 223.1 MB written = 8.4 MB of outputs + the softplus' "
+                "profiles/r2_ncu_mlp_rev_final_raw.csv.gz): 17.9 MB read, 213.0 MB written = 8.4 MB of outputs + the softplus' "
                 "scratch lines evicted before the backward sweep read them back (the rest are dropped with "
                 "discard.global.L2 after the read: round 1 wrote 787 MB; a --metrics-only capture of the same launch, "
                 "profiles/r2_mlp_rev_dram.txt, saw 13.3 + 115.8 MB); algorithmic 14.7 MB; 0.2 TB/s, off the critical path")

@@ -484,15 +484,44 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
           // second operand, whose product the next step accumulates onto the same TMEM columns.
           const int p = etid & 127, pad = P.steps[s + 1].k_steps * 16;
           if (S.to_rad == 0) {       // radiance net: [PE(x) | PE(view) | normals | 0-pad]
+            // two threads per point (rows split by frequency): ONE sincos per (frequency, component) writes its sin and its cos
+            // row (until late in round 2: pe_row() per row -- a sincos, a division and a modulo for every single row; the trace
+            // showed this epilogue at 8.3 k cycles per tile, a sixth of the radiance pass)
             const int px = P.rad_multires < 0 ? 3 : 3 + 6 * P.rad_multires;
             const int pv = P.rad_multires_view < 0 ? 3 : 3 + 6 * P.rad_multires_view;
-            for (int r = etid >> 7; r < pad; r += 2) {
-              float val = 0.0f;
-              if (r < px) val = pe_row(r, P.rad_multires, xs + 3 * p, -1);
-              else if (r < px + pv) val = pe_row(r - px, P.rad_multires_view, vs + 3 * p, -1);
-              else if (r < px + pv + 3) val = nabs[3 * p + (r - px - pv)];
-              store_elem<kF16>(act, r, p, val);
+            const int part = etid >> 7;
+            const float x3[3] = {xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]};
+            const float v3[3] = {vs[3 * p], vs[3 * p + 1], vs[3 * p + 2]};
+            if (part == 0) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) store_elem<kF16>(act, c, p, x3[c]);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) store_elem<kF16>(act, px + pv + c, p, nabs[3 * p + c]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) store_elem<kF16>(act, px + c, p, v3[c]);
             }
+            for (int qf = part; qf < P.rad_multires; qf += 2) {
+              const float f = (float)(1 << qf);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                float sn, cs;
+                __sincosf(x3[c] * f, &sn, &cs);
+                store_elem<kF16>(act, 3 + 6 * qf + c, p, sn);
+                store_elem<kF16>(act, 3 + 6 * qf + 3 + c, p, cs);
+              }
+            }
+            for (int qf = part; qf < P.rad_multires_view; qf += 2) {
+              const float f = (float)(1 << qf);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                float sn, cs;
+                __sincosf(v3[c] * f, &sn, &cs);
+                store_elem<kF16>(act, px + 3 + 6 * qf + c, p, sn);
+                store_elem<kF16>(act, px + 3 + 6 * qf + 3 + c, p, cs);
+              }
+            }
+            for (int r = px + pv + 3 + part; r < pad; r += 2) store_elem<kF16>(act, r, p, 0.0f);
           } else if (S.to_rad == 1) {   // PE(x) again (skip connection cat([PE(x), h]))
             const int npe = P.multires < 0 ? xdim : xdim * (1 + 2 * P.multires);
             for (int r = etid >> 7; r < pad; r += 2)
@@ -527,19 +556,33 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
             }
           }
         } else if (S.epi == EPI_RGB) {
+          // rows 0..2 of the accumulator = the three colour logits of the tile's points.  Lanes 0..2 of one warp park them (+ bias)
+          // in the (by now dead) view-direction staging buffer, then all 32 lanes apply the sigmoid and write the interleaved [point][3] output
+          // coalesced (until late in round 2 three lanes did all of it: 8.6 k cycles per tile, a sixth of the radiance pass)
           if (mo == 0 && q == 0) {
+            float* stage = vs;                                 // [3][n_cols] floats (n_cols <= 128)
+            const int ncols = S.n_cols;
             const float b = lane < 3 ? a.bias[S.bias_off + lane] : 0.0f;
 #pragma unroll 1
-            for (int c = 0; c < (S.n_cols >> 5); ++c) {
+            for (int c = 0; c < (ncols >> 5); ++c) {
               uint32_t raw[32];
               umma::tmem_ld32(tmem_tile + 32 * c, raw);
               umma::tmem_ld_wait();
-              if (lane < 3 && a.rgb) {
+              if (lane < 3) {
+                float4* dst = reinterpret_cast<float4*>(stage + lane * ncols + 32 * c);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int64_t gp = p0 + 32 * c + j;
-                  if (gp < a.n) a.rgb[gp * 3 + lane] = sigmoid_fast(__uint_as_float(raw[j]) + b);
-                }
+                for (int j = 0; j < 8; ++j)
+                  dst[j] = make_float4(__uint_as_float(raw[4 * j]) + b, __uint_as_float(raw[4 * j + 1]) + b,
+                                       __uint_as_float(raw[4 * j + 2]) + b, __uint_as_float(raw[4 * j + 3]) + b);
+              }
+            }
+            __syncwarp();
+            if (a.rgb) {
+              const int64_t n_left = a.n - p0;                  // points of this tile that exist
+              const int n_out = 3 * (int)(n_left < ncols ? (n_left > 0 ? n_left : 0) : ncols);
+              for (int i = lane; i < n_out; i += 32) {
+                const int pt = i / 3, ch = i - 3 * pt;
+                a.rgb[p0 * 3 + i] = sigmoid_fast(stage[ch * ncols + pt]);
               }
             }
           }

@@ -17,11 +17,12 @@ v = torch.nn.functional.normalize(torch.randn(n, 3, device=dev), dim=-1)
 net = m.implicit_surface._umma_net(m.radiance_net)
 prog = net.program(mode)
 prog.debug_flags = flags
-run(net, prog, x, v, n, 2)
+img = torch.zeros((n + 127) // 128 * 65536, dtype=torch.uint8, device=dev) if ("img" in mode or mode.startswith("radiance")) else None
+run(net, prog, x, v, n, 2, img)
 tr = torch.zeros(3, 2048, 4, dtype=torch.int64, device=dev)
 lib = _lib.get_lib()
 lib.nr_mlp_umma_set_trace(_lib.ptr(tr))
-ms = run(net, prog, x, v, n, 1)
+ms = run(net, prog, x, v, n, 1, img)
 lib.nr_mlp_umma_set_trace(None)
 torch.cuda.synchronize()
 t = tr.cpu().numpy()

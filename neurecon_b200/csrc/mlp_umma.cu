@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
     const int q = warp & 3;                         // TMEM lane quarter (hardware: warp id % 4)
     const int etid = (e & 7) * 32 + lane;           // 0..255 inside the group
     uint32_t feat_par = 0;
+    bool img_ahead = false;                         // radiance pass: this tile's feature image was requested during the previous pair
     uint32_t acc_par = 0;                           // bit t: parity of acc_ready[t]
     int tcnt = 0;
     const bool tracer = (mo == 0 && q == 0 && lane == 0 && g == 0);
@@ -246,8 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
         }
       }
       if (rad_only) {
-        // operand rows [0,256) = this tile's 64 KB block of the feature image, four 16 KB bulk copies
-        if (etid == 0) {
+        // operand rows [0,256) = this tile's 64 KB block of the feature image, four 16 KB bulk copies (already on their way if
+        // the previous pair's colour step requested them: the 64 KB come from HBM, 4 - 5 k cycles that the prologue sat out)
+        if (etid == 0 && !img_ahead) {
           umma::mbar_arrive_expect_tx(&feat_full[t], kActBytes);
           const uint8_t* src = a.feat_img + (size_t)tile * kActBytes;
 #pragma unroll
@@ -559,6 +561,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
           // rows 0..2 of the accumulator = the three colour logits of the tile's points.  Lanes 0..2 of one warp park them (+ bias)
           // in the (by now dead) view-direction staging buffer, then all 32 lanes apply the sigmoid and write the interleaved [point][3] output
           // coalesced (until late in round 2 three lanes did all of it: 8.6 k cycles per tile, a sixth of the radiance pass)
+          if (rad_only && own && etid == 0) {
+            // the operand buffer is dead once this step's MMAs have read it: request the next pair's feature image now
+            const int64_t next_pair = pair + gridDim.x, next_tile = 2 * next_pair + t;
+            img_ahead = next_pair < n_pairs && next_tile < n_tiles;
+            if (img_ahead) {
+              umma::mbar_arrive_expect_tx(&feat_full[t], kActBytes);
+              const uint8_t* src = a.feat_img + (size_t)next_tile * kActBytes;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) umma::bulk_g2s(act + c * kChunkBytes, src + c * kChunkBytes, kChunkBytes, &feat_full[t]);
+            }
+          }
           if (mo == 0 && q == 0) {
             float* stage = vs;                                 // [3][n_cols] floats (n_cols <= 128)
             const int ncols = S.n_cols;

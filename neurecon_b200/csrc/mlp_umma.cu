@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
           }
         } else if (S.epi == EPI_RGB) {
           // rows 0..2 of the accumulator = the three colour logits of the tile's points.  Lanes 0..2 of one warp park them (+ bias)
-          // in the (by now dead) view-direction staging buffer, then all 32 lanes apply the sigmoid and write the interleaved [point][3] output
+          // in the (by now dead) view-direction staging buffer, then all 256 threads of the group apply the sigmoid and write the interleaved [point][3] output
           // coalesced (until late in round 2 three lanes did all of it: 8.6 k cycles per tile, a sixth of the radiance pass)
           if (rad_only && own && etid == 0) {
             // the operand buffer is dead once this step's MMAs have read it: request the next pair's feature image now
@@ -572,28 +572,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
               for (int c = 0; c < 4; ++c) umma::bulk_g2s(act + c * kChunkBytes, src + c * kChunkBytes, kChunkBytes, &feat_full[t]);
             }
           }
-          if (mo == 0 && q == 0) {
+          if (own) {
             float* stage = vs;                                 // [3][n_cols] floats (n_cols <= 128)
-            const int ncols = S.n_cols;
-            const float b = lane < 3 ? a.bias[S.bias_off + lane] : 0.0f;
+            const int ncols = S.n_cols, nch = ncols >> 5;
+            if (q == 0) {                                      // the two warps of lane quarter 0 share the 32-column chunks
+              const float b = lane < 3 ? a.bias[S.bias_off + lane] : 0.0f;
 #pragma unroll 1
-            for (int c = 0; c < (ncols >> 5); ++c) {
-              uint32_t raw[32];
-              umma::tmem_ld32(tmem_tile + 32 * c, raw);
-              umma::tmem_ld_wait();
-              if (lane < 3) {
-                float4* dst = reinterpret_cast<float4*>(stage + lane * ncols + 32 * c);
+              for (int c = mo; c < nch; c += 2) {
+                uint32_t raw[32];
+                umma::tmem_ld32(tmem_tile + 32 * c, raw);
+                umma::tmem_ld_wait();
+                if (lane < 3) {
+                  float4* dst = reinterpret_cast<float4*>(stage + lane * ncols + 32 * c);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  dst[j] = make_float4(__uint_as_float(raw[4 * j]) + b, __uint_as_float(raw[4 * j + 1]) + b,
-                                       __uint_as_float(raw[4 * j + 2]) + b, __uint_as_float(raw[4 * j + 3]) + b);
+                  for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(raw[4 * j]) + b, __uint_as_float(raw[4 * j + 1]) + b,
+                                         __uint_as_float(raw[4 * j + 2]) + b, __uint_as_float(raw[4 * j + 3]) + b);
+                }
               }
             }
-            __syncwarp();
+            named_bar_sync(1 + t, kEpiPerTile);
             if (a.rgb) {
               const int64_t n_left = a.n - p0;                  // points of this tile that exist
               const int n_out = 3 * (int)(n_left < ncols ? (n_left > 0 ? n_left : 0) : ncols);
-              for (int i = lane; i < n_out; i += 32) {
+              for (int i = etid; i < n_out; i += kEpiPerTile) {
                 const int pt = i / 3, ch = i - 3 * pt;
                 a.rgb[p0 * 3 + i] = sigmoid_fast(stage[ch * ncols + pt]);
               }

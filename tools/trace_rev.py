@@ -36,7 +36,7 @@ who = {0: "mma w1", 1: "mma w3", 2: "epi e0 ", 3: "epi e3 ", 4: "epi e8 ", 5: "e
 ev = []
 for reg in range(8):
     for row in t[reg]:
-        if row[0] != 0 and row[3] == which * sms:
+        if row[0] != 0 and (row[3] == which * sms or (os.environ.get('NR_TRACE_TWO') and row[3] == (which + 1) * sms)):
             ev.append((int(row[2]), reg, int(row[0]), int(row[1])))
 ev.sort()
 t0 = ev[0][0]

@@ -60,3 +60,15 @@ if os.environ.get("NR_PROF_EACH"):
     evs.sort(key=lambda e: e.time_range.start)
     for e in evs:
         print("   %9.3f ms  %s" % (e.device_time_total / 1e3, e.name[:70]))
+
+if os.environ.get("NR_PROF_TIMELINE"):
+    # device-side timeline: start, duration and the idle gap before every kernel / copy of the render
+    from torch.autograd import DeviceType
+    evs = [e for e in prof.events() if e.device_type == DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    t0, prev_end = evs[0].time_range.start, None
+    for e in evs:
+        st, en = e.time_range.start, e.time_range.end
+        gap = (st - prev_end) if prev_end is not None else 0.0
+        print("   +%9.3f ms  dur %8.3f ms  gap %7.3f ms  %s" % ((st - t0) / 1e3, (en - st) / 1e3, gap / 1e3, e.name[:60]))
+        prev_end = en if prev_end is None else max(prev_end, en)

@@ -30,12 +30,13 @@ constexpr int kThreads = 640;            // 4 control warps + 2 tiles x 8 epilog
 constexpr int kEpiPerTile = 256;
 constexpr int kEpiWarpsPerTile = 8;
 constexpr int kEpiWarp0 = 4;
+// kShare (template parameter of the kernel): the wide activation steps (EPI_HIDDEN, EPI_RELU) of a tile are drained by all 16
+// epilogue warps, each group taking half of the points; otherwise by the tile's own 8 warps.  Chosen per program by the host:
+// the softplus programs on value tiles (sdf only) gain 9 % from sharing, the ReLU programs (radiance pass) lose 14 %
+// (tools/bench_mlp.py, round 2); NR_SHARE_EPILOGUE = 0 / 1 forces it for measurements.
 #ifndef NR_SHARE_EPILOGUE
-#define NR_SHARE_EPILOGUE 0
+#define NR_SHARE_EPILOGUE -1
 #endif
-// 1: the wide activation steps (EPI_HIDDEN, EPI_RELU) of a tile are drained by all 16 epilogue warps, each group
-// taking half of the points; 0: by the tile's own 8 warps.
-constexpr bool kShare = NR_SHARE_EPILOGUE != 0;
 
 struct SmemLayout {
   // offsets from the 1024-aligned base
@@ -66,7 +67,7 @@ __device__ __forceinline__ void trace_ev(long long* tr, int region, int& cnt, in
   ++cnt;
 }
 
-template <bool kF16>
+template <bool kF16, bool kShare>
 __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_constant__ DevProgram prog, const KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -685,15 +686,23 @@ extern "C" int nr_mlp_umma_forward(const nr_umma_program_t* prog, const void* im
   const size_t smem = SmemLayout::total + 1024;
   static unsigned long long attr_set = 0;  // per-device bit: the attribute is per (function, device)
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CHECK_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set |= 1ull << (dev & 63);
   }
   DevProgram dp;
   dp.p = *prog;
   KArgs ka{(const uint8_t*)image, bias, x, view, n, sdf, nabla, feat, feat_ld, rgb, normal_scale, (uint8_t*)feat_img, g_trace};
-  if (prog->operand_f16) mlp_umma_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
-  else mlp_umma_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+  const bool share = NR_SHARE_EPILOGUE >= 0 ? NR_SHARE_EPILOGUE != 0 : (!has_rad && prog->tangents == 0 && prog->input_mode == 0);
+  if (prog->operand_f16) {
+    if (share) mlp_umma_kernel<true, true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+    else mlp_umma_kernel<true, false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+  } else {
+    if (share) mlp_umma_kernel<false, true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+    else mlp_umma_kernel<false, false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(dp, ka);
+  }
   NR_CHECK_LAUNCH("mlp_umma_kernel");
   return NR_OK;
 }

@@ -59,6 +59,7 @@ struct RevArgs {
   uint8_t* feat_img;   // null, or [ceil(n/128)][64 KB]: last hidden activations as the radiance pass's operand image
   uint8_t* sig;        // [grid][2][n_sig][32 KB]
   int n_sig;
+  int store_sig;       // 0: forward-only program (ends with the sdf row): no softplus' codes
   long long* trace;    // test twin only: [8][kTraceCap][4] (event, step * 2 + tile, clock, pair) from CTA 0 (tools/trace_rev.py)
 };
 
@@ -373,7 +374,7 @@ mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
 
           // softplus' codes of this warp's columns: requested before the accumulator wait (latency under the MMAs)
           uint4 sg[kCh];
-          const bool use_sig = ((S.epi == EPI_BWD && mine && is_h) || S.epi == EPI_SDF_OUT) && !(P.debug_flags & 2);
+          const bool use_sig = ((S.epi == EPI_BWD && mine && is_h) || (S.epi == EPI_SDF_OUT && s + 1 < P.n_steps)) && !(P.debug_flags & 2);
           if (use_sig) {
 #pragma unroll
             for (int k = 0; k < kCh; ++k) sg[k] = ldcg16(sig_slot + k * kSigChunk);
@@ -393,7 +394,7 @@ mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
               // forward epilogue is bound by what its FMA / ALU pipes and issue port can take, profiles/r2_mlp_rev_epilogue.md)
               const bool do_img = S.to_rad && a.feat_img && tile < n_tiles;
               uint8_t* const img_row = a.feat_img + (size_t)tile * kActBytes + (F >> 3) * 1024 + (F & 7) * 128;
-              const bool no_codes = kProbe && (P.debug_flags & 1);
+              const bool no_codes = !a.store_sig || (kProbe && (P.debug_flags & 1));
               uint32_t raw[16], rawB[16];
               auto values = [&](const uint32_t (&r)[16], int k) {
                 const int c = c0 + k;
@@ -412,9 +413,11 @@ mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
                   }
                   store_row16<kF16>(ra, 16 * c, vv, kProbe && (P.debug_flags & 16));   // probe: no operand stores
                   if (do_img) img_row_store16<kF16>(img_row, F & 7, 16 * c, vv);
-                  const uint4 w = make_uint4(sig_pack4(d2[0], d2[1]), sig_pack4(d2[2], d2[3]), sig_pack4(d2[4], d2[5]),
-                                             sig_pack4(d2[6], d2[7]));
-                  if (!no_codes || w.x + w.y + w.z + w.w == 0x12345u) stcg16(sig_slot + k * kSigChunk, w);
+                  if (!no_codes) {
+                    const uint4 w = make_uint4(sig_pack4(d2[0], d2[1]), sig_pack4(d2[2], d2[3]), sig_pack4(d2[4], d2[5]),
+                                               sig_pack4(d2[6], d2[7]));
+                    stcg16(sig_slot + k * kSigChunk, w);
+                  }
                 } else {
                   copy_row16(ra, pes, jpe, 16 * c);
                 }
@@ -482,10 +485,12 @@ mlp_rev_kernel(const __grid_constant__ DevProgram prog, const RevArgs a) {
               }
             }
             // start of the backward pass: operand row F <- softplus'(z_last)[F, :] * w_sdf[F]  (d sdf / d z_last)
-            const float wF = a.bias[S.aux_off + F];
-            const uint32_t none[16] = {};
+            if (s + 1 < P.n_steps) {
+              const float wF = a.bias[S.aux_off + F];
+              const uint32_t none[16] = {};
 #pragma unroll
-            for (int k = 0; k < kCh; ++k) apply_sig16<kF16, false>(ra, c0 + k, none, sg[k], wF);
+              for (int k = 0; k < kCh; ++k) apply_sig16<kF16, false>(ra, c0 + k, none, sg[k], wF);
+            }
           } else if (S.epi == EPI_BWD) {
             if (mine && !(P.debug_flags & 4)) {
               uint32_t raw[16], rawB[16];
@@ -635,11 +640,11 @@ extern "C" int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* im
                                    const float* bias, size_t bias_floats, const float* x, int64_t n, float* sdf,
                                    float* nabla, float* feat, int64_t feat_ld, void* feat_img, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  NR_CHECK_ARG(prog && image && bias && x && nabla, "nr_mlp_umma_reverse: null pointer");
+  NR_CHECK_ARG(prog && image && bias && x, "nr_mlp_umma_reverse: null pointer");
   NR_CHECK_ARG(n >= 0, "nr_mlp_umma_reverse: n < 0");
   NR_CHECK_ARG(prog->reverse == 1 && prog->tangents == 0 && prog->input_mode == 0,
                "nr_mlp_umma_reverse: needs a reverse-mode program on value tiles");
-  NR_CHECK_ARG(prog->n_steps >= 3 && prog->n_steps <= NR_UMMA_MAX_STEPS, "nr_mlp_umma_reverse: n_steps=%d", prog->n_steps);
+  NR_CHECK_ARG(prog->n_steps >= 2 && prog->n_steps <= NR_UMMA_MAX_STEPS, "nr_mlp_umma_reverse: n_steps=%d", prog->n_steps);
   NR_CHECK_ARG(((uintptr_t)image & 15) == 0 && ((uintptr_t)workspace & 15) == 0 && ((uintptr_t)feat_img & 15) == 0,
                "nr_mlp_umma_reverse: image, workspace and feat_img must be 16-byte aligned");
   const int pe_dim = prog->multires < 0 ? 3 : 3 + 6 * prog->multires;
@@ -686,11 +691,17 @@ extern "C" int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* im
         NR_CHECK_ARG(false, "step %d: epi=%d is not a reverse-mode step", s, S.epi);
     }
   }
-  NR_CHECK_ARG(n_sdf == 1 && n_nabla == 1 && n_sig >= 1, "nr_mlp_umma_reverse: program needs one EPI_SDF_OUT and a final EPI_NABLA");
+  // a program that ends with the sdf row is the forward sweep alone (sdf [+ feature] of every point: no codes, no normals)
+  const bool fwd_only = prog->steps[prog->n_steps - 1].epi == EPI_SDF_OUT;
+  NR_CHECK_ARG(n_sdf == 1 && n_sig >= 1 && (fwd_only ? n_nabla == 0 : n_nabla == 1),
+               "nr_mlp_umma_reverse: program needs one EPI_SDF_OUT, last or followed by the backward sweep up to a final EPI_NABLA");
+  NR_CHECK_ARG(fwd_only || nabla, "nr_mlp_umma_reverse: nabla is null");
   if (n == 0) return NR_OK;
-  const size_t need = nr_mlp_umma_reverse_workspace(prog, n);
-  NR_CHECK_ARG(workspace && workspace_bytes >= need, "nr_mlp_umma_reverse: workspace of %zu bytes needed, %zu given", need,
-               workspace_bytes);
+  if (!fwd_only) {
+    const size_t need = nr_mlp_umma_reverse_workspace(prog, n);
+    NR_CHECK_ARG(workspace && workspace_bytes >= need, "nr_mlp_umma_reverse: workspace of %zu bytes needed, %zu given", need,
+                 workspace_bytes);
+  }
   int dev = 0, sms = 0;
   NR_CHECK_CUDA(cudaGetDevice(&dev));
   NR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -709,7 +720,7 @@ extern "C" int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* im
   }
   DevProgram dp;
   dp.p = *prog;
-  RevArgs ka{(const uint8_t*)image, bias, x, n, sdf, nabla, feat, feat_ld, (uint8_t*)feat_img, (uint8_t*)workspace, n_sig, g_rev_trace};
+  RevArgs ka{(const uint8_t*)image, bias, x, n, sdf, nabla, feat, feat_ld, (uint8_t*)feat_img, (uint8_t*)workspace, n_sig, fwd_only ? 0 : 1, g_rev_trace};
   // NEURECON_B200_REV_SHARE (measurements): 0 = every tile's epilogue on its own 8 warps, 1 = both 8-warp groups on every tile,
   // 2 = eight 168-register epilogue warps in all
   static int mode = -1;

@@ -147,6 +147,7 @@ _FUSED_MODE = os.environ.get("NEURECON_B200_FUSED", "split")   # 'split' | 'fuse
 _PAIR_KERNEL = os.environ.get("NEURECON_B200_PAIR", "0") != "0"
 # Normals of the tensor tier: reverse mode (csrc/mlp_rev.cu: forward + backward sweep on 128-point tiles, half the
 # tensor work) or, with NEURECON_B200_NABLAS=forward, the forward-mode tangent tiles of csrc/mlp_umma.cu
+_SDF_VIA_REV = os.environ.get("NEURECON_B200_SDF_VIA_REV", "1") != "0"
 _REVERSE_NABLAS = os.environ.get("NEURECON_B200_NABLAS", "reverse") != "forward"
 
 
@@ -381,6 +382,10 @@ class ImplicitSurface(nn.Module):
                     launch(p_rad, i0, m, None, nabla, None, rgb, img)
             elif mode == "nablas" and rev:
                 launch_rev(net.program("rev", want_feat=want_feat), 0, n, sdf, nabla, feat, None)
+            elif mode == "sdf" and rev and _SDF_VIA_REV:
+                # sdf (+ feature) only: the forward sweep of the reverse-mode kernel alone (its one-tanh activation on 16
+                # shared epilogue warps is faster than mlp_umma_kernel's 'sdf' program)
+                launch_rev(net.program("rev_sdf", want_feat=want_feat), 0, n, sdf, None, feat, None)
             elif mode == "split":
                 # one-CTA kernel: image = last hidden activations, the radiance pass applies the feature layer 128 columns
                 # wide; pair kernel: image = the feature, from its own 32-column step

@@ -598,7 +598,9 @@ int nr_umma_pack_a(const float* W, int64_t row_stride, int64_t col_stride, int32
  * backward sweep from the sdf row to the embedding on the same tiles.  Program: reverse = 1, steps EPI_HIDDEN x L
  * (sig_slot = layer), optional EPI_FEAT, EPI_SDF_OUT (aux_off = the sdf row's weights), EPI_BWD x (L-1) whose chunks
  * hold W_l^T (pe_fill marks the skip layer), EPI_NABLA with W_0^T.  Outputs as nr_mlp_umma_forward; feat_img, if not
- * NULL, receives the LAST HIDDEN activations as the radiance pass's operand image (to_rad on the last hidden step). */
+ * NULL, receives the LAST HIDDEN activations as the radiance pass's operand image (to_rad on the last hidden step).
+ * A program that ENDS with EPI_SDF_OUT is the forward sweep alone (ImplicitSurface.forward, models/base.py:247-263: sdf and
+ * optionally the feature of every point): nabla and workspace may then be NULL. */
 size_t nr_mlp_umma_reverse_workspace(const nr_umma_program_t* prog, int64_t n);
 int nr_mlp_umma_reverse(const nr_umma_program_t* prog, const void* image, size_t image_bytes, const float* bias,
                         size_t bias_floats, const float* x, int64_t n, float* sdf, float* nabla, float* feat,

@@ -292,8 +292,19 @@ class ImplicitSurface(nn.Module):
             return net
         return _cached(self, "umma_split", _param_key(self), build)
 
+    def forward_level_set(self, x):
+        """sdf only, for iterations that walk onto the zero level set (ray_casting.sphere_tracing_surface_points): always
+        mlp_umma_kernel's 'sdf' program in the fp16 tier.  The forward sweep of mlp_rev_kernel that `forward` uses is as close
+        to the fp32 reference (tools/check_rev_err.py; surface normals of 4096 sphere-traced rays: rms 1.07e-2 against 1.24e-2,
+        tools/check_surface_render_err.py), but the 48 rays of the reference's surface-rendering golden were pinned with this
+        program (normals 4.6e-3; 1.12e-2 with the other, over the tier's 1e-2 bar on that sample)."""
+        if self._needs_grad(x, torch.is_grad_enabled()) or not _lib.tensor_tier():
+            return self.forward(x)
+        _lib.require_cuda(x)
+        return self._run_umma(x, "sdf", sdf_via_rev=False)[0]
+
     def _run_umma(self, x, mode, want_feat=False, radiance_net=None, view_dirs=None, want_sdf=True,
-                  want_nablas=True, normal_scale=None):
+                  want_nablas=True, normal_scale=None, sdf_via_rev=True):
         """The fused tcgen05 kernel.  mode: 'sdf' | 'nablas' | 'fused' (one launch, radiance steps 32 columns wide) |
         'split' (two launches per <= 2M points: SDF net + normals + feature image, then the radiance net on 128-point
         tiles -- the radiance MMAs run 128 columns wide, 2.5x the rate of the 32-column ones)."""
@@ -382,7 +393,7 @@ class ImplicitSurface(nn.Module):
                     launch(p_rad, i0, m, None, nabla, None, rgb, img)
             elif mode == "nablas" and rev:
                 launch_rev(net.program("rev", want_feat=want_feat), 0, n, sdf, nabla, feat, None)
-            elif mode == "sdf" and rev and _SDF_VIA_REV:
+            elif mode == "sdf" and rev and _SDF_VIA_REV and sdf_via_rev:
                 # sdf (+ feature) only: the forward sweep of the reverse-mode kernel alone (its one-tanh activation on 16
                 # shared epilogue warps is faster than mlp_umma_kernel's 'sdf' program)
                 launch_rev(net.program("rev_sdf", want_feat=want_feat), 0, n, sdf, None, feat, None)

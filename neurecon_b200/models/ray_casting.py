@@ -79,7 +79,7 @@ def sphere_tracing_surface_points(implicit_surface, rays_o, rays_d, near=0.0, fa
                                                     _lib.ptr(mask), _lib.ptr(pts), st), "sphere_trace_step")
                 if _ == N_iters:
                     break
-                val = _lib.f32c(implicit_surface.forward(pts).reshape(R))
+                val = _lib.f32c(getattr(implicit_surface, "forward_level_set", implicit_surface.forward)(pts).reshape(R))
     return d_preds.reshape(prefix), pts.reshape(*prefix, 3), mask.bool().reshape(prefix)
 
 

@@ -274,3 +274,30 @@ def test_split_radiance_chunking_and_ragged_sizes():
                     assert rel_err(a_, b_[:k]) < 1e-6, k
     finally:
         base._SPLIT_POINTS = old
+
+
+def test_reverse_kernel_forward_only_program(tier):
+    """nr_mlp_umma_reverse on a program that ends with the sdf row ('rev_sdf': the forward sweep alone, ImplicitSurface.forward):
+    the sdf is the full program's sdf bit for bit, with nabla and the workspace NULL."""
+    from neurecon_b200.models import base
+    if tier != "fp16":
+        pytest.skip("reverse-mode kernel serves the fp16 tier")
+    m = build_neus(seed=1, device=DEV)
+    n = 3001
+    x = synthetic.make_points(n, extent=1.0, seed=21).to(DEV)
+    old = base._SDF_VIA_REV
+    try:
+        base._SDF_VIA_REV = True
+        with torch.no_grad():
+            sdf_fwd = m.implicit_surface.forward(x)
+            sdf_full, _, _ = m.implicit_surface.forward_with_nablas(x)
+        base._SDF_VIA_REV = False
+        with torch.no_grad():
+            sdf_umma = m.implicit_surface.forward(x)
+    finally:
+        base._SDF_VIA_REV = old
+    torch.cuda.synchronize()
+    assert torch.equal(sdf_fwd, sdf_full)
+    assert rel_err(sdf_fwd, sdf_umma) < 2e-3          # the other kernel's softplus evaluation: as close as either is to the oracle
+    osdf = _oracle(m, x.cpu(), x.cpu())[0]
+    assert rel_err(sdf_fwd, osdf) < 5e-3

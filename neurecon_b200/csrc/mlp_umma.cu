@@ -538,7 +538,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_umma_kernel(const __grid_cons
           const float lo = S.epi == EPI_RELU ? 0.0f : -INFINITY;
           if (mo < S.n_mt) {
             const float b = a.bias[S.bias_off + F];
-#pragma unroll 1
             const int nall = S.n_cols >> 4;              // 16-column chunks; split between the groups when >= 4
             const bool split = kShare && nall >= 4;
             const int cb = split ? (own ? 0 : nall >> 1) : 0, nchunk = split ? cb + (nall >> 1) : (own ? nall : 0);
